@@ -1,0 +1,153 @@
+/*
+ * metdet_b200.h -- C ABI of libmetdet_b200.so: the B200 (sm_100a) implementation of MetDetPy's
+ * per-frame line-detector hot path.  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the reference
+ * repository LilacMeteorObservatory/MetDetPy).  The reference is pure Python, so "the FFI a
+ * maintainer would add" is a ctypes binding; see INTEGRATION.md and metdetpy_b200/_lib.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MDB_ERR_* code otherwise;
+ *     mdb_last_error() returns a thread-local human-readable message for the last failure.
+ *   - the caller owns all input and output buffers; a handle owns its device memory and one CUDA
+ *     stream.  Handles are independent (no global mutable state): different handles may be driven
+ *     from different threads; one handle from one thread at a time (the reference's threading
+ *     model: MetDetPy.py:184-227 runs the detector on the main thread only).
+ *   - frames are uint8, H rows of W pixels, C-contiguous (what VanillaVideoLoader hands to
+ *     detector.update(), videoloader.py:360-388); `on_device` != 0 means the pointer is a CUDA
+ *     device pointer on the handle's device, already complete (caller synchronised its producer).
+ *   - there is NO CPU fallback: without a CUDA device every entry point that computes fails.
+ */
+#ifndef METDET_B200_H
+#define METDET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDB_OK 0
+#define MDB_ERR_INVALID (-1)   /* bad argument / unsupported configuration */
+#define MDB_ERR_CUDA (-2)      /* CUDA runtime error (message has the CUDA error string) */
+#define MDB_ERR_STATE (-3)     /* call sequence error (e.g. detect before any update) */
+#define MDB_ERR_NOMEM (-4)
+
+#define MDB_NUM_LINES_TOOMUCH 500 /* MetLib/Detector.py:30 */
+#define MDB_MAX_LINES 512         /* per-frame capacity of the raw / NMS line outputs (> 500) */
+
+#define MDB_SENS_LOW 0
+#define MDB_SENS_NORMAL 1
+#define MDB_SENS_HIGH 2
+
+/* Constructor arguments of M3Detector / LineDetector (MetLib/Detector.py:186-220, :319-322)
+ * after the host has evaluated the pure-Python parts (int(window_sec*fps), select_subarea). */
+typedef struct mdb_config {
+    int32_t width, height;
+    int32_t window;          /* n = int(window_sec * fps), 1 <= n <= 255        Detector.py:197 */
+    int32_t adaptive;        /* cfg.binary.adaptive_bi_thre                     Detector.py:204 */
+    int32_t init_value;      /* cfg.binary.init_value (used when !adaptive)     Detector.py:208 */
+    int32_t sensitivity;     /* MDB_SENS_*  (cfg.binary.sensitivity)            Detector.py:177-183 */
+    int32_t nz_interval;     /* cfg.binary.interval                             Detector.py:202 */
+    int32_t roi[4];          /* SNR_SW.std_roi = (r0, c0, r1, c1)               Detector.py:93-122 */
+    int32_t hough_threshold; /* cfg.hough_line.threshold                        Detector.py:350 */
+    int32_t hough_min_len;   /* cfg.hough_line.min_len                          Detector.py:351 */
+    int32_t hough_max_gap;   /* cfg.hough_line.max_gap                          Detector.py:344 */
+    int32_t dy_mask;         /* cfg.dynamic.dy_mask                             Detector.py:211 */
+    int32_t max_batch;       /* most frames one mdb_detect_batch call may carry (>= 1) */
+    int32_t device;          /* CUDA device ordinal */
+    int32_t apply_mask;      /* != 0: multiply incoming frames by the mask on the device
+                                (Transform.mask_with, MetLib/imgproc.py:96-101) */
+    int32_t reserved[4];
+} mdb_config;
+
+/* Per-frame scalars that M3Detector exposes as attributes (Detector.py:227-229, :342-344, :355,
+ * :373; read by visu() :394-448). */
+typedef struct mdb_frame_info {
+    int64_t timer;             /* SlidingWindow.timer after this frame          utils.py:270 */
+    int32_t bi_threshold;      /* LineDetector.bi_threshold                     Detector.py:229 */
+    int32_t n_on;              /* number of 255-pixels in dst */
+    double bi_threshold_float; /* LineDetector.bi_threshold_float               Detector.py:228 */
+    double snr;                /* SNR_SW.snr (noise EMA value)                  Detector.py:124-127 */
+    double dst_sum;            /* M3Detector.dst_sum                            Detector.py:342 */
+    double gap;                /* maxLineGap handed to HoughLinesP              Detector.py:343-344 */
+    int32_t lines_num;         /* M3Detector.lines_num (raw HoughLinesP count)  Detector.py:357 */
+    int32_t n_raw;             /* rows valid in raw_lines (0 when lines_num > 500, :358-360) */
+    int32_t n_lines;           /* M3Detector.filtered_line_num (after NMS)      Detector.py:373 */
+    int32_t reserved;
+} mdb_frame_info;
+
+typedef struct mdb_detector *mdb_handle;
+
+const char *mdb_last_error(void);
+int mdb_version(void);
+/* number of visible CUDA devices (0 if none / no driver); never fails */
+int mdb_device_count(void);
+
+/* M3Detector.__init__ (Detector.py:319-322 -> LineDetector.__init__ :186-220 -> SNR_SW.__init__
+ * :41-71).  `mask` is the host uint8 {0,1} mask of shape (height,width) (fileio.load_mask). */
+int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle *out);
+int mdb_destroy(mdb_handle h);
+
+/* M3Detector.update(new_frame) (Detector.py:225-229): SNR_SW.update (:73-91) incl. the noise
+ * sample / EMA / adaptive threshold recurrence. */
+int mdb_update(mdb_handle h, const uint8_t *frame, int on_device);
+
+/* M3Detector.detect() (Detector.py:324-392).  lines: up to MDB_MAX_LINES rows [x1,y1,x2,y2] after
+ * lineset_nms (utils.py:780-839); nonline_prob: one double per row (cls_pred[:, -1]);
+ * raw_lines (optional, may be NULL): linesp_ext, up to MDB_MAX_LINES rows. */
+int mdb_detect(mdb_handle h, mdb_frame_info *info, int32_t *lines, double *nonline_prob,
+               int32_t *raw_lines);
+
+/* T x { update(frame[t]); detect() } in one call -- the batched form of MetDetPy.py:192-198.
+ * infos[T]; lines[T][MDB_MAX_LINES][4]; nonline_prob[T][MDB_MAX_LINES]; raw_lines optional
+ * ([T][MDB_MAX_LINES][4] or NULL); dst_out optional ([T][H][W] host or device buffer, or NULL). */
+int mdb_detect_batch(mdb_handle h, const uint8_t *frames, int T, int on_device,
+                     mdb_frame_info *infos, int32_t *lines, double *nonline_prob,
+                     int32_t *raw_lines, uint8_t *dst_out, int dst_on_device);
+
+/* Asynchronous halves of mdb_detect_batch for overlapping the next batch's host->device copy with
+ * this batch's kernels: submit enqueues copy + all kernels + the small result copy and returns;
+ * collect waits for them and runs the host NMS.  One batch may be in flight per handle. */
+int mdb_submit_batch(mdb_handle h, const uint8_t *frames, int T, int on_device);
+int mdb_collect_batch(mdb_handle h, mdb_frame_info *infos, int32_t *lines, double *nonline_prob,
+                      int32_t *raw_lines, uint8_t *dst_out, int dst_on_device);
+
+/* M3Detector.dst (Detector.py:371): the binary mask of the most recent detect, (H,W) uint8. */
+int mdb_get_dst(mdb_handle h, uint8_t *dst, int on_device);
+/* device pointer of the dst masks of the most recent batch ([T][H][W]); valid until the next call */
+int mdb_get_dst_device(mdb_handle h, const uint8_t **ptr);
+
+/* SlidingWindow.max / .mean / .sum (utils.py:288-300) of the detector's main window. Any output
+ * may be NULL. Host buffers of H*W elements. */
+int mdb_get_stack(mdb_handle h, uint8_t *max_out, uint8_t *mean_out, uint32_t *sum_out);
+
+/* The handle's CUDA stream (cudaStream_t) -- for callers that time with CUDA events. */
+int mdb_get_stream(mdb_handle h, void **stream);
+/* Number of kernels this handle has launched since creation. */
+int mdb_get_launch_count(mdb_handle h, int64_t *count);
+/* Device time (ms, CUDA events on the handle's stream) the fused mask kernel(s) took in the most
+ * recent batch, and how many launches that was. */
+int mdb_get_fused_time(mdb_handle h, float *ms, int32_t *launches);
+
+/* stacker.max_stacker / MaxImgContainer (MetLib/stacker.py:43-49, :146-175, :197-213) and
+ * MergeFunction.max (MetLib/utils.py:203-204): element-wise max over T frames of frame_bytes
+ * bytes each (any layout, e.g. H*W*3 colour).  frames/out are host or device per the flags. */
+int mdb_max_stack(const uint8_t *frames, int T, size_t frame_bytes, uint8_t *out,
+                  int frames_on_device, int out_on_device, int device);
+
+/* lineset_nms (MetLib/utils.py:780-839) on the host: lines_in[n][4] -> lines_out, prob_out;
+ * returns the number of kept lines in *n_out.  Ordering: len^2 descending, ties by descending
+ * input index (what np.argsort(...)[::-1] yields for the n <= 16 insertion-sort regime). */
+int mdb_lineset_nms(const int32_t *lines_in, int n, int32_t *lines_out, double *prob_out,
+                    int32_t *n_out);
+
+/* pinned host memory for frame staging (cudaHostAlloc / cudaFreeHost) */
+int mdb_alloc_pinned(size_t bytes, void **ptr);
+int mdb_free_pinned(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METDET_B200_H */

@@ -1,0 +1,45 @@
+// Shared declarations for libmetdet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/metdet_b200.h"
+
+#define MDB_HOUGH_ANGLES 180
+#define MDB_POINT_CAP 8192  // per-frame point-list capacity of the shared-memory PPHT path
+
+// Where frame `t` (0-based global frame index) lives: slot t % R of the device frame ring.
+struct FrameSrc {
+    const uint8_t *ring;
+    const uint8_t *mask;  // {0,1} bytes, or nullptr when frames arrive already masked
+    int R;
+    size_t HW;
+    __device__ __forceinline__ const uint8_t *frame(long long t) const {
+        return ring + (size_t)(t % R) * HW;
+    }
+    __device__ __forceinline__ unsigned px(long long t, size_t p) const {
+        unsigned v = frame(t)[p];
+        return mask ? v * mask[p] : v;
+    }
+};
+
+// Scalar detector state that lives on the device so that batches never round-trip to the host.
+struct DevState {
+    double ema_value;   // EMA.cur_value           utils.py:343
+    double ema_cur_m;   // EMA.cur_momentum
+    double ema_init_m;  // EMA.init_momentum
+    double ema_warm;    // EMA.warmup_speed (0 once warm-up ended)
+    long long ema_t;    // EMA.t
+    double thr_float;   // LineDetector.bi_threshold_float
+    int bi_threshold;   // LineDetector.bi_threshold
+    int pad;
+};
+
+struct HoughParams {
+    int W, H, numrho;
+    int threshold, min_len, max_gap;
+    double mask_area;
+    int cap;        // point-list stride / smem capacity
+    int max_lines;  // rows stored per frame
+    int walk_cap;   // capacity of the per-slot line-pixel scratch
+};

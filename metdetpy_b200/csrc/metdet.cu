@@ -1,0 +1,627 @@
+// libmetdet_b200.so -- host side of the C ABI declared in include/metdet_b200.h.
+// One handle = one detector (M3Detector, MetLib/Detector.py:302-392) with its device state:
+// frame ring, dy-mask run counters, EMA/threshold scalars, per-batch outputs, Hough slots.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "hough.cuh"
+#include "kernels_basic.cuh"
+#include "stream_kernel.cuh"
+
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(MDB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+struct mdb_detector {
+    mdb_config cfg;
+    int W, H, n, R;
+    size_t HW;
+    int slots;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // device
+    uint8_t *d_ring = nullptr, *d_mask = nullptr, *d_dst = nullptr;
+    uint8_t *d_run[2] = {nullptr, nullptr};
+    int run_cur = 0;
+    DevState *d_state = nullptr;
+    unsigned long long *d_noise = nullptr;
+    int *d_thr = nullptr, *d_nlines = nullptr;
+    double *d_thrf = nullptr, *d_snr = nullptr;
+    unsigned *d_npoints = nullptr;
+    uint32_t *d_points = nullptr;
+    int32_t *d_lines = nullptr;
+    int32_t *d_accum = nullptr;
+    uint32_t *d_bitmap = nullptr, *d_walk = nullptr;
+    uint32_t *d_okeys = nullptr, *d_oidx = nullptr;  // overflow path scratch (lazy)
+    unsigned *d_on = nullptr;
+    // stream-kernel state (lazy)
+    StreamState sk;
+    // pinned host mirrors
+    int *h_thr = nullptr, *h_nlines = nullptr;
+    double *h_thrf = nullptr, *h_snr = nullptr;
+    unsigned *h_npoints = nullptr;
+    int32_t *h_lines = nullptr;
+    // host state
+    long long timer = 0, dy_timer = 0;
+    long long launches = 0;
+    int pending_T = 0;          // frames of the batch in flight (submit..collect)
+    long long pending_timer0 = 0;
+    int last_T = 0;             // frames in d_dst from the most recent batch
+    float fused_ms = 0.f;
+    int fused_launches = 0;
+    bool single_pending = false;  // per-frame API: update() done, detect() outstanding
+    HoughParams hp;
+    int use_stream_kernel = 1;
+};
+
+extern "C" const char *mdb_last_error(void) { return g_err; }
+extern "C" int mdb_version(void) { return 100; }
+extern "C" int mdb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static FrameSrc frame_src(const mdb_detector *h) {
+    FrameSrc s;
+    s.ring = h->d_ring;
+    s.mask = h->cfg.apply_mask ? h->d_mask : nullptr;
+    s.R = h->R;
+    s.HW = h->HW;
+    return s;
+}
+
+static void free_all(mdb_detector *h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void *dev[] = {h->d_ring, h->d_mask, h->d_dst, h->d_run[0], h->d_run[1], h->d_state, h->d_noise,
+                   h->d_thr, h->d_nlines, h->d_thrf, h->d_snr, h->d_npoints, h->d_points,
+                   h->d_lines, h->d_accum, h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_on};
+    for (void *p : dev)
+        if (p) cudaFree(p);
+    stream_state_free(h->sk);
+    void *pin[] = {h->h_thr, h->h_nlines, h->h_thrf, h->h_snr, h->h_npoints, h->h_lines};
+    for (void *p : pin)
+        if (p) cudaFreeHost(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle *out) {
+    if (!cfg || !mask || !out) return fail(MDB_ERR_INVALID, "mdb_create: null argument");
+    *out = nullptr;
+    if (cfg->width < 1 || cfg->height < 1 || cfg->width > 65535 || cfg->height > 65535)
+        return fail(MDB_ERR_INVALID, "mdb_create: unsupported frame size %dx%d", cfg->width, cfg->height);
+    if (cfg->window < 1 || cfg->window > 255)
+        return fail(MDB_ERR_INVALID, "mdb_create: window n=%d outside 1..255", cfg->window);
+    if (cfg->max_batch < 1) return fail(MDB_ERR_INVALID, "mdb_create: max_batch must be >= 1");
+    if (cfg->sensitivity < 0 || cfg->sensitivity > 2)
+        return fail(MDB_ERR_INVALID, "mdb_create: bad sensitivity %d", cfg->sensitivity);
+    const int r0 = cfg->roi[0], c0 = cfg->roi[1], r1 = cfg->roi[2], c1 = cfg->roi[3];
+    if (r0 < 0 || c0 < 0 || r1 > cfg->height || c1 > cfg->width || r1 <= r0 || c1 <= c0)
+        return fail(MDB_ERR_INVALID, "mdb_create: bad std_roi (%d,%d,%d,%d)", r0, c0, r1, c1);
+    if (cfg->nz_interval < 0) return fail(MDB_ERR_INVALID, "mdb_create: negative interval");
+    int ndev = mdb_device_count();
+    if (ndev == 0)
+        return fail(MDB_ERR_CUDA, "mdb_create: no CUDA device -- this library has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(MDB_ERR_INVALID, "mdb_create: device %d of %d", cfg->device, ndev);
+    CK(cudaSetDevice(cfg->device));
+
+    mdb_detector *h = new (std::nothrow) mdb_detector();
+    if (!h) return fail(MDB_ERR_NOMEM, "mdb_create: out of host memory");
+    h->cfg = *cfg;
+    h->W = cfg->width; h->H = cfg->height; h->n = cfg->window;
+    h->HW = (size_t)h->W * h->H;
+    h->R = h->n - 1 + cfg->max_batch;
+    if (h->R < h->n) h->R = h->n;
+    const int T = cfg->max_batch;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) { delete h; return fail(MDB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    h->slots = std::min(T, prop.multiProcessorCount * 2);
+
+    HoughParams &hp = h->hp;
+    hp.W = h->W; hp.H = h->H; hp.numrho = 2 * (h->W + h->H) + 1;
+    hp.threshold = cfg->hough_threshold; hp.min_len = cfg->hough_min_len; hp.max_gap = cfg->hough_max_gap;
+    unsigned long long area = 0;
+    for (size_t i = 0; i < h->HW; i++) area += mask[i];
+    hp.mask_area = (double)area;
+    hp.cap = MDB_POINT_CAP; hp.max_lines = MDB_MAX_LINES; hp.walk_cap = h->W + h->H + 2;
+
+#define ALLOC(ptr, bytes)                                                                   \
+    do {                                                                                    \
+        cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes));                              \
+        if (e_ != cudaSuccess) {                                                            \
+            int rc_ = fail(MDB_ERR_NOMEM, "cudaMalloc(%zu bytes) for %s: %s", (size_t)(bytes), #ptr, \
+                           cudaGetErrorString(e_));                                         \
+            free_all(h);                                                                    \
+            return rc_;                                                                     \
+        }                                                                                   \
+    } while (0)
+#define CKH(call)                                                                           \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            int rc_ = fail(MDB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));          \
+            free_all(h);                                                                    \
+            return rc_;                                                                     \
+        }                                                                                   \
+    } while (0)
+
+    CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKH(cudaEventCreate(&h->ev0));
+    CKH(cudaEventCreate(&h->ev1));
+    const size_t bm_words = (h->HW + 31) / 32;
+    ALLOC(h->d_ring, (size_t)h->R * h->HW);
+    ALLOC(h->d_mask, h->HW);
+    ALLOC(h->d_dst, (size_t)T * h->HW);
+    ALLOC(h->d_run[0], h->HW);
+    ALLOC(h->d_run[1], h->HW);
+    ALLOC(h->d_state, sizeof(DevState));
+    ALLOC(h->d_noise, (size_t)T * 2 * sizeof(unsigned long long));
+    ALLOC(h->d_thr, T * sizeof(int));
+    ALLOC(h->d_nlines, T * sizeof(int));
+    ALLOC(h->d_thrf, T * sizeof(double));
+    ALLOC(h->d_snr, T * sizeof(double));
+    ALLOC(h->d_npoints, T * sizeof(unsigned));
+    ALLOC(h->d_points, (size_t)T * MDB_POINT_CAP * sizeof(uint32_t));
+    ALLOC(h->d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t));
+    ALLOC(h->d_accum, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t));
+    ALLOC(h->d_bitmap, (size_t)h->slots * bm_words * sizeof(uint32_t));
+    ALLOC(h->d_walk, (size_t)h->slots * hp.walk_cap * sizeof(uint32_t));
+    ALLOC(h->d_on, sizeof(unsigned));
+    CKH(cudaMemsetAsync(h->d_ring, 0, (size_t)h->R * h->HW, h->stream));
+    CKH(cudaMemsetAsync(h->d_run[0], 0, h->HW, h->stream));
+    CKH(cudaMemsetAsync(h->d_run[1], 0, h->HW, h->stream));
+    CKH(cudaMemsetAsync(h->d_accum, 0, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t), h->stream));
+    CKH(cudaMemsetAsync(h->d_bitmap, 0, (size_t)h->slots * bm_words * sizeof(uint32_t), h->stream));
+    CKH(cudaMemsetAsync(h->d_dst, 0, (size_t)T * h->HW, h->stream));
+    CKH(cudaMemcpyAsync(h->d_mask, mask, h->HW, cudaMemcpyHostToDevice, h->stream));
+
+    CKH(cudaHostAlloc((void **)&h->h_thr, T * sizeof(int), cudaHostAllocDefault));
+    CKH(cudaHostAlloc((void **)&h->h_nlines, T * sizeof(int), cudaHostAllocDefault));
+    CKH(cudaHostAlloc((void **)&h->h_thrf, T * sizeof(double), cudaHostAllocDefault));
+    CKH(cudaHostAlloc((void **)&h->h_snr, T * sizeof(double), cudaHostAllocDefault));
+    CKH(cudaHostAlloc((void **)&h->h_npoints, T * sizeof(unsigned), cudaHostAllocDefault));
+    CKH(cudaHostAlloc((void **)&h->h_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t), cudaHostAllocDefault));
+
+    // scalar state: LineDetector.__init__ (Detector.py:204-209), SNR_SW.__init__ (:58-61)
+    DevState st;
+    memset(&st, 0, sizeof st);
+    st.ema_init_m = 1.0 - (double)cfg->nz_interval / 60.0;
+    st.ema_cur_m = st.ema_init_m;
+    st.ema_warm = (double)h->n;
+    st.ema_value = 0.0;
+    static const int abs_sens[3] = {7, 5, 3};  // low, normal, high
+    st.bi_threshold = cfg->adaptive ? abs_sens[cfg->sensitivity] : cfg->init_value;
+    st.thr_float = (double)st.bi_threshold;
+    CKH(cudaMemcpyAsync(h->d_state, &st, sizeof st, cudaMemcpyHostToDevice, h->stream));
+
+    // trig table exactly as OpenCV builds it: (float)cos((double)n * (double)(float)theta)
+    float trig[2 * MDB_HOUGH_ANGLES];
+    const float theta = (float)(3.14159265358979323846 / 180.0);
+    for (int k = 0; k < MDB_HOUGH_ANGLES; k++) {
+        trig[2 * k] = (float)cos((double)k * (double)theta);
+        trig[2 * k + 1] = (float)sin((double)k * (double)theta);
+    }
+    CKH(cudaMemcpyToSymbolAsync(c_trig, trig, sizeof trig, 0, cudaMemcpyHostToDevice, h->stream));
+    CKH(cudaFuncSetAttribute(hough_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             MDB_POINT_CAP * 8));
+    CKH(cudaStreamSynchronize(h->stream));
+    {
+        int rc = stream_state_init(h->sk, h->W, h->H, h->n, cfg->device);
+        if (rc != 0) { free_all(h); return fail(MDB_ERR_CUDA, "stream kernel init failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    }
+    *out = h;
+    return MDB_OK;
+}
+
+extern "C" int mdb_destroy(mdb_handle h) {
+    if (!h) return fail(MDB_ERR_INVALID, "mdb_destroy: null handle");
+    free_all(h);
+    return MDB_OK;
+}
+
+// ---- ingest: copy T frames into ring slots (global frame index timer .. timer+T-1) ----------
+static int ingest(mdb_detector *h, const uint8_t *frames, int T, int on_device) {
+    long long t = h->timer;
+    int done = 0;
+    while (done < T) {
+        const int slot = (int)(t % h->R);
+        const int run = std::min(T - done, h->R - slot);
+        CK(cudaMemcpyAsync(h->d_ring + (size_t)slot * h->HW, frames + (size_t)done * h->HW,
+                           (size_t)run * h->HW, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                           h->stream));
+        done += run;
+        t += run;
+    }
+    return MDB_OK;
+}
+
+static int launch_noise_thr(mdb_detector *h, int T, long long timer0) {
+    const mdb_config &c = h->cfg;
+    const int rh = c.roi[2] - c.roi[0], rw = c.roi[3] - c.roi[1];
+    const long long std_interval = (long long)c.nz_interval * h->n;
+    CK(cudaMemsetAsync(h->d_noise, 0, (size_t)T * 2 * sizeof(unsigned long long), h->stream));
+    const int gx = std::max(1, std::min((rh * rw + 255) / 256, 592));
+    noise_sample_kernel<<<dim3(gx, T), 256, 0, h->stream>>>(frame_src(h), h->W, h->n, timer0, std_interval,
+                                                          c.roi[0], c.roi[1], rh, rw, h->d_noise);
+    threshold_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_noise, T, timer0, h->n, std_interval,
+                                             (long long)rh * rw, c.adaptive, c.sensitivity, h->d_thr,
+                                             h->d_thrf, h->d_snr);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return MDB_OK;
+}
+
+// fused mask chain for frames i = 0..T-1 of the batch (global index timer0 + i)
+static int launch_fused(mdb_detector *h, int T, long long timer0, long long dy0) {
+    CK(cudaMemsetAsync(h->d_npoints, 0, T * sizeof(unsigned), h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    int nl = 0;
+    if (h->use_stream_kernel && stream_kernel_supported(h->sk, T)) {
+        int rc = stream_kernel_launch(h->sk, frame_src(h), timer0, dy0, T, h->cfg.dy_mask, h->d_thr,
+                                      h->d_run[h->run_cur], h->d_dst, h->d_npoints, h->d_points,
+                                      MDB_POINT_CAP, h->stream, &nl);
+        if (rc != 0) return fail(MDB_ERR_CUDA, "stream kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
+    } else {
+        dim3 grid((h->W + V1_TW - 1) / V1_TW, (h->H + V1_TH - 1) / V1_TH);
+        for (int i = 0; i < T; i++) {
+            const long long t = timer0 + i;
+            const int L = (int)std::min<long long>(h->n, t + 1);
+            const int Ldy = (int)std::min<long long>(h->n, dy0 + i + 1);
+            fused_frame_kernel<<<grid, 256, 0, h->stream>>>(
+                frame_src(h), h->W, h->H, h->n, t, L, Ldy, h->cfg.dy_mask, h->d_thr + i,
+                h->d_run[h->run_cur], h->d_run[h->run_cur ^ 1], h->d_dst + (size_t)i * h->HW,
+                h->d_npoints + i, h->d_points + (size_t)i * MDB_POINT_CAP, MDB_POINT_CAP);
+            if (h->cfg.dy_mask) h->run_cur ^= 1;
+            nl++;
+        }
+    }
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->fused_launches = nl;
+    h->launches += nl;
+    CK(cudaGetLastError());
+    return MDB_OK;
+}
+
+static int launch_hough_and_copy(mdb_detector *h, int T) {
+    const int grid = std::min(T, h->slots);
+    hough_batch_kernel<<<grid, HOUGH_THREADS, MDB_POINT_CAP * 8, h->stream>>>(
+        h->hp, T, h->d_npoints, h->d_points, h->d_accum, h->d_bitmap, h->d_walk, h->d_lines, h->d_nlines);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_thr, h->d_thr, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_thrf, h->d_thrf, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_snr, h->d_snr, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_npoints, h->d_npoints, T * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_nlines, h->d_nlines, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_lines, h->d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t),
+                       cudaMemcpyDeviceToHost, h->stream));
+    return MDB_OK;
+}
+
+// frames whose on-pixel count exceeded the shared-memory capacity: ordered compaction + global PPHT
+static int overflow_frame(mdb_detector *h, int i) {
+    if (!h->d_okeys) {
+        if (cudaMalloc((void **)&h->d_okeys, h->HW * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMalloc((void **)&h->d_oidx, h->HW * sizeof(uint32_t)) != cudaSuccess)
+            return fail(MDB_ERR_NOMEM, "overflow scratch: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    compact_ordered_kernel<<<1, 1024, 0, h->stream>>>(h->d_dst + (size_t)i * h->HW, h->W, h->H, h->d_okeys, h->d_on);
+    hough_global_kernel<<<1, HOUGH_THREADS, 0, h->stream>>>(h->hp, h->d_on, h->d_okeys, h->d_oidx, h->d_accum,
+                                                           h->d_bitmap, h->d_walk,
+                                                           h->d_lines + (size_t)i * MDB_MAX_LINES * 4, h->d_nlines + i);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_nlines + i, h->d_nlines + i, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_lines + (size_t)i * MDB_MAX_LINES * 4, h->d_lines + (size_t)i * MDB_MAX_LINES * 4,
+                       MDB_MAX_LINES * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MDB_OK;
+}
+
+// ---- lineset_nms on the host (MetLib/utils.py:780-839) --------------------------------------
+static int nms_host(const int32_t *in, int n, int32_t *out, double *prob) {
+    std::vector<long long> len2(n), A(n), B(n), C(n), cx(n), cy(n);
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) {
+        const long long x1 = in[4 * i], y1 = in[4 * i + 1], x2 = in[4 * i + 2], y2 = in[4 * i + 3];
+        len2[i] = (y2 - y1) * (y2 - y1) + (x2 - x1) * (x2 - x1);
+        A[i] = y2 - y1; B[i] = x1 - x2; C[i] = x2 * y1 - y2 * x1;
+        // numpy floor division of the (non-negative) coordinate sums
+        cx[i] = (x2 + x1) >= 0 ? (x2 + x1) / 2 : -((-(x2 + x1) + 1) / 2);
+        cy[i] = (y2 + y1) >= 0 ? (y2 + y1) / 2 : -((-(y2 + y1) + 1) / 2);
+        order[i] = i;
+    }
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        if (len2[a] != len2[b]) return len2[a] > len2[b];
+        return a > b;
+    });
+    std::vector<char> taken(n, 0);
+    int k = 0;
+    for (int i = 0; i < n; i++) {
+        const int a = order[i];
+        if (taken[a]) continue;
+        taken[a] = 1;
+        long long w = 0;
+        for (int j = i; j < n; j++) {
+            const int b = order[j];
+            if (taken[b]) continue;
+            const long long dx = cx[a] - cx[b], dy = cy[a] - cy[b];
+            const long long lim = len2[a] / 4;  // len2 >= 0: // == /
+            if (dx * dx + dy * dy < lim) {
+                taken[b] = 1;
+                w = std::max(w, std::llabs(A[a] * cx[b] + B[a] * cy[b] + C[a]));
+            }
+        }
+        memcpy(out + 4 * k, in + 4 * a, 4 * sizeof(int32_t));
+        double p = (double)w / std::sqrt((double)(A[a] * A[a] + B[a] * B[a])) / std::sqrt((double)len2[a]) * 2;
+        if (p > 1) p = 1;  // NaN (zero-length line) stays NaN, as in numpy
+        prob[k] = p;
+        k++;
+    }
+    return k;
+}
+
+extern "C" int mdb_lineset_nms(const int32_t *lines_in, int n, int32_t *lines_out, double *prob_out,
+                               int32_t *n_out) {
+    if (n < 0 || (n > 0 && (!lines_in || !lines_out || !prob_out)) || !n_out)
+        return fail(MDB_ERR_INVALID, "mdb_lineset_nms: bad arguments");
+    *n_out = n ? nms_host(lines_in, n, lines_out, prob_out) : 0;
+    return MDB_OK;
+}
+
+// fill infos / line outputs for frames 0..T-1 of the finished batch
+static int finish_batch(mdb_detector *h, int T, long long timer0, mdb_frame_info *infos, int32_t *lines,
+                        double *prob, int32_t *raw_lines) {
+    for (int i = 0; i < T; i++)
+        if (h->h_nlines[i] < 0) {
+            int rc = overflow_frame(h, i);
+            if (rc) return rc;
+        }
+    for (int i = 0; i < T; i++) {
+        mdb_frame_info fi;
+        memset(&fi, 0, sizeof fi);
+        fi.timer = timer0 + i + 1;
+        fi.bi_threshold = h->h_thr[i];
+        fi.bi_threshold_float = h->h_thrf[i];
+        fi.snr = h->h_snr[i];
+        fi.n_on = (int32_t)h->h_npoints[i];
+        // Detector.py:342-344 (host doubles; this TU is compiled with -ffp-contract=off)
+        volatile double ds = (double)h->h_npoints[i] / h->hp.mask_area;
+        ds = ds * 100.0;
+        fi.dst_sum = ds;
+        volatile double g = ds / 0.05;
+        g = 1.0 - g;
+        if (!(g > 0.0)) g = 0.0;
+        fi.gap = g * (double)h->cfg.hough_max_gap;
+        fi.lines_num = h->h_nlines[i];
+        const int32_t *src = h->h_lines + (size_t)i * MDB_MAX_LINES * 4;
+        int nraw = fi.lines_num > MDB_NUM_LINES_TOOMUCH ? 0 : fi.lines_num;
+        fi.n_raw = nraw;
+        if (raw_lines && nraw) memcpy(raw_lines + (size_t)i * MDB_MAX_LINES * 4, src, (size_t)nraw * 16);
+        fi.n_lines = 0;
+        if (nraw && lines && prob)
+            fi.n_lines = nms_host(src, nraw, lines + (size_t)i * MDB_MAX_LINES * 4, prob + (size_t)i * MDB_MAX_LINES);
+        if (infos) infos[i] = fi;
+    }
+    return MDB_OK;
+}
+
+// ---- per-frame API ---------------------------------------------------------------------------
+extern "C" int mdb_update(mdb_handle h, const uint8_t *frame, int on_device) {
+    if (!h || !frame) return fail(MDB_ERR_INVALID, "mdb_update: null argument");
+    if (h->pending_T) return fail(MDB_ERR_STATE, "mdb_update: a submitted batch has not been collected");
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = ingest(h, frame, 1, on_device);
+    if (rc) return rc;
+    rc = launch_noise_thr(h, 1, h->timer);
+    if (rc) return rc;
+    h->timer += 1;
+    h->single_pending = true;
+    if (!on_device) CK(cudaStreamSynchronize(h->stream));  // caller may reuse its buffer on return
+    return MDB_OK;
+}
+
+extern "C" int mdb_detect(mdb_handle h, mdb_frame_info *info, int32_t *lines, double *nonline_prob,
+                          int32_t *raw_lines) {
+    if (!h) return fail(MDB_ERR_INVALID, "mdb_detect: null handle");
+    if (h->timer == 0) return fail(MDB_ERR_STATE, "mdb_detect: no frame has been pushed yet");
+    if (h->pending_T) return fail(MDB_ERR_STATE, "mdb_detect: a submitted batch has not been collected");
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = launch_fused(h, 1, h->timer - 1, h->dy_timer);
+    if (rc) return rc;
+    rc = launch_hough_and_copy(h, 1);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->fused_ms, h->ev0, h->ev1));
+    h->dy_timer += 1;
+    h->last_T = 1;
+    h->single_pending = false;
+    return finish_batch(h, 1, h->timer - 1, info, lines, nonline_prob, raw_lines);
+}
+
+// ---- batched API -----------------------------------------------------------------------------
+extern "C" int mdb_submit_batch(mdb_handle h, const uint8_t *frames, int T, int on_device) {
+    if (!h || !frames) return fail(MDB_ERR_INVALID, "mdb_submit_batch: null argument");
+    if (T < 1 || T > h->cfg.max_batch)
+        return fail(MDB_ERR_INVALID, "mdb_submit_batch: T=%d outside 1..max_batch=%d", T, h->cfg.max_batch);
+    if (h->pending_T) return fail(MDB_ERR_STATE, "mdb_submit_batch: previous batch not collected");
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = ingest(h, frames, T, on_device);
+    if (rc) return rc;
+    const long long timer0 = h->timer;
+    rc = launch_noise_thr(h, T, timer0);
+    if (rc) return rc;
+    rc = launch_fused(h, T, timer0, h->dy_timer);
+    if (rc) return rc;
+    rc = launch_hough_and_copy(h, T);
+    if (rc) return rc;
+    h->pending_T = T;
+    h->pending_timer0 = timer0;
+    h->timer += T;
+    h->dy_timer += T;
+    return MDB_OK;
+}
+
+extern "C" int mdb_collect_batch(mdb_handle h, mdb_frame_info *infos, int32_t *lines, double *nonline_prob,
+                                 int32_t *raw_lines, uint8_t *dst_out, int dst_on_device) {
+    if (!h) return fail(MDB_ERR_INVALID, "mdb_collect_batch: null handle");
+    if (!h->pending_T) return fail(MDB_ERR_STATE, "mdb_collect_batch: nothing submitted");
+    CK(cudaSetDevice(h->cfg.device));
+    const int T = h->pending_T;
+    if (dst_out)
+        CK(cudaMemcpyAsync(dst_out, h->d_dst, (size_t)T * h->HW,
+                           dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->fused_ms, h->ev0, h->ev1));
+    h->pending_T = 0;
+    h->last_T = T;
+    return finish_batch(h, T, h->pending_timer0, infos, lines, nonline_prob, raw_lines);
+}
+
+extern "C" int mdb_detect_batch(mdb_handle h, const uint8_t *frames, int T, int on_device,
+                                mdb_frame_info *infos, int32_t *lines, double *nonline_prob,
+                                int32_t *raw_lines, uint8_t *dst_out, int dst_on_device) {
+    int rc = mdb_submit_batch(h, frames, T, on_device);
+    if (rc) return rc;
+    return mdb_collect_batch(h, infos, lines, nonline_prob, raw_lines, dst_out, dst_on_device);
+}
+
+extern "C" int mdb_get_dst(mdb_handle h, uint8_t *dst, int on_device) {
+    if (!h || !dst) return fail(MDB_ERR_INVALID, "mdb_get_dst: null argument");
+    if (h->last_T < 1) return fail(MDB_ERR_STATE, "mdb_get_dst: no detect has run yet");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(dst, h->d_dst + (size_t)(h->last_T - 1) * h->HW, h->HW,
+                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MDB_OK;
+}
+
+extern "C" int mdb_get_dst_device(mdb_handle h, const uint8_t **ptr) {
+    if (!h || !ptr) return fail(MDB_ERR_INVALID, "mdb_get_dst_device: null argument");
+    *ptr = h->d_dst;
+    return MDB_OK;
+}
+
+extern "C" int mdb_get_stack(mdb_handle h, uint8_t *max_out, uint8_t *mean_out, uint32_t *sum_out) {
+    if (!h) return fail(MDB_ERR_INVALID, "mdb_get_stack: null handle");
+    if (h->timer == 0) return fail(MDB_ERR_STATE, "mdb_get_stack: empty window");
+    CK(cudaSetDevice(h->cfg.device));
+    uint8_t *dmx = nullptr, *dmean = nullptr;
+    uint32_t *dsum = nullptr;
+    CK(cudaMalloc((void **)&dmx, h->HW));
+    CK(cudaMalloc((void **)&dmean, h->HW));
+    CK(cudaMalloc((void **)&dsum, h->HW * 4));
+    const long long t = h->timer - 1;
+    const int L = (int)std::min<long long>(h->n, h->timer);
+    stack_readback_kernel<<<592, 256, 0, h->stream>>>(frame_src(h), h->HW, h->n, t, L, dmx, dmean, dsum);
+    h->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && max_out) e = cudaMemcpyAsync(max_out, dmx, h->HW, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && mean_out) e = cudaMemcpyAsync(mean_out, dmean, h->HW, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && sum_out) e = cudaMemcpyAsync(sum_out, dsum, h->HW * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dmx); cudaFree(dmean); cudaFree(dsum);
+    if (e != cudaSuccess) return fail(MDB_ERR_CUDA, "mdb_get_stack: %s", cudaGetErrorString(e));
+    return MDB_OK;
+}
+
+extern "C" int mdb_get_stream(mdb_handle h, void **stream) {
+    if (!h || !stream) return fail(MDB_ERR_INVALID, "mdb_get_stream: null argument");
+    *stream = (void *)h->stream;
+    return MDB_OK;
+}
+
+extern "C" int mdb_get_launch_count(mdb_handle h, int64_t *count) {
+    if (!h || !count) return fail(MDB_ERR_INVALID, "mdb_get_launch_count: null argument");
+    *count = h->launches;
+    return MDB_OK;
+}
+
+extern "C" int mdb_get_fused_time(mdb_handle h, float *ms, int32_t *launches) {
+    if (!h) return fail(MDB_ERR_INVALID, "mdb_get_fused_time: null handle");
+    if (ms) *ms = h->fused_ms;
+    if (launches) *launches = h->fused_launches;
+    return MDB_OK;
+}
+
+// internal knob used by the parity tests to force the generic per-frame kernel
+extern "C" int mdb_set_option(mdb_handle h, const char *name, int value) {
+    if (!h || !name) return fail(MDB_ERR_INVALID, "mdb_set_option: null argument");
+    if (!strcmp(name, "stream_kernel")) { h->use_stream_kernel = value; return MDB_OK; }
+    return fail(MDB_ERR_INVALID, "mdb_set_option: unknown option %s", name);
+}
+
+// ---- max stack --------------------------------------------------------------------------------
+extern "C" int mdb_max_stack(const uint8_t *frames, int T, size_t frame_bytes, uint8_t *out,
+                             int frames_on_device, int out_on_device, int device) {
+    if (!frames || !out || T < 1 || frame_bytes == 0)
+        return fail(MDB_ERR_INVALID, "mdb_max_stack: bad arguments");
+    if (mdb_device_count() == 0) return fail(MDB_ERR_CUDA, "mdb_max_stack: no CUDA device (no CPU fallback)");
+    CK(cudaSetDevice(device));
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    uint8_t *d_out = out, *d_chunk = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (!out_on_device) e = cudaMalloc((void **)&d_out, frame_bytes);
+    const int chunk = frames_on_device ? T : (int)std::max<size_t>(1, std::min<size_t>(T, (512ull << 20) / frame_bytes));
+    if (e == cudaSuccess && !frames_on_device) e = cudaMalloc((void **)&d_chunk, (size_t)chunk * frame_bytes);
+    const int grid = (int)std::min<size_t>((frame_bytes / 16 + 255) / 256 + 1, 148 * 16);
+    for (int t0 = 0; e == cudaSuccess && t0 < T; t0 += chunk) {
+        const int c = std::min(chunk, T - t0);
+        const uint8_t *src = frames + (size_t)t0 * frame_bytes;
+        if (!frames_on_device) {
+            e = cudaMemcpyAsync(d_chunk, src, (size_t)c * frame_bytes, cudaMemcpyHostToDevice, st);
+            src = d_chunk;
+        }
+        if (e == cudaSuccess) {
+            max_stack_kernel<<<grid, 256, 0, st>>>(src, c, frame_bytes, d_out, t0 > 0);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess && !frames_on_device) e = cudaStreamSynchronize(st);
+    }
+    if (e == cudaSuccess && !out_on_device) e = cudaMemcpyAsync(out, d_out, frame_bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (d_chunk) cudaFree(d_chunk);
+    if (!out_on_device && d_out) cudaFree(d_out);
+    cudaStreamDestroy(st);
+    if (e != cudaSuccess) return fail(MDB_ERR_CUDA, "mdb_max_stack: %s", cudaGetErrorString(e));
+    return MDB_OK;
+}
+
+extern "C" int mdb_alloc_pinned(size_t bytes, void **ptr) {
+    if (!ptr) return fail(MDB_ERR_INVALID, "mdb_alloc_pinned: null argument");
+    CK(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return MDB_OK;
+}
+extern "C" int mdb_free_pinned(void *ptr) {
+    CK(cudaFreeHost(ptr));
+    return MDB_OK;
+}

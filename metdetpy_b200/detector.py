@@ -1,0 +1,478 @@
+"""Host-side mirror of the reference's detector interface for the M3 line-detector path.
+
+Same class names, constructor arguments, methods, attributes and return types as
+MetLib/Detector.py (`BaseDetector` :130-157, `LineDetector` :160-242, `M3Detector` :302-448,
+`SNR_SW` :34-127) and MetLib/utils.py (`SlidingWindow` :225-321, `EMA` :324-368,
+`lineset_nms` :780-839), so `MetDetPy.detect_video` (MetDetPy.py:137-142, :197-198) can drive it
+unchanged.  All pixel work happens in libmetdet_b200.so (CUDA, sm_100a) through the C ABI in
+include/metdet_b200.h; this module only marshals buffers.  No CPU fallback exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from abc import ABCMeta, abstractmethod
+from typing import Any, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import MAX_LINES, Config, FrameInfo, check
+from .config import BinaryCfg
+
+NUM_LINES_TOOMUCH = 500  # MetLib/Detector.py:30
+DEFAULT_INIT_VALUE = 5  # MetLib/Detector.py:31
+PI = np.pi / 180.0  # MetLib/utils.py:22
+_SENS_CODE = {"low": 0, "normal": 1, "high": 2}
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+def select_subarea(mask: np.ndarray, area: float) -> tuple[int, int, int, int]:
+    """SNR_SW.select_subarea (MetLib/Detector.py:93-122): centre ROI of relative area `area`, moved
+    up in 10-row steps while the un-masked share does not drop. Returns std_roi (r0, c0, r1, c1)."""
+    h, w = mask.shape[:2]
+    if area == 0:
+        raise ValueError("binary.area == 0 is not supported (the reference's own path is broken "
+                         "for it, MetLib/Detector.py:105-107)")
+    rate = area ** (1 / 2)
+    sub_h, sub_w = int(h * rate), int(w * rate)
+    if sub_h < 1 or sub_w < 1:
+        raise ValueError(f"binary.area={area} gives an empty noise ROI for a {w}x{h} frame")
+    r0, c0 = (h - sub_h) // 2, (w - sub_w) // 2
+    tot = sub_h * sub_w
+    ratio = np.sum(mask[r0:r0 + sub_h, c0:c0 + sub_w]) / tot
+    while ratio < 1:
+        r0 -= 10
+        new_ratio = np.sum(mask[r0:r0 + sub_h, c0:c0 + sub_w]) / tot
+        if new_ratio < ratio or r0 < 0:
+            r0 += 10
+            break
+        ratio = new_ratio
+    return (r0, c0, r0 + sub_h, c0 + sub_w)
+
+
+def lineset_nms(lines: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """lineset_nms (MetLib/utils.py:780-839) -- runs in the library's host C++ (mdb_lineset_nms)."""
+    lines = np.ascontiguousarray(lines, np.int32).reshape(-1, 4)
+    n = len(lines)
+    out = np.empty((max(n, 1), 4), np.int32)
+    prob = np.empty(max(n, 1), np.float64)
+    k = C.c_int32(0)
+    check(_lib.load().mdb_lineset_nms(_ptr(lines), n, _ptr(out), _ptr(prob), C.byref(k)), "lineset_nms")
+    return out[:k.value].copy(), prob[:k.value].copy()
+
+
+class EMA:
+    """EMA (MetLib/utils.py:324-368). Scalar host recurrence kept for API compatibility; inside the
+    detector the same recurrence runs on the device (threshold_kernel)."""
+
+    def __init__(self, momentum: float = 0.99, warmup_speed: float = 1) -> None:
+        assert 0 <= momentum <= 1, "momentum should be [0,1]"
+        self.init_momentum = momentum
+        self.cur_momentum = momentum
+        self.cur_value = 0
+        self.t = 0
+        self.warmup_speed = warmup_speed
+
+    def update(self, value) -> None:
+        if self.warmup_speed:
+            self.adjust_weight()
+        self.cur_value = self.cur_momentum * self.cur_value + (1 - self.cur_momentum) * value
+        self.t += 1
+
+    def adjust_weight(self) -> None:
+        k = self.t * (1 - self.init_momentum) * self.warmup_speed
+        if k < 1:
+            self.cur_momentum = self.init_momentum * (1 - (1 - k) ** 2)
+        else:
+            self.warmup_speed = 0
+            self.cur_momentum = self.init_momentum
+
+
+class _Engine:
+    """Owns one mdb_handle and its output staging buffers."""
+
+    def __init__(self, mask: np.ndarray, n: int, *, adaptive: bool, init_value: int,
+                 sensitivity: str, interval: int, roi, hough, dy_mask: bool, max_batch: int,
+                 device: int, apply_mask: bool):
+        self.lib = _lib.load()
+        if self.lib.mdb_device_count() < 1:
+            raise _lib.MetDetError("no CUDA device visible: metdetpy_b200 has no CPU fallback")
+        mask = np.ascontiguousarray(mask, np.uint8)
+        if mask.ndim != 2:
+            raise ValueError("mask must be a (H, W) uint8 array of {0,1}")
+        self.H, self.W = mask.shape
+        self.n = n
+        self.max_batch = max_batch
+        cfg = Config()
+        cfg.width, cfg.height, cfg.window = self.W, self.H, n
+        cfg.adaptive, cfg.init_value = int(bool(adaptive)), int(init_value)
+        if sensitivity not in _SENS_CODE:
+            raise KeyError(sensitivity)
+        cfg.sensitivity = _SENS_CODE[sensitivity]
+        cfg.nz_interval = int(interval)
+        for i in range(4):
+            cfg.roi[i] = int(roi[i])
+        cfg.hough_threshold, cfg.hough_min_len, cfg.hough_max_gap = (int(v) for v in hough)
+        cfg.dy_mask = int(bool(dy_mask))
+        cfg.max_batch, cfg.device, cfg.apply_mask = int(max_batch), int(device), int(bool(apply_mask))
+        self.handle = C.c_void_p()
+        check(self.lib.mdb_create(C.byref(cfg), _ptr(mask), C.byref(self.handle)), "mdb_create")
+        T = max_batch
+        self.infos = (FrameInfo * T)()
+        self.lines = np.zeros((T, MAX_LINES, 4), np.int32)
+        self.prob = np.zeros((T, MAX_LINES), np.float64)
+        self.raw = np.zeros((T, MAX_LINES, 4), np.int32)
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.mdb_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check_frame(self, frame: np.ndarray) -> np.ndarray:
+        if frame.dtype != np.uint8 or frame.shape[-2:] != (self.H, self.W):
+            raise ValueError(f"expected uint8 frame(s) of shape (..., {self.H}, {self.W}), "
+                             f"got {frame.dtype} {frame.shape}")
+        return np.ascontiguousarray(frame)
+
+    def set_option(self, name: str, value: int):
+        check(self.lib.mdb_set_option(self.handle, name.encode(), int(value)), "mdb_set_option")
+
+    def stream_ptr(self) -> int:
+        p = C.c_void_p()
+        check(self.lib.mdb_get_stream(self.handle, C.byref(p)), "mdb_get_stream")
+        return p.value or 0
+
+    def launch_count(self) -> int:
+        v = C.c_int64()
+        check(self.lib.mdb_get_launch_count(self.handle, C.byref(v)), "mdb_get_launch_count")
+        return v.value
+
+    def fused_time(self) -> tuple[float, int]:
+        ms, nl = C.c_float(), C.c_int32()
+        check(self.lib.mdb_get_fused_time(self.handle, C.byref(ms), C.byref(nl)), "mdb_get_fused_time")
+        return ms.value, nl.value
+
+
+class SlidingWindow(object):
+    """SlidingWindow (MetLib/utils.py:225-321) for uint8 frames, backed by the device frame ring:
+    `update`, `max`, `mean`, `sum`, `length`, `timer`, `cur_index`, `refresh_max`.
+    Only the reference's `dtype=np.uint8, force_int=True` mode (the one the detectors use,
+    Detector.py:53-57, :212-215) exists; anything else raises."""
+
+    def __init__(self, n: int, size: Sequence[int], dtype: type = np.uint8, force_int: bool = True,
+                 calc_std: bool = False, device: int = 0) -> None:
+        if np.dtype(dtype) != np.uint8 or not force_int or calc_std:
+            raise NotImplementedError("device SlidingWindow supports dtype=uint8, force_int=True, "
+                                      "calc_std=False (the detector configuration)")
+        if len(size) != 2:
+            raise ValueError("size must be (H, W)")
+        self.n = n
+        self.size = tuple(size)
+        self.dtype = dtype
+        self.force_int = force_int
+        self.calc_std = calc_std
+        h, w = self.size
+        self._eng = _Engine(np.ones((h, w), np.uint8), n, adaptive=False, init_value=0,
+                            sensitivity="normal", interval=0, roi=(0, 0, 1, 1), hough=(1, 1, 1),
+                            dy_mask=False, max_batch=1, device=device, apply_mask=False)
+        self.timer = 0
+        self.cur_index = 0
+
+    def update(self, new_frame: np.ndarray) -> None:
+        f = self._eng.check_frame(new_frame)
+        check(self._eng.lib.mdb_update(self._eng.handle, _ptr(f), 0), "SlidingWindow.update")
+        self.timer += 1
+        self.cur_index = (self.timer - 1) % self.n
+
+    def _stack(self, which: int):
+        h, w = self.size
+        if self.timer == 0:
+            return np.zeros((h, w), np.uint32 if which == 2 else np.uint8)
+        out = np.empty((h, w), np.uint32 if which == 2 else np.uint8)
+        args = [None, None, None]
+        args[which] = _ptr(out)
+        check(self._eng.lib.mdb_get_stack(self._eng.handle, *args), "SlidingWindow")
+        return out
+
+    @property
+    def length(self) -> int:
+        return min(self.n, self.timer)
+
+    @property
+    def max(self) -> np.ndarray:
+        return self._stack(0)
+
+    @property
+    def mean(self) -> np.ndarray:
+        return self._stack(1)
+
+    @property
+    def sum(self) -> np.ndarray:
+        return self._stack(2)
+
+    def refresh_max(self) -> np.ndarray:
+        return self.max
+
+
+class SNR_SW(object):
+    """View of the detector's main window with the attributes of SNR_SW (MetLib/Detector.py:34-127)
+    that callers read: `snr`, `std_roi`, `n`, `timer`, `length`, `max`, `mean`, `sum`."""
+
+    def __init__(self, det: "LineDetector") -> None:
+        self._det = det
+        self.n = det.stack_maxsize
+        self.std_roi = det._roi
+        self.est_snr = True
+        self.nz_interval = det.bi_cfg.interval
+        self.std_interval = self.nz_interval * self.n
+
+    @property
+    def timer(self) -> int:
+        return self._det._timer
+
+    @property
+    def length(self) -> int:
+        return min(self.n, self._det._timer)
+
+    @property
+    def snr(self) -> float:
+        return self._det._snr
+
+    def _stack(self, which: int):
+        eng = self._det._eng
+        out = np.empty((eng.H, eng.W), np.uint32 if which == 2 else np.uint8)
+        args = [None, None, None]
+        args[which] = _ptr(out)
+        check(eng.lib.mdb_get_stack(eng.handle, *args), "SNR_SW")
+        return out
+
+    @property
+    def max(self):
+        return self._stack(0)
+
+    @property
+    def mean(self):
+        return self._stack(1)
+
+    @property
+    def sum(self):
+        return self._stack(2)
+
+
+class BaseDetector(metaclass=ABCMeta):
+    """BaseDetector (MetLib/Detector.py:130-157)."""
+
+    @abstractmethod
+    def __init__(self, *args: Any) -> None:
+        pass
+
+    @abstractmethod
+    def update(self, new_frame: np.ndarray) -> None:
+        pass
+
+    @abstractmethod
+    def detect(self):
+        pass
+
+    def visu(self) -> list:
+        return []
+
+
+class LineDetector(BaseDetector):
+    """LineDetector (MetLib/Detector.py:160-242): window, adaptive threshold policy, dynamic mask.
+
+    Extra keyword arguments (not in the reference): `device` (CUDA ordinal), `max_batch` (capacity of
+    `detect_many`), `apply_mask` (multiply frames by `mask` on the device, i.e. do the loader's
+    Transform.mask_with, MetLib/imgproc.py:96-101, inside the library)."""
+    abs_sensitivity = {"high": 3, "normal": 5, "low": 7}
+
+    def __init__(self, window_sec: float, fps: float, mask: np.ndarray, num_cls: int,
+                 cfg: BinaryCfg, logger: Any = None, *, device: int = 0, max_batch: int = 1,
+                 apply_mask: bool = False):
+        self.mask = mask
+        self.num_cls = num_cls
+        self.logger = logger
+        self.mask_area = np.sum(self.mask)
+        self.bi_cfg = cfg.binary
+        self.hough_cfg = cfg.hough_line
+        self.dynamic_cfg = cfg.dynamic
+        self.stack_maxsize = int(window_sec * fps)
+        if self.bi_cfg.adaptive_bi_thre:
+            self.bi_threshold = self.abs_sensitivity[self.bi_cfg.sensitivity]
+        else:
+            self.bi_threshold = self.bi_cfg.init_value
+        self.bi_threshold_float = self.bi_threshold
+        self.max_allow_gap = 0.05
+        self._roi = select_subarea(np.asarray(mask), self.bi_cfg.area)
+        self._eng = _Engine(mask, self.stack_maxsize, adaptive=self.bi_cfg.adaptive_bi_thre,
+                            init_value=self.bi_cfg.init_value, sensitivity=self.bi_cfg.sensitivity,
+                            interval=self.bi_cfg.interval, roi=self._roi,
+                            hough=(self.hough_cfg.threshold, self.hough_cfg.min_len,
+                                   self.hough_cfg.max_gap),
+                            dy_mask=self.dynamic_cfg.dy_mask, max_batch=max_batch, device=device,
+                            apply_mask=apply_mask)
+        self._timer = 0
+        self._snr = 0
+        self.stack = SNR_SW(self)
+
+    def detect(self):
+        return [], []
+
+    def update(self, new_frame: np.ndarray) -> None:
+        f = self._eng.check_frame(new_frame)
+        check(self._eng.lib.mdb_update(self._eng.handle, _ptr(f), 0), "update")
+        self._timer += 1
+
+    def visu(self):
+        return super().visu()
+
+    def close(self):
+        self._eng.close()
+
+
+class M3Detector(LineDetector):
+    """M3Detector (MetLib/Detector.py:302-448): max-minus-mean over the window, median, threshold,
+    close, dynamic mask, probabilistic Hough, NMS.  `update`/`detect` are the reference's per-frame
+    calls; `detect_many` is the batched form (T x {update; detect}) that the throughput path uses."""
+
+    def __init__(self, window_sec: float, fps: float, mask: np.ndarray, num_cls: int,
+                 cfg: BinaryCfg, logger: Any = None, **kw):
+        super().__init__(window_sec, fps, mask, num_cls, cfg, logger, **kw)
+        self.lines_num = 0
+        self.filtered_line_num = 0
+        self.dst_sum = 0.0
+        self.linesp_ext = np.array([])
+        self._dst_cache = None
+
+    # -- reference per-frame API ---------------------------------------------------------------
+    def detect(self):
+        eng = self._eng
+        check(eng.lib.mdb_detect(eng.handle, C.byref(eng.infos[0]), _ptr(eng.lines), _ptr(eng.prob),
+                                 _ptr(eng.raw)), "detect")
+        self._dst_cache = None
+        return self._unpack(0)
+
+    def _unpack(self, i: int):
+        eng = self._eng
+        fi = eng.infos[i]
+        self.bi_threshold = fi.bi_threshold
+        self.bi_threshold_float = fi.bi_threshold_float
+        self._snr = fi.snr
+        self.dst_sum = fi.dst_sum
+        self.gap = fi.gap
+        self.lines_num = fi.lines_num
+        self.filtered_line_num = fi.n_lines
+        self.n_on = fi.n_on
+        self.linesp_ext = eng.raw[i, :fi.n_raw].copy() if fi.n_raw else np.array([])
+        k = fi.n_lines
+        if k > 0:
+            lines = eng.lines[i, :k].copy()
+            p = eng.prob[i, :k]
+            cls_pred = np.zeros((k, self.num_cls))
+            cls_pred[:, -1] = p
+            cls_pred[:, 0] = 1 - p
+        else:
+            lines = np.array([])
+            cls_pred = np.zeros((0, self.num_cls))
+        return lines, cls_pred
+
+    @property
+    def dst(self) -> np.ndarray:
+        """Binary mask of the most recent detect (Detector.py:371), fetched on demand."""
+        if self._dst_cache is None:
+            eng = self._eng
+            out = np.empty((eng.H, eng.W), np.uint8)
+            check(eng.lib.mdb_get_dst(eng.handle, _ptr(out), 0), "dst")
+            self._dst_cache = out
+        return self._dst_cache
+
+    # -- batched API ---------------------------------------------------------------------------
+    def detect_many(self, frames, *, on_device: bool = False, return_dst: bool = False,
+                    dst_out: Optional[np.ndarray] = None):
+        """Equivalent to `[ (self.update(f), self.detect())[1] for f in frames ]` in ONE library call.
+
+        frames: (T,H,W) uint8 numpy array (host), or -- with on_device=True -- an int device pointer
+        wrapped as (ptr, T).  Returns a list of (lines, cls_pred) per frame; per-frame scalars are in
+        `self.last_infos`.  With return_dst the masks come back as a (T,H,W) array as third item."""
+        eng = self._eng
+        if on_device:
+            ptr, T = frames
+        else:
+            frames = eng.check_frame(np.asarray(frames))
+            if frames.ndim != 3:
+                raise ValueError("frames must be (T, H, W)")
+            T, ptr = len(frames), frames.ctypes.data
+        if T == 0:
+            return []
+        if T > eng.max_batch:
+            raise ValueError(f"T={T} exceeds max_batch={eng.max_batch} given at construction")
+        dst = None
+        if return_dst and dst_out is None:
+            dst_out = np.empty((T, eng.H, eng.W), np.uint8)
+        if dst_out is not None:
+            dst = dst_out.ctypes.data
+        check(eng.lib.mdb_detect_batch(eng.handle, ptr, T, int(on_device), C.byref(eng.infos),
+                                       _ptr(eng.lines), _ptr(eng.prob), _ptr(eng.raw), dst, 0),
+              "detect_many")
+        self._timer += T
+        self._dst_cache = None
+        self.last_infos = [dict(timer=fi.timer, bi_threshold=fi.bi_threshold, n_on=fi.n_on,
+                                bi_threshold_float=fi.bi_threshold_float, snr=fi.snr,
+                                dst_sum=fi.dst_sum, gap=fi.gap, lines_num=fi.lines_num,
+                                n_raw=fi.n_raw, n_lines=fi.n_lines) for fi in eng.infos[:T]]
+        self.last_raw = [eng.raw[i, :eng.infos[i].n_raw].copy() for i in range(T)]
+        res = [self._unpack(i) for i in range(T)]
+        if dst_out is not None:
+            return res, dst_out
+        return res
+
+    def submit(self, ptr: int, T: int, on_device: bool):
+        """Asynchronous half of detect_many (mdb_submit_batch)."""
+        check(self._eng.lib.mdb_submit_batch(self._eng.handle, ptr, T, int(on_device)), "submit")
+        self._timer += T
+        self._pending = T
+
+    def collect(self, want_lines: bool = True):
+        """Waits for the submitted batch (mdb_collect_batch); returns list of (lines, cls_pred)."""
+        eng = self._eng
+        T = self._pending
+        check(eng.lib.mdb_collect_batch(eng.handle, C.byref(eng.infos), _ptr(eng.lines), _ptr(eng.prob),
+                                        _ptr(eng.raw), None, 0), "collect")
+        self._dst_cache = None
+        if not want_lines:
+            self._unpack(T - 1)
+            return None
+        return [self._unpack(i) for i in range(T)]
+
+    def visu(self):
+        """Reference visu() (Detector.py:394-448) needs MetLib.metvisu; without it: no overlays."""
+        try:
+            from MetLib.metvisu import (DrawRectVisu, ImgVisuAttrs, SquareColorPair,  # type: ignore
+                                        TextColorPair, TextVisu)
+        except Exception:
+            return []
+        x1, y1, x2, y2 = self.stack.std_roi
+        return [
+            ImgVisuAttrs("mix_bg", img=self.dst // 255, weight=0.5, color="yellow"),
+            TextVisu("std_value", position="left-top", color="green",
+                     text_list=[TextColorPair(text=f"STD:{self.stack.snr:.4f}")]),
+            TextVisu("bi_value", position="left-top", color="green", text_list=[TextColorPair(
+                text=f"Bi_Threshold: {self.bi_threshold} (rounded from {self.bi_threshold_float:.4f})")]),
+            TextVisu("lines_num", position="left-top", color="green", text_list=[TextColorPair(
+                text=f"Line num: {self.lines_num} (filtered: {self.filtered_line_num})")]),
+            TextVisu("area_ratio", position="left-top", color="green",
+                     text_list=[TextColorPair(text=f"Diff Area: {self.dst_sum:.2f}%")]),
+            TextVisu("lines_warning", position="left-top", color="red", text_list=[TextColorPair(
+                text="WARNING: TOO MANY LINES!" if self.lines_num > 10 else "")]),
+            DrawRectVisu("std_roi_area", pair_list=[SquareColorPair(dot_pair=([y1, x1], [y2, x2]))],
+                         color="purple"),
+        ]

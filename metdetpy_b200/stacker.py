@@ -1,0 +1,88 @@
+"""Clip-level max stacking on the GPU: `MaxImgContainer`, `max_stacker` (MetLib/stacker.py:43-49,
+:146-175, :197-213) and `MergeFunction.max` (MetLib/utils.py:203-204). Same names and call
+signatures; frames of any channel layout (the reference stacks full-resolution colour frames)."""
+from __future__ import annotations
+
+from typing import Any, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+def merge_max(image_stack: Sequence[np.ndarray], device: int = 0) -> np.ndarray:
+    """MergeFunction.max: element-wise max over a list/array of equally shaped uint8 frames."""
+    arr = np.ascontiguousarray(np.asarray(image_stack), np.uint8)
+    if arr.ndim < 2 or len(arr) == 0:
+        raise ValueError("need a non-empty stack of frames")
+    out = np.empty(arr.shape[1:], np.uint8)
+    check(_lib.load().mdb_max_stack(arr.ctypes.data, len(arr), out.nbytes, out.ctypes.data, 0, 0, device),
+          "merge_max")
+    return out
+
+
+class MaxImgContainer:
+    """Running max of appended frames (MetLib/stacker.py:43-49). Frames are buffered and reduced on
+    the device in chunks; `container` / `export()` give the current result."""
+
+    def __init__(self, chunk: int = 32, device: int = 0):
+        self._buf: list[np.ndarray] = []
+        self._acc: Optional[np.ndarray] = None
+        self._chunk = chunk
+        self._device = device
+
+    def append(self, new_frame: np.ndarray) -> None:
+        if self._acc is not None and new_frame.shape != self._acc.shape:
+            raise ValueError(f"Expect new frame has the same shape as the base frame "
+                             f"{self._acc.shape}, got {new_frame.shape}.")
+        if self._buf and new_frame.shape != self._buf[0].shape:
+            raise ValueError(f"Expect new frame has the same shape as the base frame "
+                             f"{self._buf[0].shape}, got {new_frame.shape}.")
+        self._buf.append(np.ascontiguousarray(new_frame, np.uint8))
+        if len(self._buf) >= self._chunk:
+            self._flush()
+
+    def _flush(self):
+        if not self._buf:
+            return
+        frames = self._buf if self._acc is None else [self._acc] + self._buf
+        self._acc = merge_max(frames, self._device)
+        self._buf = []
+
+    @property
+    def container(self) -> Optional[np.ndarray]:
+        self._flush()
+        return self._acc
+
+    def export(self):
+        return self.container
+
+
+def max_stacker(video_loader: Any, start_frame: Optional[int] = None, end_frame: Optional[int] = None,
+                logger: Any = None) -> Optional[np.ndarray]:
+    """max_stacker (MetLib/stacker.py:197-213) via _batch_stacker's loader protocol (:146-175):
+    reset(start,end) / start() / iterations / pop() / stop(). Returns None when no frame came."""
+    box = MaxImgContainer()
+    try:
+        if start_frame is not None or end_frame is not None:
+            video_loader.reset(start_frame=start_frame, end_frame=end_frame)
+        base_shape = None
+        video_loader.start()
+        for _ in range(video_loader.iterations):
+            img = video_loader.pop()
+            if img is None:
+                break
+            if base_shape is None:
+                base_shape = img.shape
+            elif base_shape != img.shape:
+                raise ValueError(f"Expect new frame has the same shape as the base frame "
+                                 f"{base_shape}, got {img.shape}.")
+            box.append(img)
+    except Exception as e:  # the reference logs and returns what it has (stacker.py:169-171)
+        if logger is not None:
+            logger.error(e.__repr__())
+        return box.container
+    finally:
+        video_loader.stop()
+    return box.container

@@ -4,7 +4,7 @@ This is the generator specified in SURVEY.md Appendix E / §8(d): static sky at 
 blurred stars, per-frame Gaussian sensor noise (sigma = 2 grey levels) and one anti-aliased streak
 ("meteor") every 2 s lasting 0.5 s.  The reference's behaviour on it is documented there (threshold
 settles at 8, sparse masks, one NMS line per meteor frame).  Host-side numpy/cv2 only; the frames
-are uploaded to the GPU path and fed to the CPU oracle unchanged so both see identical bytes.
+are uploaded to the GPU path and fed to the CPU checker unchanged so both see identical bytes.
 
 `speed_scale` / `thickness` exist so that small test-sized streams still contain streaks long
 enough for HoughLinesP(minLineLength=10); the defaults reproduce Appendix E exactly.
