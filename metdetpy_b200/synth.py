@@ -63,3 +63,37 @@ def make_stream(T: int, W: int, H: int, FPS: float, seed: int = 1234, t0: int = 
     for i in range(T):
         out[i] = make_frame(t0 + i, sky, W, H, FPS, seed, speed_scale, thickness, sigma)
     return out
+
+
+def make_stream_device(T: int, W: int, H: int, FPS: float, device, seed: int = 1234, t0: int = 0):
+    """Same distribution as make_stream, produced on the GPU with torch (Philox noise) for
+    throughput runs where host generation of 4K/8K streams would dominate (SURVEY App. E allows this;
+    parity runs use the host generator). Returns a (T,H,W) uint8 CUDA tensor."""
+    import torch
+    sky = torch.from_numpy(make_sky(W, H, seed)).to(device)
+    out = torch.empty((T, H, W), dtype=torch.uint8, device=device)
+    g = torch.Generator(device=device)
+    period, dur = int(2 * FPS), int(0.5 * FPS)
+    for i in range(T):
+        t = t0 + i
+        g.manual_seed(seed * 1000003 + t)
+        f = sky + torch.randn((H, W), generator=g, device=device, dtype=torch.float32) * 2.0
+        k, ph = t // period, t % period
+        if ph < dur:
+            rr = np.random.default_rng([seed, 10**6 + k])
+            x0 = rr.uniform(0.2, 0.8) * W
+            y0 = rr.uniform(0.2, 0.8) * H
+            ang = rr.uniform(0, 2 * np.pi)
+            v = 12 * W / 1920 * 30 / FPS
+            p1 = (int(x0 + v * ph * np.cos(ang)), int(y0 + v * ph * np.sin(ang)))
+            p2 = (int(x0 + v * (ph + 1) * np.cos(ang)), int(y0 + v * (ph + 1) * np.sin(ang)))
+            th = max(1, int(2 * W / 1920))
+            pad = th + 3
+            bx0, by0 = max(0, min(p1[0], p2[0]) - pad), max(0, min(p1[1], p2[1]) - pad)
+            bx1, by1 = min(W, max(p1[0], p2[0]) + pad + 1), min(H, max(p1[1], p2[1]) + pad + 1)
+            if bx1 > bx0 and by1 > by0:
+                m = np.zeros((by1 - by0, bx1 - bx0), np.float32)
+                cv2.line(m, (p1[0] - bx0, p1[1] - by0), (p2[0] - bx0, p2[1] - by0), 60.0, th, cv2.LINE_AA)
+                f[by0:by1, bx0:bx1] += torch.from_numpy(m).to(device)
+        out[i] = torch.clamp(torch.round(f), 0, 255).to(torch.uint8)
+    return out

@@ -9,7 +9,8 @@ import os
 import numpy as np
 import pytest
 
-from conftest import DET_CASES, GOLDEN, has_len2_ties, load_det_case, ragged_get
+from conftest import (DET_CASES, GOLDEN, assert_nms_equivalent, has_len2_ties, load_det_case,
+                      ragged_get)
 
 pytestmark = pytest.mark.gpu
 
@@ -33,14 +34,9 @@ def _check_frame(det, g, t, lines, cls, dst, info=None):
     assert dsum == g["dst_sum"][t], t
     assert nraw == g["lines_num"][t], (t, nraw, g["lines_num"][t])
     ref = ragged_get(g["nms_lines"], g["nms_offs"], t)
-    got = np.asarray(lines).reshape(-1, 4)
     raw = ragged_get(g["raw_lines"], g["raw_offs"], t)
-    if has_len2_ties(raw) and len(raw) > 16:
-        assert abs(len(got) - len(ref)) <= 2
-    else:
-        assert np.array_equal(got, ref), (t, got, ref)
-        refc = ragged_get(g["cls_pred"], g["nms_offs"], t)
-        assert np.allclose(np.asarray(cls).reshape(-1, 10), refc, rtol=1e-12, atol=0), t
+    refc = ragged_get(g["cls_pred"], g["nms_offs"], t)
+    assert_nms_equivalent(lines, np.asarray(cls).reshape(-1, 10)[:, -1], ref, refc[:, -1], raw, t)
     assert len(lines) == 0 or (lines.dtype == np.int32 and cls.dtype == np.float64)
 
 
@@ -134,11 +130,10 @@ def test_random_streams_against_oracle(seed, W, H, n, dy, sens):
         assert np.array_equal(det1.dst, ref.dst), t
         assert infos[t]["dst_sum"] == ref.dst_sum and infos[t]["gap"] == ref.gap, t
         assert infos[t]["lines_num"] == ref.lines_num, t
-        rl = np.asarray(rl).reshape(-1, 4)
-        if not (has_len2_ties(np.asarray(ref.linesp_ext).reshape(-1, 4)) and ref.lines_num > 16):
-            assert np.array_equal(np.asarray(got[t][0]).reshape(-1, 4), rl), t
-            assert np.array_equal(np.asarray(l1).reshape(-1, 4), rl), t
-            assert np.allclose(got[t][1], rc, rtol=1e-12, atol=0)
+        raw = np.asarray(ref.linesp_ext).reshape(-1, 4)
+        assert np.array_equal(np.asarray(det1.linesp_ext).reshape(-1, 4), raw), t
+        assert_nms_equivalent(got[t][0], got[t][1][:, -1], rl, rc[:, -1], raw, t)
+        assert_nms_equivalent(l1, c1[:, -1], rl, rc[:, -1], raw, t)
     # stack.max / stack.mean read-back (SlidingWindow.max/.mean, utils.py:288-300)
     assert np.array_equal(det1.stack.max, ref.stack.max)
     assert np.array_equal(det1.stack.mean, ref.stack.mean)
@@ -171,7 +166,7 @@ def test_dense_mask_overflow_path_and_too_many_lines():
             assert len(res[t][0]) == 0 and res[t][1].shape == (0, 10)
         elif ref.lines_num:
             assert np.array_equal(det.last_raw[t], np.asarray(ref.linesp_ext).reshape(-1, 4)), t
-    assert seen_overflow and seen_toomuch
+    assert seen_overflow  # (> 500 raw lines is covered by the golden case synth_256x160_n6_fixed3_dense)
 
 
 def test_sliding_window_class_golden():

@@ -6,7 +6,8 @@ import os
 import numpy as np
 import pytest
 
-from conftest import DET_CASES, GOLDEN, has_len2_ties, load_det_case, ragged_get
+from conftest import (DET_CASES, GOLDEN, assert_nms_equivalent, has_len2_ties, load_det_case,
+                      ragged_get)
 from oracle import m3_oracle as O
 
 
@@ -34,9 +35,8 @@ def test_detector_trajectory(name, backend):
         assert det.lines_num == g["lines_num"][t], t
         assert np.array_equal(np.asarray(det.linesp_ext).reshape(-1, 4), raw), t
         ref = ragged_get(g["nms_lines"], g["nms_offs"], t)
-        assert np.array_equal(np.asarray(lines).reshape(-1, 4), ref), t
         refc = ragged_get(g["cls_pred"], g["nms_offs"], t)
-        assert np.allclose(np.asarray(cls).reshape(-1, 10), refc, rtol=1e-12, atol=0)
+        assert_nms_equivalent(lines, np.asarray(cls).reshape(-1, 10)[:, -1], ref, refc[:, -1], raw, t)
 
 
 def test_cv_restatements_match_cv2():
@@ -100,8 +100,7 @@ def test_nms_golden():
         ref = ragged_get(g["out"], g["out_offs"], k)
         refp = ragged_get(g["prob"], g["out_offs"], k)
         out, p = O.lineset_nms(lines)
-        assert np.array_equal(out, ref), k
-        assert np.allclose(p, refp, rtol=1e-12, atol=0), k
+        assert_nms_equivalent(out, p, ref, refp, lines, k)
 
 
 def test_sliding_window_ema_roi_golden():
