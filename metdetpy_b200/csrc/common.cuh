@@ -6,7 +6,7 @@
 #include "../../include/metdet_b200.h"
 
 #define MDB_HOUGH_ANGLES 180
-#define MDB_POINT_CAP 8192  // per-frame point-list capacity of the shared-memory PPHT path
+#define MDB_POINT_CAP 4096  // per-frame point-list capacity of the shared-memory PPHT path
 
 // Where frame `t` (0-based global frame index) lives: slot t % R of the device frame ring.
 struct FrameSrc {

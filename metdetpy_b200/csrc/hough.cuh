@@ -4,17 +4,29 @@
 // MWC RNG seeded per call), its float32 rho rounding and its in-loop un-voting, so the emitted
 // segments are identical.
 //
-// Layout: every CTA ("slot") owns one int32 accumulator [180][numrho] and one H*W-bit mask in
-// global memory (L2-resident in practice: only cells of actual points are ever touched, and they
-// are reset by replaying the point list -- the arrays are never memset per frame).
-// Thread n < 180 owns accumulator row n, so votes need no atomics; the arg-max over angles is a
-// warp REDUX + one shared-memory hop.
+// Batch path (hough_batch_kernel, frames with <= MDB_POINT_CAP on-pixels):
+//   * the frame's on-pixels are sorted in shared memory (row-major == cv2's nzloc order); the image
+//     mask itself is never touched again: "is pixel q still on" = binary search in the sorted keys
+//     + a removed-bit per point, all in shared memory;
+//   * thread n < 180 owns accumulator row n of this CTA's slot ([180][numrho] int32 in global
+//     memory), so votes need no atomics; the cells of the points that will be visited next are
+//     prefetched into L2 a few visits ahead (the visiting order is known up front);
+//   * arg-max over angles = warp REDUX + one shared-memory hop (double-buffered, one barrier);
+//   * line walks are evaluated 256 steps at a time by the whole CTA (warp ballots), un-voting is a
+//     fire-and-forget RED per (pixel, angle);
+//   * accumulators are never memset: every cell a point of the frame can touch is zeroed by
+//     replaying the point list at the end.
+// Overflow path (hough_global_kernel): same algorithm, sequential walks, point list / visit order /
+// pixel bitmap in global memory -- for dense masks beyond the shared-memory capacity.
 #pragma once
+#include <limits.h>
+
 #include "common.cuh"
 
 __constant__ float c_trig[2 * MDB_HOUGH_ANGLES];  // (float)cos(n*theta), (float)sin(n*theta); host-computed
 
 #define HOUGH_THREADS 256
+#define HOUGH_PREFETCH 6  // visits of look-ahead for the accumulator-cell L2 prefetch
 
 __device__ __forceinline__ int rho_of(int x, int y, int n) {
     // plain float32 multiply/add, no FMA contraction (matches the compiled OpenCV loop)
@@ -37,19 +49,238 @@ __device__ __forceinline__ void bitonic_sort_u32(uint32_t *a, int npow2, int tid
         }
 }
 
-// Process one frame's point list. keys: N sorted (row-major) point keys (y<<16|x); idx: N u32
-// scratch. Both may live in shared or global memory.
-__device__ void ppht_frame(const HoughParams &P, uint32_t *keys, uint32_t *idx, int N, int line_gap,
-                           int32_t *accum, uint32_t *bitmap, uint32_t *walk, int32_t *lines_out,
-                           int *nlines_out) {
+__device__ __forceinline__ int line_gap_of(const HoughParams &P, unsigned n_on) {
+    // Detector.py:342-344: dst_sum = count / mask_area * 100; gap = max(0, 1 - dst_sum/0.05) * max_gap
+    const double dst_sum = __dmul_rn(__ddiv_rn((double)n_on, P.mask_area), 100.0);
+    double g = __dsub_rn(1.0, __ddiv_rn(dst_sum, 0.05));
+    if (!(g > 0.0)) g = 0.0;
+    g = __dmul_rn(g, (double)P.max_gap);
+    return (int)rint(g);  // cvRound(maxLineGap)
+}
+
+// walk geometry of OpenCV's 16.16 fixed-point line tracer
+struct Walk {
+    int x0, y0, dx0, dy0;
+    bool xflag;
+    __device__ __forceinline__ void init(int x, int y, int max_n) {
+        const float a = -c_trig[2 * max_n + 1], b = c_trig[2 * max_n];
+        x0 = x; y0 = y;
+        if (fabsf(a) > fabsf(b)) {
+            xflag = true;
+            dx0 = a > 0 ? 1 : -1;
+            dy0 = __float2int_rn(__fdiv_rn(__fmul_rn(b, 65536.0f), fabsf(a)));
+            y0 = (y0 << 16) + 32768;
+        } else {
+            xflag = false;
+            dy0 = b > 0 ? 1 : -1;
+            dx0 = __float2int_rn(__fdiv_rn(__fmul_rn(a, 65536.0f), fabsf(b)));
+            x0 = (x0 << 16) + 32768;
+        }
+    }
+    // pixel of step i in direction k
+    __device__ __forceinline__ void at(int k, int i, int &j1, int &i1) const {
+        const int xx = x0 + (k ? -dx0 : dx0) * i, yy = y0 + (k ? -dy0 : dy0) * i;
+        j1 = xflag ? xx : xx >> 16;
+        i1 = xflag ? yy >> 16 : yy;
+    }
+};
+
+// index of key in sorted keys[0..N) or -1
+__device__ __forceinline__ int find_key(const uint32_t *keys, int N, uint32_t key) {
+    int lo = 0, hi = N;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return (lo < N && keys[lo] == key) ? lo : -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Batch path
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HOUGH_THREADS)
+hough_batch_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
+                   const uint32_t *__restrict__ points, int32_t *accum_slots, int32_t *lines_out,
+                   int *nlines_out) {
+    extern __shared__ uint32_t h_sm[];
+    uint32_t *keys = h_sm;                                            // [cap]
+    uint16_t *idx = reinterpret_cast<uint16_t *>(keys + P.cap);       // [cap] visiting order
+    uint16_t *wl = idx + P.cap;                                       // [cap] pixels of the current line
+    uint32_t *rm = reinterpret_cast<uint32_t *>(wl + P.cap);          // [cap/32] removed bits
+    __shared__ int s_red[2][HOUGH_THREADS / 32];
+    __shared__ unsigned s_on[HOUGH_THREADS / 32], s_inb[HOUGH_THREADS / 32];
+    __shared__ int s_ctl[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = P.W, H = P.H, numrho = P.numrho, half = (numrho - 1) / 2;
+    int32_t *accum = accum_slots + (size_t)blockIdx.x * MDB_HOUGH_ANGLES * numrho;
+    int32_t *myrow = accum + (size_t)(tid < MDB_HOUGH_ANGLES ? tid : 0) * numrho + half;
+
+    for (int t = blockIdx.x; t < T; t += gridDim.x) {
+        const unsigned Nu = npoints[t];
+        if (Nu == 0) { if (tid == 0) nlines_out[t] = 0; continue; }
+        if (Nu > (unsigned)P.cap) { if (tid == 0) nlines_out[t] = -1; continue; }  // overflow path
+        const int N = (int)Nu;
+        const int line_gap = line_gap_of(P, Nu);
+        int32_t *lines = lines_out + (size_t)t * P.max_lines * 4;
+        int np2 = 1;
+        while (np2 < N) np2 <<= 1;
+        for (int i = tid; i < np2; i += HOUGH_THREADS)
+            keys[i] = i < N ? points[(size_t)t * P.cap + i] : 0xFFFFFFFFu;
+        for (int i = tid; i < (N + 31) / 32; i += HOUGH_THREADS) rm[i] = 0;
+        for (int i = tid; i < N; i += HOUGH_THREADS) idx[i] = (uint16_t)i;
+        __syncthreads();
+        bitonic_sort_u32(keys, np2, tid, HOUGH_THREADS);
+        // visiting order: OpenCV draws idx = rng % count and swap-removes; an in-place Fisher-Yates
+        // over an index array leaves the visit sequence in idx[N-1], idx[N-2], ..., idx[0].
+        if (tid == 0) {
+            unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
+            for (int count = N; count > 0; count--) {
+                state = (unsigned long long)(unsigned)state * 4164903690ull + (unsigned)(state >> 32);
+                const unsigned r = (unsigned)state % (unsigned)count;
+                const uint16_t a = idx[r], b = idx[count - 1];
+                idx[r] = b;
+                idx[count - 1] = a;
+            }
+            s_ctl[2] = 0;  // lines found
+        }
+        __syncthreads();
+        // warm the first visits' cells
+        if (tid < MDB_HOUGH_ANGLES)
+            for (int s = N - 1; s >= 0 && s >= N - HOUGH_PREFETCH; s--) {
+                const uint32_t k = keys[idx[s]];
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(myrow + rho_of(k & 0xffffu, k >> 16, tid)));
+            }
+        int par = 0;
+        for (int s = N - 1; s >= 0; s--) {
+            const int pi = idx[s];
+            if (tid < MDB_HOUGH_ANGLES && s >= HOUGH_PREFETCH) {
+                const uint32_t k = keys[idx[s - HOUGH_PREFETCH]];
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(myrow + rho_of(k & 0xffffu, k >> 16, tid)));
+            }
+            if ((rm[pi >> 5] >> (pi & 31)) & 1u) continue;  // removed by an earlier line (uniform)
+            const uint32_t key = keys[pi];
+            const int x = key & 0xffffu, y = key >> 16;
+            int best = INT_MIN;
+            if (tid < MDB_HOUGH_ANGLES) {
+                const int r = rho_of(x, y, tid);
+                const int v = __ldcg(myrow + r) + 1;  // L2 only: cells are also updated by REDs
+                __stcg(myrow + r, v);
+                best = v * 256 + (255 - tid);  // max value first, lowest angle on ties
+            }
+            best = __reduce_max_sync(0xffffffffu, best);
+            if (lane == 0) s_red[par][warp] = best;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < HOUGH_THREADS / 32; k++) best = max(best, s_red[par][k]);
+            par ^= 1;
+            if ((best >> 8) < P.threshold) continue;
+            const int max_n = 255 - (best & 255);
+
+            // ---- line: find both ends (mask unchanged meanwhile), 256 steps per round ----------
+            Walk wk;
+            wk.init(x, y, max_n);
+            int ends[2];  // step index of the last on-pixel per direction
+            for (int k = 0; k < 2; k++) {
+                int last_on = 0;  // step 0 is the start pixel, which is on
+                bool done = false;
+                for (int base = 0; !done; base += HOUGH_THREADS) {
+                    const int i = base + tid;
+                    int j1, i1;
+                    wk.at(k, i, j1, i1);
+                    const bool inb = j1 >= 0 && j1 < W && i1 >= 0 && i1 < H;
+                    bool on = false;
+                    if (inb) {
+                        const int f = find_key(keys, N, ((unsigned)i1 << 16) | (unsigned)j1);
+                        on = f >= 0 && !((rm[f >> 5] >> (f & 31)) & 1u);
+                    }
+                    const unsigned bo = __ballot_sync(0xffffffffu, on), bi = __ballot_sync(0xffffffffu, inb);
+                    if (lane == 0) { s_on[warp] = bo; s_inb[warp] = bi; }
+                    __syncthreads();
+                    // every thread scans the 8 ballot words identically (uniform, no divergence)
+                    for (int w = 0; w < HOUGH_THREADS / 32 && !done; w++) {
+                        unsigned onw = s_on[w];
+                        const unsigned inw = s_inb[w];
+                        const int wbase = base + w * 32;
+                        // first out-of-bounds step in this word (bounds are monotone along the walk)
+                        const int ob = inw == 0xffffffffu ? INT_MAX : wbase + __ffs(~inw) - 1;
+                        while (onw) {
+                            const int io = wbase + __ffs(onw) - 1;
+                            onw &= onw - 1;
+                            if (io - last_on - 1 > line_gap) { done = true; break; }
+                            last_on = io;
+                        }
+                        if (!done) {
+                            const int wend = min(wbase + 31, ob == INT_MAX ? INT_MAX : ob - 1);  // last in-bounds step seen
+                            if (ob != INT_MAX || wend - last_on > line_gap) done = true;
+                        }
+                    }
+                    __syncthreads();
+                }
+                ends[k] = last_on;
+            }
+            int ex0, ey0, ex1, ey1;
+            wk.at(0, ends[0], ex0, ey0);
+            wk.at(1, ends[1], ex1, ey1);
+            const bool good = abs(ex1 - ex0) >= P.min_len || abs(ey1 - ey0) >= P.min_len;
+            // ---- second pass: clear the on-pixels up to both ends; un-vote them if the line counts
+            if (tid == 0) s_ctl[1] = 0;
+            __syncthreads();
+            for (int k = 0; k < 2; k++)
+                for (int i = tid + k; i <= ends[k]; i += HOUGH_THREADS) {  // k=1 skips the shared start pixel
+                    int j1, i1;
+                    wk.at(k, i, j1, i1);
+                    const int f = find_key(keys, N, ((unsigned)i1 << 16) | (unsigned)j1);
+                    if (f >= 0 && !((rm[f >> 5] >> (f & 31)) & 1u)) {
+                        atomicOr(&rm[f >> 5], 1u << (f & 31));
+                        if (good) wl[atomicAdd(&s_ctl[1], 1)] = (uint16_t)f;
+                    }
+                }
+            __syncthreads();
+            if (good) {
+                const int nw = s_ctl[1];
+                if (tid < MDB_HOUGH_ANGLES)
+                    for (int q = 0; q < nw; q++) {
+                        const uint32_t k2 = keys[wl[q]];
+                        atomicAdd(myrow + rho_of(k2 & 0xffffu, k2 >> 16, tid), -1);  // RED, no return
+                    }
+                if (tid == 0) {
+                    const int li = s_ctl[2];
+                    if (li < P.max_lines) {
+                        lines[4 * li] = ex0; lines[4 * li + 1] = ey0;
+                        lines[4 * li + 2] = ex1; lines[4 * li + 3] = ey1;
+                    }
+                    s_ctl[2] = li + 1;
+                }
+            }
+            __syncthreads();
+        }
+        // reset: zero every accumulator cell a point of this frame can have touched
+        for (int q = tid; q < N * MDB_HOUGH_ANGLES; q += HOUGH_THREADS) {
+            const int i = q / MDB_HOUGH_ANGLES, n = q % MDB_HOUGH_ANGLES;
+            const uint32_t k = keys[i];
+            accum[(size_t)n * numrho + half + rho_of(k & 0xffffu, k >> 16, n)] = 0;
+        }
+        __syncthreads();
+        if (tid == 0) nlines_out[t] = s_ctl[2];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Overflow path: one frame, keys already sorted in global memory (compact_ordered_kernel),
+// pixel bitmap in global memory, sequential walks.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HOUGH_THREADS)
+hough_global_kernel(HoughParams P, const unsigned *n_ptr, uint32_t *keys, uint32_t *idx, int32_t *accum,
+                    uint32_t *bitmap, uint32_t *walk, int32_t *lines_out, int *nlines_out) {
     __shared__ int s_red[HOUGH_THREADS / 32];
-    __shared__ int s_ctl[8];  // [0]=good, [1]=#walk pixels, [2]=found lines
+    __shared__ int s_ctl[8];
+    const int N = (int)*n_ptr;
     const int tid = threadIdx.x;
+    if (N == 0) { if (tid == 0) *nlines_out = 0; return; }
+    const int line_gap = line_gap_of(P, (unsigned)N);
     const int W = P.W, H = P.H, numrho = P.numrho, half = (numrho - 1) / 2;
     volatile uint32_t *vbitmap = bitmap;
-
-    // visiting order: OpenCV draws idx = rng % count and swap-removes; an in-place Fisher-Yates
-    // over an index array leaves the visit sequence in idx[N-1], idx[N-2], ..., idx[0].
     for (int i = tid; i < N; i += HOUGH_THREADS) {
         idx[i] = i;
         const uint32_t k = keys[i];
@@ -69,19 +300,18 @@ __device__ void ppht_frame(const HoughParams &P, uint32_t *keys, uint32_t *idx, 
         }
     }
     __syncthreads();
-
     int32_t *myrow = accum + (size_t)(tid < MDB_HOUGH_ANGLES ? tid : 0) * numrho + half;
     for (int s = N - 1; s >= 0; s--) {
         const uint32_t key = keys[idx[s]];
         const int x = key & 0xffffu, y = key >> 16;
         const size_t p = (size_t)y * W + x;
-        if (!((vbitmap[p >> 5] >> (p & 31)) & 1u)) continue;  // removed by an earlier line (uniform)
+        if (!((vbitmap[p >> 5] >> (p & 31)) & 1u)) continue;
         int best = INT_MIN;
         if (tid < MDB_HOUGH_ANGLES) {
             const int r = rho_of(x, y, tid);
             const int v = myrow[r] + 1;
             myrow[r] = v;
-            best = v * 256 + (255 - tid);  // max value first, lowest angle on ties
+            best = v * 256 + (255 - tid);
         }
         best = __reduce_max_sync(0xffffffffu, best);
         if ((tid & 31) == 0) s_red[tid >> 5] = best;
@@ -89,58 +319,44 @@ __device__ void ppht_frame(const HoughParams &P, uint32_t *keys, uint32_t *idx, 
         best = s_red[0];
 #pragma unroll
         for (int k = 1; k < HOUGH_THREADS / 32; k++) best = max(best, s_red[k]);
-        const int max_val = best >> 8;  // arithmetic shift: floor for negatives
-        if (max_val < P.threshold) { __syncthreads(); continue; }
+        if ((best >> 8) < P.threshold) { __syncthreads(); continue; }
         const int max_n = 255 - (best & 255);
-
         if (tid == 0) {
-            const float a = -c_trig[2 * max_n + 1], b = c_trig[2 * max_n];
-            int x0 = x, y0 = y, dx0, dy0;
-            bool xflag;
-            if (fabsf(a) > fabsf(b)) {
-                xflag = true;
-                dx0 = a > 0 ? 1 : -1;
-                dy0 = __float2int_rn(__fdiv_rn(__fmul_rn(b, 65536.0f), fabsf(a)));
-                y0 = (y0 << 16) + 32768;
-            } else {
-                xflag = false;
-                dy0 = b > 0 ? 1 : -1;
-                dx0 = __float2int_rn(__fdiv_rn(__fmul_rn(a, 65536.0f), fabsf(b)));
-                x0 = (x0 << 16) + 32768;
-            }
-            int ex[2] = {0, 0}, ey[2] = {0, 0};
+            Walk wk;
+            wk.init(x, y, max_n);
+            int ends[2] = {0, 0};
             for (int k = 0; k < 2; k++) {
-                int gap = 0, xx = x0, yy = y0;
-                const int dx = k ? -dx0 : dx0, dy = k ? -dy0 : dy0;
-                for (;; xx += dx, yy += dy) {
-                    const int j1 = xflag ? xx : xx >> 16, i1 = xflag ? yy >> 16 : yy;
+                int gap = 0;
+                for (int i = 0;; i++) {
+                    int j1, i1;
+                    wk.at(k, i, j1, i1);
                     if (j1 < 0 || j1 >= W || i1 < 0 || i1 >= H) break;
                     const size_t q = (size_t)i1 * W + j1;
-                    if ((vbitmap[q >> 5] >> (q & 31)) & 1u) { gap = 0; ex[k] = j1; ey[k] = i1; }
+                    if ((vbitmap[q >> 5] >> (q & 31)) & 1u) { gap = 0; ends[k] = i; }
                     else if (++gap > line_gap) break;
                 }
             }
-            const int good = abs(ex[1] - ex[0]) >= P.min_len || abs(ey[1] - ey[0]) >= P.min_len;
+            int ex0, ey0, ex1, ey1;
+            wk.at(0, ends[0], ex0, ey0);
+            wk.at(1, ends[1], ex1, ey1);
+            const int good = abs(ex1 - ex0) >= P.min_len || abs(ey1 - ey0) >= P.min_len;
             int nw = 0;
-            for (int k = 0; k < 2; k++) {
-                int xx = x0, yy = y0;
-                const int dx = k ? -dx0 : dx0, dy = k ? -dy0 : dy0;
-                for (;; xx += dx, yy += dy) {
-                    const int j1 = xflag ? xx : xx >> 16, i1 = xflag ? yy >> 16 : yy;
+            for (int k = 0; k < 2; k++)
+                for (int i = 0; i <= ends[k]; i++) {
+                    int j1, i1;
+                    wk.at(k, i, j1, i1);
                     const size_t q = (size_t)i1 * W + j1;
                     const uint32_t wv = vbitmap[q >> 5];
                     if ((wv >> (q & 31)) & 1u) {
                         if (good && nw < P.walk_cap) walk[nw++] = ((unsigned)i1 << 16) | (unsigned)j1;
                         vbitmap[q >> 5] = wv & ~(1u << (q & 31));
                     }
-                    if (i1 == ey[k] && j1 == ex[k]) break;
                 }
-            }
             if (good) {
                 const int li = s_ctl[2];
                 if (li < P.max_lines) {
-                    lines_out[4 * li] = ex[0]; lines_out[4 * li + 1] = ey[0];
-                    lines_out[4 * li + 2] = ex[1]; lines_out[4 * li + 3] = ey[1];
+                    lines_out[4 * li] = ex0; lines_out[4 * li + 1] = ey0;
+                    lines_out[4 * li + 2] = ex1; lines_out[4 * li + 3] = ey1;
                 }
                 s_ctl[2] = li + 1;
             }
@@ -153,13 +369,12 @@ __device__ void ppht_frame(const HoughParams &P, uint32_t *keys, uint32_t *idx, 
             const int nw = s_ctl[1];
             volatile uint32_t *vwalk = walk;
             for (int k = 0; k < nw; k++) {
-                const uint32_t wk = vwalk[k];
-                myrow[rho_of(wk & 0xffffu, wk >> 16, tid)]--;
+                const uint32_t wk2 = vwalk[k];
+                myrow[rho_of(wk2 & 0xffffu, wk2 >> 16, tid)]--;
             }
         }
         __syncthreads();
     }
-    // reset: zero every accumulator cell and mask word a point of this frame can have touched
     for (long long q = tid; q < (long long)N * MDB_HOUGH_ANGLES; q += HOUGH_THREADS) {
         const int i = (int)(q / MDB_HOUGH_ANGLES), n = (int)(q % MDB_HOUGH_ANGLES);
         const uint32_t k = keys[i];
@@ -172,50 +387,4 @@ __device__ void ppht_frame(const HoughParams &P, uint32_t *keys, uint32_t *idx, 
     }
     __syncthreads();
     if (tid == 0) *nlines_out = s_ctl[2];
-    __syncthreads();
-}
-
-__device__ __forceinline__ int line_gap_of(const HoughParams &P, unsigned n_on) {
-    // Detector.py:342-344: dst_sum = count / mask_area * 100; gap = max(0, 1 - dst_sum/0.05) * max_gap
-    const double dst_sum = __dmul_rn(__ddiv_rn((double)n_on, P.mask_area), 100.0);
-    double g = __dsub_rn(1.0, __ddiv_rn(dst_sum, 0.05));
-    if (!(g > 0.0)) g = 0.0;
-    g = __dmul_rn(g, (double)P.max_gap);
-    return (int)rint(g);  // cvRound(maxLineGap)
-}
-
-// Shared-memory path: persistent CTAs loop over the frames of the batch.
-__global__ void __launch_bounds__(HOUGH_THREADS)
-hough_batch_kernel(HoughParams P, int T, const unsigned *npoints, const uint32_t *points,
-                   int32_t *accum_slots, uint32_t *bitmap_slots, uint32_t *walk_slots,
-                   int32_t *lines_out, int *nlines_out) {
-    extern __shared__ uint32_t sm[];
-    uint32_t *keys = sm, *idx = sm + P.cap;
-    const size_t bm_words = ((size_t)P.W * P.H + 31) / 32;
-    int32_t *accum = accum_slots + (size_t)blockIdx.x * MDB_HOUGH_ANGLES * P.numrho;
-    uint32_t *bitmap = bitmap_slots + (size_t)blockIdx.x * bm_words;
-    uint32_t *walk = walk_slots + (size_t)blockIdx.x * P.walk_cap;
-    for (int t = blockIdx.x; t < T; t += gridDim.x) {
-        const unsigned N = npoints[t];
-        if (N == 0) { if (threadIdx.x == 0) nlines_out[t] = 0; continue; }
-        if (N > (unsigned)P.cap) { if (threadIdx.x == 0) nlines_out[t] = -1; continue; }  // overflow path
-        int np2 = 1;
-        while (np2 < (int)N) np2 <<= 1;
-        for (int i = threadIdx.x; i < np2; i += HOUGH_THREADS)
-            keys[i] = i < (int)N ? points[(size_t)t * P.cap + i] : 0xFFFFFFFFu;
-        __syncthreads();
-        bitonic_sort_u32(keys, np2, threadIdx.x, HOUGH_THREADS);
-        ppht_frame(P, keys, idx, (int)N, line_gap_of(P, N), accum, bitmap, walk,
-                   lines_out + (size_t)t * P.max_lines * 4, nlines_out + t);
-    }
-}
-
-// Overflow path: one frame, keys already sorted in global memory (compact_ordered_kernel).
-__global__ void __launch_bounds__(HOUGH_THREADS)
-hough_global_kernel(HoughParams P, const unsigned *n_ptr, uint32_t *keys, uint32_t *idx,
-                    int32_t *accum, uint32_t *bitmap, uint32_t *walk, int32_t *lines_out,
-                    int *nlines_out) {
-    const unsigned N = *n_ptr;
-    if (N == 0) { if (threadIdx.x == 0) *nlines_out = 0; return; }
-    ppht_frame(P, keys, idx, (int)N, line_gap_of(P, N), accum, bitmap, walk, lines_out, nlines_out);
 }

@@ -14,6 +14,8 @@
 #include "kernels_basic.cuh"
 #include "stream_kernel.cuh"
 
+#define HOUGH_SMEM_BYTES (MDB_POINT_CAP * 8 + MDB_POINT_CAP / 8)  // keys u32 + order u16 + line u16 + removed bits
+
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
@@ -143,7 +145,6 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, cfg->device);
     if (e != cudaSuccess) { delete h; return fail(MDB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
-    h->slots = std::min(T, prop.multiProcessorCount * 2);
 
     HoughParams &hp = h->hp;
     hp.W = h->W; hp.H = h->H; hp.numrho = 2 * (h->W + h->H) + 1;
@@ -152,6 +153,14 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     for (size_t i = 0; i < h->HW; i++) area += mask[i];
     hp.mask_area = (double)area;
     hp.cap = MDB_POINT_CAP; hp.max_lines = MDB_MAX_LINES; hp.walk_cap = h->W + h->H + 2;
+    // Hough slots: one accumulator per frame in flight; bounded by what can be resident (6 CTAs/SM)
+    // and by a 12 GB memory budget
+    {
+        const size_t per_slot = (size_t)MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t);
+        size_t s = std::min<size_t>((size_t)T, (size_t)prop.multiProcessorCount * 6);
+        s = std::min<size_t>(s, std::max<size_t>(1, (12ull << 30) / per_slot));
+        h->slots = (int)s;
+    }
 
 #define ALLOC(ptr, bytes)                                                                   \
     do {                                                                                    \
@@ -192,14 +201,14 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     ALLOC(h->d_points, (size_t)T * MDB_POINT_CAP * sizeof(uint32_t));
     ALLOC(h->d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t));
     ALLOC(h->d_accum, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t));
-    ALLOC(h->d_bitmap, (size_t)h->slots * bm_words * sizeof(uint32_t));
-    ALLOC(h->d_walk, (size_t)h->slots * hp.walk_cap * sizeof(uint32_t));
+    ALLOC(h->d_bitmap, bm_words * sizeof(uint32_t));           // overflow path only
+    ALLOC(h->d_walk, (size_t)hp.walk_cap * sizeof(uint32_t));  // overflow path only
     ALLOC(h->d_on, sizeof(unsigned));
     CKH(cudaMemsetAsync(h->d_ring, 0, (size_t)h->R * h->HW, h->stream));
     CKH(cudaMemsetAsync(h->d_run[0], 0, h->HW, h->stream));
     CKH(cudaMemsetAsync(h->d_run[1], 0, h->HW, h->stream));
     CKH(cudaMemsetAsync(h->d_accum, 0, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t), h->stream));
-    CKH(cudaMemsetAsync(h->d_bitmap, 0, (size_t)h->slots * bm_words * sizeof(uint32_t), h->stream));
+    CKH(cudaMemsetAsync(h->d_bitmap, 0, bm_words * sizeof(uint32_t), h->stream));
     CKH(cudaMemsetAsync(h->d_dst, 0, (size_t)T * h->HW, h->stream));
     CKH(cudaMemcpyAsync(h->d_mask, mask, h->HW, cudaMemcpyHostToDevice, h->stream));
 
@@ -231,10 +240,10 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     }
     CKH(cudaMemcpyToSymbolAsync(c_trig, trig, sizeof trig, 0, cudaMemcpyHostToDevice, h->stream));
     CKH(cudaFuncSetAttribute(hough_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             MDB_POINT_CAP * 8));
+                             HOUGH_SMEM_BYTES));
     CKH(cudaStreamSynchronize(h->stream));
     {
-        int rc = stream_state_init(h->sk, h->W, h->H, h->n, cfg->device);
+        int rc = stream_state_init(h->sk, h->W, h->H, h->n, cfg->device, cfg->max_batch);
         if (rc != 0) { free_all(h); return fail(MDB_ERR_CUDA, "stream kernel init failed: %s", cudaGetErrorString(cudaGetLastError())); }
     }
     *out = h;
@@ -286,9 +295,10 @@ static int launch_fused(mdb_detector *h, int T, long long timer0, long long dy0)
     int nl = 0;
     if (h->use_stream_kernel && stream_kernel_supported(h->sk, T)) {
         int rc = stream_kernel_launch(h->sk, frame_src(h), timer0, dy0, T, h->cfg.dy_mask, h->d_thr,
-                                      h->d_run[h->run_cur], h->d_dst, h->d_npoints, h->d_points,
-                                      MDB_POINT_CAP, h->stream, &nl);
+                                      h->d_run[h->run_cur], h->d_run[h->run_cur ^ 1], h->d_dst,
+                                      h->d_npoints, h->d_points, MDB_POINT_CAP, h->stream, &nl);
         if (rc != 0) return fail(MDB_ERR_CUDA, "stream kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
+        if (h->cfg.dy_mask) h->run_cur ^= 1;
     } else {
         dim3 grid((h->W + V1_TW - 1) / V1_TW, (h->H + V1_TH - 1) / V1_TH);
         for (int i = 0; i < T; i++) {
@@ -312,8 +322,8 @@ static int launch_fused(mdb_detector *h, int T, long long timer0, long long dy0)
 
 static int launch_hough_and_copy(mdb_detector *h, int T) {
     const int grid = std::min(T, h->slots);
-    hough_batch_kernel<<<grid, HOUGH_THREADS, MDB_POINT_CAP * 8, h->stream>>>(
-        h->hp, T, h->d_npoints, h->d_points, h->d_accum, h->d_bitmap, h->d_walk, h->d_lines, h->d_nlines);
+    hough_batch_kernel<<<grid, HOUGH_THREADS, HOUGH_SMEM_BYTES, h->stream>>>(
+        h->hp, T, h->d_npoints, h->d_points, h->d_accum, h->d_lines, h->d_nlines);
     h->launches += 1;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->h_thr, h->d_thr, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream));

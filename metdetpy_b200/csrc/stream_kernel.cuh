@@ -1,13 +1,440 @@
-// Time-tiled streaming fused kernel (placeholder until the persistent kernel lands).
+// Time-tiled streaming path for whole batches (the throughput path), sm_100a.
+//
+// The reference recomputes max/mean over the n-frame ring for every frame (utils.py:269-307), i.e.
+// (n+2) bytes of traffic per pixel per frame.  Here every frame is read from HBM ONCE:
+//
+//   temporal_kernel  (stack -> diff -> threshold, fused)     reads  u8 frame, writes 1 bit / pixel
+//       each thread owns 16 consecutive pixels for the whole batch.  Its last n frames live in a
+//       private shared-memory ring fed by cp.async (LDGSTS, K frames in flight, no CTA barrier in
+//       the steady state); the sliding max is van Herk / Gil-Werman (prefix max in registers +
+//       suffix max ring in shared memory, one backward scan every n frames), the sliding sum is a
+//       running u16x2 register.  The decision  median(max - floor(sum/L)) > thr  is rewritten as
+//       "at least 5 of the 9 neighbours have  max*L - sum > thr*L",  so this kernel only emits the
+//       per-pixel predicate (exact integer arithmetic, no division) as a bit.
+//   spatial_kernel   (3x3 median == majority of 9 bits, 3x3 close, dynamic mask, dst)   reads bits,
+//       writes the u8 mask.  All 3x3 operators are bitwise on 32-pixel words; a warp walks a
+//       1024-pixel-wide strip top to bottom with neighbours exchanged by warp shuffles.  The
+//       dy-mask run-length counters (Detector.py:234-242) stay in shared memory for the whole batch
+//       and are only touched where a pixel is or was active.
+//
+// Per frame HBM traffic: H*W (frame) + H*W/8 + H*W/8 (bits out/in) + H*W (mask) = 2.25 H*W,
+// against the algorithmic 2 H*W of SURVEY.md section 8(d).
 #pragma once
 #include "common.cuh"
 
+#define ST_K 8          // frames in flight per thread (cp.async groups)
+#define SP_WARPS 4      // warps per CTA in the spatial kernel
+#define SP_USE 30       // useful 32-px words per warp strip (lanes 1..30; lanes 0 and 31 are halo)
+
 struct StreamState {
     int ok = 0;
+    int W = 0, H = 0, n = 0, max_batch = 0, device = 0;
+    int t_threads = 32;     // CTA size of the temporal kernel
+    size_t t_smem_per_thread = 0;
+    int sp_rows = 8;        // output rows per warp strip in the spatial kernel
+    uint32_t *d_bits = nullptr;  // [max_batch][H][W/32]
 };
-static inline int stream_state_init(StreamState &, int, int, int, int) { return 0; }
-static inline void stream_state_free(StreamState &) {}
-static inline bool stream_kernel_supported(const StreamState &, int) { return false; }
-static inline int stream_kernel_launch(StreamState &, FrameSrc, long long, long long, int, int, const int *,
-                                       uint8_t *, uint8_t *, unsigned *, uint32_t *, int, cudaStream_t,
-                                       int *) { return -1; }
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// even bytes (0,2) / odd bytes (1,3) of a packed u8x4 word as u16x2
+__device__ __forceinline__ unsigned ev(unsigned x) { return x & 0x00ff00ffu; }
+__device__ __forceinline__ unsigned od(unsigned x) { return prmt(x, 0u, 0x4341u); }
+__device__ __forceinline__ unsigned pack_eo(unsigned e, unsigned o) { return e | (o << 8); }
+
+template <bool MASKED>
+__global__ void __launch_bounds__(64)
+temporal_kernel(FrameSrc src, long long t0, int T, int n, int HW16, const int *__restrict__ thr,
+                uint16_t *__restrict__ bits) {
+    extern __shared__ uint4 t_smem[];
+    const int nt = blockDim.x, tid = threadIdx.x;
+    const int RS = n + ST_K;
+    uint4 *ring = t_smem;               // [RS][nt]   raw frames (slot RS-1 doubles as "frame t0-n")
+    uint4 *smx = t_smem + (size_t)RS * nt;  // [n][nt]    suffix max of the previous block, by position
+    uint8_t *thr_s = reinterpret_cast<uint8_t *>(smx + (size_t)n * nt);
+    for (int i = tid; i < T; i += nt) thr_s[i] = (uint8_t)min(max(thr[i], 0), 255);
+    __syncthreads();
+    const int g = blockIdx.x * nt + tid;
+    if (g >= HW16) return;
+    const uint8_t *gbase = src.ring + (size_t)g * 16;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + tid * 16;
+    const uint32_t slot_stride = nt * 16;
+
+    uint4 mk = make_uint4(~0u, ~0u, ~0u, ~0u);
+    if (MASKED) {
+        const uint4 m = *reinterpret_cast<const uint4 *>(src.mask + (size_t)g * 16);
+        mk = make_uint4(m.x * 0xffu, m.y * 0xffu, m.z * 0xffu, m.w * 0xffu);  // {0,1} -> {0x00,0xff}
+    }
+
+    // ---- history: frames t0-n+1 .. t0-1 -> slots 0 .. n-2 ; slot RS-1 = zeros -----------------
+    ring[(size_t)(RS - 1) * nt + tid] = make_uint4(0, 0, 0, 0);
+    for (int p = 1; p < n; p++) {
+        const long long th = t0 - n + p;
+        if (th >= 0) cp_async16(ring_s + (p - 1) * slot_stride, gbase + (size_t)(th % src.R) * src.HW);
+        else ring[(size_t)(p - 1) * nt + tid] = make_uint4(0, 0, 0, 0);
+    }
+    cp_async_commit();
+    // ---- prime the pipeline: frames t0 .. t0+K-1 -> slots n-1 .. n+K-2 -------------------------
+    int pf_slot = (int)(t0 % src.R);  // global ring slot of the next frame to prefetch
+    for (int i = 0; i < ST_K; i++) {
+        if (i < T) cp_async16(ring_s + (n - 1 + i) * slot_stride, gbase + (size_t)pf_slot * src.HW);
+        cp_async_commit();
+        if (++pf_slot == src.R) pf_slot = 0;
+    }
+    cp_async_wait<ST_K>();  // history landed
+
+    unsigned sE[4] = {0, 0, 0, 0}, sO[4] = {0, 0, 0, 0};  // window sums, u16x2 (even / odd pixels)
+    {
+        unsigned aE[4] = {0, 0, 0, 0}, aO[4] = {0, 0, 0, 0};
+        for (int p = n - 1; p >= 1; p--) {
+            uint4 v = ring[(size_t)(p - 1) * nt + tid];
+            if (MASKED) {
+                v.x &= mk.x; v.y &= mk.y; v.z &= mk.z; v.w &= mk.w;
+                ring[(size_t)(p - 1) * nt + tid] = v;
+            }
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+            uint4 o;
+            unsigned *ow = &o.x;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned e = ev(w[k]), d = od(w[k]);
+                sE[k] += e; sO[k] += d;
+                aE[k] = __vmaxu2(aE[k], e); aO[k] = __vmaxu2(aO[k], d);
+                ow[k] = pack_eo(aE[k], aO[k]);
+            }
+            smx[(size_t)p * nt + tid] = o;
+        }
+    }
+    unsigned pE[4] = {0, 0, 0, 0}, pO[4] = {0, 0, 0, 0};  // prefix max of the current block
+
+    int j = 0;                 // position inside the current block (blocks are anchored at t0)
+    int s_cur = n - 1;         // ring slot of the current frame
+    int s_old = RS - 1;        // ring slot of frame t-n (and destination of the next prefetch)
+    long long tg = t0;
+    for (int i = 0; i < T; i++, tg++) {
+        cp_async_wait<ST_K - 1>();  // this thread's copy of frame i has landed
+        uint4 xv = ring[(size_t)s_cur * nt + tid];
+        const uint4 ov = ring[(size_t)s_old * nt + tid];
+        if (MASKED) {
+            xv.x &= mk.x; xv.y &= mk.y; xv.z &= mk.z; xv.w &= mk.w;
+            ring[(size_t)s_cur * nt + tid] = xv;
+        }
+        uint4 mv = make_uint4(0, 0, 0, 0);
+        if (j + 1 < n) mv = smx[(size_t)(j + 1) * nt + tid];
+        // slot s_old is free now: fetch frame i+K into it
+        if (i + ST_K < T) cp_async16(ring_s + s_old * slot_stride, gbase + (size_t)pf_slot * src.HW);
+        cp_async_commit();
+        if (++pf_slot == src.R) pf_slot = 0;
+
+        const int L = (int)(tg + 1 < n ? tg + 1 : n);
+        const unsigned Tq = (unsigned)thr_s[i] * (unsigned)L;            // <= 255*128
+        const unsigned Cpk = (0x7fffu - Tq) * 0x00010001u;                // per-half bias
+        const unsigned xw[4] = {xv.x, xv.y, xv.z, xv.w};
+        const unsigned ow[4] = {ov.x, ov.y, ov.z, ov.w};
+        const unsigned mw[4] = {mv.x, mv.y, mv.z, mv.w};
+        unsigned M[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned e = ev(xw[k]), d = od(xw[k]);
+            sE[k] = sE[k] + e - ev(ow[k]);
+            sO[k] = sO[k] + d - od(ow[k]);
+            if (j == 0) { pE[k] = e; pO[k] = d; }
+            else { pE[k] = __vmaxu2(pE[k], e); pO[k] = __vmaxu2(pO[k], d); }
+            const unsigned wE = __vmaxu2(pE[k], ev(mw[k])), wO = __vmaxu2(pO[k], od(mw[k]));
+            // per half: max*L - sum + 0x7fff - thr*L ; bit 15 set <=> max*L - sum > thr*L
+            const unsigned vE = wE * (unsigned)L + Cpk - sE[k];
+            const unsigned vO = wO * (unsigned)L + Cpk - sO[k];
+            M[k] = prmt(vE, vO, 0xFBD9u);  // sign-replicate bytes 1,5,3,7 -> 0x00/0xff per pixel
+        }
+        const unsigned q01 = (M[0] & 0x08040201u) | (M[1] & 0x80402010u);
+        const unsigned q23 = (M[2] & 0x08040201u) | (M[3] & 0x80402010u);
+        const unsigned r01 = q01 * 0x01010101u, r23 = q23 * 0x01010101u;
+        bits[(size_t)i * HW16 + g] = (uint16_t)prmt(r01, r23, 0x4473u);
+
+        if (++j == n) {  // block complete: suffix max of its n frames, by position 1..n-1
+            j = 0;
+            unsigned aE[4] = {0, 0, 0, 0}, aO[4] = {0, 0, 0, 0};
+            int s = s_cur;
+            for (int p = n - 1; p >= 1; p--) {
+                const uint4 v = ring[(size_t)s * nt + tid];
+                const unsigned w[4] = {v.x, v.y, v.z, v.w};
+                uint4 o;
+                unsigned *owp = &o.x;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    aE[k] = __vmaxu2(aE[k], ev(w[k]));
+                    aO[k] = __vmaxu2(aO[k], od(w[k]));
+                    owp[k] = pack_eo(aE[k], aO[k]);
+                }
+                smx[(size_t)p * nt + tid] = o;
+                if (--s < 0) s = RS - 1;
+            }
+        }
+        if (++s_cur == RS) s_cur = 0;
+        if (++s_old == RS) s_old = 0;
+    }
+    cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------
+// Spatial kernel.  One warp = one strip of SP_USE words (960 px) x `rows` output rows, for all T
+// frames.  Lane l holds word column wx = strip*SP_USE - 1 + l.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned maj3(unsigned a, unsigned b, unsigned c) { return (a & b) | (c & (a | b)); }
+
+struct RowH {  // horizontal 3-sums of one bit row: s = parity, c = carry (l + w + r = s + 2c)
+    unsigned s, c;
+};
+
+__global__ void __launch_bounds__(SP_WARPS * 32)
+spatial_kernel(const uint32_t *__restrict__ bits, int W, int H, int T, int n, long long dy0, int dy_on,
+               int rows, int strips, int bands, const uint8_t *__restrict__ run_in,
+               uint8_t *__restrict__ run_out, uint8_t *__restrict__ dst,
+               unsigned *__restrict__ npoints, uint32_t *__restrict__ points, int cap) {
+    extern __shared__ uint8_t sp_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x * SP_WARPS + warp;
+    if (tile >= strips * bands) return;
+    const int strip = tile % strips, band = tile / strips;
+    const int Wb = W >> 5;
+    const int wx = strip * SP_USE - 1 + lane;
+    const bool lane_in = wx >= 0 && wx < Wb;
+    const bool lane_out = lane_in && lane >= 1 && lane <= SP_USE;
+    const int y0 = band * rows;
+    const int R1 = rows + 2;  // rows y0-1 .. y0+rows hold run state
+    const int NR = rows + 8;  // bit rows a frame needs: y0-4 .. y0+rows+3
+    // per-warp shared memory: run bytes [R1][32 lanes][32 px], prev-active words [R1][32],
+    // double-buffered bit rows [2][NR][32]
+    uint8_t *run_s = sp_smem + (size_t)warp * (R1 * 1024 + R1 * 128 + 2 * NR * 128);
+    uint32_t *prev_s = reinterpret_cast<uint32_t *>(run_s + R1 * 1024);
+    uint32_t *stage_s = prev_s + R1 * 32;
+    const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(stage_s) + lane * 4;
+    const size_t frame_words = (size_t)H * Wb;
+    // cp.async prefetch of one frame's NR bit rows (rows replicated outside the image, as medianBlur does)
+    auto prefetch = [&](int t, int buf) {
+        if (lane_in && t < T) {
+            const uint32_t *fb = bits + (size_t)t * frame_words + wx;
+            for (int r = 0; r < NR; r++) {
+                const int yc = min(max(y0 - 4 + r, 0), H - 1);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(stage_sa + (buf * NR + r) * 128),
+                             "l"(fb + (size_t)yc * Wb)
+                             : "memory");
+            }
+        }
+        cp_async_commit();
+    };
+    prefetch(0, 0);
+
+    if (dy_on) {  // load run counters of the region (zero outside the image)
+        for (int r = 0; r < R1; r++) {
+            const int y = y0 - 1 + r;
+            uint4 a = make_uint4(0, 0, 0, 0), b = a;
+            if (lane_in && y >= 0 && y < H) {
+                const uint4 *p = reinterpret_cast<const uint4 *>(run_in + (size_t)y * W + (size_t)wx * 32);
+                a = p[0]; b = p[1];
+            }
+            uint4 *q = reinterpret_cast<uint4 *>(run_s + r * 1024 + lane * 32);
+            q[0] = a; q[1] = b;
+            unsigned nz = 0;
+            const unsigned w8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+#pragma unroll
+                for (int bb = 0; bb < 4; bb++)
+                    if ((w8[k] >> (8 * bb)) & 0xffu) nz |= 1u << (4 * k + bb);
+            prev_s[r * 32 + lane] = nz;
+        }
+        __syncwarp();
+    }
+
+    const unsigned FULL = 0xffffffffu;
+    for (int t = 0; t < T; t++) {
+        prefetch(t + 1, (t + 1) & 1);
+        cp_async_wait<1>();
+        __syncwarp();
+        const uint32_t *sb = stage_s + (t & 1) * NR * 32 + lane;
+        const int Ldy = (int)((dy0 + t + 1) < n ? (dy0 + t + 1) : n);
+        RowH h0 = {0, 0}, h1 = {0, 0};            // horizontal sums of b rows yy-2, yy-1
+        unsigned hd0 = 0, hd1 = 0;                // horizontal dilations of bin rows
+        unsigned he0 = FULL, he1 = FULL;          // horizontal erosions of dil rows
+        unsigned hm0 = FULL, hm1 = FULL;          // horizontal erosions of m rows
+        unsigned act_prev = 0;                    // act of row yy-4
+        for (int yy = y0 - 4; yy < y0 + rows + 4; yy++) {
+            // ---- b row yy ---------------------------------------------------------------------
+            unsigned bw = lane_in ? sb[(yy - (y0 - 4)) * 32] : 0u;
+            unsigned Lw = __shfl_up_sync(FULL, bw, 1), Rw = __shfl_down_sync(FULL, bw, 1);
+            if (wx == 0) Lw = (bw & 1u) << 31;
+            if (wx == Wb - 1) Rw = bw >> 31;
+            const unsigned l = (bw << 1) | (Lw >> 31), r = (bw >> 1) | (Rw << 31);
+            RowH h2;
+            h2.s = l ^ bw ^ r;
+            h2.c = maj3(l, bw, r);
+            // ---- bin row yy-1 = majority of the 9 bits (>= 5) --------------------------------
+            unsigned bin = 0;
+            {
+                const int y = yy - 1;
+                if (lane_in && y >= 0 && y < H) {
+                    const unsigned ones = h0.s ^ h1.s ^ h2.s, c1 = maj3(h0.s, h1.s, h2.s);
+                    const unsigned twos = h0.c ^ h1.c ^ h2.c, c2 = maj3(h0.c, h1.c, h2.c);
+                    const unsigned t0b = c1 ^ twos, t1b = c1 & twos;  // weights 2 and 4
+                    bin = (t1b & c2) | ((t1b ^ c2) & (t0b | ones));
+                }
+            }
+            h0 = h1; h1 = h2;
+            // ---- dil row yy-2 (outside the image: ones, ignored by the erosion) ---------------
+            unsigned hd2, dil;
+            {
+                const unsigned Lb = __shfl_up_sync(FULL, bin, 1), Rb = __shfl_down_sync(FULL, bin, 1);
+                hd2 = bin | (bin << 1) | (Lb >> 31) | (bin >> 1) | (Rb << 31);
+                const int y = yy - 2;
+                dil = (lane_in && y >= 0 && y < H) ? (hd0 | hd1 | hd2) : FULL;
+                hd0 = hd1; hd1 = hd2;
+            }
+            // ---- act row yy-3 = erosion of dil --------------------------------------------------
+            unsigned act;
+            {
+                const unsigned Ld = __shfl_up_sync(FULL, dil, 1), Rd = __shfl_down_sync(FULL, dil, 1);
+                const unsigned he2 = dil & ((dil << 1) | (Ld >> 31)) & ((dil >> 1) | (Rd << 31));
+                const int y = yy - 3;
+                act = (lane_in && y >= 0 && y < H) ? (he0 & he1 & he2) : 0u;
+                he0 = he1; he1 = he2;
+            }
+            // ---- dynamic mask: run-length counters of row yy-3, m = run < Ldy -----------------
+            unsigned out_bits;
+            if (dy_on) {
+                unsigned m = FULL;
+                const int rr = yy - 3 - (y0 - 1);  // row inside the run region
+                if (rr >= 0 && rr < R1) {
+                    const unsigned prev = prev_s[rr * 32 + lane];
+                    unsigned touch = act | prev;
+                    uint8_t *rp = run_s + rr * 1024 + lane * 32;
+                    while (touch) {
+                        const int b = __ffs(touch) - 1;
+                        touch &= touch - 1;
+                        int v = rp[b];
+                        v = ((act >> b) & 1u) ? min(v + 1, 255) : 0;
+                        rp[b] = (uint8_t)v;
+                        if (v >= Ldy) m &= ~(1u << b);
+                    }
+                    prev_s[rr * 32 + lane] = act;
+                }
+                const unsigned Lm = __shfl_up_sync(FULL, m, 1), Rm = __shfl_down_sync(FULL, m, 1);
+                const unsigned hm2 = m & ((m << 1) | (Lm >> 31)) & ((m >> 1) | (Rm << 31));
+                out_bits = act_prev & hm0 & hm1 & hm2;  // row yy-4
+                hm0 = hm1; hm1 = hm2;
+                act_prev = act;
+            } else {
+                out_bits = act;  // row yy-3 ; emitted one iteration earlier than with dy
+            }
+            const int yo = dy_on ? yy - 4 : yy - 3;
+            if (lane_out && yo >= y0 && yo < y0 + rows && yo < H) {
+                uint4 a = make_uint4(0, 0, 0, 0), b = a;
+                if (out_bits) {
+                    unsigned w8[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const unsigned nib = (out_bits >> (4 * k)) & 0xfu;
+                        w8[k] = ((nib & 1u) ? 0xffu : 0u) | ((nib & 2u) ? 0xff00u : 0u) |
+                                ((nib & 4u) ? 0xff0000u : 0u) | ((nib & 8u) ? 0xff000000u : 0u);
+                    }
+                    a = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+                    b = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+                    unsigned ob = out_bits;
+                    while (ob) {
+                        const int bpos = __ffs(ob) - 1;
+                        ob &= ob - 1;
+                        const unsigned slot = atomicAdd(npoints + t, 1u);
+                        if (slot < (unsigned)cap)
+                            points[(size_t)t * cap + slot] = ((unsigned)yo << 16) | (unsigned)(wx * 32 + bpos);
+                    }
+                }
+                uint4 *o = reinterpret_cast<uint4 *>(dst + (size_t)t * W * H + (size_t)yo * W + (size_t)wx * 32);
+                __stcs(o, a);
+                __stcs(o + 1, b);
+            }
+        }
+        __syncwarp();  // all lanes done with this frame's staged rows before they are overwritten
+    }
+    cp_async_wait<0>();
+    if (dy_on) {  // persist the run counters of the rows this warp owns
+        __syncwarp();
+        for (int r = 1; r <= rows; r++) {
+            const int y = y0 - 1 + r;
+            if (lane_out && y < H) {
+                const uint4 *q = reinterpret_cast<const uint4 *>(run_s + r * 1024 + lane * 32);
+                uint4 *p = reinterpret_cast<uint4 *>(run_out + (size_t)y * W + (size_t)wx * 32);
+                p[0] = q[0]; p[1] = q[1];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+static inline void stream_state_free(StreamState &s) {
+    if (s.d_bits) cudaFree(s.d_bits);
+    s.d_bits = nullptr;
+    s.ok = 0;
+}
+
+static inline int stream_state_init(StreamState &s, int W, int H, int n, int device, int max_batch) {
+    s.W = W; s.H = H; s.n = n; s.device = device; s.max_batch = max_batch; s.ok = 0;
+    if (W % 32 != 0 || n < 2 || n > 128 || max_batch > 4096) return 0;  // generic kernel serves these
+    s.t_smem_per_thread = (size_t)(2 * n + ST_K) * 16;
+    const size_t budget = 220 * 1024;
+    s.t_threads = (budget / (s.t_smem_per_thread * 32) > 32) ? 64 : 32;
+    if (s.t_smem_per_thread * s.t_threads + max_batch > budget) return 0;
+    if (cudaMalloc((void **)&s.d_bits, (size_t)max_batch * H * (W / 32) * sizeof(uint32_t)) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;  // fall back to the generic per-frame kernel
+    }
+    s.sp_rows = 8;
+    const size_t sp_smem = (size_t)SP_WARPS * ((s.sp_rows + 2) * (1024 + 128) + 2 * (s.sp_rows + 8) * 128);
+    if (cudaFuncSetAttribute(temporal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess ||
+        cudaFuncSetAttribute(temporal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess ||
+        cudaFuncSetAttribute(temporal_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
+        cudaFuncSetAttribute(temporal_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
+        cudaFuncSetAttribute(spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem) != cudaSuccess)
+        return -1;
+    s.ok = 1;
+    return 0;
+}
+
+static inline bool stream_kernel_supported(const StreamState &s, int T) { return s.ok && T >= 1 && T <= s.max_batch; }
+
+// Launches temporal + spatial kernels for frames timer0 .. timer0+T-1. Run counters are read from
+// run_in at the start and written to run_out at the end (ping-pong: tiles of a later wave may still
+// be loading their halo while an earlier tile stores). Returns 0 / -1; *launches gets the number of kernel launches.
+static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long timer0, long long dy0, int T,
+                                       int dy_on, const int *d_thr, const uint8_t *run_in, uint8_t *run_out,
+                                       uint8_t *dst,
+                                       unsigned *npoints, uint32_t *points, int cap, cudaStream_t st,
+                                       int *launches) {
+    const int HW16 = (int)((size_t)s.W * s.H / 16);
+    const int nt = s.t_threads;
+    const size_t smem = s.t_smem_per_thread * nt + ((T + 15) & ~15);
+    const int grid = (HW16 + nt - 1) / nt;
+    if (src.mask)
+        temporal_kernel<true><<<grid, nt, smem, st>>>(src, timer0, T, s.n, HW16, d_thr, (uint16_t *)s.d_bits);
+    else
+        temporal_kernel<false><<<grid, nt, smem, st>>>(src, timer0, T, s.n, HW16, d_thr, (uint16_t *)s.d_bits);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    const int Wb = s.W / 32;
+    const int strips = (Wb + SP_USE - 1) / SP_USE, bands = (s.H + s.sp_rows - 1) / s.sp_rows;
+    const int tiles = strips * bands;
+    const size_t sp_smem = (size_t)SP_WARPS * ((s.sp_rows + 2) * (1024 + 128) + 2 * (s.sp_rows + 8) * 128);
+    spatial_kernel<<<(tiles + SP_WARPS - 1) / SP_WARPS, SP_WARPS * 32, sp_smem, st>>>(
+        s.d_bits, s.W, s.H, T, s.n, dy0, dy_on, s.sp_rows, strips, bands, run_in, run_out, dst, npoints, points, cap);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    *launches = 2;
+    return 0;
+}
