@@ -23,6 +23,18 @@ struct FrameSrc {
     }
 };
 
+// `act` bit-frames (mask after the close, before the dynamic mask; Detector.py:335) of the last n-1
+// detects plus the current batch: the dynamic mask of Detector.py:234-242 is "not on in ALL of the
+// last L act frames", so this ring replaces the reference's second n-frame SlidingWindow.
+struct ActRing {
+    uint32_t *base;  // [RA][H][Wb] 32-pixel words, row stride Wb = ceil(W/32)
+    int RA, Wb;
+    size_t frame_words;
+    __device__ __forceinline__ uint32_t *frame(long long d) const {
+        return base + (size_t)(d % RA) * frame_words;
+    }
+};
+
 // Scalar detector state that lives on the device so that batches never round-trip to the host.
 struct DevState {
     double ema_value;   // EMA.cur_value           utils.py:343

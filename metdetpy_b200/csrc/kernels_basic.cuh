@@ -109,7 +109,8 @@ __global__ void threshold_kernel(DevState *st, const unsigned long long *acc, in
 // cross-check of the time-tiled streaming kernel.
 //   stack max / floor-mean  (utils.py:288-307)  -> diff (Detector.py:327-328)
 //   -> medianBlur 3 (:329) -> threshold (:332) -> MORPH_CLOSE 3x3 (:335)
-//   -> dynamic mask: run-length < L, erode 3x3, multiply (:234-242) -> dst, on-pixel list.
+//   -> dynamic mask: not on in all of the last L act frames, erode 3x3, multiply (:234-242)
+//   -> dst, on-pixel list.
 // Tile 64x16 outputs, 4-pixel halo (median 1 + dilate 1 + erode 1 + dy-erode 1).
 // ------------------------------------------------------------------------------------------
 #define V1_TW 64
@@ -131,9 +132,9 @@ __device__ __forceinline__ int median9(int p0, int p1, int p2, int p3, int p4, i
 }
 
 __global__ void __launch_bounds__(256)
-fused_frame_kernel(FrameSrc src, int W, int H, int n, long long t, int L, int Ldy, int dy_on,
-                   const int *thr_ptr, const uint8_t *run_in, uint8_t *run_out, uint8_t *dst,
-                   unsigned *npoints, uint32_t *points, int cap) {
+fused_frame_kernel(FrameSrc src, int W, int H, int n, long long t, int L, long long d, int Ldy,
+                   int dy_on, const int *thr_ptr, ActRing ring, uint8_t *dst, unsigned *npoints,
+                   uint32_t *points, int cap) {
     __shared__ uint8_t sA[V1_RH][V1_RW], sB[V1_RH][V1_RW];
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * V1_TW - 4, y0 = blockIdx.y * V1_TH - 4;
@@ -193,12 +194,10 @@ fused_frame_kernel(FrameSrc src, int W, int H, int n, long long t, int L, int Ld
             for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
                 for (int dx = -1; dx <= 1; dx++) act &= sA[ry + dy][rx + dx];
-            if (dy_on) {
-                const size_t p = (size_t)gy * W + gx;
-                int r = run_in[p];
-                r = act ? min(r + 1, 255) : 0;
-                m = r < Ldy;
-                if (rx >= 4 && rx < 4 + V1_TW && ry >= 4 && ry < 4 + V1_TH) run_out[p] = (uint8_t)r;
+            if (dy_on && act) {  // m = 0 only if the pixel was on in all of the last Ldy act frames
+                m = 0;
+                for (int k = 1; k < Ldy; k++)
+                    if (!((ring.frame(d - k)[(size_t)gy * ring.Wb + (gx >> 5)] >> (gx & 31)) & 1u)) { m = 1; break; }
             }
         }
         sB[ry][rx] = (uint8_t)(act | (m << 1));
@@ -210,6 +209,10 @@ fused_frame_kernel(FrameSrc src, int W, int H, int n, long long t, int L, int Ld
         const int gx = x0 + rx, gy = y0 + ry;
         int on = 0;
         const bool inside = gx < W && gy < H;
+        {   // publish this frame's act bits (32 consecutive pixels of one row per warp)
+            const unsigned ab = __ballot_sync(0xffffffffu, inside && (sB[ry][rx] & 1));
+            if ((tid & 31) == 0 && inside) ring.frame(d)[(size_t)gy * ring.Wb + (gx >> 5)] = ab;
+        }
         if (inside) {
             int mm = 2;
 #pragma unroll

@@ -44,8 +44,8 @@ struct mdb_detector {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // device
     uint8_t *d_ring = nullptr, *d_mask = nullptr, *d_dst = nullptr;
-    uint8_t *d_run[2] = {nullptr, nullptr};
-    int run_cur = 0;
+    uint32_t *d_act = nullptr;  // act bit-frame ring [RA][H][Wb]
+    int RA = 0, Wb = 0;
     DevState *d_state = nullptr;
     unsigned long long *d_noise = nullptr;
     int *d_thr = nullptr, *d_nlines = nullptr;
@@ -94,11 +94,20 @@ static FrameSrc frame_src(const mdb_detector *h) {
     return s;
 }
 
+static ActRing act_ring(const mdb_detector *h) {
+    ActRing r;
+    r.base = h->d_act;
+    r.RA = h->RA;
+    r.Wb = h->Wb;
+    r.frame_words = (size_t)h->H * h->Wb;
+    return r;
+}
+
 static void free_all(mdb_detector *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void *dev[] = {h->d_ring, h->d_mask, h->d_dst, h->d_run[0], h->d_run[1], h->d_state, h->d_noise,
+    void *dev[] = {h->d_ring, h->d_mask, h->d_dst, h->d_act, h->d_state, h->d_noise,
                    h->d_thr, h->d_nlines, h->d_thrf, h->d_snr, h->d_npoints, h->d_points,
                    h->d_lines, h->d_accum, h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_on};
     for (void *p : dev)
@@ -189,8 +198,9 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     ALLOC(h->d_ring, (size_t)h->R * h->HW);
     ALLOC(h->d_mask, h->HW);
     ALLOC(h->d_dst, (size_t)T * h->HW);
-    ALLOC(h->d_run[0], h->HW);
-    ALLOC(h->d_run[1], h->HW);
+    h->Wb = (h->W + 31) / 32;
+    h->RA = h->n - 1 + T;
+    ALLOC(h->d_act, (size_t)h->RA * h->H * h->Wb * sizeof(uint32_t));
     ALLOC(h->d_state, sizeof(DevState));
     ALLOC(h->d_noise, (size_t)T * 2 * sizeof(unsigned long long));
     ALLOC(h->d_thr, T * sizeof(int));
@@ -205,8 +215,7 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     ALLOC(h->d_walk, (size_t)hp.walk_cap * sizeof(uint32_t));  // overflow path only
     ALLOC(h->d_on, sizeof(unsigned));
     CKH(cudaMemsetAsync(h->d_ring, 0, (size_t)h->R * h->HW, h->stream));
-    CKH(cudaMemsetAsync(h->d_run[0], 0, h->HW, h->stream));
-    CKH(cudaMemsetAsync(h->d_run[1], 0, h->HW, h->stream));
+    CKH(cudaMemsetAsync(h->d_act, 0, (size_t)h->RA * h->H * h->Wb * sizeof(uint32_t), h->stream));
     CKH(cudaMemsetAsync(h->d_accum, 0, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t), h->stream));
     CKH(cudaMemsetAsync(h->d_bitmap, 0, bm_words * sizeof(uint32_t), h->stream));
     CKH(cudaMemsetAsync(h->d_dst, 0, (size_t)T * h->HW, h->stream));
@@ -295,10 +304,9 @@ static int launch_fused(mdb_detector *h, int T, long long timer0, long long dy0)
     int nl = 0;
     if (h->use_stream_kernel && stream_kernel_supported(h->sk, T)) {
         int rc = stream_kernel_launch(h->sk, frame_src(h), timer0, dy0, T, h->cfg.dy_mask, h->d_thr,
-                                      h->d_run[h->run_cur], h->d_run[h->run_cur ^ 1], h->d_dst,
-                                      h->d_npoints, h->d_points, MDB_POINT_CAP, h->stream, &nl);
+                                      act_ring(h), h->d_dst, h->d_npoints, h->d_points, MDB_POINT_CAP,
+                                      h->stream, &nl);
         if (rc != 0) return fail(MDB_ERR_CUDA, "stream kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
-        if (h->cfg.dy_mask) h->run_cur ^= 1;
     } else {
         dim3 grid((h->W + V1_TW - 1) / V1_TW, (h->H + V1_TH - 1) / V1_TH);
         for (int i = 0; i < T; i++) {
@@ -306,10 +314,9 @@ static int launch_fused(mdb_detector *h, int T, long long timer0, long long dy0)
             const int L = (int)std::min<long long>(h->n, t + 1);
             const int Ldy = (int)std::min<long long>(h->n, dy0 + i + 1);
             fused_frame_kernel<<<grid, 256, 0, h->stream>>>(
-                frame_src(h), h->W, h->H, h->n, t, L, Ldy, h->cfg.dy_mask, h->d_thr + i,
-                h->d_run[h->run_cur], h->d_run[h->run_cur ^ 1], h->d_dst + (size_t)i * h->HW,
-                h->d_npoints + i, h->d_points + (size_t)i * MDB_POINT_CAP, MDB_POINT_CAP);
-            if (h->cfg.dy_mask) h->run_cur ^= 1;
+                frame_src(h), h->W, h->H, h->n, t, L, dy0 + i, Ldy, h->cfg.dy_mask, h->d_thr + i,
+                act_ring(h), h->d_dst + (size_t)i * h->HW, h->d_npoints + i,
+                h->d_points + (size_t)i * MDB_POINT_CAP, MDB_POINT_CAP);
             nl++;
         }
     }

@@ -11,14 +11,11 @@
 //       running u16x2 register.  The decision  median(max - floor(sum/L)) > thr  is rewritten as
 //       "at least 5 of the 9 neighbours have  max*L - sum > thr*L",  so this kernel only emits the
 //       per-pixel predicate (exact integer arithmetic, no division) as a bit.
-//   spatial_kernel   (3x3 median == majority of 9 bits, 3x3 close, dynamic mask, dst)   reads bits,
-//       writes the u8 mask.  All 3x3 operators are bitwise on 32-pixel words; a warp walks a
-//       1024-pixel-wide strip top to bottom with neighbours exchanged by warp shuffles.  The
-//       dy-mask run-length counters (Detector.py:234-242) stay in shared memory for the whole batch
-//       and are only touched where a pixel is or was active.
+//   act_kernel / dst_kernel  (3x3 median == majority of 9 bits, 3x3 close, dynamic mask, dst): read
+//       the bits, write the u8 mask.  All 3x3 operators are bitwise on 32-pixel words; see below.
 //
-// Per frame HBM traffic: H*W (frame) + H*W/8 + H*W/8 (bits out/in) + H*W (mask) = 2.25 H*W,
-// against the algorithmic 2 H*W of SURVEY.md section 8(d).
+// Per frame HBM traffic: H*W (frame) + 4 * H*W/8 (predicate bits and act bits, out and in)
+// + H*W (mask) = 2.5 H*W, against the algorithmic 2 H*W of SURVEY.md section 8(d).
 #pragma once
 #include "common.cuh"
 
@@ -187,8 +184,14 @@ temporal_kernel(FrameSrc src, long long t0, int T, int n, int HW16, const int *_
 }
 
 // ------------------------------------------------------------------------------------------
-// Spatial kernel.  One warp = one strip of SP_USE words (960 px) x `rows` output rows, for all T
-// frames.  Lane l holds word column wx = strip*SP_USE - 1 + l.
+// Spatial kernels: everything after the per-pixel predicate is bitwise on 32-pixel words and --
+// because the dynamic mask "pixel was on in ALL of the last L frames" (Detector.py:234-242) is the
+// AND of the last L `act` bit-frames -- carries no sequential state: both kernels are parallel over
+// (frame, strip, band).  One warp = one strip of SP_USE words (960 px; lanes 0 and 31 are halo
+// columns) walked top to bottom, neighbours exchanged with warp shuffles.
+//   act_kernel : bits -> majority-of-9 (== medianBlur 3 then threshold) -> dilate -> erode = act
+//   dst_kernel : act ring -> m = ~AND_k act(d-k) -> erode(m) -> dst = act & erode(m)
+//                -> u8 mask, on-pixel count, on-pixel list
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned maj3(unsigned a, unsigned b, unsigned c) { return (a & b) | (c & (a | b)); }
 
@@ -197,13 +200,11 @@ struct RowH {  // horizontal 3-sums of one bit row: s = parity, c = carry (l + w
 };
 
 __global__ void __launch_bounds__(SP_WARPS * 32)
-spatial_kernel(const uint32_t *__restrict__ bits, int W, int H, int T, int n, long long dy0, int dy_on,
-               int rows, int strips, int bands, const uint8_t *__restrict__ run_in,
-               uint8_t *__restrict__ run_out, uint8_t *__restrict__ dst,
-               unsigned *__restrict__ npoints, uint32_t *__restrict__ points, int cap) {
-    extern __shared__ uint8_t sp_smem[];
+act_kernel(const uint32_t *__restrict__ bits, int W, int H, int T, int rows, int strips, int bands,
+           ActRing ring, long long dy0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile = blockIdx.x * SP_WARPS + warp;
+    const int t = blockIdx.y;
     if (tile >= strips * bands) return;
     const int strip = tile % strips, band = tile / strips;
     const int Wb = W >> 5;
@@ -211,170 +212,122 @@ spatial_kernel(const uint32_t *__restrict__ bits, int W, int H, int T, int n, lo
     const bool lane_in = wx >= 0 && wx < Wb;
     const bool lane_out = lane_in && lane >= 1 && lane <= SP_USE;
     const int y0 = band * rows;
-    const int R1 = rows + 2;  // rows y0-1 .. y0+rows hold run state
-    const int NR = rows + 8;  // bit rows a frame needs: y0-4 .. y0+rows+3
-    // per-warp shared memory: run bytes [R1][32 lanes][32 px], prev-active words [R1][32],
-    // double-buffered bit rows [2][NR][32]
-    uint8_t *run_s = sp_smem + (size_t)warp * (R1 * 1024 + R1 * 128 + 2 * NR * 128);
-    uint32_t *prev_s = reinterpret_cast<uint32_t *>(run_s + R1 * 1024);
-    uint32_t *stage_s = prev_s + R1 * 32;
-    const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(stage_s) + lane * 4;
-    const size_t frame_words = (size_t)H * Wb;
-    // cp.async prefetch of one frame's NR bit rows (rows replicated outside the image, as medianBlur does)
-    auto prefetch = [&](int t, int buf) {
-        if (lane_in && t < T) {
-            const uint32_t *fb = bits + (size_t)t * frame_words + wx;
-            for (int r = 0; r < NR; r++) {
-                const int yc = min(max(y0 - 4 + r, 0), H - 1);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(stage_sa + (buf * NR + r) * 128),
-                             "l"(fb + (size_t)yc * Wb)
-                             : "memory");
-            }
-        }
-        cp_async_commit();
-    };
-    prefetch(0, 0);
-
-    if (dy_on) {  // load run counters of the region (zero outside the image)
-        for (int r = 0; r < R1; r++) {
-            const int y = y0 - 1 + r;
-            uint4 a = make_uint4(0, 0, 0, 0), b = a;
-            if (lane_in && y >= 0 && y < H) {
-                const uint4 *p = reinterpret_cast<const uint4 *>(run_in + (size_t)y * W + (size_t)wx * 32);
-                a = p[0]; b = p[1];
-            }
-            uint4 *q = reinterpret_cast<uint4 *>(run_s + r * 1024 + lane * 32);
-            q[0] = a; q[1] = b;
-            unsigned nz = 0;
-            const unsigned w8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-#pragma unroll
-                for (int bb = 0; bb < 4; bb++)
-                    if ((w8[k] >> (8 * bb)) & 0xffu) nz |= 1u << (4 * k + bb);
-            prev_s[r * 32 + lane] = nz;
-        }
-        __syncwarp();
-    }
-
     const unsigned FULL = 0xffffffffu;
-    for (int t = 0; t < T; t++) {
-        prefetch(t + 1, (t + 1) & 1);
-        cp_async_wait<1>();
-        __syncwarp();
-        const uint32_t *sb = stage_s + (t & 1) * NR * 32 + lane;
-        const int Ldy = (int)((dy0 + t + 1) < n ? (dy0 + t + 1) : n);
-        RowH h0 = {0, 0}, h1 = {0, 0};            // horizontal sums of b rows yy-2, yy-1
-        unsigned hd0 = 0, hd1 = 0;                // horizontal dilations of bin rows
-        unsigned he0 = FULL, he1 = FULL;          // horizontal erosions of dil rows
-        unsigned hm0 = FULL, hm1 = FULL;          // horizontal erosions of m rows
-        unsigned act_prev = 0;                    // act of row yy-4
-        for (int yy = y0 - 4; yy < y0 + rows + 4; yy++) {
-            // ---- b row yy ---------------------------------------------------------------------
-            unsigned bw = lane_in ? sb[(yy - (y0 - 4)) * 32] : 0u;
-            unsigned Lw = __shfl_up_sync(FULL, bw, 1), Rw = __shfl_down_sync(FULL, bw, 1);
-            if (wx == 0) Lw = (bw & 1u) << 31;
-            if (wx == Wb - 1) Rw = bw >> 31;
-            const unsigned l = (bw << 1) | (Lw >> 31), r = (bw >> 1) | (Rw << 31);
-            RowH h2;
-            h2.s = l ^ bw ^ r;
-            h2.c = maj3(l, bw, r);
-            // ---- bin row yy-1 = majority of the 9 bits (>= 5) --------------------------------
-            unsigned bin = 0;
-            {
-                const int y = yy - 1;
-                if (lane_in && y >= 0 && y < H) {
-                    const unsigned ones = h0.s ^ h1.s ^ h2.s, c1 = maj3(h0.s, h1.s, h2.s);
-                    const unsigned twos = h0.c ^ h1.c ^ h2.c, c2 = maj3(h0.c, h1.c, h2.c);
-                    const unsigned t0b = c1 ^ twos, t1b = c1 & twos;  // weights 2 and 4
-                    bin = (t1b & c2) | ((t1b ^ c2) & (t0b | ones));
-                }
-            }
-            h0 = h1; h1 = h2;
-            // ---- dil row yy-2 (outside the image: ones, ignored by the erosion) ---------------
-            unsigned hd2, dil;
-            {
-                const unsigned Lb = __shfl_up_sync(FULL, bin, 1), Rb = __shfl_down_sync(FULL, bin, 1);
-                hd2 = bin | (bin << 1) | (Lb >> 31) | (bin >> 1) | (Rb << 31);
-                const int y = yy - 2;
-                dil = (lane_in && y >= 0 && y < H) ? (hd0 | hd1 | hd2) : FULL;
-                hd0 = hd1; hd1 = hd2;
-            }
-            // ---- act row yy-3 = erosion of dil --------------------------------------------------
-            unsigned act;
-            {
-                const unsigned Ld = __shfl_up_sync(FULL, dil, 1), Rd = __shfl_down_sync(FULL, dil, 1);
-                const unsigned he2 = dil & ((dil << 1) | (Ld >> 31)) & ((dil >> 1) | (Rd << 31));
-                const int y = yy - 3;
-                act = (lane_in && y >= 0 && y < H) ? (he0 & he1 & he2) : 0u;
-                he0 = he1; he1 = he2;
-            }
-            // ---- dynamic mask: run-length counters of row yy-3, m = run < Ldy -----------------
-            unsigned out_bits;
-            if (dy_on) {
-                unsigned m = FULL;
-                const int rr = yy - 3 - (y0 - 1);  // row inside the run region
-                if (rr >= 0 && rr < R1) {
-                    const unsigned prev = prev_s[rr * 32 + lane];
-                    unsigned touch = act | prev;
-                    uint8_t *rp = run_s + rr * 1024 + lane * 32;
-                    while (touch) {
-                        const int b = __ffs(touch) - 1;
-                        touch &= touch - 1;
-                        int v = rp[b];
-                        v = ((act >> b) & 1u) ? min(v + 1, 255) : 0;
-                        rp[b] = (uint8_t)v;
-                        if (v >= Ldy) m &= ~(1u << b);
-                    }
-                    prev_s[rr * 32 + lane] = act;
-                }
-                const unsigned Lm = __shfl_up_sync(FULL, m, 1), Rm = __shfl_down_sync(FULL, m, 1);
-                const unsigned hm2 = m & ((m << 1) | (Lm >> 31)) & ((m >> 1) | (Rm << 31));
-                out_bits = act_prev & hm0 & hm1 & hm2;  // row yy-4
-                hm0 = hm1; hm1 = hm2;
-                act_prev = act;
-            } else {
-                out_bits = act;  // row yy-3 ; emitted one iteration earlier than with dy
-            }
-            const int yo = dy_on ? yy - 4 : yy - 3;
-            if (lane_out && yo >= y0 && yo < y0 + rows && yo < H) {
-                uint4 a = make_uint4(0, 0, 0, 0), b = a;
-                if (out_bits) {
-                    unsigned w8[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const unsigned nib = (out_bits >> (4 * k)) & 0xfu;
-                        w8[k] = ((nib & 1u) ? 0xffu : 0u) | ((nib & 2u) ? 0xff00u : 0u) |
-                                ((nib & 4u) ? 0xff0000u : 0u) | ((nib & 8u) ? 0xff000000u : 0u);
-                    }
-                    a = make_uint4(w8[0], w8[1], w8[2], w8[3]);
-                    b = make_uint4(w8[4], w8[5], w8[6], w8[7]);
-                    unsigned ob = out_bits;
-                    while (ob) {
-                        const int bpos = __ffs(ob) - 1;
-                        ob &= ob - 1;
-                        const unsigned slot = atomicAdd(npoints + t, 1u);
-                        if (slot < (unsigned)cap)
-                            points[(size_t)t * cap + slot] = ((unsigned)yo << 16) | (unsigned)(wx * 32 + bpos);
-                    }
-                }
-                uint4 *o = reinterpret_cast<uint4 *>(dst + (size_t)t * W * H + (size_t)yo * W + (size_t)wx * 32);
-                __stcs(o, a);
-                __stcs(o + 1, b);
+    const uint32_t *fb = bits + (size_t)t * H * Wb + (lane_in ? wx : 0);
+    uint32_t *ob = ring.frame(dy0 + t) + (lane_in ? wx : 0);
+    RowH h0 = {0, 0}, h1 = {0, 0};
+    unsigned hd0 = 0, hd1 = 0, he0 = FULL, he1 = FULL;
+    // rows y0-3 .. y0+rows+2 of b are needed; software-prefetch one row ahead
+    unsigned nxt = lane_in ? __ldg(fb + (size_t)min(max(y0 - 3, 0), H - 1) * Wb) : 0u;
+    for (int yy = y0 - 3; yy < y0 + rows + 3; yy++) {
+        const unsigned bw = nxt;
+        if (yy + 1 < y0 + rows + 3) nxt = lane_in ? __ldg(fb + (size_t)min(max(yy + 1, 0), H - 1) * Wb) : 0u;
+        // ---- horizontal sums of b row yy (rows/cols replicated outside the image: medianBlur) --
+        unsigned Lw = __shfl_up_sync(FULL, bw, 1), Rw = __shfl_down_sync(FULL, bw, 1);
+        if (wx == 0) Lw = (bw & 1u) << 31;
+        if (wx == Wb - 1) Rw = bw >> 31;
+        const unsigned l = (bw << 1) | (Lw >> 31), r = (bw >> 1) | (Rw << 31);
+        RowH h2;
+        h2.s = l ^ bw ^ r;
+        h2.c = maj3(l, bw, r);
+        // ---- bin row yy-1 = at least 5 of the 9 bits ----------------------------------------
+        unsigned bin = 0;
+        {
+            const int y = yy - 1;
+            if (lane_in && y >= 0 && y < H) {
+                const unsigned ones = h0.s ^ h1.s ^ h2.s, c1 = maj3(h0.s, h1.s, h2.s);
+                const unsigned twos = h0.c ^ h1.c ^ h2.c, c2 = maj3(h0.c, h1.c, h2.c);
+                const unsigned t0b = c1 ^ twos, t1b = c1 & twos;  // weights 2 and 4
+                bin = (t1b & c2) | ((t1b ^ c2) & (t0b | ones));
             }
         }
-        __syncwarp();  // all lanes done with this frame's staged rows before they are overwritten
+        h0 = h1; h1 = h2;
+        // ---- dil row yy-2 (outside the image: ones, ignored by the erosion) -------------------
+        unsigned dil;
+        {
+            const unsigned Lb = __shfl_up_sync(FULL, bin, 1), Rb = __shfl_down_sync(FULL, bin, 1);
+            const unsigned hd2 = bin | (bin << 1) | (Lb >> 31) | (bin >> 1) | (Rb << 31);
+            const int y = yy - 2;
+            dil = (lane_in && y >= 0 && y < H) ? (hd0 | hd1 | hd2) : FULL;
+            hd0 = hd1; hd1 = hd2;
+        }
+        // ---- act row yy-3 = erosion of dil ---------------------------------------------------
+        {
+            const unsigned Ld = __shfl_up_sync(FULL, dil, 1), Rd = __shfl_down_sync(FULL, dil, 1);
+            const unsigned he2 = dil & ((dil << 1) | (Ld >> 31)) & ((dil >> 1) | (Rd << 31));
+            const int y = yy - 3;
+            if (lane_out && y >= y0 && y < y0 + rows && y < H) ob[(size_t)y * Wb] = he0 & he1 & he2;
+            he0 = he1; he1 = he2;
+        }
     }
-    cp_async_wait<0>();
-    if (dy_on) {  // persist the run counters of the rows this warp owns
-        __syncwarp();
-        for (int r = 1; r <= rows; r++) {
-            const int y = y0 - 1 + r;
-            if (lane_out && y < H) {
-                const uint4 *q = reinterpret_cast<const uint4 *>(run_s + r * 1024 + lane * 32);
-                uint4 *p = reinterpret_cast<uint4 *>(run_out + (size_t)y * W + (size_t)wx * 32);
-                p[0] = q[0]; p[1] = q[1];
+}
+
+__device__ __forceinline__ unsigned nib_to_bytes(unsigned nib) {
+    return ((nib & 1u) ? 0xffu : 0u) | ((nib & 2u) ? 0xff00u : 0u) | ((nib & 4u) ? 0xff0000u : 0u) |
+           ((nib & 8u) ? 0xff000000u : 0u);
+}
+
+__global__ void __launch_bounds__(SP_WARPS * 32)
+dst_kernel(ActRing ring, int W, int H, int T, int n, long long dy0, int dy_on, int rows, int strips,
+           int bands, uint8_t *__restrict__ dst, unsigned *__restrict__ npoints,
+           uint32_t *__restrict__ points, int cap) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x * SP_WARPS + warp;
+    const int t = blockIdx.y;
+    if (tile >= strips * bands) return;
+    const int strip = tile % strips, band = tile / strips;
+    const int Wb = W >> 5;
+    const int wx = strip * SP_USE - 1 + lane;
+    const bool lane_in = wx >= 0 && wx < Wb;
+    const bool lane_out = lane_in && lane >= 1 && lane <= SP_USE;
+    const int y0 = band * rows;
+    const unsigned FULL = 0xffffffffu;
+    const long long d = dy0 + t;
+    const int L = (int)((d + 1) < n ? (d + 1) : n);  // SlidingWindow.length of the dy window
+    const uint32_t *cur = ring.frame(d) + (lane_in ? wx : 0);
+    unsigned hm0 = FULL, hm1 = FULL, act_prev = 0;
+    const int ylast = dy_on ? y0 + rows + 1 : y0 + rows;
+    for (int yy = dy_on ? y0 - 1 : y0; yy < ylast; yy++) {
+        const bool row_in = yy >= 0 && yy < H;
+        const unsigned act = (lane_in && row_in) ? __ldg(cur + (size_t)yy * Wb) : 0u;
+        unsigned out_bits;
+        int yo;
+        if (dy_on) {
+            // m = not(on in all of the last L frames); the loop ends as soon as the AND is empty
+            unsigned acc = act;
+            for (int k = 1; k < L && acc; k++) acc &= __ldg(ring.frame(d - k) + wx + (size_t)yy * Wb);
+            const unsigned m = ~acc;  // rows / columns outside the image: act = 0 -> m = ones
+            const unsigned Lm = __shfl_up_sync(FULL, m, 1), Rm = __shfl_down_sync(FULL, m, 1);
+            const unsigned hm2 = m & ((m << 1) | (Lm >> 31)) & ((m >> 1) | (Rm << 31));
+            out_bits = act_prev & hm0 & hm1 & hm2;  // row yy-1
+            hm0 = hm1; hm1 = hm2;
+            act_prev = act;
+            yo = yy - 1;
+        } else {
+            out_bits = act;
+            yo = yy;
+        }
+        if (lane_out && yo >= y0 && yo < y0 + rows && yo < H) {
+            uint4 a = make_uint4(0, 0, 0, 0), b = a;
+            if (out_bits) {
+                a = make_uint4(nib_to_bytes(out_bits & 15u), nib_to_bytes((out_bits >> 4) & 15u),
+                               nib_to_bytes((out_bits >> 8) & 15u), nib_to_bytes((out_bits >> 12) & 15u));
+                b = make_uint4(nib_to_bytes((out_bits >> 16) & 15u), nib_to_bytes((out_bits >> 20) & 15u),
+                               nib_to_bytes((out_bits >> 24) & 15u), nib_to_bytes(out_bits >> 28));
+                const unsigned c = __popc(out_bits);
+                unsigned slot = atomicAdd(npoints + t, c);
+                unsigned ob = out_bits;
+                while (ob) {
+                    const int bpos = __ffs(ob) - 1;
+                    ob &= ob - 1;
+                    if (slot < (unsigned)cap)
+                        points[(size_t)t * cap + slot] = ((unsigned)yo << 16) | (unsigned)(wx * 32 + bpos);
+                    slot++;
+                }
             }
+            uint4 *o = reinterpret_cast<uint4 *>(dst + (size_t)t * W * H + (size_t)yo * W + (size_t)wx * 32);
+            __stcs(o, a);
+            __stcs(o + 1, b);
         }
     }
 }
@@ -397,13 +350,11 @@ static inline int stream_state_init(StreamState &s, int W, int H, int n, int dev
         cudaGetLastError();
         return 0;  // fall back to the generic per-frame kernel
     }
-    s.sp_rows = 8;
-    const size_t sp_smem = (size_t)SP_WARPS * ((s.sp_rows + 2) * (1024 + 128) + 2 * (s.sp_rows + 8) * 128);
+    s.sp_rows = 32;
     if (cudaFuncSetAttribute(temporal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess ||
         cudaFuncSetAttribute(temporal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess ||
         cudaFuncSetAttribute(temporal_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
-        cudaFuncSetAttribute(temporal_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
-        cudaFuncSetAttribute(spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem) != cudaSuccess)
+        cudaFuncSetAttribute(temporal_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess)
         return -1;
     s.ok = 1;
     return 0;
@@ -411,12 +362,10 @@ static inline int stream_state_init(StreamState &s, int W, int H, int n, int dev
 
 static inline bool stream_kernel_supported(const StreamState &s, int T) { return s.ok && T >= 1 && T <= s.max_batch; }
 
-// Launches temporal + spatial kernels for frames timer0 .. timer0+T-1. Run counters are read from
-// run_in at the start and written to run_out at the end (ping-pong: tiles of a later wave may still
-// be loading their halo while an earlier tile stores). Returns 0 / -1; *launches gets the number of kernel launches.
+// Launches temporal + act + dst kernels for frames timer0 .. timer0+T-1 (dy indices dy0 ..).
+// Returns 0 / -1; *launches gets the number of kernel launches.
 static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long timer0, long long dy0, int T,
-                                       int dy_on, const int *d_thr, const uint8_t *run_in, uint8_t *run_out,
-                                       uint8_t *dst,
+                                       int dy_on, const int *d_thr, ActRing ring, uint8_t *dst,
                                        unsigned *npoints, uint32_t *points, int cap, cudaStream_t st,
                                        int *launches) {
     const int HW16 = (int)((size_t)s.W * s.H / 16);
@@ -431,10 +380,12 @@ static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long t
     const int Wb = s.W / 32;
     const int strips = (Wb + SP_USE - 1) / SP_USE, bands = (s.H + s.sp_rows - 1) / s.sp_rows;
     const int tiles = strips * bands;
-    const size_t sp_smem = (size_t)SP_WARPS * ((s.sp_rows + 2) * (1024 + 128) + 2 * (s.sp_rows + 8) * 128);
-    spatial_kernel<<<(tiles + SP_WARPS - 1) / SP_WARPS, SP_WARPS * 32, sp_smem, st>>>(
-        s.d_bits, s.W, s.H, T, s.n, dy0, dy_on, s.sp_rows, strips, bands, run_in, run_out, dst, npoints, points, cap);
+    dim3 g((tiles + SP_WARPS - 1) / SP_WARPS, T);
+    act_kernel<<<g, SP_WARPS * 32, 0, st>>>(s.d_bits, s.W, s.H, T, s.sp_rows, strips, bands, ring, dy0);
     if (cudaGetLastError() != cudaSuccess) return -1;
-    *launches = 2;
+    dst_kernel<<<g, SP_WARPS * 32, 0, st>>>(ring, s.W, s.H, T, s.n, dy0, dy_on, s.sp_rows, strips, bands, dst,
+                                            npoints, points, cap);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    *launches = 3;
     return 0;
 }

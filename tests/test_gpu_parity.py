@@ -72,7 +72,7 @@ def test_batched_api_matches_reference_golden(name, batch, stream_kernel):
         res, dst = det.detect_many(g["frames"][s:s + batch], return_dst=True)
         nb = len(res)
         streamed = stream_kernel and W % 32 == 0 and 2 <= g["n"] <= 128
-        assert det._eng.fused_time()[1] == (2 if streamed else nb)  # temporal+spatial vs one launch per frame
+        assert det._eng.fused_time()[1] == (3 if streamed else nb)  # temporal+spatial vs one launch per frame
         for i, (lines, cls) in enumerate(res):
             _check_frame(det, g, s + i, lines, cls, dst[i], det.last_infos[i])
             raw = ragged_get(g["raw_lines"], g["raw_offs"], s + i)
