@@ -96,12 +96,216 @@ __device__ __forceinline__ int find_key(const uint32_t *keys, int N, uint32_t ke
 }
 
 // ------------------------------------------------------------------------------------------
-// Batch path
+// Visiting order. OpenCV draws idx = rng % count and swap-removes; an in-place Fisher-Yates over an
+// index array leaves the visit sequence in idx[N-1], idx[N-2], ..., idx[0].  It depends only on
+// the NUMBER of on-pixels, so it is produced for all frames of the batch up front (one CTA per
+// frame, one lane runs the sequential generator in shared memory, the warp writes it out).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+ppht_order_kernel(int T, int cap, const unsigned *__restrict__ npoints, uint16_t *__restrict__ order) {
+    extern __shared__ uint16_t o_sm[];
+    const int t = blockIdx.x, lane = threadIdx.x;
+    const unsigned Nu = npoints[t];
+    if (Nu == 0 || Nu > (unsigned)cap) return;
+    const int N = (int)Nu;
+    for (int i = lane; i < N; i += 32) o_sm[i] = (uint16_t)i;
+    __syncwarp();
+    if (lane == 0) {
+        unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
+        for (int count = N; count > 0; count--) {
+            state = (unsigned long long)(unsigned)state * 4164903690ull + (unsigned)(state >> 32);
+            const unsigned r = (unsigned)state % (unsigned)count;
+            const uint16_t a = o_sm[r], b = o_sm[count - 1];
+            o_sm[r] = b;
+            o_sm[count - 1] = a;
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < N; i += 32) order[(size_t)t * cap + i] = o_sm[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// Tier 1: accumulator in SHARED memory.  Row n only needs the rho interval [min_n, max_n] that the
+// frame's points project onto, so the table has sum_n (max_n - min_n + 1) int16 cells (un-voting a
+// long line drives its cell to minus the line length, so int8 is not enough); when that fits (a
+// streak up to ~800 px long does) the whole PPHT of the frame runs on-chip.  Frames whose table
+// would not fit are flagged (-2) for tier 2.
+// ------------------------------------------------------------------------------------------
+#define HOUGH_TABLE_BYTES (186 * 1024)
+
+__global__ void __launch_bounds__(HOUGH_THREADS)
+hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
+                  const uint32_t *__restrict__ points, const uint16_t *__restrict__ order,
+                  int32_t *lines_out, int *nlines_out) {
+    extern __shared__ uint32_t h_sm[];
+    uint32_t *keys = h_sm;                                            // [cap]
+    uint16_t *idx = reinterpret_cast<uint16_t *>(keys + P.cap);       // [cap] visiting order
+    uint16_t *wl = idx + P.cap;                                       // [cap] pixels of the current line
+    uint32_t *rm = reinterpret_cast<uint32_t *>(wl + P.cap);          // [cap/32] removed bits
+    int16_t *table = reinterpret_cast<int16_t *>(rm + P.cap / 32);    // [HOUGH_TABLE_BYTES / 2]
+    __shared__ int s_red[2][HOUGH_THREADS / 32];
+    __shared__ unsigned s_on[HOUGH_THREADS / 32], s_inb[HOUGH_THREADS / 32];
+    __shared__ int s_ctl[8];
+    __shared__ int s_base[MDB_HOUGH_ANGLES + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = P.W, H = P.H;
+
+    for (int t = blockIdx.x; t < T; t += gridDim.x) {
+        const unsigned Nu = npoints[t];
+        if (Nu == 0) { if (tid == 0) nlines_out[t] = 0; continue; }
+        if (Nu > (unsigned)P.cap) { if (tid == 0) nlines_out[t] = -1; continue; }  // overflow path
+        const int N = (int)Nu;
+        const int line_gap = line_gap_of(P, Nu);
+        int32_t *lines = lines_out + (size_t)t * P.max_lines * 4;
+        int np2 = 1;
+        while (np2 < N) np2 <<= 1;
+        for (int i = tid; i < np2; i += HOUGH_THREADS)
+            keys[i] = i < N ? points[(size_t)t * P.cap + i] : 0xFFFFFFFFu;
+        for (int i = tid; i < (N + 31) / 32; i += HOUGH_THREADS) rm[i] = 0;
+        for (int i = tid; i < N; i += HOUGH_THREADS) idx[i] = order[(size_t)t * P.cap + i];
+        if (tid == 0) { s_ctl[2] = 0; s_ctl[3] = 0; }
+        __syncthreads();
+        bitonic_sort_u32(keys, np2, tid, HOUGH_THREADS);
+        // per-angle rho interval of this frame's points
+        int mn = INT_MAX, mx = INT_MIN;
+        if (tid < MDB_HOUGH_ANGLES) {
+            for (int i = 0; i < N; i++) {
+                const uint32_t k = keys[i];
+                const int r = rho_of(k & 0xffffu, k >> 16, tid);
+                mn = min(mn, r); mx = max(mx, r);
+            }
+            s_base[tid + 1] = mx - mn + 1;
+        }
+        if (tid == 0) s_base[0] = 0;
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+            for (int k = 1; k <= MDB_HOUGH_ANGLES; k++) { acc += s_base[k]; s_base[k] = acc; }
+        }
+        __syncthreads();
+        const int total = s_base[MDB_HOUGH_ANGLES];
+        if (total > HOUGH_TABLE_BYTES / 2) {  // does not fit on-chip: tier 2
+            if (tid == 0) nlines_out[t] = -2;
+            __syncthreads();
+            continue;
+        }
+        for (int i = tid; i < (total + 1) / 2; i += HOUGH_THREADS) reinterpret_cast<uint32_t *>(table)[i] = 0;
+        int16_t *myrow = table + (tid < MDB_HOUGH_ANGLES ? s_base[tid] - mn : 0);
+        __syncthreads();
+
+        int par = 0;
+        bool sat = false;
+        for (int s = N - 1; s >= 0; s--) {
+            const int pi = idx[s];
+            if ((rm[pi >> 5] >> (pi & 31)) & 1u) continue;  // removed by an earlier line (uniform)
+            const uint32_t key = keys[pi];
+            const int x = key & 0xffffu, y = key >> 16;
+            int best = INT_MIN;
+            if (tid < MDB_HOUGH_ANGLES) {
+                const int r = rho_of(x, y, tid);
+                const int v = (int)myrow[r] + 1;
+                myrow[r] = (int16_t)v;
+                sat |= v >= 32767;
+                best = v * 256 + (255 - tid);  // max value first, lowest angle on ties
+            }
+            best = __reduce_max_sync(0xffffffffu, best);
+            if (lane == 0) s_red[par][warp] = best;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < HOUGH_THREADS / 32; k++) best = max(best, s_red[par][k]);
+            par ^= 1;
+            if ((best >> 8) < P.threshold) continue;
+            const int max_n = 255 - (best & 255);
+
+            // ---- line: find both ends (mask unchanged meanwhile), 256 steps per round ----------
+            Walk wk;
+            wk.init(x, y, max_n);
+            int ends[2];
+            for (int k = 0; k < 2; k++) {
+                int last_on = 0;
+                bool done = false;
+                for (int base = 0; !done; base += HOUGH_THREADS) {
+                    const int i = base + tid;
+                    int j1, i1;
+                    wk.at(k, i, j1, i1);
+                    const bool inb = j1 >= 0 && j1 < W && i1 >= 0 && i1 < H;
+                    bool on = false;
+                    if (inb) {
+                        const int f = find_key(keys, N, ((unsigned)i1 << 16) | (unsigned)j1);
+                        on = f >= 0 && !((rm[f >> 5] >> (f & 31)) & 1u);
+                    }
+                    const unsigned bo = __ballot_sync(0xffffffffu, on), bi = __ballot_sync(0xffffffffu, inb);
+                    if (lane == 0) { s_on[warp] = bo; s_inb[warp] = bi; }
+                    __syncthreads();
+                    for (int w = 0; w < HOUGH_THREADS / 32 && !done; w++) {
+                        unsigned onw = s_on[w];
+                        const unsigned inw = s_inb[w];
+                        const int wbase = base + w * 32;
+                        const int ob = inw == 0xffffffffu ? INT_MAX : wbase + __ffs(~inw) - 1;
+                        while (onw) {
+                            const int io = wbase + __ffs(onw) - 1;
+                            onw &= onw - 1;
+                            if (io - last_on - 1 > line_gap) { done = true; break; }
+                            last_on = io;
+                        }
+                        if (!done && (ob != INT_MAX || wbase + 31 - last_on > line_gap)) done = true;
+                    }
+                    __syncthreads();
+                }
+                ends[k] = last_on;
+            }
+            int ex0, ey0, ex1, ey1;
+            wk.at(0, ends[0], ex0, ey0);
+            wk.at(1, ends[1], ex1, ey1);
+            const bool good = abs(ex1 - ex0) >= P.min_len || abs(ey1 - ey0) >= P.min_len;
+            if (tid == 0) s_ctl[1] = 0;
+            __syncthreads();
+            for (int k = 0; k < 2; k++)
+                for (int i = tid + k; i <= ends[k]; i += HOUGH_THREADS) {  // k=1 skips the shared start pixel
+                    int j1, i1;
+                    wk.at(k, i, j1, i1);
+                    const int f = find_key(keys, N, ((unsigned)i1 << 16) | (unsigned)j1);
+                    if (f >= 0 && !((rm[f >> 5] >> (f & 31)) & 1u)) {
+                        atomicOr(&rm[f >> 5], 1u << (f & 31));
+                        if (good) wl[atomicAdd(&s_ctl[1], 1)] = (uint16_t)f;
+                    }
+                }
+            __syncthreads();
+            if (good) {
+                const int nw = s_ctl[1];
+                if (tid < MDB_HOUGH_ANGLES)
+                    for (int q = 0; q < nw; q++) {
+                        const uint32_t k2 = keys[wl[q]];
+                        const int r = rho_of(k2 & 0xffffu, k2 >> 16, tid);
+                        const int v = (int)myrow[r] - 1;
+                        myrow[r] = (int16_t)v;
+                        sat |= v <= -32768;
+                    }
+                if (tid == 0) {
+                    const int li = s_ctl[2];
+                    if (li < P.max_lines) {
+                        lines[4 * li] = ex0; lines[4 * li + 1] = ey0;
+                        lines[4 * li + 2] = ex1; lines[4 * li + 3] = ey1;
+                    }
+                    s_ctl[2] = li + 1;
+                }
+            }
+            __syncthreads();
+        }
+        if (sat) s_ctl[3] = 1;
+        __syncthreads();
+        if (tid == 0) nlines_out[t] = s_ctl[3] ? -2 : s_ctl[2];  // a saturated cell (impossible for N <= cap): tier 2
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Tier 2: same algorithm with the accumulator in global memory ([180][numrho] int32 per slot)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(HOUGH_THREADS)
-hough_batch_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
+hough_tier2_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
                    const uint32_t *__restrict__ points, int32_t *accum_slots, int32_t *lines_out,
-                   int *nlines_out) {
+                   int *nlines_out, long long *prof) {
     extern __shared__ uint32_t h_sm[];
     uint32_t *keys = h_sm;                                            // [cap]
     uint16_t *idx = reinterpret_cast<uint16_t *>(keys + P.cap);       // [cap] visiting order
@@ -117,9 +321,10 @@ hough_batch_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
 
     for (int t = blockIdx.x; t < T; t += gridDim.x) {
         const unsigned Nu = npoints[t];
-        if (Nu == 0) { if (tid == 0) nlines_out[t] = 0; continue; }
-        if (Nu > (unsigned)P.cap) { if (tid == 0) nlines_out[t] = -1; continue; }  // overflow path
+        if (nlines_out[t] != -2) continue;  // only frames the shared-memory tier handed over
+        __syncthreads();
         const int N = (int)Nu;
+        long long pc0 = clock64(), p_setup = 0, p_vote = 0, p_walk = 0, p_unvote = 0, p_reset = 0, n_vote = 0, n_line = 0;
         const int line_gap = line_gap_of(P, Nu);
         int32_t *lines = lines_out + (size_t)t * P.max_lines * 4;
         int np2 = 1;
@@ -151,7 +356,9 @@ hough_batch_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(myrow + rho_of(k & 0xffffu, k >> 16, tid)));
             }
         int par = 0;
+        p_setup = clock64() - pc0;
         for (int s = N - 1; s >= 0; s--) {
+            long long c0 = clock64();
             const int pi = idx[s];
             if (tid < MDB_HOUGH_ANGLES && s >= HOUGH_PREFETCH) {
                 const uint32_t k = keys[idx[s - HOUGH_PREFETCH]];
@@ -173,7 +380,9 @@ hough_batch_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
 #pragma unroll
             for (int k = 0; k < HOUGH_THREADS / 32; k++) best = max(best, s_red[par][k]);
             par ^= 1;
+            p_vote += clock64() - c0; n_vote++;
             if ((best >> 8) < P.threshold) continue;
+            c0 = clock64(); n_line++;
             const int max_n = 255 - (best & 255);
 
             // ---- line: find both ends (mask unchanged meanwhile), 256 steps per round ----------
@@ -225,6 +434,7 @@ hough_batch_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
             // ---- second pass: clear the on-pixels up to both ends; un-vote them if the line counts
             if (tid == 0) s_ctl[1] = 0;
             __syncthreads();
+            p_walk += clock64() - c0; c0 = clock64();
             for (int k = 0; k < 2; k++)
                 for (int i = tid + k; i <= ends[k]; i += HOUGH_THREADS) {  // k=1 skips the shared start pixel
                     int j1, i1;
@@ -253,7 +463,9 @@ hough_batch_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
                 }
             }
             __syncthreads();
+            p_unvote += clock64() - c0;
         }
+        long long c1 = clock64();
         // reset: zero every accumulator cell a point of this frame can have touched
         for (int q = tid; q < N * MDB_HOUGH_ANGLES; q += HOUGH_THREADS) {
             const int i = q / MDB_HOUGH_ANGLES, n = q % MDB_HOUGH_ANGLES;
@@ -261,7 +473,13 @@ hough_batch_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
             accum[(size_t)n * numrho + half + rho_of(k & 0xffffu, k >> 16, n)] = 0;
         }
         __syncthreads();
+        p_reset = clock64() - c1;
         if (tid == 0) nlines_out[t] = s_ctl[2];
+        if (prof && tid == 0) {
+            long long *o = prof + (size_t)t * 10;
+            o[0] = N; o[1] = p_setup; o[2] = p_vote; o[3] = p_walk; o[4] = p_unvote; o[5] = p_reset;
+            o[6] = n_vote; o[7] = n_line; o[8] = clock64() - pc0; o[9] = s_ctl[2];
+        }
         __syncthreads();
     }
 }

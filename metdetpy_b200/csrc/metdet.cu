@@ -57,6 +57,9 @@ struct mdb_detector {
     uint32_t *d_bitmap = nullptr, *d_walk = nullptr;
     uint32_t *d_okeys = nullptr, *d_oidx = nullptr;  // overflow path scratch (lazy)
     unsigned *d_on = nullptr;
+    uint16_t *d_order = nullptr;  // [T][cap] PPHT visiting order per frame
+    int sm_count = 148;
+    long long *d_prof = nullptr;  // optional per-frame PPHT phase cycle counters (debug)
     // stream-kernel state (lazy)
     StreamState sk;
     // pinned host mirrors
@@ -109,7 +112,7 @@ static void free_all(mdb_detector *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void *dev[] = {h->d_ring, h->d_mask, h->d_dst, h->d_act, h->d_state, h->d_noise,
                    h->d_thr, h->d_nlines, h->d_thrf, h->d_snr, h->d_npoints, h->d_points,
-                   h->d_lines, h->d_accum, h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_on};
+                   h->d_lines, h->d_accum, h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_on, h->d_prof, h->d_order};
     for (void *p : dev)
         if (p) cudaFree(p);
     stream_state_free(h->sk);
@@ -162,12 +165,11 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     for (size_t i = 0; i < h->HW; i++) area += mask[i];
     hp.mask_area = (double)area;
     hp.cap = MDB_POINT_CAP; hp.max_lines = MDB_MAX_LINES; hp.walk_cap = h->W + h->H + 2;
-    // Hough slots: one accumulator per frame in flight; bounded by what can be resident (6 CTAs/SM)
-    // and by a 12 GB memory budget
+    // tier-2 Hough slots (global-memory accumulators): one per frame in flight, 4 GB budget
     {
         const size_t per_slot = (size_t)MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t);
-        size_t s = std::min<size_t>((size_t)T, (size_t)prop.multiProcessorCount * 6);
-        s = std::min<size_t>(s, std::max<size_t>(1, (12ull << 30) / per_slot));
+        size_t s = std::min<size_t>((size_t)T, (size_t)prop.multiProcessorCount * 2);
+        s = std::min<size_t>(s, std::max<size_t>(1, (4ull << 30) / per_slot));
         h->slots = (int)s;
     }
 
@@ -214,6 +216,8 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     ALLOC(h->d_bitmap, bm_words * sizeof(uint32_t));           // overflow path only
     ALLOC(h->d_walk, (size_t)hp.walk_cap * sizeof(uint32_t));  // overflow path only
     ALLOC(h->d_on, sizeof(unsigned));
+    ALLOC(h->d_order, (size_t)T * MDB_POINT_CAP * sizeof(uint16_t));
+    h->sm_count = prop.multiProcessorCount;
     CKH(cudaMemsetAsync(h->d_ring, 0, (size_t)h->R * h->HW, h->stream));
     CKH(cudaMemsetAsync(h->d_act, 0, (size_t)h->RA * h->H * h->Wb * sizeof(uint32_t), h->stream));
     CKH(cudaMemsetAsync(h->d_accum, 0, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t), h->stream));
@@ -248,8 +252,10 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
         trig[2 * k + 1] = (float)sin((double)k * (double)theta);
     }
     CKH(cudaMemcpyToSymbolAsync(c_trig, trig, sizeof trig, 0, cudaMemcpyHostToDevice, h->stream));
-    CKH(cudaFuncSetAttribute(hough_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CKH(cudaFuncSetAttribute(hough_tier2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              HOUGH_SMEM_BYTES));
+    CKH(cudaFuncSetAttribute(hough_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             HOUGH_SMEM_BYTES + HOUGH_TABLE_BYTES));
     CKH(cudaStreamSynchronize(h->stream));
     {
         int rc = stream_state_init(h->sk, h->W, h->H, h->n, cfg->device, cfg->max_batch);
@@ -329,9 +335,12 @@ static int launch_fused(mdb_detector *h, int T, long long timer0, long long dy0)
 
 static int launch_hough_and_copy(mdb_detector *h, int T) {
     const int grid = std::min(T, h->slots);
-    hough_batch_kernel<<<grid, HOUGH_THREADS, HOUGH_SMEM_BYTES, h->stream>>>(
-        h->hp, T, h->d_npoints, h->d_points, h->d_accum, h->d_lines, h->d_nlines);
-    h->launches += 1;
+    ppht_order_kernel<<<T, 32, MDB_POINT_CAP * 2, h->stream>>>(T, MDB_POINT_CAP, h->d_npoints, h->d_order);
+    hough_smem_kernel<<<std::min(T, h->sm_count), HOUGH_THREADS, HOUGH_SMEM_BYTES + HOUGH_TABLE_BYTES, h->stream>>>(
+        h->hp, T, h->d_npoints, h->d_points, h->d_order, h->d_lines, h->d_nlines);
+    hough_tier2_kernel<<<grid, HOUGH_THREADS, HOUGH_SMEM_BYTES, h->stream>>>(
+        h->hp, T, h->d_npoints, h->d_points, h->d_accum, h->d_lines, h->d_nlines, h->d_prof);
+    h->launches += 3;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->h_thr, h->d_thr, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(h->h_thrf, h->d_thrf, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -590,8 +599,21 @@ extern "C" int mdb_get_fused_time(mdb_handle h, float *ms, int32_t *launches) {
 }
 
 // internal knob used by the parity tests to force the generic per-frame kernel
+extern "C" int mdb_debug_hough_profile(mdb_handle h, long long *out, int T) {
+    if (!h || !out || !h->d_prof) return fail(MDB_ERR_INVALID, "mdb_debug_hough_profile: not enabled");
+    CK(cudaMemcpy(out, h->d_prof, (size_t)T * 10 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return MDB_OK;
+}
+
 extern "C" int mdb_set_option(mdb_handle h, const char *name, int value) {
     if (!h || !name) return fail(MDB_ERR_INVALID, "mdb_set_option: null argument");
+    if (!strcmp(name, "hough_profile")) {
+        if (value && !h->d_prof) {
+            CK(cudaMalloc((void **)&h->d_prof, (size_t)h->cfg.max_batch * 10 * sizeof(long long)));
+            CK(cudaMemset(h->d_prof, 0, (size_t)h->cfg.max_batch * 10 * sizeof(long long)));
+        }
+        return MDB_OK;
+    }
     if (!strcmp(name, "stream_kernel")) { h->use_stream_kernel = value; return MDB_OK; }
     return fail(MDB_ERR_INVALID, "mdb_set_option: unknown option %s", name);
 }
