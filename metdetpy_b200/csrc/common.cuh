@@ -8,14 +8,18 @@
 #define MDB_HOUGH_ANGLES 180
 #define MDB_POINT_CAP 4096  // per-frame point-list capacity of the shared-memory PPHT path
 
-// Where frame `t` (0-based global frame index) lives: slot t % R of the device frame ring.
+// Where frame `t` (0-based global frame index) lives: frames of the batch in flight may be read
+// straight from the caller's device buffer (`cur`, frame t0 at offset 0: zero-copy), everything
+// older -- and host-fed batches -- from slot t % R of the device frame ring.
 struct FrameSrc {
     const uint8_t *ring;
+    const uint8_t *cur;   // nullptr: every frame is in the ring
     const uint8_t *mask;  // {0,1} bytes, or nullptr when frames arrive already masked
+    long long t0;         // global index of cur's first frame
     int R;
     size_t HW;
     __device__ __forceinline__ const uint8_t *frame(long long t) const {
-        return ring + (size_t)(t % R) * HW;
+        return (cur && t >= t0) ? cur + (size_t)(t - t0) * HW : ring + (size_t)(t % R) * HW;
     }
     __device__ __forceinline__ unsigned px(long long t, size_t p) const {
         unsigned v = frame(t)[p];

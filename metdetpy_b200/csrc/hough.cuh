@@ -485,20 +485,64 @@ hough_tier2_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
 }
 
 // ------------------------------------------------------------------------------------------
-// Overflow path: one frame, keys already sorted in global memory (compact_ordered_kernel),
-// pixel bitmap in global memory, sequential walks.
+// Tier 3 (overflow path): dense masks beyond the shared-memory capacity.  One CTA walks the flagged
+// frames of the batch: ordered compaction of the frame's dst mask into a global point list (row-major
+// == sorted), visiting order and pixel bitmap in global memory, sequential walks.  Slow, rare, and
+// entirely on the device (no host round trip, so batches can stay pipelined).
 // ------------------------------------------------------------------------------------------
+__device__ int compact_ordered(const uint8_t *dst, int W, int H, uint32_t *keys) {
+    __shared__ unsigned c_wsum[HOUGH_THREADS / 32];
+    __shared__ unsigned c_base;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) c_base = 0;
+    __syncthreads();
+    const size_t HW = (size_t)W * H;
+    for (size_t start = 0; start < HW; start += HOUGH_THREADS * 8) {
+        const size_t p0 = start + (size_t)tid * 8;
+        unsigned bits = 0;
+        for (int k = 0; k < 8; k++)
+            if (p0 + k < HW && dst[p0 + k]) bits |= 1u << k;
+        const unsigned c = __popc(bits);
+        unsigned inc = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) c_wsum[w] = inc;
+        __syncthreads();
+        unsigned woff = 0, tot = 0;
+        for (int k = 0; k < HOUGH_THREADS / 32; k++) {
+            if (k < w) woff += c_wsum[k];
+            tot += c_wsum[k];
+        }
+        unsigned off = c_base + woff + inc - c;
+        for (int k = 0; k < 8; k++)
+            if (bits >> k & 1) {
+                const size_t p = p0 + k;
+                keys[off++] = ((unsigned)(p / W) << 16) | (unsigned)(p % W);
+            }
+        __syncthreads();
+        if (tid == 0) c_base += tot;
+        __syncthreads();
+    }
+    return (int)c_base;
+}
+
 __global__ void __launch_bounds__(HOUGH_THREADS)
-hough_global_kernel(HoughParams P, const unsigned *n_ptr, uint32_t *keys, uint32_t *idx, int32_t *accum,
-                    uint32_t *bitmap, uint32_t *walk, int32_t *lines_out, int *nlines_out) {
+hough_tier3_kernel(HoughParams P, int T, const uint8_t *dst, uint32_t *keys, uint32_t *idx, int32_t *accum,
+                   uint32_t *bitmap, uint32_t *walk, int32_t *lines_all, int *nlines_all) {
     __shared__ int s_red[HOUGH_THREADS / 32];
     __shared__ int s_ctl[8];
-    const int N = (int)*n_ptr;
     const int tid = threadIdx.x;
-    if (N == 0) { if (tid == 0) *nlines_out = 0; return; }
-    const int line_gap = line_gap_of(P, (unsigned)N);
     const int W = P.W, H = P.H, numrho = P.numrho, half = (numrho - 1) / 2;
     volatile uint32_t *vbitmap = bitmap;
+    for (int t = 0; t < T; t++) {
+    if (nlines_all[t] != -1) continue;
+    __syncthreads();
+    int32_t *lines_out = lines_all + (size_t)t * P.max_lines * 4;
+    const int N = compact_ordered(dst + (size_t)t * W * H, W, H, keys);
+    if (N == 0) { if (tid == 0) nlines_all[t] = 0; continue; }
+    const int line_gap = line_gap_of(P, (unsigned)N);
     for (int i = tid; i < N; i += HOUGH_THREADS) {
         idx[i] = i;
         const uint32_t k = keys[i];
@@ -604,5 +648,7 @@ hough_global_kernel(HoughParams P, const unsigned *n_ptr, uint32_t *keys, uint32
         bitmap[p >> 5] = 0;
     }
     __syncthreads();
-    if (tid == 0) *nlines_out = s_ctl[2];
+    if (tid == 0) nlines_all[t] = s_ctl[2];
+    __syncthreads();
+    }
 }

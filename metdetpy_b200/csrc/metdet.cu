@@ -35,13 +35,28 @@ static int fail(int code, const char *fmt, ...) {
                         __FILE__, __LINE__);                                                  \
     } while (0)
 
+#define NCTX 2  // batches that may be in flight (submit .. collect) per handle
+
+// host-visible results of one batch (pinned) + its completion events
+struct BatchCtx {
+    int *h_thr = nullptr, *h_nlines = nullptr;
+    double *h_thrf = nullptr, *h_snr = nullptr;
+    unsigned *h_npoints = nullptr;
+    int32_t *h_lines = nullptr;
+    cudaEvent_t ev_f0 = nullptr, ev_f1 = nullptr, ev_done = nullptr;
+    int T = 0;  // 0: free
+    long long timer0 = 0;
+    long long seq = 0;
+};
+
 struct mdb_detector {
     mdb_config cfg;
     int W, H, n, R;
     size_t HW;
     int slots;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr, cstream = nullptr;  // compute / host->device copies
+    cudaEvent_t ev_copy = nullptr;
     // device
     uint8_t *d_ring = nullptr, *d_mask = nullptr, *d_dst = nullptr;
     uint32_t *d_act = nullptr;  // act bit-frame ring [RA][H][Wb]
@@ -52,45 +67,37 @@ struct mdb_detector {
     double *d_thrf = nullptr, *d_snr = nullptr;
     unsigned *d_npoints = nullptr;
     uint32_t *d_points = nullptr;
-    int32_t *d_lines = nullptr;
-    int32_t *d_accum = nullptr;
-    uint32_t *d_bitmap = nullptr, *d_walk = nullptr;
-    uint32_t *d_okeys = nullptr, *d_oidx = nullptr;  // overflow path scratch (lazy)
-    unsigned *d_on = nullptr;
     uint16_t *d_order = nullptr;  // [T][cap] PPHT visiting order per frame
-    int sm_count = 148;
+    int32_t *d_lines = nullptr;
+    int32_t *d_accum = nullptr;   // tier-2/3 accumulators [slots][180][numrho]
+    uint32_t *d_bitmap = nullptr, *d_walk = nullptr, *d_okeys = nullptr, *d_oidx = nullptr;  // tier 3
     long long *d_prof = nullptr;  // optional per-frame PPHT phase cycle counters (debug)
-    // stream-kernel state (lazy)
     StreamState sk;
-    // pinned host mirrors
-    int *h_thr = nullptr, *h_nlines = nullptr;
-    double *h_thrf = nullptr, *h_snr = nullptr;
-    unsigned *h_npoints = nullptr;
-    int32_t *h_lines = nullptr;
+    BatchCtx ctx[NCTX];
     // host state
     long long timer = 0, dy_timer = 0;
     long long launches = 0;
-    int pending_T = 0;          // frames of the batch in flight (submit..collect)
-    long long pending_timer0 = 0;
-    int last_T = 0;             // frames in d_dst from the most recent batch
+    long long submitted = 0, collected = 0;  // batch sequence numbers
+    int last_T = 0;                           // frames in d_dst from the most recent batch
     float fused_ms = 0.f;
-    int fused_launches = 0;
-    bool single_pending = false;  // per-frame API: update() done, detect() outstanding
+    int fused_launches = 0, last_fused_launches = 0;
     HoughParams hp;
     int use_stream_kernel = 1;
 };
 
 extern "C" const char *mdb_last_error(void) { return g_err; }
-extern "C" int mdb_version(void) { return 100; }
+extern "C" int mdb_version(void) { return 101; }
 extern "C" int mdb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
 
-static FrameSrc frame_src(const mdb_detector *h) {
+static FrameSrc frame_src(const mdb_detector *h, const uint8_t *cur, long long t0) {
     FrameSrc s;
     s.ring = h->d_ring;
+    s.cur = cur;
+    s.t0 = t0;
     s.mask = h->cfg.apply_mask ? h->d_mask : nullptr;
     s.R = h->R;
     s.HW = h->HW;
@@ -110,18 +117,24 @@ static void free_all(mdb_detector *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void *dev[] = {h->d_ring, h->d_mask, h->d_dst, h->d_act, h->d_state, h->d_noise,
-                   h->d_thr, h->d_nlines, h->d_thrf, h->d_snr, h->d_npoints, h->d_points,
-                   h->d_lines, h->d_accum, h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_on, h->d_prof, h->d_order};
+    if (h->cstream) cudaStreamSynchronize(h->cstream);
+    void *dev[] = {h->d_ring, h->d_mask, h->d_dst, h->d_act, h->d_state, h->d_noise, h->d_thr, h->d_nlines,
+                   h->d_thrf, h->d_snr, h->d_npoints, h->d_points, h->d_order, h->d_lines, h->d_accum,
+                   h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_prof};
     for (void *p : dev)
         if (p) cudaFree(p);
     stream_state_free(h->sk);
-    void *pin[] = {h->h_thr, h->h_nlines, h->h_thrf, h->h_snr, h->h_npoints, h->h_lines};
-    for (void *p : pin)
-        if (p) cudaFreeHost(p);
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->ev1) cudaEventDestroy(h->ev1);
+    for (BatchCtx &c : h->ctx) {
+        void *pin[] = {c.h_thr, c.h_nlines, c.h_thrf, c.h_snr, c.h_npoints, c.h_lines};
+        for (void *p : pin)
+            if (p) cudaFreeHost(p);
+        if (c.ev_f0) cudaEventDestroy(c.ev_f0);
+        if (c.ev_f1) cudaEventDestroy(c.ev_f1);
+        if (c.ev_done) cudaEventDestroy(c.ev_done);
+    }
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->cstream) cudaStreamDestroy(h->cstream);
     delete h;
 }
 
@@ -151,12 +164,13 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     h->cfg = *cfg;
     h->W = cfg->width; h->H = cfg->height; h->n = cfg->window;
     h->HW = (size_t)h->W * h->H;
-    h->R = h->n - 1 + cfg->max_batch;
-    if (h->R < h->n) h->R = h->n;
     const int T = cfg->max_batch;
+    // ring: history (n-1) + two batches, so the copy of batch k+1 never lands on frames batch k reads
+    h->R = h->n - 1 + (T > 1 ? 2 * T : 1);
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, cfg->device);
     if (e != cudaSuccess) { delete h; return fail(MDB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    h->sm_count = prop.multiProcessorCount;
 
     HoughParams &hp = h->hp;
     hp.W = h->W; hp.H = h->H; hp.numrho = 2 * (h->W + h->H) + 1;
@@ -194,14 +208,14 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     } while (0)
 
     CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CKH(cudaEventCreate(&h->ev0));
-    CKH(cudaEventCreate(&h->ev1));
+    CKH(cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
+    CKH(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
     const size_t bm_words = (h->HW + 31) / 32;
+    h->Wb = (h->W + 31) / 32;
+    h->RA = h->n - 1 + T;
     ALLOC(h->d_ring, (size_t)h->R * h->HW);
     ALLOC(h->d_mask, h->HW);
     ALLOC(h->d_dst, (size_t)T * h->HW);
-    h->Wb = (h->W + 31) / 32;
-    h->RA = h->n - 1 + T;
     ALLOC(h->d_act, (size_t)h->RA * h->H * h->Wb * sizeof(uint32_t));
     ALLOC(h->d_state, sizeof(DevState));
     ALLOC(h->d_noise, (size_t)T * 2 * sizeof(unsigned long long));
@@ -211,26 +225,28 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     ALLOC(h->d_snr, T * sizeof(double));
     ALLOC(h->d_npoints, T * sizeof(unsigned));
     ALLOC(h->d_points, (size_t)T * MDB_POINT_CAP * sizeof(uint32_t));
+    ALLOC(h->d_order, (size_t)T * MDB_POINT_CAP * sizeof(uint16_t));
     ALLOC(h->d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t));
     ALLOC(h->d_accum, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t));
-    ALLOC(h->d_bitmap, bm_words * sizeof(uint32_t));           // overflow path only
-    ALLOC(h->d_walk, (size_t)hp.walk_cap * sizeof(uint32_t));  // overflow path only
-    ALLOC(h->d_on, sizeof(unsigned));
-    ALLOC(h->d_order, (size_t)T * MDB_POINT_CAP * sizeof(uint16_t));
-    h->sm_count = prop.multiProcessorCount;
+    ALLOC(h->d_bitmap, bm_words * sizeof(uint32_t));
+    ALLOC(h->d_walk, (size_t)hp.walk_cap * sizeof(uint32_t));
     CKH(cudaMemsetAsync(h->d_ring, 0, (size_t)h->R * h->HW, h->stream));
     CKH(cudaMemsetAsync(h->d_act, 0, (size_t)h->RA * h->H * h->Wb * sizeof(uint32_t), h->stream));
     CKH(cudaMemsetAsync(h->d_accum, 0, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t), h->stream));
     CKH(cudaMemsetAsync(h->d_bitmap, 0, bm_words * sizeof(uint32_t), h->stream));
     CKH(cudaMemsetAsync(h->d_dst, 0, (size_t)T * h->HW, h->stream));
     CKH(cudaMemcpyAsync(h->d_mask, mask, h->HW, cudaMemcpyHostToDevice, h->stream));
-
-    CKH(cudaHostAlloc((void **)&h->h_thr, T * sizeof(int), cudaHostAllocDefault));
-    CKH(cudaHostAlloc((void **)&h->h_nlines, T * sizeof(int), cudaHostAllocDefault));
-    CKH(cudaHostAlloc((void **)&h->h_thrf, T * sizeof(double), cudaHostAllocDefault));
-    CKH(cudaHostAlloc((void **)&h->h_snr, T * sizeof(double), cudaHostAllocDefault));
-    CKH(cudaHostAlloc((void **)&h->h_npoints, T * sizeof(unsigned), cudaHostAllocDefault));
-    CKH(cudaHostAlloc((void **)&h->h_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t), cudaHostAllocDefault));
+    for (BatchCtx &c : h->ctx) {
+        CKH(cudaHostAlloc((void **)&c.h_thr, T * sizeof(int), cudaHostAllocDefault));
+        CKH(cudaHostAlloc((void **)&c.h_nlines, T * sizeof(int), cudaHostAllocDefault));
+        CKH(cudaHostAlloc((void **)&c.h_thrf, T * sizeof(double), cudaHostAllocDefault));
+        CKH(cudaHostAlloc((void **)&c.h_snr, T * sizeof(double), cudaHostAllocDefault));
+        CKH(cudaHostAlloc((void **)&c.h_npoints, T * sizeof(unsigned), cudaHostAllocDefault));
+        CKH(cudaHostAlloc((void **)&c.h_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t), cudaHostAllocDefault));
+        CKH(cudaEventCreate(&c.ev_f0));
+        CKH(cudaEventCreate(&c.ev_f1));
+        CKH(cudaEventCreateWithFlags(&c.ev_done, cudaEventDisableTiming));
+    }
 
     // scalar state: LineDetector.__init__ (Detector.py:204-209), SNR_SW.__init__ (:58-61)
     DevState st;
@@ -271,29 +287,29 @@ extern "C" int mdb_destroy(mdb_handle h) {
     return MDB_OK;
 }
 
-// ---- ingest: copy T frames into ring slots (global frame index timer .. timer+T-1) ----------
-static int ingest(mdb_detector *h, const uint8_t *frames, int T, int on_device) {
-    long long t = h->timer;
-    int done = 0;
+// ---- frames into ring slots (global frame index t0 .. t0+T-1), on stream `st` ----------------
+static int copy_to_ring(mdb_detector *h, const uint8_t *frames, int first, int T, long long t0,
+                        cudaMemcpyKind kind, cudaStream_t st) {
+    long long t = t0 + first;
+    int done = first;
     while (done < T) {
         const int slot = (int)(t % h->R);
         const int run = std::min(T - done, h->R - slot);
         CK(cudaMemcpyAsync(h->d_ring + (size_t)slot * h->HW, frames + (size_t)done * h->HW,
-                           (size_t)run * h->HW, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                           h->stream));
+                           (size_t)run * h->HW, kind, st));
         done += run;
         t += run;
     }
     return MDB_OK;
 }
 
-static int launch_noise_thr(mdb_detector *h, int T, long long timer0) {
+static int launch_noise_thr(mdb_detector *h, const FrameSrc &src, int T, long long timer0) {
     const mdb_config &c = h->cfg;
     const int rh = c.roi[2] - c.roi[0], rw = c.roi[3] - c.roi[1];
     const long long std_interval = (long long)c.nz_interval * h->n;
     CK(cudaMemsetAsync(h->d_noise, 0, (size_t)T * 2 * sizeof(unsigned long long), h->stream));
     const int gx = std::max(1, std::min((rh * rw + 255) / 256, 592));
-    noise_sample_kernel<<<dim3(gx, T), 256, 0, h->stream>>>(frame_src(h), h->W, h->n, timer0, std_interval,
+    noise_sample_kernel<<<dim3(gx, T), 256, 0, h->stream>>>(src, h->W, h->n, timer0, std_interval,
                                                           c.roi[0], c.roi[1], rh, rw, h->d_noise);
     threshold_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_noise, T, timer0, h->n, std_interval,
                                              (long long)rh * rw, c.adaptive, c.sensitivity, h->d_thr,
@@ -304,14 +320,13 @@ static int launch_noise_thr(mdb_detector *h, int T, long long timer0) {
 }
 
 // fused mask chain for frames i = 0..T-1 of the batch (global index timer0 + i)
-static int launch_fused(mdb_detector *h, int T, long long timer0, long long dy0) {
+static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T, long long timer0, long long dy0) {
     CK(cudaMemsetAsync(h->d_npoints, 0, T * sizeof(unsigned), h->stream));
-    CK(cudaEventRecord(h->ev0, h->stream));
+    CK(cudaEventRecord(c.ev_f0, h->stream));
     int nl = 0;
     if (h->use_stream_kernel && stream_kernel_supported(h->sk, T)) {
-        int rc = stream_kernel_launch(h->sk, frame_src(h), timer0, dy0, T, h->cfg.dy_mask, h->d_thr,
-                                      act_ring(h), h->d_dst, h->d_npoints, h->d_points, MDB_POINT_CAP,
-                                      h->stream, &nl);
+        int rc = stream_kernel_launch(h->sk, src, timer0, dy0, T, h->cfg.dy_mask, h->d_thr, act_ring(h),
+                                      h->d_dst, h->d_npoints, h->d_points, MDB_POINT_CAP, h->stream, &nl);
         if (rc != 0) return fail(MDB_ERR_CUDA, "stream kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
         dim3 grid((h->W + V1_TW - 1) / V1_TW, (h->H + V1_TH - 1) / V1_TH);
@@ -320,55 +335,42 @@ static int launch_fused(mdb_detector *h, int T, long long timer0, long long dy0)
             const int L = (int)std::min<long long>(h->n, t + 1);
             const int Ldy = (int)std::min<long long>(h->n, dy0 + i + 1);
             fused_frame_kernel<<<grid, 256, 0, h->stream>>>(
-                frame_src(h), h->W, h->H, h->n, t, L, dy0 + i, Ldy, h->cfg.dy_mask, h->d_thr + i,
-                act_ring(h), h->d_dst + (size_t)i * h->HW, h->d_npoints + i,
-                h->d_points + (size_t)i * MDB_POINT_CAP, MDB_POINT_CAP);
+                src, h->W, h->H, h->n, t, L, dy0 + i, Ldy, h->cfg.dy_mask, h->d_thr + i, act_ring(h),
+                h->d_dst + (size_t)i * h->HW, h->d_npoints + i, h->d_points + (size_t)i * MDB_POINT_CAP,
+                MDB_POINT_CAP);
             nl++;
         }
     }
-    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventRecord(c.ev_f1, h->stream));
     h->fused_launches = nl;
     h->launches += nl;
     CK(cudaGetLastError());
     return MDB_OK;
 }
 
-static int launch_hough_and_copy(mdb_detector *h, int T) {
-    const int grid = std::min(T, h->slots);
+static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
     ppht_order_kernel<<<T, 32, MDB_POINT_CAP * 2, h->stream>>>(T, MDB_POINT_CAP, h->d_npoints, h->d_order);
     hough_smem_kernel<<<std::min(T, h->sm_count), HOUGH_THREADS, HOUGH_SMEM_BYTES + HOUGH_TABLE_BYTES, h->stream>>>(
         h->hp, T, h->d_npoints, h->d_points, h->d_order, h->d_lines, h->d_nlines);
-    hough_tier2_kernel<<<grid, HOUGH_THREADS, HOUGH_SMEM_BYTES, h->stream>>>(
+    hough_tier2_kernel<<<std::min(T, h->slots), HOUGH_THREADS, HOUGH_SMEM_BYTES, h->stream>>>(
         h->hp, T, h->d_npoints, h->d_points, h->d_accum, h->d_lines, h->d_nlines, h->d_prof);
-    h->launches += 3;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h->h_thr, h->d_thr, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_thrf, h->d_thrf, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_snr, h->d_snr, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_npoints, h->d_npoints, T * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_nlines, h->d_nlines, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_lines, h->d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t),
-                       cudaMemcpyDeviceToHost, h->stream));
-    return MDB_OK;
-}
-
-// frames whose on-pixel count exceeded the shared-memory capacity: ordered compaction + global PPHT
-static int overflow_frame(mdb_detector *h, int i) {
-    if (!h->d_okeys) {
+    if (!h->d_okeys) {  // tier-3 scratch, allocated once
         if (cudaMalloc((void **)&h->d_okeys, h->HW * sizeof(uint32_t)) != cudaSuccess ||
             cudaMalloc((void **)&h->d_oidx, h->HW * sizeof(uint32_t)) != cudaSuccess)
-            return fail(MDB_ERR_NOMEM, "overflow scratch: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail(MDB_ERR_NOMEM, "tier-3 scratch: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    compact_ordered_kernel<<<1, 1024, 0, h->stream>>>(h->d_dst + (size_t)i * h->HW, h->W, h->H, h->d_okeys, h->d_on);
-    hough_global_kernel<<<1, HOUGH_THREADS, 0, h->stream>>>(h->hp, h->d_on, h->d_okeys, h->d_oidx, h->d_accum,
-                                                           h->d_bitmap, h->d_walk,
-                                                           h->d_lines + (size_t)i * MDB_MAX_LINES * 4, h->d_nlines + i);
-    h->launches += 2;
+    hough_tier3_kernel<<<1, HOUGH_THREADS, 0, h->stream>>>(h->hp, T, h->d_dst, h->d_okeys, h->d_oidx, h->d_accum,
+                                                          h->d_bitmap, h->d_walk, h->d_lines, h->d_nlines);
+    h->launches += 4;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h->h_nlines + i, h->d_nlines + i, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_lines + (size_t)i * MDB_MAX_LINES * 4, h->d_lines + (size_t)i * MDB_MAX_LINES * 4,
-                       MDB_MAX_LINES * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(c.h_thr, h->d_thr, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(c.h_thrf, h->d_thrf, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(c.h_snr, h->d_snr, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(c.h_npoints, h->d_npoints, T * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(c.h_nlines, h->d_nlines, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(c.h_lines, h->d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(c.ev_done, h->stream));
     return MDB_OK;
 }
 
@@ -423,32 +425,29 @@ extern "C" int mdb_lineset_nms(const int32_t *lines_in, int n, int32_t *lines_ou
     return MDB_OK;
 }
 
-// fill infos / line outputs for frames 0..T-1 of the finished batch
-static int finish_batch(mdb_detector *h, int T, long long timer0, mdb_frame_info *infos, int32_t *lines,
+// fill infos / line outputs for frames 0..T-1 of a finished batch (pure host work)
+static int finish_batch(mdb_detector *h, const BatchCtx &c, mdb_frame_info *infos, int32_t *lines,
                         double *prob, int32_t *raw_lines) {
-    for (int i = 0; i < T; i++)
-        if (h->h_nlines[i] < 0) {
-            int rc = overflow_frame(h, i);
-            if (rc) return rc;
-        }
+    const int T = c.T;
     for (int i = 0; i < T; i++) {
         mdb_frame_info fi;
         memset(&fi, 0, sizeof fi);
-        fi.timer = timer0 + i + 1;
-        fi.bi_threshold = h->h_thr[i];
-        fi.bi_threshold_float = h->h_thrf[i];
-        fi.snr = h->h_snr[i];
-        fi.n_on = (int32_t)h->h_npoints[i];
+        fi.timer = c.timer0 + i + 1;
+        fi.bi_threshold = c.h_thr[i];
+        fi.bi_threshold_float = c.h_thrf[i];
+        fi.snr = c.h_snr[i];
+        fi.n_on = (int32_t)c.h_npoints[i];
         // Detector.py:342-344 (host doubles; this TU is compiled with -ffp-contract=off)
-        volatile double ds = (double)h->h_npoints[i] / h->hp.mask_area;
+        volatile double ds = (double)c.h_npoints[i] / h->hp.mask_area;
         ds = ds * 100.0;
         fi.dst_sum = ds;
         volatile double g = ds / 0.05;
         g = 1.0 - g;
         if (!(g > 0.0)) g = 0.0;
         fi.gap = g * (double)h->cfg.hough_max_gap;
-        fi.lines_num = h->h_nlines[i];
-        const int32_t *src = h->h_lines + (size_t)i * MDB_MAX_LINES * 4;
+        if (c.h_nlines[i] < 0) return fail(MDB_ERR_STATE, "internal: frame %d left unresolved by the Hough tiers", i);
+        fi.lines_num = c.h_nlines[i];
+        const int32_t *src = c.h_lines + (size_t)i * MDB_MAX_LINES * 4;
         int nraw = fi.lines_num > MDB_NUM_LINES_TOOMUCH ? 0 : fi.lines_num;
         fi.n_raw = nraw;
         if (raw_lines && nraw) memcpy(raw_lines + (size_t)i * MDB_MAX_LINES * 4, src, (size_t)nraw * 16);
@@ -460,17 +459,18 @@ static int finish_batch(mdb_detector *h, int T, long long timer0, mdb_frame_info
     return MDB_OK;
 }
 
+static int in_flight(const mdb_detector *h) { return (int)(h->submitted - h->collected); }
+
 // ---- per-frame API ---------------------------------------------------------------------------
 extern "C" int mdb_update(mdb_handle h, const uint8_t *frame, int on_device) {
     if (!h || !frame) return fail(MDB_ERR_INVALID, "mdb_update: null argument");
-    if (h->pending_T) return fail(MDB_ERR_STATE, "mdb_update: a submitted batch has not been collected");
+    if (in_flight(h)) return fail(MDB_ERR_STATE, "mdb_update: a submitted batch has not been collected");
     CK(cudaSetDevice(h->cfg.device));
-    int rc = ingest(h, frame, 1, on_device);
+    int rc = copy_to_ring(h, frame, 0, 1, h->timer, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream);
     if (rc) return rc;
-    rc = launch_noise_thr(h, 1, h->timer);
+    rc = launch_noise_thr(h, frame_src(h, nullptr, 0), 1, h->timer);
     if (rc) return rc;
     h->timer += 1;
-    h->single_pending = true;
     if (!on_device) CK(cudaStreamSynchronize(h->stream));  // caller may reuse its buffer on return
     return MDB_OK;
 }
@@ -479,18 +479,23 @@ extern "C" int mdb_detect(mdb_handle h, mdb_frame_info *info, int32_t *lines, do
                           int32_t *raw_lines) {
     if (!h) return fail(MDB_ERR_INVALID, "mdb_detect: null handle");
     if (h->timer == 0) return fail(MDB_ERR_STATE, "mdb_detect: no frame has been pushed yet");
-    if (h->pending_T) return fail(MDB_ERR_STATE, "mdb_detect: a submitted batch has not been collected");
+    if (in_flight(h)) return fail(MDB_ERR_STATE, "mdb_detect: a submitted batch has not been collected");
     CK(cudaSetDevice(h->cfg.device));
-    int rc = launch_fused(h, 1, h->timer - 1, h->dy_timer);
+    BatchCtx &c = h->ctx[0];
+    int rc = launch_fused(h, c, frame_src(h, nullptr, 0), 1, h->timer - 1, h->dy_timer);
     if (rc) return rc;
-    rc = launch_hough_and_copy(h, 1);
+    rc = launch_hough_and_copy(h, c, 1);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaEventElapsedTime(&h->fused_ms, h->ev0, h->ev1));
+    CK(cudaEventElapsedTime(&h->fused_ms, c.ev_f0, c.ev_f1));
+    h->last_fused_launches = h->fused_launches;
     h->dy_timer += 1;
     h->last_T = 1;
-    h->single_pending = false;
-    return finish_batch(h, 1, h->timer - 1, info, lines, nonline_prob, raw_lines);
+    c.T = 1;
+    c.timer0 = h->timer - 1;
+    rc = finish_batch(h, c, info, lines, nonline_prob, raw_lines);
+    c.T = 0;
+    return rc;
 }
 
 // ---- batched API -----------------------------------------------------------------------------
@@ -498,19 +503,41 @@ extern "C" int mdb_submit_batch(mdb_handle h, const uint8_t *frames, int T, int 
     if (!h || !frames) return fail(MDB_ERR_INVALID, "mdb_submit_batch: null argument");
     if (T < 1 || T > h->cfg.max_batch)
         return fail(MDB_ERR_INVALID, "mdb_submit_batch: T=%d outside 1..max_batch=%d", T, h->cfg.max_batch);
-    if (h->pending_T) return fail(MDB_ERR_STATE, "mdb_submit_batch: previous batch not collected");
+    if (in_flight(h) >= NCTX) return fail(MDB_ERR_STATE, "mdb_submit_batch: %d batches already in flight", NCTX);
     CK(cudaSetDevice(h->cfg.device));
-    int rc = ingest(h, frames, T, on_device);
-    if (rc) return rc;
+    BatchCtx &c = h->ctx[h->submitted % NCTX];
     const long long timer0 = h->timer;
-    rc = launch_noise_thr(h, T, timer0);
+    FrameSrc src;
+    if (on_device) {
+        src = frame_src(h, frames, timer0);  // zero-copy: kernels read the caller's buffer
+    } else {
+        // the copy runs on its own stream so that it overlaps the previous batch's kernels; the ring
+        // holds two batches + history, so it only has to wait for the batch before the previous one
+        BatchCtx &prev2 = h->ctx[(h->submitted + NCTX - 2) % NCTX];
+        if (h->submitted >= 2) CK(cudaStreamWaitEvent(h->cstream, prev2.ev_done, 0));
+        int rc = copy_to_ring(h, frames, 0, T, timer0, cudaMemcpyHostToDevice, h->cstream);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev_copy, h->cstream));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+        src = frame_src(h, nullptr, 0);
+    }
+    int rc = launch_noise_thr(h, src, T, timer0);
     if (rc) return rc;
-    rc = launch_fused(h, T, timer0, h->dy_timer);
+    rc = launch_fused(h, c, src, T, timer0, h->dy_timer);
     if (rc) return rc;
-    rc = launch_hough_and_copy(h, T);
+    if (on_device) {  // keep the last n-1 frames as history for the next batch
+        const int keep = std::min(T, h->n - 1);
+        if (keep > 0) {
+            rc = copy_to_ring(h, frames, T - keep, T, timer0, cudaMemcpyDeviceToDevice, h->stream);
+            if (rc) return rc;
+        }
+    }
+    rc = launch_hough_and_copy(h, c, T);
     if (rc) return rc;
-    h->pending_T = T;
-    h->pending_timer0 = timer0;
+    c.T = T;
+    c.timer0 = timer0;
+    c.seq = h->submitted;
+    h->submitted += 1;
     h->timer += T;
     h->dy_timer += T;
     return MDB_OK;
@@ -519,22 +546,32 @@ extern "C" int mdb_submit_batch(mdb_handle h, const uint8_t *frames, int T, int 
 extern "C" int mdb_collect_batch(mdb_handle h, mdb_frame_info *infos, int32_t *lines, double *nonline_prob,
                                  int32_t *raw_lines, uint8_t *dst_out, int dst_on_device) {
     if (!h) return fail(MDB_ERR_INVALID, "mdb_collect_batch: null handle");
-    if (!h->pending_T) return fail(MDB_ERR_STATE, "mdb_collect_batch: nothing submitted");
+    if (!in_flight(h)) return fail(MDB_ERR_STATE, "mdb_collect_batch: nothing submitted");
     CK(cudaSetDevice(h->cfg.device));
-    const int T = h->pending_T;
-    if (dst_out)
+    BatchCtx &c = h->ctx[h->collected % NCTX];
+    const int T = c.T;
+    if (dst_out) {
+        if (in_flight(h) > 1)
+            return fail(MDB_ERR_STATE, "mdb_collect_batch: dst of this batch was overwritten by the batch "
+                                       "submitted after it; collect before submitting when dst is wanted");
         CK(cudaMemcpyAsync(dst_out, h->d_dst, (size_t)T * h->HW,
                            dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    CK(cudaEventElapsedTime(&h->fused_ms, h->ev0, h->ev1));
-    h->pending_T = 0;
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    CK(cudaEventSynchronize(c.ev_done));
+    CK(cudaEventElapsedTime(&h->fused_ms, c.ev_f0, c.ev_f1));
+    h->last_fused_launches = h->fused_launches;
+    int rc = finish_batch(h, c, infos, lines, nonline_prob, raw_lines);
     h->last_T = T;
-    return finish_batch(h, T, h->pending_timer0, infos, lines, nonline_prob, raw_lines);
+    c.T = 0;
+    h->collected += 1;
+    return rc;
 }
 
 extern "C" int mdb_detect_batch(mdb_handle h, const uint8_t *frames, int T, int on_device,
                                 mdb_frame_info *infos, int32_t *lines, double *nonline_prob,
                                 int32_t *raw_lines, uint8_t *dst_out, int dst_on_device) {
+    if (h && in_flight(h)) return fail(MDB_ERR_STATE, "mdb_detect_batch: a submitted batch has not been collected");
     int rc = mdb_submit_batch(h, frames, T, on_device);
     if (rc) return rc;
     return mdb_collect_batch(h, infos, lines, nonline_prob, raw_lines, dst_out, dst_on_device);
@@ -543,6 +580,7 @@ extern "C" int mdb_detect_batch(mdb_handle h, const uint8_t *frames, int T, int 
 extern "C" int mdb_get_dst(mdb_handle h, uint8_t *dst, int on_device) {
     if (!h || !dst) return fail(MDB_ERR_INVALID, "mdb_get_dst: null argument");
     if (h->last_T < 1) return fail(MDB_ERR_STATE, "mdb_get_dst: no detect has run yet");
+    if (in_flight(h)) return fail(MDB_ERR_STATE, "mdb_get_dst: a batch is in flight");
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaMemcpyAsync(dst, h->d_dst + (size_t)(h->last_T - 1) * h->HW, h->HW,
                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
@@ -559,6 +597,7 @@ extern "C" int mdb_get_dst_device(mdb_handle h, const uint8_t **ptr) {
 extern "C" int mdb_get_stack(mdb_handle h, uint8_t *max_out, uint8_t *mean_out, uint32_t *sum_out) {
     if (!h) return fail(MDB_ERR_INVALID, "mdb_get_stack: null handle");
     if (h->timer == 0) return fail(MDB_ERR_STATE, "mdb_get_stack: empty window");
+    if (in_flight(h)) return fail(MDB_ERR_STATE, "mdb_get_stack: a batch is in flight");
     CK(cudaSetDevice(h->cfg.device));
     uint8_t *dmx = nullptr, *dmean = nullptr;
     uint32_t *dsum = nullptr;
@@ -567,7 +606,7 @@ extern "C" int mdb_get_stack(mdb_handle h, uint8_t *max_out, uint8_t *mean_out, 
     CK(cudaMalloc((void **)&dsum, h->HW * 4));
     const long long t = h->timer - 1;
     const int L = (int)std::min<long long>(h->n, h->timer);
-    stack_readback_kernel<<<592, 256, 0, h->stream>>>(frame_src(h), h->HW, h->n, t, L, dmx, dmean, dsum);
+    stack_readback_kernel<<<592, 256, 0, h->stream>>>(frame_src(h, nullptr, 0), h->HW, h->n, t, L, dmx, dmean, dsum);
     h->launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && max_out) e = cudaMemcpyAsync(max_out, dmx, h->HW, cudaMemcpyDeviceToHost, h->stream);
@@ -594,17 +633,17 @@ extern "C" int mdb_get_launch_count(mdb_handle h, int64_t *count) {
 extern "C" int mdb_get_fused_time(mdb_handle h, float *ms, int32_t *launches) {
     if (!h) return fail(MDB_ERR_INVALID, "mdb_get_fused_time: null handle");
     if (ms) *ms = h->fused_ms;
-    if (launches) *launches = h->fused_launches;
+    if (launches) *launches = h->last_fused_launches;
     return MDB_OK;
 }
 
-// internal knob used by the parity tests to force the generic per-frame kernel
 extern "C" int mdb_debug_hough_profile(mdb_handle h, long long *out, int T) {
     if (!h || !out || !h->d_prof) return fail(MDB_ERR_INVALID, "mdb_debug_hough_profile: not enabled");
     CK(cudaMemcpy(out, h->d_prof, (size_t)T * 10 * sizeof(long long), cudaMemcpyDeviceToHost));
     return MDB_OK;
 }
 
+// internal knobs used by the parity tests (force the generic per-frame kernel) and debugging
 extern "C" int mdb_set_option(mdb_handle h, const char *name, int value) {
     if (!h || !name) return fail(MDB_ERR_INVALID, "mdb_set_option: null argument");
     if (!strcmp(name, "hough_profile")) {

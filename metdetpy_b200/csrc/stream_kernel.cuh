@@ -63,7 +63,9 @@ temporal_kernel(FrameSrc src, long long t0, int T, int n, int HW16, const int *_
     __syncthreads();
     const int g = blockIdx.x * nt + tid;
     if (g >= HW16) return;
-    const uint8_t *gbase = src.ring + (size_t)g * 16;
+    // frames of this batch: contiguous in the caller's buffer (zero-copy) or slots of the ring
+    const uint8_t *gbase = (src.cur ? src.cur : src.ring) + (size_t)g * 16;
+    const int Rw = src.cur ? 0x7fffffff : src.R;  // no wrap in the caller's buffer
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + tid * 16;
     const uint32_t slot_stride = nt * 16;
 
@@ -77,16 +79,16 @@ temporal_kernel(FrameSrc src, long long t0, int T, int n, int HW16, const int *_
     ring[(size_t)(RS - 1) * nt + tid] = make_uint4(0, 0, 0, 0);
     for (int p = 1; p < n; p++) {
         const long long th = t0 - n + p;
-        if (th >= 0) cp_async16(ring_s + (p - 1) * slot_stride, gbase + (size_t)(th % src.R) * src.HW);
+        if (th >= 0) cp_async16(ring_s + (p - 1) * slot_stride, src.frame(th) + (size_t)g * 16);
         else ring[(size_t)(p - 1) * nt + tid] = make_uint4(0, 0, 0, 0);
     }
     cp_async_commit();
     // ---- prime the pipeline: frames t0 .. t0+K-1 -> slots n-1 .. n+K-2 -------------------------
-    int pf_slot = (int)(t0 % src.R);  // global ring slot of the next frame to prefetch
+    int pf_slot = src.cur ? (int)(t0 - src.t0) : (int)(t0 % src.R);  // slot of the next frame to prefetch
     for (int i = 0; i < ST_K; i++) {
         if (i < T) cp_async16(ring_s + (n - 1 + i) * slot_stride, gbase + (size_t)pf_slot * src.HW);
         cp_async_commit();
-        if (++pf_slot == src.R) pf_slot = 0;
+        if (++pf_slot == Rw) pf_slot = 0;
     }
     cp_async_wait<ST_K>();  // history landed
 
@@ -131,7 +133,7 @@ temporal_kernel(FrameSrc src, long long t0, int T, int n, int HW16, const int *_
         // slot s_old is free now: fetch frame i+K into it
         if (i + ST_K < T) cp_async16(ring_s + s_old * slot_stride, gbase + (size_t)pf_slot * src.HW);
         cp_async_commit();
-        if (++pf_slot == src.R) pf_slot = 0;
+        if (++pf_slot == Rw) pf_slot = 0;
 
         const int L = (int)(tg + 1 < n ? tg + 1 : n);
         const unsigned Tq = (unsigned)thr_s[i] * (unsigned)L;            // <= 255*128

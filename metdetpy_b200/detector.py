@@ -436,18 +436,25 @@ class M3Detector(LineDetector):
         return res
 
     def submit(self, ptr: int, T: int, on_device: bool):
-        """Asynchronous half of detect_many (mdb_submit_batch)."""
+        """Asynchronous half of detect_many (mdb_submit_batch): enqueues the copy (host input) and all
+        kernels of one batch and returns.  Up to two batches may be in flight, so the host->device
+        copy of the next batch overlaps the kernels of this one.  Host buffers should be pinned and
+        must stay untouched until the matching collect(); device buffers likewise."""
         check(self._eng.lib.mdb_submit_batch(self._eng.handle, ptr, T, int(on_device)), "submit")
         self._timer += T
-        self._pending = T
+        if not hasattr(self, "_pending"):
+            self._pending = []
+        self._pending.append(T)
 
     def collect(self, want_lines: bool = True):
-        """Waits for the submitted batch (mdb_collect_batch); returns list of (lines, cls_pred)."""
+        """Waits for the oldest submitted batch (mdb_collect_batch); returns its list of
+        (lines, cls_pred), or None with want_lines=False (scalars of the last frame still update)."""
         eng = self._eng
-        T = self._pending
+        T = self._pending.pop(0)
         check(eng.lib.mdb_collect_batch(eng.handle, C.byref(eng.infos), _ptr(eng.lines), _ptr(eng.prob),
                                         _ptr(eng.raw), None, 0), "collect")
         self._dst_cache = None
+        self.last_infos = eng.infos
         if not want_lines:
             self._unpack(T - 1)
             return None
