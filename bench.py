@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=40, help="frames in the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--generic-kernel", action="store_true", help="force the per-frame fused kernel")
+    ap.add_argument("--wpt", type=int, default=0, help="temporal kernel words per thread (2 or 4; 0 = default)")
     return ap.parse_args()
 
 
@@ -179,6 +180,8 @@ def main_ours(a):
     det = M3Detector(n / a.fps + 1e-9, a.fps, mask, 10, make_cfg(a), None, device=local, max_batch=B)
     if a.generic_kernel:
         det._eng.set_option("stream_kernel", 0)
+    if a.wpt:
+        det._eng.set_option("temporal_wpt", a.wpt)
     ext = torch.cuda.ExternalStream(det._eng.stream_ptr(), device=dev)
 
     # this rank's chunk of the stream: frames [rank*chunk, ...); generated on the device

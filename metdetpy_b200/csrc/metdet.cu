@@ -654,6 +654,11 @@ extern "C" int mdb_set_option(mdb_handle h, const char *name, int value) {
         return MDB_OK;
     }
     if (!strcmp(name, "stream_kernel")) { h->use_stream_kernel = value; return MDB_OK; }
+    if (!strcmp(name, "temporal_wpt")) {
+        if (!h->sk.ok || stream_state_config(h->sk, value) != 0)
+            return fail(MDB_ERR_INVALID, "mdb_set_option: temporal_wpt=%d not possible here", value);
+        return MDB_OK;
+    }
     return fail(MDB_ERR_INVALID, "mdb_set_option: unknown option %s", name);
 }
 

@@ -27,15 +27,13 @@ struct StreamState {
     int ok = 0;
     int W = 0, H = 0, n = 0, max_batch = 0, device = 0;
     int t_threads = 32;     // CTA size of the temporal kernel
+    int t_wpt = 2;          // 32-bit words (4 px) per thread in the temporal kernel
     size_t t_smem_per_thread = 0;
     int sp_rows = 8;        // output rows per warp strip in the spatial kernel
     uint32_t *d_bits = nullptr;  // [max_batch][H][W/32]
 };
 
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -49,101 +47,142 @@ __device__ __forceinline__ unsigned ev(unsigned x) { return x & 0x00ff00ffu; }
 __device__ __forceinline__ unsigned od(unsigned x) { return prmt(x, 0u, 0x4341u); }
 __device__ __forceinline__ unsigned pack_eo(unsigned e, unsigned o) { return e | (o << 8); }
 
-template <bool MASKED>
-__global__ void __launch_bounds__(64)
-temporal_kernel(FrameSrc src, long long t0, int T, int n, int HW16, const int *__restrict__ thr,
-                uint16_t *__restrict__ bits) {
+// WPT = 32-bit words (4 pixels each) per thread: 4 (16 px, 16-byte accesses) or 2 (8 px, 8-byte
+// accesses -- twice the resident warps for the same shared-memory footprint per pixel).
+template <int WPT> struct VecT;
+template <> struct VecT<4> { typedef uint4 type; };
+template <> struct VecT<2> { typedef uint2 type; };
+
+template <int WPT>
+__device__ __forceinline__ void cp_async_vec(uint32_t saddr, const void *g) {
+    if (WPT == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
+}
+template <int WPT>
+__device__ __forceinline__ void lds_vec(unsigned (&w)[WPT], uint32_t saddr) {
+    if (WPT == 4) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(saddr));
+    else asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(saddr));
+}
+template <int WPT>
+__device__ __forceinline__ void sts_vec(uint32_t saddr, const unsigned (&w)[WPT]) {
+    if (WPT == 4) asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+    else asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(saddr), "r"(w[0]), "r"(w[1]) : "memory");
+}
+
+template <bool MASKED, int WPT>
+__global__ void __launch_bounds__(128)
+temporal_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *__restrict__ thr,
+                uint8_t *__restrict__ bits) {
+    constexpr int VB = WPT * 4;  // bytes (= pixels) per thread per frame
     extern __shared__ uint4 t_smem[];
     const int nt = blockDim.x, tid = threadIdx.x;
     const int RS = n + ST_K;
-    uint4 *ring = t_smem;               // [RS][nt]   raw frames (slot RS-1 doubles as "frame t0-n")
-    uint4 *smx = t_smem + (size_t)RS * nt;  // [n][nt]    suffix max of the previous block, by position
-    uint8_t *thr_s = reinterpret_cast<uint8_t *>(smx + (size_t)n * nt);
+    // shared memory: ring [RS][nt] raw frames (slot RS-1 doubles as "frame t0-n"), smx [n][nt] suffix
+    // max of the previous block by position, thr_s [T]
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(t_smem);
+    const uint32_t slot_stride = nt * VB;
+    const uint32_t ring_s = smem0 + tid * VB;
+    const uint32_t smx_s = ring_s + RS * slot_stride;
+    uint8_t *thr_s = reinterpret_cast<uint8_t *>(t_smem) + (size_t)(RS + n) * slot_stride;
     for (int i = tid; i < T; i += nt) thr_s[i] = (uint8_t)min(max(thr[i], 0), 255);
     __syncthreads();
     const int g = blockIdx.x * nt + tid;
-    if (g >= HW16) return;
+    if (g >= HWG) return;
     // frames of this batch: contiguous in the caller's buffer (zero-copy) or slots of the ring
-    const uint8_t *gbase = (src.cur ? src.cur : src.ring) + (size_t)g * 16;
+    const uint8_t *gbase = (src.cur ? src.cur : src.ring) + (size_t)g * VB;
     const int Rw = src.cur ? 0x7fffffff : src.R;  // no wrap in the caller's buffer
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + tid * 16;
-    const uint32_t slot_stride = nt * 16;
 
-    uint4 mk = make_uint4(~0u, ~0u, ~0u, ~0u);
+    unsigned mk[WPT];
+#pragma unroll
+    for (int k = 0; k < WPT; k++) mk[k] = ~0u;
     if (MASKED) {
-        const uint4 m = *reinterpret_cast<const uint4 *>(src.mask + (size_t)g * 16);
-        mk = make_uint4(m.x * 0xffu, m.y * 0xffu, m.z * 0xffu, m.w * 0xffu);  // {0,1} -> {0x00,0xff}
+        const unsigned *m = reinterpret_cast<const unsigned *>(src.mask + (size_t)g * VB);
+#pragma unroll
+        for (int k = 0; k < WPT; k++) mk[k] = m[k] * 0xffu;  // {0,1} -> {0x00,0xff}
     }
+    unsigned zero[WPT];
+#pragma unroll
+    for (int k = 0; k < WPT; k++) zero[k] = 0;
 
     // ---- history: frames t0-n+1 .. t0-1 -> slots 0 .. n-2 ; slot RS-1 = zeros -----------------
-    ring[(size_t)(RS - 1) * nt + tid] = make_uint4(0, 0, 0, 0);
+    sts_vec<WPT>(ring_s + (RS - 1) * slot_stride, zero);
     for (int p = 1; p < n; p++) {
         const long long th = t0 - n + p;
-        if (th >= 0) cp_async16(ring_s + (p - 1) * slot_stride, src.frame(th) + (size_t)g * 16);
-        else ring[(size_t)(p - 1) * nt + tid] = make_uint4(0, 0, 0, 0);
+        if (th >= 0) cp_async_vec<WPT>(ring_s + (p - 1) * slot_stride, src.frame(th) + (size_t)g * VB);
+        else sts_vec<WPT>(ring_s + (p - 1) * slot_stride, zero);
     }
     cp_async_commit();
     // ---- prime the pipeline: frames t0 .. t0+K-1 -> slots n-1 .. n+K-2 -------------------------
     int pf_slot = src.cur ? (int)(t0 - src.t0) : (int)(t0 % src.R);  // slot of the next frame to prefetch
     for (int i = 0; i < ST_K; i++) {
-        if (i < T) cp_async16(ring_s + (n - 1 + i) * slot_stride, gbase + (size_t)pf_slot * src.HW);
+        if (i < T) cp_async_vec<WPT>(ring_s + (n - 1 + i) * slot_stride, gbase + (size_t)pf_slot * src.HW);
         cp_async_commit();
         if (++pf_slot == Rw) pf_slot = 0;
     }
     cp_async_wait<ST_K>();  // history landed
 
-    unsigned sE[4] = {0, 0, 0, 0}, sO[4] = {0, 0, 0, 0};  // window sums, u16x2 (even / odd pixels)
+    unsigned sE[WPT], sO[WPT];  // window sums, u16x2 (even / odd pixels)
     {
-        unsigned aE[4] = {0, 0, 0, 0}, aO[4] = {0, 0, 0, 0};
-        for (int p = n - 1; p >= 1; p--) {
-            uint4 v = ring[(size_t)(p - 1) * nt + tid];
-            if (MASKED) {
-                v.x &= mk.x; v.y &= mk.y; v.z &= mk.z; v.w &= mk.w;
-                ring[(size_t)(p - 1) * nt + tid] = v;
-            }
-            const unsigned w[4] = {v.x, v.y, v.z, v.w};
-            uint4 o;
-            unsigned *ow = &o.x;
+        unsigned aE[WPT], aO[WPT];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < WPT; k++) sE[k] = sO[k] = aE[k] = aO[k] = 0;
+        for (int p = n - 1; p >= 1; p--) {
+            unsigned w[WPT], o[WPT];
+            lds_vec<WPT>(w, ring_s + (p - 1) * slot_stride);
+            if (MASKED) {
+#pragma unroll
+                for (int k = 0; k < WPT; k++) w[k] &= mk[k];
+                sts_vec<WPT>(ring_s + (p - 1) * slot_stride, w);
+            }
+#pragma unroll
+            for (int k = 0; k < WPT; k++) {
                 const unsigned e = ev(w[k]), d = od(w[k]);
                 sE[k] += e; sO[k] += d;
                 aE[k] = __vmaxu2(aE[k], e); aO[k] = __vmaxu2(aO[k], d);
-                ow[k] = pack_eo(aE[k], aO[k]);
+                o[k] = pack_eo(aE[k], aO[k]);
             }
-            smx[(size_t)p * nt + tid] = o;
+            sts_vec<WPT>(smx_s + p * slot_stride, o);
         }
     }
-    unsigned pE[4] = {0, 0, 0, 0}, pO[4] = {0, 0, 0, 0};  // prefix max of the current block
+    unsigned pE[WPT], pO[WPT];  // prefix max of the current block
+#pragma unroll
+    for (int k = 0; k < WPT; k++) pE[k] = pO[k] = 0;
 
-    int j = 0;                 // position inside the current block (blocks are anchored at t0)
-    int s_cur = n - 1;         // ring slot of the current frame
-    int s_old = RS - 1;        // ring slot of frame t-n (and destination of the next prefetch)
+    int j = 0;                                              // position inside the current block
+    uint32_t a_cur = ring_s + (n - 1) * slot_stride;        // smem address of the current frame's slot
+    uint32_t a_old = ring_s + (RS - 1) * slot_stride;       // frame t-n; destination of the next prefetch
+    const uint32_t a_end = ring_s + RS * slot_stride;
+    uint32_t a_smx = smx_s + slot_stride;                   // suffix max at position j+1
+    uint8_t *bout = bits + (size_t)g * WPT / 2;             // WPT*4 bits per thread and frame
+    const size_t bstride = (size_t)HWG * WPT / 2;
+    const uint8_t *pf_ptr = gbase + (size_t)pf_slot * src.HW;
     long long tg = t0;
     for (int i = 0; i < T; i++, tg++) {
         cp_async_wait<ST_K - 1>();  // this thread's copy of frame i has landed
-        uint4 xv = ring[(size_t)s_cur * nt + tid];
-        const uint4 ov = ring[(size_t)s_old * nt + tid];
+        unsigned xw[WPT], ow[WPT], mw[WPT];
+        lds_vec<WPT>(xw, a_cur);
+        lds_vec<WPT>(ow, a_old);
         if (MASKED) {
-            xv.x &= mk.x; xv.y &= mk.y; xv.z &= mk.z; xv.w &= mk.w;
-            ring[(size_t)s_cur * nt + tid] = xv;
+#pragma unroll
+            for (int k = 0; k < WPT; k++) xw[k] &= mk[k];
+            sts_vec<WPT>(a_cur, xw);
         }
-        uint4 mv = make_uint4(0, 0, 0, 0);
-        if (j + 1 < n) mv = smx[(size_t)(j + 1) * nt + tid];
-        // slot s_old is free now: fetch frame i+K into it
-        if (i + ST_K < T) cp_async16(ring_s + s_old * slot_stride, gbase + (size_t)pf_slot * src.HW);
+        if (j + 1 < n) lds_vec<WPT>(mw, a_smx);
+        else {
+#pragma unroll
+            for (int k = 0; k < WPT; k++) mw[k] = 0;
+        }
+        // slot a_old is free now: fetch frame i+K into it
+        if (i + ST_K < T) cp_async_vec<WPT>(a_old, pf_ptr);
         cp_async_commit();
-        if (++pf_slot == Rw) pf_slot = 0;
+        if (++pf_slot == Rw) { pf_slot = 0; pf_ptr = gbase; } else pf_ptr += src.HW;
 
         const int L = (int)(tg + 1 < n ? tg + 1 : n);
         const unsigned Tq = (unsigned)thr_s[i] * (unsigned)L;            // <= 255*128
         const unsigned Cpk = (0x7fffu - Tq) * 0x00010001u;                // per-half bias
-        const unsigned xw[4] = {xv.x, xv.y, xv.z, xv.w};
-        const unsigned ow[4] = {ov.x, ov.y, ov.z, ov.w};
-        const unsigned mw[4] = {mv.x, mv.y, mv.z, mv.w};
-        unsigned M[4];
+        unsigned M[WPT];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < WPT; k++) {
             const unsigned e = ev(xw[k]), d = od(xw[k]);
             sE[k] = sE[k] + e - ev(ow[k]);
             sO[k] = sO[k] + d - od(ow[k]);
@@ -156,31 +195,39 @@ temporal_kernel(FrameSrc src, long long t0, int T, int n, int HW16, const int *_
             M[k] = prmt(vE, vO, 0xFBD9u);  // sign-replicate bytes 1,5,3,7 -> 0x00/0xff per pixel
         }
         const unsigned q01 = (M[0] & 0x08040201u) | (M[1] & 0x80402010u);
-        const unsigned q23 = (M[2] & 0x08040201u) | (M[3] & 0x80402010u);
-        const unsigned r01 = q01 * 0x01010101u, r23 = q23 * 0x01010101u;
-        bits[(size_t)i * HW16 + g] = (uint16_t)prmt(r01, r23, 0x4473u);
+        const unsigned r01 = q01 * 0x01010101u;
+        if (WPT == 4) {
+            const unsigned q23 = (M[2 % WPT] & 0x08040201u) | (M[3 % WPT] & 0x80402010u);
+            const unsigned r23 = q23 * 0x01010101u;
+            *reinterpret_cast<uint16_t *>(bout) = (uint16_t)prmt(r01, r23, 0x4473u);
+        } else {
+            *bout = (uint8_t)(r01 >> 24);
+        }
+        bout += bstride;
 
         if (++j == n) {  // block complete: suffix max of its n frames, by position 1..n-1
             j = 0;
-            unsigned aE[4] = {0, 0, 0, 0}, aO[4] = {0, 0, 0, 0};
-            int s = s_cur;
-            for (int p = n - 1; p >= 1; p--) {
-                const uint4 v = ring[(size_t)s * nt + tid];
-                const unsigned w[4] = {v.x, v.y, v.z, v.w};
-                uint4 o;
-                unsigned *owp = &o.x;
+            a_smx = smx_s;
+            unsigned aE[WPT], aO[WPT];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < WPT; k++) aE[k] = aO[k] = 0;
+            uint32_t a = a_cur;
+            for (int p = n - 1; p >= 1; p--) {
+                unsigned w[WPT], o[WPT];
+                lds_vec<WPT>(w, a);
+#pragma unroll
+                for (int k = 0; k < WPT; k++) {
                     aE[k] = __vmaxu2(aE[k], ev(w[k]));
                     aO[k] = __vmaxu2(aO[k], od(w[k]));
-                    owp[k] = pack_eo(aE[k], aO[k]);
+                    o[k] = pack_eo(aE[k], aO[k]);
                 }
-                smx[(size_t)p * nt + tid] = o;
-                if (--s < 0) s = RS - 1;
+                sts_vec<WPT>(smx_s + p * slot_stride, o);
+                a = (a == ring_s) ? a_end - slot_stride : a - slot_stride;
             }
         }
-        if (++s_cur == RS) s_cur = 0;
-        if (++s_old == RS) s_old = 0;
+        a_smx += slot_stride;
+        a_cur += slot_stride; if (a_cur == a_end) a_cur = ring_s;
+        a_old += slot_stride; if (a_old == a_end) a_old = ring_s;
     }
     cp_async_wait<0>();
 }
@@ -341,23 +388,37 @@ static inline void stream_state_free(StreamState &s) {
     s.ok = 0;
 }
 
+// choose words-per-thread of the temporal kernel and derive its CTA size / shared memory
+static inline int stream_state_config(StreamState &s, int wpt) {
+    if (wpt != 2 && wpt != 4) return -1;
+    const size_t budget = 220 * 1024;
+    const size_t per_thread = (size_t)(2 * s.n + ST_K) * 4 * wpt;
+    const size_t per_warp = per_thread * 32;
+    const int threads = budget / per_warp > 32 ? (budget / per_warp > 64 ? 128 : 64) : 32;
+    if (per_thread * threads + s.max_batch > budget) return -1;
+    s.t_wpt = wpt;
+    s.t_smem_per_thread = per_thread;
+    s.t_threads = threads;
+    return 0;
+}
+
 static inline int stream_state_init(StreamState &s, int W, int H, int n, int device, int max_batch) {
     s.W = W; s.H = H; s.n = n; s.device = device; s.max_batch = max_batch; s.ok = 0;
     if (W % 32 != 0 || n < 2 || n > 128 || max_batch > 4096) return 0;  // generic kernel serves these
-    s.t_smem_per_thread = (size_t)(2 * n + ST_K) * 16;
     const size_t budget = 220 * 1024;
-    s.t_threads = (budget / (s.t_smem_per_thread * 32) > 32) ? 64 : 32;
-    if (s.t_smem_per_thread * s.t_threads + max_batch > budget) return 0;
+    if (stream_state_config(s, 2) != 0) return 0;
     if (cudaMalloc((void **)&s.d_bits, (size_t)max_batch * H * (W / 32) * sizeof(uint32_t)) != cudaSuccess) {
         cudaGetLastError();
         return 0;  // fall back to the generic per-frame kernel
     }
     s.sp_rows = 32;
-    if (cudaFuncSetAttribute(temporal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess ||
-        cudaFuncSetAttribute(temporal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess ||
-        cudaFuncSetAttribute(temporal_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
-        cudaFuncSetAttribute(temporal_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess)
+#define ST_SETATTR(K)                                                                                      \
+    if (cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess || \
+        cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess)       \
         return -1;
+    ST_SETATTR((temporal_kernel<false, 2>)) ST_SETATTR((temporal_kernel<true, 2>))
+    ST_SETATTR((temporal_kernel<false, 4>)) ST_SETATTR((temporal_kernel<true, 4>))
+#undef ST_SETATTR
     s.ok = 1;
     return 0;
 }
@@ -370,14 +431,18 @@ static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long t
                                        int dy_on, const int *d_thr, ActRing ring, uint8_t *dst,
                                        unsigned *npoints, uint32_t *points, int cap, cudaStream_t st,
                                        int *launches) {
-    const int HW16 = (int)((size_t)s.W * s.H / 16);
+    const int HWG = (int)((size_t)s.W * s.H / (4 * s.t_wpt));  // pixel groups = threads
     const int nt = s.t_threads;
     const size_t smem = s.t_smem_per_thread * nt + ((T + 15) & ~15);
-    const int grid = (HW16 + nt - 1) / nt;
-    if (src.mask)
-        temporal_kernel<true><<<grid, nt, smem, st>>>(src, timer0, T, s.n, HW16, d_thr, (uint16_t *)s.d_bits);
-    else
-        temporal_kernel<false><<<grid, nt, smem, st>>>(src, timer0, T, s.n, HW16, d_thr, (uint16_t *)s.d_bits);
+    const int grid = (HWG + nt - 1) / nt;
+    uint8_t *bits8 = reinterpret_cast<uint8_t *>(s.d_bits);
+    if (s.t_wpt == 2) {
+        if (src.mask) temporal_kernel<true, 2><<<grid, nt, smem, st>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
+        else temporal_kernel<false, 2><<<grid, nt, smem, st>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
+    } else {
+        if (src.mask) temporal_kernel<true, 4><<<grid, nt, smem, st>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
+        else temporal_kernel<false, 4><<<grid, nt, smem, st>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
+    }
     if (cudaGetLastError() != cudaSuccess) return -1;
     const int Wb = s.W / 32;
     const int strips = (Wb + SP_USE - 1) / SP_USE, bands = (s.H + s.sp_rows - 1) / s.sp_rows;
