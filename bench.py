@@ -215,6 +215,29 @@ def main_ours(a):
     fused_ms, fused_launches = 0.0, 0
     t0 = time.perf_counter()
     e0.record(ext)
+    # the two exchanges of the time-sharded path, with real payloads, inside the timed
+    # region: all-gather of this step's noise-sample triples, gather of this step's line records
+    CAP_REC = 8192
+    rec_buf = torch.zeros((CAP_REC, 6), dtype=torch.float64, device=dev) if world > 1 else None
+    rec_all = [torch.zeros_like(rec_buf) for _ in range(world)] if world > 1 else None
+    smp_buf = torch.zeros((64, 3), dtype=torch.int64, device=dev) if world > 1 else None
+    smp_all = [torch.zeros_like(smp_buf) for _ in range(world)] if world > 1 else None
+    gathered = 0
+
+    def exchange(res, step):
+        nonlocal gathered
+        rows = [[step * B + i, *l.tolist(), float(c[-1])] for i, (ls, cs) in enumerate(res) for l, c in zip(ls, cs)]
+        rows = rows[:CAP_REC - 1]
+        host = torch.zeros((CAP_REC, 6), dtype=torch.float64)
+        if rows:
+            host[:len(rows)] = torch.tensor(rows, dtype=torch.float64)
+        host[CAP_REC - 1, 0] = len(rows)
+        rec_buf.copy_(host)
+        dist.all_gather(smp_all, smp_buf)
+        dist.all_gather(rec_all, rec_buf)
+        if rank == 0:
+            gathered += int(sum(int(b[CAP_REC - 1, 0].item()) for b in rec_all))
+
     submit_dev(a.warmup)
     for s in range(a.steps):
         if s + 1 < a.steps:
@@ -223,6 +246,8 @@ def main_ours(a):
         nlines += sum(len(r[0]) for r in res)
         ms, nl = det._eng.fused_time()
         fused_ms += ms; fused_launches += nl
+        if world > 1:
+            exchange(res, s)
     e1.record(ext)
     barrier()
     wall = time.perf_counter() - t0
@@ -235,14 +260,7 @@ def main_ours(a):
     wall_max = float(el.item())
     value = world * a.steps * B / wall_max
 
-    # gather of detected segments to rank 0 (the only cross-GPU exchange of this path)
-    if world > 1:
-        cnt = torch.tensor([nlines], device=dev, dtype=torch.int64)
-        allc = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(allc, cnt)
-        nlines_total = int(sum(int(c.item()) for c in allc))
-    else:
-        nlines_total = nlines
+    nlines_total = gathered if world > 1 else nlines
 
     # ---- end to end through the public API with HOST (pinned) buffers -------------------------
     e2e = None

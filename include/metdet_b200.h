@@ -114,6 +114,25 @@ int mdb_submit_batch(mdb_handle h, const uint8_t *frames, int T, int on_device);
 int mdb_collect_batch(mdb_handle h, mdb_frame_info *infos, int32_t *lines, double *nonline_prob,
                       int32_t *raw_lines, uint8_t *dst_out, int dst_on_device);
 
+/* ---- time-sharded streams (one detector per GPU, each owning a chunk of the frame sequence) -----
+ * The reference is a single sequential loop (MetDetPy.py:184-227); these three calls are what lets
+ * G detectors reproduce it exactly on G chunks:
+ *  mdb_seek        start the frame counter (SlidingWindow.timer, utils.py:270) at a global index, so
+ *                  that warm-up rules (length = min(n, timer)) fire only at the true stream start.
+ *  mdb_noise_sums  the integer sums behind SNR_SW.update's noise sample (Detector.py:81-91) for every
+ *                  sample timer inside `frames` (global index of frames[0] = t0): sums[2i] = sum d,
+ *                  sums[2i+1] = sum d^2 for frame i (zero if that timer is no sample or its window
+ *                  starts before t0). Stateless. The EMA / threshold recurrence is then replayed on
+ *                  the host over the samples of all chunks.
+ *  mdb_submit_batch_thr  mdb_submit_batch with per-frame thresholds supplied by the caller instead of
+ *                  the handle's own recurrence. */
+int mdb_seek(mdb_handle h, int64_t timer);
+int mdb_noise_sums(const uint8_t *frames, int T, int on_device, int64_t t0, int width, int height,
+                   int window, int nz_interval, const int32_t *roi, const uint8_t *mask,
+                   uint64_t *sums, int device);
+int mdb_submit_batch_thr(mdb_handle h, const uint8_t *frames, int T, int on_device, const int32_t *thr,
+                         const double *thr_float, const double *snr);
+
 /* M3Detector.dst (Detector.py:371): the binary mask of the most recent detect, (H,W) uint8. */
 int mdb_get_dst(mdb_handle h, uint8_t *dst, int on_device);
 /* device pointer of the dst masks of the most recent batch ([T][H][W]); valid until the next call */

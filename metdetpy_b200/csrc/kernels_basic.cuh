@@ -15,10 +15,10 @@ __device__ __forceinline__ bool is_noise_sample(long long tau, int n, long long 
 
 __global__ void __launch_bounds__(256)
 noise_sample_kernel(FrameSrc src, int W, int n, long long timer0, long long std_interval, int r0,
-                    int c0, int rh, int rw, unsigned long long *acc) {
+                    int c0, int rh, int rw, unsigned long long *acc, long long min_tau) {
     const int i = blockIdx.y;
     const long long tau = timer0 + i + 1;
-    if (!is_noise_sample(tau, n, std_interval)) return;
+    if (tau < min_tau || !is_noise_sample(tau, n, std_interval)) return;
     const int L = (int)(tau < n ? tau : n);
     const long long t = tau - 1;
     unsigned long long d1 = 0, d2 = 0;

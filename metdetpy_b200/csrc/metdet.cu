@@ -75,7 +75,7 @@ struct mdb_detector {
     StreamState sk;
     BatchCtx ctx[NCTX];
     // host state
-    long long timer = 0, dy_timer = 0;
+    long long timer = 0, dy_timer = 0, seek0 = 0;
     long long launches = 0;
     long long submitted = 0, collected = 0;  // batch sequence numbers
     int last_T = 0;                           // frames in d_dst from the most recent batch
@@ -310,7 +310,7 @@ static int launch_noise_thr(mdb_detector *h, const FrameSrc &src, int T, long lo
     CK(cudaMemsetAsync(h->d_noise, 0, (size_t)T * 2 * sizeof(unsigned long long), h->stream));
     const int gx = std::max(1, std::min((rh * rw + 255) / 256, 592));
     noise_sample_kernel<<<dim3(gx, T), 256, 0, h->stream>>>(src, h->W, h->n, timer0, std_interval,
-                                                          c.roi[0], c.roi[1], rh, rw, h->d_noise);
+                                                          c.roi[0], c.roi[1], rh, rw, h->d_noise, 0);
     threshold_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_noise, T, timer0, h->n, std_interval,
                                              (long long)rh * rw, c.adaptive, c.sensitivity, h->d_thr,
                                              h->d_thrf, h->d_snr);
@@ -499,7 +499,8 @@ extern "C" int mdb_detect(mdb_handle h, mdb_frame_info *info, int32_t *lines, do
 }
 
 // ---- batched API -----------------------------------------------------------------------------
-extern "C" int mdb_submit_batch(mdb_handle h, const uint8_t *frames, int T, int on_device) {
+static int submit_impl(mdb_handle h, const uint8_t *frames, int T, int on_device, const int32_t *thr,
+                       const double *thrf, const double *snr) {
     if (!h || !frames) return fail(MDB_ERR_INVALID, "mdb_submit_batch: null argument");
     if (T < 1 || T > h->cfg.max_batch)
         return fail(MDB_ERR_INVALID, "mdb_submit_batch: T=%d outside 1..max_batch=%d", T, h->cfg.max_batch);
@@ -521,8 +522,15 @@ extern "C" int mdb_submit_batch(mdb_handle h, const uint8_t *frames, int T, int 
         CK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
         src = frame_src(h, nullptr, 0);
     }
-    int rc = launch_noise_thr(h, src, T, timer0);
-    if (rc) return rc;
+    int rc;
+    if (thr) {  // thresholds supplied by the caller (time-sharded streams): no local EMA recurrence
+        CK(cudaMemcpyAsync(h->d_thr, thr, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_thrf, thrf, T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_snr, snr, T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        rc = launch_noise_thr(h, src, T, timer0);
+        if (rc) return rc;
+    }
     rc = launch_fused(h, c, src, T, timer0, h->dy_timer);
     if (rc) return rc;
     if (on_device) {  // keep the last n-1 frames as history for the next batch
@@ -540,6 +548,63 @@ extern "C" int mdb_submit_batch(mdb_handle h, const uint8_t *frames, int T, int 
     h->submitted += 1;
     h->timer += T;
     h->dy_timer += T;
+    return MDB_OK;
+}
+
+extern "C" int mdb_submit_batch(mdb_handle h, const uint8_t *frames, int T, int on_device) {
+    return submit_impl(h, frames, T, on_device, nullptr, nullptr, nullptr);
+}
+
+extern "C" int mdb_submit_batch_thr(mdb_handle h, const uint8_t *frames, int T, int on_device,
+                                    const int32_t *thr, const double *thr_float, const double *snr) {
+    if (!thr || !thr_float || !snr) return fail(MDB_ERR_INVALID, "mdb_submit_batch_thr: null threshold arrays");
+    return submit_impl(h, frames, T, on_device, thr, thr_float, snr);
+}
+
+extern "C" int mdb_seek(mdb_handle h, int64_t timer) {
+    if (!h || timer < 0) return fail(MDB_ERR_INVALID, "mdb_seek: bad argument");
+    if (h->timer != 0 || h->submitted != 0) return fail(MDB_ERR_STATE, "mdb_seek: only before the first frame");
+    h->timer = h->dy_timer = timer;
+    h->seek0 = timer;
+    return MDB_OK;
+}
+
+extern "C" int mdb_noise_sums(const uint8_t *frames, int T, int on_device, int64_t t0, int width, int height,
+                              int window, int nz_interval, const int32_t *roi, const uint8_t *mask,
+                              uint64_t *sums, int device) {
+    if (!frames || !roi || !sums || T < 1 || width < 1 || height < 1 || window < 1 || t0 < 0)
+        return fail(MDB_ERR_INVALID, "mdb_noise_sums: bad arguments");
+    if (mdb_device_count() == 0) return fail(MDB_ERR_CUDA, "mdb_noise_sums: no CUDA device (no CPU fallback)");
+    CK(cudaSetDevice(device));
+    const size_t HW = (size_t)width * height;
+    uint8_t *d_frames = nullptr, *d_mask = nullptr;
+    unsigned long long *d_acc = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_acc, (size_t)T * 16);
+    if (e == cudaSuccess) e = cudaMemset(d_acc, 0, (size_t)T * 16);
+    if (e == cudaSuccess && !on_device) {
+        e = cudaMalloc((void **)&d_frames, (size_t)T * HW);
+        if (e == cudaSuccess) e = cudaMemcpy(d_frames, frames, (size_t)T * HW, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess && mask) {
+        e = cudaMalloc((void **)&d_mask, HW);
+        if (e == cudaSuccess) e = cudaMemcpy(d_mask, mask, HW, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) {
+        FrameSrc src;
+        src.ring = nullptr; src.cur = on_device ? frames : d_frames; src.t0 = t0; src.mask = d_mask; src.R = 1; src.HW = HW;
+        const int rh = roi[2] - roi[0], rw = roi[3] - roi[1];
+        const int gx = std::max(1, std::min((rh * rw + 255) / 256, 592));
+        // only samples whose whole window lies inside the supplied frames (or starts at global frame 0)
+        const long long min_tau = t0 == 0 ? 0 : t0 + window;
+        noise_sample_kernel<<<dim3(gx, T), 256>>>(src, width, window, t0, (long long)nz_interval * window, roi[0],
+                                                 roi[1], rh, rw, d_acc, min_tau);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpy(sums, d_acc, (size_t)T * 16, cudaMemcpyDeviceToHost);
+    }
+    if (d_frames) cudaFree(d_frames);
+    if (d_mask) cudaFree(d_mask);
+    if (d_acc) cudaFree(d_acc);
+    if (e != cudaSuccess) return fail(MDB_ERR_CUDA, "mdb_noise_sums: %s", cudaGetErrorString(e));
     return MDB_OK;
 }
 

@@ -1,0 +1,245 @@
+"""Time-sharding of one frame stream over several detectors (one per GPU) with exact results.
+
+The reference is one sequential loop (MetDetPy.py:184-227).  Its only cross-frame state is
+  * the n-frame window (utils.py:225-321)             -> each shard re-ingests a look-back halo,
+  * the dy-mask window over `act` (Detector.py:234-242) -> halo of 2n-2 frames in total,
+  * the noise EMA -> threshold (Detector.py:73-91, :225-229), a scalar recurrence over noise samples
+    taken at timers 2..n and every interval*n frames.
+So: every rank computes the integer noise sums of the sample timers inside its
+own chunk (`mdb_noise_sums`), the ranks all-gather those few numbers, every rank replays the scalar
+recurrence from t = 0 and gets bit-identical thresholds, then runs its chunk (+ halo, outputs of halo
+frames dropped) with those thresholds (`mdb_seek`, `mdb_submit_batch_thr`).  Frames never cross GPUs;
+the collectives move O(#samples) and O(#segments) values.  Line records are gathered to rank 0, which
+feeds the (sequential, stateful) MeteorCollector in frame order.
+
+The compute engine is injected, so the host logic (planning, exchange, replay, gather) is testable on
+CPU with gloo; `CudaEngine` is the product engine.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+_SENS = {"low": (2.0, 4.4), "normal": (1.2, 3.6), "high": (0.9, 3.0)}  # Detector.py:177-182
+_ABS_SENS = {"high": 3, "normal": 5, "low": 7}  # Detector.py:183
+
+
+@dataclass
+class Shard:
+    rank: int
+    start: int       # first frame whose result this rank reports
+    end: int         # one past the last
+    halo_start: int  # first frame this rank ingests (start - (2n-2), clipped at 0)
+
+
+def plan_shards(total_frames: int, world: int, n: int) -> list[Shard]:
+    """Contiguous chunks, as equal as possible; look-back halo of 2n-2 frames."""
+    base, rem = divmod(total_frames, world)
+    out, s = [], 0
+    for r in range(world):
+        e = s + base + (1 if r < rem else 0)
+        out.append(Shard(r, s, e, max(0, s - (2 * n - 2))))
+        s = e
+    return out
+
+
+def is_noise_sample(tau: int, n: int, interval: int) -> bool:
+    """SNR_SW.update's schedule (Detector.py:82-91); tau = SlidingWindow.timer after the update."""
+    return (1 < tau <= n) or (tau > n and interval * n > 0 and tau % (interval * n) == 0)
+
+
+def sigma_from_sums(s1: int, s2: int, L: int, roi_pixels: int) -> float:
+    """np.std of the ROI window from exact integer sums -- same operations, in the
+    same order, as the device threshold kernel."""
+    N = float(L * roi_pixels)
+    mean = float(s1) / N
+    var = float(s2) / N - mean * mean
+    return math.sqrt(var) if var > 0 else 0.0
+
+
+def replay_thresholds(samples: dict[int, float], total_frames: int, n: int, *, adaptive: bool,
+                      init_value: int, sensitivity: str, interval: int):
+    """EMA.update (utils.py:334-368) over all noise samples in timer order + LineDetector.update's
+    threshold rule (Detector.py:225-229). Returns (thr int32[T], thr_float f64[T], snr f64[T])."""
+    m0 = 1.0 - interval / 60.0
+    cur_m, warm, t_ema, value = m0, float(n), 0, 0.0
+    thr = _ABS_SENS[sensitivity] if adaptive else init_value
+    thr_f = float(thr)
+    a, b = _SENS[sensitivity]
+    out_thr = np.empty(total_frames, np.int32)
+    out_f = np.empty(total_frames, np.float64)
+    out_snr = np.empty(total_frames, np.float64)
+    for i in range(total_frames):
+        tau = i + 1
+        if is_noise_sample(tau, n, interval):
+            if tau not in samples:
+                raise KeyError(f"noise sample for timer {tau} is missing")
+            sigma = samples[tau]
+            if warm != 0.0:
+                k = (t_ema * (1.0 - m0)) * warm
+                if k < 1.0:
+                    u = 1.0 - k
+                    cur_m = m0 * (1.0 - u * u)
+                else:
+                    warm, cur_m = 0.0, m0
+            value = cur_m * value + (1.0 - cur_m) * sigma
+            t_ema += 1
+        if adaptive and value != 0.0:
+            thr_f = a * (value * value) + b
+            thr = int(round(thr_f))  # Python round(): half to even, as the reference
+        out_thr[i], out_f[i], out_snr[i] = thr, thr_f, value
+    return out_thr, out_f, out_snr
+
+
+# ---------------------------------------------------------------------------------------------
+class CudaEngine:
+    """Product engine: libmetdet_b200 on one GPU."""
+
+    def __init__(self, mask: np.ndarray, n: int, fps: float, cfg, *, device: int = 0, max_batch: int = 64,
+                 apply_mask: bool = False):
+        from . import _lib
+        from .detector import select_subarea
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.mask = np.ascontiguousarray(mask, np.uint8)
+        self.n, self.fps, self.cfg, self.device, self.max_batch = n, fps, cfg, device, max_batch
+        self.apply_mask = apply_mask
+        self.roi = select_subarea(self.mask, cfg.binary.area)
+        self.roi_pixels = (self.roi[2] - self.roi[0]) * (self.roi[3] - self.roi[1])
+
+    def noise_sums(self, frames: np.ndarray, t0: int) -> np.ndarray:
+        """(T,2) uint64 integer sums for the frames' sample timers (mdb_noise_sums)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        T, H, W = frames.shape
+        sums = np.zeros((T, 2), np.uint64)
+        roi = (C.c_int32 * 4)(*self.roi)
+        self._lib.check(self.lib.mdb_noise_sums(frames.ctypes.data, T, 0, t0, W, H, self.n,
+                                                int(self.cfg.binary.interval), roi,
+                                                self.mask.ctypes.data if self.apply_mask else None,
+                                                sums.ctypes.data, self.device), "mdb_noise_sums")
+        return sums
+
+    def detect_chunk(self, frames: np.ndarray, t0: int, thr, thr_f, snr, want_dst: bool = False):
+        """Run frames (global index of frames[0] = t0) with the given per-frame thresholds.
+        Returns per-frame (lines, cls_pred) and, optionally, the masks."""
+        from .detector import M3Detector
+        det = M3Detector(self.n / self.fps + 1e-9, self.fps, self.mask, 10, self.cfg, None, device=self.device,
+                         max_batch=self.max_batch, apply_mask=self.apply_mask)
+        eng = det._eng
+        self._lib.check(self.lib.mdb_seek(eng.handle, t0), "mdb_seek")
+        frames = np.ascontiguousarray(frames, np.uint8)
+        res, dsts = [], []
+        thr = np.ascontiguousarray(thr, np.int32)
+        thr_f = np.ascontiguousarray(thr_f, np.float64)
+        snr = np.ascontiguousarray(snr, np.float64)
+        for s in range(0, len(frames), self.max_batch):
+            T = min(self.max_batch, len(frames) - s)
+            self._lib.check(self.lib.mdb_submit_batch_thr(eng.handle, frames[s:s + T].ctypes.data, T, 0,
+                                                          thr[s:s + T].ctypes.data, thr_f[s:s + T].ctypes.data,
+                                                          snr[s:s + T].ctypes.data), "mdb_submit_batch_thr")
+            det._pending = [T]
+            dst = np.empty((T,) + frames.shape[1:], np.uint8) if want_dst else None
+            self._lib.check(self.lib.mdb_collect_batch(eng.handle, C.byref(eng.infos), eng.lines.ctypes.data,
+                                                       eng.prob.ctypes.data, eng.raw.ctypes.data,
+                                                       dst.ctypes.data if want_dst else None, 0), "collect")
+            res += [det._unpack(i) for i in range(T)]
+            if want_dst:
+                dsts.append(dst)
+        det.close()
+        return res, (np.concatenate(dsts) if want_dst else None)
+
+
+# ---------------------------------------------------------------------------------------------
+def local_samples(engine, frames: np.ndarray, shard: Shard, n: int, interval: int):
+    """(timer, sum d, sum d^2) of the noise samples this rank owns: timers in (start, end]."""
+    sums = engine.noise_sums(frames, shard.halo_start)
+    out = []
+    for tau in range(shard.start + 1, shard.end + 1):
+        if is_noise_sample(tau, n, interval):
+            i = tau - 1 - shard.halo_start
+            out.append((tau, int(sums[i, 0]), int(sums[i, 1])))
+    return out
+
+
+def exchange_samples(mine: Sequence[tuple], group=None, device="cpu") -> list[tuple]:
+    """all-gather of the ranks' (timer, s1, s2) triples (int64; a few dozen values)."""
+    import torch
+    import torch.distributed as dist
+    if group is None and not (dist.is_available() and dist.is_initialized()):
+        return sorted(mine)
+    world = dist.get_world_size(group)
+    cnt = torch.tensor([len(mine)], dtype=torch.int64, device=device)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt, group=group)
+    cap = max(1, int(max(int(c.item()) for c in cnts)))
+    buf = torch.zeros((cap, 3), dtype=torch.int64, device=device)
+    if mine:
+        buf[:len(mine)] = torch.tensor(mine, dtype=torch.int64, device=device)
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf, group=group)
+    out = []
+    for c, b in zip(cnts, bufs):
+        out += [tuple(int(v) for v in row) for row in b[:int(c.item())].cpu().tolist()]
+    return sorted(out)
+
+
+def gather_lines(per_frame, first_frame: int, group=None, device="cpu"):
+    """Gather (frame, x1, y1, x2, y2, nonline_prob) records to rank 0 (others get None).
+    per_frame: list of (lines, cls_pred) for frames first_frame, first_frame+1, ..."""
+    import torch
+    import torch.distributed as dist
+    rec = []
+    for i, (lines, cls) in enumerate(per_frame):
+        rows = np.asarray(lines).reshape(-1, 4)
+        if len(rows) == 0:
+            continue
+        probs = np.asarray(cls).reshape(len(rows), -1)[:, -1]
+        for row, p in zip(rows, probs):
+            rec.append([first_frame + i, *[int(v) for v in row], float(p)])
+    if group is None and not (dist.is_available() and dist.is_initialized()):
+        return rec
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    cnt = torch.tensor([len(rec)], dtype=torch.int64, device=device)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt, group=group)
+    cap = max(1, int(max(int(c.item()) for c in cnts)))
+    buf = torch.zeros((cap, 6), dtype=torch.float64, device=device)
+    if rec:
+        buf[:len(rec)] = torch.tensor(rec, dtype=torch.float64, device=device)
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf, group=group)  # NCCL has no gather-to-one for ragged data; counts trim it
+    if rank != 0:
+        return None
+    out = []
+    for c, b in zip(cnts, bufs):
+        out += b[:int(c.item())].cpu().tolist()
+    out.sort(key=lambda r: r[0])
+    return [[int(r[0]), int(r[1]), int(r[2]), int(r[3]), int(r[4]), r[5]] for r in out]
+
+
+def detect_sharded(engine, frames: np.ndarray, shard: Shard, total_frames: int, n: int, cfg, *, group=None,
+                   device="cpu", want_dst: bool = False):
+    """One rank's part of a time-sharded run. `frames` = frames halo_start .. end-1 of the stream.
+    Returns (per-frame results for start..end-1, dst or None, gathered records on rank 0)."""
+    b = cfg.binary
+    mine = local_samples(engine, frames, shard, n, int(b.interval))
+    allsum = exchange_samples(mine, group, device)
+    samples = {}
+    for tau, s1, s2 in allsum:
+        samples[tau] = sigma_from_sums(s1, s2, min(n, tau), engine.roi_pixels)
+    # a rank only needs thresholds up to its own end; samples of later ranks are ignored by the replay
+    thr, thr_f, snr = replay_thresholds({k: v for k, v in samples.items() if k <= shard.end}, shard.end, n,
+                                        adaptive=bool(b.adaptive_bi_thre), init_value=int(b.init_value),
+                                        sensitivity=b.sensitivity, interval=int(b.interval))
+    h0 = shard.halo_start
+    res, dst = engine.detect_chunk(frames, h0, thr[h0:shard.end], thr_f[h0:shard.end], snr[h0:shard.end], want_dst)
+    skip = shard.start - h0
+    res = res[skip:]
+    if dst is not None:
+        dst = dst[skip:]
+    records = gather_lines(res, shard.start, group, device)
+    return res, dst, records, (thr[shard.start:shard.end], thr_f[shard.start:shard.end], snr[shard.start:shard.end])

@@ -230,3 +230,37 @@ def test_error_behaviour():
     assert len(lines) == 0 and cls.shape == (0, 10)
     with pytest.raises(ValueError):
         M3Detector(100, 30, np.ones((8, 8), np.uint8), 10, BinaryCfg())  # window 3000 > 255
+
+
+@pytest.mark.parametrize("name,world", [("synth_384x216_n12_dyon_mask", 3), ("clip_192x144_n25", 2),
+                                        ("synth_203x157_n3_high", 4)])
+def test_time_sharded_equals_reference_golden(name, world):
+    """Time-sharding with `world` virtual ranks on one GPU: per-shard noise sums
+    (mdb_noise_sums) -> merged -> threshold replay -> per-shard run with halo (mdb_seek,
+    mdb_submit_batch_thr).  Every frame must equal the reference's sequential run."""
+    from metdetpy_b200 import sharding as S
+    g = load_det_case(name)
+    cfg, n, T = _cfg(g["cfg"]), g["n"], len(g["frames"])
+    eng = S.CudaEngine(g["mask"], n, g["fps"], cfg, max_batch=16)
+    assert tuple(eng.roi) == tuple(g["std_roi"])
+    shards = S.plan_shards(T, world, n)
+    samples = {}
+    for sh in shards:
+        for tau, s1, s2 in S.local_samples(eng, g["frames"][sh.halo_start:sh.end], sh, n, g["cfg"]["interval"]):
+            samples[tau] = S.sigma_from_sums(s1, s2, min(n, tau), eng.roi_pixels)
+    c = g["cfg"]
+    thr, thr_f, snr = S.replay_thresholds(samples, T, n, adaptive=c["adaptive"], init_value=c["init_value"],
+                                          sensitivity=c["sensitivity"], interval=c["interval"])
+    assert np.array_equal(thr, g["bi_threshold"])
+    assert np.allclose(snr, g["snr"], rtol=1e-12, atol=0)
+    for sh in shards:
+        h0 = sh.halo_start
+        res, dst = eng.detect_chunk(g["frames"][h0:sh.end], h0, thr[h0:sh.end], thr_f[h0:sh.end], snr[h0:sh.end],
+                                    want_dst=True)
+        for t in range(sh.start, sh.end):
+            assert np.array_equal(dst[t - h0], g["dst"][t]), (sh.rank, t)
+            lines, cls = res[t - h0]
+            ref = ragged_get(g["nms_lines"], g["nms_offs"], t)
+            refc = ragged_get(g["cls_pred"], g["nms_offs"], t)
+            raw = ragged_get(g["raw_lines"], g["raw_offs"], t)
+            assert_nms_equivalent(lines, np.asarray(cls).reshape(-1, 10)[:, -1], ref, refc[:, -1], raw, t)
