@@ -34,6 +34,12 @@ __device__ __forceinline__ int rho_of(int x, int y, int n) {
     return __float2int_rn(r);  // cvRound: round half to even
 }
 
+// same, with the angle's cos/sin already in registers (thread n owns angle n: reading c_trig[2*n]
+// from every lane would serialise on the constant cache)
+__device__ __forceinline__ int rho_cs(int x, int y, float c, float s) {
+    return __float2int_rn(__fadd_rn(__fmul_rn((float)x, c), __fmul_rn((float)y, s)));
+}
+
 __device__ __forceinline__ void bitonic_sort_u32(uint32_t *a, int npow2, int tid, int nthreads) {
     for (int k = 2; k <= npow2; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -136,7 +142,7 @@ ppht_order_kernel(int T, int cap, const unsigned *__restrict__ npoints, uint16_t
 __global__ void __launch_bounds__(HOUGH_THREADS)
 hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
                   const uint32_t *__restrict__ points, const uint16_t *__restrict__ order,
-                  int32_t *lines_out, int *nlines_out) {
+                  int32_t *lines_out, int *nlines_out, unsigned *queue, long long *prof) {
     extern __shared__ uint32_t h_sm[];
     uint32_t *keys = h_sm;                                            // [cap]
     uint16_t *idx = reinterpret_cast<uint16_t *>(keys + P.cap);       // [cap] visiting order
@@ -147,14 +153,24 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
     __shared__ unsigned s_on[HOUGH_THREADS / 32], s_inb[HOUGH_THREADS / 32];
     __shared__ int s_ctl[8];
     __shared__ int s_base[MDB_HOUGH_ANGLES + 1];
+    __shared__ int s_next;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = P.W, H = P.H;
+    const float my_c = c_trig[2 * (tid < MDB_HOUGH_ANGLES ? tid : 0)], my_s = c_trig[2 * (tid < MDB_HOUGH_ANGLES ? tid : 0) + 1];
 
-    for (int t = blockIdx.x; t < T; t += gridDim.x) {
+    for (;;) {
+        // frames are handed out dynamically: their cost varies by orders of magnitude
+        __syncthreads();
+        if (tid == 0) s_next = (int)atomicAdd(queue, 1u);
+        __syncthreads();
+        const int t = s_next;
+        if (t >= T) break;
         const unsigned Nu = npoints[t];
         if (Nu == 0) { if (tid == 0) nlines_out[t] = 0; continue; }
         if (Nu > (unsigned)P.cap) { if (tid == 0) nlines_out[t] = -1; continue; }  // overflow path
         const int N = (int)Nu;
+        const long long pc0 = clock64();
+        long long p_setup = 0, p_vote = 0, p_walk = 0, p_unvote = 0, n_vote = 0, n_line = 0;
         const int line_gap = line_gap_of(P, Nu);
         int32_t *lines = lines_out + (size_t)t * P.max_lines * 4;
         int np2 = 1;
@@ -169,9 +185,10 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
         // per-angle rho interval of this frame's points
         int mn = INT_MAX, mx = INT_MIN;
         if (tid < MDB_HOUGH_ANGLES) {
+#pragma unroll 4
             for (int i = 0; i < N; i++) {
                 const uint32_t k = keys[i];
-                const int r = rho_of(k & 0xffffu, k >> 16, tid);
+                const int r = rho_cs(k & 0xffffu, k >> 16, my_c, my_s);
                 mn = min(mn, r); mx = max(mx, r);
             }
             s_base[tid + 1] = mx - mn + 1;
@@ -195,14 +212,20 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
 
         int par = 0;
         bool sat = false;
+        p_setup = clock64() - pc0;
+        int pi_n = idx[N - 1];
+        uint32_t key_n = keys[pi_n];
         for (int s = N - 1; s >= 0; s--) {
-            const int pi = idx[s];
+            long long c0 = clock64();
+            // candidate s was fetched one iteration ago; fetch candidate s-1 now (keys / order never change)
+            const int pi = pi_n;
+            const uint32_t key = key_n;
+            if (s > 0) { pi_n = idx[s - 1]; key_n = keys[pi_n]; }
             if ((rm[pi >> 5] >> (pi & 31)) & 1u) continue;  // removed by an earlier line (uniform)
-            const uint32_t key = keys[pi];
             const int x = key & 0xffffu, y = key >> 16;
             int best = INT_MIN;
             if (tid < MDB_HOUGH_ANGLES) {
-                const int r = rho_of(x, y, tid);
+                const int r = rho_cs(x, y, my_c, my_s);
                 const int v = (int)myrow[r] + 1;
                 myrow[r] = (int16_t)v;
                 sat |= v >= 32767;
@@ -214,7 +237,9 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
 #pragma unroll
             for (int k = 0; k < HOUGH_THREADS / 32; k++) best = max(best, s_red[par][k]);
             par ^= 1;
+            p_vote += clock64() - c0; n_vote++;
             if ((best >> 8) < P.threshold) continue;
+            c0 = clock64(); n_line++;
             const int max_n = 255 - (best & 255);
 
             // ---- line: find both ends (mask unchanged meanwhile), 256 steps per round ----------
@@ -242,6 +267,10 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
                         const unsigned inw = s_inb[w];
                         const int wbase = base + w * 32;
                         const int ob = inw == 0xffffffffu ? INT_MAX : wbase + __ffs(~inw) - 1;
+                        if (onw == 0xffffffffu && wbase - last_on - 1 <= line_gap) {  // solid run: no per-bit work
+                            last_on = wbase + 31;
+                            continue;
+                        }
                         while (onw) {
                             const int io = wbase + __ffs(onw) - 1;
                             onw &= onw - 1;
@@ -260,6 +289,7 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
             const bool good = abs(ex1 - ex0) >= P.min_len || abs(ey1 - ey0) >= P.min_len;
             if (tid == 0) s_ctl[1] = 0;
             __syncthreads();
+            p_walk += clock64() - c0; c0 = clock64();
             for (int k = 0; k < 2; k++)
                 for (int i = tid + k; i <= ends[k]; i += HOUGH_THREADS) {  // k=1 skips the shared start pixel
                     int j1, i1;
@@ -273,14 +303,37 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
             __syncthreads();
             if (good) {
                 const int nw = s_ctl[1];
-                if (tid < MDB_HOUGH_ANGLES)
-                    for (int q = 0; q < nw; q++) {
-                        const uint32_t k2 = keys[wl[q]];
-                        const int r = rho_of(k2 & 0xffffu, k2 >> 16, tid);
-                        const int v = (int)myrow[r] - 1;
-                        myrow[r] = (int16_t)v;
-                        sat |= v <= -32768;
+                if (tid < MDB_HOUGH_ANGLES) {
+                    // four pixels per round: the four cell reads are issued together; equal cells inside
+                    // a round are forwarded through registers so the result equals the sequential order
+                    int q = 0;
+                    for (; q + 4 <= nw; q += 4) {
+                        int r[4], v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const uint32_t k2 = keys[wl[q + u]];
+                            r[u] = rho_cs(k2 & 0xffffu, k2 >> 16, my_c, my_s);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) v[u] = (int)myrow[r[u]];
+                        v[0] -= 1;
+                        v[1] = (r[1] == r[0] ? v[0] : v[1]) - 1;
+                        v[2] = (r[2] == r[1] ? v[1] : (r[2] == r[0] ? v[0] : v[2])) - 1;
+                        v[3] = (r[3] == r[2] ? v[2] : (r[3] == r[1] ? v[1] : (r[3] == r[0] ? v[0] : v[3]))) - 1;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            myrow[r[u]] = (int16_t)v[u];
+                            sat |= v[u] <= -32768;
+                        }
                     }
+                    for (; q < nw; q++) {
+                        const uint32_t k2 = keys[wl[q]];
+                        const int rc = rho_cs(k2 & 0xffffu, k2 >> 16, my_c, my_s);
+                        const int v1 = (int)myrow[rc] - 1;
+                        myrow[rc] = (int16_t)v1;
+                        sat |= v1 <= -32768;
+                    }
+                }
                 if (tid == 0) {
                     const int li = s_ctl[2];
                     if (li < P.max_lines) {
@@ -291,6 +344,12 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
                 }
             }
             __syncthreads();
+            p_unvote += clock64() - c0;
+        }
+        if (prof && tid == 0) {
+            long long *o = prof + (size_t)t * 10;
+            o[0] = N; o[1] = p_setup; o[2] = p_vote; o[3] = p_walk; o[4] = p_unvote; o[5] = 0;
+            o[6] = n_vote; o[7] = n_line; o[8] = clock64() - pc0; o[9] = s_ctl[2];
         }
         if (sat) s_ctl[3] = 1;
         __syncthreads();
@@ -318,6 +377,7 @@ hough_tier2_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
     const int W = P.W, H = P.H, numrho = P.numrho, half = (numrho - 1) / 2;
     int32_t *accum = accum_slots + (size_t)blockIdx.x * MDB_HOUGH_ANGLES * numrho;
     int32_t *myrow = accum + (size_t)(tid < MDB_HOUGH_ANGLES ? tid : 0) * numrho + half;
+    const float my_c = c_trig[2 * (tid < MDB_HOUGH_ANGLES ? tid : 0)], my_s = c_trig[2 * (tid < MDB_HOUGH_ANGLES ? tid : 0) + 1];
 
     for (int t = blockIdx.x; t < T; t += gridDim.x) {
         const unsigned Nu = npoints[t];
@@ -353,7 +413,7 @@ hough_tier2_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
         if (tid < MDB_HOUGH_ANGLES)
             for (int s = N - 1; s >= 0 && s >= N - HOUGH_PREFETCH; s--) {
                 const uint32_t k = keys[idx[s]];
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(myrow + rho_of(k & 0xffffu, k >> 16, tid)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(myrow + rho_cs(k & 0xffffu, k >> 16, my_c, my_s)));
             }
         int par = 0;
         p_setup = clock64() - pc0;
@@ -362,14 +422,14 @@ hough_tier2_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
             const int pi = idx[s];
             if (tid < MDB_HOUGH_ANGLES && s >= HOUGH_PREFETCH) {
                 const uint32_t k = keys[idx[s - HOUGH_PREFETCH]];
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(myrow + rho_of(k & 0xffffu, k >> 16, tid)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(myrow + rho_cs(k & 0xffffu, k >> 16, my_c, my_s)));
             }
             if ((rm[pi >> 5] >> (pi & 31)) & 1u) continue;  // removed by an earlier line (uniform)
             const uint32_t key = keys[pi];
             const int x = key & 0xffffu, y = key >> 16;
             int best = INT_MIN;
             if (tid < MDB_HOUGH_ANGLES) {
-                const int r = rho_of(x, y, tid);
+                const int r = rho_cs(x, y, my_c, my_s);
                 const int v = __ldcg(myrow + r) + 1;  // L2 only: cells are also updated by REDs
                 __stcg(myrow + r, v);
                 best = v * 256 + (255 - tid);  // max value first, lowest angle on ties
@@ -451,7 +511,7 @@ hough_tier2_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
                 if (tid < MDB_HOUGH_ANGLES)
                     for (int q = 0; q < nw; q++) {
                         const uint32_t k2 = keys[wl[q]];
-                        atomicAdd(myrow + rho_of(k2 & 0xffffu, k2 >> 16, tid), -1);  // RED, no return
+                        atomicAdd(myrow + rho_cs(k2 & 0xffffu, k2 >> 16, my_c, my_s), -1);  // RED, no return
                     }
                 if (tid == 0) {
                     const int li = s_ctl[2];
@@ -536,6 +596,13 @@ hough_tier3_kernel(HoughParams P, int T, const uint8_t *dst, uint32_t *keys, uin
     const int tid = threadIdx.x;
     const int W = P.W, H = P.H, numrho = P.numrho, half = (numrho - 1) / 2;
     volatile uint32_t *vbitmap = bitmap;
+    __shared__ int s_any;
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    for (int t = tid; t < T; t += HOUGH_THREADS)
+        if (nlines_all[t] == -1) s_any = 1;
+    __syncthreads();
+    if (!s_any) return;  // the usual case: no dense frame in this batch
     for (int t = 0; t < T; t++) {
     if (nlines_all[t] != -1) continue;
     __syncthreads();

@@ -21,14 +21,19 @@ noise_sample_kernel(FrameSrc src, int W, int n, long long timer0, long long std_
     if (tau < min_tau || !is_noise_sample(tau, n, std_interval)) return;
     const int L = (int)(tau < n ? tau : n);
     const long long t = tau - 1;
+    __shared__ const uint8_t *fp[256];  // window frame pointers (n <= 255), resolved once per block
+    for (int k = threadIdx.x; k < L; k += blockDim.x) fp[k] = src.frame(t - k);
+    __syncthreads();
     unsigned long long d1 = 0, d2 = 0;
     const int total = rh * rw;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
         const int y = r0 + q / rw, x = c0 + q % rw;
         const size_t p = (size_t)y * W + x;
+        const unsigned mk = src.mask ? src.mask[p] : 1u;
         unsigned sx = 0, sxx = 0;
+#pragma unroll 4
         for (int k = 0; k < L; k++) {
-            unsigned v = src.px(t - k, p);
+            const unsigned v = fp[k][p] * mk;
             sx += v;
             sxx += v * v;
         }
@@ -140,14 +145,19 @@ fused_frame_kernel(FrameSrc src, int W, int H, int n, long long t, int L, long l
     const int x0 = blockIdx.x * V1_TW - 4, y0 = blockIdx.y * V1_TH - 4;
     const int thr = *thr_ptr;
     const int nwin = (int)((t + 1) < n ? (t + 1) : n);  // frames that exist in the window
+    __shared__ const uint8_t *fp[256];  // window frame pointers, resolved once per block
+    for (int k = tid; k < nwin; k += 256) fp[k] = src.frame(t - k);
+    __syncthreads();
     // stage 0: diff on the whole region, replicated border (medianBlur's border mode)
     for (int q = tid; q < V1_RW * V1_RH; q += 256) {
         const int rx = q % V1_RW, ry = q / V1_RW;
         const int gx = min(max(x0 + rx, 0), W - 1), gy = min(max(y0 + ry, 0), H - 1);
         const size_t p = (size_t)gy * W + gx;
+        const unsigned mk = src.mask ? src.mask[p] : 1u;
         unsigned mx = 0, sm = 0;
+#pragma unroll 4
         for (int k = 0; k < nwin; k++) {
-            unsigned v = src.px(t - k, p);
+            const unsigned v = fp[k][p] * mk;
             mx = max(mx, v);
             sm += v;
         }
@@ -240,11 +250,15 @@ fused_frame_kernel(FrameSrc src, int W, int H, int n, long long t, int L, long l
 __global__ void stack_readback_kernel(FrameSrc src, size_t HW, int n, long long t, int L,
                                       uint8_t *mx_out, uint8_t *mean_out, uint32_t *sum_out) {
     const int nwin = (int)((t + 1) < n ? (t + 1) : n);
+    __shared__ const uint8_t *fp[256];
+    for (int k = threadIdx.x; k < nwin; k += blockDim.x) fp[k] = src.frame(t - k);
+    __syncthreads();
     for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < HW;
          p += (size_t)gridDim.x * blockDim.x) {
+        const unsigned mk = src.mask ? src.mask[p] : 1u;
         unsigned mx = 0, sm = 0;
         for (int k = 0; k < nwin; k++) {
-            unsigned v = src.px(t - k, p);
+            const unsigned v = fp[k][p] * mk;
             mx = max(mx, v);
             sm += v;
         }

@@ -68,6 +68,7 @@ struct mdb_detector {
     unsigned *d_npoints = nullptr;
     uint32_t *d_points = nullptr;
     uint16_t *d_order = nullptr;  // [T][cap] PPHT visiting order per frame
+    unsigned *d_queue = nullptr;  // work-queue head of the tier-1 Hough kernel
     int32_t *d_lines = nullptr;
     int32_t *d_accum = nullptr;   // tier-2/3 accumulators [slots][180][numrho]
     uint32_t *d_bitmap = nullptr, *d_walk = nullptr, *d_okeys = nullptr, *d_oidx = nullptr;  // tier 3
@@ -120,7 +121,7 @@ static void free_all(mdb_detector *h) {
     if (h->cstream) cudaStreamSynchronize(h->cstream);
     void *dev[] = {h->d_ring, h->d_mask, h->d_dst, h->d_act, h->d_state, h->d_noise, h->d_thr, h->d_nlines,
                    h->d_thrf, h->d_snr, h->d_npoints, h->d_points, h->d_order, h->d_lines, h->d_accum,
-                   h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_prof};
+                   h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_prof, h->d_queue};
     for (void *p : dev)
         if (p) cudaFree(p);
     stream_state_free(h->sk);
@@ -226,6 +227,7 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     ALLOC(h->d_npoints, T * sizeof(unsigned));
     ALLOC(h->d_points, (size_t)T * MDB_POINT_CAP * sizeof(uint32_t));
     ALLOC(h->d_order, (size_t)T * MDB_POINT_CAP * sizeof(uint16_t));
+    ALLOC(h->d_queue, sizeof(unsigned));
     ALLOC(h->d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t));
     ALLOC(h->d_accum, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t));
     ALLOC(h->d_bitmap, bm_words * sizeof(uint32_t));
@@ -349,9 +351,10 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
 }
 
 static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
+    CK(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), h->stream));
     ppht_order_kernel<<<T, 32, MDB_POINT_CAP * 2, h->stream>>>(T, MDB_POINT_CAP, h->d_npoints, h->d_order);
     hough_smem_kernel<<<std::min(T, h->sm_count), HOUGH_THREADS, HOUGH_SMEM_BYTES + HOUGH_TABLE_BYTES, h->stream>>>(
-        h->hp, T, h->d_npoints, h->d_points, h->d_order, h->d_lines, h->d_nlines);
+        h->hp, T, h->d_npoints, h->d_points, h->d_order, h->d_lines, h->d_nlines, h->d_queue, h->d_prof);
     hough_tier2_kernel<<<std::min(T, h->slots), HOUGH_THREADS, HOUGH_SMEM_BYTES, h->stream>>>(
         h->hp, T, h->d_npoints, h->d_points, h->d_accum, h->d_lines, h->d_nlines, h->d_prof);
     if (!h->d_okeys) {  // tier-3 scratch, allocated once

@@ -356,27 +356,36 @@ dst_kernel(ActRing ring, int W, int H, int T, int n, long long dy0, int dy_on, i
             out_bits = act;
             yo = yy;
         }
-        if (lane_out && yo >= y0 && yo < y0 + rows && yo < H) {
-            uint4 a = make_uint4(0, 0, 0, 0), b = a;
-            if (out_bits) {
-                a = make_uint4(nib_to_bytes(out_bits & 15u), nib_to_bytes((out_bits >> 4) & 15u),
-                               nib_to_bytes((out_bits >> 8) & 15u), nib_to_bytes((out_bits >> 12) & 15u));
-                b = make_uint4(nib_to_bytes((out_bits >> 16) & 15u), nib_to_bytes((out_bits >> 20) & 15u),
-                               nib_to_bytes((out_bits >> 24) & 15u), nib_to_bytes(out_bits >> 28));
-                const unsigned c = __popc(out_bits);
-                unsigned slot = atomicAdd(npoints + t, c);
-                unsigned ob = out_bits;
-                while (ob) {
-                    const int bpos = __ffs(ob) - 1;
-                    ob &= ob - 1;
-                    if (slot < (unsigned)cap)
-                        points[(size_t)t * cap + slot] = ((unsigned)yo << 16) | (unsigned)(wx * 32 + bpos);
-                    slot++;
+        if (yo >= y0 && yo < y0 + rows && yo < H) {  // warp-uniform
+            uint8_t *orow = dst + (size_t)t * W * H + (size_t)yo * W + (size_t)strip * SP_USE * 32;
+            const bool mine = lane_out;
+            if (!__any_sync(FULL, mine && out_bits != 0)) {
+                // the common case: nothing on in this 960-pixel row segment -> fully coalesced zero fill
+                const int nbytes = min(SP_USE, Wb - strip * SP_USE) * 32;
+                for (int off = lane * 16; off < nbytes; off += 512)
+                    __stcs(reinterpret_cast<uint4 *>(orow + off), make_uint4(0, 0, 0, 0));
+            } else if (mine) {
+                uint4 a = make_uint4(0, 0, 0, 0), b = a;
+                if (out_bits) {
+                    a = make_uint4(nib_to_bytes(out_bits & 15u), nib_to_bytes((out_bits >> 4) & 15u),
+                                   nib_to_bytes((out_bits >> 8) & 15u), nib_to_bytes((out_bits >> 12) & 15u));
+                    b = make_uint4(nib_to_bytes((out_bits >> 16) & 15u), nib_to_bytes((out_bits >> 20) & 15u),
+                                   nib_to_bytes((out_bits >> 24) & 15u), nib_to_bytes(out_bits >> 28));
+                    const unsigned c = __popc(out_bits);
+                    unsigned slot = atomicAdd(npoints + t, c);
+                    unsigned ob = out_bits;
+                    while (ob) {
+                        const int bpos = __ffs(ob) - 1;
+                        ob &= ob - 1;
+                        if (slot < (unsigned)cap)
+                            points[(size_t)t * cap + slot] = ((unsigned)yo << 16) | (unsigned)(wx * 32 + bpos);
+                        slot++;
+                    }
                 }
+                uint4 *o = reinterpret_cast<uint4 *>(orow + (size_t)(lane - 1) * 32);
+                __stcs(o, a);
+                __stcs(o + 1, b);
             }
-            uint4 *o = reinterpret_cast<uint4 *>(dst + (size_t)t * W * H + (size_t)yo * W + (size_t)wx * 32);
-            __stcs(o, a);
-            __stcs(o + 1, b);
         }
     }
 }

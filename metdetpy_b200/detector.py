@@ -23,6 +23,9 @@ NUM_LINES_TOOMUCH = 500  # MetLib/Detector.py:30
 DEFAULT_INIT_VALUE = 5  # MetLib/Detector.py:31
 PI = np.pi / 180.0  # MetLib/utils.py:22
 _SENS_CODE = {"low": 0, "normal": 1, "high": 2}
+_INFO_DTYPE = np.dtype([("timer", "<i8"), ("bi_threshold", "<i4"), ("n_on", "<i4"), ("bi_threshold_float", "<f8"),
+                        ("snr", "<f8"), ("dst_sum", "<f8"), ("gap", "<f8"), ("lines_num", "<i4"), ("n_raw", "<i4"),
+                        ("n_lines", "<i4"), ("reserved", "<i4")])
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -361,6 +364,25 @@ class M3Detector(LineDetector):
         self._dst_cache = None
         return self._unpack(0)
 
+    def _unpack_all(self, T: int):
+        """Results of a finished batch as a list of (lines, cls_pred); only frames that have lines
+        cost any per-frame Python work."""
+        eng = self._eng
+        info = np.frombuffer(eng.infos, dtype=_INFO_DTYPE, count=T)
+        nl = info["n_lines"]
+        empty = (np.array([]), np.zeros((0, self.num_cls)))
+        out = [empty] * T
+        for i in np.nonzero(nl)[0]:
+            k = int(nl[i])
+            cls_pred = np.zeros((k, self.num_cls))
+            p = eng.prob[i, :k]
+            cls_pred[:, -1] = p
+            cls_pred[:, 0] = 1 - p
+            out[i] = (eng.lines[i, :k].copy(), cls_pred)
+        self._unpack(T - 1)
+        self.last_infos = info.copy()
+        return out
+
     def _unpack(self, i: int):
         eng = self._eng
         fi = eng.infos[i]
@@ -454,11 +476,10 @@ class M3Detector(LineDetector):
         check(eng.lib.mdb_collect_batch(eng.handle, C.byref(eng.infos), _ptr(eng.lines), _ptr(eng.prob),
                                         _ptr(eng.raw), None, 0), "collect")
         self._dst_cache = None
-        self.last_infos = eng.infos
         if not want_lines:
             self._unpack(T - 1)
             return None
-        return [self._unpack(i) for i in range(T)]
+        return self._unpack_all(T)
 
     def visu(self):
         """Reference visu() (Detector.py:394-448) needs MetLib.metvisu; without it: no overlays."""
