@@ -141,77 +141,84 @@ temporal_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *__
                 aE[k] = __vmaxu2(aE[k], e); aO[k] = __vmaxu2(aO[k], d);
                 o[k] = pack_eo(aE[k], aO[k]);
             }
-            sts_vec<WPT>(smx_s + p * slot_stride, o);
+            sts_vec<WPT>(smx_s + (p - 1) * slot_stride, o);
         }
     }
-    unsigned pE[WPT], pO[WPT];  // prefix max of the current block
-#pragma unroll
-    for (int k = 0; k < WPT; k++) pE[k] = pO[k] = 0;
+    // suffix-max slots: position p (1..n-1) lives in slot p-1; slot n-1 stays zero ("position n")
+    sts_vec<WPT>(smx_s + (n - 1) * slot_stride, zero);
 
-    int j = 0;                                              // position inside the current block
     uint32_t a_cur = ring_s + (n - 1) * slot_stride;        // smem address of the current frame's slot
     uint32_t a_old = ring_s + (RS - 1) * slot_stride;       // frame t-n; destination of the next prefetch
     const uint32_t a_end = ring_s + RS * slot_stride;
-    uint32_t a_smx = smx_s + slot_stride;                   // suffix max at position j+1
     uint8_t *bout = bits + (size_t)g * WPT / 2;             // WPT*4 bits per thread and frame
     const size_t bstride = (size_t)HWG * WPT / 2;
+    // next frame to prefetch: contiguous in the caller's buffer, or ring slots that may wrap once
     const uint8_t *pf_ptr = gbase + (size_t)pf_slot * src.HW;
-    long long tg = t0;
-    for (int i = 0; i < T; i++, tg++) {
-        cp_async_wait<ST_K - 1>();  // this thread's copy of frame i has landed
-        unsigned xw[WPT], ow[WPT], mw[WPT];
-        lds_vec<WPT>(xw, a_cur);
-        lds_vec<WPT>(ow, a_old);
-        if (MASKED) {
+    const uint8_t *pf_wrap = gbase + (size_t)Rw * src.HW;   // never reached in zero-copy mode
+    int pf_left = T - ST_K;                                  // frames still to be prefetched
+    int L = (int)(t0 + 1 < n ? t0 + 1 : n);                  // SlidingWindow.length of the current frame
+    int i = 0;
+    while (i < T) {
+        const int nb = min(n, T - i);  // frames of this block
+        unsigned pE[WPT], pO[WPT];     // prefix max of the current block (0 = identity: first frame sets it)
 #pragma unroll
-            for (int k = 0; k < WPT; k++) xw[k] &= mk[k];
-            sts_vec<WPT>(a_cur, xw);
-        }
-        if (j + 1 < n) lds_vec<WPT>(mw, a_smx);
-        else {
+        for (int k = 0; k < WPT; k++) pE[k] = pO[k] = 0;
+        uint32_t a_smx = smx_s;        // suffix max at position j+1
+        for (int j = 0; j < nb; j++, i++) {
+            cp_async_wait<ST_K - 1>();  // this thread's copy of frame i has landed
+            unsigned xw[WPT], ow[WPT], mw[WPT];
+            lds_vec<WPT>(xw, a_cur);
+            lds_vec<WPT>(ow, a_old);
+            lds_vec<WPT>(mw, a_smx);
+            if (MASKED) {
 #pragma unroll
-            for (int k = 0; k < WPT; k++) mw[k] = 0;
-        }
-        // slot a_old is free now: fetch frame i+K into it
-        if (i + ST_K < T) cp_async_vec<WPT>(a_old, pf_ptr);
-        cp_async_commit();
-        if (++pf_slot == Rw) { pf_slot = 0; pf_ptr = gbase; } else pf_ptr += src.HW;
+                for (int k = 0; k < WPT; k++) xw[k] &= mk[k];
+                sts_vec<WPT>(a_cur, xw);
+            }
+            // slot a_old is free now: fetch frame i+K into it
+            if (pf_left > 0) cp_async_vec<WPT>(a_old, pf_ptr);
+            cp_async_commit();
+            pf_left--;
+            pf_ptr += src.HW;
+            if (pf_ptr == pf_wrap) pf_ptr = gbase;
 
-        const int L = (int)(tg + 1 < n ? tg + 1 : n);
-        const unsigned Tq = (unsigned)thr_s[i] * (unsigned)L;            // <= 255*128
-        const unsigned Cpk = (0x7fffu - Tq) * 0x00010001u;                // per-half bias
-        unsigned M[WPT];
+            const unsigned Tq = (unsigned)thr_s[i] * (unsigned)L;            // <= 255*128
+            const unsigned Cpk = (0x7fffu - Tq) * 0x00010001u;                // per-half bias
+            unsigned M[WPT];
 #pragma unroll
-        for (int k = 0; k < WPT; k++) {
-            const unsigned e = ev(xw[k]), d = od(xw[k]);
-            sE[k] = sE[k] + e - ev(ow[k]);
-            sO[k] = sO[k] + d - od(ow[k]);
-            if (j == 0) { pE[k] = e; pO[k] = d; }
-            else { pE[k] = __vmaxu2(pE[k], e); pO[k] = __vmaxu2(pO[k], d); }
-            const unsigned wE = __vmaxu2(pE[k], ev(mw[k])), wO = __vmaxu2(pO[k], od(mw[k]));
-            // per half: max*L - sum + 0x7fff - thr*L ; bit 15 set <=> max*L - sum > thr*L
-            const unsigned vE = wE * (unsigned)L + Cpk - sE[k];
-            const unsigned vO = wO * (unsigned)L + Cpk - sO[k];
-            M[k] = prmt(vE, vO, 0xFBD9u);  // sign-replicate bytes 1,5,3,7 -> 0x00/0xff per pixel
+            for (int k = 0; k < WPT; k++) {
+                const unsigned e = ev(xw[k]), d = od(xw[k]);
+                sE[k] = sE[k] + e - ev(ow[k]);
+                sO[k] = sO[k] + d - od(ow[k]);
+                pE[k] = __vmaxu2(pE[k], e);
+                pO[k] = __vmaxu2(pO[k], d);
+                const unsigned wE = __vmaxu2(pE[k], ev(mw[k])), wO = __vmaxu2(pO[k], od(mw[k]));
+                // per half: max*L - sum + 0x7fff - thr*L ; bit 15 set <=> max*L - sum > thr*L
+                const unsigned vE = wE * (unsigned)L + Cpk - sE[k];
+                const unsigned vO = wO * (unsigned)L + Cpk - sO[k];
+                M[k] = prmt(vE, vO, 0xFBD9u);  // sign-replicate bytes 1,5,3,7 -> 0x00/0xff per pixel
+            }
+            const unsigned q01 = (M[0] & 0x08040201u) | (M[1] & 0x80402010u);
+            const unsigned r01 = q01 * 0x01010101u;
+            if (WPT == 4) {
+                const unsigned q23 = (M[2 % WPT] & 0x08040201u) | (M[3 % WPT] & 0x80402010u);
+                const unsigned r23 = q23 * 0x01010101u;
+                *reinterpret_cast<uint16_t *>(bout) = (uint16_t)prmt(r01, r23, 0x4473u);
+            } else {
+                *bout = (uint8_t)(r01 >> 24);
+            }
+            bout += bstride;
+            L += (L < n);
+            a_smx += slot_stride;
+            a_cur += slot_stride; if (a_cur == a_end) a_cur = ring_s;
+            a_old += slot_stride; if (a_old == a_end) a_old = ring_s;
         }
-        const unsigned q01 = (M[0] & 0x08040201u) | (M[1] & 0x80402010u);
-        const unsigned r01 = q01 * 0x01010101u;
-        if (WPT == 4) {
-            const unsigned q23 = (M[2 % WPT] & 0x08040201u) | (M[3 % WPT] & 0x80402010u);
-            const unsigned r23 = q23 * 0x01010101u;
-            *reinterpret_cast<uint16_t *>(bout) = (uint16_t)prmt(r01, r23, 0x4473u);
-        } else {
-            *bout = (uint8_t)(r01 >> 24);
-        }
-        bout += bstride;
-
-        if (++j == n) {  // block complete: suffix max of its n frames, by position 1..n-1
-            j = 0;
-            a_smx = smx_s;
+        if (nb == n && i < T) {  // block complete and more frames follow: suffix max by position 1..n-1
             unsigned aE[WPT], aO[WPT];
 #pragma unroll
             for (int k = 0; k < WPT; k++) aE[k] = aO[k] = 0;
-            uint32_t a = a_cur;
+            uint32_t a = (a_cur == ring_s) ? a_end - slot_stride : a_cur - slot_stride;  // last frame of the block
+            uint32_t o_s = smx_s + (n - 2) * slot_stride;
             for (int p = n - 1; p >= 1; p--) {
                 unsigned w[WPT], o[WPT];
                 lds_vec<WPT>(w, a);
@@ -221,13 +228,11 @@ temporal_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *__
                     aO[k] = __vmaxu2(aO[k], od(w[k]));
                     o[k] = pack_eo(aE[k], aO[k]);
                 }
-                sts_vec<WPT>(smx_s + p * slot_stride, o);
+                sts_vec<WPT>(o_s, o);
+                o_s -= slot_stride;
                 a = (a == ring_s) ? a_end - slot_stride : a - slot_stride;
             }
         }
-        a_smx += slot_stride;
-        a_cur += slot_stride; if (a_cur == a_end) a_cur = ring_s;
-        a_old += slot_stride; if (a_old == a_end) a_old = ring_s;
     }
     cp_async_wait<0>();
 }
