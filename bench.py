@@ -16,7 +16,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -31,14 +30,14 @@ UNIT = "frames/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--fps", type=float, default=30.0)
     ap.add_argument("--window", type=int, default=30)
-    ap.add_argument("--batch", type=int, default=128, help="frames per step (per GPU)")
+    ap.add_argument("--batch", type=int, default=512, help="frames per step (per GPU)")
     ap.add_argument("--no-dy", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=40, help="frames in the cpu_baseline sample")
@@ -54,41 +53,60 @@ def workload_name(a):
 
 
 # ---------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md): one
+    `nvidia-smi -lms` process streams samples; nothing runs in this process while timing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
         self.index = index
+        self.proc = None
         self.rows = []
-        self.stop_flag = False
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        for line in out.strip().splitlines():
+            self.rows.append([c.strip() for c in line.split(",")])
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        def num(v):
+            try:
+                return float(v)
+            except Exception:
+                return None
+        rows = [r for r in self.rows if len(r) >= 9]
+        pw = [num(r[3]) for r in rows if num(r[3]) is not None]
+        # "under load": samples whose power draw is above the midpoint of the observed range
+        thr = (min(pw) + max(pw)) / 2 if pw else 0
+        load = [r for r in rows if num(r[3]) is not None and num(r[3]) >= thr] or rows
+        sm = [num(r[1]) for r in load if num(r[1]) is not None]
+        mx = [num(r[2]) for r in rows if num(r[2]) is not None]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for nm, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+        for r in rows:
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(rows), "power_w_max": max(pw) if pw else None}
 
 
 def make_cfg(a):
@@ -251,7 +269,7 @@ def main_ours(a):
     e1.record(ext)
     barrier()
     wall = time.perf_counter() - t0
-    sampler.stop_flag = True
+    sampler.stop()
     launches = det._eng.launch_count() - l0
     dev_ms = e0.elapsed_time(e1)
     el = torch.tensor([wall], device=dev, dtype=torch.float64)
