@@ -152,11 +152,11 @@ temporal_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *__
     const uint32_t a_end = ring_s + RS * slot_stride;
     uint8_t *bout = bits + (size_t)g * WPT / 2;             // WPT*4 bits per thread and frame
     const size_t bstride = (size_t)HWG * WPT / 2;
-    // next frame to prefetch: contiguous in the caller's buffer, or ring slots that may wrap once
-    const uint8_t *pf_ptr = gbase + (size_t)pf_slot * src.HW;
-    const uint8_t *pf_wrap = gbase + (size_t)Rw * src.HW;   // never reached in zero-copy mode
+    // next frame to prefetch = slot pf_slot: contiguous in the caller's buffer, or ring slots that wrap
     int pf_left = T - ST_K;                                  // frames still to be prefetched
+    const uint32_t thr_sa = smem0 + (RS + n) * slot_stride;  // shared address of thr_s
     int L = (int)(t0 + 1 < n ? t0 + 1 : n);                  // SlidingWindow.length of the current frame
+    const unsigned one = (unsigned)(n > 0), neg1 = 0u - one; // opaque to the compiler on purpose
     int i = 0;
     while (i < T) {
         const int nb = min(n, T - i);  // frames of this block
@@ -176,20 +176,23 @@ temporal_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *__
                 sts_vec<WPT>(a_cur, xw);
             }
             // slot a_old is free now: fetch frame i+K into it
-            if (pf_left > 0) cp_async_vec<WPT>(a_old, pf_ptr);
+            if (pf_left > 0) cp_async_vec<WPT>(a_old, gbase + (size_t)pf_slot * src.HW);
             cp_async_commit();
             pf_left--;
-            pf_ptr += src.HW;
-            if (pf_ptr == pf_wrap) pf_ptr = gbase;
+            if (++pf_slot == Rw) pf_slot = 0;
 
-            const unsigned Tq = (unsigned)thr_s[i] * (unsigned)L;            // <= 255*128
+            unsigned thr_i;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(thr_i) : "r"(thr_sa + i));
+            const unsigned Tq = thr_i * (unsigned)L;                          // <= 255*128
             const unsigned Cpk = (0x7fffu - Tq) * 0x00010001u;                // per-half bias
             unsigned M[WPT];
 #pragma unroll
             for (int k = 0; k < WPT; k++) {
                 const unsigned e = ev(xw[k]), d = od(xw[k]);
-                sE[k] = sE[k] + e - ev(ow[k]);
-                sO[k] = sO[k] + d - od(ow[k]);
+                // running sums on the FMA pipe (IMAD with a run-time 1 / -1): the ALU pipe, which carries
+                // every LOP3 / PRMT / VIMNMX of this loop, is the bottleneck of the kernel
+                sE[k] = ev(ow[k]) * neg1 + (e * one + sE[k]);
+                sO[k] = od(ow[k]) * neg1 + (d * one + sO[k]);
                 pE[k] = __vmaxu2(pE[k], e);
                 pO[k] = __vmaxu2(pO[k], d);
                 const unsigned wE = __vmaxu2(pE[k], ev(mw[k])), wO = __vmaxu2(pO[k], od(mw[k]));
