@@ -66,9 +66,11 @@ class ClockSampler:
         self.rows = []
 
     def start(self):
+        if os.environ.get("BENCH_NO_SMI"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", os.environ.get("BENCH_SMI_MS", "100")], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None

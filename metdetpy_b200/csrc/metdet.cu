@@ -43,7 +43,18 @@ struct BatchCtx {
     double *h_thrf = nullptr, *h_snr = nullptr;
     unsigned *h_npoints = nullptr;
     int32_t *h_lines = nullptr;
-    cudaEvent_t ev_f0 = nullptr, ev_f1 = nullptr, ev_done = nullptr;
+    int *d_thr = nullptr;            // per-frame thresholds of this batch (device)
+    double *d_thrf = nullptr, *d_snr = nullptr;
+    uint8_t *d_dst = nullptr;        // [T][H][W] masks of this batch
+    unsigned *d_npoints = nullptr;   // [T] on-pixel counts
+    uint32_t *d_points = nullptr;    // [T][cap] on-pixel lists
+    uint16_t *d_order = nullptr;     // [T][cap] PPHT visiting order per frame
+    unsigned *d_queue = nullptr;     // work-queue head of the tier-1 Hough kernel
+    int32_t *d_lines = nullptr;      // [T][MDB_MAX_LINES][4]
+    int *d_nlines = nullptr;         // [T]
+    // ev_f0..ev_f1: temporal+act on the front stream; ev_d0..ev_d1: dst on the back stream
+    cudaEvent_t ev_f0 = nullptr, ev_f1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr, ev_done = nullptr;
+    cudaEvent_t tl[12] = {};         // optional timeline marks (debug)
     int T = 0;  // 0: free
     long long timer0 = 0;
     long long seq = 0;
@@ -55,21 +66,17 @@ struct mdb_detector {
     size_t HW;
     int slots;
     int sm_count = 148;
-    cudaStream_t stream = nullptr, cstream = nullptr;  // compute / host->device copies
+    // stream: noise, thresholds, temporal, act | stream2: dst | stream3: Hough, result copy-out |
+    // cstream: host->device frames.  The stages of consecutive batches overlap (two batches in flight):
+    // the write-only dst pass and the shared-memory-bound Hough pass hide under the ALU-bound temporal pass.
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr, cstream = nullptr;
     cudaEvent_t ev_copy = nullptr;
     // device
-    uint8_t *d_ring = nullptr, *d_mask = nullptr, *d_dst = nullptr;
+    uint8_t *d_ring = nullptr, *d_mask = nullptr;
     uint32_t *d_act = nullptr;  // act bit-frame ring [RA][H][Wb]
     int RA = 0, Wb = 0;
     DevState *d_state = nullptr;
     unsigned long long *d_noise = nullptr;
-    int *d_thr = nullptr, *d_nlines = nullptr;
-    double *d_thrf = nullptr, *d_snr = nullptr;
-    unsigned *d_npoints = nullptr;
-    uint32_t *d_points = nullptr;
-    uint16_t *d_order = nullptr;  // [T][cap] PPHT visiting order per frame
-    unsigned *d_queue = nullptr;  // work-queue head of the tier-1 Hough kernel
-    int32_t *d_lines = nullptr;
     int32_t *d_accum = nullptr;   // tier-2/3 accumulators [slots][180][numrho]
     uint32_t *d_bitmap = nullptr, *d_walk = nullptr, *d_okeys = nullptr, *d_oidx = nullptr;  // tier 3
     long long *d_prof = nullptr;  // optional per-frame PPHT phase cycle counters (debug)
@@ -79,12 +86,20 @@ struct mdb_detector {
     long long timer = 0, dy_timer = 0, seek0 = 0;
     long long launches = 0;
     long long submitted = 0, collected = 0;  // batch sequence numbers
-    int last_T = 0;                           // frames in d_dst from the most recent batch
+    int last_T = 0;                           // frames in the most recently finished batch
+    int last_ctx = 0;                         // ... and which context holds its dst
     float fused_ms = 0.f;
     int fused_launches = 0, last_fused_launches = 0;
     HoughParams hp;
     int use_stream_kernel = 1;
+    int timeline = 0;                // debug: record per-kernel timeline events
+    cudaEvent_t tl_base = nullptr;
 };
+
+#define TL(c, i, st)                                                  \
+    do {                                                              \
+        if (h->timeline) cudaEventRecord((c).tl[i], st);              \
+    } while (0)
 
 extern "C" const char *mdb_last_error(void) { return g_err; }
 extern "C" int mdb_version(void) { return 101; }
@@ -118,12 +133,19 @@ static void free_all(mdb_detector *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream2) cudaStreamSynchronize(h->stream2);
+    if (h->stream3) cudaStreamSynchronize(h->stream3);
     if (h->cstream) cudaStreamSynchronize(h->cstream);
-    void *dev[] = {h->d_ring, h->d_mask, h->d_dst, h->d_act, h->d_state, h->d_noise, h->d_thr, h->d_nlines,
-                   h->d_thrf, h->d_snr, h->d_npoints, h->d_points, h->d_order, h->d_lines, h->d_accum,
-                   h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_prof, h->d_queue};
+    void *dev[] = {h->d_ring, h->d_mask, h->d_act, h->d_state, h->d_noise, h->d_accum,
+                   h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_prof};
     for (void *p : dev)
         if (p) cudaFree(p);
+    for (BatchCtx &c : h->ctx) {
+        void *cd[] = {c.d_thr, c.d_thrf, c.d_snr, c.d_dst, c.d_npoints, c.d_points, c.d_order, c.d_queue,
+                      c.d_lines, c.d_nlines};
+        for (void *p : cd)
+            if (p) cudaFree(p);
+    }
     stream_state_free(h->sk);
     for (BatchCtx &c : h->ctx) {
         void *pin[] = {c.h_thr, c.h_nlines, c.h_thrf, c.h_snr, c.h_npoints, c.h_lines};
@@ -131,10 +153,14 @@ static void free_all(mdb_detector *h) {
             if (p) cudaFreeHost(p);
         if (c.ev_f0) cudaEventDestroy(c.ev_f0);
         if (c.ev_f1) cudaEventDestroy(c.ev_f1);
+        if (c.ev_d0) cudaEventDestroy(c.ev_d0);
+        if (c.ev_d1) cudaEventDestroy(c.ev_d1);
         if (c.ev_done) cudaEventDestroy(c.ev_done);
     }
     if (h->ev_copy) cudaEventDestroy(h->ev_copy);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->cstream) cudaStreamDestroy(h->cstream);
     delete h;
 }
@@ -209,26 +235,32 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     } while (0)
 
     CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKH(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    CKH(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
     CKH(cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
     CKH(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
     const size_t bm_words = (h->HW + 31) / 32;
     h->Wb = (h->W + 31) / 32;
-    h->RA = h->n - 1 + T;
+    h->RA = h->n - 1 + (T > 1 ? 2 * T : 1);  // two batches: act of batch k+1 is written while dst of batch k reads
     ALLOC(h->d_ring, (size_t)h->R * h->HW);
     ALLOC(h->d_mask, h->HW);
-    ALLOC(h->d_dst, (size_t)T * h->HW);
     ALLOC(h->d_act, (size_t)h->RA * h->H * h->Wb * sizeof(uint32_t));
     ALLOC(h->d_state, sizeof(DevState));
     ALLOC(h->d_noise, (size_t)T * 2 * sizeof(unsigned long long));
-    ALLOC(h->d_thr, T * sizeof(int));
-    ALLOC(h->d_nlines, T * sizeof(int));
-    ALLOC(h->d_thrf, T * sizeof(double));
-    ALLOC(h->d_snr, T * sizeof(double));
-    ALLOC(h->d_npoints, T * sizeof(unsigned));
-    ALLOC(h->d_points, (size_t)T * MDB_POINT_CAP * sizeof(uint32_t));
-    ALLOC(h->d_order, (size_t)T * MDB_POINT_CAP * sizeof(uint16_t));
-    ALLOC(h->d_queue, sizeof(unsigned));
-    ALLOC(h->d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t));
+    for (int k = 0; k < NCTX; k++) {
+        BatchCtx &c = h->ctx[k];
+        ALLOC(c.d_thr, T * sizeof(int));
+        ALLOC(c.d_thrf, T * sizeof(double));
+        ALLOC(c.d_snr, T * sizeof(double));
+        ALLOC(c.d_dst, (size_t)T * h->HW);
+        ALLOC(c.d_npoints, T * sizeof(unsigned));
+        ALLOC(c.d_points, (size_t)T * MDB_POINT_CAP * sizeof(uint32_t));
+        ALLOC(c.d_order, (size_t)T * MDB_POINT_CAP * sizeof(uint16_t));
+        ALLOC(c.d_queue, sizeof(unsigned));
+        ALLOC(c.d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t));
+        ALLOC(c.d_nlines, T * sizeof(int));
+        CKH(cudaMemsetAsync(c.d_dst, 0, (size_t)T * h->HW, h->stream));
+    }
     ALLOC(h->d_accum, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t));
     ALLOC(h->d_bitmap, bm_words * sizeof(uint32_t));
     ALLOC(h->d_walk, (size_t)hp.walk_cap * sizeof(uint32_t));
@@ -236,7 +268,6 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     CKH(cudaMemsetAsync(h->d_act, 0, (size_t)h->RA * h->H * h->Wb * sizeof(uint32_t), h->stream));
     CKH(cudaMemsetAsync(h->d_accum, 0, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t), h->stream));
     CKH(cudaMemsetAsync(h->d_bitmap, 0, bm_words * sizeof(uint32_t), h->stream));
-    CKH(cudaMemsetAsync(h->d_dst, 0, (size_t)T * h->HW, h->stream));
     CKH(cudaMemcpyAsync(h->d_mask, mask, h->HW, cudaMemcpyHostToDevice, h->stream));
     for (BatchCtx &c : h->ctx) {
         CKH(cudaHostAlloc((void **)&c.h_thr, T * sizeof(int), cudaHostAllocDefault));
@@ -247,6 +278,8 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
         CKH(cudaHostAlloc((void **)&c.h_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t), cudaHostAllocDefault));
         CKH(cudaEventCreate(&c.ev_f0));
         CKH(cudaEventCreate(&c.ev_f1));
+        CKH(cudaEventCreate(&c.ev_d0));
+        CKH(cudaEventCreate(&c.ev_d1));
         CKH(cudaEventCreateWithFlags(&c.ev_done, cudaEventDisableTiming));
     }
 
@@ -305,45 +338,53 @@ static int copy_to_ring(mdb_detector *h, const uint8_t *frames, int first, int T
     return MDB_OK;
 }
 
-static int launch_noise_thr(mdb_detector *h, const FrameSrc &src, int T, long long timer0) {
+static int launch_noise_thr(mdb_detector *h, BatchCtx &bc, const FrameSrc &src, int T, long long timer0) {
     const mdb_config &c = h->cfg;
     const int rh = c.roi[2] - c.roi[0], rw = c.roi[3] - c.roi[1];
     const long long std_interval = (long long)c.nz_interval * h->n;
+    TL(bc, 0, h->stream);
     CK(cudaMemsetAsync(h->d_noise, 0, (size_t)T * 2 * sizeof(unsigned long long), h->stream));
     const int gx = std::max(1, std::min((rh * rw + 255) / 256, 592));
     noise_sample_kernel<<<dim3(gx, T), 256, 0, h->stream>>>(src, h->W, h->n, timer0, std_interval,
                                                           c.roi[0], c.roi[1], rh, rw, h->d_noise, 0);
     threshold_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_noise, T, timer0, h->n, std_interval,
-                                             (long long)rh * rw, c.adaptive, c.sensitivity, h->d_thr,
-                                             h->d_thrf, h->d_snr);
+                                             (long long)rh * rw, c.adaptive, c.sensitivity, bc.d_thr,
+                                             bc.d_thrf, bc.d_snr);
     h->launches += 2;
+    TL(bc, 1, h->stream);
     CK(cudaGetLastError());
     return MDB_OK;
 }
 
-// fused mask chain for frames i = 0..T-1 of the batch (global index timer0 + i)
+// fused mask chain for frames i = 0..T-1 of the batch (global index timer0 + i): temporal + act on the
+// front stream, dst on the back stream
 static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T, long long timer0, long long dy0) {
-    CK(cudaMemsetAsync(h->d_npoints, 0, T * sizeof(unsigned), h->stream));
+    CK(cudaMemsetAsync(c.d_npoints, 0, T * sizeof(unsigned), h->stream2));
     CK(cudaEventRecord(c.ev_f0, h->stream));
     int nl = 0;
     if (h->use_stream_kernel && stream_kernel_supported(h->sk, T)) {
-        int rc = stream_kernel_launch(h->sk, src, timer0, dy0, T, h->cfg.dy_mask, h->d_thr, act_ring(h),
-                                      h->d_dst, h->d_npoints, h->d_points, MDB_POINT_CAP, h->stream, &nl);
+        int rc = stream_kernel_launch(h->sk, src, timer0, dy0, T, h->cfg.dy_mask, c.d_thr, act_ring(h),
+                                      c.d_dst, c.d_npoints, c.d_points, MDB_POINT_CAP, h->stream, h->stream2,
+                                      c.ev_f1, c.ev_d0, &nl);
         if (rc != 0) return fail(MDB_ERR_CUDA, "stream kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
+        // generic per-frame kernel: the whole chain runs on the back stream, after the front stream's thresholds
+        CK(cudaEventRecord(c.ev_f1, h->stream));
+        CK(cudaStreamWaitEvent(h->stream2, c.ev_f1, 0));
+        CK(cudaEventRecord(c.ev_d0, h->stream2));
         dim3 grid((h->W + V1_TW - 1) / V1_TW, (h->H + V1_TH - 1) / V1_TH);
         for (int i = 0; i < T; i++) {
             const long long t = timer0 + i;
             const int L = (int)std::min<long long>(h->n, t + 1);
             const int Ldy = (int)std::min<long long>(h->n, dy0 + i + 1);
-            fused_frame_kernel<<<grid, 256, 0, h->stream>>>(
-                src, h->W, h->H, h->n, t, L, dy0 + i, Ldy, h->cfg.dy_mask, h->d_thr + i, act_ring(h),
-                h->d_dst + (size_t)i * h->HW, h->d_npoints + i, h->d_points + (size_t)i * MDB_POINT_CAP,
+            fused_frame_kernel<<<grid, 256, 0, h->stream2>>>(
+                src, h->W, h->H, h->n, t, L, dy0 + i, Ldy, h->cfg.dy_mask, c.d_thr + i, act_ring(h),
+                c.d_dst + (size_t)i * h->HW, c.d_npoints + i, c.d_points + (size_t)i * MDB_POINT_CAP,
                 MDB_POINT_CAP);
             nl++;
         }
     }
-    CK(cudaEventRecord(c.ev_f1, h->stream));
+    CK(cudaEventRecord(c.ev_d1, h->stream2));
     h->fused_launches = nl;
     h->launches += nl;
     CK(cudaGetLastError());
@@ -351,29 +392,34 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
 }
 
 static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
-    CK(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), h->stream));
-    ppht_order_kernel<<<T, 32, MDB_POINT_CAP * 2, h->stream>>>(T, MDB_POINT_CAP, h->d_npoints, h->d_order);
-    hough_smem_kernel<<<std::min(T, h->sm_count), HOUGH_THREADS, HOUGH_SMEM_BYTES + HOUGH_TABLE_BYTES, h->stream>>>(
-        h->hp, T, h->d_npoints, h->d_points, h->d_order, h->d_lines, h->d_nlines, h->d_queue, h->d_prof);
-    hough_tier2_kernel<<<std::min(T, h->slots), HOUGH_THREADS, HOUGH_SMEM_BYTES, h->stream>>>(
-        h->hp, T, h->d_npoints, h->d_points, h->d_accum, h->d_lines, h->d_nlines, h->d_prof);
+    CK(cudaStreamWaitEvent(h->stream3, c.ev_d1, 0));  // dst (stream2) has produced the on-pixel lists
+    CK(cudaMemsetAsync(c.d_queue, 0, sizeof(unsigned), h->stream3));
+    TL(c, 4, h->stream3);
+    ppht_order_kernel<<<T, 32, MDB_POINT_CAP * 2, h->stream3>>>(T, MDB_POINT_CAP, c.d_npoints, c.d_order);
+    hough_smem_kernel<<<std::min(T, h->sm_count), HOUGH_THREADS, HOUGH_SMEM_BYTES + HOUGH_TABLE_BYTES, h->stream3>>>(
+        h->hp, T, c.d_npoints, c.d_points, c.d_order, c.d_lines, c.d_nlines, c.d_queue, h->d_prof);
+    TL(c, 5, h->stream3);
+    hough_tier2_kernel<<<std::min(T, h->slots), HOUGH_THREADS, HOUGH_SMEM_BYTES, h->stream3>>>(
+        h->hp, T, c.d_npoints, c.d_points, h->d_accum, c.d_lines, c.d_nlines, h->d_prof);
     if (!h->d_okeys) {  // tier-3 scratch, allocated once
         if (cudaMalloc((void **)&h->d_okeys, h->HW * sizeof(uint32_t)) != cudaSuccess ||
             cudaMalloc((void **)&h->d_oidx, h->HW * sizeof(uint32_t)) != cudaSuccess)
             return fail(MDB_ERR_NOMEM, "tier-3 scratch: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    hough_tier3_kernel<<<1, HOUGH_THREADS, 0, h->stream>>>(h->hp, T, h->d_dst, h->d_okeys, h->d_oidx, h->d_accum,
-                                                          h->d_bitmap, h->d_walk, h->d_lines, h->d_nlines);
+    hough_tier3_kernel<<<1, HOUGH_THREADS, 0, h->stream3>>>(h->hp, T, c.d_dst, h->d_okeys, h->d_oidx, h->d_accum,
+                                                          h->d_bitmap, h->d_walk, c.d_lines, c.d_nlines);
     h->launches += 4;
+    TL(c, 6, h->stream3);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c.h_thr, h->d_thr, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(c.h_thrf, h->d_thrf, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(c.h_snr, h->d_snr, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(c.h_npoints, h->d_npoints, T * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(c.h_nlines, h->d_nlines, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(c.h_lines, h->d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t),
-                       cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaEventRecord(c.ev_done, h->stream));
+    CK(cudaMemcpyAsync(c.h_thr, c.d_thr, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream3));
+    CK(cudaMemcpyAsync(c.h_thrf, c.d_thrf, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream3));
+    CK(cudaMemcpyAsync(c.h_snr, c.d_snr, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream3));
+    CK(cudaMemcpyAsync(c.h_npoints, c.d_npoints, T * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream3));
+    CK(cudaMemcpyAsync(c.h_nlines, c.d_nlines, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream3));
+    CK(cudaMemcpyAsync(c.h_lines, c.d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t),
+                       cudaMemcpyDeviceToHost, h->stream3));
+    CK(cudaEventRecord(c.ev_done, h->stream3));
+    TL(c, 7, h->stream3);
     return MDB_OK;
 }
 
@@ -471,7 +517,7 @@ extern "C" int mdb_update(mdb_handle h, const uint8_t *frame, int on_device) {
     CK(cudaSetDevice(h->cfg.device));
     int rc = copy_to_ring(h, frame, 0, 1, h->timer, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream);
     if (rc) return rc;
-    rc = launch_noise_thr(h, frame_src(h, nullptr, 0), 1, h->timer);
+    rc = launch_noise_thr(h, h->ctx[0], frame_src(h, nullptr, 0), 1, h->timer);
     if (rc) return rc;
     h->timer += 1;
     if (!on_device) CK(cudaStreamSynchronize(h->stream));  // caller may reuse its buffer on return
@@ -489,11 +535,17 @@ extern "C" int mdb_detect(mdb_handle h, mdb_frame_info *info, int32_t *lines, do
     if (rc) return rc;
     rc = launch_hough_and_copy(h, c, 1);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(h->stream));
-    CK(cudaEventElapsedTime(&h->fused_ms, c.ev_f0, c.ev_f1));
+    CK(cudaStreamSynchronize(h->stream3));
+    {
+        float a = 0.f, b = 0.f;
+        CK(cudaEventElapsedTime(&a, c.ev_f0, c.ev_f1));
+        CK(cudaEventElapsedTime(&b, c.ev_d0, c.ev_d1));
+        h->fused_ms = a + b;
+    }
     h->last_fused_launches = h->fused_launches;
     h->dy_timer += 1;
     h->last_T = 1;
+    h->last_ctx = 0;
     c.T = 1;
     c.timer0 = h->timer - 1;
     rc = finish_batch(h, c, info, lines, nonline_prob, raw_lines);
@@ -527,11 +579,11 @@ static int submit_impl(mdb_handle h, const uint8_t *frames, int T, int on_device
     }
     int rc;
     if (thr) {  // thresholds supplied by the caller (time-sharded streams): no local EMA recurrence
-        CK(cudaMemcpyAsync(h->d_thr, thr, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_thrf, thrf, T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_snr, snr, T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(c.d_thr, thr, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(c.d_thrf, thrf, T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(c.d_snr, snr, T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     } else {
-        rc = launch_noise_thr(h, src, T, timer0);
+        rc = launch_noise_thr(h, c, src, T, timer0);
         if (rc) return rc;
     }
     rc = launch_fused(h, c, src, T, timer0, h->dy_timer);
@@ -619,18 +671,21 @@ extern "C" int mdb_collect_batch(mdb_handle h, mdb_frame_info *infos, int32_t *l
     BatchCtx &c = h->ctx[h->collected % NCTX];
     const int T = c.T;
     if (dst_out) {
-        if (in_flight(h) > 1)
-            return fail(MDB_ERR_STATE, "mdb_collect_batch: dst of this batch was overwritten by the batch "
-                                       "submitted after it; collect before submitting when dst is wanted");
-        CK(cudaMemcpyAsync(dst_out, h->d_dst, (size_t)T * h->HW,
-                           dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaEventSynchronize(c.ev_done));
+        CK(cudaMemcpy(dst_out, c.d_dst, (size_t)T * h->HW,
+                      dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
     }
     CK(cudaEventSynchronize(c.ev_done));
-    CK(cudaEventElapsedTime(&h->fused_ms, c.ev_f0, c.ev_f1));
+    {
+        float a = 0.f, b = 0.f;
+        CK(cudaEventElapsedTime(&a, c.ev_f0, c.ev_f1));
+        CK(cudaEventElapsedTime(&b, c.ev_d0, c.ev_d1));
+        h->fused_ms = a + b;  // temporal + act (front stream) and dst (back stream), each bracketed by events
+    }
     h->last_fused_launches = h->fused_launches;
     int rc = finish_batch(h, c, infos, lines, nonline_prob, raw_lines);
     h->last_T = T;
+    h->last_ctx = (int)(h->collected % NCTX);
     c.T = 0;
     h->collected += 1;
     return rc;
@@ -650,15 +705,14 @@ extern "C" int mdb_get_dst(mdb_handle h, uint8_t *dst, int on_device) {
     if (h->last_T < 1) return fail(MDB_ERR_STATE, "mdb_get_dst: no detect has run yet");
     if (in_flight(h)) return fail(MDB_ERR_STATE, "mdb_get_dst: a batch is in flight");
     CK(cudaSetDevice(h->cfg.device));
-    CK(cudaMemcpyAsync(dst, h->d_dst + (size_t)(h->last_T - 1) * h->HW, h->HW,
-                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(dst, h->ctx[h->last_ctx].d_dst + (size_t)(h->last_T - 1) * h->HW, h->HW,
+                  on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
     return MDB_OK;
 }
 
 extern "C" int mdb_get_dst_device(mdb_handle h, const uint8_t **ptr) {
     if (!h || !ptr) return fail(MDB_ERR_INVALID, "mdb_get_dst_device: null argument");
-    *ptr = h->d_dst;
+    *ptr = h->ctx[h->last_ctx].d_dst;
     return MDB_OK;
 }
 
@@ -705,6 +759,19 @@ extern "C" int mdb_get_fused_time(mdb_handle h, float *ms, int32_t *launches) {
     return MDB_OK;
 }
 
+// debug: ms offsets (from the moment the timeline was enabled) of the marks of the batch collected last:
+// [0] front start, [1] thresholds done, [2] = ev_f0 (temporal start), [3] = ev_f1 (act done),
+// [4] dst done (= back: order start), [5] tier-1 Hough done, [6] all Hough done, [7] results copied,
+// [8] = ev_d0 (dst start)
+extern "C" int mdb_debug_timeline(mdb_handle h, float *out) {
+    if (!h || !out || !h->timeline) return fail(MDB_ERR_INVALID, "mdb_debug_timeline: not enabled");
+    BatchCtx &c = h->ctx[(h->collected + NCTX - 1) % NCTX];
+    cudaEvent_t ev[9] = {c.tl[0], c.tl[1], c.ev_f0, c.ev_f1, c.tl[4], c.tl[5], c.tl[6], c.tl[7], c.ev_d0};
+    for (int i = 0; i < 9; i++)
+        if (cudaEventElapsedTime(&out[i], h->tl_base, ev[i]) != cudaSuccess) { cudaGetLastError(); out[i] = -1.f; }
+    return MDB_OK;
+}
+
 extern "C" int mdb_debug_hough_profile(mdb_handle h, long long *out, int T) {
     if (!h || !out || !h->d_prof) return fail(MDB_ERR_INVALID, "mdb_debug_hough_profile: not enabled");
     CK(cudaMemcpy(out, h->d_prof, (size_t)T * 10 * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -722,6 +789,16 @@ extern "C" int mdb_set_option(mdb_handle h, const char *name, int value) {
         return MDB_OK;
     }
     if (!strcmp(name, "stream_kernel")) { h->use_stream_kernel = value; return MDB_OK; }
+    if (!strcmp(name, "timeline")) {
+        if (value && !h->tl_base) {
+            for (BatchCtx &c : h->ctx)
+                for (cudaEvent_t &e : c.tl) CK(cudaEventCreate(&e));
+            CK(cudaEventCreate(&h->tl_base));
+            CK(cudaEventRecord(h->tl_base, h->stream));
+        }
+        h->timeline = value;
+        return MDB_OK;
+    }
     if (!strcmp(name, "temporal_wpt")) {
         if (!h->sk.ok || stream_state_config(h->sk, value) != 0)
             return fail(MDB_ERR_INVALID, "mdb_set_option: temporal_wpt=%d not possible here", value);

@@ -442,33 +442,38 @@ static inline int stream_state_init(StreamState &s, int W, int H, int n, int dev
 
 static inline bool stream_kernel_supported(const StreamState &s, int T) { return s.ok && T >= 1 && T <= s.max_batch; }
 
-// Launches temporal + act + dst kernels for frames timer0 .. timer0+T-1 (dy indices dy0 ..).
-// Returns 0 / -1; *launches gets the number of kernel launches.
+// Launches temporal + act (stream st1) and dst (stream st2, after `ev_act`) for frames
+// timer0 .. timer0+T-1 (dy indices dy0 ..).  The split lets the write-only dst pass (HBM write
+// bandwidth alone tops out near 60 % of the copy peak) overlap the read-only, ALU-heavy temporal pass
+// of the NEXT batch.  Returns 0 / -1; *launches gets the number of kernel launches.
 static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long timer0, long long dy0, int T,
                                        int dy_on, const int *d_thr, ActRing ring, uint8_t *dst,
-                                       unsigned *npoints, uint32_t *points, int cap, cudaStream_t st,
-                                       int *launches) {
+                                       unsigned *npoints, uint32_t *points, int cap, cudaStream_t st1,
+                                       cudaStream_t st2, cudaEvent_t ev_f1, cudaEvent_t ev_d0, int *launches) {
     const int HWG = (int)((size_t)s.W * s.H / (4 * s.t_wpt));  // pixel groups = threads
     const int nt = s.t_threads;
     const size_t smem = s.t_smem_per_thread * nt + ((T + 15) & ~15);
     const int grid = (HWG + nt - 1) / nt;
     uint8_t *bits8 = reinterpret_cast<uint8_t *>(s.d_bits);
     if (s.t_wpt == 2) {
-        if (src.mask) temporal_kernel<true, 2><<<grid, nt, smem, st>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
-        else temporal_kernel<false, 2><<<grid, nt, smem, st>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
+        if (src.mask) temporal_kernel<true, 2><<<grid, nt, smem, st1>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
+        else temporal_kernel<false, 2><<<grid, nt, smem, st1>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
     } else {
-        if (src.mask) temporal_kernel<true, 4><<<grid, nt, smem, st>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
-        else temporal_kernel<false, 4><<<grid, nt, smem, st>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
+        if (src.mask) temporal_kernel<true, 4><<<grid, nt, smem, st1>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
+        else temporal_kernel<false, 4><<<grid, nt, smem, st1>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
     const int Wb = s.W / 32;
     const int strips = (Wb + SP_USE - 1) / SP_USE, bands = (s.H + s.sp_rows - 1) / s.sp_rows;
     const int tiles = strips * bands;
     dim3 g((tiles + SP_WARPS - 1) / SP_WARPS, T);
-    act_kernel<<<g, SP_WARPS * 32, 0, st>>>(s.d_bits, s.W, s.H, T, s.sp_rows, strips, bands, ring, dy0);
+    act_kernel<<<g, SP_WARPS * 32, 0, st1>>>(s.d_bits, s.W, s.H, T, s.sp_rows, strips, bands, ring, dy0);
     if (cudaGetLastError() != cudaSuccess) return -1;
-    dst_kernel<<<g, SP_WARPS * 32, 0, st>>>(ring, s.W, s.H, T, s.n, dy0, dy_on, s.sp_rows, strips, bands, dst,
-                                            npoints, points, cap);
+    if (cudaEventRecord(ev_f1, st1) != cudaSuccess) return -1;
+    if (cudaStreamWaitEvent(st2, ev_f1, 0) != cudaSuccess) return -1;
+    if (cudaEventRecord(ev_d0, st2) != cudaSuccess) return -1;
+    dst_kernel<<<g, SP_WARPS * 32, 0, st2>>>(ring, s.W, s.H, T, s.n, dy0, dy_on, s.sp_rows, strips, bands, dst,
+                                             npoints, points, cap);
     if (cudaGetLastError() != cudaSuccess) return -1;
     *launches = 3;
     return 0;
