@@ -137,18 +137,24 @@ ppht_order_kernel(int T, int cap, const unsigned *__restrict__ npoints, uint16_t
 // streak up to ~800 px long does) the whole PPHT of the frame runs on-chip.  Frames whose table
 // would not fit are flagged (-2) for tier 2.
 // ------------------------------------------------------------------------------------------
-#define HOUGH_TABLE_BYTES (186 * 1024)
+#define HOUGH_TABLE_BYTES (186 * 1024)       // tier 1b: one CTA per SM
+#define HOUGH_TABLE_BYTES_SMALL (92 * 1024)  // tier 1a: two CTAs per SM
+#define HOUGH_CAP_SMALL 2048
 
 __global__ void __launch_bounds__(HOUGH_THREADS)
 hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
                   const uint32_t *__restrict__ points, const uint16_t *__restrict__ order,
-                  int32_t *lines_out, int *nlines_out, unsigned *queue, long long *prof) {
+                  int32_t *lines_out, int *nlines_out, unsigned *queue, long long *prof, int lcap,
+                  int table_bytes, int stage) {
+    // stage 0 (tier 1a): every frame; up to lcap = 2048 points and a 92 KB table, two CTAs per SM.
+    // stage 1 (tier 1b): frames stage 0 flagged -2; up to 4096 points and a 186 KB table.
     extern __shared__ uint32_t h_sm[];
-    uint32_t *keys = h_sm;                                            // [cap]
-    uint16_t *idx = reinterpret_cast<uint16_t *>(keys + P.cap);       // [cap] visiting order
-    uint16_t *wl = idx + P.cap;                                       // [cap] pixels of the current line
-    uint32_t *rm = reinterpret_cast<uint32_t *>(wl + P.cap);          // [cap/32] removed bits
-    int16_t *table = reinterpret_cast<int16_t *>(rm + P.cap / 32);    // [HOUGH_TABLE_BYTES / 2]
+    uint32_t *keys = h_sm;                                            // [lcap]
+    uint16_t *idx = reinterpret_cast<uint16_t *>(keys + lcap);        // [lcap] visiting order
+    uint16_t *wl = idx + lcap;                                        // [lcap] pixels of the current line
+    uint32_t *rm = reinterpret_cast<uint32_t *>(wl + lcap);           // [lcap/32] removed bits
+    int16_t *table = reinterpret_cast<int16_t *>(rm + lcap / 32);     // [table_bytes / 2]
+    const int fail_flag = stage == 0 ? -2 : -3;
     __shared__ int s_red[2][HOUGH_THREADS / 32];
     __shared__ unsigned s_on[HOUGH_THREADS / 32], s_inb[HOUGH_THREADS / 32];
     __shared__ int s_ctl[8];
@@ -166,8 +172,11 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
         const int t = s_next;
         if (t >= T) break;
         const unsigned Nu = npoints[t];
-        if (Nu == 0) { if (tid == 0) nlines_out[t] = 0; continue; }
-        if (Nu > (unsigned)P.cap) { if (tid == 0) nlines_out[t] = -1; continue; }  // overflow path
+        if (stage == 0) {
+            if (Nu == 0) { if (tid == 0) nlines_out[t] = 0; continue; }
+            if (Nu > (unsigned)P.cap) { if (tid == 0) nlines_out[t] = -1; continue; }  // tier 3 (dense)
+            if (Nu > (unsigned)lcap) { if (tid == 0) nlines_out[t] = -2; continue; }    // tier 1b
+        } else if (nlines_out[t] != -2) continue;
         const int N = (int)Nu;
         const long long pc0 = clock64();
         long long p_setup = 0, p_vote = 0, p_walk = 0, p_unvote = 0, n_vote = 0, n_line = 0;
@@ -201,8 +210,8 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
         }
         __syncthreads();
         const int total = s_base[MDB_HOUGH_ANGLES];
-        if (total > HOUGH_TABLE_BYTES / 2) {  // does not fit on-chip: tier 2
-            if (tid == 0) nlines_out[t] = -2;
+        if (total > table_bytes / 2) {  // does not fit in this tier's table: next tier
+            if (tid == 0) nlines_out[t] = fail_flag;
             __syncthreads();
             continue;
         }
@@ -353,7 +362,7 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
         }
         if (sat) s_ctl[3] = 1;
         __syncthreads();
-        if (tid == 0) nlines_out[t] = s_ctl[3] ? -2 : s_ctl[2];  // a saturated cell (impossible for N <= cap): tier 2
+        if (tid == 0) nlines_out[t] = s_ctl[3] ? -3 : s_ctl[2];  // a saturated cell (impossible for N <= cap): tier 2
         __syncthreads();
     }
 }
@@ -381,7 +390,7 @@ hough_tier2_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
 
     for (int t = blockIdx.x; t < T; t += gridDim.x) {
         const unsigned Nu = npoints[t];
-        if (nlines_out[t] != -2) continue;  // only frames the shared-memory tier handed over
+        if (nlines_out[t] != -3) continue;  // only frames the shared-memory tiers handed over
         __syncthreads();
         const int N = (int)Nu;
         long long pc0 = clock64(), p_setup = 0, p_vote = 0, p_walk = 0, p_unvote = 0, p_reset = 0, n_vote = 0, n_line = 0;

@@ -15,6 +15,7 @@
 #include "stream_kernel.cuh"
 
 #define HOUGH_SMEM_BYTES (MDB_POINT_CAP * 8 + MDB_POINT_CAP / 8)  // keys u32 + order u16 + line u16 + removed bits
+#define HOUGH_SMEM_SMALL (HOUGH_CAP_SMALL * 8 + HOUGH_CAP_SMALL / 8)
 
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -256,7 +257,7 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
         ALLOC(c.d_npoints, T * sizeof(unsigned));
         ALLOC(c.d_points, (size_t)T * MDB_POINT_CAP * sizeof(uint32_t));
         ALLOC(c.d_order, (size_t)T * MDB_POINT_CAP * sizeof(uint16_t));
-        ALLOC(c.d_queue, sizeof(unsigned));
+        ALLOC(c.d_queue, 2 * sizeof(unsigned));
         ALLOC(c.d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t));
         ALLOC(c.d_nlines, T * sizeof(int));
         CKH(cudaMemsetAsync(c.d_dst, 0, (size_t)T * h->HW, h->stream));
@@ -393,11 +394,16 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
 
 static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
     CK(cudaStreamWaitEvent(h->stream3, c.ev_d1, 0));  // dst (stream2) has produced the on-pixel lists
-    CK(cudaMemsetAsync(c.d_queue, 0, sizeof(unsigned), h->stream3));
+    CK(cudaMemsetAsync(c.d_queue, 0, 2 * sizeof(unsigned), h->stream3));
     TL(c, 4, h->stream3);
     ppht_order_kernel<<<T, 32, MDB_POINT_CAP * 2, h->stream3>>>(T, MDB_POINT_CAP, c.d_npoints, c.d_order);
+    // tier 1a: 2 CTAs/SM (2048 points, 92 KB table); tier 1b: 1 CTA/SM (4096 points, 186 KB table)
+    hough_smem_kernel<<<std::min(T, 2 * h->sm_count), HOUGH_THREADS, HOUGH_SMEM_SMALL + HOUGH_TABLE_BYTES_SMALL, h->stream3>>>(
+        h->hp, T, c.d_npoints, c.d_points, c.d_order, c.d_lines, c.d_nlines, c.d_queue, h->d_prof,
+        HOUGH_CAP_SMALL, HOUGH_TABLE_BYTES_SMALL, 0);
     hough_smem_kernel<<<std::min(T, h->sm_count), HOUGH_THREADS, HOUGH_SMEM_BYTES + HOUGH_TABLE_BYTES, h->stream3>>>(
-        h->hp, T, c.d_npoints, c.d_points, c.d_order, c.d_lines, c.d_nlines, c.d_queue, h->d_prof);
+        h->hp, T, c.d_npoints, c.d_points, c.d_order, c.d_lines, c.d_nlines, c.d_queue + 1, h->d_prof,
+        MDB_POINT_CAP, HOUGH_TABLE_BYTES, 1);
     TL(c, 5, h->stream3);
     hough_tier2_kernel<<<std::min(T, h->slots), HOUGH_THREADS, HOUGH_SMEM_BYTES, h->stream3>>>(
         h->hp, T, c.d_npoints, c.d_points, h->d_accum, c.d_lines, c.d_nlines, h->d_prof);
@@ -408,7 +414,7 @@ static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
     }
     hough_tier3_kernel<<<1, HOUGH_THREADS, 0, h->stream3>>>(h->hp, T, c.d_dst, h->d_okeys, h->d_oidx, h->d_accum,
                                                           h->d_bitmap, h->d_walk, c.d_lines, c.d_nlines);
-    h->launches += 4;
+    h->launches += 5;
     TL(c, 6, h->stream3);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c.h_thr, c.d_thr, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream3));
