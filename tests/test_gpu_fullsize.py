@@ -1,0 +1,114 @@
+"""GPU parity at BASELINE.json's full sizes (configs 2-5), through the C ABI.
+
+(1) against the CPU oracle (cv2 backend = the reference's own numpy+cv2 calls) on a bounded number of
+    frames of the SURVEY App. E synthetic stream -- masks, thresholds and segments must be identical;
+(2) size-independent properties on longer runs: the streaming kernels and the generic per-frame
+    kernel (two independent implementations) agree bit for bit; splitting the stream into different
+    batch sizes changes nothing; `on-pixel count == popcount(dst)`; dst is {0,255}; zero-copy device
+    input == host input."""
+import numpy as np
+import pytest
+
+from conftest import assert_nms_equivalent
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(dy=True):
+    from metdetpy_b200 import BinaryCfg, BinaryCoreCfg, DynamicCfg, HoughLineCfg
+    return BinaryCfg(BinaryCoreCfg(True, 7, "normal", 0.1, 2), HoughLineCfg(10, 10, 10), DynamicCfg(dy, 5))
+
+
+def _synthetic_mask(H, W):
+    """Stand-in for test/mask-east.jpg (not shipped to the GPU box): ground + a tree line, ~90 % open."""
+    m = np.ones((H, W), np.uint8)
+    m[int(H * 0.93):, :] = 0
+    xs = np.arange(W)
+    ridge = (H * 0.93 - H * 0.05 * (1 + np.sin(xs / W * 9.0))).astype(int)
+    for x in range(0, W, 1):
+        m[ridge[x]:, x] = 0
+    return m
+
+
+@pytest.mark.parametrize("name,W,H,fps,n,dy,masked,T", [
+    ("config2_1080p_n5", 1920, 1080, 30, 5, False, False, 40),
+    ("config3_4k_n30", 3840, 2160, 30, 30, True, False, 48),
+    ("config4_4k60_n60_mask", 3840, 2160, 60, 60, True, True, 76),
+    ("config5_8k_n30", 7680, 4320, 30, 30, True, False, 40),
+])
+def test_baseline_config_against_oracle(name, W, H, fps, n, dy, masked, T):
+    from metdetpy_b200 import synth
+    from metdetpy_b200.detector import M3Detector
+    from oracle import m3_oracle as O
+    frames = synth.make_stream(T, W, H, fps)
+    mask = _synthetic_mask(H, W) if masked else np.ones((H, W), np.uint8)
+    ref = O.M3DetectorOracle(n / fps + 1e-9, fps, mask, 10, adaptive=True, init_value=7, sensitivity="normal",
+                             area=0.1, interval=2, hough=(10, 10, 10), dy_mask=dy,
+                             backend="cv2" if O.cv2 is not None else "numpy")
+    # the loader's mask_with (imgproc.py:96-101) happens on the device (apply_mask) for the masked config
+    det = M3Detector(n / fps + 1e-9, fps, mask, 10, _cfg(dy), None, max_batch=16, apply_mask=masked)
+    assert tuple(det.stack.std_roi) == tuple(ref.stack.std_roi)
+    nz_frames = 0
+    for s in range(0, T, 16):
+        res, dst = det.detect_many(frames[s:s + 16], return_dst=True)
+        for i, (lines, cls) in enumerate(res):
+            t = s + i
+            f = frames[t] * mask if masked else frames[t]
+            ref.update(f)
+            rl, rc = ref.detect()
+            info = det.last_infos[i]
+            assert info["bi_threshold"] == ref.bi_threshold, (t, info["bi_threshold"], ref.bi_threshold)
+            assert info["snr"] == pytest.approx(float(ref.stack.snr), rel=1e-12, abs=0), t
+            assert np.array_equal(dst[i], ref.dst), (t, int(np.count_nonzero(dst[i] != ref.dst)))
+            assert info["dst_sum"] == ref.dst_sum and info["gap"] == ref.gap, t
+            assert info["lines_num"] == ref.lines_num, t
+            raw = np.asarray(ref.linesp_ext).reshape(-1, 4)
+            assert np.array_equal(det.last_raw[i].reshape(-1, 4), raw), t
+            assert_nms_equivalent(lines, np.asarray(cls).reshape(-1, 10)[:, -1], rl,
+                                  np.asarray(rc).reshape(-1, 10)[:, -1], raw, t)
+            nz_frames += int(info["n_on"] > 0)
+    assert nz_frames > 0, "the stream never lit a pixel: generator or thresholds changed"
+    det.close()
+
+
+def test_4k_streaming_vs_generic_kernel_and_batch_split_invariance():
+    import torch
+    from metdetpy_b200 import synth
+    from metdetpy_b200.detector import M3Detector
+    W, H, fps, n, T = 3840, 2160, 30, 30, 96
+    dev = torch.device("cuda", 0)
+    xd = synth.make_stream_device(T, W, H, fps, dev)
+    torch.cuda.synchronize()
+    frames = xd.cpu().numpy()
+    mask = np.ones((H, W), np.uint8)
+
+    def run(batches, stream_kernel, on_device):
+        det = M3Detector(n / fps + 1e-9, fps, mask, 10, _cfg(True), None, max_batch=max(batches))
+        det._eng.set_option("stream_kernel", stream_kernel)
+        out, s = [], 0
+        for b in batches:
+            if on_device:
+                res, dst = det.detect_many((xd[s:s + b].data_ptr(), b), on_device=True, return_dst=True)
+            else:
+                res, dst = det.detect_many(frames[s:s + b], return_dst=True)
+            for i in range(b):
+                info = det.last_infos[i]
+                assert set(np.unique(dst[i])) <= {0, 255}
+                assert int(np.count_nonzero(dst[i])) == info["n_on"]
+                out.append((dst[i].copy(), info["bi_threshold"], info["lines_num"], det.last_raw[i].copy(),
+                            np.asarray(res[i][0]).reshape(-1, 4).copy()))
+            s += b
+        det.close()
+        return out
+
+    a = run([96], 1, True)                 # one batch, streaming kernels, zero-copy device input
+    b = run([7, 25, 64], 1, False)         # ragged batches, host input
+    c = run([48, 48], 0, False)            # generic per-frame kernel
+    lit = 0
+    for t in range(T):
+        for other in (b, c):
+            assert np.array_equal(a[t][0], other[t][0]), t
+            assert a[t][1] == other[t][1] and a[t][2] == other[t][2], t
+            assert np.array_equal(a[t][3], other[t][3]) and np.array_equal(a[t][4], other[t][4]), t
+        lit += a[t][2] > 0
+    assert lit > 10
