@@ -202,6 +202,9 @@ def main_ours(a):
         det._eng.set_option("stream_kernel", 0)
     if a.wpt:
         det._eng.set_option("temporal_wpt", a.wpt)
+    for kv in os.environ.get("MDB_OPTS", "").split(","):
+        if "=" in kv:
+            det._eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     ext = torch.cuda.ExternalStream(det._eng.stream_ptr(), device=dev)
 
     # this rank's chunk of the stream: frames [rank*chunk, ...); generated on the device

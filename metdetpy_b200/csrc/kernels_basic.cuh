@@ -13,10 +13,16 @@ __device__ __forceinline__ bool is_noise_sample(long long tau, int n, long long 
     return (tau > 1 && tau <= n) || (tau > n && std_interval > 0 && tau % std_interval == 0);
 }
 
+struct SampleList {  // frames of the batch that are noise samples (usually a handful)
+    int count;       // < 0: not listed, every frame of the batch gets a grid row and tests itself
+    int idx[63];
+};
+
 __global__ void __launch_bounds__(256)
 noise_sample_kernel(FrameSrc src, int W, int n, long long timer0, long long std_interval, int r0,
-                    int c0, int rh, int rw, unsigned long long *acc, long long min_tau) {
-    const int i = blockIdx.y;
+                    int c0, int rh, int rw, unsigned long long *acc, long long min_tau,
+                    const __grid_constant__ SampleList sl) {
+    const int i = sl.count < 0 ? blockIdx.y : sl.idx[blockIdx.y];
     const long long tau = timer0 + i + 1;
     if (tau < min_tau || !is_noise_sample(tau, n, std_interval)) return;
     const int L = (int)(tau < n ? tau : n);

@@ -46,7 +46,9 @@ struct BatchCtx {
     int32_t *h_lines = nullptr;
     int *d_thr = nullptr;            // per-frame thresholds of this batch (device)
     double *d_thrf = nullptr, *d_snr = nullptr;
-    uint8_t *d_dst = nullptr;        // [T][H][W] masks of this batch
+    uint8_t *d_dst = nullptr;        // [T][H][W] masks of this batch (persistent: zero where dstbits is zero)
+    uint32_t *d_dstbits = nullptr;   // [T][H][Wb] what d_dst currently holds, 1 bit per pixel (streaming path)
+    bool dst_dirty = false;          // the generic kernel rewrote d_dst without maintaining d_dstbits
     unsigned *d_npoints = nullptr;   // [T] on-pixel counts
     uint32_t *d_points = nullptr;    // [T][cap] on-pixel lists
     uint16_t *d_order = nullptr;     // [T][cap] PPHT visiting order per frame
@@ -142,7 +144,7 @@ static void free_all(mdb_detector *h) {
     for (void *p : dev)
         if (p) cudaFree(p);
     for (BatchCtx &c : h->ctx) {
-        void *cd[] = {c.d_thr, c.d_thrf, c.d_snr, c.d_dst, c.d_npoints, c.d_points, c.d_order, c.d_queue,
+        void *cd[] = {c.d_thr, c.d_thrf, c.d_snr, c.d_dst, c.d_dstbits, c.d_npoints, c.d_points, c.d_order, c.d_queue,
                       c.d_lines, c.d_nlines};
         for (void *p : cd)
             if (p) cudaFree(p);
@@ -261,6 +263,8 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
         ALLOC(c.d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t));
         ALLOC(c.d_nlines, T * sizeof(int));
         CKH(cudaMemsetAsync(c.d_dst, 0, (size_t)T * h->HW, h->stream));
+        ALLOC(c.d_dstbits, (size_t)T * h->H * h->Wb * sizeof(uint32_t));
+        CKH(cudaMemsetAsync(c.d_dstbits, 0, (size_t)T * h->H * h->Wb * sizeof(uint32_t), h->stream));
     }
     ALLOC(h->d_accum, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t));
     ALLOC(h->d_bitmap, bm_words * sizeof(uint32_t));
@@ -346,8 +350,18 @@ static int launch_noise_thr(mdb_detector *h, BatchCtx &bc, const FrameSrc &src, 
     TL(bc, 0, h->stream);
     CK(cudaMemsetAsync(h->d_noise, 0, (size_t)T * 2 * sizeof(unsigned long long), h->stream));
     const int gx = std::max(1, std::min((rh * rw + 255) / 256, 592));
-    noise_sample_kernel<<<dim3(gx, T), 256, 0, h->stream>>>(src, h->W, h->n, timer0, std_interval,
-                                                          c.roi[0], c.roi[1], rh, rw, h->d_noise, 0);
+    SampleList sl;
+    sl.count = 0;
+    for (int i = 0; i < T && sl.count >= 0; i++) {
+        const long long tau = timer0 + i + 1;
+        if ((tau > 1 && tau <= h->n) || (tau > h->n && std_interval > 0 && tau % std_interval == 0)) {
+            if (sl.count < 63) sl.idx[sl.count++] = i;
+            else sl.count = -1;  // too many to list: one grid row per frame
+        }
+    }
+    if (sl.count != 0)
+        noise_sample_kernel<<<dim3(gx, sl.count < 0 ? T : sl.count), 256, 0, h->stream>>>(
+            src, h->W, h->n, timer0, std_interval, c.roi[0], c.roi[1], rh, rw, h->d_noise, 0, sl);
     threshold_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_noise, T, timer0, h->n, std_interval,
                                              (long long)rh * rw, c.adaptive, c.sensitivity, bc.d_thr,
                                              bc.d_thrf, bc.d_snr);
@@ -364,8 +378,13 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
     CK(cudaEventRecord(c.ev_f0, h->stream));
     int nl = 0;
     if (h->use_stream_kernel && stream_kernel_supported(h->sk, T)) {
+        if (c.dst_dirty) {  // the generic kernel wrote this buffer last: resynchronise buffer and bitmap
+            CK(cudaMemsetAsync(c.d_dst, 0, (size_t)h->cfg.max_batch * h->HW, h->stream2));
+            CK(cudaMemsetAsync(c.d_dstbits, 0, (size_t)h->cfg.max_batch * h->H * h->Wb * sizeof(uint32_t), h->stream2));
+            c.dst_dirty = false;
+        }
         int rc = stream_kernel_launch(h->sk, src, timer0, dy0, T, h->cfg.dy_mask, c.d_thr, act_ring(h),
-                                      c.d_dst, c.d_npoints, c.d_points, MDB_POINT_CAP, h->stream, h->stream2,
+                                      c.d_dst, c.d_dstbits, c.d_npoints, c.d_points, MDB_POINT_CAP, h->stream, h->stream2,
                                       c.ev_f1, c.ev_d0, &nl);
         if (rc != 0) return fail(MDB_ERR_CUDA, "stream kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
@@ -373,6 +392,7 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
         CK(cudaEventRecord(c.ev_f1, h->stream));
         CK(cudaStreamWaitEvent(h->stream2, c.ev_f1, 0));
         CK(cudaEventRecord(c.ev_d0, h->stream2));
+        c.dst_dirty = true;
         dim3 grid((h->W + V1_TW - 1) / V1_TW, (h->H + V1_TH - 1) / V1_TH);
         for (int i = 0; i < T; i++) {
             const long long t = timer0 + i;
@@ -657,8 +677,10 @@ extern "C" int mdb_noise_sums(const uint8_t *frames, int T, int on_device, int64
         const int gx = std::max(1, std::min((rh * rw + 255) / 256, 592));
         // only samples whose whole window lies inside the supplied frames (or starts at global frame 0)
         const long long min_tau = t0 == 0 ? 0 : t0 + window;
+        SampleList sl;
+        sl.count = -1;
         noise_sample_kernel<<<dim3(gx, T), 256>>>(src, width, window, t0, (long long)nz_interval * window, roi[0],
-                                                 roi[1], rh, rw, d_acc, min_tau);
+                                                 roi[1], rh, rw, d_acc, min_tau, sl);
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpy(sums, d_acc, (size_t)T * 16, cudaMemcpyDeviceToHost);
     }
@@ -805,6 +827,9 @@ extern "C" int mdb_set_option(mdb_handle h, const char *name, int value) {
         h->timeline = value;
         return MDB_OK;
     }
+    if (!strcmp(name, "dst_exp")) { h->sk.dst_exp = value; return MDB_OK; }
+    if (!strcmp(name, "sp_rows")) { h->sk.sp_rows = value; return MDB_OK; }
+    if (!strcmp(name, "dst_rows")) { h->sk.dst_rows = value; return MDB_OK; }
     if (!strcmp(name, "temporal_wpt")) {
         if (!h->sk.ok || stream_state_config(h->sk, value) != 0)
             return fail(MDB_ERR_INVALID, "mdb_set_option: temporal_wpt=%d not possible here", value);

@@ -21,6 +21,7 @@
 
 #define ST_K 8          // frames in flight per thread (cp.async groups)
 #define SP_WARPS 4      // warps per CTA in the spatial kernel
+#define SP_MLP 8        // rows loaded per warp before they are processed (memory-level parallelism)
 #define SP_USE 30       // useful 32-px words per warp strip (lanes 1..30; lanes 0 and 31 are halo)
 
 struct StreamState {
@@ -28,6 +29,8 @@ struct StreamState {
     int W = 0, H = 0, n = 0, max_batch = 0, device = 0;
     int t_threads = 32;     // CTA size of the temporal kernel
     int t_wpt = 2;          // 32-bit words (4 px) per thread in the temporal kernel
+    int dst_exp = 0;        // debug: experiment switches of dst_kernel
+    int dst_rows = 32;      // output rows per warp strip in dst_kernel
     size_t t_smem_per_thread = 0;
     int sp_rows = 8;        // output rows per warp strip in the spatial kernel
     uint32_t *d_bits = nullptr;  // [max_batch][H][W/32]
@@ -274,11 +277,24 @@ act_kernel(const uint32_t *__restrict__ bits, int W, int H, int T, int rows, int
     uint32_t *ob = ring.frame(dy0 + t) + (lane_in ? wx : 0);
     RowH h0 = {0, 0}, h1 = {0, 0};
     unsigned hd0 = 0, hd1 = 0, he0 = FULL, he1 = FULL;
-    // rows y0-3 .. y0+rows+2 of b are needed; software-prefetch one row ahead
-    unsigned nxt = lane_in ? __ldg(fb + (size_t)min(max(y0 - 3, 0), H - 1) * Wb) : 0u;
-    for (int yy = y0 - 3; yy < y0 + rows + 3; yy++) {
-        const unsigned bw = nxt;
-        if (yy + 1 < y0 + rows + 3) nxt = lane_in ? __ldg(fb + (size_t)min(max(yy + 1, 0), H - 1) * Wb) : 0u;
+    // rows y0-3 .. y0+rows+2 of b are needed; SP_MLP rows are loaded at a time so that every warp keeps
+    // several independent 128-byte requests in flight (the pass is DRAM-latency-bound otherwise)
+    const int y_first = y0 - 3, y_last = y0 + rows + 3;
+    for (int yb = y_first; yb < y_last; yb += SP_MLP) {
+    unsigned rowbuf[SP_MLP];
+    {   // the row pointer advances only inside the image: rows outside repeat the edge row (medianBlur)
+        const uint32_t *pr = fb + (unsigned)min(max(yb, 0), H - 1) * (unsigned)Wb;
+#pragma unroll
+        for (int u = 0; u < SP_MLP; u++) {
+            rowbuf[u] = __ldg(pr);
+            if ((unsigned)(yb + u) < (unsigned)(H - 1)) pr += Wb;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < SP_MLP; u++) {
+        const int yy = yb + u;
+        if (yy >= y_last) break;
+        const unsigned bw = lane_in ? rowbuf[u] : 0u;
         // ---- horizontal sums of b row yy (rows/cols replicated outside the image: medianBlur) --
         unsigned Lw = __shfl_up_sync(FULL, bw, 1), Rw = __shfl_down_sync(FULL, bw, 1);
         if (wx == 0) Lw = (bw & 1u) << 31;
@@ -317,6 +333,7 @@ act_kernel(const uint32_t *__restrict__ bits, int W, int H, int T, int rows, int
             he0 = he1; he1 = he2;
         }
     }
+    }
 }
 
 __device__ __forceinline__ unsigned nib_to_bytes(unsigned nib) {
@@ -326,8 +343,8 @@ __device__ __forceinline__ unsigned nib_to_bytes(unsigned nib) {
 
 __global__ void __launch_bounds__(SP_WARPS * 32)
 dst_kernel(ActRing ring, int W, int H, int T, int n, long long dy0, int dy_on, int rows, int strips,
-           int bands, uint8_t *__restrict__ dst, unsigned *__restrict__ npoints,
-           uint32_t *__restrict__ points, int cap) {
+           int bands, uint8_t *__restrict__ dst, uint32_t *__restrict__ dstbits,
+           unsigned *__restrict__ npoints, uint32_t *__restrict__ points, int cap, int exp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile = blockIdx.x * SP_WARPS + warp;
     const int t = blockIdx.y;
@@ -344,9 +361,40 @@ dst_kernel(ActRing ring, int W, int H, int T, int n, long long dy0, int dy_on, i
     const uint32_t *cur = ring.frame(d) + (lane_in ? wx : 0);
     unsigned hm0 = FULL, hm1 = FULL, act_prev = 0;
     const int ylast = dy_on ? y0 + rows + 1 : y0 + rows;
-    for (int yy = dy_on ? y0 - 1 : y0; yy < ylast; yy++) {
-        const bool row_in = yy >= 0 && yy < H;
-        const unsigned act = (lane_in && row_in) ? __ldg(cur + (size_t)yy * Wb) : 0u;
+    const int yfirst = dy_on ? y0 - 1 : y0;
+    const int ylag = dy_on ? 1 : 0;  // the output row trails the input row by this much
+    const uint32_t *dbase = dstbits + (size_t)t * H * Wb + (lane_in ? wx : 0);
+    const unsigned lmask = lane_in ? FULL : 0u, omask = lane_out ? FULL : 0u;
+    for (int yb = yfirst; yb < ylast; yb += SP_MLP) {
+    unsigned actbuf[SP_MLP], prevbuf[SP_MLP];
+    {   // row pointers advance by one row only inside the image (rows outside repeat the edge row: always a
+        // valid address, no predicated loads, no per-load index arithmetic)
+        const uint32_t *pa = cur + (unsigned)min(max(yb, 0), H - 1) * (unsigned)Wb;
+        const uint32_t *pd = dbase + (unsigned)min(max(yb - ylag, 0), H - 1) * (unsigned)Wb;
+#pragma unroll
+        for (int u = 0; u < SP_MLP; u++) {
+            const int yy = yb + u;
+            actbuf[u] = __ldg(pa);
+            prevbuf[u] = *pd;
+            if ((unsigned)yy < (unsigned)(H - 1)) pa += Wb;
+            if ((unsigned)(yy - ylag) < (unsigned)(H - 1)) pd += Wb;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < SP_MLP; u++) {
+        const int yy = yb + u;
+        if (yy >= ylast) break;
+        const int yo_u = yy - ylag;
+        const unsigned act = ((unsigned)yy < (unsigned)H) ? (actbuf[u] & lmask) : 0u;
+        const unsigned prev_u = ((unsigned)(yo_u - y0) < (unsigned)rows && yo_u < H) ? (prevbuf[u] & omask) : 0u;
+        // almost every 960-pixel row segment is empty now, was empty one row ago, and holds zeros in
+        // the mask buffer: nothing to compute or to write (m = all ones, so the eroded m is too)
+        if (!__any_sync(FULL, (act | act_prev | prev_u) != 0u)) {
+            hm0 = hm1;
+            hm1 = FULL;
+            act_prev = 0;
+            continue;
+        }
         unsigned out_bits;
         int yo;
         if (dy_on) {
@@ -364,21 +412,22 @@ dst_kernel(ActRing ring, int W, int H, int T, int n, long long dy0, int dy_on, i
             out_bits = act;
             yo = yy;
         }
-        if (yo >= y0 && yo < y0 + rows && yo < H) {  // warp-uniform
-            uint8_t *orow = dst + (size_t)t * W * H + (size_t)yo * W + (size_t)strip * SP_USE * 32;
-            const bool mine = lane_out;
-            if (!__any_sync(FULL, mine && out_bits != 0)) {
-                // the common case: nothing on in this 960-pixel row segment -> fully coalesced zero fill
-                const int nbytes = min(SP_USE, Wb - strip * SP_USE) * 32;
-                for (int off = lane * 16; off < nbytes; off += 512)
-                    __stcs(reinterpret_cast<uint4 *>(orow + off), make_uint4(0, 0, 0, 0));
-            } else if (mine) {
-                uint4 a = make_uint4(0, 0, 0, 0), b = a;
+        if (yo >= y0 && yo < y0 + rows && yo < H && lane_out) {
+            // The u8 mask buffer is persistent and almost everywhere zero, and HBM write-only bandwidth
+            // is the scarcest resource of this pass: `dstbits` remembers what the buffer holds (1 bit per
+            // pixel), so only 32-pixel words that are or were non-zero are rewritten.
+            uint32_t *pb = dstbits + ((size_t)t * H + yo) * Wb + wx;
+            const unsigned prev = prev_u;
+            if (prev | out_bits) {
+                uint4 a = make_uint4(nib_to_bytes(out_bits & 15u), nib_to_bytes((out_bits >> 4) & 15u),
+                                     nib_to_bytes((out_bits >> 8) & 15u), nib_to_bytes((out_bits >> 12) & 15u));
+                uint4 b = make_uint4(nib_to_bytes((out_bits >> 16) & 15u), nib_to_bytes((out_bits >> 20) & 15u),
+                                     nib_to_bytes((out_bits >> 24) & 15u), nib_to_bytes(out_bits >> 28));
+                uint4 *o = reinterpret_cast<uint4 *>(dst + (size_t)t * W * H + (size_t)yo * W + (size_t)wx * 32);
+                o[0] = a;
+                o[1] = b;
+                if (prev != out_bits) *pb = out_bits;
                 if (out_bits) {
-                    a = make_uint4(nib_to_bytes(out_bits & 15u), nib_to_bytes((out_bits >> 4) & 15u),
-                                   nib_to_bytes((out_bits >> 8) & 15u), nib_to_bytes((out_bits >> 12) & 15u));
-                    b = make_uint4(nib_to_bytes((out_bits >> 16) & 15u), nib_to_bytes((out_bits >> 20) & 15u),
-                                   nib_to_bytes((out_bits >> 24) & 15u), nib_to_bytes(out_bits >> 28));
                     const unsigned c = __popc(out_bits);
                     unsigned slot = atomicAdd(npoints + t, c);
                     unsigned ob = out_bits;
@@ -390,11 +439,9 @@ dst_kernel(ActRing ring, int W, int H, int T, int n, long long dy0, int dy_on, i
                         slot++;
                     }
                 }
-                uint4 *o = reinterpret_cast<uint4 *>(orow + (size_t)(lane - 1) * 32);
-                __stcs(o, a);
-                __stcs(o + 1, b);
             }
         }
+    }
     }
 }
 
@@ -423,12 +470,15 @@ static inline int stream_state_init(StreamState &s, int W, int H, int n, int dev
     s.W = W; s.H = H; s.n = n; s.device = device; s.max_batch = max_batch; s.ok = 0;
     if (W % 32 != 0 || n < 2 || n > 128 || max_batch > 4096) return 0;  // generic kernel serves these
     const size_t budget = 220 * 1024;
-    if (stream_state_config(s, 2) != 0) return 0;
+    // 16 px per thread needs fewer instructions per pixel, 8 px per thread doubles the resident warps:
+    // the wider variant only pays when its ring still leaves >= 8 warps per SM
+    const bool wide = (size_t)(2 * n + ST_K) * 16 * 32 * 8 <= budget;
+    if (stream_state_config(s, wide ? 4 : 2) != 0 && stream_state_config(s, 2) != 0) return 0;
     if (cudaMalloc((void **)&s.d_bits, (size_t)max_batch * H * (W / 32) * sizeof(uint32_t)) != cudaSuccess) {
         cudaGetLastError();
         return 0;  // fall back to the generic per-frame kernel
     }
-    s.sp_rows = 32;
+    s.sp_rows = 64;
 #define ST_SETATTR(K)                                                                                      \
     if (cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess || \
         cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess)       \
@@ -447,7 +497,7 @@ static inline bool stream_kernel_supported(const StreamState &s, int T) { return
 // bandwidth alone tops out near 60 % of the copy peak) overlap the read-only, ALU-heavy temporal pass
 // of the NEXT batch.  Returns 0 / -1; *launches gets the number of kernel launches.
 static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long timer0, long long dy0, int T,
-                                       int dy_on, const int *d_thr, ActRing ring, uint8_t *dst,
+                                       int dy_on, const int *d_thr, ActRing ring, uint8_t *dst, uint32_t *dstbits,
                                        unsigned *npoints, uint32_t *points, int cap, cudaStream_t st1,
                                        cudaStream_t st2, cudaEvent_t ev_f1, cudaEvent_t ev_d0, int *launches) {
     const int HWG = (int)((size_t)s.W * s.H / (4 * s.t_wpt));  // pixel groups = threads
@@ -472,8 +522,10 @@ static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long t
     if (cudaEventRecord(ev_f1, st1) != cudaSuccess) return -1;
     if (cudaStreamWaitEvent(st2, ev_f1, 0) != cudaSuccess) return -1;
     if (cudaEventRecord(ev_d0, st2) != cudaSuccess) return -1;
-    dst_kernel<<<g, SP_WARPS * 32, 0, st2>>>(ring, s.W, s.H, T, s.n, dy0, dy_on, s.sp_rows, strips, bands, dst,
-                                             npoints, points, cap);
+    const int dbands = (s.H + s.dst_rows - 1) / s.dst_rows;
+    dim3 gd((strips * dbands + SP_WARPS - 1) / SP_WARPS, T);
+    dst_kernel<<<gd, SP_WARPS * 32, 0, st2>>>(ring, s.W, s.H, T, s.n, dy0, dy_on, s.dst_rows, strips, dbands, dst,
+                                              dstbits, npoints, points, cap, s.dst_exp);
     if (cudaGetLastError() != cudaSuccess) return -1;
     *launches = 3;
     return 0;
