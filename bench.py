@@ -330,6 +330,10 @@ def main_ours(a):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         alg_bytes = 2.0 * HW * B * a.steps  # read the new u8 frame once + write the u8 mask once
         achieved = alg_bytes / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else None
+        # DRAM bytes of the chain from the ncu --set full capture in profiles/r01_ncu_full_summary.txt
+        # (4K, n=30, 512 frames: temporal 5.01 GB + act 1.02 GB + dst 1.10 GB = 1.68 H*W per frame), per launch
+        default_cfg = (W, H, n, B) == (3840, 2160, 30, 512) and not a.no_dy
+        traffic = 1.68 * HW * B / 3.0 if default_cfg else None
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": wall_max / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -340,8 +344,10 @@ def main_ours(a):
             "device_ms_per_step": dev_ms / a.steps,
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "kernel": "fused stack->diff->median->threshold->close->dy-mask",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "traffic_note": "bytes per launch (avg of the 3 launches of the chain), ncu capture profiles/r01_ncu_full_summary.txt",
+                         "algorithmic_bytes_per_launch": 2.0 * HW * B / 3.0,
+                         "kernel": "fused mask chain: temporal_kernel (stack->diff->threshold) + act_kernel (median+close) + dst_kernel (dy-mask, mask bytes)",
                          "kernel_ms_per_launch": fused_ms / max(fused_launches, 1),
                          "kernel_launches": fused_launches,
                          "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s"},
