@@ -109,7 +109,7 @@ int mdb_detect_batch(mdb_handle h, const uint8_t *frames, int T, int on_device,
 
 /* Asynchronous halves of mdb_detect_batch for overlapping the next batch's host->device copy with
  * this batch's kernels: submit enqueues copy + all kernels + the small result copy and returns;
- * collect waits for the OLDEST submitted batch and runs the host NMS.  Up to two batches may be in
+ * collect waits for the OLDEST submitted batch and runs the host NMS.  Up to three batches may be in
  * flight per handle (submit, submit, collect, submit, collect, ...); each keeps its own dst masks. */
 int mdb_submit_batch(mdb_handle h, const uint8_t *frames, int T, int on_device);
 int mdb_collect_batch(mdb_handle h, mdb_frame_info *infos, int32_t *lines, double *nonline_prob,

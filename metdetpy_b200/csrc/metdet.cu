@@ -36,7 +36,7 @@ static int fail(int code, const char *fmt, ...) {
                         __FILE__, __LINE__);                                                  \
     } while (0)
 
-#define NCTX 2  // batches that may be in flight (submit .. collect) per handle
+#define NCTX 3  // batches that may be in flight (submit .. collect) per handle
 
 // host-visible results of one batch (pinned) + its completion events
 struct BatchCtx {
@@ -49,6 +49,11 @@ struct BatchCtx {
     uint8_t *d_dst = nullptr;        // [T][H][W] masks of this batch (persistent: zero where dstbits is zero)
     uint32_t *d_dstbits = nullptr;   // [T][H][Wb] what d_dst currently holds, 1 bit per pixel (streaming path)
     bool dst_dirty = false;          // the generic kernel rewrote d_dst without maintaining d_dstbits
+    uint32_t *d_alist = nullptr;     // [T][SPX_ACAP] non-zero act words per frame (streaming path)
+    unsigned *d_acount = nullptr;    // [T]
+    uint32_t *d_wlist = nullptr;     // [T][SPX_WCAP] non-zero words of each d_dst slot
+    unsigned *d_wcount = nullptr;    // [T]
+    unsigned *d_dense = nullptr;     // [1 + T] frames whose lists overflowed
     unsigned *d_npoints = nullptr;   // [T] on-pixel counts
     uint32_t *d_points = nullptr;    // [T][cap] on-pixel lists
     uint16_t *d_order = nullptr;     // [T][cap] PPHT visiting order per frame
@@ -145,7 +150,7 @@ static void free_all(mdb_detector *h) {
         if (p) cudaFree(p);
     for (BatchCtx &c : h->ctx) {
         void *cd[] = {c.d_thr, c.d_thrf, c.d_snr, c.d_dst, c.d_dstbits, c.d_npoints, c.d_points, c.d_order, c.d_queue,
-                      c.d_lines, c.d_nlines};
+                      c.d_lines, c.d_nlines, c.d_alist, c.d_acount, c.d_wlist, c.d_wcount, c.d_dense};
         for (void *p : cd)
             if (p) cudaFree(p);
     }
@@ -237,10 +242,15 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
         }                                                                                   \
     } while (0)
 
-    CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CKH(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
-    CKH(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
-    CKH(cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
+    {   // the back half of batch k (dst, Hough: short, latency-bound) must not queue behind the thousands of
+        // CTAs of batch k+1's temporal pass: it runs at a higher stream priority
+        int prio_lo = 0, prio_hi = 0;
+        CKH(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CKH(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_lo));
+        CKH(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_hi));
+        CKH(cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, prio_hi));
+        CKH(cudaStreamCreateWithPriority(&h->cstream, cudaStreamNonBlocking, prio_lo));
+    }
     CKH(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
     const size_t bm_words = (h->HW + 31) / 32;
     h->Wb = (h->W + 31) / 32;
@@ -265,6 +275,14 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
         CKH(cudaMemsetAsync(c.d_dst, 0, (size_t)T * h->HW, h->stream));
         ALLOC(c.d_dstbits, (size_t)T * h->H * h->Wb * sizeof(uint32_t));
         CKH(cudaMemsetAsync(c.d_dstbits, 0, (size_t)T * h->H * h->Wb * sizeof(uint32_t), h->stream));
+        ALLOC(c.d_alist, (size_t)T * SPX_ACAP * sizeof(uint32_t));
+        ALLOC(c.d_acount, T * sizeof(unsigned));
+        ALLOC(c.d_wlist, (size_t)T * SPX_WCAP * sizeof(uint32_t));
+        ALLOC(c.d_wcount, T * sizeof(unsigned));
+        ALLOC(c.d_dense, (size_t)(T + 1) * sizeof(unsigned));
+        CKH(cudaMemsetAsync(c.d_acount, 0, T * sizeof(unsigned), h->stream));
+        CKH(cudaMemsetAsync(c.d_wcount, 0, T * sizeof(unsigned), h->stream));
+        CKH(cudaMemsetAsync(c.d_dense, 0, (size_t)(T + 1) * sizeof(unsigned), h->stream));
     }
     ALLOC(h->d_accum, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t));
     ALLOC(h->d_bitmap, bm_words * sizeof(uint32_t));
@@ -381,11 +399,14 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
         if (c.dst_dirty) {  // the generic kernel wrote this buffer last: resynchronise buffer and bitmap
             CK(cudaMemsetAsync(c.d_dst, 0, (size_t)h->cfg.max_batch * h->HW, h->stream2));
             CK(cudaMemsetAsync(c.d_dstbits, 0, (size_t)h->cfg.max_batch * h->H * h->Wb * sizeof(uint32_t), h->stream2));
+            CK(cudaMemsetAsync(c.d_wcount, 0, (size_t)h->cfg.max_batch * sizeof(unsigned), h->stream2));
             c.dst_dirty = false;
         }
+        SparseLists sl;
+        sl.alist = c.d_alist; sl.acount = c.d_acount; sl.wlist = c.d_wlist; sl.wcount = c.d_wcount; sl.dense = c.d_dense;
         int rc = stream_kernel_launch(h->sk, src, timer0, dy0, T, h->cfg.dy_mask, c.d_thr, act_ring(h),
-                                      c.d_dst, c.d_dstbits, c.d_npoints, c.d_points, MDB_POINT_CAP, h->stream, h->stream2,
-                                      c.ev_f1, c.ev_d0, &nl);
+                                      c.d_dst, c.d_dstbits, c.d_npoints, c.d_points, MDB_POINT_CAP, sl, h->stream,
+                                      h->stream2, c.ev_f1, c.ev_d0, &nl);
         if (rc != 0) return fail(MDB_ERR_CUDA, "stream kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
         // generic per-frame kernel: the whole chain runs on the back stream, after the front stream's thresholds
@@ -595,13 +616,20 @@ static int submit_impl(mdb_handle h, const uint8_t *frames, int T, int on_device
     } else {
         // the copy runs on its own stream so that it overlaps the previous batch's kernels; the ring
         // holds two batches + history, so it only has to wait for the batch before the previous one
+        // (its readers are the front-stream kernels of that batch)
         BatchCtx &prev2 = h->ctx[(h->submitted + NCTX - 2) % NCTX];
-        if (h->submitted >= 2) CK(cudaStreamWaitEvent(h->cstream, prev2.ev_done, 0));
+        if (h->submitted >= 2) CK(cudaStreamWaitEvent(h->cstream, prev2.ev_f1, 0));
         int rc = copy_to_ring(h, frames, 0, T, timer0, cudaMemcpyHostToDevice, h->cstream);
         if (rc) return rc;
         CK(cudaEventRecord(h->ev_copy, h->cstream));
         CK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
         src = frame_src(h, nullptr, 0);
+    }
+    if (h->submitted >= 2) {
+        // the act ring holds two batches + history: this batch's act frames land on those of the batch
+        // before the previous one, whose dst pass (back stream) must have read them
+        BatchCtx &prev2 = h->ctx[(h->submitted + NCTX - 2) % NCTX];
+        CK(cudaStreamWaitEvent(h->stream, prev2.ev_d1, 0));
     }
     int rc;
     if (thr) {  // thresholds supplied by the caller (time-sharded streams): no local EMA recurrence
@@ -827,7 +855,8 @@ extern "C" int mdb_set_option(mdb_handle h, const char *name, int value) {
         h->timeline = value;
         return MDB_OK;
     }
-    if (!strcmp(name, "dst_exp")) { h->sk.dst_exp = value; return MDB_OK; }
+    if (!strcmp(name, "force_dense")) { h->sk.force_dense = value; return MDB_OK; }
+    if (!strcmp(name, "force_strip")) { h->sk.force_strip = value; return MDB_OK; }
     if (!strcmp(name, "sp_rows")) { h->sk.sp_rows = value; return MDB_OK; }
     if (!strcmp(name, "dst_rows")) { h->sk.dst_rows = value; return MDB_OK; }
     if (!strcmp(name, "temporal_wpt")) {

@@ -11,26 +11,26 @@
 //       running u16x2 register.  The decision  median(max - floor(sum/L)) > thr  is rewritten as
 //       "at least 5 of the 9 neighbours have  max*L - sum > thr*L",  so this kernel only emits the
 //       per-pixel predicate (exact integer arithmetic, no division) as a bit.
-//   act_kernel / dst_kernel  (3x3 median == majority of 9 bits, 3x3 close, dynamic mask, dst): read
-//       the bits, write the u8 mask.  All 3x3 operators are bitwise on 32-pixel words; see below.
+//   act4_kernel / dst_sparse_kernel (spatial_kernel.cuh: 3x3 median == majority of 9 bits, 3x3 close,
+//       dynamic mask, dst): read the bits, write the u8 mask.  All 3x3 operators are bitwise on
+//       32-pixel words.
 //
 // Per frame HBM traffic: H*W (frame) + 4 * H*W/8 (predicate bits and act bits, out and in)
 // + H*W (mask) = 2.5 H*W, against the algorithmic 2 H*W of SURVEY.md section 8(d).
 #pragma once
 #include "common.cuh"
+#include "spatial_kernel.cuh"
 
 #define ST_K 8          // frames in flight per thread (cp.async groups)
-#define SP_WARPS 4      // warps per CTA in the spatial kernel
-#define SP_MLP 8        // rows loaded per warp before they are processed (memory-level parallelism)
-#define SP_USE 30       // useful 32-px words per warp strip (lanes 1..30; lanes 0 and 31 are halo)
 
 struct StreamState {
     int ok = 0;
     int W = 0, H = 0, n = 0, max_batch = 0, device = 0;
     int t_threads = 32;     // CTA size of the temporal kernel
     int t_wpt = 2;          // 32-bit words (4 px) per thread in the temporal kernel
-    int dst_exp = 0;        // debug: experiment switches of dst_kernel
-    int dst_rows = 32;      // output rows per warp strip in dst_kernel
+    int dst_rows = 32;      // output rows per warp strip in dst_dense_kernel
+    int force_dense = 0;    // test hook: dst of every frame by the full-scan kernel
+    int force_strip = 0;    // test hook: act by the warp-strip kernel even when W % 128 == 0
     size_t t_smem_per_thread = 0;
     int sp_rows = 8;        // output rows per warp strip in the spatial kernel
     uint32_t *d_bits = nullptr;  // [max_batch][H][W/32]
@@ -244,208 +244,6 @@ temporal_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *__
 }
 
 // ------------------------------------------------------------------------------------------
-// Spatial kernels: everything after the per-pixel predicate is bitwise on 32-pixel words and --
-// because the dynamic mask "pixel was on in ALL of the last L frames" (Detector.py:234-242) is the
-// AND of the last L `act` bit-frames -- carries no sequential state: both kernels are parallel over
-// (frame, strip, band).  One warp = one strip of SP_USE words (960 px; lanes 0 and 31 are halo
-// columns) walked top to bottom, neighbours exchanged with warp shuffles.
-//   act_kernel : bits -> majority-of-9 (== medianBlur 3 then threshold) -> dilate -> erode = act
-//   dst_kernel : act ring -> m = ~AND_k act(d-k) -> erode(m) -> dst = act & erode(m)
-//                -> u8 mask, on-pixel count, on-pixel list
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned maj3(unsigned a, unsigned b, unsigned c) { return (a & b) | (c & (a | b)); }
-
-struct RowH {  // horizontal 3-sums of one bit row: s = parity, c = carry (l + w + r = s + 2c)
-    unsigned s, c;
-};
-
-__global__ void __launch_bounds__(SP_WARPS * 32)
-act_kernel(const uint32_t *__restrict__ bits, int W, int H, int T, int rows, int strips, int bands,
-           ActRing ring, long long dy0) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = blockIdx.x * SP_WARPS + warp;
-    const int t = blockIdx.y;
-    if (tile >= strips * bands) return;
-    const int strip = tile % strips, band = tile / strips;
-    const int Wb = W >> 5;
-    const int wx = strip * SP_USE - 1 + lane;
-    const bool lane_in = wx >= 0 && wx < Wb;
-    const bool lane_out = lane_in && lane >= 1 && lane <= SP_USE;
-    const int y0 = band * rows;
-    const unsigned FULL = 0xffffffffu;
-    const uint32_t *fb = bits + (size_t)t * H * Wb + (lane_in ? wx : 0);
-    uint32_t *ob = ring.frame(dy0 + t) + (lane_in ? wx : 0);
-    RowH h0 = {0, 0}, h1 = {0, 0};
-    unsigned hd0 = 0, hd1 = 0, he0 = FULL, he1 = FULL;
-    // rows y0-3 .. y0+rows+2 of b are needed; SP_MLP rows are loaded at a time so that every warp keeps
-    // several independent 128-byte requests in flight (the pass is DRAM-latency-bound otherwise)
-    const int y_first = y0 - 3, y_last = y0 + rows + 3;
-    for (int yb = y_first; yb < y_last; yb += SP_MLP) {
-    unsigned rowbuf[SP_MLP];
-    {   // the row pointer advances only inside the image: rows outside repeat the edge row (medianBlur)
-        const uint32_t *pr = fb + (unsigned)min(max(yb, 0), H - 1) * (unsigned)Wb;
-#pragma unroll
-        for (int u = 0; u < SP_MLP; u++) {
-            rowbuf[u] = __ldg(pr);
-            if ((unsigned)(yb + u) < (unsigned)(H - 1)) pr += Wb;
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < SP_MLP; u++) {
-        const int yy = yb + u;
-        if (yy >= y_last) break;
-        const unsigned bw = lane_in ? rowbuf[u] : 0u;
-        // ---- horizontal sums of b row yy (rows/cols replicated outside the image: medianBlur) --
-        unsigned Lw = __shfl_up_sync(FULL, bw, 1), Rw = __shfl_down_sync(FULL, bw, 1);
-        if (wx == 0) Lw = (bw & 1u) << 31;
-        if (wx == Wb - 1) Rw = bw >> 31;
-        const unsigned l = (bw << 1) | (Lw >> 31), r = (bw >> 1) | (Rw << 31);
-        RowH h2;
-        h2.s = l ^ bw ^ r;
-        h2.c = maj3(l, bw, r);
-        // ---- bin row yy-1 = at least 5 of the 9 bits ----------------------------------------
-        unsigned bin = 0;
-        {
-            const int y = yy - 1;
-            if (lane_in && y >= 0 && y < H) {
-                const unsigned ones = h0.s ^ h1.s ^ h2.s, c1 = maj3(h0.s, h1.s, h2.s);
-                const unsigned twos = h0.c ^ h1.c ^ h2.c, c2 = maj3(h0.c, h1.c, h2.c);
-                const unsigned t0b = c1 ^ twos, t1b = c1 & twos;  // weights 2 and 4
-                bin = (t1b & c2) | ((t1b ^ c2) & (t0b | ones));
-            }
-        }
-        h0 = h1; h1 = h2;
-        // ---- dil row yy-2 (outside the image: ones, ignored by the erosion) -------------------
-        unsigned dil;
-        {
-            const unsigned Lb = __shfl_up_sync(FULL, bin, 1), Rb = __shfl_down_sync(FULL, bin, 1);
-            const unsigned hd2 = bin | (bin << 1) | (Lb >> 31) | (bin >> 1) | (Rb << 31);
-            const int y = yy - 2;
-            dil = (lane_in && y >= 0 && y < H) ? (hd0 | hd1 | hd2) : FULL;
-            hd0 = hd1; hd1 = hd2;
-        }
-        // ---- act row yy-3 = erosion of dil ---------------------------------------------------
-        {
-            const unsigned Ld = __shfl_up_sync(FULL, dil, 1), Rd = __shfl_down_sync(FULL, dil, 1);
-            const unsigned he2 = dil & ((dil << 1) | (Ld >> 31)) & ((dil >> 1) | (Rd << 31));
-            const int y = yy - 3;
-            if (lane_out && y >= y0 && y < y0 + rows && y < H) ob[(size_t)y * Wb] = he0 & he1 & he2;
-            he0 = he1; he1 = he2;
-        }
-    }
-    }
-}
-
-__device__ __forceinline__ unsigned nib_to_bytes(unsigned nib) {
-    return ((nib & 1u) ? 0xffu : 0u) | ((nib & 2u) ? 0xff00u : 0u) | ((nib & 4u) ? 0xff0000u : 0u) |
-           ((nib & 8u) ? 0xff000000u : 0u);
-}
-
-__global__ void __launch_bounds__(SP_WARPS * 32)
-dst_kernel(ActRing ring, int W, int H, int T, int n, long long dy0, int dy_on, int rows, int strips,
-           int bands, uint8_t *__restrict__ dst, uint32_t *__restrict__ dstbits,
-           unsigned *__restrict__ npoints, uint32_t *__restrict__ points, int cap, int exp) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = blockIdx.x * SP_WARPS + warp;
-    const int t = blockIdx.y;
-    if (tile >= strips * bands) return;
-    const int strip = tile % strips, band = tile / strips;
-    const int Wb = W >> 5;
-    const int wx = strip * SP_USE - 1 + lane;
-    const bool lane_in = wx >= 0 && wx < Wb;
-    const bool lane_out = lane_in && lane >= 1 && lane <= SP_USE;
-    const int y0 = band * rows;
-    const unsigned FULL = 0xffffffffu;
-    const long long d = dy0 + t;
-    const int L = (int)((d + 1) < n ? (d + 1) : n);  // SlidingWindow.length of the dy window
-    const uint32_t *cur = ring.frame(d) + (lane_in ? wx : 0);
-    unsigned hm0 = FULL, hm1 = FULL, act_prev = 0;
-    const int ylast = dy_on ? y0 + rows + 1 : y0 + rows;
-    const int yfirst = dy_on ? y0 - 1 : y0;
-    const int ylag = dy_on ? 1 : 0;  // the output row trails the input row by this much
-    const uint32_t *dbase = dstbits + (size_t)t * H * Wb + (lane_in ? wx : 0);
-    const unsigned lmask = lane_in ? FULL : 0u, omask = lane_out ? FULL : 0u;
-    for (int yb = yfirst; yb < ylast; yb += SP_MLP) {
-    unsigned actbuf[SP_MLP], prevbuf[SP_MLP];
-    {   // row pointers advance by one row only inside the image (rows outside repeat the edge row: always a
-        // valid address, no predicated loads, no per-load index arithmetic)
-        const uint32_t *pa = cur + (unsigned)min(max(yb, 0), H - 1) * (unsigned)Wb;
-        const uint32_t *pd = dbase + (unsigned)min(max(yb - ylag, 0), H - 1) * (unsigned)Wb;
-#pragma unroll
-        for (int u = 0; u < SP_MLP; u++) {
-            const int yy = yb + u;
-            actbuf[u] = __ldg(pa);
-            prevbuf[u] = *pd;
-            if ((unsigned)yy < (unsigned)(H - 1)) pa += Wb;
-            if ((unsigned)(yy - ylag) < (unsigned)(H - 1)) pd += Wb;
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < SP_MLP; u++) {
-        const int yy = yb + u;
-        if (yy >= ylast) break;
-        const int yo_u = yy - ylag;
-        const unsigned act = ((unsigned)yy < (unsigned)H) ? (actbuf[u] & lmask) : 0u;
-        const unsigned prev_u = ((unsigned)(yo_u - y0) < (unsigned)rows && yo_u < H) ? (prevbuf[u] & omask) : 0u;
-        // almost every 960-pixel row segment is empty now, was empty one row ago, and holds zeros in
-        // the mask buffer: nothing to compute or to write (m = all ones, so the eroded m is too)
-        if (!__any_sync(FULL, (act | act_prev | prev_u) != 0u)) {
-            hm0 = hm1;
-            hm1 = FULL;
-            act_prev = 0;
-            continue;
-        }
-        unsigned out_bits;
-        int yo;
-        if (dy_on) {
-            // m = not(on in all of the last L frames); the loop ends as soon as the AND is empty
-            unsigned acc = act;
-            for (int k = 1; k < L && acc; k++) acc &= __ldg(ring.frame(d - k) + wx + (size_t)yy * Wb);
-            const unsigned m = ~acc;  // rows / columns outside the image: act = 0 -> m = ones
-            const unsigned Lm = __shfl_up_sync(FULL, m, 1), Rm = __shfl_down_sync(FULL, m, 1);
-            const unsigned hm2 = m & ((m << 1) | (Lm >> 31)) & ((m >> 1) | (Rm << 31));
-            out_bits = act_prev & hm0 & hm1 & hm2;  // row yy-1
-            hm0 = hm1; hm1 = hm2;
-            act_prev = act;
-            yo = yy - 1;
-        } else {
-            out_bits = act;
-            yo = yy;
-        }
-        if (yo >= y0 && yo < y0 + rows && yo < H && lane_out) {
-            // The u8 mask buffer is persistent and almost everywhere zero, and HBM write-only bandwidth
-            // is the scarcest resource of this pass: `dstbits` remembers what the buffer holds (1 bit per
-            // pixel), so only 32-pixel words that are or were non-zero are rewritten.
-            uint32_t *pb = dstbits + ((size_t)t * H + yo) * Wb + wx;
-            const unsigned prev = prev_u;
-            if (prev | out_bits) {
-                uint4 a = make_uint4(nib_to_bytes(out_bits & 15u), nib_to_bytes((out_bits >> 4) & 15u),
-                                     nib_to_bytes((out_bits >> 8) & 15u), nib_to_bytes((out_bits >> 12) & 15u));
-                uint4 b = make_uint4(nib_to_bytes((out_bits >> 16) & 15u), nib_to_bytes((out_bits >> 20) & 15u),
-                                     nib_to_bytes((out_bits >> 24) & 15u), nib_to_bytes(out_bits >> 28));
-                uint4 *o = reinterpret_cast<uint4 *>(dst + (size_t)t * W * H + (size_t)yo * W + (size_t)wx * 32);
-                o[0] = a;
-                o[1] = b;
-                if (prev != out_bits) *pb = out_bits;
-                if (out_bits) {
-                    const unsigned c = __popc(out_bits);
-                    unsigned slot = atomicAdd(npoints + t, c);
-                    unsigned ob = out_bits;
-                    while (ob) {
-                        const int bpos = __ffs(ob) - 1;
-                        ob &= ob - 1;
-                        if (slot < (unsigned)cap)
-                            points[(size_t)t * cap + slot] = ((unsigned)yo << 16) | (unsigned)(wx * 32 + bpos);
-                        slot++;
-                    }
-                }
-            }
-        }
-    }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 static inline void stream_state_free(StreamState &s) {
     if (s.d_bits) cudaFree(s.d_bits);
     s.d_bits = nullptr;
@@ -493,18 +291,18 @@ static inline int stream_state_init(StreamState &s, int W, int H, int n, int dev
 static inline bool stream_kernel_supported(const StreamState &s, int T) { return s.ok && T >= 1 && T <= s.max_batch; }
 
 // Launches temporal + act (stream st1) and dst (stream st2, after `ev_act`) for frames
-// timer0 .. timer0+T-1 (dy indices dy0 ..).  The split lets the write-only dst pass (HBM write
-// bandwidth alone tops out near 60 % of the copy peak) overlap the read-only, ALU-heavy temporal pass
-// of the NEXT batch.  Returns 0 / -1; *launches gets the number of kernel launches.
+// timer0 .. timer0+T-1 (dy indices dy0 ..).  The split lets the sparse dst pass overlap the
+// temporal pass of the NEXT batch.  Returns 0 / -1; *launches gets the number of kernel launches.
 static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long timer0, long long dy0, int T,
                                        int dy_on, const int *d_thr, ActRing ring, uint8_t *dst, uint32_t *dstbits,
-                                       unsigned *npoints, uint32_t *points, int cap, cudaStream_t st1,
+                                       unsigned *npoints, uint32_t *points, int cap, SparseLists sl, cudaStream_t st1,
                                        cudaStream_t st2, cudaEvent_t ev_f1, cudaEvent_t ev_d0, int *launches) {
     const int HWG = (int)((size_t)s.W * s.H / (4 * s.t_wpt));  // pixel groups = threads
     const int nt = s.t_threads;
     const size_t smem = s.t_smem_per_thread * nt + ((T + 15) & ~15);
     const int grid = (HWG + nt - 1) / nt;
     uint8_t *bits8 = reinterpret_cast<uint8_t *>(s.d_bits);
+    if (cudaMemsetAsync(sl.acount, 0, (size_t)T * sizeof(unsigned), st1) != cudaSuccess) return -1;
     if (s.t_wpt == 2) {
         if (src.mask) temporal_kernel<true, 2><<<grid, nt, smem, st1>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
         else temporal_kernel<false, 2><<<grid, nt, smem, st1>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
@@ -514,19 +312,32 @@ static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long t
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
     const int Wb = s.W / 32;
-    const int strips = (Wb + SP_USE - 1) / SP_USE, bands = (s.H + s.sp_rows - 1) / s.sp_rows;
-    const int tiles = strips * bands;
-    dim3 g((tiles + SP_WARPS - 1) / SP_WARPS, T);
-    act_kernel<<<g, SP_WARPS * 32, 0, st1>>>(s.d_bits, s.W, s.H, T, s.sp_rows, strips, bands, ring, dy0);
+    const int strips = (Wb + SP_USE - 1) / SP_USE;
+    if (Wb % 4 == 0 && !s.force_strip) {
+        const int chunks = Wb / 4, bands = (s.H + s.sp_rows - 1) / s.sp_rows;
+        dim3 g((chunks * bands + A4_THREADS - 1) / A4_THREADS, T);
+        act4_kernel<<<g, A4_THREADS, 0, st1>>>(s.d_bits, s.H, Wb, s.sp_rows, chunks, bands, ring, dy0, sl);
+    } else {
+        const int bands = (s.H + s.sp_rows - 1) / s.sp_rows;
+        dim3 g((strips * bands + SP_WARPS - 1) / SP_WARPS, T);
+        act_kernel<<<g, SP_WARPS * 32, 0, st1>>>(s.d_bits, s.W, s.H, T, s.sp_rows, strips, bands, ring, dy0, sl);
+    }
     if (cudaGetLastError() != cudaSuccess) return -1;
     if (cudaEventRecord(ev_f1, st1) != cudaSuccess) return -1;
     if (cudaStreamWaitEvent(st2, ev_f1, 0) != cudaSuccess) return -1;
     if (cudaEventRecord(ev_d0, st2) != cudaSuccess) return -1;
-    const int dbands = (s.H + s.dst_rows - 1) / s.dst_rows;
-    dim3 gd((strips * dbands + SP_WARPS - 1) / SP_WARPS, T);
-    dst_kernel<<<gd, SP_WARPS * 32, 0, st2>>>(ring, s.W, s.H, T, s.n, dy0, dy_on, s.dst_rows, strips, dbands, dst,
-                                              dstbits, npoints, points, cap, s.dst_exp);
+    if (cudaMemsetAsync(sl.dense, 0, sizeof(unsigned), st2) != cudaSuccess) return -1;
+    if (s.force_dense) {  // test hook: every frame takes the full-scan path
+        dst_force_dense_kernel<<<(T + 127) / 128, 128, 0, st2>>>(T, sl);
+    } else {
+        dst_sparse_kernel<<<T, 256, 0, st2>>>(ring, s.W, s.H, s.n, dy0, dy_on, dst, dstbits, npoints, points, cap, sl);
+    }
     if (cudaGetLastError() != cudaSuccess) return -1;
-    *launches = 3;
+    const int dbands = (s.H + s.dst_rows - 1) / s.dst_rows;
+    dim3 gd((strips * dbands + SP_WARPS - 1) / SP_WARPS, std::min(T, DENSE_GY));
+    dst_dense_kernel<<<gd, SP_WARPS * 32, 0, st2>>>(ring, s.W, s.H, s.n, dy0, dy_on, s.dst_rows, strips, dbands, dst,
+                                                    dstbits, npoints, points, cap, sl);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    *launches = 4;
     return 0;
 }

@@ -459,7 +459,7 @@ class M3Detector(LineDetector):
 
     def submit(self, ptr: int, T: int, on_device: bool):
         """Asynchronous half of detect_many (mdb_submit_batch): enqueues the copy (host input) and all
-        kernels of one batch and returns.  Up to two batches may be in flight, so the host->device
+        kernels of one batch and returns.  Up to three batches may be in flight, so the host->device
         copy of the next batch overlaps the kernels of this one.  Host buffers should be pinned and
         must stay untouched until the matching collect(); device buffers likewise."""
         check(self._eng.lib.mdb_submit_batch(self._eng.handle, ptr, T, int(on_device)), "submit")

@@ -65,10 +65,16 @@ def make_stream(T: int, W: int, H: int, FPS: float, seed: int = 1234, t0: int = 
     return out
 
 
-def make_stream_device(T: int, W: int, H: int, FPS: float, device, seed: int = 1234, t0: int = 0):
+def make_stream_device(T: int, W: int, H: int, FPS: float, device, seed: int = 1234, t0: int = 0,
+                       loop: int = 0, quiet: int = 0):
     """Same distribution as make_stream, produced on the GPU with torch (Philox noise) for
     throughput runs where host generation of 4K/8K streams would dominate (SURVEY App. E allows this;
-    parity runs use the host generator). Returns a (T,H,W) uint8 CUDA tensor."""
+    parity runs use the host generator). Returns a (T,H,W) uint8 CUDA tensor.
+
+    loop > 0 makes the stream cyclic with period `loop` frames (a benchmark replays a few resident
+    batches): a streak that would still be inside the detector's window (`quiet` frames) when the
+    stream jumps back to frame 0 is left out, so the replayed stream never shows two streaks in one
+    window -- which the continuous stream (one streak every 2 s, 0.5 s long) cannot do either."""
     import torch
     sky = torch.from_numpy(make_sky(W, H, seed)).to(device)
     out = torch.empty((T, H, W), dtype=torch.uint8, device=device)
@@ -78,7 +84,10 @@ def make_stream_device(T: int, W: int, H: int, FPS: float, device, seed: int = 1
         t = t0 + i
         g.manual_seed(seed * 1000003 + t)
         f = sky + torch.randn((H, W), generator=g, device=device, dtype=torch.float32) * 2.0
-        k, ph = t // period, t % period
+        tm = t % loop if loop > 0 else t
+        k, ph = tm // period, tm % period
+        if loop > 0 and k * period + dur + quiet > loop:
+            ph = dur  # this streak would straddle the wrap: not drawn
         if ph < dur:
             rr = np.random.default_rng([seed, 10**6 + k])
             x0 = rr.uniform(0.2, 0.8) * W

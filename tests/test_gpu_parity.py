@@ -57,26 +57,54 @@ def test_per_frame_api_matches_reference_golden(name):
     det.close()
 
 
-@pytest.mark.parametrize("stream_kernel", [0, 1])
+@pytest.mark.parametrize("mode", ["generic", "stream", "stream_dense_dst", "stream_strip_act"])
 @pytest.mark.parametrize("batch", [1, 7, 32])
 @pytest.mark.parametrize("name", DET_CASES)
-def test_batched_api_matches_reference_golden(name, batch, stream_kernel):
+def test_batched_api_matches_reference_golden(name, batch, mode):
+    """generic = one fused launch per frame; stream = temporal + act4/act + sparse dst; the two extra
+    modes force the full-scan dst kernel (list-overflow path) and the warp-strip act kernel."""
     from metdetpy_b200.detector import M3Detector
     g = load_det_case(name)
     det = M3Detector(g["n"] / g["fps"] + 1e-9, g["fps"], g["mask"], 10, _cfg(g["cfg"]), None,
                      max_batch=batch)
+    stream_kernel = int(mode != "generic")
     det._eng.set_option("stream_kernel", stream_kernel)
+    det._eng.set_option("force_dense", int(mode == "stream_dense_dst"))
+    det._eng.set_option("force_strip", int(mode == "stream_strip_act"))
     T = len(g["frames"])
     W = g["frames"].shape[2]
     for s in range(0, T, batch):
         res, dst = det.detect_many(g["frames"][s:s + batch], return_dst=True)
         nb = len(res)
         streamed = stream_kernel and W % 32 == 0 and 2 <= g["n"] <= 128
-        assert det._eng.fused_time()[1] == (3 if streamed else nb)  # temporal+spatial vs one launch per frame
+        assert det._eng.fused_time()[1] == (4 if streamed else nb)  # temporal+act+dst(sparse,dense) vs one launch per frame
         for i, (lines, cls) in enumerate(res):
             _check_frame(det, g, s + i, lines, cls, dst[i], det.last_infos[i])
             raw = ragged_get(g["raw_lines"], g["raw_offs"], s + i)
             assert np.array_equal(det.last_raw[i].reshape(-1, 4), raw), s + i
+    det.close()
+
+
+@pytest.mark.parametrize("name", ["synth_384x216_n12_dyon_mask", "synth_256x160_n6_fixed3_dense"])
+def test_sparse_and_dense_dst_kernels_share_the_mask_buffer(name):
+    """The persistent u8 mask buffer, its 1-bit shadow and the non-zero word list must stay consistent
+    when batches alternate between the list-driven dst kernel, the full-scan one and the generic
+    per-frame kernel, with batch sizes that change (slots reused after being skipped)."""
+    from metdetpy_b200.detector import M3Detector
+    g = load_det_case(name)
+    det = M3Detector(g["n"] / g["fps"] + 1e-9, g["fps"], g["mask"], 10, _cfg(g["cfg"]), None, max_batch=9)
+    T = len(g["frames"])
+    s, k = 0, 0
+    sizes = [9, 4, 9, 1, 7, 9, 2]
+    while s < T:
+        b = min(sizes[k % len(sizes)], T - s)
+        det._eng.set_option("force_dense", int(k % 3 == 1))
+        det._eng.set_option("stream_kernel", int(k % 5 != 3))
+        res, dst = det.detect_many(g["frames"][s:s + b], return_dst=True)
+        for i, (lines, cls) in enumerate(res):
+            _check_frame(det, g, s + i, lines, cls, dst[i], det.last_infos[i])
+        s += b
+        k += 1
     det.close()
 
 
