@@ -855,6 +855,7 @@ extern "C" int mdb_set_option(mdb_handle h, const char *name, int value) {
         h->timeline = value;
         return MDB_OK;
     }
+    if (!strcmp(name, "temporal_version")) { h->sk.t_version = value == 1 ? 1 : 2; return MDB_OK; }
     if (!strcmp(name, "force_dense")) { h->sk.force_dense = value; return MDB_OK; }
     if (!strcmp(name, "force_strip")) { h->sk.force_strip = value; return MDB_OK; }
     if (!strcmp(name, "sp_rows")) { h->sk.sp_rows = value; return MDB_OK; }

@@ -20,6 +20,7 @@
 #pragma once
 #include "common.cuh"
 #include "spatial_kernel.cuh"
+#include "temporal_kernel.cuh"
 
 #define ST_K 8          // frames in flight per thread (cp.async groups)
 
@@ -28,6 +29,7 @@ struct StreamState {
     int W = 0, H = 0, n = 0, max_batch = 0, device = 0;
     int t_threads = 32;     // CTA size of the temporal kernel
     int t_wpt = 2;          // 32-bit words (4 px) per thread in the temporal kernel
+    int t_version = 2;      // 2: temporal2_kernel (temporal_kernel.cuh); 1: the first-generation kernel below
     int dst_rows = 32;      // output rows per warp strip in dst_dense_kernel
     int force_dense = 0;    // test hook: dst of every frame by the full-scan kernel
     int force_strip = 0;    // test hook: act by the warp-strip kernel even when W % 128 == 0
@@ -283,6 +285,11 @@ static inline int stream_state_init(StreamState &s, int W, int H, int n, int dev
         return -1;
     ST_SETATTR((temporal_kernel<false, 2>)) ST_SETATTR((temporal_kernel<true, 2>))
     ST_SETATTR((temporal_kernel<false, 4>)) ST_SETATTR((temporal_kernel<true, 4>))
+#define ST_SETATTR2(NT)                                                                            \
+    ST_SETATTR((temporal2_kernel<false, 2, NT>)) ST_SETATTR((temporal2_kernel<true, 2, NT>))      \
+    ST_SETATTR((temporal2_kernel<false, 4, NT>)) ST_SETATTR((temporal2_kernel<true, 4, NT>))
+    ST_SETATTR2(32) ST_SETATTR2(64) ST_SETATTR2(128)
+#undef ST_SETATTR2
 #undef ST_SETATTR
     s.ok = 1;
     return 0;
@@ -303,7 +310,19 @@ static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long t
     const int grid = (HWG + nt - 1) / nt;
     uint8_t *bits8 = reinterpret_cast<uint8_t *>(s.d_bits);
     if (cudaMemsetAsync(sl.acount, 0, (size_t)T * sizeof(unsigned), st1) != cudaSuccess) return -1;
-    if (s.t_wpt == 2) {
+    if (s.t_version == 2) {
+#define T2_LAUNCH(M, WP, NT) temporal2_kernel<M, WP, NT><<<grid, NT, smem, st1>>>(src, timer0, T, s.n, HWG, d_thr, bits8)
+#define T2_NT(M, WP)                                              \
+    do {                                                          \
+        if (nt == 32) T2_LAUNCH(M, WP, 32);                       \
+        else if (nt == 64) T2_LAUNCH(M, WP, 64);                  \
+        else T2_LAUNCH(M, WP, 128);                               \
+    } while (0)
+        if (s.t_wpt == 2) { if (src.mask) T2_NT(true, 2); else T2_NT(false, 2); }
+        else { if (src.mask) T2_NT(true, 4); else T2_NT(false, 4); }
+#undef T2_NT
+#undef T2_LAUNCH
+    } else if (s.t_wpt == 2) {
         if (src.mask) temporal_kernel<true, 2><<<grid, nt, smem, st1>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
         else temporal_kernel<false, 2><<<grid, nt, smem, st1>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
     } else {

@@ -1,0 +1,254 @@
+// temporal2_kernel: stack -> diff -> threshold fused (SlidingWindow.max / .mean, utils.py:269-307;
+// M3Detector.detect, Detector.py:327-332), one predicate bit per pixel, every frame read once.
+//
+// Same algorithm as temporal_kernel (stream_kernel.cuh) -- per-thread shared-memory ring fed by
+// cp.async, van Herk / Gil-Werman sliding max, running window sums, integer predicate
+// max*L - sum > thr*L -- restructured for the instruction issue limit, which is what bounds this
+// pass on sm_100a (the ALU pipe issues one warp instruction every two cycles per SM sub-partition):
+//
+//   * "high-byte form": VIMNMX.U16x2 compares 16-bit lanes, and the high byte of a lane decides, so
+//     the max chain of the ODD pixels runs on the packed u8x4 words as they are, and the EVEN pixels'
+//     chain on  x << 8  (one IMAD on the FMA pipe).  Low bytes carry garbage that never reaches a
+//     high byte.  No unpacking of the new frame or of the suffix-max words; one PRMT per lane pair
+//     extracts the clean window max at the end.
+//   * window sums: W = sum of the raw packed words (mod 2^32) and O = sum of the odd pixels (u16x2);
+//     the even sums are W - 256*O (one IMAD).  Only the odd lanes of new / evicted words are unpacked.
+//   * the frame loop is cut into runs inside which no ring pointer wraps, L is constant and the
+//     prefetch predicate does not change, so a frame costs no pointer selects or compares; shared
+//     memory slots are addressed with immediate offsets (CTA size is a template parameter).
+#pragma once
+#include "common.cuh"
+
+#define T2_K 8  // frames in flight per thread (cp.async groups)
+
+__device__ __forceinline__ void t2_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void t2_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ unsigned t2_prmt(unsigned a, unsigned b, unsigned sel) {
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// bytes 1 and 3 of x as clean u16x2 lanes
+__device__ __forceinline__ unsigned t2_hi(unsigned x) { return t2_prmt(x, 0u, 0x4341u); }
+
+template <int WPT>
+__device__ __forceinline__ void t2_cp(uint32_t saddr, const void *g) {
+    if (WPT == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
+}
+template <int WPT>
+__device__ __forceinline__ void t2_lds(unsigned (&w)[WPT], uint32_t saddr) {
+    if (WPT == 4) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2 % WPT]), "=r"(w[3 % WPT]) : "r"(saddr));
+    else asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(saddr));
+}
+template <int WPT>
+__device__ __forceinline__ void t2_sts(uint32_t saddr, const unsigned (&w)[WPT]) {
+    if (WPT == 4) asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(w[0]), "r"(w[1]), "r"(w[2 % WPT]), "r"(w[3 % WPT]) : "memory");
+    else asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(saddr), "r"(w[0]), "r"(w[1]) : "memory");
+}
+
+// per-thread running state of the window
+template <int WPT>
+struct T2State {
+    unsigned pO[WPT], pE[WPT];  // prefix max of the current block, high-byte form (odd / even pixels)
+    unsigned Wd[WPT];           // sum of the raw words of the window, mod 2^32
+    unsigned Od[WPT];           // sum of the odd pixels of the window, u16x2
+};
+
+// One frame.  ac / ao / asx: shared addresses of the frame's slot, of frame t-n's slot (which then
+// receives the prefetch), of the suffix-max word for this position.  Lu = window length, cpk = per-lane
+// bias (0x7fff - thr*L) * 0x10001.
+template <bool MASKED, int WPT>
+__device__ __forceinline__ void t2_step(T2State<WPT> &st, const unsigned (&mk)[WPT], uint32_t ac, uint32_t ao,
+                                        uint32_t asx, bool pf, const uint8_t *gp, unsigned Lu, unsigned cpk,
+                                        uint8_t *bp) {
+    t2_wait<T2_K - 1>();  // this thread's copy of the frame has landed
+    unsigned xw[WPT], ow[WPT], mw[WPT];
+    t2_lds<WPT>(xw, ac);
+    t2_lds<WPT>(ow, ao);
+    t2_lds<WPT>(mw, asx);
+    if (MASKED) {
+#pragma unroll
+        for (int k = 0; k < WPT; k++) xw[k] &= mk[k];
+        t2_sts<WPT>(ac, xw);
+    }
+    if (pf) t2_cp<WPT>(ao, gp);  // slot of frame t-n is free now: fetch frame t+K into it
+    t2_commit();
+    unsigned M[WPT];
+#pragma unroll
+    for (int k = 0; k < WPT; k++) {
+        const unsigned x = xw[k], x8 = x << 8, m = mw[k], m8 = m << 8;
+        st.pO[k] = __vmaxu2(st.pO[k], x);
+        st.pE[k] = __vmaxu2(st.pE[k], x8);
+        const unsigned wO = t2_hi(__vmaxu2(st.pO[k], m));   // window max, odd pixels, clean u16x2
+        const unsigned wE = t2_hi(__vmaxu2(st.pE[k], m8));  // ... even pixels
+        st.Wd[k] = st.Wd[k] + x - ow[k];
+        st.Od[k] = st.Od[k] + t2_hi(x) - t2_hi(ow[k]);
+        const unsigned sE = st.Wd[k] - (st.Od[k] << 8);
+        // per lane: max*L - sum + 0x7fff - thr*L ; bit 15 set <=> max*L - sum > thr*L
+        const unsigned vO = wO * Lu + cpk - st.Od[k];
+        const unsigned vE = wE * Lu + cpk - sE;
+        M[k] = t2_prmt(vE, vO, 0xFBD9u);  // sign-replicate bytes 1,5,3,7 -> 0x00/0xff per pixel
+    }
+    const unsigned q01 = (M[0] & 0x08040201u) | (M[1] & 0x80402010u);
+    const unsigned r01 = q01 * 0x01010101u;
+    if (WPT == 4) {
+        const unsigned q23 = (M[2 % WPT] & 0x08040201u) | (M[3 % WPT] & 0x80402010u);
+        const unsigned r23 = q23 * 0x01010101u;
+        *reinterpret_cast<uint16_t *>(bp) = (uint16_t)t2_prmt(r01, r23, 0x4473u);
+    } else {
+        *bp = (uint8_t)(r01 >> 24);
+    }
+}
+
+// Backward scan over `cnt` raw frames ending at slot a (descending slots, no wrap inside): suffix max
+// by position, stored packed at so, so - S, ...
+template <int WPT, uint32_t S>
+__device__ __forceinline__ void t2_scan_run(unsigned (&aO)[WPT], unsigned (&aE)[WPT], uint32_t a, uint32_t so,
+                                            int cnt) {
+#pragma unroll 2
+    for (int u = 0; u < cnt; u++) {
+        unsigned w[WPT], o[WPT];
+        t2_lds<WPT>(w, a);
+#pragma unroll
+        for (int k = 0; k < WPT; k++) {
+            aO[k] = __vmaxu2(aO[k], w[k]);
+            aE[k] = __vmaxu2(aE[k], w[k] << 8);
+            o[k] = t2_prmt(aE[k], aO[k], 0x7351u);  // high bytes: E0 O0 E1 O1 = pixel order
+        }
+        t2_sts<WPT>(so, o);
+        a -= S;
+        so -= S;
+    }
+}
+
+template <bool MASKED, int WPT, int NT>
+__global__ void __launch_bounds__(NT)
+temporal2_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *__restrict__ thr,
+                 uint8_t *__restrict__ bits) {
+    constexpr int VB = WPT * 4;           // bytes (= pixels) per thread per frame
+    constexpr uint32_t S = NT * VB;       // bytes between consecutive slots
+    extern __shared__ uint4 t_smem[];
+    const int tid = threadIdx.x;
+    const int R = n + T2_K;
+    // shared memory: ring [R][NT] raw frames, smx [n][NT] suffix max of the previous block by position
+    // (slot p-1 = position p; slot n-1 stays zero), thr_s [T]
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(t_smem);
+    const uint32_t ring_s = smem0 + tid * VB;
+    const uint32_t smx_s = ring_s + R * S;
+    uint8_t *thr_s = reinterpret_cast<uint8_t *>(t_smem) + (size_t)(R + n) * S;
+    for (int i = tid; i < T; i += NT) thr_s[i] = (uint8_t)min(max(thr[i], 0), 255);
+    __syncthreads();
+    const int g = blockIdx.x * NT + tid;
+    if (g >= HWG) return;
+    const uint8_t *gbase = (src.cur ? src.cur : src.ring) + (size_t)g * VB;
+    const int Rw = src.cur ? 0x7fffffff : src.R;  // the caller's buffer does not wrap
+    const unsigned HWu = (unsigned)src.HW;
+
+    unsigned mk[WPT], zero[WPT];
+#pragma unroll
+    for (int k = 0; k < WPT; k++) { mk[k] = ~0u; zero[k] = 0u; }
+    if (MASKED) {
+        const unsigned *m = reinterpret_cast<const unsigned *>(src.mask + (size_t)g * VB);
+#pragma unroll
+        for (int k = 0; k < WPT; k++) mk[k] = m[k] * 0xffu;  // {0,1} -> {0x00,0xff}
+    }
+
+    // ---- history: frames t0-n+1 .. t0-1 -> slots 0 .. n-2 ; slot R-1 = zeros ("frame t0-n") ----
+    t2_sts<WPT>(ring_s + (R - 1) * S, zero);
+    for (int p = 1; p < n; p++) {
+        const long long th = t0 - n + p;
+        if (th >= 0) t2_cp<WPT>(ring_s + (p - 1) * S, src.frame(th) + (size_t)g * VB);
+        else t2_sts<WPT>(ring_s + (p - 1) * S, zero);
+    }
+    t2_commit();
+    // ---- prime the pipeline: frames 0 .. K-1 of the batch -> slots n-1 .. n+K-2 -------------------
+    int pf_slot = src.cur ? (int)(t0 - src.t0) : (int)(t0 % src.R);  // source slot of the next frame to fetch
+    for (int i = 0; i < T2_K; i++) {
+        if (i < T) t2_cp<WPT>(ring_s + (n - 1 + i) * S, gbase + (size_t)pf_slot * HWu);
+        t2_commit();
+        if (++pf_slot == Rw) pf_slot = 0;
+    }
+    t2_wait<T2_K>();  // history landed
+
+    T2State<WPT> st;
+    {
+        unsigned aO[WPT], aE[WPT];
+#pragma unroll
+        for (int k = 0; k < WPT; k++) st.Wd[k] = st.Od[k] = aO[k] = aE[k] = 0u;
+        for (int p = n - 1; p >= 1; p--) {
+            unsigned w[WPT], o[WPT];
+            t2_lds<WPT>(w, ring_s + (p - 1) * S);
+            if (MASKED) {
+#pragma unroll
+                for (int k = 0; k < WPT; k++) w[k] &= mk[k];
+                t2_sts<WPT>(ring_s + (p - 1) * S, w);
+            }
+#pragma unroll
+            for (int k = 0; k < WPT; k++) {
+                st.Wd[k] += w[k];
+                st.Od[k] += t2_hi(w[k]);
+                aO[k] = __vmaxu2(aO[k], w[k]);
+                aE[k] = __vmaxu2(aE[k], w[k] << 8);
+                o[k] = t2_prmt(aE[k], aO[k], 0x7351u);
+            }
+            t2_sts<WPT>(smx_s + (p - 1) * S, o);
+        }
+    }
+    t2_sts<WPT>(smx_s + (n - 1) * S, zero);
+
+    const size_t bstride = (size_t)HWG * WPT / 2;          // WPT*4 bits per thread and frame
+    uint8_t *bout = bits + (size_t)g * WPT / 2;
+    int c = n - 1;   // ring slot of the current frame
+    int o = R - 1;   // ring slot of frame t-n (then: destination of the prefetch of frame t+K)
+    int i = 0;
+    while (i < T) {
+        const int nb = min(n, T - i);  // frames of this block
+#pragma unroll
+        for (int k = 0; k < WPT; k++) st.pO[k] = st.pE[k] = 0u;  // 0 = identity of max
+        int j = 0;
+        while (j < nb) {
+            // a run: no ring pointer wraps, constant L, constant prefetch predicate
+            const long long tg = t0 + i;
+            const bool warm = tg + 1 < n;
+            const unsigned Lu = (unsigned)(warm ? tg + 1 : n);  // SlidingWindow.length
+            const bool pf = i + T2_K < T;
+            int run = min(min(nb - j, R - c), min(R - o, Rw - pf_slot));
+            if (pf) run = min(run, T - T2_K - i);
+            if (warm) run = 1;
+            uint32_t ac = ring_s + c * S, ao = ring_s + o * S, asx = smx_s + j * S;
+            const uint8_t *gp = gbase + (size_t)pf_slot * HWu;
+            uint8_t *bp = bout + (size_t)i * bstride;
+            const uint8_t *tp = thr_s + i;
+            const unsigned bias = 0x7fffu;
+#pragma unroll 2
+            for (int u = 0; u < run; u++) {
+                const unsigned cpk = (bias - (unsigned)tp[u] * Lu) * 0x00010001u;
+                t2_step<MASKED, WPT>(st, mk, ac, ao, asx, pf, gp, Lu, cpk, bp);
+                ac += S; ao += S; asx += S;
+                gp += HWu;
+                bp += bstride;
+            }
+            i += run; j += run;
+            c += run; if (c == R) c = 0;
+            o += run; if (o == R) o = 0;
+            pf_slot += run; if (pf_slot >= Rw) pf_slot = 0;
+        }
+        if (nb == n && i < T) {  // block complete and more frames follow: suffix max by position 1..n-1
+            unsigned aO[WPT], aE[WPT];
+#pragma unroll
+            for (int k = 0; k < WPT; k++) aO[k] = aE[k] = 0u;
+            int a = c == 0 ? R - 1 : c - 1;  // slot of the block's last frame
+            int p = n - 1;
+            while (p >= 1) {
+                const int cnt = min(p, a + 1);
+                t2_scan_run<WPT, S>(aO, aE, ring_s + a * S, smx_s + (p - 1) * S, cnt);
+                p -= cnt;
+                a -= cnt;
+                if (a < 0) a = R - 1;
+            }
+        }
+    }
+    t2_wait<0>();
+}
