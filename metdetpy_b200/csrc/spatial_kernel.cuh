@@ -77,26 +77,31 @@ act4_kernel(const uint32_t *__restrict__ bits, int H, int Wb, int rows, int chun
 #pragma unroll
     for (int i = 0; i < 4; i++) he0[i] = he1[i] = FULL;
     const int y_stop = yend + 3;  // rows y0-3 .. yend+2 of the predicate bits are consumed
-    for (int yb = y0 - 3; yb < y_stop; yb += A4_MLP) {
+    // rows are loaded A4_MLP at a time, one group ahead of the arithmetic (the pass is otherwise bound
+    // by DRAM latency: a warp alternates between waiting for its rows and ~100 ALU ops per row)
+    struct Rows {
         uint4 rb[A4_MLP];
         unsigned rl[A4_MLP], rr[A4_MLP];
-        {   // rows outside the image repeat the edge row (medianBlur replicates)
-            const uint32_t *pr = fb + (size_t)min(max(yb, 0), H - 1) * Wb;
+    };
+    auto load_rows = [&](Rows &r, int yb) {
+        // rows outside the image repeat the edge row (medianBlur replicates)
+        const uint32_t *pr = fb + (size_t)min(max(yb, 0), H - 1) * Wb;
 #pragma unroll
-            for (int u = 0; u < A4_MLP; u++) {
-                rb[u] = __ldg(reinterpret_cast<const uint4 *>(pr));
-                rl[u] = __ldg(pr + lo);
-                rr[u] = __ldg(pr + ro);
-                if ((unsigned)(yb + u) < (unsigned)(H - 1)) pr += Wb;
-            }
+        for (int u = 0; u < A4_MLP; u++) {
+            r.rb[u] = __ldg(reinterpret_cast<const uint4 *>(pr));
+            r.rl[u] = __ldg(pr + lo);
+            r.rr[u] = __ldg(pr + ro);
+            if ((unsigned)(yb + u) < (unsigned)(H - 1)) pr += Wb;
         }
+    };
+    auto process_rows = [&](const Rows &r, int yb) {
 #pragma unroll
         for (int u = 0; u < A4_MLP; u++) {
             const int yy = yb + u;  // rows past y_stop are computed too (loads are clamped, stores guarded)
             unsigned w[5];
-            w[0] = rb[u].x; w[1] = rb[u].y; w[2] = rb[u].z; w[3] = rb[u].w;
-            const unsigned Lw = ledge ? 0u - (w[0] & 1u) : rl[u];
-            const unsigned Rw = redge ? 0u - (w[3] >> 31) : rr[u];
+            w[0] = r.rb[u].x; w[1] = r.rb[u].y; w[2] = r.rb[u].z; w[3] = r.rb[u].w;
+            const unsigned Lw = ledge ? 0u - (w[0] & 1u) : r.rl[u];
+            const unsigned Rw = redge ? 0u - (w[3] >> 31) : r.rr[u];
             w[4] = (Lw & 0xe0000000u) | (Rw & 0x1fffffffu);
             // ---- horizontal 3-sums of predicate row yy: l + w + r = s + 2c ---------------------
             unsigned hs2[5], hc2[5];
@@ -114,9 +119,10 @@ act4_kernel(const uint32_t *__restrict__ bits, int H, int Wb, int rows, int chun
             for (int i = 0; i < 5; i++) {
                 const unsigned ones = hs0[i] ^ hs1[i] ^ hs2[i], c1 = maj3(hs0[i], hs1[i], hs2[i]);
                 const unsigned twos = hc0[i] ^ hc1[i] ^ hc2[i], c2 = maj3(hc0[i], hc1[i], hc2[i]);
-                // count = ones + 2 (c1 + twos) + 4 c2 >= 5
-                const unsigned all3 = ones & c1 & twos, any3 = ones | c1 | twos;
-                bin[i] = bin_in ? (all3 | (c2 & any3)) : 0u;
+                // count = ones + 2 (c1 + twos) + 4 c2 >= 5  <=>  c2 ? (ones | c1 | twos) : (ones & c1 & twos)
+                // and  c ? (a | b) : (a & b) == maj3(a, b, c): two LOP3
+                const unsigned m5 = maj3(maj3(ones, c1, c2), twos, c2);
+                bin[i] = bin_in ? m5 : 0u;
                 hs0[i] = hs1[i]; hc0[i] = hc1[i]; hs1[i] = hs2[i]; hc1[i] = hc2[i];
             }
             bin[4] &= xv;
@@ -150,6 +156,21 @@ act4_kernel(const uint32_t *__restrict__ bits, int H, int Wb, int rows, int chun
                 }
             }
         }
+    };
+    Rows ra, rb2;
+    int yb = y0 - 3;
+    load_rows(ra, yb);
+    for (;;) {  // two groups per iteration: the register sets ping-pong, no moves
+        const bool more1 = yb + A4_MLP < y_stop;
+        if (more1) load_rows(rb2, yb + A4_MLP);
+        process_rows(ra, yb);
+        if (!more1) break;
+        yb += A4_MLP;
+        const bool more2 = yb + A4_MLP < y_stop;
+        if (more2) load_rows(ra, yb + A4_MLP);
+        process_rows(rb2, yb);
+        if (!more2) break;
+        yb += A4_MLP;
     }
 }
 

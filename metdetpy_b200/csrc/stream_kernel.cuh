@@ -253,16 +253,25 @@ static inline void stream_state_free(StreamState &s) {
 }
 
 // choose words-per-thread of the temporal kernel and derive its CTA size / shared memory
-static inline int stream_state_config(StreamState &s, int wpt) {
+// (nt_req > 0 forces the CTA size; otherwise the largest CTA that keeps the most warps per SM)
+static inline int stream_state_config(StreamState &s, int wpt, int nt_req = 0) {
     if (wpt != 2 && wpt != 4) return -1;
-    const size_t budget = 220 * 1024;
+    const size_t sm_bytes = 228 * 1024, cta_max = 220 * 1024, reserved = 1024;
     const size_t per_thread = (size_t)(2 * s.n + ST_K) * 4 * wpt;
-    const size_t per_warp = per_thread * 32;
-    const int threads = budget / per_warp > 32 ? (budget / per_warp > 64 ? 128 : 64) : 32;
-    if (per_thread * threads + s.max_batch > budget) return -1;
+    const size_t table = ((size_t)2 * s.max_batch + 15) & ~(size_t)15;  // u16 bias per frame
+    int best_nt = 0;
+    size_t best_warps = 0;
+    for (int nt = 128; nt >= 32; nt >>= 1) {
+        if (nt_req && nt != nt_req) continue;
+        const size_t cta = per_thread * nt + table;
+        if (cta > cta_max) continue;
+        const size_t warps = sm_bytes / (cta + reserved) * (nt / 32);
+        if (warps > best_warps) { best_warps = warps; best_nt = nt; }
+    }
+    if (!best_nt) return -1;
     s.t_wpt = wpt;
     s.t_smem_per_thread = per_thread;
-    s.t_threads = threads;
+    s.t_threads = best_nt;
     return 0;
 }
 
@@ -306,7 +315,7 @@ static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long t
                                        cudaStream_t st2, cudaEvent_t ev_f1, cudaEvent_t ev_d0, int *launches) {
     const int HWG = (int)((size_t)s.W * s.H / (4 * s.t_wpt));  // pixel groups = threads
     const int nt = s.t_threads;
-    const size_t smem = s.t_smem_per_thread * nt + ((T + 15) & ~15);
+    const size_t smem = s.t_smem_per_thread * nt + (((size_t)2 * T + 15) & ~(size_t)15);
     const int grid = (HWG + nt - 1) / nt;
     uint8_t *bits8 = reinterpret_cast<uint8_t *>(s.d_bits);
     if (cudaMemsetAsync(sl.acount, 0, (size_t)T * sizeof(unsigned), st1) != cudaSuccess) return -1;

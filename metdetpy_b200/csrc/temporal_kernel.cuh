@@ -56,35 +56,47 @@ struct T2State {
     unsigned Od[WPT];           // sum of the odd pixels of the window, u16x2
 };
 
-// One frame.  ac / ao / asx: shared addresses of the frame's slot, of frame t-n's slot (which then
-// receives the prefetch), of the suffix-max word for this position.  Lu = window length, cpk = per-lane
-// bias (0x7fff - thr*L) * 0x10001.
-template <bool MASKED, int WPT>
-__device__ __forceinline__ void t2_step(T2State<WPT> &st, const unsigned (&mk)[WPT], uint32_t ac, uint32_t ao,
-                                        uint32_t asx, bool pf, const uint8_t *gp, unsigned Lu, unsigned cpk,
-                                        uint8_t *bp) {
-    t2_wait<T2_K - 1>();  // this thread's copy of the frame has landed
+// Operands of one frame: its raw word(s), frame t-n's, the suffix-max word(s) of its position.
+template <int WPT>
+struct T2Ops {
     unsigned xw[WPT], ow[WPT], mw[WPT];
-    t2_lds<WPT>(xw, ac);
-    t2_lds<WPT>(ow, ao);
-    t2_lds<WPT>(mw, asx);
+};
+
+// Load stage of one frame.  ac / ao / asx: shared addresses of the frame's slot, of frame t-n's slot
+// (which then receives the prefetch of frame t+K), of the suffix-max word for this position.
+template <bool MASKED, int WPT>
+__device__ __forceinline__ void t2_load(T2Ops<WPT> &q, const unsigned (&mk)[WPT], uint32_t ac, uint32_t ao,
+                                        uint32_t asx) {
+    t2_lds<WPT>(q.xw, ac);
+    t2_lds<WPT>(q.ow, ao);
+    t2_lds<WPT>(q.mw, asx);
     if (MASKED) {
 #pragma unroll
-        for (int k = 0; k < WPT; k++) xw[k] &= mk[k];
-        t2_sts<WPT>(ac, xw);
+        for (int k = 0; k < WPT; k++) q.xw[k] &= mk[k];
+        t2_sts<WPT>(ac, q.xw);
     }
-    if (pf) t2_cp<WPT>(ao, gp);  // slot of frame t-n is free now: fetch frame t+K into it
-    t2_commit();
+}
+// base + idx * stride as one IMAD.WIDE on the FMA pipe (no 64-bit pointer increments on the ALU pipe)
+__device__ __forceinline__ const uint8_t *t2_addr(const uint8_t *base, unsigned idx, unsigned stride) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(idx), "r"(stride), "l"((unsigned long long)base));
+    return reinterpret_cast<const uint8_t *>(r);
+}
+
+// Compute stage.  Lu = window length, cpk = per-lane bias (0x7fff - thr*L) * 0x10001.
+template <int WPT>
+__device__ __forceinline__ void t2_compute(T2State<WPT> &st, const T2Ops<WPT> &q, unsigned Lu, unsigned cpk,
+                                           uint8_t *bp) {
     unsigned M[WPT];
 #pragma unroll
     for (int k = 0; k < WPT; k++) {
-        const unsigned x = xw[k], x8 = x << 8, m = mw[k], m8 = m << 8;
+        const unsigned x = q.xw[k], x8 = x << 8, m = q.mw[k], m8 = m << 8;
         st.pO[k] = __vmaxu2(st.pO[k], x);
         st.pE[k] = __vmaxu2(st.pE[k], x8);
         const unsigned wO = t2_hi(__vmaxu2(st.pO[k], m));   // window max, odd pixels, clean u16x2
         const unsigned wE = t2_hi(__vmaxu2(st.pE[k], m8));  // ... even pixels
-        st.Wd[k] = st.Wd[k] + x - ow[k];
-        st.Od[k] = st.Od[k] + t2_hi(x) - t2_hi(ow[k]);
+        st.Wd[k] = st.Wd[k] + x - q.ow[k];
+        st.Od[k] = st.Od[k] + t2_hi(x) - t2_hi(q.ow[k]);
         const unsigned sE = st.Wd[k] - (st.Od[k] << 8);
         // per lane: max*L - sum + 0x7fff - thr*L ; bit 15 set <=> max*L - sum > thr*L
         const unsigned vO = wO * Lu + cpk - st.Od[k];
@@ -137,8 +149,12 @@ temporal2_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *_
     const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(t_smem);
     const uint32_t ring_s = smem0 + tid * VB;
     const uint32_t smx_s = ring_s + R * S;
-    uint8_t *thr_s = reinterpret_cast<uint8_t *>(t_smem) + (size_t)(R + n) * S;
-    for (int i = tid; i < T; i += NT) thr_s[i] = (uint8_t)min(max(thr[i], 0), 255);
+    // per-frame lane bias 0x7fff - thr*L (L = SlidingWindow.length of that frame), u16
+    uint16_t *thr_s = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(t_smem) + (size_t)(R + n) * S);
+    for (int i = tid; i < T; i += NT) {
+        const long long Li = t0 + i + 1 < n ? t0 + i + 1 : n;
+        thr_s[i] = (uint16_t)(0x7fff - min(max(thr[i], 0), 255) * (int)Li);
+    }
     __syncthreads();
     const int g = blockIdx.x * NT + tid;
     if (g >= HWG) return;
@@ -220,15 +236,32 @@ temporal2_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *_
             uint32_t ac = ring_s + c * S, ao = ring_s + o * S, asx = smx_s + j * S;
             const uint8_t *gp = gbase + (size_t)pf_slot * HWu;
             uint8_t *bp = bout + (size_t)i * bstride;
-            const uint8_t *tp = thr_s + i;
-            const unsigned bias = 0x7fffu;
-#pragma unroll 2
-            for (int u = 0; u < run; u++) {
-                const unsigned cpk = (bias - (unsigned)tp[u] * Lu) * 0x00010001u;
-                t2_step<MASKED, WPT>(st, mk, ac, ao, asx, pf, gp, Lu, cpk, bp);
-                ac += S; ao += S; asx += S;
-                gp += HWu;
-                bp += bstride;
+            const uint16_t *tp = thr_s + i;
+            const uint8_t *gp1 = gp + HWu;
+            uint8_t *bp1 = bp + bstride;
+            const unsigned bs32 = (unsigned)bstride;
+            // frames are taken two at a time: both frames' shared-memory loads first, then both
+            // prefetches back to back (ptxas pads every LDS -> LDGSTS transition with three dummy LDS)
+            T2Ops<WPT> qa, qb;
+            unsigned u = 0;
+            for (; u + 2 <= (unsigned)run; u += 2) {
+                t2_wait<T2_K - 2>();  // frames u and u+1 have landed
+                t2_load<MASKED, WPT>(qa, mk, ac, ao, asx);
+                t2_load<MASKED, WPT>(qb, mk, ac + S, ao + S, asx + S);
+                if (pf) t2_cp<WPT>(ao, t2_addr(gp, u, HWu));  // slot of frame t-n is free: fetch frame t+K
+                t2_commit();
+                if (pf) t2_cp<WPT>(ao + S, t2_addr(gp1, u, HWu));
+                t2_commit();
+                t2_compute<WPT>(st, qa, Lu, (unsigned)tp[u] * 0x00010001u, (uint8_t *)t2_addr(bp, u, bs32));
+                t2_compute<WPT>(st, qb, Lu, (unsigned)tp[u + 1] * 0x00010001u, (uint8_t *)t2_addr(bp1, u, bs32));
+                ac += 2 * S; ao += 2 * S; asx += 2 * S;
+            }
+            if (u < (unsigned)run) {  // odd run: one frame left
+                t2_wait<T2_K - 1>();
+                t2_load<MASKED, WPT>(qa, mk, ac, ao, asx);
+                if (pf) t2_cp<WPT>(ao, t2_addr(gp, u, HWu));
+                t2_commit();
+                t2_compute<WPT>(st, qa, Lu, (unsigned)tp[u] * 0x00010001u, (uint8_t *)t2_addr(bp, u, bs32));
             }
             i += run; j += run;
             c += run; if (c == R) c = 0;
