@@ -351,9 +351,10 @@ def main_ours(a):
         achieved = alg_bytes / (alone_ms * 1e-3) / 1e9 if alone_ms > 0 else None
         in_step = 2.0 * HW * B * a.steps / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else None
         # DRAM bytes of the chain from the ncu --set full capture in profiles/r01_ncu_full_summary.txt
-        # (4K, n=30, 512 frames: temporal 5.01 GB + act 1.02 GB + dst 1.10 GB = 1.68 H*W per frame), per launch
+        # (4K, n=30, 512 frames: temporal2 4.49 + 0.52 GB, act4 0.59 + 0.49 GB, dst_sparse 0.02 GB
+        # = 6.11 GB = 1.44 H*W per frame), averaged over the chain's 4 launches like `achieved`
         default_cfg = (W, H, n, B) == (3840, 2160, 30, 512) and not a.no_dy
-        traffic = 1.68 * HW * B / 3.0 if default_cfg else None
+        traffic = 1.438 * HW * B / 4.0 if default_cfg else None
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": wall_max / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -365,7 +366,7 @@ def main_ours(a):
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "traffic_note": "bytes per launch (avg of the 3 launches of the chain), ncu capture profiles/r01_ncu_full_summary.txt",
+                         "traffic_note": "DRAM bytes per launch (avg of the 4 launches of the chain), ncu --set full capture profiles/r01_ncu_full_summary.txt",
                          "algorithmic_bytes_per_launch": 2.0 * HW * B * alone_steps / max(alone_launches, 1),
                          "kernel": "fused mask chain: temporal_kernel (stack->diff->threshold) + act4_kernel (median+close) + dst_sparse/dense_kernel (dy-mask, mask bytes)",
                          "kernel_ms_per_launch": alone_ms / max(alone_launches, 1),
@@ -375,7 +376,7 @@ def main_ours(a):
                                    "flight (chain alone on the GPU) right after the timed region",
                          "achieved_inside_timed_region": in_step,
                          "inside_note": "same events during the timed region, where the chain shares the SMs with the Hough pass "
-                                        "and the next batch's temporal pass (two batches in flight): elapsed, not busy, time",
+                                        "and the next batch's temporal pass (three batches in flight): elapsed, not busy, time",
                          "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s"},
             "clocks": sampler.summary(), "nms_lines_total": nlines_total,
         }
