@@ -163,6 +163,36 @@ int mdb_max_stack(const uint8_t *frames, int T, size_t frame_bytes, uint8_t *out
 int mdb_lineset_nms(const int32_t *lines_in, int n, int32_t *lines_out, double *prob_out,
                     int32_t *n_out);
 
+/* ---- loader preprocessing on the device ---------------------------
+ * Replaces, for uint8 frames, what the reference's video loader applies to every decoded frame:
+ *   Transform.opencv_resize   = cv2.resize(img, dsize, INTER_LINEAR)   MetLib/imgproc.py:82-85
+ *   Transform.opencv_BGR2GRAY = cv2.cvtColor(img, COLOR_BGR2GRAY)      MetLib/imgproc.py:87-88 (:90-91 RGB)
+ *   Transform.mask_with       = img * mask                             MetLib/imgproc.py:96-101
+ *   Transform.exec_transform  (the chain, built at MetLib/videoloader.py:300-308)  imgproc.py:129-139
+ *   MergeFunction.max over exp_frame consecutive frames                MetLib/utils.py:203-204, videoloader.py:388
+ * Results are bit-exact with cv2 (fixed-point resize and gray).  channels = 1 (gray source: resize and
+ * mask only) or 3 (interleaved BGR, or RGB with rgb_order = 1; output is always one channel).
+ * mask: host pointer to dst_h*dst_w bytes of {0,1}, or NULL.  The handle owns its stream, the tap
+ * tables, the mask and an output buffer of max_out frames. */
+typedef struct mdb_preproc *mdb_preproc_handle;
+int mdb_preproc_create(int src_w, int src_h, int channels, int rgb_order, int dst_w, int dst_h,
+                       const uint8_t *mask, int exp_frame, int max_out, int device,
+                       mdb_preproc_handle *out);
+/* T source frames ([T][src_h][src_w][channels], host or device) -> ceil(T / exp_frame) output frames
+ * ([.][dst_h][dst_w]).  out = NULL keeps the result in the handle's device buffer (see
+ * mdb_preproc_output) so that it can be fed to mdb_submit_batch(..., on_device = 1) without leaving
+ * the GPU; otherwise it is copied to `out` (host or device per out_on_device).  Synchronous. */
+int mdb_preproc_run(mdb_preproc_handle h, const uint8_t *frames, int T, int frames_on_device,
+                    uint8_t *out, int out_on_device, int32_t *n_out);
+int mdb_preproc_output(mdb_preproc_handle h, const uint8_t **device_ptr);
+/* device time (ms, CUDA events) of the most recent run's kernel */
+int mdb_preproc_time(mdb_preproc_handle h, float *ms);
+int mdb_preproc_destroy(mdb_preproc_handle h);
+/* host-only: the source index pair and 11-bit weights cv2's 8-bit INTER_LINEAR uses for every
+ * destination coordinate of one axis (x axis: clamp_fraction = 1, y axis: 0) -- what the kernel consumes */
+int mdb_preproc_axis_taps(int dst, int src, int clamp_fraction, int32_t *s0, int32_t *s1, int32_t *w0,
+                          int32_t *w1);
+
 /* pinned host memory for frame staging (cudaHostAlloc / cudaFreeHost) */
 int mdb_alloc_pinned(size_t bytes, void **ptr);
 int mdb_free_pinned(void *ptr);

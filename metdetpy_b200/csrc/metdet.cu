@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "hough.cuh"
 #include "kernels_basic.cuh"
+#include "preproc.cuh"
 #include "stream_kernel.cuh"
 
 #define HOUGH_SMEM_BYTES (MDB_POINT_CAP * 8 + MDB_POINT_CAP / 8)  // keys u32 + order u16 + line u16 + removed bits
@@ -907,6 +908,166 @@ extern "C" int mdb_max_stack(const uint8_t *frames, int T, size_t frame_bytes, u
     if (!out_on_device && d_out) cudaFree(d_out);
     cudaStreamDestroy(st);
     if (e != cudaSuccess) return fail(MDB_ERR_CUDA, "mdb_max_stack: %s", cudaGetErrorString(e));
+    return MDB_OK;
+}
+
+// ---- loader preprocessing ---------------------------------------------------------------------
+struct mdb_preproc {
+    PreParams P;
+    int device = 0, max_out = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    PreTap *d_xt = nullptr, *d_yt = nullptr;
+    uint8_t *d_mask = nullptr, *d_out = nullptr, *d_in = nullptr;
+    size_t in_cap = 0;
+    float last_ms = 0.f;
+};
+
+// OpenCV's 8-bit INTER_LINEAR taps (oracle/preproc_oracle.py: axis_taps): float32 position, 11-bit weights
+static void pre_axis_taps(int dst, int src, bool clamp_fraction, int stride, std::vector<PreTap> &taps) {
+    taps.resize(dst);
+    const double scale = (double)src / (double)dst;
+    for (int d = 0; d < dst; d++) {
+        volatile float f = (float)(((double)d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        volatile float fr = f - (float)s;
+        if (clamp_fraction) {
+            if (s < 0) { fr = 0.f; s = 0; }
+            if (s >= src - 1) { fr = 0.f; s = src - 1; }
+        }
+        volatile float one_minus = 1.0f - fr;
+        volatile float p1 = fr * 2048.0f, p0 = one_minus * 2048.0f;
+        PreTap t;
+        t.w1 = (int)nearbyintf(p1);  // cvRound: half to even (default rounding mode)
+        t.w0 = (int)nearbyintf(p0);
+        t.s0 = std::min(std::max(s, 0), src - 1) * stride;
+        t.s1 = std::min(std::max(s + 1, 0), src - 1) * stride;
+        taps[d] = t;
+    }
+}
+
+extern "C" int mdb_preproc_axis_taps(int dst, int src, int clamp_fraction, int32_t *s0, int32_t *s1, int32_t *w0,
+                                     int32_t *w1) {
+    if (dst < 1 || src < 1 || !s0 || !s1 || !w0 || !w1) return fail(MDB_ERR_INVALID, "mdb_preproc_axis_taps: bad arguments");
+    std::vector<PreTap> t;
+    pre_axis_taps(dst, src, clamp_fraction != 0, 1, t);
+    for (int d = 0; d < dst; d++) { s0[d] = t[d].s0; s1[d] = t[d].s1; w0[d] = t[d].w0; w1[d] = t[d].w1; }
+    return MDB_OK;
+}
+
+static void preproc_free(mdb_preproc *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void *dev[] = {h->d_xt, h->d_yt, h->d_mask, h->d_out, h->d_in};
+    for (void *p : dev)
+        if (p) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int mdb_preproc_create(int src_w, int src_h, int channels, int rgb_order, int dst_w, int dst_h,
+                                  const uint8_t *mask, int exp_frame, int max_out, int device,
+                                  mdb_preproc_handle *out) {
+    if (!out) return fail(MDB_ERR_INVALID, "mdb_preproc_create: null argument");
+    *out = nullptr;
+    if (src_w < 1 || src_h < 1 || dst_w < 1 || dst_h < 1 || src_w > 65535 || src_h > 65535 || dst_w > 65535 || dst_h > 65535)
+        return fail(MDB_ERR_INVALID, "mdb_preproc_create: bad sizes %dx%d -> %dx%d", src_w, src_h, dst_w, dst_h);
+    if (channels != 1 && channels != 3)
+        return fail(MDB_ERR_INVALID, "mdb_preproc_create: channels must be 1 or 3 (got %d)", channels);
+    if (exp_frame < 1 || max_out < 1) return fail(MDB_ERR_INVALID, "mdb_preproc_create: exp_frame and max_out must be >= 1");
+    const int ndev = mdb_device_count();
+    if (ndev == 0) return fail(MDB_ERR_CUDA, "mdb_preproc_create: no CUDA device -- this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(MDB_ERR_INVALID, "mdb_preproc_create: device %d of %d", device, ndev);
+    CK(cudaSetDevice(device));
+    mdb_preproc *h = new (std::nothrow) mdb_preproc();
+    if (!h) return fail(MDB_ERR_NOMEM, "mdb_preproc_create: out of host memory");
+    h->device = device; h->max_out = max_out;
+    PreParams &P = h->P;
+    P.src_w = src_w; P.src_h = src_h; P.channels = channels; P.dst_w = dst_w; P.dst_h = dst_h;
+    P.resize = (src_w != dst_w || src_h != dst_h) ? 1 : 0;
+    P.rgb = rgb_order ? 1 : 0; P.exp_frame = exp_frame;
+    P.xt = P.yt = nullptr; P.mask = nullptr;
+    std::vector<PreTap> xt, yt;
+    pre_axis_taps(dst_w, src_w, true, channels, xt);
+    pre_axis_taps(dst_h, src_h, false, 1, yt);
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_xt, xt.size() * sizeof(PreTap));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_yt, yt.size() * sizeof(PreTap));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_out, (size_t)max_out * dst_w * dst_h);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_xt, xt.data(), xt.size() * sizeof(PreTap), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_yt, yt.data(), yt.size() * sizeof(PreTap), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && mask) {
+        e = cudaMalloc((void **)&h->d_mask, (size_t)dst_w * dst_h);
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_mask, mask, (size_t)dst_w * dst_h, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        int rc = fail(MDB_ERR_CUDA, "mdb_preproc_create: %s", cudaGetErrorString(e));
+        preproc_free(h);
+        return rc;
+    }
+    P.xt = h->d_xt; P.yt = h->d_yt; P.mask = h->d_mask;
+    *out = h;
+    return MDB_OK;
+}
+
+extern "C" int mdb_preproc_run(mdb_preproc_handle h, const uint8_t *frames, int T, int frames_on_device,
+                               uint8_t *out, int out_on_device, int32_t *n_out) {
+    if (!h || !frames) return fail(MDB_ERR_INVALID, "mdb_preproc_run: null argument");
+    if (T < 1) return fail(MDB_ERR_INVALID, "mdb_preproc_run: T=%d", T);
+    const PreParams &P = h->P;
+    const int G = (T + P.exp_frame - 1) / P.exp_frame;
+    if (G > h->max_out) return fail(MDB_ERR_INVALID, "mdb_preproc_run: %d output frames exceed max_out=%d", G, h->max_out);
+    CK(cudaSetDevice(h->device));
+    const size_t in_bytes = (size_t)T * P.src_w * P.src_h * P.channels;
+    const uint8_t *d_frames = frames;
+    if (!frames_on_device) {
+        if (h->in_cap < in_bytes) {
+            if (h->d_in) CK(cudaFree(h->d_in));
+            h->d_in = nullptr; h->in_cap = 0;
+            if (cudaMalloc((void **)&h->d_in, in_bytes) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(MDB_ERR_NOMEM, "mdb_preproc_run: cudaMalloc(%zu bytes) for the source frames", in_bytes);
+            }
+            h->in_cap = in_bytes;
+        }
+        CK(cudaMemcpyAsync(h->d_in, frames, in_bytes, cudaMemcpyHostToDevice, h->stream));
+        d_frames = h->d_in;
+    }
+    dim3 grid((P.dst_w + 255) / 256, P.dst_h, G);
+    CK(cudaEventRecord(h->ev0, h->stream));
+    if (P.channels == 3) preproc_kernel<3><<<grid, 256, 0, h->stream>>>(P, d_frames, T, h->d_out);
+    else preproc_kernel<1><<<grid, 256, 0, h->stream>>>(P, d_frames, T, h->d_out);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    if (out)
+        CK(cudaMemcpyAsync(out, h->d_out, (size_t)G * P.dst_w * P.dst_h,
+                           out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    if (n_out) *n_out = G;
+    return MDB_OK;
+}
+
+extern "C" int mdb_preproc_output(mdb_preproc_handle h, const uint8_t **device_ptr) {
+    if (!h || !device_ptr) return fail(MDB_ERR_INVALID, "mdb_preproc_output: null argument");
+    *device_ptr = h->d_out;
+    return MDB_OK;
+}
+
+extern "C" int mdb_preproc_time(mdb_preproc_handle h, float *ms) {
+    if (!h || !ms) return fail(MDB_ERR_INVALID, "mdb_preproc_time: null argument");
+    *ms = h->last_ms;
+    return MDB_OK;
+}
+
+extern "C" int mdb_preproc_destroy(mdb_preproc_handle h) {
+    if (!h) return fail(MDB_ERR_INVALID, "mdb_preproc_destroy: null handle");
+    preproc_free(h);
     return MDB_OK;
 }
 

@@ -232,7 +232,41 @@ def case_hough():
     print("hough: 40 masks, lines per mask", [len(x) for x in outs])
 
 
-CASES = dict(synth_small=case_synth_small, synth_dy_mask=case_synth_dy_mask, odd=case_odd_size,
+def case_preproc():
+    """Loader preprocessing by the reference's own Transform (MetLib/imgproc.py:70-139) and
+    MergeFunction.max (MetLib/utils.py:203-204): resize -> BGR2GRAY -> mask, exp_frame merge."""
+    from MetLib.imgproc import Transform
+    from MetLib.utils import MergeFunction
+    rng = np.random.default_rng(77)
+    out = {}
+    cases = [("down4_rgb", 8, (192, 108, 3), (48, 27), True, 2), ("ratio_rgb", 5, (150, 90, 3), (64, 37), True, 1),
+             ("up_gray", 4, (40, 30, 1), (96, 54), False, 3), ("same_rgb", 3, (64, 32, 3), (64, 32), True, 1)]
+    for name, T, (W0, H0, C), (W, H), gray, exp in cases:
+        base = rng.integers(0, 256, (H0, W0, C), dtype=np.uint8)
+        frames = np.stack([np.clip(base.astype(int) + rng.integers(-40, 40, base.shape), 0, 255).astype(np.uint8)
+                           for _ in range(T)])
+        if C == 1:
+            frames = frames[..., 0]
+        mask = (rng.random((H, W)) > 0.2).astype(np.uint8)
+        tr = Transform()
+        if (W0, H0) != (W, H):
+            tr.opencv_resize([W, H])
+        if gray:
+            tr.opencv_BGR2GRAY()
+        tr.mask_with(mask)
+        res = []
+        for s in range(0, T, exp):
+            group = [tr.exec_transform(f) for f in frames[s:s + exp]]
+            res.append(group[0] if len(group) == 1 else MergeFunction.max(group))
+        out[f"{name}_frames"] = frames
+        out[f"{name}_mask"] = mask
+        out[f"{name}_out"] = np.stack(res)
+        out[f"{name}_cfg"] = np.array([W, H, int(gray), exp])
+        print("preproc", name, frames.shape, "->", out[f"{name}_out"].shape)
+    np.savez_compressed(os.path.join(HERE, "preproc.npz"), names=np.array([c[0] for c in cases]), **out)
+
+
+CASES = dict(preproc=case_preproc, synth_small=case_synth_small, synth_dy_mask=case_synth_dy_mask, odd=case_odd_size,
              dense=case_fixed_thr_dense, low=case_low_sens, clip=case_real_clip, nms=case_nms,
              sw=case_sliding_window, hough=case_hough)
 
