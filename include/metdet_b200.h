@@ -59,7 +59,9 @@ typedef struct mdb_config {
     int32_t device;          /* CUDA device ordinal */
     int32_t apply_mask;      /* != 0: multiply incoming frames by the mask on the device
                                 (Transform.mask_with, MetLib/imgproc.py:96-101) */
-    int32_t reserved[4];
+    int32_t detector;  /* 0 = M3Detector (Detector.py:302-392), 1 = ClassicDetector (Detector.py:245-299:
+                        * window is 4 frames whatever `window` says, dy_mask ignored, fixed maxLineGap, no NMS) */
+    int32_t reserved[3];
 } mdb_config;
 
 /* Per-frame scalars that M3Detector exposes as attributes (Detector.py:227-229, :342-344, :355,

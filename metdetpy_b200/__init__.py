@@ -1,17 +1,21 @@
 """metdetpy_b200 -- B200 (sm_100a) implementation of MetDetPy's M3 line-detector hot path.
 
-Drop-in classes: `M3Detector`, `LineDetector`, `SlidingWindow`, `SNR_SW`, `EMA`, `lineset_nms`
-(MetLib/Detector.py, MetLib/utils.py) and `max_stacker`, `MaxImgContainer` (MetLib/stacker.py).
+Drop-in classes: `M3Detector`, `ClassicDetector`, `LineDetector`, `SlidingWindow`, `SNR_SW`, `EMA`,
+`lineset_nms` (MetLib/Detector.py, MetLib/utils.py), `max_stacker`, `MaxImgContainer` (MetLib/stacker.py)
+and the loader's `Transform` / `MergeFunction` (MetLib/imgproc.py, MetLib/utils.py; module `imgproc`).
 The CUDA library is loaded on first use; there is no CPU fallback."""
 from .config import BinaryCfg, BinaryCoreCfg, DynamicCfg, HoughLineCfg  # noqa: F401
 
-__all__ = ["M3Detector", "LineDetector", "BaseDetector", "SlidingWindow", "SNR_SW", "EMA",
+__all__ = ["M3Detector", "ClassicDetector", "Transform", "LineDetector", "BaseDetector", "SlidingWindow", "SNR_SW", "EMA",
            "lineset_nms", "select_subarea", "max_stacker", "MaxImgContainer", "merge_max",
            "BinaryCfg", "BinaryCoreCfg", "HoughLineCfg", "DynamicCfg", "register_with_metlib"]
 
 
 def __getattr__(name):
-    if name in ("M3Detector", "LineDetector", "BaseDetector", "SlidingWindow", "SNR_SW", "EMA",
+    if name == "Transform":
+        from . import imgproc
+        return imgproc.Transform
+    if name in ("M3Detector", "ClassicDetector", "LineDetector", "BaseDetector", "SlidingWindow", "SNR_SW", "EMA",
                 "lineset_nms", "select_subarea"):
         from . import detector
         return getattr(detector, name)
@@ -29,11 +33,12 @@ def register_with_metlib():
     import MetLib  # the reference package must be importable
     import MetLib.Detector as D
 
-    from .detector import M3Detector
+    from .detector import ClassicDetector, M3Detector
     D.M3Detector = M3Detector
+    D.ClassicDetector = ClassicDetector
     MetLib.M3Detector = M3Detector
-    MetLib.available_detectors = [M3Detector if getattr(c, "__name__", "") == "M3Detector" else c
-                                  for c in MetLib.available_detectors]
+    ours = {"M3Detector": M3Detector, "ClassicDetector": ClassicDetector}
+    MetLib.available_detectors = [ours.get(getattr(c, "__name__", ""), c) for c in MetLib.available_detectors]
     # get_xxx closes over a dict built at import time (MetLib/__init__.py:16-25): rebuild it
     MetLib.get_detector = MetLib.get_xxx("detector", MetLib.available_detectors)
     main = sys.modules.get("MetDetPy")

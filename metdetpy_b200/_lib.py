@@ -20,7 +20,7 @@ class Config(C.Structure):
                 ("nz_interval", C.c_int32), ("roi", C.c_int32 * 4), ("hough_threshold", C.c_int32),
                 ("hough_min_len", C.c_int32), ("hough_max_gap", C.c_int32), ("dy_mask", C.c_int32),
                 ("max_batch", C.c_int32), ("device", C.c_int32), ("apply_mask", C.c_int32),
-                ("reserved", C.c_int32 * 4)]
+                ("detector", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class FrameInfo(C.Structure):

@@ -58,4 +58,5 @@ struct HoughParams {
     int cap;        // point-list stride / smem capacity
     int max_lines;  // rows stored per frame
     int walk_cap;   // capacity of the per-slot line-pixel scratch
+    int fixed_gap;  // >= 0: maxLineGap is this constant (ClassicDetector); < 0: M3's adaptive gap
 };

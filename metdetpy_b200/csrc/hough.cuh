@@ -56,6 +56,7 @@ __device__ __forceinline__ void bitonic_sort_u32(uint32_t *a, int npow2, int tid
 }
 
 __device__ __forceinline__ int line_gap_of(const HoughParams &P, unsigned n_on) {
+    if (P.fixed_gap >= 0) return P.fixed_gap;  // ClassicDetector: maxLineGap = hough_cfg.max_gap (Detector.py:284-289)
     // Detector.py:342-344: dst_sum = count / mask_area * 100; gap = max(0, 1 - dst_sum/0.05) * max_gap
     const double dst_sum = __dmul_rn(__ddiv_rn((double)n_on, P.mask_area), 100.0);
     double g = __dsub_rn(1.0, __ddiv_rn(dst_sum, 0.05));

@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "hough.cuh"
+#include "classic.cuh"
 #include "kernels_basic.cuh"
 #include "preproc.cuh"
 #include "stream_kernel.cuh"
@@ -90,6 +91,7 @@ struct mdb_detector {
     uint32_t *d_bitmap = nullptr, *d_walk = nullptr, *d_okeys = nullptr, *d_oidx = nullptr;  // tier 3
     long long *d_prof = nullptr;  // optional per-frame PPHT phase cycle counters (debug)
     StreamState sk;
+    uint32_t *d_cbits = nullptr;  // ClassicDetector: three bit planes [3][max_batch][H][Wb] (a, b, dst)
     BatchCtx ctx[NCTX];
     // host state
     long long timer = 0, dy_timer = 0, seek0 = 0;
@@ -146,7 +148,7 @@ static void free_all(mdb_detector *h) {
     if (h->stream3) cudaStreamSynchronize(h->stream3);
     if (h->cstream) cudaStreamSynchronize(h->cstream);
     void *dev[] = {h->d_ring, h->d_mask, h->d_act, h->d_state, h->d_noise, h->d_accum,
-                   h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_prof};
+                   h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_prof, h->d_cbits};
     for (void *p : dev)
         if (p) cudaFree(p);
     for (BatchCtx &c : h->ctx) {
@@ -198,7 +200,9 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     mdb_detector *h = new (std::nothrow) mdb_detector();
     if (!h) return fail(MDB_ERR_NOMEM, "mdb_create: out of host memory");
     h->cfg = *cfg;
-    h->W = cfg->width; h->H = cfg->height; h->n = cfg->window;
+    if (cfg->detector != 0 && cfg->detector != 1) { delete h; return fail(MDB_ERR_INVALID, "mdb_create: unknown detector kind %d", cfg->detector); }
+    if (cfg->detector == 1) { h->cfg.window = 4; h->cfg.dy_mask = 0; }  // ClassicDetector.classic_max_size, Detector.py:249-254
+    h->W = cfg->width; h->H = cfg->height; h->n = h->cfg.window;
     h->HW = (size_t)h->W * h->H;
     const int T = cfg->max_batch;
     // ring: history (n-1) + two batches, so the copy of batch k+1 never lands on frames batch k reads
@@ -215,6 +219,7 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     for (size_t i = 0; i < h->HW; i++) area += mask[i];
     hp.mask_area = (double)area;
     hp.cap = MDB_POINT_CAP; hp.max_lines = MDB_MAX_LINES; hp.walk_cap = h->W + h->H + 2;
+    hp.fixed_gap = cfg->detector == 1 ? cfg->hough_max_gap : -1;
     // tier-2 Hough slots (global-memory accumulators): one per frame in flight, 4 GB budget
     {
         const size_t per_slot = (size_t)MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t);
@@ -285,6 +290,7 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
         CKH(cudaMemsetAsync(c.d_wcount, 0, T * sizeof(unsigned), h->stream));
         CKH(cudaMemsetAsync(c.d_dense, 0, (size_t)(T + 1) * sizeof(unsigned), h->stream));
     }
+    if (cfg->detector == 1) ALLOC(h->d_cbits, (size_t)3 * T * h->H * h->Wb * sizeof(uint32_t));
     ALLOC(h->d_accum, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t));
     ALLOC(h->d_bitmap, bm_words * sizeof(uint32_t));
     ALLOC(h->d_walk, (size_t)hp.walk_cap * sizeof(uint32_t));
@@ -333,7 +339,7 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
                              HOUGH_SMEM_BYTES + HOUGH_TABLE_BYTES));
     CKH(cudaStreamSynchronize(h->stream));
     {
-        int rc = stream_state_init(h->sk, h->W, h->H, h->n, cfg->device, cfg->max_batch);
+        int rc = cfg->detector == 1 ? 0 : stream_state_init(h->sk, h->W, h->H, h->n, cfg->device, cfg->max_batch);
         if (rc != 0) { free_all(h); return fail(MDB_ERR_CUDA, "stream kernel init failed: %s", cudaGetErrorString(cudaGetLastError())); }
     }
     *out = h;
@@ -396,7 +402,27 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
     CK(cudaMemsetAsync(c.d_npoints, 0, T * sizeof(unsigned), h->stream2));
     CK(cudaEventRecord(c.ev_f0, h->stream));
     int nl = 0;
-    if (h->use_stream_kernel && stream_kernel_supported(h->sk, T)) {
+    if (h->cfg.detector == 1) {
+        // ClassicDetector: bit planes on the front stream (after the thresholds), expansion on the back stream
+        const size_t plane = (size_t)h->cfg.max_batch * h->H * h->Wb;
+        uint32_t *ab = h->d_cbits, *bb = h->d_cbits + plane, *db = h->d_cbits + 2 * plane;
+        const int nthreads = h->H * h->Wb;
+        if (h->W % 16 == 0)
+            classic_bits_kernel<true><<<(nthreads + 255) / 256, 256, 0, h->stream>>>(src, h->W, h->H, h->Wb, timer0, T, c.d_thr, ab, bb);
+        else
+            classic_bits_kernel<false><<<(nthreads + 255) / 256, 256, 0, h->stream>>>(src, h->W, h->H, h->Wb, timer0, T, c.d_thr, ab, bb);
+        const int rows = 64, strips = (h->Wb + SP_USE - 1) / SP_USE, bands = (h->H + rows - 1) / rows;
+        classic_spatial_kernel<<<dim3((strips * bands + SP_WARPS - 1) / SP_WARPS, T), SP_WARPS * 32, 0, h->stream>>>(
+            ab, bb, h->H, h->Wb, rows, strips, bands, db);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c.ev_f1, h->stream));
+        CK(cudaStreamWaitEvent(h->stream2, c.ev_f1, 0));
+        CK(cudaEventRecord(c.ev_d0, h->stream2));
+        c.dst_dirty = true;
+        classic_expand_kernel<<<dim3((h->W + 255) / 256, h->H, T), 256, 0, h->stream2>>>(
+            db, h->W, h->H, h->Wb, c.d_dst, c.d_npoints, c.d_points, MDB_POINT_CAP);
+        nl = 3;
+    } else if (h->use_stream_kernel && stream_kernel_supported(h->sk, T)) {
         if (c.dst_dirty) {  // the generic kernel wrote this buffer last: resynchronise buffer and bitmap
             CK(cudaMemsetAsync(c.d_dst, 0, (size_t)h->cfg.max_batch * h->HW, h->stream2));
             CK(cudaMemsetAsync(c.d_dstbits, 0, (size_t)h->cfg.max_batch * h->H * h->Wb * sizeof(uint32_t), h->stream2));
@@ -546,10 +572,11 @@ static int finish_batch(mdb_detector *h, const BatchCtx &c, mdb_frame_info *info
         fi.lines_num = c.h_nlines[i];
         const int32_t *src = c.h_lines + (size_t)i * MDB_MAX_LINES * 4;
         int nraw = fi.lines_num > MDB_NUM_LINES_TOOMUCH ? 0 : fi.lines_num;
+        if (h->cfg.detector == 1) nraw = std::min(fi.lines_num, MDB_MAX_LINES);  // ClassicDetector keeps every segment
         fi.n_raw = nraw;
         if (raw_lines && nraw) memcpy(raw_lines + (size_t)i * MDB_MAX_LINES * 4, src, (size_t)nraw * 16);
         fi.n_lines = 0;
-        if (nraw && lines && prob)
+        if (nraw && lines && prob && h->cfg.detector == 0)
             fi.n_lines = nms_host(src, nraw, lines + (size_t)i * MDB_MAX_LINES * 4, prob + (size_t)i * MDB_MAX_LINES);
         if (infos) infos[i] = fi;
     }
@@ -923,7 +950,7 @@ struct mdb_preproc {
     float last_ms = 0.f;
 };
 
-// OpenCV's 8-bit INTER_LINEAR taps (oracle/preproc_oracle.py: axis_taps): float32 position, 11-bit weights
+// OpenCV's 8-bit INTER_LINEAR taps: float32 position, 11-bit weights (checked against the test-suite's CPU checker)
 static void pre_axis_taps(int dst, int src, bool clamp_fraction, int stride, std::vector<PreTap> &taps) {
     taps.resize(dst);
     const double scale = (double)src / (double)dst;

@@ -5,7 +5,7 @@
 //     -> np.max over exp_frame consecutive frames                              (MergeFunction.max, utils.py:203-204)
 // fused into one pass: a thread produces one output pixel of one merged frame.  The arithmetic is
 // OpenCV's 8-bit fixed point (11-bit weights, (((b*(h>>4))>>16)+...+2)>>2 vertical pass, 15-bit gray
-// weights), restated and pinned in oracle/preproc_oracle.py; results are bit-exact.
+// weights), restated and pinned by the CPU checker of the test-suite; results are bit-exact.
 #pragma once
 #include "common.cuh"
 

@@ -99,7 +99,7 @@ class _Engine:
 
     def __init__(self, mask: np.ndarray, n: int, *, adaptive: bool, init_value: int,
                  sensitivity: str, interval: int, roi, hough, dy_mask: bool, max_batch: int,
-                 device: int, apply_mask: bool):
+                 device: int, apply_mask: bool, detector: int = 0):
         self.lib = _lib.load()
         if self.lib.mdb_device_count() < 1:
             raise _lib.MetDetError("no CUDA device visible: metdetpy_b200 has no CPU fallback")
@@ -121,6 +121,7 @@ class _Engine:
         cfg.hough_threshold, cfg.hough_min_len, cfg.hough_max_gap = (int(v) for v in hough)
         cfg.dy_mask = int(bool(dy_mask))
         cfg.max_batch, cfg.device, cfg.apply_mask = int(max_batch), int(device), int(bool(apply_mask))
+        cfg.detector = int(detector)
         self.handle = C.c_void_p()
         check(self.lib.mdb_create(C.byref(cfg), _ptr(mask), C.byref(self.handle)), "mdb_create")
         T = max_batch
@@ -300,7 +301,7 @@ class LineDetector(BaseDetector):
 
     def __init__(self, window_sec: float, fps: float, mask: np.ndarray, num_cls: int,
                  cfg: BinaryCfg, logger: Any = None, *, device: int = 0, max_batch: int = 1,
-                 apply_mask: bool = False):
+                 apply_mask: bool = False, _detector: int = 0):
         self.mask = mask
         self.num_cls = num_cls
         self.logger = logger
@@ -322,7 +323,7 @@ class LineDetector(BaseDetector):
                             hough=(self.hough_cfg.threshold, self.hough_cfg.min_len,
                                    self.hough_cfg.max_gap),
                             dy_mask=self.dynamic_cfg.dy_mask, max_batch=max_batch, device=device,
-                            apply_mask=apply_mask)
+                            apply_mask=apply_mask, detector=_detector)
         self._timer = 0
         self._snr = 0
         self.stack = SNR_SW(self)
@@ -340,6 +341,87 @@ class LineDetector(BaseDetector):
 
     def close(self):
         self._eng.close()
+
+
+class ClassicDetector(LineDetector):
+    """ClassicDetector (MetLib/Detector.py:245-299): 4-frame window, frame absdiff -> threshold -> dilate
+    -> invert, bitwise-and, second absdiff -> threshold -> dilate, HoughLinesP with the configured
+    maxLineGap; every raw segment is returned, cls_pred[:, 0] = 1 (no NMS).  `detect_many` is the
+    batched form.  Kernels: csrc/classic.cuh."""
+    classic_max_size = 4
+
+    def __init__(self, window_sec: float, fps: float, mask: np.ndarray, num_cls: int,
+                 cfg: BinaryCfg, logger: Any = None, **kw):
+        window_sec = self.classic_max_size / fps  # Detector.py:254: the argument is ignored
+        if int(window_sec * fps) != self.classic_max_size:
+            raise NotImplementedError(f"fps={fps}: int((4/fps)*fps) != 4 -- the reference's window collapses to 3 "
+                                      "frames there and its frame indices alias (Detector.py:254-261); not reproduced")
+        super().__init__(window_sec, fps, mask, num_cls, cfg, logger, _detector=1, **kw)
+        self.linesp_ext = []
+        self._dst_cache = None
+
+    def _result(self, i: int):
+        eng = self._eng
+        fi = eng.infos[i]
+        if fi.lines_num > MAX_LINES:
+            raise _lib.MetDetError(f"{fi.lines_num} Hough segments in one frame exceed the library's capacity of {MAX_LINES}")
+        self.bi_threshold = fi.bi_threshold
+        self.bi_threshold_float = fi.bi_threshold_float
+        self._snr = fi.snr
+        if fi.timer < self.stack_maxsize:
+            return [], []  # fewer than four frames: LineDetector.detect() (Detector.py:222-223, :264-265)
+        lines = eng.raw[i, :fi.n_raw].copy() if fi.n_raw else []
+        cls_pred = np.zeros((len(lines), self.num_cls))
+        cls_pred[:, 0] = 1
+        return lines, cls_pred
+
+    def detect(self):
+        eng = self._eng
+        check(eng.lib.mdb_detect(eng.handle, C.byref(eng.infos[0]), _ptr(eng.lines), _ptr(eng.prob),
+                                 _ptr(eng.raw)), "detect")
+        self._dst_cache = None
+        lines, cls_pred = self._result(0)
+        self.linesp_ext = lines
+        return lines, cls_pred
+
+    @property
+    def dst(self) -> np.ndarray:
+        """The thresholded, dilated difference mask HoughLinesP saw (a local of detect() in the
+        reference, Detector.py:274-281; zeros before the fourth frame)."""
+        if self._dst_cache is None:
+            out = np.empty((self._eng.H, self._eng.W), np.uint8)
+            check(self._eng.lib.mdb_get_dst(self._eng.handle, _ptr(out), 0), "dst")
+            self._dst_cache = out
+        return self._dst_cache
+
+    def detect_many(self, frames, *, on_device: bool = False, return_dst: bool = False):
+        """`[ (self.update(f), self.detect())[1] for f in frames ]` in one library call."""
+        eng = self._eng
+        if on_device:
+            ptr, T = frames
+        else:
+            frames = eng.check_frame(np.asarray(frames))
+            if frames.ndim != 3:
+                raise ValueError("frames must be (T, H, W)")
+            T, ptr = len(frames), frames.ctypes.data
+        if T == 0:
+            return []
+        if T > eng.max_batch:
+            raise ValueError(f"T={T} exceeds max_batch={eng.max_batch} given at construction")
+        dst_out = np.empty((T, eng.H, eng.W), np.uint8) if return_dst else None
+        check(eng.lib.mdb_detect_batch(eng.handle, ptr, T, int(on_device), C.byref(eng.infos), _ptr(eng.lines),
+                                       _ptr(eng.prob), _ptr(eng.raw), _ptr(dst_out), 0), "detect_many")
+        self._timer += T
+        self._dst_cache = None
+        self.last_infos = [dict(timer=fi.timer, bi_threshold=fi.bi_threshold, n_on=fi.n_on,
+                                bi_threshold_float=fi.bi_threshold_float, snr=fi.snr, lines_num=fi.lines_num)
+                           for fi in eng.infos[:T]]
+        res = [self._result(i) for i in range(T)]
+        self.linesp_ext = res[-1][0]
+        return (res, dst_out) if return_dst else res
+
+    def visu(self):
+        raise NotImplementedError  # as the reference (Detector.py:298-299)
 
 
 class M3Detector(LineDetector):

@@ -232,6 +232,58 @@ def case_hough():
     print("hough: 40 masks, lines per mask", [len(x) for x in outs])
 
 
+def run_classic_case(name, frames, mask, fps, cfg_tuple, hough):
+    """Real MetLib.Detector.ClassicDetector (Detector.py:245-299) trajectory."""
+    from MetLib.Detector import ClassicDetector
+    adaptive, init_value, sens, area, interval = cfg_tuple
+    cfg = BinaryCfg(BinaryCoreCfg(adaptive, init_value, sens, area, interval), HoughLineCfg(*hough), DynamicCfg(False, 5))
+    det = ClassicDetector(window_sec=1.0, fps=fps, mask=mask, num_cls=10, cfg=cfg, logger=BaseMetLog())
+    assert det.stack_maxsize == 4
+    T, H, W = frames.shape
+    thr, thrf, snr, raw, cls0 = [], [], [], [], []
+    masks = np.zeros((T, (H * W + 7) // 8), np.uint8)
+    for t in range(T):
+        det.update(frames[t])
+        lines, cp = det.detect()
+        thr.append(int(det.bi_threshold)); thrf.append(float(det.bi_threshold_float)); snr.append(float(det.stack.snr))
+        lines = np.asarray(lines, np.int32).reshape(-1, 4)
+        raw.append(lines)
+        cp = np.asarray(cp, np.float64).reshape(-1, 10)
+        assert len(cp) == len(lines) and (len(cp) == 0 or (np.all(cp[:, 0] == 1) and np.all(cp[:, 1:] == 0)))
+        if t >= 3:
+            # the reference keeps `dst` local to detect(): recompute it here from the detector's own ring
+            # and threshold with the same cv2 calls (Detector.py:268-281) to record the mask as well
+            sw, ci = det.stack.sliding_window, det.stack.cur_index
+            d23 = cv2.threshold(cv2.absdiff(sw[ci - 1], sw[ci]), det.bi_threshold, 255, cv2.THRESH_BINARY)[1]
+            d23 = 255 - cv2.dilate(d23, det.cv_op)
+            dd = cv2.absdiff(cv2.bitwise_and(d23, sw[ci - 3]), cv2.bitwise_and(d23, sw[ci - 2]))
+            dd = cv2.dilate(cv2.threshold(dd, det.bi_threshold, 255, cv2.THRESH_BINARY)[1], det.cv_op)
+            lp = cv2.HoughLinesP(dd, rho=1, theta=np.pi / 180, threshold=hough[0], minLineLength=hough[1], maxLineGap=hough[2])
+            assert np.array_equal(lines, np.zeros((0, 4), np.int32) if lp is None else lp[:, 0, :])
+            masks[t] = np.packbits(dd.reshape(-1) > 0)
+    r, ro = ragged(raw, 4, np.int32)
+    path = os.path.join(HERE, f"classic_{name}.npz")
+    np.savez_compressed(path, frames=frames, mask=mask, fps=fps, cfg=np.array([adaptive, init_value, area, interval], np.float64),
+                        sens=sens, hough=np.array(hough), bi_threshold=np.array(thr), bi_threshold_float=np.array(thrf),
+                        snr=np.array(snr), dst_bits=masks, raw_lines=r, raw_offs=ro)
+    print("classic", name, frames.shape, "thr", sorted(set(thr)), "frames with lines", sum(len(x) > 0 for x in raw),
+          "max lines", max(len(x) for x in raw))
+
+
+def case_classic():
+    W, H, FPS, T = 320, 240, 30, 50
+    frames = synth.make_stream(T, W, H, FPS, speed_scale=3.0, thickness=2)
+    run_classic_case("synth_320x240", frames, np.ones((H, W), np.uint8), FPS, (True, 7, "normal", 0.1, 2), (10, 10, 10))
+    W, H, FPS, T = 203, 157, 25, 40
+    frames = synth.make_stream(T, W, H, FPS, speed_scale=2.0, thickness=2, sigma=3.0)
+    mask = np.ones((H, W), np.uint8); mask[:30, :50] = 0
+    run_classic_case("odd_203x157_mask", frames * mask[None], mask, FPS, (True, 7, "high", 0.2, 1), (8, 8, 3))
+    rng = np.random.default_rng(3)
+    W, H, T = 256, 160, 12
+    frames = rng.integers(0, 50, (T, H, W)).astype(np.uint8)
+    run_classic_case("dense_256x160_fixed", frames, np.ones((H, W), np.uint8), 30, (False, 20, "normal", 0.1, 2), (10, 10, 10))
+
+
 def case_preproc():
     """Loader preprocessing by the reference's own Transform (MetLib/imgproc.py:70-139) and
     MergeFunction.max (MetLib/utils.py:203-204): resize -> BGR2GRAY -> mask, exp_frame merge."""
@@ -266,7 +318,7 @@ def case_preproc():
     np.savez_compressed(os.path.join(HERE, "preproc.npz"), names=np.array([c[0] for c in cases]), **out)
 
 
-CASES = dict(preproc=case_preproc, synth_small=case_synth_small, synth_dy_mask=case_synth_dy_mask, odd=case_odd_size,
+CASES = dict(preproc=case_preproc, classic=case_classic, synth_small=case_synth_small, synth_dy_mask=case_synth_dy_mask, odd=case_odd_size,
              dense=case_fixed_thr_dense, low=case_low_sens, clip=case_real_clip, nms=case_nms,
              sw=case_sliding_window, hough=case_hough)
 
