@@ -126,26 +126,36 @@ classic_spatial_kernel(const uint32_t *__restrict__ abits, const uint32_t *__res
     }
 }
 
-// bits -> u8 mask (0 / 255) + on-pixel count and list; bits beyond the row end are masked off here
+// bits -> u8 mask (0 / 255) + on-pixel count and list; one thread per 32-pixel word; bits beyond the row
+// end are masked off here
+template <bool ALIGNED>
 __global__ void __launch_bounds__(256)
 classic_expand_kernel(const uint32_t *__restrict__ dbits, int W, int H, int Wb, uint8_t *__restrict__ dst,
                       unsigned *__restrict__ npoints, uint32_t *__restrict__ points, int cap) {
-    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, t = blockIdx.z;
-    const bool inside = x < W;
-    int on = 0;
-    if (inside) {
-        on = (dbits[((size_t)t * H + y) * Wb + (x >> 5)] >> (x & 31)) & 1u;
-        dst[((size_t)t * H + y) * W + x] = on ? 255 : 0;
+    const int idx = blockIdx.x * 256 + threadIdx.x, t = blockIdx.y;
+    if (idx >= H * Wb) return;
+    const int wx = idx % Wb, y = idx / Wb;
+    const int npx = min(32, W - wx * 32);
+    unsigned bits = dbits[(size_t)t * H * Wb + idx];
+    if (npx < 32) bits &= (1u << npx) - 1u;
+    uint8_t *o = dst + ((size_t)t * H + y) * W + (size_t)wx * 32;
+    if (ALIGNED && npx == 32) {
+        uint4 *o4 = reinterpret_cast<uint4 *>(o);
+        o4[0] = make_uint4(nib_to_bytes(bits & 15u), nib_to_bytes((bits >> 4) & 15u), nib_to_bytes((bits >> 8) & 15u),
+                           nib_to_bytes((bits >> 12) & 15u));
+        o4[1] = make_uint4(nib_to_bytes((bits >> 16) & 15u), nib_to_bytes((bits >> 20) & 15u),
+                           nib_to_bytes((bits >> 24) & 15u), nib_to_bytes(bits >> 28));
+    } else {
+        for (int j = 0; j < npx; j++) o[j] = ((bits >> j) & 1u) ? 255 : 0;
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, on);
-    if (bal) {
-        const int lane = threadIdx.x & 31;
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(npoints + t, __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (on) {
-            const unsigned slot = base + __popc(bal & ((1u << lane) - 1));
-            if (slot < (unsigned)cap) points[(size_t)t * cap + slot] = ((unsigned)y << 16) | (unsigned)x;
+    if (bits) {
+        unsigned slot = atomicAdd(npoints + t, __popc(bits));
+        unsigned ob = bits;
+        while (ob) {
+            const int bpos = __ffs(ob) - 1;
+            ob &= ob - 1;
+            if (slot < (unsigned)cap) points[(size_t)t * cap + slot] = ((unsigned)y << 16) | (unsigned)(wx * 32 + bpos);
+            slot++;
         }
     }
 }

@@ -419,8 +419,12 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
         CK(cudaStreamWaitEvent(h->stream2, c.ev_f1, 0));
         CK(cudaEventRecord(c.ev_d0, h->stream2));
         c.dst_dirty = true;
-        classic_expand_kernel<<<dim3((h->W + 255) / 256, h->H, T), 256, 0, h->stream2>>>(
-            db, h->W, h->H, h->Wb, c.d_dst, c.d_npoints, c.d_points, MDB_POINT_CAP);
+        if (h->W % 16 == 0)
+            classic_expand_kernel<true><<<dim3((nthreads + 255) / 256, T), 256, 0, h->stream2>>>(
+                db, h->W, h->H, h->Wb, c.d_dst, c.d_npoints, c.d_points, MDB_POINT_CAP);
+        else
+            classic_expand_kernel<false><<<dim3((nthreads + 255) / 256, T), 256, 0, h->stream2>>>(
+                db, h->W, h->H, h->Wb, c.d_dst, c.d_npoints, c.d_points, MDB_POINT_CAP);
         nl = 3;
     } else if (h->use_stream_kernel && stream_kernel_supported(h->sk, T)) {
         if (c.dst_dirty) {  // the generic kernel wrote this buffer last: resynchronise buffer and bitmap
