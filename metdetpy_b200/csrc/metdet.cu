@@ -64,6 +64,7 @@ struct BatchCtx {
     int *d_nlines = nullptr;         // [T]
     // ev_f0..ev_f1: temporal+act on the front stream; ev_d0..ev_d1: dst on the back stream
     cudaEvent_t ev_f0 = nullptr, ev_f1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_thr = nullptr;    // thresholds of this batch are on the device (scalar stream)
     cudaEvent_t tl[12] = {};         // optional timeline marks (debug)
     int T = 0;  // 0: free
     long long timer0 = 0;
@@ -79,8 +80,10 @@ struct mdb_detector {
     // stream: noise, thresholds, temporal, act | stream2: dst | stream3: Hough, result copy-out |
     // cstream: host->device frames.  The stages of consecutive batches overlap (two batches in flight):
     // the write-only dst pass and the shared-memory-bound Hough pass hide under the ALU-bound temporal pass.
-    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr, cstream = nullptr;
-    cudaEvent_t ev_copy = nullptr;
+    // sstream ("scalar"): noise samples + threshold recurrence + history copy of batch k+1 run beside batch k's temporal pass
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr, cstream = nullptr, sstream = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_front = nullptr;
+    bool front_dirty = false;        // the per-frame API touched the scalar state on the front stream
     // device
     uint8_t *d_ring = nullptr, *d_mask = nullptr;
     uint32_t *d_act = nullptr;  // act bit-frame ring [RA][H][Wb]
@@ -147,6 +150,7 @@ static void free_all(mdb_detector *h) {
     if (h->stream2) cudaStreamSynchronize(h->stream2);
     if (h->stream3) cudaStreamSynchronize(h->stream3);
     if (h->cstream) cudaStreamSynchronize(h->cstream);
+    if (h->sstream) cudaStreamSynchronize(h->sstream);
     void *dev[] = {h->d_ring, h->d_mask, h->d_act, h->d_state, h->d_noise, h->d_accum,
                    h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_prof, h->d_cbits};
     for (void *p : dev)
@@ -167,8 +171,11 @@ static void free_all(mdb_detector *h) {
         if (c.ev_d0) cudaEventDestroy(c.ev_d0);
         if (c.ev_d1) cudaEventDestroy(c.ev_d1);
         if (c.ev_done) cudaEventDestroy(c.ev_done);
+        if (c.ev_thr) cudaEventDestroy(c.ev_thr);
     }
     if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+    if (h->ev_front) cudaEventDestroy(h->ev_front);
+    if (h->sstream) cudaStreamDestroy(h->sstream);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream3) cudaStreamDestroy(h->stream3);
@@ -256,7 +263,9 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
         CKH(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_hi));
         CKH(cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, prio_hi));
         CKH(cudaStreamCreateWithPriority(&h->cstream, cudaStreamNonBlocking, prio_lo));
+        CKH(cudaStreamCreateWithPriority(&h->sstream, cudaStreamNonBlocking, prio_hi));
     }
+    CKH(cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming));
     CKH(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
     const size_t bm_words = (h->HW + 31) / 32;
     h->Wb = (h->W + 31) / 32;
@@ -311,6 +320,7 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
         CKH(cudaEventCreate(&c.ev_d0));
         CKH(cudaEventCreate(&c.ev_d1));
         CKH(cudaEventCreateWithFlags(&c.ev_done, cudaEventDisableTiming));
+        CKH(cudaEventCreateWithFlags(&c.ev_thr, cudaEventDisableTiming));
     }
 
     // scalar state: LineDetector.__init__ (Detector.py:204-209), SNR_SW.__init__ (:58-61)
@@ -368,12 +378,13 @@ static int copy_to_ring(mdb_detector *h, const uint8_t *frames, int first, int T
     return MDB_OK;
 }
 
-static int launch_noise_thr(mdb_detector *h, BatchCtx &bc, const FrameSrc &src, int T, long long timer0) {
+static int launch_noise_thr(mdb_detector *h, BatchCtx &bc, const FrameSrc &src, int T, long long timer0,
+                            cudaStream_t st) {
     const mdb_config &c = h->cfg;
     const int rh = c.roi[2] - c.roi[0], rw = c.roi[3] - c.roi[1];
     const long long std_interval = (long long)c.nz_interval * h->n;
-    TL(bc, 0, h->stream);
-    CK(cudaMemsetAsync(h->d_noise, 0, (size_t)T * 2 * sizeof(unsigned long long), h->stream));
+    TL(bc, 0, st);
+    CK(cudaMemsetAsync(h->d_noise, 0, (size_t)T * 2 * sizeof(unsigned long long), st));
     const int gx = std::max(1, std::min((rh * rw + 255) / 256, 592));
     SampleList sl;
     sl.count = 0;
@@ -385,13 +396,13 @@ static int launch_noise_thr(mdb_detector *h, BatchCtx &bc, const FrameSrc &src, 
         }
     }
     if (sl.count != 0)
-        noise_sample_kernel<<<dim3(gx, sl.count < 0 ? T : sl.count), 256, 0, h->stream>>>(
+        noise_sample_kernel<<<dim3(gx, sl.count < 0 ? T : sl.count), 256, 0, st>>>(
             src, h->W, h->n, timer0, std_interval, c.roi[0], c.roi[1], rh, rw, h->d_noise, 0, sl);
-    threshold_kernel<<<1, 32, 0, h->stream>>>(h->d_state, h->d_noise, T, timer0, h->n, std_interval,
+    threshold_kernel<<<1, 32, 0, st>>>(h->d_state, h->d_noise, T, timer0, h->n, std_interval,
                                              (long long)rh * rw, c.adaptive, c.sensitivity, bc.d_thr,
                                              bc.d_thrf, bc.d_snr);
     h->launches += 2;
-    TL(bc, 1, h->stream);
+    TL(bc, 1, st);
     CK(cudaGetLastError());
     return MDB_OK;
 }
@@ -589,14 +600,25 @@ static int finish_batch(mdb_detector *h, const BatchCtx &c, mdb_frame_info *info
 
 static int in_flight(const mdb_detector *h) { return (int)(h->submitted - h->collected); }
 
+// the per-frame calls and the read-backs work on the front stream: order it after whatever the scalar
+// stream still has queued from batched calls (history copy of the last batch)
+static int front_after_scalar(mdb_detector *h) {
+    CK(cudaEventRecord(h->ev_front, h->sstream));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_front, 0));
+    return MDB_OK;
+}
+
 // ---- per-frame API ---------------------------------------------------------------------------
 extern "C" int mdb_update(mdb_handle h, const uint8_t *frame, int on_device) {
     if (!h || !frame) return fail(MDB_ERR_INVALID, "mdb_update: null argument");
     if (in_flight(h)) return fail(MDB_ERR_STATE, "mdb_update: a submitted batch has not been collected");
     CK(cudaSetDevice(h->cfg.device));
-    int rc = copy_to_ring(h, frame, 0, 1, h->timer, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream);
+    int rc = front_after_scalar(h);
     if (rc) return rc;
-    rc = launch_noise_thr(h, h->ctx[0], frame_src(h, nullptr, 0), 1, h->timer);
+    rc = copy_to_ring(h, frame, 0, 1, h->timer, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream);
+    if (rc) return rc;
+    rc = launch_noise_thr(h, h->ctx[0], frame_src(h, nullptr, 0), 1, h->timer, h->stream);
+    h->front_dirty = true;
     if (rc) return rc;
     h->timer += 1;
     if (!on_device) CK(cudaStreamSynchronize(h->stream));  // caller may reuse its buffer on return
@@ -643,6 +665,11 @@ static int submit_impl(mdb_handle h, const uint8_t *frames, int T, int on_device
     BatchCtx &c = h->ctx[h->submitted % NCTX];
     const long long timer0 = h->timer;
     FrameSrc src;
+    if (h->front_dirty) {  // per-frame calls updated the scalar state on the front stream: order the scalar stream after them
+        CK(cudaEventRecord(h->ev_front, h->stream));
+        CK(cudaStreamWaitEvent(h->sstream, h->ev_front, 0));
+        h->front_dirty = false;
+    }
     if (on_device) {
         src = frame_src(h, frames, timer0);  // zero-copy: kernels read the caller's buffer
     } else {
@@ -654,7 +681,7 @@ static int submit_impl(mdb_handle h, const uint8_t *frames, int T, int on_device
         int rc = copy_to_ring(h, frames, 0, T, timer0, cudaMemcpyHostToDevice, h->cstream);
         if (rc) return rc;
         CK(cudaEventRecord(h->ev_copy, h->cstream));
-        CK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+        CK(cudaStreamWaitEvent(h->sstream, h->ev_copy, 0));
         src = frame_src(h, nullptr, 0);
     }
     if (h->submitted >= 2) {
@@ -663,24 +690,33 @@ static int submit_impl(mdb_handle h, const uint8_t *frames, int T, int on_device
         BatchCtx &prev2 = h->ctx[(h->submitted + NCTX - 2) % NCTX];
         CK(cudaStreamWaitEvent(h->stream, prev2.ev_d1, 0));
     }
+    // scalar stream: thresholds of this batch (noise samples + EMA recurrence) and, for device input, the copy
+    // of its last n-1 frames into the ring (history of the next batch).  None of it depends on the previous
+    // batch's mask chain, so it runs beside that batch's temporal pass instead of in front of this one's.
     int rc;
     if (thr) {  // thresholds supplied by the caller (time-sharded streams): no local EMA recurrence
-        CK(cudaMemcpyAsync(c.d_thr, thr, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(c.d_thrf, thrf, T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(c.d_snr, snr, T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(c.d_thr, thr, T * sizeof(int32_t), cudaMemcpyHostToDevice, h->sstream));
+        CK(cudaMemcpyAsync(c.d_thrf, thrf, T * sizeof(double), cudaMemcpyHostToDevice, h->sstream));
+        CK(cudaMemcpyAsync(c.d_snr, snr, T * sizeof(double), cudaMemcpyHostToDevice, h->sstream));
     } else {
-        rc = launch_noise_thr(h, c, src, T, timer0);
+        rc = launch_noise_thr(h, c, src, T, timer0, h->sstream);
         if (rc) return rc;
     }
-    rc = launch_fused(h, c, src, T, timer0, h->dy_timer);
-    if (rc) return rc;
+    CK(cudaEventRecord(c.ev_thr, h->sstream));
     if (on_device) {  // keep the last n-1 frames as history for the next batch
         const int keep = std::min(T, h->n - 1);
         if (keep > 0) {
-            rc = copy_to_ring(h, frames, T - keep, T, timer0, cudaMemcpyDeviceToDevice, h->stream);
+            // the slots they land on belonged to the batch before the previous one: if that one was host-fed its
+            // frames live there and its front-stream kernels must have read them
+            BatchCtx &prev2 = h->ctx[(h->submitted + NCTX - 2) % NCTX];
+            if (h->submitted >= 2) CK(cudaStreamWaitEvent(h->sstream, prev2.ev_f1, 0));
+            rc = copy_to_ring(h, frames, T - keep, T, timer0, cudaMemcpyDeviceToDevice, h->sstream);
             if (rc) return rc;
         }
     }
+    CK(cudaStreamWaitEvent(h->stream, c.ev_thr, 0));
+    rc = launch_fused(h, c, src, T, timer0, h->dy_timer);
+    if (rc) return rc;
     rc = launch_hough_and_copy(h, c, T);
     if (rc) return rc;
     c.T = T;
@@ -816,6 +852,10 @@ extern "C" int mdb_get_stack(mdb_handle h, uint8_t *max_out, uint8_t *mean_out, 
     CK(cudaMalloc((void **)&dsum, h->HW * 4));
     const long long t = h->timer - 1;
     const int L = (int)std::min<long long>(h->n, h->timer);
+    {
+        int rc = front_after_scalar(h);
+        if (rc) { cudaFree(dmx); cudaFree(dmean); cudaFree(dsum); return rc; }
+    }
     stack_readback_kernel<<<592, 256, 0, h->stream>>>(frame_src(h, nullptr, 0), h->HW, h->n, t, L, dmx, dmean, dsum);
     h->launches += 1;
     cudaError_t e = cudaGetLastError();

@@ -33,3 +33,17 @@ d2 = M3Detector(3 / FPS + 1e-9, FPS, np.ones((H, W), np.uint8), 10, cfg2, None, 
 d2.detect_many(dense)
 print("dense n_on", [i["n_on"] for i in d2.last_infos])
 print("maxstack", stacker.merge_max(frames[:5]).sum())
+# loader preprocessing (resize -> gray -> mask -> exposure merge), ClassicDetector (aligned and odd widths)
+from metdetpy_b200.imgproc import Transform
+from metdetpy_b200.detector import ClassicDetector
+bgr = rng.integers(0, 256, (5, 50, 70, 3), dtype=np.uint8)
+tr = Transform(); tr.opencv_resize([33, 21]); tr.opencv_BGR2GRAY(); tr.mask_with(np.ones((21, 33), np.uint8))
+print("preproc", tr.exec_transform_many(bgr, 2).sum()); tr.close()
+for Wc in (256, 203):
+    fr = synth.make_stream(12, Wc, 96, FPS, speed_scale=3.0, thickness=2)
+    cd = ClassicDetector(1.0, FPS, np.ones((96, Wc), np.uint8), 10, cfg, None, max_batch=5)
+    n = 0
+    for s in range(0, 12, 5):
+        n += sum(len(r[0]) for r in cd.detect_many(fr[s:s + 5]))
+    cd.update(fr[0]); cd.detect(); _ = cd.dst
+    print("classic", Wc, "lines", n); cd.close()
