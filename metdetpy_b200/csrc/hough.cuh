@@ -138,9 +138,13 @@ ppht_order_kernel(int T, int cap, const unsigned *__restrict__ npoints, uint16_t
 // streak up to ~800 px long does) the whole PPHT of the frame runs on-chip.  Frames whose table
 // would not fit are flagged (-2) for tier 2.
 // ------------------------------------------------------------------------------------------
-#define HOUGH_TABLE_BYTES (186 * 1024)       // tier 1b: one CTA per SM
-#define HOUGH_TABLE_BYTES_SMALL (92 * 1024)  // tier 1a: two CTAs per SM
+#define HOUGH_TABLE_BYTES (184 * 1024)       // tier 1b: one CTA per SM
+#define HOUGH_TABLE_BYTES_SMALL (90 * 1024)  // tier 1a: two CTAs per SM
+// per-point shared memory of the tier-1 kernel: key u32, visit order u16, inverse order u16, line pixels u16,
+// removed bits by sorted position and by visit position
+#define HOUGH1_POINT_BYTES(cap) ((cap) * 10 + (cap) / 4)
 #define HOUGH_CAP_SMALL 2048
+#define HOUGH_SPEC 4  // points whose votes are taken per barrier in the shared-memory tiers
 
 __global__ void __launch_bounds__(HOUGH_THREADS)
 hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
@@ -153,10 +157,12 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
     uint32_t *keys = h_sm;                                            // [lcap]
     uint16_t *idx = reinterpret_cast<uint16_t *>(keys + lcap);        // [lcap] visiting order
     uint16_t *wl = idx + lcap;                                        // [lcap] pixels of the current line
-    uint32_t *rm = reinterpret_cast<uint32_t *>(wl + lcap);           // [lcap/32] removed bits
-    int16_t *table = reinterpret_cast<int16_t *>(rm + lcap / 32);     // [table_bytes / 2]
+    uint16_t *inv = wl + lcap;                                        // [lcap] sorted position -> visit position
+    uint32_t *rm = reinterpret_cast<uint32_t *>(inv + lcap);          // [lcap/32] removed bits by sorted position
+    uint32_t *rmv = rm + lcap / 32;                                   // [lcap/32] removed bits by visit position
+    int16_t *table = reinterpret_cast<int16_t *>(rmv + lcap / 32);    // [table_bytes / 2]
     const int fail_flag = stage == 0 ? -2 : -3;
-    __shared__ int s_red[2][HOUGH_THREADS / 32];
+    __shared__ int s_red[2][HOUGH_THREADS / 32][HOUGH_SPEC];
     __shared__ unsigned s_on[HOUGH_THREADS / 32], s_inb[HOUGH_THREADS / 32];
     __shared__ int s_ctl[8];
     __shared__ int s_base[MDB_HOUGH_ANGLES + 1];
@@ -187,8 +193,12 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
         while (np2 < N) np2 <<= 1;
         for (int i = tid; i < np2; i += HOUGH_THREADS)
             keys[i] = i < N ? points[(size_t)t * P.cap + i] : 0xFFFFFFFFu;
-        for (int i = tid; i < (N + 31) / 32; i += HOUGH_THREADS) rm[i] = 0;
-        for (int i = tid; i < N; i += HOUGH_THREADS) idx[i] = order[(size_t)t * P.cap + i];
+        for (int i = tid; i < (N + 31) / 32; i += HOUGH_THREADS) rm[i] = rmv[i] = 0;
+        for (int i = tid; i < N; i += HOUGH_THREADS) {
+            const uint16_t o = order[(size_t)t * P.cap + i];
+            idx[i] = o;
+            inv[o] = (uint16_t)i;
+        }
         if (tid == 0) { s_ctl[2] = 0; s_ctl[3] = 0; }
         __syncthreads();
         bitonic_sort_u32(keys, np2, tid, HOUGH_THREADS);
@@ -201,7 +211,10 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
                 const int r = rho_cs(k & 0xffffu, k >> 16, my_c, my_s);
                 mn = min(mn, r); mx = max(mx, r);
             }
-            s_base[tid + 1] = mx - mn + 1;
+            // row length in cells, padded to an ODD number of 32-bit words: thread n's cell address is roughly affine
+            // in n (row start + projection), and an even word stride between neighbouring rows would put a whole
+            // warp's 32 votes into a handful of shared-memory banks
+            s_base[tid + 1] = ((((mx - mn + 1) + 1) >> 1) | 1) << 1;
         }
         if (tid == 0) s_base[0] = 0;
         __syncthreads();
@@ -223,33 +236,74 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
         int par = 0;
         bool sat = false;
         p_setup = clock64() - pc0;
-        int pi_n = idx[N - 1];
-        uint32_t key_n = keys[pi_n];
-        for (int s = N - 1; s >= 0; s--) {
+        // Votes are taken HOUGH_SPEC points at a time: thread n adds the votes of the next (not yet removed)
+        // points to its own row one after the other, reading each cell right after its own increment, so every
+        // point's arg-max is the one the sequential algorithm sees; the four arg-max reductions share one
+        // barrier.  Lines are rare (a few per frame): when point j of a group yields one, the votes of the points
+        // after it are taken back and the scan resumes right behind j, after the line has been removed.
+        int s = N - 1;
+        for (;;) {
             long long c0 = clock64();
-            // candidate s was fetched one iteration ago; fetch candidate s-1 now (keys / order never change)
-            const int pi = pi_n;
-            const uint32_t key = key_n;
-            if (s > 0) { pi_n = idx[s - 1]; key_n = keys[pi_n]; }
-            if ((rm[pi >> 5] >> (pi & 31)) & 1u) continue;  // removed by an earlier line (uniform)
-            const int x = key & 0xffffu, y = key >> 16;
-            int best = INT_MIN;
-            if (tid < MDB_HOUGH_ANGLES) {
-                const int r = rho_cs(x, y, my_c, my_s);
-                const int v = (int)myrow[r] + 1;
-                myrow[r] = (int16_t)v;
-                sat |= v >= 32767;
-                best = v * 256 + (255 - tid);  // max value first, lowest angle on ties
+            int cs[HOUGH_SPEC], cnt = 0;
+            uint32_t ck[HOUGH_SPEC];
+#pragma unroll
+            for (int j = 0; j < HOUGH_SPEC; j++) { cs[j] = -1; ck[j] = 0; }
+            while (cnt < HOUGH_SPEC && s >= 0) {  // uniform: every thread walks the same bit list
+                // not yet removed visit positions <= s of this 32-position word, highest first
+                const unsigned m = ~rmv[s >> 5] & (0xffffffffu >> (31 - (s & 31)));
+                if (!m) { s = (s & ~31) - 1; continue; }
+                s = (s & ~31) + 31 - __clz(m);
+#pragma unroll
+                for (int j = 0; j < HOUGH_SPEC; j++)
+                    if (j == cnt) cs[j] = s;
+                cnt++;
+                s--;
             }
-            best = __reduce_max_sync(0xffffffffu, best);
-            if (lane == 0) s_red[par][warp] = best;
+#pragma unroll
+            for (int j = 0; j < HOUGH_SPEC; j++)
+                if (j < cnt) ck[j] = keys[idx[cs[j]]];
+            if (cnt == 0) break;
+            int bj[HOUGH_SPEC], rj[HOUGH_SPEC];
+#pragma unroll
+            for (int j = 0; j < HOUGH_SPEC; j++) { bj[j] = INT_MIN; rj[j] = 0; }
+            if (tid < MDB_HOUGH_ANGLES) {
+#pragma unroll
+                for (int j = 0; j < HOUGH_SPEC; j++)
+                    if (j < cnt) {
+                        const int r = rho_cs(ck[j] & 0xffffu, ck[j] >> 16, my_c, my_s);
+                        const int v = (int)myrow[r] + 1;
+                        myrow[r] = (int16_t)v;
+                        sat |= v >= 32767;
+                        bj[j] = v * 256 + (255 - tid);  // max value first, lowest angle on ties
+                        rj[j] = r;
+                    }
+            }
+#pragma unroll
+            for (int j = 0; j < HOUGH_SPEC; j++) {
+                bj[j] = __reduce_max_sync(0xffffffffu, bj[j]);
+                if (lane == 0) s_red[par][warp][j] = bj[j];
+            }
             __syncthreads();
 #pragma unroll
-            for (int k = 0; k < HOUGH_THREADS / 32; k++) best = max(best, s_red[par][k]);
+            for (int j = 0; j < HOUGH_SPEC; j++)
+#pragma unroll
+                for (int k = 0; k < HOUGH_THREADS / 32; k++) bj[j] = max(bj[j], s_red[par][k][j]);
             par ^= 1;
-            p_vote += clock64() - c0; n_vote++;
-            if ((best >> 8) < P.threshold) continue;
+            int trig = -1;
+#pragma unroll
+            for (int j = 0; j < HOUGH_SPEC; j++)
+                if (trig < 0 && j < cnt && (bj[j] >> 8) >= P.threshold) trig = j;
+            p_vote += clock64() - c0; n_vote += trig < 0 ? cnt : trig + 1;
+            if (trig < 0) continue;
             c0 = clock64(); n_line++;
+            uint32_t key = 0;
+            int best = 0;
+#pragma unroll
+            for (int j = 0; j < HOUGH_SPEC; j++) {
+                if (j == trig) { key = ck[j]; best = bj[j]; s = cs[j] - 1; }
+                if (j > trig && j < cnt && tid < MDB_HOUGH_ANGLES) myrow[rj[j]] = (int16_t)((int)myrow[rj[j]] - 1);
+            }
+            const int x = key & 0xffffu, y = key >> 16;
             const int max_n = 255 - (best & 255);
 
             // ---- line: find both ends (mask unchanged meanwhile), 256 steps per round ----------
@@ -307,6 +361,8 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
                     const int f = find_key(keys, N, ((unsigned)i1 << 16) | (unsigned)j1);
                     if (f >= 0 && !((rm[f >> 5] >> (f & 31)) & 1u)) {
                         atomicOr(&rm[f >> 5], 1u << (f & 31));
+                        const int sv = inv[f];
+                        atomicOr(&rmv[sv >> 5], 1u << (sv & 31));
                         if (good) wl[atomicAdd(&s_ctl[1], 1)] = (uint16_t)f;
                     }
                 }

@@ -17,7 +17,8 @@
 #include "stream_kernel.cuh"
 
 #define HOUGH_SMEM_BYTES (MDB_POINT_CAP * 8 + MDB_POINT_CAP / 8)  // keys u32 + order u16 + line u16 + removed bits
-#define HOUGH_SMEM_SMALL (HOUGH_CAP_SMALL * 8 + HOUGH_CAP_SMALL / 8)
+#define HOUGH_SMEM_SMALL HOUGH1_POINT_BYTES(HOUGH_CAP_SMALL)   // tier 1a
+#define HOUGH_SMEM_LARGE HOUGH1_POINT_BYTES(MDB_POINT_CAP)     // tier 1b
 
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -346,7 +347,7 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     CKH(cudaFuncSetAttribute(hough_tier2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              HOUGH_SMEM_BYTES));
     CKH(cudaFuncSetAttribute(hough_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             HOUGH_SMEM_BYTES + HOUGH_TABLE_BYTES));
+                             HOUGH_SMEM_LARGE + HOUGH_TABLE_BYTES));
     CKH(cudaStreamSynchronize(h->stream));
     {
         int rc = cfg->detector == 1 ? 0 : stream_state_init(h->sk, h->W, h->H, h->n, cfg->device, cfg->max_batch);
@@ -484,7 +485,7 @@ static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
     hough_smem_kernel<<<std::min(T, 2 * h->sm_count), HOUGH_THREADS, HOUGH_SMEM_SMALL + HOUGH_TABLE_BYTES_SMALL, h->stream3>>>(
         h->hp, T, c.d_npoints, c.d_points, c.d_order, c.d_lines, c.d_nlines, c.d_queue, h->d_prof,
         HOUGH_CAP_SMALL, HOUGH_TABLE_BYTES_SMALL, 0);
-    hough_smem_kernel<<<std::min(T, h->sm_count), HOUGH_THREADS, HOUGH_SMEM_BYTES + HOUGH_TABLE_BYTES, h->stream3>>>(
+    hough_smem_kernel<<<std::min(T, h->sm_count), HOUGH_THREADS, HOUGH_SMEM_LARGE + HOUGH_TABLE_BYTES, h->stream3>>>(
         h->hp, T, c.d_npoints, c.d_points, c.d_order, c.d_lines, c.d_nlines, c.d_queue + 1, h->d_prof,
         MDB_POINT_CAP, HOUGH_TABLE_BYTES, 1);
     TL(c, 5, h->stream3);
