@@ -35,9 +35,17 @@ __device__ __forceinline__ int rho_of(int x, int y, int n) {
 }
 
 // same, with the angle's cos/sin already in registers (thread n owns angle n: reading c_trig[2*n]
-// from every lane would serialise on the constant cache)
+// from every lane would serialise on the constant cache).  The int <-> float conversions are done with
+// magic-number adds instead of I2F / F2I: those run on the quarter-rate XU pipe, and 180 threads x
+// (votes + un-votes + range scan) made it the busiest unit of the kernel.  Exact: 0x4B000000 | v is the
+// float 2^23 + v for 0 <= v < 2^23, and adding 1.5 * 2^23 to |r| < 2^22 rounds to the nearest integer,
+// ties to even, exactly like cvRound / F2I.RN.
+__device__ __forceinline__ float u16_to_float(unsigned v) {
+    return __fsub_rn(__uint_as_float(0x4B000000u | v), 8388608.0f);
+}
 __device__ __forceinline__ int rho_cs(int x, int y, float c, float s) {
-    return __float2int_rn(__fadd_rn(__fmul_rn((float)x, c), __fmul_rn((float)y, s)));
+    const float r = __fadd_rn(__fmul_rn(u16_to_float((unsigned)x), c), __fmul_rn(u16_to_float((unsigned)y), s));
+    return __float_as_int(__fadd_rn(r, 12582912.0f)) - 0x4B400000;
 }
 
 __device__ __forceinline__ void bitonic_sort_u32(uint32_t *a, int npow2, int tid, int nthreads) {
@@ -249,15 +257,20 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
 #pragma unroll
             for (int j = 0; j < HOUGH_SPEC; j++) { cs[j] = -1; ck[j] = 0; }
             while (cnt < HOUGH_SPEC && s >= 0) {  // uniform: every thread walks the same bit list
-                // not yet removed visit positions <= s of this 32-position word, highest first
-                const unsigned m = ~rmv[s >> 5] & (0xffffffffu >> (31 - (s & 31)));
-                if (!m) { s = (s & ~31) - 1; continue; }
-                s = (s & ~31) + 31 - __clz(m);
+                // not yet removed visit positions <= s of this 32-position word, highest first; one load serves
+                // up to HOUGH_SPEC candidates
+                const int wbase = s & ~31;
+                unsigned m = ~rmv[s >> 5] & (0xffffffffu >> (31 - (s & 31)));
+                while (m && cnt < HOUGH_SPEC) {
+                    const int b = 31 - __clz(m);
+                    m ^= 1u << b;
 #pragma unroll
-                for (int j = 0; j < HOUGH_SPEC; j++)
-                    if (j == cnt) cs[j] = s;
-                cnt++;
-                s--;
+                    for (int j = 0; j < HOUGH_SPEC; j++)
+                        if (j == cnt) cs[j] = wbase + b;
+                    cnt++;
+                    s = wbase + b - 1;
+                }
+                if (!m) s = min(s, wbase - 1);
             }
 #pragma unroll
             for (int j = 0; j < HOUGH_SPEC; j++)
