@@ -68,6 +68,7 @@ struct BatchCtx {
     cudaEvent_t ev_thr = nullptr;    // thresholds of this batch are on the device (scalar stream)
     cudaEvent_t tl[12] = {};         // optional timeline marks (debug)
     int T = 0;  // 0: free
+    int bits_parity = 0;  // which predicate-bit buffer this batch uses
     long long timer0 = 0;
     long long seq = 0;
 };
@@ -449,7 +450,7 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
         sl.alist = c.d_alist; sl.acount = c.d_acount; sl.wlist = c.d_wlist; sl.wcount = c.d_wcount; sl.dense = c.d_dense;
         int rc = stream_kernel_launch(h->sk, src, timer0, dy0, T, h->cfg.dy_mask, c.d_thr, act_ring(h),
                                       c.d_dst, c.d_dstbits, c.d_npoints, c.d_points, MDB_POINT_CAP, sl, h->stream,
-                                      h->stream2, c.ev_f1, c.ev_d0, &nl);
+                                      h->stream2, c.ev_f1, c.ev_d0, (int)(c.bits_parity & 1), &nl);
         if (rc != 0) return fail(MDB_ERR_CUDA, "stream kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
         // generic per-frame kernel: the whole chain runs on the back stream, after the front stream's thresholds
@@ -716,6 +717,7 @@ static int submit_impl(mdb_handle h, const uint8_t *frames, int T, int on_device
         }
     }
     CK(cudaStreamWaitEvent(h->stream, c.ev_thr, 0));
+    c.bits_parity = (int)(h->submitted & 1);
     rc = launch_fused(h, c, src, T, timer0, h->dy_timer);
     if (rc) return rc;
     rc = launch_hough_and_copy(h, c, T);

@@ -35,7 +35,9 @@ struct StreamState {
     int force_strip = 0;    // test hook: act by the warp-strip kernel even when W % 128 == 0
     size_t t_smem_per_thread = 0;
     int sp_rows = 8;        // output rows per warp strip in the spatial kernel
-    uint32_t *d_bits = nullptr;  // [max_batch][H][W/32]
+    // predicate bits [max_batch][H][W/32], two buffers: batch k+1's temporal pass (front stream) writes one
+    // while batch k's act pass (back stream) still reads the other
+    uint32_t *d_bits = nullptr, *d_bits2 = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -248,7 +250,8 @@ temporal_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *__
 // ------------------------------------------------------------------------------------------
 static inline void stream_state_free(StreamState &s) {
     if (s.d_bits) cudaFree(s.d_bits);
-    s.d_bits = nullptr;
+    if (s.d_bits2) cudaFree(s.d_bits2);
+    s.d_bits = s.d_bits2 = nullptr;
     s.ok = 0;
 }
 
@@ -283,8 +286,10 @@ static inline int stream_state_init(StreamState &s, int W, int H, int n, int dev
     // the wider variant only pays when its ring still leaves >= 8 warps per SM
     const bool wide = (size_t)(2 * n + ST_K) * 16 * 32 * 8 <= budget;
     if (stream_state_config(s, wide ? 4 : 2) != 0 && stream_state_config(s, 2) != 0) return 0;
-    if (cudaMalloc((void **)&s.d_bits, (size_t)max_batch * H * (W / 32) * sizeof(uint32_t)) != cudaSuccess) {
+    if (cudaMalloc((void **)&s.d_bits, (size_t)max_batch * H * (W / 32) * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc((void **)&s.d_bits2, (size_t)max_batch * H * (W / 32) * sizeof(uint32_t)) != cudaSuccess) {
         cudaGetLastError();
+        stream_state_free(s);
         return 0;  // fall back to the generic per-frame kernel
     }
     s.sp_rows = 64;
@@ -306,19 +311,22 @@ static inline int stream_state_init(StreamState &s, int W, int H, int n, int dev
 
 static inline bool stream_kernel_supported(const StreamState &s, int T) { return s.ok && T >= 1 && T <= s.max_batch; }
 
-// Launches temporal + act (stream st1) and dst (stream st2, after `ev_act`) for frames
-// timer0 .. timer0+T-1 (dy indices dy0 ..).  The split lets the sparse dst pass overlap the
-// temporal pass of the NEXT batch.  Returns 0 / -1; *launches gets the number of kernel launches.
+// Launches the temporal pass (stream st1) and act + dst (stream st2, after `ev_f1`) for frames
+// timer0 .. timer0+T-1 (dy indices dy0 ..).  The split lets the spatial passes of batch k (ALU-bound bit
+// logic, list-driven dst) run beside the temporal pass of batch k+1, which leaves a third of the ALU pipe
+// and most of the register file idle.  `parity` selects the predicate-bit buffer.
+// Returns 0 / -1; *launches gets the number of kernel launches.
 static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long timer0, long long dy0, int T,
                                        int dy_on, const int *d_thr, ActRing ring, uint8_t *dst, uint32_t *dstbits,
                                        unsigned *npoints, uint32_t *points, int cap, SparseLists sl, cudaStream_t st1,
-                                       cudaStream_t st2, cudaEvent_t ev_f1, cudaEvent_t ev_d0, int *launches) {
+                                       cudaStream_t st2, cudaEvent_t ev_f1, cudaEvent_t ev_d0, int parity,
+                                       int *launches) {
+    uint32_t *const bits = parity ? s.d_bits2 : s.d_bits;
     const int HWG = (int)((size_t)s.W * s.H / (4 * s.t_wpt));  // pixel groups = threads
     const int nt = s.t_threads;
     const size_t smem = s.t_smem_per_thread * nt + (((size_t)2 * T + 15) & ~(size_t)15);
     const int grid = (HWG + nt - 1) / nt;
-    uint8_t *bits8 = reinterpret_cast<uint8_t *>(s.d_bits);
-    if (cudaMemsetAsync(sl.acount, 0, (size_t)T * sizeof(unsigned), st1) != cudaSuccess) return -1;
+    uint8_t *bits8 = reinterpret_cast<uint8_t *>(bits);
     if (s.t_version == 2) {
 #define T2_LAUNCH(M, WP, NT) temporal2_kernel<M, WP, NT><<<grid, NT, smem, st1>>>(src, timer0, T, s.n, HWG, d_thr, bits8)
 #define T2_NT(M, WP)                                              \
@@ -339,21 +347,22 @@ static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long t
         else temporal_kernel<false, 4><<<grid, nt, smem, st1>>>(src, timer0, T, s.n, HWG, d_thr, bits8);
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
+    if (cudaEventRecord(ev_f1, st1) != cudaSuccess) return -1;
+    if (cudaStreamWaitEvent(st2, ev_f1, 0) != cudaSuccess) return -1;
+    if (cudaEventRecord(ev_d0, st2) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(sl.acount, 0, (size_t)T * sizeof(unsigned), st2) != cudaSuccess) return -1;
     const int Wb = s.W / 32;
     const int strips = (Wb + SP_USE - 1) / SP_USE;
     if (Wb % 4 == 0 && !s.force_strip) {
         const int chunks = Wb / 4, bands = (s.H + s.sp_rows - 1) / s.sp_rows;
         dim3 g((chunks * bands + A4_THREADS - 1) / A4_THREADS, T);
-        act4_kernel<<<g, A4_THREADS, 0, st1>>>(s.d_bits, s.H, Wb, s.sp_rows, chunks, bands, ring, dy0, sl);
+        act4_kernel<<<g, A4_THREADS, 0, st2>>>(bits, s.H, Wb, s.sp_rows, chunks, bands, ring, dy0, sl);
     } else {
         const int bands = (s.H + s.sp_rows - 1) / s.sp_rows;
         dim3 g((strips * bands + SP_WARPS - 1) / SP_WARPS, T);
-        act_kernel<<<g, SP_WARPS * 32, 0, st1>>>(s.d_bits, s.W, s.H, T, s.sp_rows, strips, bands, ring, dy0, sl);
+        act_kernel<<<g, SP_WARPS * 32, 0, st2>>>(bits, s.W, s.H, T, s.sp_rows, strips, bands, ring, dy0, sl);
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
-    if (cudaEventRecord(ev_f1, st1) != cudaSuccess) return -1;
-    if (cudaStreamWaitEvent(st2, ev_f1, 0) != cudaSuccess) return -1;
-    if (cudaEventRecord(ev_d0, st2) != cudaSuccess) return -1;
     if (cudaMemsetAsync(sl.dense, 0, sizeof(unsigned), st2) != cudaSuccess) return -1;
     if (s.force_dense) {  // test hook: every frame takes the full-scan path
         dst_force_dense_kernel<<<(T + 127) / 128, 128, 0, st2>>>(T, sl);
