@@ -57,12 +57,13 @@ def test_per_frame_api_matches_reference_golden(name):
     det.close()
 
 
-@pytest.mark.parametrize("mode", ["generic", "stream", "stream_dense_dst", "stream_strip_act"])
+@pytest.mark.parametrize("mode", ["generic", "stream", "stream_dense_dst", "stream_strip_act", "stream_temporal_v1"])
 @pytest.mark.parametrize("batch", [1, 7, 32])
 @pytest.mark.parametrize("name", DET_CASES)
 def test_batched_api_matches_reference_golden(name, batch, mode):
-    """generic = one fused launch per frame; stream = temporal + act4/act + sparse dst; the two extra
-    modes force the full-scan dst kernel (list-overflow path) and the warp-strip act kernel."""
+    """generic = one fused launch per frame; stream = temporal2 + act4/act + sparse dst; the extra modes
+    force the full-scan dst kernel (list-overflow path), the warp-strip act kernel and the
+    first-generation temporal kernel."""
     from metdetpy_b200.detector import M3Detector
     g = load_det_case(name)
     det = M3Detector(g["n"] / g["fps"] + 1e-9, g["fps"], g["mask"], 10, _cfg(g["cfg"]), None,
@@ -71,6 +72,7 @@ def test_batched_api_matches_reference_golden(name, batch, mode):
     det._eng.set_option("stream_kernel", stream_kernel)
     det._eng.set_option("force_dense", int(mode == "stream_dense_dst"))
     det._eng.set_option("force_strip", int(mode == "stream_strip_act"))
+    det._eng.set_option("temporal_version", 1 if mode == "stream_temporal_v1" else 2)
     T = len(g["frames"])
     W = g["frames"].shape[2]
     for s in range(0, T, batch):
