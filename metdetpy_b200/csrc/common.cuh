@@ -6,7 +6,9 @@
 #include "../../include/metdet_b200.h"
 
 #define MDB_HOUGH_ANGLES 180
-#define MDB_POINT_CAP 4096  // per-frame point-list capacity of the shared-memory PPHT path
+#define MDB_POINT_CAP 16384    // per-frame on-pixel list capacity (= most points the tier-2 PPHT kernel takes)
+#define HOUGH_CAP_LARGE 4096   // most points of the shared-memory PPHT tier 1b
+#define HOUGH_ORDER_CAP 4096   // the PPHT visiting order is precomputed per batch for frames up to this size
 
 // Where frame `t` (0-based global frame index) lives: frames of the batch in flight may be read
 // straight from the caller's device buffer (`cur`, frame t0 at offset 0: zero-copy), everything

@@ -4,7 +4,7 @@
 // MWC RNG seeded per call), its float32 rho rounding and its in-loop un-voting, so the emitted
 // segments are identical.
 //
-// Batch path (hough_batch_kernel, frames with <= MDB_POINT_CAP on-pixels):
+// Batch path (frames with <= MDB_POINT_CAP on-pixels; shared-memory tiers up to HOUGH_CAP_LARGE):
 //   * the frame's on-pixels are sorted in shared memory (row-major == cv2's nzloc order); the image
 //     mask itself is never touched again: "is pixel q still on" = binary search in the sorted keys
 //     + a removed-bit per point, all in shared memory;
@@ -191,7 +191,10 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
             if (Nu == 0) { if (tid == 0) nlines_out[t] = 0; continue; }
             if (Nu > (unsigned)P.cap) { if (tid == 0) nlines_out[t] = -1; continue; }  // tier 3 (dense)
             if (Nu > (unsigned)lcap) { if (tid == 0) nlines_out[t] = -2; continue; }    // tier 1b
-        } else if (nlines_out[t] != -2) continue;
+        } else {
+            if (nlines_out[t] != -2) continue;
+            if (Nu > (unsigned)lcap) { if (tid == 0) nlines_out[t] = -3; continue; }  // too many points for tier 1b: tier 2
+        }
         const int N = (int)Nu;
         const long long pc0 = clock64();
         long long p_setup = 0, p_vote = 0, p_walk = 0, p_unvote = 0, n_vote = 0, n_line = 0;
@@ -203,7 +206,7 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
             keys[i] = i < N ? points[(size_t)t * P.cap + i] : 0xFFFFFFFFu;
         for (int i = tid; i < (N + 31) / 32; i += HOUGH_THREADS) rm[i] = rmv[i] = 0;
         for (int i = tid; i < N; i += HOUGH_THREADS) {
-            const uint16_t o = order[(size_t)t * P.cap + i];
+            const uint16_t o = order[(size_t)t * HOUGH_ORDER_CAP + i];
             idx[i] = o;
             inv[o] = (uint16_t)i;
         }

@@ -18,7 +18,7 @@
 
 #define HOUGH_SMEM_BYTES (MDB_POINT_CAP * 8 + MDB_POINT_CAP / 8)  // keys u32 + order u16 + line u16 + removed bits
 #define HOUGH_SMEM_SMALL HOUGH1_POINT_BYTES(HOUGH_CAP_SMALL)   // tier 1a
-#define HOUGH_SMEM_LARGE HOUGH1_POINT_BYTES(MDB_POINT_CAP)     // tier 1b
+#define HOUGH_SMEM_LARGE HOUGH1_POINT_BYTES(HOUGH_CAP_LARGE)   // tier 1b
 
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -285,7 +285,7 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
         ALLOC(c.d_dst, (size_t)T * h->HW);
         ALLOC(c.d_npoints, T * sizeof(unsigned));
         ALLOC(c.d_points, (size_t)T * MDB_POINT_CAP * sizeof(uint32_t));
-        ALLOC(c.d_order, (size_t)T * MDB_POINT_CAP * sizeof(uint16_t));
+        ALLOC(c.d_order, (size_t)T * HOUGH_ORDER_CAP * sizeof(uint16_t));
         ALLOC(c.d_queue, 2 * sizeof(unsigned));
         ALLOC(c.d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t));
         ALLOC(c.d_nlines, T * sizeof(int));
@@ -481,14 +481,14 @@ static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
     CK(cudaStreamWaitEvent(h->stream3, c.ev_d1, 0));  // dst (stream2) has produced the on-pixel lists
     CK(cudaMemsetAsync(c.d_queue, 0, 2 * sizeof(unsigned), h->stream3));
     TL(c, 4, h->stream3);
-    ppht_order_kernel<<<T, 32, MDB_POINT_CAP * 2, h->stream3>>>(T, MDB_POINT_CAP, c.d_npoints, c.d_order);
+    ppht_order_kernel<<<T, 32, HOUGH_ORDER_CAP * 2, h->stream3>>>(T, HOUGH_ORDER_CAP, c.d_npoints, c.d_order);
     // tier 1a: 2 CTAs/SM (2048 points, 92 KB table); tier 1b: 1 CTA/SM (4096 points, 186 KB table)
     hough_smem_kernel<<<std::min(T, 2 * h->sm_count), HOUGH_THREADS, HOUGH_SMEM_SMALL + HOUGH_TABLE_BYTES_SMALL, h->stream3>>>(
         h->hp, T, c.d_npoints, c.d_points, c.d_order, c.d_lines, c.d_nlines, c.d_queue, h->d_prof,
         HOUGH_CAP_SMALL, HOUGH_TABLE_BYTES_SMALL, 0);
     hough_smem_kernel<<<std::min(T, h->sm_count), HOUGH_THREADS, HOUGH_SMEM_LARGE + HOUGH_TABLE_BYTES, h->stream3>>>(
         h->hp, T, c.d_npoints, c.d_points, c.d_order, c.d_lines, c.d_nlines, c.d_queue + 1, h->d_prof,
-        MDB_POINT_CAP, HOUGH_TABLE_BYTES, 1);
+        HOUGH_CAP_LARGE, HOUGH_TABLE_BYTES, 1);
     TL(c, 5, h->stream3);
     hough_tier2_kernel<<<std::min(T, h->slots), HOUGH_THREADS, HOUGH_SMEM_BYTES, h->stream3>>>(
         h->hp, T, c.d_npoints, c.d_points, h->d_accum, c.d_lines, c.d_nlines, h->d_prof);

@@ -174,8 +174,10 @@ def test_random_streams_against_oracle(seed, W, H, n, dy, sens):
     assert np.array_equal(det1.stack.sum, ref.stack.sum)
 
 
-def test_dense_mask_overflow_path_and_too_many_lines():
-    """> MDB_POINT_CAP on-pixels (global-memory PPHT path) and > 500 raw lines (Detector.py:358-360)."""
+@pytest.mark.parametrize("thr,lo,hi", [(12, 4096, 16384), (10, 16384, 1 << 30)])
+def test_dense_mask_overflow_path_and_too_many_lines(thr, lo, hi):
+    """Masks beyond the shared-memory PPHT tiers: 4096 < on-pixels <= 16384 (tier 2: global-memory accumulator,
+    one CTA per frame) and > 16384 (tier 3: point list in global memory); > 500 raw lines (Detector.py:358-360)."""
     from metdetpy_b200 import BinaryCfg, BinaryCoreCfg, DynamicCfg, HoughLineCfg
     from metdetpy_b200.detector import M3Detector
     from oracle import m3_oracle as O
@@ -183,9 +185,9 @@ def test_dense_mask_overflow_path_and_too_many_lines():
     H, W, n, T = 240, 320, 3, 8
     frames = rng.integers(0, 40, (T, H, W)).astype(np.uint8)
     mask = np.ones((H, W), np.uint8)
-    kw = dict(adaptive=False, init_value=12, sensitivity="normal", area=0.1, interval=2, hough=(10, 10, 10), dy_mask=False)
+    kw = dict(adaptive=False, init_value=thr, sensitivity="normal", area=0.1, interval=2, hough=(10, 10, 10), dy_mask=False)
     ref = O.M3DetectorOracle(n / 10 + 1e-9, 10, mask, 10, backend="numpy", **kw)
-    cfg = BinaryCfg(BinaryCoreCfg(False, 12, "normal", 0.1, 2), HoughLineCfg(10, 10, 10), DynamicCfg(False, 5))
+    cfg = BinaryCfg(BinaryCoreCfg(False, thr, "normal", 0.1, 2), HoughLineCfg(10, 10, 10), DynamicCfg(False, 5))
     det = M3Detector(n / 10 + 1e-9, 10, mask, 10, cfg, None, max_batch=T)
     res, dst = det.detect_many(frames, return_dst=True)
     seen_overflow = seen_toomuch = False
@@ -194,7 +196,7 @@ def test_dense_mask_overflow_path_and_too_many_lines():
         assert np.array_equal(dst[t], ref.dst), t
         info = det.last_infos[t]
         assert info["lines_num"] == ref.lines_num, (t, info["lines_num"], ref.lines_num)
-        seen_overflow |= info["n_on"] > 4096
+        seen_overflow |= lo < info["n_on"] <= hi
         if ref.lines_num > 500:
             seen_toomuch = True
             assert len(res[t][0]) == 0 and res[t][1].shape == (0, 10)
