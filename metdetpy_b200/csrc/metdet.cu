@@ -935,6 +935,12 @@ extern "C" int mdb_set_option(mdb_handle h, const char *name, int value) {
             return fail(MDB_ERR_INVALID, "mdb_set_option: temporal_nt=%d not possible here", value);
         return MDB_OK;
     }
+    if (!strcmp(name, "temporal_kdiv")) {
+        h->sk.t_kdiv_req = value;
+        if (!h->sk.ok || stream_state_config(h->sk, h->sk.t_wpt) != 0)
+            return fail(MDB_ERR_INVALID, "mdb_set_option: temporal_kdiv=%d not possible here", value);
+        return MDB_OK;
+    }
     if (!strcmp(name, "temporal_version")) { h->sk.t_version = value == 1 ? 1 : 2; return MDB_OK; }
     if (!strcmp(name, "force_dense")) { h->sk.force_dense = value; return MDB_OK; }
     if (!strcmp(name, "force_strip")) { h->sk.force_strip = value; return MDB_OK; }

@@ -30,6 +30,8 @@ struct StreamState {
     int t_threads = 32;     // CTA size of the temporal kernel
     int t_wpt = 2;          // 32-bit words (4 px) per thread in the temporal kernel
     int t_version = 2;      // 2: temporal2_kernel (temporal_kernel.cuh); 1: the first-generation kernel below
+    int t_kdiv = 1;         // temporal2: sub-blocks per window (divides n)
+    int t_kdiv_req = 0;     // test hook: force this many sub-blocks (0 = choose)
     int dst_rows = 32;      // output rows per warp strip in dst_dense_kernel
     int force_dense = 0;    // test hook: dst of every frame by the full-scan kernel
     int force_strip = 0;    // test hook: act by the warp-strip kernel even when W % 128 == 0
@@ -255,19 +257,39 @@ static inline void stream_state_free(StreamState &s) {
     s.ok = 0;
 }
 
+// sub-blocks per window for temporal2.  Splitting the window saves shared memory (more resident warps) but every
+// block end costs a register FIFO update and a scan set-up, and runs get shorter: it pays for long windows only
+// (measured at 4K: n = 30 is fastest with one block -- chain 2.25 ms vs 2.47 / 2.71 ms with 3 / 6 blocks; n = 60:
+// 3.44 ms with one block, 3.12 / 3.01 / 2.98 / 3.12 ms with 2 / 3 / 4 / 6).
+static inline int stream_choose_kdiv(int n, int req) {
+    if (req >= 1 && req <= T2_KMAX && n % req == 0 && n / req >= 2) return req;
+    if (n < 48) return 1;
+    for (int k = T2_KMAX; k >= 2; k--)
+        if (n % k == 0 && n / k >= 15) return k;
+    return 1;
+}
+
+// shared memory of one temporal CTA: per-thread ring + suffix slots, u16 bias per frame, one "bias changes" bit per frame
+static inline size_t stream_temporal_smem(const StreamState &s, int nt, int T, int version) {
+    const int slots = version == 2 ? s.n + ST_K + s.n / s.t_kdiv : 2 * s.n + ST_K;
+    return (size_t)slots * 4 * s.t_wpt * nt + (((size_t)2 * T + 15) & ~(size_t)15);
+}
+
 // choose words-per-thread of the temporal kernel and derive its CTA size / shared memory
 // (nt_req > 0 forces the CTA size; otherwise the largest CTA that keeps the most warps per SM)
 static inline int stream_state_config(StreamState &s, int wpt, int nt_req = 0) {
     if (wpt != 2 && wpt != 4) return -1;
     const size_t sm_bytes = 228 * 1024, cta_max = 220 * 1024, reserved = 1024;
-    const size_t per_thread = (size_t)(2 * s.n + ST_K) * 4 * wpt;
-    const size_t table = ((size_t)2 * s.max_batch + 15) & ~(size_t)15;  // u16 bias per frame
+    s.t_kdiv = stream_choose_kdiv(s.n, s.t_kdiv_req);
+    const size_t per_thread_v1 = (size_t)(2 * s.n + ST_K) * 4 * wpt;  // the first-generation kernel must fit too
+    const size_t per_thread = (size_t)(s.n + ST_K + s.n / s.t_kdiv) * 4 * wpt;
+    const size_t table = ((size_t)2 * s.max_batch + 15) & ~(size_t)15;
     int best_nt = 0;
     size_t best_warps = 0;
     for (int nt = 128; nt >= 32; nt >>= 1) {
         if (nt_req && nt != nt_req) continue;
+        if (per_thread_v1 * nt + table > cta_max) continue;
         const size_t cta = per_thread * nt + table;
-        if (cta > cta_max) continue;
         const size_t warps = sm_bytes / (cta + reserved) * (nt / 32);
         if (warps > best_warps) { best_warps = warps; best_nt = nt; }
     }
@@ -299,9 +321,11 @@ static inline int stream_state_init(StreamState &s, int W, int H, int n, int dev
         return -1;
     ST_SETATTR((temporal_kernel<false, 2>)) ST_SETATTR((temporal_kernel<true, 2>))
     ST_SETATTR((temporal_kernel<false, 4>)) ST_SETATTR((temporal_kernel<true, 4>))
-#define ST_SETATTR2(NT)                                                                            \
-    ST_SETATTR((temporal2_kernel<false, 2, NT>)) ST_SETATTR((temporal2_kernel<true, 2, NT>))      \
-    ST_SETATTR((temporal2_kernel<false, 4, NT>)) ST_SETATTR((temporal2_kernel<true, 4, NT>))
+#define ST_SETATTR2(NT)                                                                                          \
+    ST_SETATTR((temporal2_kernel<false, 2, NT, false>)) ST_SETATTR((temporal2_kernel<true, 2, NT, false>))      \
+    ST_SETATTR((temporal2_kernel<false, 4, NT, false>)) ST_SETATTR((temporal2_kernel<true, 4, NT, false>))      \
+    ST_SETATTR((temporal2_kernel<false, 2, NT, true>)) ST_SETATTR((temporal2_kernel<true, 2, NT, true>))        \
+    ST_SETATTR((temporal2_kernel<false, 4, NT, true>)) ST_SETATTR((temporal2_kernel<true, 4, NT, true>))
     ST_SETATTR2(32) ST_SETATTR2(64) ST_SETATTR2(128)
 #undef ST_SETATTR2
 #undef ST_SETATTR
@@ -324,11 +348,15 @@ static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long t
     uint32_t *const bits = parity ? s.d_bits2 : s.d_bits;
     const int HWG = (int)((size_t)s.W * s.H / (4 * s.t_wpt));  // pixel groups = threads
     const int nt = s.t_threads;
-    const size_t smem = s.t_smem_per_thread * nt + (((size_t)2 * T + 15) & ~(size_t)15);
+    const size_t smem = stream_temporal_smem(s, nt, T, s.t_version);
     const int grid = (HWG + nt - 1) / nt;
     uint8_t *bits8 = reinterpret_cast<uint8_t *>(bits);
     if (s.t_version == 2) {
-#define T2_LAUNCH(M, WP, NT) temporal2_kernel<M, WP, NT><<<grid, NT, smem, st1>>>(src, timer0, T, s.n, HWG, d_thr, bits8)
+#define T2_LAUNCH(M, WP, NT)                                                                                            \
+    do {                                                                                                                \
+        if (s.t_kdiv > 1) temporal2_kernel<M, WP, NT, true><<<grid, NT, smem, st1>>>(src, timer0, T, s.n, s.t_kdiv, HWG, d_thr, bits8); \
+        else temporal2_kernel<M, WP, NT, false><<<grid, NT, smem, st1>>>(src, timer0, T, s.n, 1, HWG, d_thr, bits8);   \
+    } while (0)
 #define T2_NT(M, WP)                                              \
     do {                                                          \
         if (nt == 32) T2_LAUNCH(M, WP, 32);                       \

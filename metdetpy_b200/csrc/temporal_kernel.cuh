@@ -13,6 +13,12 @@
 //     extracts the clean window max at the end.
 //   * window sums: W = sum of the raw packed words (mod 2^32) and O = sum of the odd pixels (u16x2);
 //     the even sums are W - 256*O (one IMAD).  Only the odd lanes of new / evicted words are unpacked.
+//   * sub-blocked van Herk: with the window split into k blocks of b = n/k frames (k divides n) a window is the
+//     suffix of its oldest block + (k-1) whole blocks + the prefix of the current block.  Only the OLDEST block
+//     needs a suffix-max array (b slots instead of n; it is rebuilt from the raw ring at every block end), the
+//     whole blocks' maxima sit in registers, and VIMNMX3 combines prefix, middle maximum and suffix in the one
+//     instruction the two-block scheme needs as well.  Shared memory per pixel: n + K + n/k bytes instead of
+//     2n + K, i.e. half again as many resident warps at n = 30.
 //   * the frame loop is cut into runs inside which no ring pointer wraps, L is constant and the
 //     prefetch predicate does not change, so a frame costs no pointer selects or compares; shared
 //     memory slots are addressed with immediate offsets (CTA size is a template parameter).
@@ -54,6 +60,42 @@ struct T2State {
     unsigned pO[WPT], pE[WPT];  // prefix max of the current block, high-byte form (odd / even pixels)
     unsigned Wd[WPT];           // sum of the raw words of the window, mod 2^32
     unsigned Od[WPT];           // sum of the odd pixels of the window, u16x2
+    unsigned mO[WPT], mE[WPT];  // max over the whole blocks inside the window (high-byte form; 0 when k == 1)
+};
+
+#define T2_KMAX 6  // most sub-blocks per window
+// maxima of the last T2_KMAX-1 finished blocks, oldest first (high-byte form)
+template <int WPT>
+struct T2Fifo {
+    unsigned fO[T2_KMAX - 1][WPT], fE[T2_KMAX - 1][WPT];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int q = 0; q < T2_KMAX - 1; q++)
+#pragma unroll
+            for (int k = 0; k < WPT; k++) fO[q][k] = fE[q][k] = 0u;
+    }
+    __device__ __forceinline__ void push(const unsigned (&bO)[WPT], const unsigned (&bE)[WPT]) {
+#pragma unroll
+        for (int q = 0; q + 1 < T2_KMAX - 1; q++)
+#pragma unroll
+            for (int k = 0; k < WPT; k++) { fO[q][k] = fO[q + 1][k]; fE[q][k] = fE[q + 1][k]; }
+#pragma unroll
+        for (int k = 0; k < WPT; k++) { fO[T2_KMAX - 2][k] = bO[k]; fE[T2_KMAX - 2][k] = bE[k]; }
+    }
+    // max over the newest `cnt` entries (cnt = k-1 whole blocks inside the window)
+    __device__ __forceinline__ void newest_max(int cnt, unsigned (&mO)[WPT], unsigned (&mE)[WPT]) const {
+#pragma unroll
+        for (int k = 0; k < WPT; k++) mO[k] = mE[k] = 0u;
+#pragma unroll
+        for (int q = 0; q < T2_KMAX - 1; q++) {
+            const bool use = q >= T2_KMAX - 1 - cnt;
+#pragma unroll
+            for (int k = 0; k < WPT; k++) {
+                mO[k] = __vmaxu2(mO[k], use ? fO[q][k] : 0u);
+                mE[k] = __vmaxu2(mE[k], use ? fE[q][k] : 0u);
+            }
+        }
+    }
 };
 
 // Operands of one frame: its raw word(s), frame t-n's, the suffix-max word(s) of its position.
@@ -84,7 +126,8 @@ __device__ __forceinline__ const uint8_t *t2_addr(const uint8_t *base, unsigned 
 }
 
 // Compute stage.  Lu = window length, cpk = per-lane bias (0x7fff - thr*L) * 0x10001.
-template <int WPT>
+// SUB: the window holds whole blocks between its oldest block and the current one (sub-blocked scheme).
+template <int WPT, bool SUB>
 __device__ __forceinline__ void t2_compute(T2State<WPT> &st, const T2Ops<WPT> &q, unsigned Lu, unsigned cpk,
                                            uint8_t *bp) {
     unsigned M[WPT];
@@ -93,8 +136,9 @@ __device__ __forceinline__ void t2_compute(T2State<WPT> &st, const T2Ops<WPT> &q
         const unsigned x = q.xw[k], x8 = x << 8, m = q.mw[k], m8 = m << 8;
         st.pO[k] = __vmaxu2(st.pO[k], x);
         st.pE[k] = __vmaxu2(st.pE[k], x8);
-        const unsigned wO = t2_hi(__vmaxu2(st.pO[k], m));   // window max, odd pixels, clean u16x2
-        const unsigned wE = t2_hi(__vmaxu2(st.pE[k], m8));  // ... even pixels
+        // window max = prefix of this block, whole blocks in between, suffix of the oldest block (one VIMNMX3)
+        const unsigned wO = t2_hi(SUB ? __vimax3_u16x2(st.pO[k], m, st.mO[k]) : __vmaxu2(st.pO[k], m));    // odd pixels, clean u16x2
+        const unsigned wE = t2_hi(SUB ? __vimax3_u16x2(st.pE[k], m8, st.mE[k]) : __vmaxu2(st.pE[k], m8));  // ... even pixels
         st.Wd[k] = st.Wd[k] + x - q.ow[k];
         st.Od[k] = st.Od[k] + t2_hi(x) - t2_hi(q.ow[k]);
         const unsigned sE = st.Wd[k] - (st.Od[k] << 8);
@@ -135,22 +179,24 @@ __device__ __forceinline__ void t2_scan_run(unsigned (&aO)[WPT], unsigned (&aE)[
     }
 }
 
-template <bool MASKED, int WPT, int NT>
+template <bool MASKED, int WPT, int NT, bool SUB>
 __global__ void __launch_bounds__(NT)
-temporal2_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *__restrict__ thr,
+temporal2_kernel(FrameSrc src, long long t0, int T, int n, int kdiv, int HWG, const int *__restrict__ thr,
                  uint8_t *__restrict__ bits) {
     constexpr int VB = WPT * 4;           // bytes (= pixels) per thread per frame
     constexpr uint32_t S = NT * VB;       // bytes between consecutive slots
     extern __shared__ uint4 t_smem[];
     const int tid = threadIdx.x;
     const int R = n + T2_K;
-    // shared memory: ring [R][NT] raw frames, smx [n][NT] suffix max of the previous block by position
-    // (slot p-1 = position p; slot n-1 stays zero), thr_s [T]
+    if (!SUB) kdiv = 1;
+    const int b = n / kdiv;  // block length (kdiv divides n; kdiv == 1: the classic two-block scheme)
+    // shared memory: ring [R][NT] raw frames, smx [b][NT] suffix max of the window's oldest block by position
+    // (slot p-1 = position p; slot b-1 stays zero), thr_s [T]
     const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(t_smem);
     const uint32_t ring_s = smem0 + tid * VB;
     const uint32_t smx_s = ring_s + R * S;
     // per-frame lane bias 0x7fff - thr*L (L = SlidingWindow.length of that frame), u16
-    uint16_t *thr_s = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(t_smem) + (size_t)(R + n) * S);
+    uint16_t *thr_s = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(t_smem) + (size_t)(R + b) * S);
     for (int i = tid; i < T; i += NT) {
         const long long Li = t0 + i + 1 < n ? t0 + i + 1 : n;
         thr_s[i] = (uint16_t)(0x7fff - min(max(thr[i], 0), 255) * (int)Li);
@@ -189,11 +235,39 @@ temporal2_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *_
     t2_wait<T2_K>();  // history landed
 
     T2State<WPT> st;
+    T2Fifo<WPT> fifo;
+    if (SUB) fifo.clear();
     {
+        // history position p (1 .. n-1) = frame t0-n+p lives in ring slot p-1; block q = p / b (0 = oldest, only its
+        // positions 1 .. b-1 exist), position inside the block p % b
+#pragma unroll
+        for (int k = 0; k < WPT; k++) st.Wd[k] = st.Od[k] = 0u;
+        for (int q = 1; SUB && q < kdiv; q++) {  // whole blocks between the oldest one and the batch: their maxima
+            unsigned bO[WPT], bE[WPT];
+#pragma unroll
+            for (int k = 0; k < WPT; k++) bO[k] = bE[k] = 0u;
+            for (int p = q * b; p < (q + 1) * b; p++) {
+                unsigned w[WPT];
+                t2_lds<WPT>(w, ring_s + (p - 1) * S);
+                if (MASKED) {
+#pragma unroll
+                    for (int k = 0; k < WPT; k++) w[k] &= mk[k];
+                    t2_sts<WPT>(ring_s + (p - 1) * S, w);
+                }
+#pragma unroll
+                for (int k = 0; k < WPT; k++) {
+                    st.Wd[k] += w[k];
+                    st.Od[k] += t2_hi(w[k]);
+                    bO[k] = __vmaxu2(bO[k], w[k]);
+                    bE[k] = __vmaxu2(bE[k], w[k] << 8);
+                }
+            }
+            fifo.push(bO, bE);
+        }
         unsigned aO[WPT], aE[WPT];
 #pragma unroll
-        for (int k = 0; k < WPT; k++) st.Wd[k] = st.Od[k] = aO[k] = aE[k] = 0u;
-        for (int p = n - 1; p >= 1; p--) {
+        for (int k = 0; k < WPT; k++) aO[k] = aE[k] = 0u;
+        for (int p = b - 1; p >= 1; p--) {  // oldest block: suffix max by position
             unsigned w[WPT], o[WPT];
             t2_lds<WPT>(w, ring_s + (p - 1) * S);
             if (MASKED) {
@@ -211,8 +285,9 @@ temporal2_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *_
             }
             t2_sts<WPT>(smx_s + (p - 1) * S, o);
         }
+        if (SUB) fifo.newest_max(kdiv - 1, st.mO, st.mE);
     }
-    t2_sts<WPT>(smx_s + (n - 1) * S, zero);
+    t2_sts<WPT>(smx_s + (b - 1) * S, zero);
 
     const size_t bstride = (size_t)HWG * WPT / 2;          // WPT*4 bits per thread and frame
     uint8_t *bout = bits + (size_t)g * WPT / 2;
@@ -220,7 +295,7 @@ temporal2_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *_
     int o = R - 1;   // ring slot of frame t-n (then: destination of the prefetch of frame t+K)
     int i = 0;
     while (i < T) {
-        const int nb = min(n, T - i);  // frames of this block
+        const int nb = min(b, T - i);  // frames of this block
 #pragma unroll
         for (int k = 0; k < WPT; k++) st.pO[k] = st.pE[k] = 0u;  // 0 = identity of max
         int j = 0;
@@ -252,8 +327,8 @@ temporal2_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *_
                 t2_commit();
                 if (pf) t2_cp<WPT>(ao + S, t2_addr(gp1, u, HWu));
                 t2_commit();
-                t2_compute<WPT>(st, qa, Lu, (unsigned)tp[u] * 0x00010001u, (uint8_t *)t2_addr(bp, u, bs32));
-                t2_compute<WPT>(st, qb, Lu, (unsigned)tp[u + 1] * 0x00010001u, (uint8_t *)t2_addr(bp1, u, bs32));
+                t2_compute<WPT, SUB>(st, qa, Lu, (unsigned)tp[u] * 0x00010001u, (uint8_t *)t2_addr(bp, u, bs32));
+                t2_compute<WPT, SUB>(st, qb, Lu, (unsigned)tp[u + 1] * 0x00010001u, (uint8_t *)t2_addr(bp1, u, bs32));
                 ac += 2 * S; ao += 2 * S; asx += 2 * S;
             }
             if (u < (unsigned)run) {  // odd run: one frame left
@@ -261,19 +336,27 @@ temporal2_kernel(FrameSrc src, long long t0, int T, int n, int HWG, const int *_
                 t2_load<MASKED, WPT>(qa, mk, ac, ao, asx);
                 if (pf) t2_cp<WPT>(ao, t2_addr(gp, u, HWu));
                 t2_commit();
-                t2_compute<WPT>(st, qa, Lu, (unsigned)tp[u] * 0x00010001u, (uint8_t *)t2_addr(bp, u, bs32));
+                t2_compute<WPT, SUB>(st, qa, Lu, (unsigned)tp[u] * 0x00010001u, (uint8_t *)t2_addr(bp, u, bs32));
             }
             i += run; j += run;
             c += run; if (c == R) c = 0;
             o += run; if (o == R) o = 0;
             pf_slot += run; if (pf_slot >= Rw) pf_slot = 0;
         }
-        if (nb == n && i < T) {  // block complete and more frames follow: suffix max by position 1..n-1
+        if (nb == b && i < T) {
+            // block complete and more frames follow: it joins the whole blocks of the window (maximum = its final
+            // prefix), and the window's new oldest block -- the b oldest frames still in the raw ring, positions
+            // 0 .. b-1 at slots c+K .. c+K+b-1 (mod R) -- gets its suffix max by position 1 .. b-1
+            if (SUB) {
+                fifo.push(st.pO, st.pE);
+                fifo.newest_max(kdiv - 1, st.mO, st.mE);
+            }
             unsigned aO[WPT], aE[WPT];
 #pragma unroll
             for (int k = 0; k < WPT; k++) aO[k] = aE[k] = 0u;
-            int a = c == 0 ? R - 1 : c - 1;  // slot of the block's last frame
-            int p = n - 1;
+            int a = c + T2_K + b - 1;  // slot of the oldest block's last frame
+            if (a >= R) a -= R;
+            int p = b - 1;
             while (p >= 1) {
                 const int cnt = min(p, a + 1);
                 t2_scan_run<WPT, S>(aO, aE, ring_s + a * S, smx_s + (p - 1) * S, cnt);

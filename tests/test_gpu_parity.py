@@ -57,7 +57,8 @@ def test_per_frame_api_matches_reference_golden(name):
     det.close()
 
 
-@pytest.mark.parametrize("mode", ["generic", "stream", "stream_dense_dst", "stream_strip_act", "stream_temporal_v1"])
+@pytest.mark.parametrize("mode", ["generic", "stream", "stream_dense_dst", "stream_strip_act", "stream_temporal_v1",
+                                  "stream_subblocks"])
 @pytest.mark.parametrize("batch", [1, 7, 32])
 @pytest.mark.parametrize("name", DET_CASES)
 def test_batched_api_matches_reference_golden(name, batch, mode):
@@ -69,10 +70,16 @@ def test_batched_api_matches_reference_golden(name, batch, mode):
     det = M3Detector(g["n"] / g["fps"] + 1e-9, g["fps"], g["mask"], 10, _cfg(g["cfg"]), None,
                      max_batch=batch)
     stream_kernel = int(mode != "generic")
+    W = g["frames"].shape[2]
     det._eng.set_option("stream_kernel", stream_kernel)
     det._eng.set_option("force_dense", int(mode == "stream_dense_dst"))
     det._eng.set_option("force_strip", int(mode == "stream_strip_act"))
     det._eng.set_option("temporal_version", 1 if mode == "stream_temporal_v1" else 2)
+    if mode == "stream_subblocks":  # sub-blocked van Herk (long windows use it by default): force a split of n
+        k = next((k for k in (5, 4, 3, 2) if g["n"] % k == 0 and g["n"] // k >= 2), 0)
+        if not k or W % 32 or not 2 <= g["n"] <= 128:
+            pytest.skip("window not divisible / streaming path not used")
+        det._eng.set_option("temporal_kdiv", k)
     T = len(g["frames"])
     W = g["frames"].shape[2]
     for s in range(0, T, batch):
