@@ -452,7 +452,7 @@ hough_tier2_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
     uint16_t *idx = reinterpret_cast<uint16_t *>(keys + P.cap);       // [cap] visiting order
     uint16_t *wl = idx + P.cap;                                       // [cap] pixels of the current line
     uint32_t *rm = reinterpret_cast<uint32_t *>(wl + P.cap);          // [cap/32] removed bits
-    __shared__ int s_red[2][HOUGH_THREADS / 32];
+    __shared__ int s_red[2][HOUGH_THREADS / 32][HOUGH_SPEC];
     __shared__ unsigned s_on[HOUGH_THREADS / 32], s_inb[HOUGH_THREADS / 32];
     __shared__ int s_ctl[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -499,32 +499,84 @@ hough_tier2_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
             }
         int par = 0;
         p_setup = clock64() - pc0;
-        for (int s = N - 1; s >= 0; s--) {
+        // votes are taken HOUGH_SPEC points per barrier as in the shared-memory tiers: here it is the L2 round trips
+        // of the four cell reads that overlap (the cells were prefetched a few visits ahead)
+        int s = N - 1;
+        for (;;) {
             long long c0 = clock64();
-            const int pi = idx[s];
-            if (tid < MDB_HOUGH_ANGLES && s >= HOUGH_PREFETCH) {
-                const uint32_t k = keys[idx[s - HOUGH_PREFETCH]];
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(myrow + rho_cs(k & 0xffffu, k >> 16, my_c, my_s)));
+            int cs[HOUGH_SPEC], cnt = 0;
+            uint32_t ck[HOUGH_SPEC];
+#pragma unroll
+            for (int j = 0; j < HOUGH_SPEC; j++) { cs[j] = -1; ck[j] = 0; }
+            while (cnt < HOUGH_SPEC && s >= 0) {  // uniform: every thread walks the same list
+                const int pi = idx[s];
+                if (tid < MDB_HOUGH_ANGLES && s >= HOUGH_PREFETCH) {
+                    const uint32_t k = keys[idx[s - HOUGH_PREFETCH]];
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(myrow + rho_cs(k & 0xffffu, k >> 16, my_c, my_s)));
+                }
+                if (!((rm[pi >> 5] >> (pi & 31)) & 1u)) {
+                    const uint32_t kk = keys[pi];
+#pragma unroll
+                    for (int j = 0; j < HOUGH_SPEC; j++)
+                        if (j == cnt) { cs[j] = s; ck[j] = kk; }
+                    cnt++;
+                }
+                s--;
             }
-            if ((rm[pi >> 5] >> (pi & 31)) & 1u) continue;  // removed by an earlier line (uniform)
-            const uint32_t key = keys[pi];
-            const int x = key & 0xffffu, y = key >> 16;
-            int best = INT_MIN;
+            if (cnt == 0) break;
+            int bj[HOUGH_SPEC], rj[HOUGH_SPEC], vj[HOUGH_SPEC];
+#pragma unroll
+            for (int j = 0; j < HOUGH_SPEC; j++) { bj[j] = INT_MIN; rj[j] = 0; vj[j] = 0; }
             if (tid < MDB_HOUGH_ANGLES) {
-                const int r = rho_cs(x, y, my_c, my_s);
-                const int v = __ldcg(myrow + r) + 1;  // L2 only: cells are also updated by REDs
-                __stcg(myrow + r, v);
-                best = v * 256 + (255 - tid);  // max value first, lowest angle on ties
+#pragma unroll
+                for (int j = 0; j < HOUGH_SPEC; j++)
+                    if (j < cnt) rj[j] = rho_cs(ck[j] & 0xffffu, ck[j] >> 16, my_c, my_s);
+#pragma unroll
+                for (int j = 0; j < HOUGH_SPEC; j++)
+                    if (j < cnt) vj[j] = __ldcg(myrow + rj[j]);  // L2 only: cells are also updated by REDs
+                // the four reads are issued together; equal cells inside the group are forwarded through
+                // registers so that every point sees the count the sequential order gives it
+#pragma unroll
+                for (int j = 0; j < HOUGH_SPEC; j++)
+                    if (j < cnt) {
+                        int base = vj[j];
+#pragma unroll
+                        for (int i = 0; i < j; i++)
+                            if (rj[i] == rj[j]) base = vj[i];  // the latest earlier vote for the same cell wins
+                        vj[j] = base + 1;
+                        bj[j] = vj[j] * 256 + (255 - tid);  // max value first, lowest angle on ties
+                    }
+#pragma unroll
+                for (int j = 0; j < HOUGH_SPEC; j++)
+                    if (j < cnt) __stcg(myrow + rj[j], vj[j]);
             }
-            best = __reduce_max_sync(0xffffffffu, best);
-            if (lane == 0) s_red[par][warp] = best;
+#pragma unroll
+            for (int j = 0; j < HOUGH_SPEC; j++) {
+                bj[j] = __reduce_max_sync(0xffffffffu, bj[j]);
+                if (lane == 0) s_red[par][warp][j] = bj[j];
+            }
             __syncthreads();
 #pragma unroll
-            for (int k = 0; k < HOUGH_THREADS / 32; k++) best = max(best, s_red[par][k]);
+            for (int j = 0; j < HOUGH_SPEC; j++)
+#pragma unroll
+                for (int k = 0; k < HOUGH_THREADS / 32; k++) bj[j] = max(bj[j], s_red[par][k][j]);
             par ^= 1;
-            p_vote += clock64() - c0; n_vote++;
-            if ((best >> 8) < P.threshold) continue;
+            int trig = -1;
+#pragma unroll
+            for (int j = 0; j < HOUGH_SPEC; j++)
+                if (trig < 0 && j < cnt && (bj[j] >> 8) >= P.threshold) trig = j;
+            p_vote += clock64() - c0; n_vote += trig < 0 ? cnt : trig + 1;
+            if (trig < 0) continue;
             c0 = clock64(); n_line++;
+            uint32_t key = 0;
+            int best = 0;
+#pragma unroll
+            for (int j = 0; j < HOUGH_SPEC; j++) {
+                if (j == trig) { key = ck[j]; best = bj[j]; s = cs[j] - 1; }
+                // take back the votes of the points behind the one that yielded a line
+                if (j > trig && j < cnt && tid < MDB_HOUGH_ANGLES) __stcg(myrow + rj[j], __ldcg(myrow + rj[j]) - 1);
+            }
+            const int x = key & 0xffffu, y = key >> 16;
             const int max_n = 255 - (best & 255);
 
             // ---- line: find both ends (mask unchanged meanwhile), 256 steps per round ----------
@@ -609,10 +661,32 @@ hough_tier2_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
         }
         long long c1 = clock64();
         // reset: zero every accumulator cell a point of this frame can have touched
-        for (int q = tid; q < N * MDB_HOUGH_ANGLES; q += HOUGH_THREADS) {
-            const int i = q / MDB_HOUGH_ANGLES, n = q % MDB_HOUGH_ANGLES;
-            const uint32_t k = keys[i];
-            accum[(size_t)n * numrho + half + rho_of(k & 0xffffu, k >> 16, n)] = 0;
+        // Row n was only touched inside the rho interval its points project onto: find the intervals (thread n
+        // owns row n, cos/sin in registers) and clear them with coalesced stores -- N * 180 scattered 4-byte
+        // stores from one SM are bound by its load/store transaction rate (1.3 M cycles for a 6.5 k-point frame).
+        {
+            float vmin = 3.0e38f, vmax = -3.0e38f;
+            if (tid < MDB_HOUGH_ANGLES) {
+#pragma unroll 4
+                for (int i = 0; i < N; i++) {
+                    const uint32_t k = keys[i];
+                    const float v = __fadd_rn(__fmul_rn(u16_to_float(k & 0xffffu), my_c), __fmul_rn(u16_to_float(k >> 16), my_s));
+                    vmin = fminf(vmin, v);
+                    vmax = fmaxf(vmax, v);
+                }
+            }
+            // rounding is monotone: the rounded extremes bound every rounded projection
+            int *s_lo = reinterpret_cast<int *>(wl), *s_hi = s_lo + MDB_HOUGH_ANGLES;  // wl is free now (>= 2 * 180 ints)
+            __syncthreads();
+            if (tid < MDB_HOUGH_ANGLES) {
+                s_lo[tid] = __float_as_int(__fadd_rn(vmin, 12582912.0f)) - 0x4B400000;
+                s_hi[tid] = __float_as_int(__fadd_rn(vmax, 12582912.0f)) - 0x4B400000;
+            }
+            __syncthreads();
+            for (int n = warp; n < MDB_HOUGH_ANGLES; n += HOUGH_THREADS / 32) {
+                int32_t *row = accum + (size_t)n * numrho + half;
+                for (int r = s_lo[n] + lane; r <= s_hi[n]; r += 32) __stcg(row + r, 0);
+            }
         }
         __syncthreads();
         p_reset = clock64() - c1;
