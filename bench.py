@@ -230,7 +230,9 @@ def main_reference(a):
         return
     from metdetpy_b200 import synth
     det, threads = cpu_reference_detector(a)
-    per_step = 8
+    # a step = a bounded sample of the workload: 8 frames, fewer when many steps are asked for, so that the whole
+    # run (frame synthesis on the host included) stays within a few minutes
+    per_step = max(1, min(8, 240 // max(1, a.warmup + a.steps)))
     sky = synth.make_sky(a.width, a.height)
     total = a.window + 2 + (a.warmup + a.steps) * per_step
     frames = [synth.make_frame(t, sky, a.width, a.height, a.fps) for t in range(total)]

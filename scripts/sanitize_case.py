@@ -21,6 +21,11 @@ for mode in ("stream", "stream_dense_dst", "stream_strip_act", "temporal_v1", "g
         tot += sum(len(r[0]) for r in res)
     print(mode, "lines", tot)
     det.close()
+# sub-blocked temporal kernel (window 6 = 3 blocks of 2)
+det = M3Detector(6 / FPS + 1e-9, FPS, mask, 10, cfg, None, max_batch=8, apply_mask=True)
+det._eng.set_option("temporal_kdiv", 3)
+print("subblocks lines", sum(len(r[0]) for s in range(0, T, 8) for r in det.detect_many(frames[s:s + 8])))
+det.close()
 det = M3Detector(n / FPS + 1e-9, FPS, mask, 10, cfg, None)
 for t in range(8):
     det.update(frames[t] * mask); det.detect()
