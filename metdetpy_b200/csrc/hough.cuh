@@ -159,8 +159,8 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
                   const uint32_t *__restrict__ points, const uint16_t *__restrict__ order,
                   int32_t *lines_out, int *nlines_out, unsigned *queue, long long *prof, int lcap,
                   int table_bytes, int stage) {
-    // stage 0 (tier 1a): every frame; up to lcap = 2048 points and a 92 KB table, two CTAs per SM.
-    // stage 1 (tier 1b): frames stage 0 flagged -2; up to 4096 points and a 186 KB table.
+    // stage 0 (tier 1a): every frame; up to lcap = 2048 points and a 90 KB table, two CTAs per SM.
+    // stage 1 (tier 1b): frames stage 0 flagged -2; up to 4096 points and a 184 KB table (more points: tier 2).
     extern __shared__ uint32_t h_sm[];
     uint32_t *keys = h_sm;                                            // [lcap]
     uint16_t *idx = reinterpret_cast<uint16_t *>(keys + lcap);        // [lcap] visiting order

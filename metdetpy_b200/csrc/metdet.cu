@@ -63,7 +63,7 @@ struct BatchCtx {
     unsigned *d_queue = nullptr;     // work-queue head of the tier-1 Hough kernel
     int32_t *d_lines = nullptr;      // [T][MDB_MAX_LINES][4]
     int *d_nlines = nullptr;         // [T]
-    // ev_f0..ev_f1: temporal+act on the front stream; ev_d0..ev_d1: dst on the back stream
+    // ev_f0..ev_f1: temporal pass on the front stream; ev_d0..ev_d1: act + dst on the back stream
     cudaEvent_t ev_f0 = nullptr, ev_f1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr, ev_done = nullptr;
     cudaEvent_t ev_thr = nullptr;    // thresholds of this batch are on the device (scalar stream)
     cudaEvent_t tl[12] = {};         // optional timeline marks (debug)
@@ -80,7 +80,7 @@ struct mdb_detector {
     int slots;
     int sm_count = 148;
     // stream: noise, thresholds, temporal, act | stream2: dst | stream3: Hough, result copy-out |
-    // cstream: host->device frames.  The stages of consecutive batches overlap (two batches in flight):
+    // cstream: host->device frames.  The stages of consecutive batches overlap (three batches in flight):
     // the write-only dst pass and the shared-memory-bound Hough pass hide under the ALU-bound temporal pass.
     // sstream ("scalar"): noise samples + threshold recurrence + history copy of batch k+1 run beside batch k's temporal pass
     cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr, cstream = nullptr, sstream = nullptr;
@@ -409,7 +409,7 @@ static int launch_noise_thr(mdb_detector *h, BatchCtx &bc, const FrameSrc &src, 
     return MDB_OK;
 }
 
-// fused mask chain for frames i = 0..T-1 of the batch (global index timer0 + i): temporal + act on the
+// fused mask chain for frames i = 0..T-1 of the batch (global index timer0 + i): temporal pass on the
 // front stream, dst on the back stream
 static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T, long long timer0, long long dy0) {
     CK(cudaMemsetAsync(c.d_npoints, 0, T * sizeof(unsigned), h->stream2));
@@ -482,7 +482,7 @@ static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
     CK(cudaMemsetAsync(c.d_queue, 0, 2 * sizeof(unsigned), h->stream3));
     TL(c, 4, h->stream3);
     ppht_order_kernel<<<T, 32, HOUGH_ORDER_CAP * 2, h->stream3>>>(T, HOUGH_ORDER_CAP, c.d_npoints, c.d_order);
-    // tier 1a: 2 CTAs/SM (2048 points, 92 KB table); tier 1b: 1 CTA/SM (4096 points, 186 KB table)
+    // tier 1a: 2 CTAs/SM (2048 points, 90 KB table); tier 1b: 1 CTA/SM (4096 points, 184 KB table)
     hough_smem_kernel<<<std::min(T, 2 * h->sm_count), HOUGH_THREADS, HOUGH_SMEM_SMALL + HOUGH_TABLE_BYTES_SMALL, h->stream3>>>(
         h->hp, T, c.d_npoints, c.d_points, c.d_order, c.d_lines, c.d_nlines, c.d_queue, h->d_prof,
         HOUGH_CAP_SMALL, HOUGH_TABLE_BYTES_SMALL, 0);
@@ -807,7 +807,7 @@ extern "C" int mdb_collect_batch(mdb_handle h, mdb_frame_info *infos, int32_t *l
         float a = 0.f, b = 0.f;
         CK(cudaEventElapsedTime(&a, c.ev_f0, c.ev_f1));
         CK(cudaEventElapsedTime(&b, c.ev_d0, c.ev_d1));
-        h->fused_ms = a + b;  // temporal + act (front stream) and dst (back stream), each bracketed by events
+        h->fused_ms = a + b;  // temporal (front stream) and act + dst (back stream), each bracketed by events
     }
     h->last_fused_launches = h->fused_launches;
     int rc = finish_batch(h, c, infos, lines, nonline_prob, raw_lines);

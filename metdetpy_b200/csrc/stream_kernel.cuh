@@ -16,7 +16,8 @@
 //       32-pixel words.
 //
 // Per frame HBM traffic: H*W (frame) + 4 * H*W/8 (predicate bits and act bits, out and in)
-// + H*W (mask) = 2.5 H*W, against the algorithmic 2 H*W of SURVEY.md section 8(d).
+// + the mask bytes that change (the u8 mask buffer is persistent) = 1.44 H*W measured, against the algorithmic
+// 2 H*W of SURVEY.md section 8(d).
 #pragma once
 #include "common.cuh"
 #include "spatial_kernel.cuh"
