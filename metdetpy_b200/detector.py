@@ -67,6 +67,21 @@ def lineset_nms(lines: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
     return out[:k.value].copy(), prob[:k.value].copy()
 
 
+class _RaggedRows:
+    """Per-frame row blocks of one flat (K, 4) array: `rows[i]` -> the (k_i, 4) segments of frame i."""
+
+    def __init__(self, flat: np.ndarray, offs: np.ndarray):
+        self.flat, self.offs = flat, offs
+
+    def __len__(self) -> int:
+        return len(self.offs) - 1
+
+    def __getitem__(self, i: int) -> np.ndarray:
+        if i < 0:
+            i += len(self)
+        return self.flat[self.offs[i]:self.offs[i + 1]]
+
+
 class EMA:
     """EMA (MetLib/utils.py:324-368). Scalar host recurrence kept for API compatibility; inside the
     detector the same recurrence runs on the device (threshold_kernel)."""
@@ -506,7 +521,9 @@ class M3Detector(LineDetector):
 
         frames: (T,H,W) uint8 numpy array (host), or -- with on_device=True -- an int device pointer
         wrapped as (ptr, T).  Returns a list of (lines, cls_pred) per frame; per-frame scalars are in
-        `self.last_infos`.  With return_dst the masks come back as a (T,H,W) array as third item."""
+        `self.last_infos` (structured array: timer, bi_threshold, n_on, bi_threshold_float, snr, dst_sum,
+        gap, lines_num, n_raw, n_lines), raw Hough segments in `self.last_raw[i]`.  With return_dst the masks
+        come back as a (T,H,W) array as second item.  Only frames that have lines cost per-frame Python work."""
         eng = self._eng
         if on_device:
             ptr, T = frames
@@ -529,12 +546,10 @@ class M3Detector(LineDetector):
               "detect_many")
         self._timer += T
         self._dst_cache = None
-        self.last_infos = [dict(timer=fi.timer, bi_threshold=fi.bi_threshold, n_on=fi.n_on,
-                                bi_threshold_float=fi.bi_threshold_float, snr=fi.snr,
-                                dst_sum=fi.dst_sum, gap=fi.gap, lines_num=fi.lines_num,
-                                n_raw=fi.n_raw, n_lines=fi.n_lines) for fi in eng.infos[:T]]
-        self.last_raw = [eng.raw[i, :eng.infos[i].n_raw].copy() for i in range(T)]
-        res = [self._unpack(i) for i in range(T)]
+        res = self._unpack_all(T)  # also sets last_infos (structured array, one record per frame)
+        nraw = self.last_infos["n_raw"]
+        sel = np.arange(MAX_LINES)[None, :] < nraw[:, None]
+        self.last_raw = _RaggedRows(eng.raw[:T][sel].reshape(-1, 4), np.concatenate(([0], np.cumsum(nraw))))
         if dst_out is not None:
             return res, dst_out
         return res

@@ -161,7 +161,7 @@ def test_random_streams_against_oracle(seed, W, H, n, dy, sens):
     got, dsts, infos = [], [], []
     for s in range(0, T, 11):
         r, d = det.detect_many(frames[s:s + 11], return_dst=True)
-        got += r; dsts += list(d); infos += det.last_infos
+        got += r; dsts += list(d); infos += list(det.last_infos)
     for t in range(T):
         ref.update(frames[t]); rl, rc = ref.detect()
         det1.update(frames[t]); l1, c1 = det1.detect()
