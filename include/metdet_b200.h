@@ -165,6 +165,13 @@ int mdb_max_stack(const uint8_t *frames, int T, size_t frame_bytes, uint8_t *out
 int mdb_lineset_nms(const int32_t *lines_in, int n, int32_t *lines_out, double *prob_out,
                     int32_t *n_out);
 
+/* FastGaussianContainer.append over T frames (MetLib/stacker.py:52-59; FastGaussianParam.__init__/__add__,
+ * MetLib/utils.py:435-452, :485-493): per element sum_out = sum of the frames as uint16 and sq_out = sum of
+ * their squares as uint32, both wrapping like numpy's fixed-width adds (n = T is the caller's).  accumulate != 0
+ * continues from the values already in sum_out / sq_out.  frames/outputs are host or device per the flags. */
+int mdb_gauss_stack(const uint8_t *frames, int T, size_t frame_bytes, uint16_t *sum_out, uint32_t *sq_out,
+                    int frames_on_device, int out_on_device, int accumulate, int device);
+
 /* ---- loader preprocessing on the device ---------------------------
  * Replaces, for uint8 frames, what the reference's video loader applies to every decoded frame:
  *   Transform.opencv_resize   = cv2.resize(img, dsize, INTER_LINEAR)   MetLib/imgproc.py:82-85

@@ -353,3 +353,73 @@ max_stack_kernel(const uint8_t *frames, int T, size_t frame_bytes, uint8_t *out,
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// FastGaussianContainer (MetLib/stacker.py:52-59) / FastGaussianParam.__add__ (MetLib/utils.py:485-493):
+// per element the sum of the frames as uint16 and the sum of their squares as uint32 -- both WRAP exactly
+// as numpy's fixed-width adds do (the reference documents the overflow as a limit of the class,
+// utils.py:427).  One pass over the T frames; a thread owns 4 consecutive bytes.
+__global__ void __launch_bounds__(256)
+gauss_stack_kernel(const uint8_t *__restrict__ frames, int T, size_t frame_bytes, uint16_t *__restrict__ sum,
+                   uint32_t *__restrict__ sq, int accumulate) {
+    const bool aligned = (((uintptr_t)frames | (uintptr_t)sum | (uintptr_t)sq | frame_bytes) & 15) == 0;
+    if (aligned) {  // 16 bytes per thread, four frames' loads in flight
+        const size_t nvec = frame_bytes / 16;
+        for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+            unsigned s[16], q[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) s[j] = q[j] = 0;
+            if (accumulate) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) { s[j] = sum[v * 16 + j]; q[j] = sq[v * 16 + j]; }
+            }
+            const uint4 *fp = reinterpret_cast<const uint4 *>(frames) + v;
+            const size_t fstride = frame_bytes / 16;
+            int t = 0;
+            for (; t + 4 <= T; t += 4) {
+                uint4 x[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) x[u] = __ldcs(fp + (size_t)(t + u) * fstride);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const unsigned w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const unsigned b = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                        s[j] += b;
+                        q[j] += b * b;
+                    }
+                }
+            }
+            for (; t < T; t++) {
+                const uint4 xv = __ldcs(fp + (size_t)t * fstride);
+                const unsigned w[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const unsigned b = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                    s[j] += b;
+                    q[j] += b * b;
+                }
+            }
+            uint4 *so = reinterpret_cast<uint4 *>(sum + v * 16);
+            so[0] = make_uint4((s[0] & 0xffffu) | (s[1] << 16), (s[2] & 0xffffu) | (s[3] << 16),
+                               (s[4] & 0xffffu) | (s[5] << 16), (s[6] & 0xffffu) | (s[7] << 16));
+            so[1] = make_uint4((s[8] & 0xffffu) | (s[9] << 16), (s[10] & 0xffffu) | (s[11] << 16),
+                               (s[12] & 0xffffu) | (s[13] << 16), (s[14] & 0xffffu) | (s[15] << 16));
+            uint4 *qo = reinterpret_cast<uint4 *>(sq + v * 16);
+#pragma unroll
+            for (int j = 0; j < 4; j++) qo[j] = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+        }
+        return;
+    }
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < frame_bytes; p += (size_t)gridDim.x * blockDim.x) {
+        unsigned s = accumulate ? sum[p] : 0u, q = accumulate ? sq[p] : 0u;
+        for (int t = 0; t < T; t++) {
+            const unsigned b = frames[(size_t)t * frame_bytes + p];
+            s += b;
+            q += b * b;
+        }
+        sum[p] = (uint16_t)s;
+        sq[p] = q;
+    }
+}

@@ -991,6 +991,53 @@ extern "C" int mdb_max_stack(const uint8_t *frames, int T, size_t frame_bytes, u
     return MDB_OK;
 }
 
+// ---- Gaussian stack (sum, sum of squares) ------------------------------------------------------
+extern "C" int mdb_gauss_stack(const uint8_t *frames, int T, size_t frame_bytes, uint16_t *sum_out, uint32_t *sq_out,
+                               int frames_on_device, int out_on_device, int accumulate, int device) {
+    if (!frames || !sum_out || !sq_out || T < 1 || frame_bytes == 0)
+        return fail(MDB_ERR_INVALID, "mdb_gauss_stack: bad arguments");
+    if (mdb_device_count() == 0) return fail(MDB_ERR_CUDA, "mdb_gauss_stack: no CUDA device (no CPU fallback)");
+    CK(cudaSetDevice(device));
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    uint16_t *d_sum = sum_out;
+    uint32_t *d_sq = sq_out;
+    uint8_t *d_chunk = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (!out_on_device) {
+        e = cudaMalloc((void **)&d_sum, frame_bytes * 2);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&d_sq, frame_bytes * 4);
+        if (e == cudaSuccess && accumulate) e = cudaMemcpyAsync(d_sum, sum_out, frame_bytes * 2, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && accumulate) e = cudaMemcpyAsync(d_sq, sq_out, frame_bytes * 4, cudaMemcpyHostToDevice, st);
+    }
+    const int chunk = frames_on_device ? T : (int)std::max<size_t>(1, std::min<size_t>(T, (512ull << 20) / frame_bytes));
+    if (e == cudaSuccess && !frames_on_device) e = cudaMalloc((void **)&d_chunk, (size_t)chunk * frame_bytes);
+    const int grid = (int)std::min<size_t>((frame_bytes / 16 + 255) / 256 + 1, 148 * 32);
+    for (int t0 = 0; e == cudaSuccess && t0 < T; t0 += chunk) {
+        const int c = std::min(chunk, T - t0);
+        const uint8_t *src = frames + (size_t)t0 * frame_bytes;
+        if (!frames_on_device) {
+            e = cudaMemcpyAsync(d_chunk, src, (size_t)c * frame_bytes, cudaMemcpyHostToDevice, st);
+            src = d_chunk;
+        }
+        if (e == cudaSuccess) {
+            gauss_stack_kernel<<<grid, 256, 0, st>>>(src, c, frame_bytes, d_sum, d_sq, accumulate || t0 > 0);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess && !frames_on_device) e = cudaStreamSynchronize(st);
+    }
+    if (e == cudaSuccess && !out_on_device) {
+        e = cudaMemcpyAsync(sum_out, d_sum, frame_bytes * 2, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(sq_out, d_sq, frame_bytes * 4, cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (d_chunk) cudaFree(d_chunk);
+    if (!out_on_device) { if (d_sum) cudaFree(d_sum); if (d_sq) cudaFree(d_sq); }
+    cudaStreamDestroy(st);
+    if (e != cudaSuccess) return fail(MDB_ERR_CUDA, "mdb_gauss_stack: %s", cudaGetErrorString(e));
+    return MDB_OK;
+}
+
 // ---- loader preprocessing ---------------------------------------------------------------------
 struct mdb_preproc {
     PreParams P;

@@ -1,6 +1,8 @@
-"""Clip-level max stacking on the GPU: `MaxImgContainer`, `max_stacker` (MetLib/stacker.py:43-49,
-:146-175, :197-213) and `MergeFunction.max` (MetLib/utils.py:203-204). Same names and call
-signatures; frames of any channel layout (the reference stacks full-resolution colour frames)."""
+"""Clip-level stacking on the GPU: `MaxImgContainer`, `max_stacker` (MetLib/stacker.py:43-49,
+:146-175, :197-213), `MergeFunction.max` (MetLib/utils.py:203-204) and `FastGaussianContainer` /
+`FastGaussianParam` (MetLib/stacker.py:52-59, MetLib/utils.py:418-513: streaming sum and sum of squares).
+Same names and call signatures; frames of any channel layout (the reference stacks full-resolution
+colour frames)."""
 from __future__ import annotations
 
 from typing import Any, Optional, Sequence
@@ -54,6 +56,74 @@ class MaxImgContainer:
     def container(self) -> Optional[np.ndarray]:
         self._flush()
         return self._acc
+
+    def export(self):
+        return self.container
+
+
+class FastGaussianParam:
+    """Result view of the device accumulation with the reference's attribute names and formulas
+    (MetLib/utils.py:418-513): `sum_mu` (uint16), `square_sum` (uint32), `n` (int16), `mu`, `var`.
+    The integer fields wrap exactly as the reference's numpy adds do."""
+
+    def __init__(self, sum_mu: np.ndarray, square_sum: np.ndarray, n: np.ndarray, ddof: int = 1):
+        self.sum_mu, self.square_sum, self.n, self.ddof = sum_mu, square_sum, n, ddof
+
+    @property
+    def mu(self) -> np.ndarray:  # utils.py:454-456
+        return np.round(self.sum_mu / self.n)
+
+    @property
+    def var(self) -> np.ndarray:  # utils.py:458-465
+        sum_mu = np.array(self.sum_mu, dtype=self.square_sum.dtype)
+        return (self.square_sum - np.square(sum_mu) / self.n) / (self.n - self.ddof)
+
+    @property
+    def shape(self):
+        return self.sum_mu.shape
+
+
+class FastGaussianContainer:
+    """FastGaussianContainer (MetLib/stacker.py:52-59): `append(frame)` adds the frame to the running
+    per-element sum / sum of squares.  Frames are buffered and reduced on the device in chunks."""
+
+    def __init__(self, chunk: int = 32, device: int = 0):
+        self._buf: list[np.ndarray] = []
+        self._sum: Optional[np.ndarray] = None
+        self._sq: Optional[np.ndarray] = None
+        self._count = 0
+        self._chunk = chunk
+        self._device = device
+
+    def append(self, new_frame: np.ndarray) -> None:
+        if self._buf and new_frame.shape != self._buf[0].shape or \
+                self._sum is not None and new_frame.shape != self._sum.shape:
+            raise ValueError("Expect new frame has the same shape as the base frame")
+        self._buf.append(np.ascontiguousarray(new_frame, np.uint8))
+        if len(self._buf) >= self._chunk:
+            self._flush()
+
+    def _flush(self):
+        if not self._buf:
+            return
+        arr = np.ascontiguousarray(np.stack(self._buf))
+        acc = self._sum is not None
+        if not acc:
+            self._sum = np.empty(arr.shape[1:], np.uint16)
+            self._sq = np.empty(arr.shape[1:], np.uint32)
+        check(_lib.load().mdb_gauss_stack(arr.ctypes.data, len(arr), arr[0].nbytes, self._sum.ctypes.data,
+                                          self._sq.ctypes.data, 0, 0, int(acc), self._device), "FastGaussianContainer")
+        self._count += len(arr)
+        self._buf = []
+
+    @property
+    def container(self) -> Optional[FastGaussianParam]:
+        self._flush()
+        if self._sum is None:
+            return None
+        # n: np.ones_like(sum_mu, dtype=int16) added once per frame (utils.py:450-451, :490-493): wraps at 2^15
+        n = np.full(self._sum.shape, np.array(self._count).astype(np.int64).astype(np.int16), np.int16)
+        return FastGaussianParam(self._sum, self._sq, n)
 
     def export(self):
         return self.container

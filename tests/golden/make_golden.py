@@ -284,6 +284,25 @@ def case_classic():
     run_classic_case("dense_256x160_fixed", frames, np.ones((H, W), np.uint8), 30, (False, 20, "normal", 0.1, 2), (10, 10, 10))
 
 
+def case_gauss_stack():
+    """FastGaussianContainer (MetLib/stacker.py:52-59) on colour frames; second case overflows uint16 sums."""
+    from MetLib.stacker import FastGaussianContainer
+    rng = np.random.default_rng(11)
+    out = {}
+    for name, T, shape, lo, hi in [("rgb40", 40, (36, 50, 3), 0, 256), ("wrap300", 300, (9, 13), 200, 256)]:
+        frames = rng.integers(lo, hi, (T,) + shape, dtype=np.uint8)
+        box = FastGaussianContainer()
+        for f in frames:
+            box.append(f)
+        g = box.container
+        with np.errstate(all="ignore"):
+            mu, var = g.mu, g.var
+        out.update({f"{name}_frames": frames, f"{name}_sum": g.sum_mu, f"{name}_sq": g.square_sum, f"{name}_n": g.n,
+                    f"{name}_mu": mu, f"{name}_var": var})
+        print("gauss", name, frames.shape, g.sum_mu.dtype, g.square_sum.dtype, g.n.dtype, int(g.sum_mu.max()), int(g.n.flat[0]))
+    np.savez_compressed(os.path.join(HERE, "gauss_stack.npz"), names=np.array(["rgb40", "wrap300"]), **out)
+
+
 def case_preproc():
     """Loader preprocessing by the reference's own Transform (MetLib/imgproc.py:70-139) and
     MergeFunction.max (MetLib/utils.py:203-204): resize -> BGR2GRAY -> mask, exp_frame merge."""
@@ -318,7 +337,7 @@ def case_preproc():
     np.savez_compressed(os.path.join(HERE, "preproc.npz"), names=np.array([c[0] for c in cases]), **out)
 
 
-CASES = dict(preproc=case_preproc, classic=case_classic, synth_small=case_synth_small, synth_dy_mask=case_synth_dy_mask, odd=case_odd_size,
+CASES = dict(preproc=case_preproc, gauss=case_gauss_stack, classic=case_classic, synth_small=case_synth_small, synth_dy_mask=case_synth_dy_mask, odd=case_odd_size,
              dense=case_fixed_thr_dense, low=case_low_sens, clip=case_real_clip, nms=case_nms,
              sw=case_sliding_window, hough=case_hough)
 
