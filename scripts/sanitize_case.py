@@ -38,6 +38,12 @@ d2 = M3Detector(3 / FPS + 1e-9, FPS, np.ones((H, W), np.uint8), 10, cfg2, None, 
 d2.detect_many(dense)
 print("dense n_on", [i["n_on"] for i in d2.last_infos])
 print("maxstack", stacker.merge_max(frames[:5]).sum())
+# streaming Gaussian stack: aligned (16-byte) and odd-sized frames, accumulation across chunks
+for shp in ((32, 48, 3), (7, 11, 3)):
+    box = stacker.FastGaussianContainer(chunk=3)
+    for f in rng.integers(0, 256, (8,) + shp, dtype=np.uint8):
+        box.append(f)
+    print("gauss", shp, int(box.container.sum_mu.sum()))
 # loader preprocessing (resize -> gray -> mask -> exposure merge), ClassicDetector (aligned and odd widths)
 from metdetpy_b200.imgproc import Transform
 from metdetpy_b200.detector import ClassicDetector
