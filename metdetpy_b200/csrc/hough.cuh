@@ -746,11 +746,23 @@ __device__ int compact_ordered(const uint8_t *dst, int W, int H, uint32_t *keys)
 
 __global__ void __launch_bounds__(HOUGH_THREADS)
 hough_tier3_kernel(HoughParams P, int T, const uint8_t *dst, uint32_t *keys, uint32_t *idx, int32_t *accum,
-                   uint32_t *bitmap, uint32_t *walk, int32_t *lines_all, int *nlines_all) {
+                   uint32_t *bitmap, uint32_t *walk, int32_t *lines_all, int *nlines_all, unsigned *queue) {
+    // one CTA per scratch slot (point list, visiting order, accumulator, pixel bitmap, walk buffer); the CTAs
+    // claim frame indices from a queue, so the dense frames of a batch are worked on side by side
     __shared__ int s_red[HOUGH_THREADS / 32];
     __shared__ int s_ctl[8];
+    __shared__ int s_next;
     const int tid = threadIdx.x;
     const int W = P.W, H = P.H, numrho = P.numrho, half = (numrho - 1) / 2;
+    {
+        const size_t HWs = (size_t)W * H;
+        keys += (size_t)blockIdx.x * HWs;
+        idx += (size_t)blockIdx.x * HWs;
+        accum += (size_t)blockIdx.x * MDB_HOUGH_ANGLES * numrho;
+        bitmap += (size_t)blockIdx.x * ((HWs + 31) / 32);
+        walk += (size_t)blockIdx.x * P.walk_cap;
+    }
+    const float my_c = c_trig[2 * (tid < MDB_HOUGH_ANGLES ? tid : 0)], my_s = c_trig[2 * (tid < MDB_HOUGH_ANGLES ? tid : 0) + 1];
     volatile uint32_t *vbitmap = bitmap;
     __shared__ int s_any;
     if (tid == 0) s_any = 0;
@@ -759,9 +771,13 @@ hough_tier3_kernel(HoughParams P, int T, const uint8_t *dst, uint32_t *keys, uin
         if (nlines_all[t] == -1) s_any = 1;
     __syncthreads();
     if (!s_any) return;  // the usual case: no dense frame in this batch
-    for (int t = 0; t < T; t++) {
-    if (nlines_all[t] != -1) continue;
+    for (;;) {
     __syncthreads();
+    if (tid == 0) s_next = (int)atomicAdd(queue, 1u);
+    __syncthreads();
+    const int t = s_next;
+    if (t >= T) break;
+    if (nlines_all[t] != -1) continue;  // (only the CTA that claimed t ever writes nlines_all[t])
     int32_t *lines_out = lines_all + (size_t)t * P.max_lines * 4;
     const int N = compact_ordered(dst + (size_t)t * W * H, W, H, keys);
     if (N == 0) { if (tid == 0) nlines_all[t] = 0; continue; }
@@ -793,7 +809,7 @@ hough_tier3_kernel(HoughParams P, int T, const uint8_t *dst, uint32_t *keys, uin
         if (!((vbitmap[p >> 5] >> (p & 31)) & 1u)) continue;
         int best = INT_MIN;
         if (tid < MDB_HOUGH_ANGLES) {
-            const int r = rho_of(x, y, tid);
+            const int r = rho_cs(x, y, my_c, my_s);
             const int v = myrow[r] + 1;
             myrow[r] = v;
             best = v * 256 + (255 - tid);
@@ -855,16 +871,13 @@ hough_tier3_kernel(HoughParams P, int T, const uint8_t *dst, uint32_t *keys, uin
             volatile uint32_t *vwalk = walk;
             for (int k = 0; k < nw; k++) {
                 const uint32_t wk2 = vwalk[k];
-                myrow[rho_of(wk2 & 0xffffu, wk2 >> 16, tid)]--;
+                myrow[rho_cs(wk2 & 0xffffu, wk2 >> 16, my_c, my_s)]--;
             }
         }
         __syncthreads();
     }
-    for (long long q = tid; q < (long long)N * MDB_HOUGH_ANGLES; q += HOUGH_THREADS) {
-        const int i = (int)(q / MDB_HOUGH_ANGLES), n = (int)(q % MDB_HOUGH_ANGLES);
-        const uint32_t k = keys[i];
-        accum[(size_t)n * numrho + half + rho_of(k & 0xffffu, k >> 16, n)] = 0;
-    }
+    // dense frame: its points project onto (nearly) the whole accumulator -- clear the slot with coalesced stores
+    for (size_t q = tid; q < (size_t)MDB_HOUGH_ANGLES * numrho; q += HOUGH_THREADS) accum[q] = 0;
     for (int i = tid; i < N; i += HOUGH_THREADS) {
         const uint32_t k = keys[i];
         const size_t p = (size_t)(k >> 16) * W + (k & 0xffffu);

@@ -78,6 +78,7 @@ struct mdb_detector {
     int W, H, n, R;
     size_t HW;
     int slots;
+    int slots3 = 1;  // tier-3 scratch slots (dense frames worked on side by side)
     int sm_count = 148;
     // stream: noise, thresholds, temporal, act | stream2: dst | stream3: Hough, result copy-out |
     // cstream: host->device frames.  The stages of consecutive batches overlap (three batches in flight):
@@ -286,7 +287,7 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
         ALLOC(c.d_npoints, T * sizeof(unsigned));
         ALLOC(c.d_points, (size_t)T * MDB_POINT_CAP * sizeof(uint32_t));
         ALLOC(c.d_order, (size_t)T * HOUGH_ORDER_CAP * sizeof(uint16_t));
-        ALLOC(c.d_queue, 2 * sizeof(unsigned));
+        ALLOC(c.d_queue, 4 * sizeof(unsigned));
         ALLOC(c.d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t));
         ALLOC(c.d_nlines, T * sizeof(int));
         CKH(cudaMemsetAsync(c.d_dst, 0, (size_t)T * h->HW, h->stream));
@@ -303,12 +304,13 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     }
     if (cfg->detector == 1) ALLOC(h->d_cbits, (size_t)3 * T * h->H * h->Wb * sizeof(uint32_t));
     ALLOC(h->d_accum, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t));
-    ALLOC(h->d_bitmap, bm_words * sizeof(uint32_t));
-    ALLOC(h->d_walk, (size_t)hp.walk_cap * sizeof(uint32_t));
+    h->slots3 = std::max(1, std::min(std::min(h->slots, T), 8));
+    ALLOC(h->d_bitmap, (size_t)h->slots3 * bm_words * sizeof(uint32_t));
+    ALLOC(h->d_walk, (size_t)h->slots3 * hp.walk_cap * sizeof(uint32_t));
     CKH(cudaMemsetAsync(h->d_ring, 0, (size_t)h->R * h->HW, h->stream));
     CKH(cudaMemsetAsync(h->d_act, 0, (size_t)h->RA * h->H * h->Wb * sizeof(uint32_t), h->stream));
     CKH(cudaMemsetAsync(h->d_accum, 0, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t), h->stream));
-    CKH(cudaMemsetAsync(h->d_bitmap, 0, bm_words * sizeof(uint32_t), h->stream));
+    CKH(cudaMemsetAsync(h->d_bitmap, 0, (size_t)h->slots3 * bm_words * sizeof(uint32_t), h->stream));
     CKH(cudaMemcpyAsync(h->d_mask, mask, h->HW, cudaMemcpyHostToDevice, h->stream));
     for (BatchCtx &c : h->ctx) {
         CKH(cudaHostAlloc((void **)&c.h_thr, T * sizeof(int), cudaHostAllocDefault));
@@ -479,7 +481,7 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
 
 static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
     CK(cudaStreamWaitEvent(h->stream3, c.ev_d1, 0));  // dst (stream2) has produced the on-pixel lists
-    CK(cudaMemsetAsync(c.d_queue, 0, 2 * sizeof(unsigned), h->stream3));
+    CK(cudaMemsetAsync(c.d_queue, 0, 4 * sizeof(unsigned), h->stream3));
     TL(c, 4, h->stream3);
     ppht_order_kernel<<<T, 32, HOUGH_ORDER_CAP * 2, h->stream3>>>(T, HOUGH_ORDER_CAP, c.d_npoints, c.d_order);
     // tier 1a: 2 CTAs/SM (2048 points, 90 KB table); tier 1b: 1 CTA/SM (4096 points, 184 KB table)
@@ -493,12 +495,13 @@ static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
     hough_tier2_kernel<<<std::min(T, h->slots), HOUGH_THREADS, HOUGH_SMEM_BYTES, h->stream3>>>(
         h->hp, T, c.d_npoints, c.d_points, h->d_accum, c.d_lines, c.d_nlines, h->d_prof);
     if (!h->d_okeys) {  // tier-3 scratch, allocated once
-        if (cudaMalloc((void **)&h->d_okeys, h->HW * sizeof(uint32_t)) != cudaSuccess ||
-            cudaMalloc((void **)&h->d_oidx, h->HW * sizeof(uint32_t)) != cudaSuccess)
+        if (cudaMalloc((void **)&h->d_okeys, (size_t)h->slots3 * h->HW * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMalloc((void **)&h->d_oidx, (size_t)h->slots3 * h->HW * sizeof(uint32_t)) != cudaSuccess)
             return fail(MDB_ERR_NOMEM, "tier-3 scratch: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    hough_tier3_kernel<<<1, HOUGH_THREADS, 0, h->stream3>>>(h->hp, T, c.d_dst, h->d_okeys, h->d_oidx, h->d_accum,
-                                                          h->d_bitmap, h->d_walk, c.d_lines, c.d_nlines);
+    hough_tier3_kernel<<<h->slots3, HOUGH_THREADS, 0, h->stream3>>>(h->hp, T, c.d_dst, h->d_okeys, h->d_oidx, h->d_accum,
+                                                                   h->d_bitmap, h->d_walk, c.d_lines, c.d_nlines,
+                                                                   c.d_queue + 2);
     h->launches += 5;
     TL(c, 6, h->stream3);
     CK(cudaGetLastError());
