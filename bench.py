@@ -392,12 +392,20 @@ def main_ours(a):
     # ---- end to end through the public API with HOST (pinned) buffers -------------------------
     e2e = None
     if not a.no_e2e:
-        hosts = []
-        for s in range(min(distinct, 2)):
-            hb = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
-            hb.copy_(batches[s])
-            hosts.append(hb)
+        hosts, ok = [], 1
+        try:  # two pinned staging buffers per rank (B*H*W bytes each); all ranks must agree to go on
+            for s in range(min(distinct, 2)):
+                hb = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
+                hb.copy_(batches[s])
+                hosts.append(hb)
+        except Exception as exc:
+            print(f"rank {rank}: no pinned host memory for the end-to-end leg: {exc!r}", file=sys.stderr)
+            hosts, ok = [], 0
+        okt = torch.tensor([ok], device=dev, dtype=torch.int32)
+        if world > 1:
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         torch.cuda.synchronize()
+    if not a.no_e2e and int(okt.item()) == 1:
         def submit_host(s):
             hb = hosts[s % len(hosts)]
             det.submit(hb.data_ptr(), B, False)
