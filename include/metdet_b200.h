@@ -152,6 +152,19 @@ int mdb_get_launch_count(mdb_handle h, int64_t *count);
 /* Device time (ms, CUDA events on the handle's stream) the fused mask kernel(s) took in the most
  * recent batch, and how many launches that was. */
 int mdb_get_fused_time(mdb_handle h, float *ms, int32_t *launches);
+/* Read-only counters / timings of the most recent batch by name: "temporal_ms" (stack->diff->threshold pass),
+ * "spatial_ms" (median + close + dy-mask + mask bytes), "temporal_generation" (which temporal kernel ran: 3 =
+ * register ring, 2 = shared-memory ring, 1 = first generation, 0 = none), "stream_kernel" (1 if the time-tiled
+ * streaming path serves this handle).  Unknown names return MDB_ERR_INVALID. */
+int mdb_get_info(mdb_handle h, const char *name, double *value);
+/* Tuning / test knobs by name (the parity tests force every kernel variant through these): "stream_kernel" (0 = the
+ * generic per-frame kernel), "temporal_version" (1, 2, 3), "t3_variant", "temporal_wpt", "temporal_nt", "temporal_kdiv",
+ * "force_dense", "force_strip", "sp_rows", "dst_rows", "timeline", "hough_profile".  Not needed in production. */
+int mdb_set_option(mdb_handle h, const char *name, int value);
+/* debug: event timeline of the batch collected last (after mdb_set_option("timeline", 1)): out[9] ms offsets */
+int mdb_debug_timeline(mdb_handle h, float *out);
+/* debug: per-frame PPHT phase cycle counters (after mdb_set_option("hough_profile", 1)): out[T][10] */
+int mdb_debug_hough_profile(mdb_handle h, long long *out, int T);
 
 /* stacker.max_stacker / MaxImgContainer (MetLib/stacker.py:43-49, :146-175, :197-213) and
  * MergeFunction.max (MetLib/utils.py:203-204): element-wise max over T frames of frame_bytes

@@ -54,6 +54,9 @@ SYMBOLS = {
     "mdb_alloc_pinned": (_I, [_SZ, C.POINTER(_VP)]),
     "mdb_free_pinned": (_I, [_VP]),
     "mdb_set_option": (_I, [_VP, C.c_char_p, _I]),
+    "mdb_get_info": (_I, [_VP, C.c_char_p, C.POINTER(C.c_double)]),
+    "mdb_debug_timeline": (_I, [_VP, _VP]),
+    "mdb_debug_hough_profile": (_I, [_VP, _VP, _I]),
     "mdb_seek": (_I, [_VP, C.c_int64]),
     "mdb_noise_sums": (_I, [_VP, _I, _I, C.c_int64, _I, _I, _I, _I, _VP, _VP, _VP, _I]),
     "mdb_submit_batch_thr": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP]),

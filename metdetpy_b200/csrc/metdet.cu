@@ -66,6 +66,7 @@ struct BatchCtx {
     // ev_f0..ev_f1: temporal pass on the front stream; ev_d0..ev_d1: act + dst on the back stream
     cudaEvent_t ev_f0 = nullptr, ev_f1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr, ev_done = nullptr;
     cudaEvent_t ev_thr = nullptr;    // thresholds of this batch are on the device (scalar stream)
+    cudaEvent_t ev_src = nullptr;    // the scalar stream is done with this batch's frames (noise samples, history copy)
     cudaEvent_t tl[12] = {};         // optional timeline marks (debug)
     int T = 0;  // 0: free
     int bits_parity = 0;  // which predicate-bit buffer this batch uses
@@ -89,6 +90,7 @@ struct mdb_detector {
     bool front_dirty = false;        // the per-frame API touched the scalar state on the front stream
     // device
     uint8_t *d_ring = nullptr, *d_mask = nullptr;
+    uint8_t *d_stage[2] = {nullptr, nullptr};  // host-fed batches land here (contiguous), alternating; allocated on first use
     uint32_t *d_act = nullptr;  // act bit-frame ring [RA][H][Wb]
     int RA = 0, Wb = 0;
     DevState *d_state = nullptr;
@@ -105,7 +107,7 @@ struct mdb_detector {
     long long submitted = 0, collected = 0;  // batch sequence numbers
     int last_T = 0;                           // frames in the most recently finished batch
     int last_ctx = 0;                         // ... and which context holds its dst
-    float fused_ms = 0.f;
+    float fused_ms = 0.f, temporal_ms = 0.f, spatial_ms = 0.f;
     int fused_launches = 0, last_fused_launches = 0;
     HoughParams hp;
     int use_stream_kernel = 1;
@@ -154,7 +156,7 @@ static void free_all(mdb_detector *h) {
     if (h->stream3) cudaStreamSynchronize(h->stream3);
     if (h->cstream) cudaStreamSynchronize(h->cstream);
     if (h->sstream) cudaStreamSynchronize(h->sstream);
-    void *dev[] = {h->d_ring, h->d_mask, h->d_act, h->d_state, h->d_noise, h->d_accum,
+    void *dev[] = {h->d_ring, h->d_mask, h->d_stage[0], h->d_stage[1], h->d_act, h->d_state, h->d_noise, h->d_accum,
                    h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_prof, h->d_cbits};
     for (void *p : dev)
         if (p) cudaFree(p);
@@ -175,6 +177,7 @@ static void free_all(mdb_detector *h) {
         if (c.ev_d1) cudaEventDestroy(c.ev_d1);
         if (c.ev_done) cudaEventDestroy(c.ev_done);
         if (c.ev_thr) cudaEventDestroy(c.ev_thr);
+        if (c.ev_src) cudaEventDestroy(c.ev_src);
     }
     if (h->ev_copy) cudaEventDestroy(h->ev_copy);
     if (h->ev_front) cudaEventDestroy(h->ev_front);
@@ -325,6 +328,7 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
         CKH(cudaEventCreate(&c.ev_d1));
         CKH(cudaEventCreateWithFlags(&c.ev_done, cudaEventDisableTiming));
         CKH(cudaEventCreateWithFlags(&c.ev_thr, cudaEventDisableTiming));
+        CKH(cudaEventCreateWithFlags(&c.ev_src, cudaEventDisableTiming));
     }
 
     // scalar state: LineDetector.__init__ (Detector.py:204-209), SNR_SW.__init__ (:58-61)
@@ -637,7 +641,9 @@ extern "C" int mdb_detect(mdb_handle h, mdb_frame_info *info, int32_t *lines, do
     if (in_flight(h)) return fail(MDB_ERR_STATE, "mdb_detect: a submitted batch has not been collected");
     CK(cudaSetDevice(h->cfg.device));
     BatchCtx &c = h->ctx[0];
-    int rc = launch_fused(h, c, frame_src(h, nullptr, 0), 1, h->timer - 1, h->dy_timer);
+    int rc = front_after_scalar(h);  // the history copy of the last batch runs on the scalar stream
+    if (rc) return rc;
+    rc = launch_fused(h, c, frame_src(h, nullptr, 0), 1, h->timer - 1, h->dy_timer);
     if (rc) return rc;
     rc = launch_hough_and_copy(h, c, 1);
     if (rc) return rc;
@@ -646,7 +652,7 @@ extern "C" int mdb_detect(mdb_handle h, mdb_frame_info *info, int32_t *lines, do
         float a = 0.f, b = 0.f;
         CK(cudaEventElapsedTime(&a, c.ev_f0, c.ev_f1));
         CK(cudaEventElapsedTime(&b, c.ev_d0, c.ev_d1));
-        h->fused_ms = a + b;
+        h->fused_ms = a + b; h->temporal_ms = a; h->spatial_ms = b;
     }
     h->last_fused_launches = h->fused_launches;
     h->dy_timer += 1;
@@ -675,28 +681,51 @@ static int submit_impl(mdb_handle h, const uint8_t *frames, int T, int on_device
         CK(cudaStreamWaitEvent(h->sstream, h->ev_front, 0));
         h->front_dirty = false;
     }
-    if (on_device) {
-        src = frame_src(h, frames, timer0);  // zero-copy: kernels read the caller's buffer
+    BatchCtx &prev2 = h->ctx[(h->submitted + NCTX - 2) % NCTX];  // the batch before the previous one
+    const bool have_prev2 = h->submitted >= 2;
+    const uint8_t *dev_frames = frames;
+    if (!on_device && T > 1) {
+        // host frames are copied into one of two contiguous staging buffers and then take the zero-copy path: the
+        // kernels read a batch's frames from one contiguous block, the ring only ever holds history.  The copy runs
+        // on its own stream so that it overlaps the previous batch's kernels; the buffer it lands in belonged to
+        // the batch before the previous one, all of whose readers must be done (temporal pass / generic kernels /
+        // noise samples + history copy).
+        uint8_t *&stage = h->d_stage[h->submitted & 1];
+        if (!stage && cudaMalloc((void **)&stage, (size_t)h->cfg.max_batch * h->HW) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(MDB_ERR_NOMEM, "staging buffer of %zu bytes for host frames", (size_t)h->cfg.max_batch * h->HW);
+        }
+        if (have_prev2) {
+            CK(cudaStreamWaitEvent(h->cstream, prev2.ev_f1, 0));
+            CK(cudaStreamWaitEvent(h->cstream, prev2.ev_d1, 0));
+            CK(cudaStreamWaitEvent(h->cstream, prev2.ev_src, 0));
+        }
+        CK(cudaMemcpyAsync(stage, frames, (size_t)T * h->HW, cudaMemcpyHostToDevice, h->cstream));
+        CK(cudaEventRecord(h->ev_copy, h->cstream));
+        CK(cudaStreamWaitEvent(h->sstream, h->ev_copy, 0));
+        dev_frames = stage;
+    }
+    if (on_device || T > 1) {
+        src = frame_src(h, dev_frames, timer0);  // zero-copy: kernels read the batch from one contiguous block
     } else {
-        // the copy runs on its own stream so that it overlaps the previous batch's kernels; the ring
-        // holds two batches + history, so it only has to wait for the batch before the previous one
-        // (its readers are the front-stream kernels of that batch)
-        BatchCtx &prev2 = h->ctx[(h->submitted + NCTX - 2) % NCTX];
-        if (h->submitted >= 2) CK(cudaStreamWaitEvent(h->cstream, prev2.ev_f1, 0));
+        // a single host frame goes straight into its ring slot
+        if (have_prev2) {
+            CK(cudaStreamWaitEvent(h->cstream, prev2.ev_f1, 0));
+            CK(cudaStreamWaitEvent(h->cstream, prev2.ev_d1, 0));
+        }
         int rc = copy_to_ring(h, frames, 0, T, timer0, cudaMemcpyHostToDevice, h->cstream);
         if (rc) return rc;
         CK(cudaEventRecord(h->ev_copy, h->cstream));
         CK(cudaStreamWaitEvent(h->sstream, h->ev_copy, 0));
         src = frame_src(h, nullptr, 0);
     }
-    if (h->submitted >= 2) {
+    if (have_prev2) {
         // the act ring holds two batches + history: this batch's act frames land on those of the batch
         // before the previous one, whose dst pass (back stream) must have read them
-        BatchCtx &prev2 = h->ctx[(h->submitted + NCTX - 2) % NCTX];
         CK(cudaStreamWaitEvent(h->stream, prev2.ev_d1, 0));
     }
-    // scalar stream: thresholds of this batch (noise samples + EMA recurrence) and, for device input, the copy
-    // of its last n-1 frames into the ring (history of the next batch).  None of it depends on the previous
+    // scalar stream: thresholds of this batch (noise samples + EMA recurrence) and the copy of its last n frames into
+    // the ring (history of the next batch, and what mdb_get_stack reads).  None of it depends on the previous
     // batch's mask chain, so it runs beside that batch's temporal pass instead of in front of this one's.
     int rc;
     if (thr) {  // thresholds supplied by the caller (time-sharded streams): no local EMA recurrence
@@ -708,17 +737,18 @@ static int submit_impl(mdb_handle h, const uint8_t *frames, int T, int on_device
         if (rc) return rc;
     }
     CK(cudaEventRecord(c.ev_thr, h->sstream));
-    if (on_device) {  // keep the last n-1 frames as history for the next batch
-        const int keep = std::min(T, h->n - 1);
-        if (keep > 0) {
-            // the slots they land on belonged to the batch before the previous one: if that one was host-fed its
-            // frames live there and its front-stream kernels must have read them
-            BatchCtx &prev2 = h->ctx[(h->submitted + NCTX - 2) % NCTX];
-            if (h->submitted >= 2) CK(cudaStreamWaitEvent(h->sstream, prev2.ev_f1, 0));
-            rc = copy_to_ring(h, frames, T - keep, T, timer0, cudaMemcpyDeviceToDevice, h->sstream);
-            if (rc) return rc;
+    if (src.cur) {
+        const int keep = std::min(T, h->n);
+        // the slots they land on may still be read as history by the batch before the previous one: its temporal
+        // pass (front stream) or, on the generic path, its per-frame kernels (back stream) must be done
+        if (have_prev2) {
+            CK(cudaStreamWaitEvent(h->sstream, prev2.ev_f1, 0));
+            CK(cudaStreamWaitEvent(h->sstream, prev2.ev_d1, 0));
         }
+        rc = copy_to_ring(h, dev_frames, T - keep, T, timer0, cudaMemcpyDeviceToDevice, h->sstream);
+        if (rc) return rc;
     }
+    CK(cudaEventRecord(c.ev_src, h->sstream));
     CK(cudaStreamWaitEvent(h->stream, c.ev_thr, 0));
     c.bits_parity = (int)(h->submitted & 1);
     rc = launch_fused(h, c, src, T, timer0, h->dy_timer);
@@ -811,6 +841,7 @@ extern "C" int mdb_collect_batch(mdb_handle h, mdb_frame_info *infos, int32_t *l
         CK(cudaEventElapsedTime(&a, c.ev_f0, c.ev_f1));
         CK(cudaEventElapsedTime(&b, c.ev_d0, c.ev_d1));
         h->fused_ms = a + b;  // temporal (front stream) and act + dst (back stream), each bracketed by events
+        h->temporal_ms = a; h->spatial_ms = b;
     }
     h->last_fused_launches = h->fused_launches;
     int rc = finish_batch(h, c, infos, lines, nonline_prob, raw_lines);
@@ -893,6 +924,16 @@ extern "C" int mdb_get_fused_time(mdb_handle h, float *ms, int32_t *launches) {
     return MDB_OK;
 }
 
+// read-only counters and timings by name (tests, bench): see include/metdet_b200.h
+extern "C" int mdb_get_info(mdb_handle h, const char *name, double *value) {
+    if (!h || !name || !value) return fail(MDB_ERR_INVALID, "mdb_get_info: null argument");
+    if (!strcmp(name, "temporal_generation")) { *value = h->sk.t_last; return MDB_OK; }
+    if (!strcmp(name, "temporal_ms")) { *value = h->temporal_ms; return MDB_OK; }
+    if (!strcmp(name, "spatial_ms")) { *value = h->spatial_ms; return MDB_OK; }
+    if (!strcmp(name, "stream_kernel")) { *value = h->sk.ok && h->use_stream_kernel; return MDB_OK; }
+    return fail(MDB_ERR_INVALID, "mdb_get_info: unknown name %s", name);
+}
+
 // debug: ms offsets (from the moment the timeline was enabled) of the marks of the batch collected last:
 // [0] front start, [1] thresholds done, [2] = ev_f0 (temporal start), [3] = ev_f1 (act done),
 // [4] dst done (= back: order start), [5] tier-1 Hough done, [6] all Hough done, [7] results copied,
@@ -944,7 +985,8 @@ extern "C" int mdb_set_option(mdb_handle h, const char *name, int value) {
             return fail(MDB_ERR_INVALID, "mdb_set_option: temporal_kdiv=%d not possible here", value);
         return MDB_OK;
     }
-    if (!strcmp(name, "temporal_version")) { h->sk.t_version = value == 1 ? 1 : 2; return MDB_OK; }
+    if (!strcmp(name, "temporal_version")) { h->sk.t_version = value >= 1 && value <= 3 ? value : 3; return MDB_OK; }
+    if (!strcmp(name, "t3_variant")) { h->sk.t3_variant = value; return MDB_OK; }
     if (!strcmp(name, "force_dense")) { h->sk.force_dense = value; return MDB_OK; }
     if (!strcmp(name, "force_strip")) { h->sk.force_strip = value; return MDB_OK; }
     if (!strcmp(name, "sp_rows")) { h->sk.sp_rows = value; return MDB_OK; }

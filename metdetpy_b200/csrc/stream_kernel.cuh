@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "spatial_kernel.cuh"
 #include "temporal_kernel.cuh"
+#include "temporal3_dispatch.cuh"
 
 #define ST_K 8          // frames in flight per thread (cp.async groups)
 
@@ -30,7 +31,10 @@ struct StreamState {
     int W = 0, H = 0, n = 0, max_batch = 0, device = 0;
     int t_threads = 32;     // CTA size of the temporal kernel
     int t_wpt = 2;          // 32-bit words (4 px) per thread in the temporal kernel
-    int t_version = 2;      // 2: temporal2_kernel (temporal_kernel.cuh); 1: the first-generation kernel below
+    int t_version = 3;      // 3: temporal3_kernel (register ring; falls back to 2 for windows without a shape or frames
+                            // that are not contiguous); 2: temporal2_kernel (temporal_kernel.cuh); 1: the first-generation kernel below
+    int t3_variant = 0;     // tuning hook (temporal3_dispatch.cuh)
+    int t_last = 0;         // which generation the last launch used
     int t_kdiv = 1;         // temporal2: sub-blocks per window (divides n)
     int t_kdiv_req = 0;     // test hook: force this many sub-blocks (0 = choose)
     int dst_rows = 32;      // output rows per warp strip in dst_dense_kernel
@@ -41,6 +45,7 @@ struct StreamState {
     // predicate bits [max_batch][H][W/32], two buffers: batch k+1's temporal pass (front stream) writes one
     // while batch k's act pass (back stream) still reads the other
     uint32_t *d_bits = nullptr, *d_bits2 = nullptr;
+    T3Table t3tab;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -255,6 +260,7 @@ static inline void stream_state_free(StreamState &s) {
     if (s.d_bits) cudaFree(s.d_bits);
     if (s.d_bits2) cudaFree(s.d_bits2);
     s.d_bits = s.d_bits2 = nullptr;
+    for (uint2 *&p : s.t3tab.d_tab) { if (p) cudaFree(p); p = nullptr; }
     s.ok = 0;
 }
 
@@ -309,13 +315,16 @@ static inline int stream_state_init(StreamState &s, int W, int H, int n, int dev
     // the wider variant only pays when its ring still leaves >= 8 warps per SM
     const bool wide = (size_t)(2 * n + ST_K) * 16 * 32 * 8 <= budget;
     if (stream_state_config(s, wide ? 4 : 2) != 0 && stream_state_config(s, 2) != 0) return 0;
-    if (cudaMalloc((void **)&s.d_bits, (size_t)max_batch * H * (W / 32) * sizeof(uint32_t)) != cudaSuccess ||
-        cudaMalloc((void **)&s.d_bits2, (size_t)max_batch * H * (W / 32) * sizeof(uint32_t)) != cudaSuccess) {
+    if (cudaMalloc((void **)&s.d_bits, (size_t)(max_batch + T3_SLACK_PLANES) * H * (W / 32) * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc((void **)&s.d_bits2, (size_t)(max_batch + T3_SLACK_PLANES) * H * (W / 32) * sizeof(uint32_t)) != cudaSuccess) {
         cudaGetLastError();
         stream_state_free(s);
         return 0;  // fall back to the generic per-frame kernel
     }
     s.sp_rows = 64;
+    s.t3tab.cap = max_batch + T3_SLACK_PLANES;
+    for (uint2 *&p : s.t3tab.d_tab)
+        if (cudaMalloc((void **)&p, (size_t)s.t3tab.cap * sizeof(uint2)) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
 #define ST_SETATTR(K)                                                                                      \
     if (cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess || \
         cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess)       \
@@ -349,10 +358,17 @@ static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long t
     uint32_t *const bits = parity ? s.d_bits2 : s.d_bits;
     const int HWG = (int)((size_t)s.W * s.H / (4 * s.t_wpt));  // pixel groups = threads
     const int nt = s.t_threads;
-    const size_t smem = stream_temporal_smem(s, nt, T, s.t_version);
+    const size_t smem = stream_temporal_smem(s, nt, T, s.t_version == 1 ? 1 : 2);
     const int grid = (HWG + nt - 1) / nt;
     uint8_t *bits8 = reinterpret_cast<uint8_t *>(bits);
-    if (s.t_version == 2) {
+    int t3rc = -2;
+    if (s.t_version == 3) {
+        t3rc = temporal3_launch(s.n, s.t3_variant, src, timer0, T, (int)((size_t)s.W * s.H / 8), d_thr, bits8, s.t3tab, parity, st1);
+        if (t3rc == -1) return -1;
+    }
+    s.t_last = t3rc == 0 ? 3 : (s.t_version == 1 ? 1 : 2);
+    if (t3rc == 0) {
+    } else if (s.t_version != 1) {
 #define T2_LAUNCH(M, WP, NT)                                                                                            \
     do {                                                                                                                \
         if (s.t_kdiv > 1) temporal2_kernel<M, WP, NT, true><<<grid, NT, smem, st1>>>(src, timer0, T, s.n, s.t_kdiv, HWG, d_thr, bits8); \

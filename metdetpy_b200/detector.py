@@ -165,6 +165,11 @@ class _Engine:
     def set_option(self, name: str, value: int):
         check(self.lib.mdb_set_option(self.handle, name.encode(), int(value)), "mdb_set_option")
 
+    def info(self, name: str) -> float:
+        v = C.c_double()
+        check(self.lib.mdb_get_info(self.handle, name.encode(), C.byref(v)), "mdb_get_info")
+        return v.value
+
     def stream_ptr(self) -> int:
         p = C.c_void_p()
         check(self.lib.mdb_get_stream(self.handle, C.byref(p)), "mdb_get_stream")

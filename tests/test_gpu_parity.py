@@ -58,13 +58,13 @@ def test_per_frame_api_matches_reference_golden(name):
 
 
 @pytest.mark.parametrize("mode", ["generic", "stream", "stream_dense_dst", "stream_strip_act", "stream_temporal_v1",
-                                  "stream_subblocks"])
+                                  "stream_temporal_v2", "stream_subblocks"])
 @pytest.mark.parametrize("batch", [1, 7, 32])
 @pytest.mark.parametrize("name", DET_CASES)
 def test_batched_api_matches_reference_golden(name, batch, mode):
-    """generic = one fused launch per frame; stream = temporal2 + act4/act + sparse dst; the extra modes
-    force the full-scan dst kernel (list-overflow path), the warp-strip act kernel and the
-    first-generation temporal kernel."""
+    """generic = one fused launch per frame; stream = temporal3 (register ring; temporal2 for single-frame
+    batches) + act4/act + sparse dst; the extra modes force the full-scan dst kernel (list-overflow path), the
+    warp-strip act kernel and the first- and second-generation temporal kernels."""
     from metdetpy_b200.detector import M3Detector
     g = load_det_case(name)
     det = M3Detector(g["n"] / g["fps"] + 1e-9, g["fps"], g["mask"], 10, _cfg(g["cfg"]), None,
@@ -74,7 +74,7 @@ def test_batched_api_matches_reference_golden(name, batch, mode):
     det._eng.set_option("stream_kernel", stream_kernel)
     det._eng.set_option("force_dense", int(mode == "stream_dense_dst"))
     det._eng.set_option("force_strip", int(mode == "stream_strip_act"))
-    det._eng.set_option("temporal_version", 1 if mode == "stream_temporal_v1" else 2)
+    det._eng.set_option("temporal_version", {"stream_temporal_v1": 1, "stream_temporal_v2": 2, "stream_subblocks": 2}.get(mode, 3))
     if mode == "stream_subblocks":  # sub-blocked van Herk (long windows use it by default): force a split of n
         k = next((k for k in (5, 4, 3, 2) if g["n"] % k == 0 and g["n"] // k >= 2), 0)
         if not k or W % 32 or not 2 <= g["n"] <= 128:
@@ -179,6 +179,115 @@ def test_random_streams_against_oracle(seed, W, H, n, dy, sens):
     assert np.array_equal(det1.stack.max, ref.stack.max)
     assert np.array_equal(det1.stack.mean, ref.stack.mean)
     assert np.array_equal(det1.stack.sum, ref.stack.sum)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16, 18, 20, 21, 24, 25, 28, 30, 32, 36, 40, 48, 50,
+                               60, 64, 11, 33])
+@pytest.mark.parametrize("apply_mask", [False, True])
+def test_temporal3_every_window_shape_against_oracle(n, apply_mask):
+    _temporal3_case(n, apply_mask, 0)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 16, 17, 18, 19, 20, 21, 22, 23])
+def test_temporal3_tuning_variants_against_oracle(variant):
+    """The alternative shapes of the n = 30 window (temporal3_dispatch.cuh): register-fed (1-6) and bulk-copy-fed
+    (cp.async.bulk + mbarrier stage ring, 7-12)."""
+    _temporal3_case(30, variant % 2 == 0, variant)
+
+
+def _temporal3_case(n, apply_mask, variant):
+    """Every (U, BL, P, K) shape of temporal3_kernel (temporal3_dispatch.cuh; n = 11 and 33 have none and take
+    temporal2): batches that end inside a van Herk block, start in the warm-up, and hand history over through the
+    ring; device-side masking.  Mask, threshold and on-pixel count must equal the CPU oracle bit for bit."""
+    from metdetpy_b200 import BinaryCfg, BinaryCoreCfg, DynamicCfg, HoughLineCfg
+    from metdetpy_b200.detector import M3Detector
+    from oracle import m3_oracle as O
+    rng = np.random.default_rng(100 + n)
+    W, H = 96, 40
+    sizes = [n + 3, 2, 2 * n + 1, 7, 3 * n - 1, n, 1, n + 1]
+    T = sum(sizes)
+    base = rng.integers(20, 60, (H, W))
+    frames = np.clip(base[None] + rng.normal(0, 2.5, (T, H, W)), 0, 255).astype(np.uint8)
+    for t in range(T):
+        x, y = (7 * t) % (W - 14), (3 * t) % (H - 3)
+        frames[t, y:y + 2, x:x + 14] = 180 + (t % 70)
+        if t % 9 == 0:
+            frames[t, H // 2:H // 2 + 4, W // 2:W // 2 + 4] = 255
+    mask = np.ones((H, W), np.uint8)
+    mask[: H // 6, : W // 3] = 0
+    masked = frames * mask[None]
+    kw = dict(adaptive=True, init_value=7, sensitivity="normal", area=0.2, interval=1, hough=(6, 6, 4), dy_mask=True)
+    ref = O.M3DetectorOracle(n / 10 + 1e-9, 10, mask, 10, backend="numpy", **kw)
+    cfg = BinaryCfg(BinaryCoreCfg(True, 7, "normal", 0.2, 1), HoughLineCfg(6, 6, 4), DynamicCfg(True, 5))
+    det = M3Detector(n / 10 + 1e-9, 10, mask, 10, cfg, None, max_batch=max(sizes), apply_mask=apply_mask)
+    det._eng.set_option("t3_variant", variant)
+    s = 0
+    for b in sizes:
+        res, dst = det.detect_many((frames if apply_mask else masked)[s:s + b], return_dst=True)
+        for i in range(b):
+            ref.update(masked[s + i]); ref.detect()
+            info = det.last_infos[i]
+            assert info["bi_threshold"] == ref.bi_threshold, (s + i)
+            assert np.array_equal(dst[i], ref.dst), (n, s + i, int(np.count_nonzero(dst[i] != ref.dst)))
+            assert info["n_on"] == int(np.count_nonzero(ref.dst)), s + i
+        if b > 1:  # single host frames go through the ring and the second-generation kernel
+            assert det._eng.info("temporal_generation") == (2 if n in (11, 33) else 3), (n, b)
+        s += b
+    det.close()
+
+
+def test_stack_readback_after_device_batches():
+    """SNR_SW.max / .mean / .sum (utils.py:288-300) after batched calls: the ring must hold the last n frames of a
+    batch, not n-1 (the window of the newest frame)."""
+    from metdetpy_b200 import BinaryCfg
+    from metdetpy_b200.detector import M3Detector
+    rng = np.random.default_rng(5)
+    n, H, W = 6, 32, 64
+    frames = rng.integers(0, 256, (40, H, W), dtype=np.uint8)
+    det = M3Detector(n / 10 + 1e-9, 10, np.ones((H, W), np.uint8), 10, BinaryCfg(), None, max_batch=16)
+    s = 0
+    for b in [16, 3, 16, 5]:
+        det.detect_many(frames[s:s + b])
+        s += b
+        win = frames[max(0, s - n):s].astype(np.uint32)
+        assert np.array_equal(det.stack.max, win.max(0).astype(np.uint8)), s
+        assert np.array_equal(det.stack.sum, win.sum(0)), s
+        assert np.array_equal(det.stack.mean, (win.sum(0) // min(n, s)).astype(np.uint8)), s
+    det.close()
+
+
+def test_three_batches_in_flight_generic_kernel():
+    """submit / collect with three batches in flight on the generic per-frame kernel (width not a multiple of 32):
+    ring slots and staging buffers must not be overwritten while an older batch still reads them."""
+    from metdetpy_b200 import BinaryCfg, BinaryCoreCfg, DynamicCfg, HoughLineCfg
+    from metdetpy_b200.detector import M3Detector
+    from oracle import m3_oracle as O
+    rng = np.random.default_rng(8)
+    n, H, W, B = 5, 120, 203, 6
+    T = 14 * B
+    frames = np.clip(40 + rng.normal(0, 3, (T, H, W)), 0, 255).astype(np.uint8)
+    for t in range(T):
+        frames[t, (3 * t) % (H - 2):(3 * t) % (H - 2) + 2, (5 * t) % (W - 20):(5 * t) % (W - 20) + 20] = 220
+    mask = np.ones((H, W), np.uint8)
+    kw = dict(adaptive=True, init_value=7, sensitivity="normal", area=0.2, interval=1, hough=(6, 6, 4), dy_mask=True)
+    ref = O.M3DetectorOracle(n / 10 + 1e-9, 10, mask, 10, backend="numpy", **kw)
+    cfg = BinaryCfg(BinaryCoreCfg(True, 7, "normal", 0.2, 1), HoughLineCfg(6, 6, 4), DynamicCfg(True, 5))
+    det = M3Detector(n / 10 + 1e-9, 10, mask, 10, cfg, None, max_batch=B)
+    want = []
+    for t in range(T):
+        ref.update(frames[t]); ref.detect()
+        want.append((ref.bi_threshold, int(np.count_nonzero(ref.dst)), ref.lines_num))
+    got = []
+    nb = T // B
+    for k in range(min(3, nb)):
+        det.submit(frames[k * B:(k + 1) * B].ctypes.data, B, False)
+    for k in range(nb):
+        det.collect()
+        got += [(int(i["bi_threshold"]), int(i["n_on"]), int(i["lines_num"])) for i in det.last_infos[:B]]
+        if k + 3 < nb:
+            det.submit(frames[(k + 3) * B:(k + 4) * B].ctypes.data, B, False)
+    assert got == want
+    det.close()
 
 
 @pytest.mark.parametrize("thr,lo,hi", [(12, 4096, 16384), (10, 16384, 1 << 30)])
