@@ -152,6 +152,15 @@ int mdb_get_launch_count(mdb_handle h, int64_t *count);
 /* Device time (ms, CUDA events on the handle's stream) the fused mask kernel(s) took in the most
  * recent batch, and how many launches that was. */
 int mdb_get_fused_time(mdb_handle h, float *ms, int32_t *launches);
+/* Back to the state right after mdb_create (empty window, initial thresholds, timer 0) without giving up the
+ * device buffers; mdb_seek may follow.  No batch may be in flight. */
+int mdb_reset(mdb_handle h);
+/* Noise sums (the integer pair per noise sample that SNR_SW.update, MetLib/Detector.py:73-91, turns into a
+ * standard deviation) of the sample timers among the DEVICE frames t0 .. t0+T-1, T <= max_batch + window, on the
+ * handle's own stream and buffers.  Only samples whose whole window lies inside the supplied frames (or starts at
+ * global frame 0) are evaluated; sums[T][2] (host) is zero elsewhere.  Synchronous.  This is what one rank of a
+ * time-sharded run computes for its chunk before the ranks exchange the sums and replay the threshold recurrence. */
+int mdb_noise_sums_dev(mdb_handle h, const uint8_t *frames, int T, int64_t t0, uint64_t *sums);
 /* Read-only counters / timings of the most recent batch by name: "temporal_ms" (stack->diff->threshold pass),
  * "spatial_ms" (median + close + dy-mask + mask bytes), "temporal_generation" (which temporal kernel ran: 3 =
  * register ring, 2 = shared-memory ring, 1 = first generation, 0 = none), "stream_kernel" (1 if the time-tiled

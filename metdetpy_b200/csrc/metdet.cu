@@ -95,6 +95,8 @@ struct mdb_detector {
     int RA = 0, Wb = 0;
     DevState *d_state = nullptr;
     unsigned long long *d_noise = nullptr;
+    unsigned long long *d_noise2 = nullptr;  // mdb_noise_sums_dev: [max_batch + n][2]
+    unsigned long long *h_noise2 = nullptr;  // pinned staging of the same size
     int32_t *d_accum = nullptr;   // tier-2/3 accumulators [slots][180][numrho]
     uint32_t *d_bitmap = nullptr, *d_walk = nullptr, *d_okeys = nullptr, *d_oidx = nullptr;  // tier 3
     long long *d_prof = nullptr;  // optional per-frame PPHT phase cycle counters (debug)
@@ -156,7 +158,8 @@ static void free_all(mdb_detector *h) {
     if (h->stream3) cudaStreamSynchronize(h->stream3);
     if (h->cstream) cudaStreamSynchronize(h->cstream);
     if (h->sstream) cudaStreamSynchronize(h->sstream);
-    void *dev[] = {h->d_ring, h->d_mask, h->d_stage[0], h->d_stage[1], h->d_act, h->d_state, h->d_noise, h->d_accum,
+    if (h->h_noise2) cudaFreeHost(h->h_noise2);
+    void *dev[] = {h->d_ring, h->d_mask, h->d_stage[0], h->d_stage[1], h->d_act, h->d_state, h->d_noise, h->d_noise2, h->d_accum,
                    h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_prof, h->d_cbits};
     for (void *p : dev)
         if (p) cudaFree(p);
@@ -187,6 +190,20 @@ static void free_all(mdb_detector *h) {
     if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->cstream) cudaStreamDestroy(h->cstream);
     delete h;
+}
+
+// initial scalar state: LineDetector.__init__ (Detector.py:204-209), SNR_SW.__init__ (:58-61)
+static DevState initial_state(const mdb_detector *h) {
+    DevState st;
+    memset(&st, 0, sizeof st);
+    st.ema_init_m = 1.0 - (double)h->cfg.nz_interval / 60.0;
+    st.ema_cur_m = st.ema_init_m;
+    st.ema_warm = (double)h->n;
+    st.ema_value = 0.0;
+    static const int abs_sens[3] = {7, 5, 3};  // low, normal, high
+    st.bi_threshold = h->cfg.adaptive ? abs_sens[h->cfg.sensitivity] : h->cfg.init_value;
+    st.thr_float = (double)st.bi_threshold;
+    return st;
 }
 
 extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle *out) {
@@ -331,16 +348,7 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
         CKH(cudaEventCreateWithFlags(&c.ev_src, cudaEventDisableTiming));
     }
 
-    // scalar state: LineDetector.__init__ (Detector.py:204-209), SNR_SW.__init__ (:58-61)
-    DevState st;
-    memset(&st, 0, sizeof st);
-    st.ema_init_m = 1.0 - (double)cfg->nz_interval / 60.0;
-    st.ema_cur_m = st.ema_init_m;
-    st.ema_warm = (double)h->n;
-    st.ema_value = 0.0;
-    static const int abs_sens[3] = {7, 5, 3};  // low, normal, high
-    st.bi_threshold = cfg->adaptive ? abs_sens[cfg->sensitivity] : cfg->init_value;
-    st.thr_float = (double)st.bi_threshold;
+    const DevState st = initial_state(h);
     CKH(cudaMemcpyAsync(h->d_state, &st, sizeof st, cudaMemcpyHostToDevice, h->stream));
 
     // trig table exactly as OpenCV builds it: (float)cos((double)n * (double)(float)theta)
@@ -779,6 +787,63 @@ extern "C" int mdb_seek(mdb_handle h, int64_t timer) {
     if (h->timer != 0 || h->submitted != 0) return fail(MDB_ERR_STATE, "mdb_seek: only before the first frame");
     h->timer = h->dy_timer = timer;
     h->seek0 = timer;
+    return MDB_OK;
+}
+
+extern "C" int mdb_reset(mdb_handle h) {
+    if (!h) return fail(MDB_ERR_INVALID, "mdb_reset: null handle");
+    if (in_flight(h)) return fail(MDB_ERR_STATE, "mdb_reset: a submitted batch has not been collected");
+    CK(cudaSetDevice(h->cfg.device));
+    for (cudaStream_t st : {h->stream, h->stream2, h->stream3, h->cstream, h->sstream}) CK(cudaStreamSynchronize(st));
+    CK(cudaMemsetAsync(h->d_ring, 0, (size_t)h->R * h->HW, h->stream));
+    CK(cudaMemsetAsync(h->d_act, 0, (size_t)h->RA * h->H * h->Wb * sizeof(uint32_t), h->stream));
+    const DevState st = initial_state(h);
+    CK(cudaMemcpyAsync(h->d_state, &st, sizeof st, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->timer = h->dy_timer = h->seek0 = 0;
+    h->submitted = h->collected = 0;
+    h->last_T = 0;
+    h->front_dirty = false;
+    return MDB_OK;
+}
+
+// Noise sums of the sample timers among device frames t0 .. t0+T-1, on the handle's scalar stream and buffers (no
+// allocation): what a rank of a time-sharded run computes for its chunk before the thresholds are replayed.
+extern "C" int mdb_noise_sums_dev(mdb_handle h, const uint8_t *frames, int T, int64_t t0, uint64_t *sums) {
+    if (!h || !frames || !sums || T < 1 || t0 < 0) return fail(MDB_ERR_INVALID, "mdb_noise_sums_dev: bad arguments");
+    const int cap = h->cfg.max_batch + h->n;
+    if (T > cap) return fail(MDB_ERR_INVALID, "mdb_noise_sums_dev: T=%d exceeds max_batch + window = %d", T, cap);
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->d_noise2) {
+        CK(cudaMalloc((void **)&h->d_noise2, (size_t)cap * 16));
+        CK(cudaHostAlloc((void **)&h->h_noise2, (size_t)cap * 16, cudaHostAllocDefault));
+    }
+    const mdb_config &c = h->cfg;
+    const int rh = c.roi[2] - c.roi[0], rw = c.roi[3] - c.roi[1];
+    const long long std_interval = (long long)c.nz_interval * h->n;
+    const long long min_tau = t0 == 0 ? 0 : t0 + h->n;  // the whole window must lie inside the supplied frames
+    SampleList sl;
+    sl.count = 0;
+    for (int i = 0; i < T && sl.count >= 0; i++) {
+        const long long tau = t0 + i + 1;
+        if (tau >= min_tau && ((tau > 1 && tau <= h->n) || (tau > h->n && std_interval > 0 && tau % std_interval == 0))) {
+            if (sl.count < 63) sl.idx[sl.count++] = i;
+            else sl.count = -1;
+        }
+    }
+    memset(sums, 0, (size_t)T * 16);
+    if (sl.count == 0) return MDB_OK;
+    FrameSrc src;
+    src.ring = nullptr; src.cur = frames; src.t0 = t0; src.mask = c.apply_mask ? h->d_mask : nullptr; src.R = 1; src.HW = h->HW;
+    CK(cudaMemsetAsync(h->d_noise2, 0, (size_t)T * 16, h->sstream));
+    const int gx = std::max(1, std::min((rh * rw + 255) / 256, 592));
+    noise_sample_kernel<<<dim3(gx, sl.count < 0 ? T : sl.count), 256, 0, h->sstream>>>(
+        src, h->W, h->n, t0, std_interval, c.roi[0], c.roi[1], rh, rw, h->d_noise2, min_tau, sl);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    CK(cudaMemcpyAsync(h->h_noise2, h->d_noise2, (size_t)T * 16, cudaMemcpyDeviceToHost, h->sstream));
+    CK(cudaStreamSynchronize(h->sstream));
+    memcpy(sums, h->h_noise2, (size_t)T * 16);
     return MDB_OK;
 }
 

@@ -63,12 +63,12 @@ static inline int temporal3_launch(int n, int variant, const FrameSrc &src, long
     }
     if (n == 30 && variant) {
         switch (variant) {
-            T3_CASE(1, 30, 15, 1, 5, 4)
+            T3_CASE(1, 30, 15, 1, 5, 3)
             T3_CASE(2, 30, 10, 1, 6, 3)
-            T3_CASE(3, 30, 10, 1, 5, 4)
+            T3_CASE(3, 30, 10, 1, 5, 3)
             T3_CASE(4, 30, 15, 1, 6, 3)
             T3_CASE(5, 30, 10, 1, 10, 3)
-            T3_CASE(6, 30, 6, 1, 6, 4)
+            T3_CASE(6, 30, 6, 1, 6, 3)
             T3_BULK(7, 30, 10, 1, 5, 4)
             T3_BULK(8, 30, 10, 1, 5, 3)
             T3_BULK(9, 30, 15, 1, 5, 3)
@@ -81,7 +81,7 @@ static inline int temporal3_launch(int n, int variant, const FrameSrc &src, long
             T3_PF(16, 30, 10, 1, 10, 3)
             T3_PF(17, 30, 10, 1, 2, 4)
             T3_CASE(18, 15, 15, 2, 5, 4)
-            T3_CASE(19, 15, 15, 2, 15, 4)
+            T3_CASE(19, 30, 10, 1, 6, 4)
             T3_CASE(20, 15, 5, 2, 5, 5)
             T3_CASE(21, 15, 5, 2, 15, 5)
             T3_CASE(22, 15, 15, 2, 15, 5)
@@ -103,14 +103,16 @@ static inline int temporal3_launch(int n, int variant, const FrameSrc &src, long
         T3_CASE(14, 14, 14, 1, 7, 5)
         T3_CASE(15, 15, 15, 1, 5, 5)
         T3_CASE(16, 16, 16, 1, 8, 5)
-        T3_CASE(18, 18, 9, 1, 6, 4)
-        T3_CASE(20, 20, 10, 1, 5, 4)
-        T3_CASE(21, 21, 7, 1, 7, 4)
-        T3_CASE(24, 24, 12, 1, 6, 4)
-        T3_CASE(25, 25, 5, 1, 5, 4)
-        T3_CASE(28, 28, 14, 1, 7, 4)
-        T3_CASE(30, 30, 10, 1, 6, 4)
-        T3_CASE(32, 32, 16, 1, 8, 4)
+        // measured at 4K, n = 30 (scripts/t3_tune.py): half of the ring in the shared-memory page and all of a body's
+        // frames in flight (no spills at 128 registers, 16 warps per SM) beats the whole ring in registers
+        T3_CASE(18, 9, 9, 2, 9, 4)
+        T3_CASE(20, 10, 10, 2, 10, 4)
+        T3_CASE(21, 21, 7, 1, 7, 3)
+        T3_CASE(24, 12, 12, 2, 12, 4)
+        T3_CASE(25, 25, 5, 1, 5, 3)
+        T3_CASE(28, 14, 14, 2, 14, 4)
+        T3_CASE(30, 15, 15, 2, 15, 4)
+        T3_CASE(32, 16, 16, 2, 16, 4)
         T3_CASE(36, 18, 9, 2, 6, 3)
         T3_CASE(40, 20, 10, 2, 5, 3)
         T3_CASE(48, 24, 12, 2, 6, 3)

@@ -64,8 +64,11 @@ T3_HD const uint8_t *addr(const uint8_t *base, unsigned idx, unsigned stride) {
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(idx), "r"(stride), "l"((unsigned long long)base));
     return reinterpret_cast<const uint8_t *>(r);
 }
-// sum of the four bytes of q (disjoint bits: an OR) in the low byte: one IDP.4A instead of IMAD + SHF
-T3_HD unsigned bytesum(unsigned q) { return __dp4a(q, 0x01010101u, 0u); }
+// eight 0x00/0xff pixel bytes (two words, pixel order) -> one byte of bits: two IDP.4A with signed weights -2^k
+// (0xff = -1 as s8), instead of two LOP3 + multiply + shift on the ALU pipe
+T3_HD unsigned bits8(unsigned m0, unsigned m1) {
+    return (unsigned)__dp4a((int)m1, (int)0x80C0E0F0, __dp4a((int)m0, (int)0xF8FCFEFF, 0));
+}
 // ---- bulk-copy feed (FEED = 1): cp.async.bulk global -> shared, completion on an mbarrier (UBLKCP + SYNCS in SASS)
 T3_HD uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 T3_HD void mbar_init(uint32_t bar, unsigned count) {
@@ -119,7 +122,14 @@ T3_HD void ldg8_if(unsigned &x, unsigned &y, const uint8_t *p, int idx, int rem)
     if (idx < rem) { const uint2 v = ldg8(p); x = v.x; y = v.y; }
 }
 T3_HD const uint8_t *addr(const uint8_t *base, unsigned idx, unsigned stride) { return base + (size_t)idx * stride; }
-T3_HD unsigned bytesum(unsigned q) { return (q & 0xff) + ((q >> 8) & 0xff) + ((q >> 16) & 0xff) + (q >> 24); }
+T3_HD unsigned bits8(unsigned m0, unsigned m1) {
+    unsigned r = 0;
+    for (int k = 0; k < 4; k++) {
+        if ((m0 >> (8 * k)) & 0x80) r |= 1u << k;
+        if ((m1 >> (8 * k)) & 0x80) r |= 16u << k;
+    }
+    return r;
+}
 // the bulk-copy feed is not emulated: the host build reads the frames straight from memory
 T3_HD uint32_t smem_u32(const void *) { return 0; }
 T3_HD void mbar_init(uint32_t, unsigned) {}
@@ -250,7 +260,7 @@ T3_HD void thread_main(const FrameSrc &src, long long t0, int T, int g, int tid,
 
     // ---- batch frames: contiguous at src.cur ---------------------------------------------------------------
     // 32-bit strides: a frame's address is  base + immediate * HW  (one IMAD.WIDE.U32); (U + K) * HW < 2^32
-    const unsigned HWu = (unsigned)HW, bsu = (unsigned)bstride;
+    const unsigned HWu = (unsigned)HW;
     const uint8_t *gcur = src.cur + off;
     constexpr int KR = FEED == 1 ? 1 : K;
     // FEED = 2: register feed as FEED = 0, plus thread 0 of the CTA asks the TMA unit to pull the CTA's pixels of the
@@ -297,7 +307,7 @@ T3_HD void thread_main(const FrameSrc &src, long long t0, int T, int g, int tid,
     // frames left, kept in a vector register (nz is zero, but not provably): the per-frame "is there a frame K
     // ahead" test is then one ISETP instead of a uniform compare + a predicate transfer
     const int nz = g >> 31;
-    const unsigned one = (unsigned)(T > 0);  // 1, but not provably: pointer += stride stays ONE IMAD.WIDE.U32 (FMA pipe)
+
     unsigned parity = 0;  // FEED 1: body number & 1
     int fbase = 0;        // FEED 1: first frame of the body
     for (int rem = T + nz; rem > 0; rem -= U) {
@@ -325,7 +335,7 @@ T3_HD void thread_main(const FrameSrc &src, long long t0, int T, int g, int tid,
             } else {
                 x0 = pf0[j % KR]; x1 = pf1[j % KR];
                 ldg8_if(pf0[j % KR], pf1[j % KR], gp, j + K, rem);
-                gp = addr(gp, one, HWu);
+                gp += HW;
             }
             if (MASKED) { x0 &= mk0; x1 &= mk1; }
             const unsigned o0 = r0[j], o1 = r1[j];  // frame t-N leaves the window
@@ -354,9 +364,8 @@ T3_HD void thread_main(const FrameSrc &src, long long t0, int T, int g, int tid,
             const unsigned va1 = wa1 * Lu + cpk - SA1, vb1 = wb1 * Lu + cpk - SB1;
             const unsigned M0 = prmt(va0, vb0, 0xFBD9u);  // sign-replicate bytes 1,5,3,7 -> 0x00/0xff per pixel
             const unsigned M1 = prmt(va1, vb1, 0xFBD9u);
-            const unsigned q = (M0 & 0x08040201u) | (M1 & 0x80402010u);
-            *const_cast<uint8_t *>(bo) = (uint8_t)bytesum(q);
-            bo = addr(bo, one, bsu);
+            *const_cast<uint8_t *>(bo) = (uint8_t)bits8(M0, M1);
+            bo += bstride;
             if (FEED == 1 && j % K == K - 1) {
                 // stage consumed.  Its data was read into registers above; the arrive orders those reads before the
                 // producer's next bulk copy into the stage.

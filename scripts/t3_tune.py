@@ -47,6 +47,6 @@ if n == 30:
                     (9, "bulk BL15 K5 minb3"), (10, "bulk BL10 K10 minb4"), (11, "bulk BL6 K6 minb4"),
                     (12, "bulk BL10 K3 minb4"), (13, "L2pf BL10 K5 minb4"), (14, "L2pf BL10 K3 minb4"),
                     (15, "L2pf BL10 K6 minb4"), (16, "L2pf BL10 K10 minb3"), (17, "L2pf BL10 K2 minb4"),
-                    (18, "U15 P2 BL15 K5 minb4"), (19, "U15 P2 BL15 K15 minb4"), (20, "U15 P2 BL5 K5 minb5"),
+                    (18, "U15 P2 BL15 K5 minb4"), (19, "U30 P1 BL10 K6 minb4 (spills)"), (20, "U15 P2 BL5 K5 minb5"),
                     (21, "U15 P2 BL5 K15 minb5"), (22, "U15 P2 BL15 K15 minb5"), (23, "BL10 K15 minb3")]:
         run(f"temporal3 variant {v}: {name}", {"temporal_version": 3, "t3_variant": v})
