@@ -4,10 +4,19 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 A step = one pass of the hot path (T x {update; detect}: noise sample + threshold recurrence, fused
-stack->diff->median->threshold->close->dy-mask kernel, PPHT Hough, NMS) over one batch of
-`--batch` synthetic frames. Workload at every N: BASELINE.json configs[2] -- synthetic 3840x2160
-@30 fps, window n=30, adaptive threshold, dynamic mask, HoughLinesP (per GPU; weak scaling: each
-rank owns its own time chunk of the stream).  Prints ONE JSON line (see README / DESIGN.md).
+stack->diff->median->threshold->close->dy-mask chain, PPHT Hough, NMS) over `--bps` batches of `--batch`
+synthetic frames per GPU.  Workload at every N: BASELINE.json configs[2] -- synthetic 3840x2160 @30 fps,
+window n=30, adaptive threshold, dynamic mask, HoughLinesP.
+
+N = 1: one sequential stream on the product pipeline (three batches in flight).
+N > 1: ONE stream of N time chunks (weak scaling: K steps per rank) through the time-sharded algorithm of
+SURVEY 8(e) on the same pipeline: every rank computes the integer noise sums of its chunk (mdb_noise_sums_dev), one
+NCCL all-gather of the (timer, sum d, sum d^2) triples, bit-identical threshold replay (mdb_replay_thresholds),
+mdb_seek + a (2n-2)-frame halo batch + the chunk with replayed thresholds (mdb_submit_batch_thr); line records are
+all-gathered once per step on a side stream.  No frame crosses GPUs.  Every rank then re-runs frames 0 .. end of its
+chunk sequentially and compares per-batch digests (thresholds, on-pixel counts, raw Hough segments): "sharded_parity".
+
+Prints ONE JSON line (see README / DESIGN.md).
 """
 from __future__ import annotations
 
@@ -25,32 +34,38 @@ sys.path.insert(0, REPO)
 
 METRIC = "4K frames/sec through M3Detector.detect()"
 UNIT = "frames/s"
+DISTINCT = 4  # resident batches of the periodic synthetic stream
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--fps", type=float, default=30.0)
     ap.add_argument("--window", type=int, default=30)
-    ap.add_argument("--batch", type=int, default=512, help="frames per step (per GPU)")
+    ap.add_argument("--batch", type=int, default=512, help="frames per library call (per GPU)")
+    ap.add_argument("--bps", type=int, default=12, help="batches per step (a multiple of 4 keeps every rank's chunk in phase "
+                                                        "with the replayed stream)")
     ap.add_argument("--no-dy", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=40, help="frames in the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the side measurements of the SURVEY 8f rows")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (2, 4, 5)")
+    ap.add_argument("--no-extra", action="store_true", help="skip per_frame_api and dense_regime")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sequential re-run that checks the sharded result")
+    ap.add_argument("--parity-budget", type=int, default=2600, help="most batches a rank re-runs sequentially for the parity check")
     ap.add_argument("--generic-kernel", action="store_true", help="force the per-frame fused kernel")
-    ap.add_argument("--wpt", type=int, default=0, help="temporal kernel words per thread (2 or 4; 0 = default)")
     return ap.parse_args()
 
 
 def workload_name(a):
     return (f"synthetic {a.width}x{a.height} @{a.fps:g}fps, window={a.window}, adaptive threshold, "
-            f"dy_mask={'off' if a.no_dy else 'on'}, HoughLinesP(10,10,10), batch={a.batch} frames/step/GPU")
+            f"dy_mask={'off' if a.no_dy else 'on'}, HoughLinesP(10,10,10)")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -112,29 +127,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(rows), "power_w_max": max(pw) if pw else None}
 
 
-def make_cfg(a):
+def make_cfg(dy=True, adaptive=True, init_value=7):
     from metdetpy_b200 import BinaryCfg, BinaryCoreCfg, DynamicCfg, HoughLineCfg
-    return BinaryCfg(BinaryCoreCfg(True, 7, "normal", 0.1, 2), HoughLineCfg(10, 10, 10),
-                     DynamicCfg(not a.no_dy, 5))
+    return BinaryCfg(BinaryCoreCfg(adaptive, init_value, "normal", 0.1, 2), HoughLineCfg(10, 10, 10), DynamicCfg(dy, 5))
 
 
-def cpu_reference_detector(a):
+def cpu_reference_detector(W, H, n, fps, dy=True, adaptive=True, init_value=7, mask=None):
     """The reference's CPU implementation of the path: the oracle in its cv2 backend executes the same
     numpy + cv2 calls, in the same order, as MetLib/Detector.py (the reference is pure Python and
     /root/reference does not exist on the GPU box)."""
     from oracle import m3_oracle as O
     import cv2
-    mask = np.ones((a.height, a.width), np.uint8)
-    det = O.M3DetectorOracle(a.window / a.fps + 1e-9, a.fps, mask, 10, adaptive=True, init_value=7,
+    mask = np.ones((H, W), np.uint8) if mask is None else mask
+    det = O.M3DetectorOracle(n / fps + 1e-9, fps, mask, 10, adaptive=adaptive, init_value=init_value,
                              sensitivity="normal", area=0.1, interval=2, hough=(10, 10, 10),
-                             dy_mask=not a.no_dy, backend="cv2")
+                             dy_mask=dy, backend="cv2")
     return det, cv2.getNumThreads()
 
 
 def run_cpu_sample(a, nframes):
     """Bounded CPU sample: fill the window (untimed), then time `nframes` x (update; detect)."""
     from metdetpy_b200 import synth
-    det, threads = cpu_reference_detector(a)
+    det, threads = cpu_reference_detector(a.width, a.height, a.window, a.fps, dy=not a.no_dy)
     sky = synth.make_sky(a.width, a.height)
     warm = a.window + 2
     frames = [synth.make_frame(t, sky, a.width, a.height, a.fps) for t in range(warm + nframes)]
@@ -147,7 +161,36 @@ def run_cpu_sample(a, nframes):
     return nframes / dt, threads, warm
 
 
-def measure_next_rows(a, batch0, dev, peak):
+# ---------------------------------------------------------------------------------------------
+class Stream:
+    """Periodic synthetic stream resident on the device: frame t has the content of frame t mod P (P = DISTINCT * B),
+    generated with that period (synth.make_stream_device).  In front of the period sit `pad` frames that repeat its
+    end, so that every batch and every look-back halo / noise window is one contiguous block of memory."""
+
+    def __init__(self, B, W, H, fps, dev, pad, distinct=DISTINCT, quiet=0, t_base=0):
+        import torch
+        from metdetpy_b200 import synth
+        self.B, self.W, self.H, self.pad, self.P = B, W, H, pad, distinct * B
+        self.HW = W * H
+        self.buf = torch.empty((pad + self.P, H, W), dtype=torch.uint8, device=dev)
+        for s in range(distinct):
+            self.buf[pad + s * B: pad + (s + 1) * B] = synth.make_stream_device(B, W, H, fps, dev, t0=t_base + s * B,
+                                                                                 loop=self.P, quiet=quiet)
+        if pad:
+            self.buf[:pad] = self.buf[self.P:self.P + pad]
+        torch.cuda.synchronize()
+        self.base = self.buf.data_ptr()
+
+    def ptr(self, t):
+        """device address of global frame t (valid for reads of up to B frames when t % B == 0, and `pad` frames back)"""
+        return self.base + (self.pad + t % self.P) * self.HW
+
+    def view(self, t, T):
+        i = self.pad + t % self.P
+        return self.buf[i:i + T]
+
+
+def measure_next_rows(a, batch0_ptr, dev, peak):
     """Side measurements of the SURVEY 8(f) rows built so far (not part of the headline value):
     loader preprocessing (4K BGR -> 960x540 gray) and ClassicDetector on the bench's 4K stream."""
     import cv2
@@ -191,21 +234,20 @@ def measure_next_rows(a, batch0, dev, peak):
     # fixed threshold 20: with the adaptive one the 4-frame noise estimate puts the threshold at ~7 grey levels on
     # this sigma=2 stream and frame differences light up ~10 % of the pixels -- a regime in which the reference's
     # own cv2.HoughLinesP needs minutes per 4K frame; the fixed value leaves the streaks (amplitude 60)
-    from metdetpy_b200 import BinaryCfg, BinaryCoreCfg, DynamicCfg, HoughLineCfg
-    ccfg = BinaryCfg(BinaryCoreCfg(False, 20, "normal", 0.1, 2), HoughLineCfg(10, 10, 10), DynamicCfg(False, 5))
+    ccfg = make_cfg(dy=False, adaptive=False, init_value=20)
     det = ClassicDetector(1.0, a.fps, mask, 10, ccfg, None, device=dev.index or 0, max_batch=B)
     for _ in range(2):
-        det.detect_many((batch0.data_ptr(), B), on_device=True)
+        det.detect_many((batch0_ptr, B), on_device=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     reps = 5
     for _ in range(reps):
-        det.detect_many((batch0.data_ptr(), B), on_device=True)
+        det.detect_many((batch0_ptr, B), on_device=True)
     dt = time.perf_counter() - t0
     chain_ms, _ = det._eng.fused_time()
     ref = CO.ClassicDetectorOracle(1.0, a.fps, mask, 10, adaptive=False, init_value=20, sensitivity="normal", area=0.1,
                                    interval=2, hough=(10, 10, 10), backend="cv2")
-    host = batch0[:12].cpu().numpy()
+    host = _dev_view(batch0_ptr, 12, a.height, a.width, dev).cpu().numpy()
     for f in host[:4]:
         ref.update(f); ref.detect()
     t0 = time.perf_counter()
@@ -224,12 +266,25 @@ def measure_next_rows(a, batch0, dev, peak):
     return out
 
 
+_VIEWS = {}
+
+
+def _dev_view(ptr, T, H, W, dev):
+    """torch view of T frames at a raw device address inside one of the resident streams"""
+    for st in _VIEWS.values():
+        off = ptr - st.base
+        if 0 <= off < st.buf.numel():
+            i = off // st.HW
+            return st.buf[i:i + T]
+    raise ValueError("address not inside a resident stream")
+
+
 def main_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from metdetpy_b200 import synth
-    det, threads = cpu_reference_detector(a)
+    det, threads = cpu_reference_detector(a.width, a.height, a.window, a.fps, dy=not a.no_dy)
     # a step = a bounded sample of the workload: 8 frames, fewer when many steps are asked for, so that the whole
     # run (frame synthesis on the host included) stays within a few minutes
     per_step = max(1, min(8, 240 // max(1, a.warmup + a.steps)))
@@ -253,15 +308,72 @@ def main_reference(a):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload_name(a), "frames_per_step": per_step},
+        "config": {"workload": workload_name(a)}, "frames_per_step": per_step,
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ---------------------------------------------------------------------------------------------
+class LineGather:
+    """All-gather of line records (frame, x1, y1, x2, y2, nonline_prob), one call per step, on a side stream with the
+    collective launched asynchronously: nothing on the submitting thread waits for it before the end of the job."""
+    CAP = 8192
+    SLOTS = 4
+
+    def __init__(self, world, dev):
+        import torch
+        self.world, self.dev = world, dev
+        self.stream = torch.cuda.Stream(device=dev, priority=-1)
+        self.host = [torch.zeros((self.CAP, 6), dtype=torch.float64).pin_memory() for _ in range(self.SLOTS)]
+        self.devb = [torch.zeros((self.CAP, 6), dtype=torch.float64, device=dev) for _ in range(self.SLOTS)]
+        self.all = [torch.zeros((world * self.CAP, 6), dtype=torch.float64, device=dev) for _ in range(self.SLOTS)]
+        self.work = [None] * self.SLOTS
+        self.copied = [None] * self.SLOTS  # event: the pinned buffer of the slot has been read by its H2D copy
+        self.k = 0
+        self.fill = 0
+        self.total = torch.zeros((), dtype=torch.float64, device=dev)
+        self.dropped = 0
+
+    def add_batch(self, det, T, first_frame):
+        from metdetpy_b200 import sharding as S
+        s = self.k % self.SLOTS
+        if self.fill == 0 and self.copied[s] is not None:
+            self.copied[s].synchronize()  # four steps old: long done
+        rows = self.host[s].numpy()
+        room = self.CAP - 1 - self.fill
+        k = S.pack_line_records(det, T, first_frame, rows[self.fill:self.fill + room])
+        want = int(det.last_infos["n_lines"][:T].sum())
+        self.dropped += want - k
+        self.fill += k
+
+    def flush(self):
+        """end of a step: ship what has been packed"""
+        import torch
+        import torch.distributed as dist
+        s = self.k % self.SLOTS
+        self.host[s].numpy()[self.CAP - 1, 0] = self.fill
+        with torch.cuda.stream(self.stream):
+            self.devb[s].copy_(self.host[s], non_blocking=True)
+            self.copied[s] = torch.cuda.Event()
+            self.copied[s].record(self.stream)
+            self.work[s] = dist.all_gather_into_tensor(self.all[s], self.devb[s], async_op=True)
+            self.work[s].wait()  # orders the side stream after the collective; the host does not block
+            self.total += self.all[s].view(self.world, self.CAP, 6)[:, self.CAP - 1, 0].sum()
+        self.k += 1
+        self.fill = 0
+
+    def finish(self):
+        """waits for the outstanding exchanges; returns the number of records all ranks shipped since the last finish"""
+        self.stream.synchronize()
+        v = int(self.total.item())
+        self.total.zero_()
+        return v
 
 
 def main_ours(a):
     import torch
     import torch.distributed as dist
-    from metdetpy_b200 import _lib, synth
+    from metdetpy_b200 import sharding as S
     from metdetpy_b200.detector import M3Detector
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -274,119 +386,199 @@ def main_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    W, H, n, B = a.width, a.height, a.window, a.batch
+    W, H, n, B, bps = a.width, a.height, a.window, a.batch, a.bps
     HW = W * H
+    if world > 1 and bps % DISTINCT:
+        raise SystemExit(f"--bps must be a multiple of {DISTINCT} for --gpus > 1")
     mask = np.ones((H, W), np.uint8)
-    det = M3Detector(n / a.fps + 1e-9, a.fps, mask, 10, make_cfg(a), None, device=local, max_batch=B)
+    det = M3Detector(n / a.fps + 1e-9, a.fps, mask, 10, make_cfg(dy=not a.no_dy), None, device=local, max_batch=B)
     if a.generic_kernel:
         det._eng.set_option("stream_kernel", 0)
-    if a.wpt:
-        det._eng.set_option("temporal_wpt", a.wpt)
     for kv in os.environ.get("MDB_OPTS", "").split(","):
         if "=" in kv:
             det._eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     ext = torch.cuda.ExternalStream(det._eng.stream_ptr(), device=dev)
-
-    # this rank's chunk of the stream: frames [rank*chunk, ...); generated on the device
-    nsteps = a.warmup + a.steps
-    distinct = min(nsteps, 4)  # distinct batches kept resident; cycled (each > L2: B*HW bytes)
-    t_base = rank * distinct * B * 50  # a multiple of the replay period: every rank gets its own noise
-    # the resident batches are replayed cyclically: the stream is generated with that period (synth.py)
-    batches = [synth.make_stream_device(B, W, H, a.fps, dev, t0=t_base + s * B, loop=distinct * B, quiet=n)
-               for s in range(distinct)]
-    torch.cuda.synchronize()
+    pad = 2 * n - 2
+    stream = Stream(B, W, H, a.fps, dev, pad, quiet=n)
+    _VIEWS["main"] = stream
+    interval = 2
+    roi = det.stack.std_roi
+    roi_px = (roi[2] - roi[0]) * (roi[3] - roi[1])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput ("value") ------------------------------------------------
-    # three batches in flight: the host-side part of batch s (result copy-out, NMS) and its Hough pass
-    # overlap the kernels of batches s+1, s+2
-    def submit_dev(s):
-        x = batches[s % distinct]
-        det.submit(x.data_ptr(), B, True)
+    def allmax(x):
+        el = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        return float(el.item())
 
-    nlines = 0
-    for s in range(a.warmup):
-        submit_dev(s)
-        det.collect()
+    trace = [] if os.environ.get("BENCH_TRACE") else None
+    acc = {"fused_ms": 0.0, "batches": 0, "lines": 0}
+
+    # ---- N = 1: one sequential stream, three batches in flight ---------------------------------------------------
+    def sequential(first_batch, nbatches, on_batch=None, timed=False):
+        AHEAD = 2
+        for s in range(min(AHEAD, nbatches)):
+            det.submit(stream.ptr((first_batch + s) * B), B, True)
+        for s in range(nbatches):
+            if s + AHEAD < nbatches:
+                det.submit(stream.ptr((first_batch + s + AHEAD) * B), B, True)
+            res = det.collect()
+            if timed:
+                acc["lines"] += sum(len(r[0]) for r in res)
+                acc["fused_ms"] += det._eng.fused_time()[0]
+                acc["batches"] += 1
+                if trace is not None and (s + 1) % bps == 0:
+                    trace.append(time.perf_counter())
+            if on_batch is not None:
+                on_batch(det, (first_batch + s) * B)
+
+    # ---- N > 1: one job of the time-sharded algorithm over `steps` steps per rank --------------------------------
+    def sharded_job(steps, vrank=rank, vworld=world, gather=None, digests=None, timed=False, group_exchange=True):
+        C = steps * bps * B                       # frames per rank
+        sh = S.Shard(vrank, vrank * C, (vrank + 1) * C, max(0, vrank * C - pad))
+        # phase A: integer noise sums of the sample timers of this rank's chunk
+        segs = [S.Segment(stream.ptr(t), B, t, history=pad) for t in range(sh.start, sh.end, B)]
+        mine = S.chunk_noise_samples(det, segs, n, interval, sh.start, sh.end, HW)
+        # phase B: all-gather of the triples (one packed int64 tensor; every rank owns the same number of samples +-1)
+        if group_exchange and world > 1:
+            cap = C // (interval * n) + n + 2
+            buf = torch.zeros((cap, 3), dtype=torch.int64)
+            buf[0, 0] = len(mine)
+            if mine:
+                buf[1:1 + len(mine)] = torch.tensor(mine, dtype=torch.int64)
+            dbuf = buf.to(dev, non_blocking=False)
+            allb = torch.zeros((world * cap, 3), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allb, dbuf)
+            allh = allb.cpu().view(world, cap, 3).numpy()
+            samples = []
+            for r in range(vrank + 1):  # later ranks' samples are not needed for this rank's thresholds
+                k = int(allh[r, 0, 0])
+                samples += [tuple(int(v) for v in row) for row in allh[r, 1:1 + k]]
+        else:
+            samples = list(mine)
+            for r in range(vrank):      # virtual ranks on one GPU: compute the earlier chunks' samples here
+                segs_r = [S.Segment(stream.ptr(t), B, t, history=pad) for t in range(r * C, (r + 1) * C, B)]
+                samples += S.chunk_noise_samples(det, segs_r, n, interval, r * C, (r + 1) * C, HW)
+        # phase C: bit-identical threshold replay for the frames this rank ingests
+        thr, thr_f, snr = S.replay_thresholds_native(samples, roi_px, n, sh.halo_start, sh.end, adaptive=True, init_value=7,
+                                                     sensitivity="normal", interval=interval)
+        # phase D: seek + halo batch + chunk, three batches in flight; line records shipped once per step
+        run = ([S.Segment(stream.ptr(sh.halo_start), sh.start - sh.halo_start, sh.halo_start)] if sh.start > sh.halo_start else []) + segs
+        state = {"k": 0}
+
+        def on_batch(d, sg):
+            state["k"] += 1
+            if timed:
+                acc["fused_ms"] += d._eng.fused_time()[0]
+                acc["batches"] += 1
+            if digests is not None:
+                digests.append(S.batch_digest(d, sg.T))
+            if gather is not None:
+                gather.add_batch(d, sg.T, sg.t0)
+                if state["k"] % bps == 0:
+                    gather.flush()
+            elif timed:
+                acc["lines"] += int(d.last_infos["n_lines"][:sg.T].sum())
+            if trace is not None and timed and state["k"] % bps == 0:
+                trace.append(time.perf_counter())
+        S.run_chunk(det, run, sh, thr, thr_f, snr, thr_base=sh.halo_start, on_batch=on_batch)
+        return sh
+
+    # ---- warm-up + timed region ------------------------------------------------------------------------------------
+    gather = LineGather(world, dev) if world > 1 else None
+    digests = []
+    if world == 1:
+        sequential(0, a.warmup * bps)
+    else:
+        sharded_job(max(1, a.warmup), gather=gather)
+        gather.finish()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = det._eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fused_ms, fused_launches = 0.0, 0
+    barrier()
     t0 = time.perf_counter()
     e0.record(ext)
-    # the two exchanges of the time-sharded path, with real payloads, inside the timed
-    # region: all-gather of this step's noise-sample triples, gather of this step's line records
-    CAP_REC = 8192
-    rec_buf = torch.zeros((CAP_REC, 6), dtype=torch.float64, device=dev) if world > 1 else None
-    rec_all = [torch.zeros_like(rec_buf) for _ in range(world)] if world > 1 else None
-    rec_host = torch.zeros((CAP_REC, 6), dtype=torch.float64).pin_memory() if world > 1 else None
-    smp_buf = torch.zeros((64, 3), dtype=torch.int64, device=dev) if world > 1 else None
-    smp_all = [torch.zeros_like(smp_buf) for _ in range(world)] if world > 1 else None
-    gathered_dev = torch.zeros((), dtype=torch.float64, device=dev)
-
-    def exchange(res, step):
-        nonlocal gathered_dev
-        # this step's line records (frame, x1, y1, x2, y2, nonline_prob), built without a per-frame Python loop
-        eng = det._eng
-        nl = det.last_infos["n_lines"][:B]
-        sel = np.arange(eng.lines.shape[1])[None, :] < nl[:, None]
-        k = min(int(nl.sum()), CAP_REC - 1)
-        rh = rec_host.numpy()
-        rh[:k, 0] = (step * B + np.repeat(np.arange(B), nl))[:k]
-        rh[:k, 1:5] = eng.lines[:B][sel][:k]
-        rh[:k, 5] = eng.prob[:B][sel][:k]
-        rh[CAP_REC - 1, 0] = k
-        rec_buf.copy_(rec_host, non_blocking=True)
-        dist.all_gather(smp_all, smp_buf)
-        dist.all_gather(rec_all, rec_buf)
-        for b in rec_all:  # rank 0 would hand these rows to the collector; here they are only counted
-            gathered_dev += b[CAP_REC - 1, 0]
-
-    trace = [] if os.environ.get("BENCH_TRACE") else None
-    AHEAD = 2  # batches submitted ahead of the one being collected (three in flight)
-    for s in range(min(AHEAD, a.steps)):
-        submit_dev(a.warmup + s)
-    for s in range(a.steps):
-        if s + AHEAD < a.steps:
-            submit_dev(a.warmup + s + AHEAD)
-        res = det.collect()
-        if trace is not None:
-            trace.append(time.perf_counter() - t0)
-        nlines += sum(len(r[0]) for r in res)
-        ms, nl = det._eng.fused_time()
-        fused_ms += ms; fused_launches += nl
-        if world > 1:
-            exchange(res, s)
+    if world == 1:
+        sequential(a.warmup * bps, a.steps * bps, timed=True)
+        nlines_total = acc["lines"]
+    else:
+        sharded_job(a.steps, gather=gather, digests=digests, timed=True)
+        nlines_total = gather.finish()
     e1.record(ext)
     barrier()
     wall = time.perf_counter() - t0
     sampler.stop()
     launches = det._eng.launch_count() - l0
-    if trace:
-        print("step end times (ms):", " ".join(f"{x * 1e3:.2f}" for x in trace), file=sys.stderr)
+    wall_max = allmax(wall)
+    value = world * a.steps * bps * B / wall_max
     dev_ms = e0.elapsed_time(e1)
-    el = torch.tensor([wall], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(el, op=dist.ReduceOp.MAX)
-    wall_max = float(el.item())
-    value = world * a.steps * B / wall_max
+    fused_ms, fused_batches = acc["fused_ms"], acc["batches"]
+    if trace:
+        steps_ms = np.diff(np.array([t0] + trace)) * 1e3
+        print(f"rank {rank} step times (ms): " + " ".join(f"{x:.2f}" for x in steps_ms), file=sys.stderr)
 
-    nlines_total = int(gathered_dev.item()) if world > 1 else nlines
+    # ---- parity of the time-sharded result against one sequential pass of the same frames ------------------------
+    parity = None
+    if not a.no_parity:
+        if world > 1:
+            nb = (rank + 1) * a.steps * bps
+            ok, scope = 1, "every rank re-ran frames 0 .. end of its chunk sequentially"
+            if nb <= a.parity_budget:
+                det.reset()
+                seq = []
+                first = rank * a.steps * bps
+
+                def on_b(d, t0_):
+                    if t0_ >= first * B:
+                        seq.append(S.batch_digest(d, B))
+                sequential(0, nb, on_batch=on_b)
+                ok = int(seq == digests and len(seq) == a.steps * bps)
+                checked = 1
+            else:
+                checked = 0
+            okt = torch.tensor([ok, checked], device=dev, dtype=torch.int64)
+            mn = okt.clone(); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+            sm = okt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            parity = {"ok": bool(mn[0].item()), "ranks_checked": int(sm[1].item()), "frames_per_rank": a.steps * bps * B,
+                      "scope": scope if int(sm[1].item()) == world else
+                      f"ranks whose sequential prefix fits {a.parity_budget} batches re-ran frames 0 .. end of their chunk",
+                      "compared": "per-batch digests of bi_threshold, on-pixel count, raw segment count and raw Hough segments of every frame"}
+        else:
+            # one GPU: the sharded protocol with two virtual ranks over a short stream, against the sequential pass
+            st = 1
+            seq = []
+            det.reset()
+            sequential(0, 2 * st * bps, on_batch=lambda d, t0_: seq.append(S.batch_digest(d, B)))
+            got = []
+            for vr in range(2):
+                dg = []
+                sharded_job(st, vrank=vr, vworld=2, digests=dg, group_exchange=False)
+                got += dg
+            parity = {"ok": bool(got == seq and len(seq) == 2 * st * bps), "ranks_checked": 2, "frames_per_rank": st * bps * B,
+                      "scope": "two virtual ranks on this GPU (reset + seek + halo + replayed thresholds) against one sequential pass",
+                      "compared": "per-batch digests of bi_threshold, on-pixel count, raw segment count and raw Hough segments of every frame"}
+        det.reset()
+    barrier()
 
     # ---- the mask chain timed alone (roofline): one batch in flight, so nothing else shares the SMs;
-    # CUDA events on the library's own streams bracket temporal+act (front stream) and dst (back stream)
-    alone_ms, alone_launches, alone_steps = 0.0, 0, max(3, min(a.steps, 8))
-    for s in range(alone_steps):
-        submit_dev(nsteps + s)
+    # CUDA events on the library's own streams bracket the temporal pass (front stream) and act + dst (back stream)
+    det.reset()
+    alone_ms, alone_t, alone_launches, alone_steps = 0.0, 0.0, 0, 8
+    for s in range(alone_steps + 2):
+        det.submit(stream.ptr(s * B), B, True)
         det.collect(want_lines=False)
-        ms, nl = det._eng.fused_time()
-        alone_ms += ms; alone_launches += nl
+        if s >= 2:
+            ms, nl = det._eng.fused_time()
+            alone_ms += ms; alone_launches += nl
+            alone_t += det._eng.info("temporal_ms")
+    temporal_gen = int(det._eng.info("temporal_generation"))
     barrier()
 
     # ---- end to end through the public API with HOST (pinned) buffers -------------------------
@@ -394,9 +586,9 @@ def main_ours(a):
     if not a.no_e2e:
         hosts, ok = [], 1
         try:  # two pinned staging buffers per rank (B*H*W bytes each); all ranks must agree to go on
-            for s in range(min(distinct, 2)):
+            for s in range(2):
                 hb = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
-                hb.copy_(batches[s])
+                hb.copy_(stream.view(s * B, B))
                 hosts.append(hb)
         except Exception as exc:
             print(f"rank {rank}: no pinned host memory for the end-to-end leg: {exc!r}", file=sys.stderr)
@@ -405,74 +597,100 @@ def main_ours(a):
         if world > 1:
             dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         torch.cuda.synchronize()
-    if not a.no_e2e and int(okt.item()) == 1:
-        def submit_host(s):
-            hb = hosts[s % len(hosts)]
-            det.submit(hb.data_ptr(), B, False)
-        for s in range(max(1, a.warmup // 2)):
-            submit_host(s)
-            det.collect()
-        barrier()
-        t0 = time.perf_counter()
-        submit_host(0)
-        for s in range(a.steps):
-            if s + 1 < a.steps:
-                submit_host(s + 1)  # its H2D copy overlaps the kernels of batch s
-            det.collect()           # D2H of the results + host NMS
-        barrier()
-        w2 = time.perf_counter() - t0
-        el = torch.tensor([w2], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(el, op=dist.ReduceOp.MAX)
-        d2h = B * (4 + 8 + 8 + 4 + 4 + 512 * 16)  # thr, thr_float, snr, n_on, n_lines, raw segments
-        e2e = {"value": world * a.steps * B / float(el.item()), "unit": UNIT,
-               "h2d_bytes_per_step": B * HW, "d2h_bytes_per_step": d2h}
+        if int(okt.item()) == 1:
+            det.reset()
+            nb = max(8, min(a.steps * bps, 24))
+
+            def submit_host(s):
+                det.submit(hosts[s % len(hosts)].data_ptr(), B, False)
+            for s in range(3):
+                submit_host(s)
+                det.collect()
+            barrier()
+            t0e = time.perf_counter()
+            submit_host(0)
+            for s in range(nb):
+                if s + 1 < nb:
+                    submit_host(s + 1)  # its H2D copy overlaps the kernels of batch s
+                det.collect()           # D2H of the results + host NMS
+            barrier()
+            w2 = allmax(time.perf_counter() - t0e)
+            d2h = B * (4 + 8 + 8 + 4 + 4 + 512 * 16)  # thr, thr_float, snr, n_on, n_lines, raw segments
+            e2e = {"value": world * nb * B / w2, "unit": UNIT, "h2d_bytes_per_step": bps * B * HW,
+                   "d2h_bytes_per_step": bps * d2h, "batches_timed": nb,
+                   "h2d_gbs_per_rank": nb * B * HW / w2 / 1e9,
+                   "mode": "one host-fed stream per rank (pinned buffers -> staging copy -> zero-copy kernels), H2D of batch k+1 "
+                           "overlapping the kernels of batch k"}
+            del hosts
+
+    extra = {}
+    if rank == 0 and world == 1:
+        peaks = _peaks()
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        if not a.no_extra:
+            for name, fn in (("per_frame_api", lambda: measure_per_frame(a, det, stream, dev)),
+                             ("dense_regime", lambda: measure_dense(a, stream, dev))):
+                try:
+                    extra[name] = fn()
+                except Exception as e:  # a side measurement must never take the headline line down
+                    extra[name] = {"error": repr(e)}
+        if not a.no_next_rows:
+            try:
+                extra["next_rows"] = measure_next_rows(a, stream.ptr(0), dev, peak)
+            except Exception as e:
+                extra["next_rows"] = {"error": repr(e)}
+    det.close()
+    if rank == 0 and world == 1 and not a.no_configs:
+        del stream.buf
+        _VIEWS.clear()
+        torch.cuda.empty_cache()
+        try:
+            extra["configs"] = measure_configs(a, dev, float(_peaks().get("hbm_gbs", 6650.0)))
+        except Exception as e:
+            extra["configs"] = {"error": repr(e)}
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
+        peaks = _peaks()
         peak = float(peaks.get("hbm_gbs", 6650.0))
         alg_bytes = 2.0 * HW * B * alone_steps  # read the new u8 frame once + write the u8 mask once
         achieved = alg_bytes / (alone_ms * 1e-3) / 1e9 if alone_ms > 0 else None
-        in_step = 2.0 * HW * B * a.steps / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else None
-        # DRAM bytes of the chain from the ncu --set full capture in profiles/r01_ncu_full_summary.txt
-        # (4K, n=30, 512 frames: temporal2 4.49 + 0.52 GB, act4 0.59 + 0.49 GB, dst_sparse 0.02 GB
-        # = 6.11 GB = 1.44 H*W per frame), averaged over the chain's 4 launches like `achieved`
-        default_cfg = (W, H, n, B) == (3840, 2160, 30, 512) and not a.no_dy
-        traffic = 1.438 * HW * B / 4.0 if default_cfg else None
+        in_step = 2.0 * HW * B * fused_batches / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else None
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": wall_max / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_name(a), "frames_per_step_per_gpu": B,
-                       "l2_policy": f"inputs larger than L2 ({B * HW / 1e6:.0f} MB per batch, {distinct} batches cycled)",
-                       "sharding": "time chunks, one per rank; no frame crosses GPUs"},
+            "config": {"workload": workload_name(a)},
+            "run": {"frames_per_step_per_gpu": bps * B, "batches_per_step": bps, "frames_per_call": B,
+                    "l2_policy": f"inputs larger than L2 ({B * HW / 1e6:.0f} MB per batch, {DISTINCT} batches cycled)",
+                    "sharding": ("one stream of N time chunks: (2n-2)-frame halo, all-gather of integer noise sums, threshold replay, "
+                                 "line records all-gathered once per step on a side stream; no frame crosses GPUs") if world > 1 else
+                                "one sequential stream, three batches in flight"},
+            "sharded_parity": (parity or {}).get("ok"), "parity": parity,
             "device_ms_per_step": dev_ms / a.steps,
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "traffic_note": "DRAM bytes per launch (avg of the 4 launches of the chain), ncu --set full capture profiles/r01_ncu_full_summary.txt",
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": _traffic_from_profile(W, H, n, B),
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (average over the launches of the chain) "
+                                         "from the committed ncu --set full capture of this configuration under profiles/ (null: none committed)",
                          "algorithmic_bytes_per_launch": 2.0 * HW * B * alone_steps / max(alone_launches, 1),
-                         "kernel": "fused mask chain: temporal_kernel (stack->diff->threshold) + act4_kernel (median+close) + dst_sparse/dense_kernel (dy-mask, mask bytes)",
+                         "kernel": f"fused mask chain: temporal{temporal_gen}_kernel (stack->diff->threshold) + act4_kernel (median+close) + dst_sparse/dense_kernel (dy-mask, mask bytes)",
                          "kernel_ms_per_launch": alone_ms / max(alone_launches, 1),
                          "kernel_launches": alone_launches,
-                         "chain_ms_per_step": alone_ms / alone_steps,
-                         "timing": f"CUDA events on the library's streams around the chain, {alone_steps} steps with one batch in "
+                         "chain_ms_per_batch": alone_ms / alone_steps,
+                         "temporal_ms_per_batch": alone_t / alone_steps,
+                         "timing": f"CUDA events on the library's streams around the chain, {alone_steps} batches with one batch in "
                                    "flight (chain alone on the GPU) right after the timed region",
                          "achieved_inside_timed_region": in_step,
+                         "frac_inside_timed_region": (in_step / peak) if in_step else None,
                          "inside_note": "same events during the timed region, where the chain shares the SMs with the Hough pass "
                                         "and the next batch's temporal pass (three batches in flight): elapsed, not busy, time",
                          "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s"},
             "clocks": sampler.summary(), "nms_lines_total": nlines_total,
         }
-        if not a.no_next_rows and world == 1:
-            try:
-                out["next_rows"] = measure_next_rows(a, batches[0], dev, peak)
-            except Exception as e:  # a side measurement must never take the headline line down
-                out["next_rows"] = {"error": repr(e)}
+        if gather is not None and gather.dropped:
+            out["line_records_dropped"] = gather.dropped
+        out.update(extra)
         if not a.no_cpu_baseline and world == 1:
             v, threads, warm = run_cpu_sample(a, a.cpu_frames)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
@@ -482,6 +700,150 @@ def main_ours(a):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _traffic_from_profile(W, H, n, B):
+    """DRAM bytes per launch of the mask chain from the committed ncu capture of this configuration
+    (profiles/chain_traffic.json, written by profiles/ncu_summary.py --traffic from an ncu --set full raw CSV)."""
+    try:
+        tab = json.load(open(os.path.join(REPO, "profiles", "chain_traffic.json")))
+        e = tab.get(f"{W}x{H}_n{n}_b{B}")
+        return e["bytes_per_launch"] if e else None
+    except Exception:
+        return None
+
+
+def measure_per_frame(a, det, stream, dev):
+    """The reference's own call pattern (MetDetPy.py:197-198): update(frame); detect() per frame, frames in pinned host
+    memory."""
+    import torch
+    W, H = a.width, a.height
+    F = 96
+    host = torch.empty((F, H, W), dtype=torch.uint8).pin_memory()
+    host.copy_(stream.view(0, F))
+    frames = host.numpy()
+    det.reset()
+    for t in range(32):
+        det.update(frames[t]); det.detect()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for t in range(32, F):
+        det.update(frames[t]); det.detect()
+    dt = time.perf_counter() - t0
+    return {"value": (F - 32) / dt, "unit": UNIT, "frames": F - 32,
+            "call": "M3Detector.update(frame); M3Detector.detect() per frame from pinned host memory (MetDetPy.py:197-198)",
+            "h2d_bytes_per_frame": W * H}
+
+
+def measure_dense(a, stream, dev):
+    """Dense-mask regime (~5e4 on-pixels per frame on the noisy real 4K clip): the same 4K stream with a
+    fixed low threshold so that sensor noise lights up tens of thousands of pixels per frame; every frame takes the
+    global-memory PPHT tiers.  CPU arm: the reference's numpy + cv2 calls on the same frames."""
+    import torch
+    from metdetpy_b200.detector import M3Detector
+    W, H, n = a.width, a.height, a.window
+    T = 64
+    mask = np.ones((H, W), np.uint8)
+    out = None
+    for thr in (6, 5):
+        det = M3Detector(n / a.fps + 1e-9, a.fps, mask, 10, make_cfg(dy=True, adaptive=False, init_value=thr), None,
+                         device=dev.index or 0, max_batch=T)
+        det.detect_many((stream.ptr(0), T), on_device=True)          # fills the window
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        det.detect_many((stream.ptr(T), T), on_device=True)
+        dt = time.perf_counter() - t0
+        non = det.last_infos["n_on"].astype(np.float64)
+        raw = det.last_infos["lines_num"].astype(np.float64)
+        det.close()
+        out = {"threshold": thr, "frames": T, "value": T / dt, "unit": UNIT, "on_pixels_mean": float(non.mean()),
+               "on_pixels_max": float(non.max()), "raw_segments_mean": float(raw.mean()),
+               "tiers": {"<=2048 (1a)": int((non <= 2048).sum()), "<=4096 (1b)": int(((non > 2048) & (non <= 4096)).sum()),
+                         "<=16384 (2)": int(((non > 4096) & (non <= 16384)).sum()), ">16384 (3)": int((non > 16384).sum())}}
+        if non.mean() >= 5000:
+            break
+    # CPU arm on a few of the same frames
+    ref, threads = cpu_reference_detector(W, H, n, a.fps, dy=True, adaptive=False, init_value=out["threshold"])
+    host = stream.view(T - n - 2, n + 2 + 6).cpu().numpy()
+    for f in host[:n + 2]:
+        ref.update(f); ref.detect()
+    t0 = time.perf_counter()
+    for f in host[n + 2:]:
+        ref.update(f); ref.detect()
+    cpu = 6 / (time.perf_counter() - t0)
+    out["cpu_baseline"] = {"value": cpu, "unit": UNIT, "kind": "port", "cores": os.cpu_count(),
+                           "sample": f"6 frames of the same stream, fixed threshold {out['threshold']}; cv2 threads {threads}"}
+    out["speedup_vs_cpu"] = out["value"] / cpu
+    return out
+
+
+def measure_configs(a, dev, peak):
+    """The other BASELINE.json configs on ONE GPU (device-resident frames, three batches in flight): frames/s, the mask
+    chain alone and its fraction of the HBM roofline."""
+    import torch
+    from metdetpy_b200.detector import M3Detector
+    res = {}
+    cases = [("config2_1080p_n5", 1920, 1080, 30.0, 5, False, None, 2048),
+             ("config4_4k60_n60_mask", 3840, 2160, 60.0, 60, True, "mask-east", 512),
+             ("config5_8k_n30", 7680, 4320, 30.0, 30, True, None, 128)]
+    for name, W, H, fps, n, dy, mk, B in cases:
+        HW = W * H
+        mask = np.ones((H, W), np.uint8)
+        note = None
+        if mk:
+            mask, note = load_bench_mask(W, H)
+        det = M3Detector(n / fps + 1e-9, fps, mask, 10, make_cfg(dy=dy), None, device=dev.index or 0, max_batch=B,
+                         apply_mask=mk is not None)
+        st = Stream(B, W, H, fps, dev, 0, distinct=2, quiet=n)
+        nb = 10
+        for s in range(3):
+            det.submit(st.ptr(s * B), B, True); det.collect()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        det.submit(st.ptr(3 * B), B, True); det.submit(st.ptr(4 * B), B, True)
+        for s in range(nb):
+            if s + 2 < nb:
+                det.submit(st.ptr((5 + s) * B), B, True)
+            det.collect()
+        dt = time.perf_counter() - t0
+        chain = []
+        for s in range(5):
+            det.submit(st.ptr(s * B), B, True); det.collect(want_lines=False)
+            chain.append(det._eng.fused_time()[0])
+        chain_ms = float(np.median(chain[1:]))
+        res[name] = {"workload": f"synthetic {W}x{H} @{fps:g}fps, window={n}, dy_mask={'on' if dy else 'off'}, "
+                                 f"{'mask applied on the device, ' if mk else ''}{B} frames per call",
+                     "frames_per_s": nb * B / dt, "chain_ms_per_call": chain_ms,
+                     "temporal_generation": int(det._eng.info("temporal_generation")),
+                     "roofline_frac": 2.0 * HW * B / (chain_ms * 1e-3) / 1e9 / peak}
+        if note:
+            res[name]["mask"] = note
+        det.close()
+        del st
+        torch.cuda.empty_cache()
+    return res
+
+
+def load_bench_mask(W, H):
+    """Config 4's mask: the reference's bundled test/mask-east.jpg through fileio.load_mask at this size, committed
+    bit-packed under tests/golden/ (made by tests/golden/make_golden.py); a synthetic horizon mask if it is absent."""
+    p = os.path.join(REPO, "tests", "golden", f"mask_east_{W}x{H}.npz")
+    if os.path.exists(p):
+        z = np.load(p)
+        m = np.unpackbits(z["bits"])[:H * W].reshape(H, W).astype(np.uint8)
+        return m, "test/mask-east.jpg through fileio.load_mask (tests/golden)"
+    m = np.ones((H, W), np.uint8)
+    yy = np.arange(H)[:, None]
+    xx = np.arange(W)[None, :]
+    m[yy > H * 0.82 + 0.05 * H * np.sin(xx / W * 7.0)] = 0
+    return m, "synthetic horizon mask (tests/golden/mask_east file absent)"
 
 
 if __name__ == "__main__":

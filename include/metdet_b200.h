@@ -156,11 +156,20 @@ int mdb_get_fused_time(mdb_handle h, float *ms, int32_t *launches);
  * device buffers; mdb_seek may follow.  No batch may be in flight. */
 int mdb_reset(mdb_handle h);
 /* Noise sums (the integer pair per noise sample that SNR_SW.update, MetLib/Detector.py:73-91, turns into a
- * standard deviation) of the sample timers among the DEVICE frames t0 .. t0+T-1, T <= max_batch + window, on the
- * handle's own stream and buffers.  Only samples whose whole window lies inside the supplied frames (or starts at
- * global frame 0) are evaluated; sums[T][2] (host) is zero elsewhere.  Synchronous.  This is what one rank of a
- * time-sharded run computes for its chunk before the ranks exchange the sums and replay the threshold recurrence. */
-int mdb_noise_sums_dev(mdb_handle h, const uint8_t *frames, int T, int64_t t0, uint64_t *sums);
+ * standard deviation) of the sample timers among DEVICE frames, for nseg segments in one call: segment k = T[k] frames
+ * at frames[k], global index of the first one t0[k].  Only samples whose whole window lies inside their segment (or
+ * starts at global frame 0) are evaluated; sums[sum of T][2] (host, segments concatenated) is zero elsewhere.  Runs on
+ * the handle's own stream and buffers; synchronous.  This is what one rank of a time-sharded run computes for its
+ * chunk before the ranks exchange the sums and replay the threshold recurrence. */
+int mdb_noise_sums_dev(mdb_handle h, int nseg, const uint8_t *const *frames, const int32_t *T, const int64_t *t0,
+                       uint64_t *sums);
+/* Host-only: EMA.update (MetLib/utils.py:334-368) over nsamples noise samples (timers ascending, sums[k][2] as
+ * produced by mdb_noise_sums*) and LineDetector.update's threshold rule (MetLib/Detector.py:225-229) for frames
+ * 0 .. t_end-1; thr / thr_float / snr receive the values of frames t_begin .. t_end-1.  Bit-identical to what a
+ * detector handle computes on the device for the same samples.  Every sample timer up to t_end must be present. */
+int mdb_replay_thresholds(int nsamples, const int64_t *timers, const uint64_t *sums, int64_t roi_pixels, int window,
+                          int nz_interval, int adaptive, int init_value, int sensitivity, int64_t t_begin,
+                          int64_t t_end, int32_t *thr, double *thr_float, double *snr);
 /* Read-only counters / timings of the most recent batch by name: "temporal_ms" (stack->diff->threshold pass),
  * "spatial_ms" (median + close + dy-mask + mask bytes), "temporal_generation" (which temporal kernel ran: 3 =
  * register ring, 2 = shared-memory ring, 1 = first generation, 0 = none), "stream_kernel" (1 if the time-tiled

@@ -56,7 +56,8 @@ SYMBOLS = {
     "mdb_set_option": (_I, [_VP, C.c_char_p, _I]),
     "mdb_get_info": (_I, [_VP, C.c_char_p, C.POINTER(C.c_double)]),
     "mdb_reset": (_I, [_VP]),
-    "mdb_noise_sums_dev": (_I, [_VP, _VP, _I, C.c_int64, _VP]),
+    "mdb_noise_sums_dev": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
+    "mdb_replay_thresholds": (_I, [_I, _VP, _VP, C.c_int64, _I, _I, _I, _I, _I, C.c_int64, C.c_int64, _VP, _VP, _VP]),
     "mdb_debug_timeline": (_I, [_VP, _VP]),
     "mdb_debug_hough_profile": (_I, [_VP, _VP, _I]),
     "mdb_seek": (_I, [_VP, C.c_int64]),

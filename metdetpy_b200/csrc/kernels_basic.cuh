@@ -63,6 +63,85 @@ noise_sample_kernel(FrameSrc src, int W, int n, long long timer0, long long std_
     }
 }
 
+// Same sums, four pixels per 32-bit load (W % 4 == 0, n <= 128): the ROI rows are widened to 4-pixel alignment and the
+// pixels outside [c0, c0 + rw) are masked out.  Per word and frame: sum of squares of the four bytes by one IDP.4A
+// (it only enters d2 summed over pixels), per-pixel sums as u16x2 pairs of the even and the odd bytes.  The loads of a
+// window's frames are independent, so a thread keeps several in flight.
+__global__ void __launch_bounds__(256)
+noise_sample4_kernel(FrameSrc src, int W, int n, long long timer0, long long std_interval, int r0, int c0, int rh,
+                     int rw, unsigned long long *acc, long long min_tau, const __grid_constant__ SampleList sl) {
+    const int i = sl.count < 0 ? blockIdx.y : sl.idx[blockIdx.y];
+    const long long tau = timer0 + i + 1;
+    if (tau < min_tau || !is_noise_sample(tau, n, std_interval)) return;
+    const int L = (int)(tau < n ? tau : n);
+    const long long t = tau - 1;
+    __shared__ const uint8_t *fp[128];
+    for (int k = threadIdx.x; k < L; k += blockDim.x) fp[k] = src.frame(t - k);
+    __syncthreads();
+    const int c0a = c0 & ~3, c1a = (c0 + rw + 3) & ~3;
+    const int wpr = (c1a - c0a) >> 2;  // words per ROI row
+    const int total = rh * wpr;
+    unsigned long long d1 = 0, d2 = 0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const int y = r0 + q / wpr, x = c0a + ((q % wpr) << 2);
+        const size_t p = (size_t)y * W + x;
+        unsigned keep = 0u;  // 0xff for the bytes of this word that are ROI pixels (and unmasked)
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if (x + b >= c0 && x + b < c0 + rw) keep |= 0xffu << (8 * b);
+        if (src.mask) keep &= *reinterpret_cast<const unsigned *>(src.mask + p) * 0xffu;
+        unsigned se = 0, so = 0, sq = 0;  // even / odd byte sums (u16x2), sum of squares of all four bytes
+#pragma unroll 6
+        for (int k = 0; k < L; k++) {
+            const unsigned v = __ldg(reinterpret_cast<const unsigned *>(fp[k] + p)) & keep;
+            se += v & 0x00ff00ffu;
+            so += (v >> 8) & 0x00ff00ffu;
+            sq = __dp4a(v, v, sq);
+        }
+        d2 += sq;
+        const unsigned sx4[4] = {se & 0xffffu, so & 0xffffu, se >> 16, so >> 16};
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const unsigned sx = sx4[b], m = sx / (unsigned)L;
+            d1 += sx - (unsigned)L * m;
+            // sum of d^2 = sxx - 2 m sx + L m^2; the sxx part is already in; a masked-out pixel has sx = m = 0
+            d2 += (unsigned long long)((long long)L * m * m - 2ll * m * sx);
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    }
+    __shared__ unsigned long long s1[8], s2[8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s1[w] = d1; s2[w] = d2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); k++) { d1 += s1[k]; d2 += s2[k]; }
+        atomicAdd(&acc[2 * i], d1);
+        atomicAdd(&acc[2 * i + 1], d2);
+    }
+}
+
+static inline void launch_noise_samples(const FrameSrc &src, int W, int n, long long timer0, long long std_interval,
+                                        const int *roi, unsigned long long *acc, long long min_tau, const SampleList &sl,
+                                        int T, cudaStream_t st) {
+    const int rh = roi[2] - roi[0], rw = roi[3] - roi[1];
+    const int rows = sl.count < 0 ? T : sl.count;
+    const bool mask_ok = !src.mask || ((uintptr_t)src.mask & 3) == 0;
+    const bool base_ok = ((uintptr_t)src.ring & 3) == 0 && ((uintptr_t)src.cur & 3) == 0 && (src.HW & 3) == 0;
+    if (W % 4 == 0 && n <= 128 && mask_ok && base_ok) {
+        const int words = rh * ((((roi[1] + rw + 3) & ~3) - (roi[1] & ~3)) >> 2);
+        const int gx = std::max(1, std::min((words + 255) / 256, 1184));
+        noise_sample4_kernel<<<dim3(gx, rows), 256, 0, st>>>(src, W, n, timer0, std_interval, roi[0], roi[1], rh, rw, acc,
+                                                           min_tau, sl);
+    } else {
+        const int gx = std::max(1, std::min((rh * rw + 255) / 256, 592));
+        noise_sample_kernel<<<dim3(gx, rows), 256, 0, st>>>(src, W, n, timer0, std_interval, roi[0], roi[1], rh, rw, acc,
+                                                          min_tau, sl);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Scalar recurrence of one batch, one thread: EMA.update (MetLib/utils.py:334-368) on every noise
 // sample, then LineDetector.update's threshold rule (MetLib/Detector.py:225-229, :177-183).

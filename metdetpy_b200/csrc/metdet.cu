@@ -97,6 +97,7 @@ struct mdb_detector {
     unsigned long long *d_noise = nullptr;
     unsigned long long *d_noise2 = nullptr;  // mdb_noise_sums_dev: [max_batch + n][2]
     unsigned long long *h_noise2 = nullptr;  // pinned staging of the same size
+    size_t noise2_cap = 0;
     int32_t *d_accum = nullptr;   // tier-2/3 accumulators [slots][180][numrho]
     uint32_t *d_bitmap = nullptr, *d_walk = nullptr, *d_okeys = nullptr, *d_oidx = nullptr;  // tier 3
     long long *d_prof = nullptr;  // optional per-frame PPHT phase cycle counters (debug)
@@ -401,7 +402,6 @@ static int launch_noise_thr(mdb_detector *h, BatchCtx &bc, const FrameSrc &src, 
     const long long std_interval = (long long)c.nz_interval * h->n;
     TL(bc, 0, st);
     CK(cudaMemsetAsync(h->d_noise, 0, (size_t)T * 2 * sizeof(unsigned long long), st));
-    const int gx = std::max(1, std::min((rh * rw + 255) / 256, 592));
     SampleList sl;
     sl.count = 0;
     for (int i = 0; i < T && sl.count >= 0; i++) {
@@ -411,9 +411,7 @@ static int launch_noise_thr(mdb_detector *h, BatchCtx &bc, const FrameSrc &src, 
             else sl.count = -1;  // too many to list: one grid row per frame
         }
     }
-    if (sl.count != 0)
-        noise_sample_kernel<<<dim3(gx, sl.count < 0 ? T : sl.count), 256, 0, st>>>(
-            src, h->W, h->n, timer0, std_interval, c.roi[0], c.roi[1], rh, rw, h->d_noise, 0, sl);
+    if (sl.count != 0) launch_noise_samples(src, h->W, h->n, timer0, std_interval, c.roi, h->d_noise, 0, sl, T, st);
     threshold_kernel<<<1, 32, 0, st>>>(h->d_state, h->d_noise, T, timer0, h->n, std_interval,
                                              (long long)rh * rw, c.adaptive, c.sensitivity, bc.d_thr,
                                              bc.d_thrf, bc.d_snr);
@@ -807,43 +805,134 @@ extern "C" int mdb_reset(mdb_handle h) {
     return MDB_OK;
 }
 
-// Noise sums of the sample timers among device frames t0 .. t0+T-1, on the handle's scalar stream and buffers (no
-// allocation): what a rank of a time-sharded run computes for its chunk before the thresholds are replayed.
-extern "C" int mdb_noise_sums_dev(mdb_handle h, const uint8_t *frames, int T, int64_t t0, uint64_t *sums) {
-    if (!h || !frames || !sums || T < 1 || t0 < 0) return fail(MDB_ERR_INVALID, "mdb_noise_sums_dev: bad arguments");
-    const int cap = h->cfg.max_batch + h->n;
-    if (T > cap) return fail(MDB_ERR_INVALID, "mdb_noise_sums_dev: T=%d exceeds max_batch + window = %d", T, cap);
+// Noise sums of the sample timers among device frames, for several segments in one call, on the handle's scalar
+// stream and buffers: what a rank of a time-sharded run computes for its chunk before the thresholds are replayed.
+extern "C" int mdb_noise_sums_dev(mdb_handle h, int nseg, const uint8_t *const *frames, const int32_t *T, const int64_t *t0,
+                                  uint64_t *sums) {
+    if (!h || !frames || !T || !t0 || !sums || nseg < 1) return fail(MDB_ERR_INVALID, "mdb_noise_sums_dev: bad arguments");
+    size_t total = 0;
+    for (int k = 0; k < nseg; k++) {
+        if (!frames[k] || T[k] < 1 || t0[k] < 0) return fail(MDB_ERR_INVALID, "mdb_noise_sums_dev: bad segment %d", k);
+        total += (size_t)T[k];
+    }
     CK(cudaSetDevice(h->cfg.device));
-    if (!h->d_noise2) {
-        CK(cudaMalloc((void **)&h->d_noise2, (size_t)cap * 16));
-        CK(cudaHostAlloc((void **)&h->h_noise2, (size_t)cap * 16, cudaHostAllocDefault));
+    if (h->noise2_cap < total) {
+        if (h->d_noise2) CK(cudaFree(h->d_noise2));
+        if (h->h_noise2) CK(cudaFreeHost(h->h_noise2));
+        h->d_noise2 = h->h_noise2 = nullptr;
+        h->noise2_cap = 0;
+        CK(cudaMalloc((void **)&h->d_noise2, total * 16));
+        CK(cudaHostAlloc((void **)&h->h_noise2, total * 16, cudaHostAllocDefault));
+        h->noise2_cap = total;
     }
     const mdb_config &c = h->cfg;
-    const int rh = c.roi[2] - c.roi[0], rw = c.roi[3] - c.roi[1];
     const long long std_interval = (long long)c.nz_interval * h->n;
-    const long long min_tau = t0 == 0 ? 0 : t0 + h->n;  // the whole window must lie inside the supplied frames
-    SampleList sl;
-    sl.count = 0;
-    for (int i = 0; i < T && sl.count >= 0; i++) {
-        const long long tau = t0 + i + 1;
-        if (tau >= min_tau && ((tau > 1 && tau <= h->n) || (tau > h->n && std_interval > 0 && tau % std_interval == 0))) {
-            if (sl.count < 63) sl.idx[sl.count++] = i;
-            else sl.count = -1;
+    CK(cudaMemsetAsync(h->d_noise2, 0, total * 16, h->sstream));
+    size_t off = 0;
+    for (int k = 0; k < nseg; k++) {
+        const long long min_tau = t0[k] == 0 ? 0 : t0[k] + h->n;  // the whole window must lie inside the supplied frames
+        // sample frames of the segment, 63 per launch
+        int i = 0;
+        while (i < T[k]) {
+            SampleList sl;
+            sl.count = 0;
+            for (; i < T[k] && sl.count < 63; i++) {
+                const long long tau = t0[k] + i + 1;
+                if (tau >= min_tau && ((tau > 1 && tau <= h->n) || (tau > h->n && std_interval > 0 && tau % std_interval == 0)))
+                    sl.idx[sl.count++] = i;
+            }
+            if (sl.count == 0) break;
+            FrameSrc src;
+            src.ring = nullptr; src.cur = frames[k]; src.t0 = t0[k]; src.mask = c.apply_mask ? h->d_mask : nullptr; src.R = 1; src.HW = h->HW;
+            launch_noise_samples(src, h->W, h->n, t0[k], std_interval, c.roi, h->d_noise2 + 2 * off, min_tau, sl, T[k], h->sstream);
+            CK(cudaGetLastError());
+            h->launches += 1;
         }
+        off += (size_t)T[k];
     }
-    memset(sums, 0, (size_t)T * 16);
-    if (sl.count == 0) return MDB_OK;
-    FrameSrc src;
-    src.ring = nullptr; src.cur = frames; src.t0 = t0; src.mask = c.apply_mask ? h->d_mask : nullptr; src.R = 1; src.HW = h->HW;
-    CK(cudaMemsetAsync(h->d_noise2, 0, (size_t)T * 16, h->sstream));
-    const int gx = std::max(1, std::min((rh * rw + 255) / 256, 592));
-    noise_sample_kernel<<<dim3(gx, sl.count < 0 ? T : sl.count), 256, 0, h->sstream>>>(
-        src, h->W, h->n, t0, std_interval, c.roi[0], c.roi[1], rh, rw, h->d_noise2, min_tau, sl);
-    CK(cudaGetLastError());
-    h->launches += 1;
-    CK(cudaMemcpyAsync(h->h_noise2, h->d_noise2, (size_t)T * 16, cudaMemcpyDeviceToHost, h->sstream));
+    CK(cudaMemcpyAsync(h->h_noise2, h->d_noise2, total * 16, cudaMemcpyDeviceToHost, h->sstream));
     CK(cudaStreamSynchronize(h->sstream));
-    memcpy(sums, h->h_noise2, (size_t)T * 16);
+    memcpy(sums, h->h_noise2, total * 16);
+    return MDB_OK;
+}
+
+// EMA.update (MetLib/utils.py:334-368) over the noise samples in timer order + LineDetector.update's threshold rule
+// (MetLib/Detector.py:225-229): the scalar recurrence of threshold_kernel on the host (same IEEE double operations; this
+// TU is compiled without FMA contraction), for frames 0 .. t_end-1; outputs for frames t_begin .. t_end-1.
+extern "C" int mdb_replay_thresholds(int nsamples, const int64_t *timers, const uint64_t *sums, int64_t roi_pixels,
+                                     int window, int nz_interval, int adaptive, int init_value, int sensitivity,
+                                     int64_t t_begin, int64_t t_end, int32_t *thr, double *thr_float, double *snr) {
+    if (nsamples < 0 || (nsamples && (!timers || !sums)) || !thr || !thr_float || !snr || t_begin < 0 || t_end < t_begin ||
+        window < 1 || sensitivity < 0 || sensitivity > 2)
+        return fail(MDB_ERR_INVALID, "mdb_replay_thresholds: bad arguments");
+    const int n = window;
+    const long long std_interval = (long long)nz_interval * n;
+    volatile double ema_init_m = 1.0 - (double)nz_interval / 60.0;
+    double ema_cur_m = ema_init_m, ema_warm = (double)n, ema_value = 0.0;
+    long long ema_t = 0;
+    static const int abs_sens[3] = {7, 5, 3};
+    int bi = adaptive ? abs_sens[sensitivity] : init_value;
+    double thrf = (double)bi;
+    const double a = sensitivity == MDB_SENS_LOW ? 2.0 : (sensitivity == MDB_SENS_NORMAL ? 1.2 : 0.9);
+    const double b = sensitivity == MDB_SENS_LOW ? 4.4 : (sensitivity == MDB_SENS_NORMAL ? 3.6 : 3.0);
+    int k = 0;
+    long long t = 0;
+    auto emit = [&](long long upto) {  // frames t .. upto-1 carry the current values
+        for (long long u = std::max<long long>(t, t_begin); u < upto; u++) {
+            thr[u - t_begin] = bi; thr_float[u - t_begin] = thrf; snr[u - t_begin] = ema_value;
+        }
+        t = upto;
+    };
+    while (t < t_end) {
+        // next sample timer at or after t+1
+        while (k < nsamples && timers[k] < t + 1) k++;
+        long long next_tau = t_end + 1;
+        for (long long tau = t + 1; tau <= t_end; ) {
+            const bool is = (tau > 1 && tau <= n) || (tau > n && std_interval > 0 && tau % std_interval == 0);
+            if (is) { next_tau = tau; break; }
+            tau = tau <= n ? tau + 1 : (std_interval > 0 ? (tau / std_interval + 1) * std_interval : t_end + 1);
+        }
+        if (next_tau > t_end) { emit(t_end); break; }
+        emit(next_tau - 1);  // frames before the sample frame keep the old values
+        if (k >= nsamples || timers[k] != next_tau)
+            return fail(MDB_ERR_INVALID, "mdb_replay_thresholds: the noise sample of timer %lld is missing", next_tau);
+        const int L = (int)(next_tau < n ? next_tau : n);
+        volatile double N = (double)(L * roi_pixels);
+        volatile double s1 = (double)sums[2 * k], s2 = (double)sums[2 * k + 1];
+        volatile double mean = s1 / N;
+        volatile double q = s2 / N;
+        volatile double mm = mean * mean;
+        volatile double var = q - mm;
+        if (var < 0) var = 0;
+        const double sigma = std::sqrt((double)var);
+        if (ema_warm != 0.0) {
+            volatile double one_m = 1.0 - ema_init_m;
+            volatile double kk = (double)ema_t * one_m;
+            kk = kk * ema_warm;
+            if (kk < 1.0) {
+                volatile double u = 1.0 - kk;
+                volatile double uu = u * u;
+                volatile double w = 1.0 - uu;
+                ema_cur_m = ema_init_m * w;
+            } else {
+                ema_warm = 0.0;
+                ema_cur_m = ema_init_m;
+            }
+        }
+        volatile double p1 = ema_cur_m * ema_value;
+        volatile double om = 1.0 - ema_cur_m;
+        volatile double p2 = om * sigma;
+        ema_value = p1 + p2;
+        ema_t++;
+        k++;
+        if (adaptive && ema_value != 0.0) {
+            volatile double x2 = ema_value * ema_value;
+            volatile double ax = a * x2;
+            thrf = ax + b;
+            bi = (int)std::nearbyint(thrf);  // Python round(): half to even (default rounding mode)
+        }
+        emit(next_tau);  // the sample frame itself already carries the new values
+    }
     return MDB_OK;
 }
 
@@ -870,14 +959,11 @@ extern "C" int mdb_noise_sums(const uint8_t *frames, int T, int on_device, int64
     if (e == cudaSuccess) {
         FrameSrc src;
         src.ring = nullptr; src.cur = on_device ? frames : d_frames; src.t0 = t0; src.mask = d_mask; src.R = 1; src.HW = HW;
-        const int rh = roi[2] - roi[0], rw = roi[3] - roi[1];
-        const int gx = std::max(1, std::min((rh * rw + 255) / 256, 592));
         // only samples whose whole window lies inside the supplied frames (or starts at global frame 0)
         const long long min_tau = t0 == 0 ? 0 : t0 + window;
         SampleList sl;
         sl.count = -1;
-        noise_sample_kernel<<<dim3(gx, T), 256>>>(src, width, window, t0, (long long)nz_interval * window, roi[0],
-                                                 roi[1], rh, rw, d_acc, min_tau, sl);
+        launch_noise_samples(src, width, window, t0, (long long)nz_interval * window, roi, d_acc, min_tau, sl, T, 0);
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpy(sums, d_acc, (size_t)T * 16, cudaMemcpyDeviceToHost);
     }

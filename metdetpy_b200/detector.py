@@ -570,6 +570,50 @@ class M3Detector(LineDetector):
             self._pending = []
         self._pending.append(T)
 
+    def submit_thr(self, ptr: int, T: int, on_device: bool, thr: np.ndarray, thr_f: np.ndarray, snr: np.ndarray):
+        """submit() with the per-frame thresholds supplied by the caller instead of the detector's own noise / EMA
+        recurrence (mdb_submit_batch_thr): the form a rank of a time-sharded run uses (sharding.py).  The three
+        arrays (int32, float64, float64; T entries) are copied before the call returns."""
+        thr = np.ascontiguousarray(thr, np.int32)
+        thr_f = np.ascontiguousarray(thr_f, np.float64)
+        snr = np.ascontiguousarray(snr, np.float64)
+        if not (len(thr) == len(thr_f) == len(snr) == T):
+            raise ValueError("threshold arrays must have T entries")
+        check(self._eng.lib.mdb_submit_batch_thr(self._eng.handle, ptr, T, int(on_device), _ptr(thr), _ptr(thr_f),
+                                                 _ptr(snr)), "submit_thr")
+        self._timer += T
+        if not hasattr(self, "_pending"):
+            self._pending = []
+        self._pending.append(T)
+
+    def seek(self, timer: int):
+        """Start the frame counter at a global frame index (mdb_seek; only before the first frame / after reset())."""
+        check(self._eng.lib.mdb_seek(self._eng.handle, int(timer)), "seek")
+        self._timer = int(timer)
+
+    def reset(self):
+        """Back to the freshly constructed state, keeping the device buffers (mdb_reset)."""
+        check(self._eng.lib.mdb_reset(self._eng.handle), "reset")
+        self._timer = 0
+        self._pending = []
+        self._dst_cache = None
+
+    def noise_sums_device(self, segments) -> list:
+        """Integer noise sums of the sample timers among device frames (mdb_noise_sums_dev), several segments in one
+        call.  segments: iterable of (ptr, T, t0); returns one (T, 2) uint64 array per segment (zero rows for frames
+        that are no sample or whose window is not inside the segment)."""
+        segs = list(segments)
+        if not segs:
+            return []
+        ptrs = (C.c_void_p * len(segs))(*[int(s[0]) for s in segs])
+        Ts = np.array([int(s[1]) for s in segs], np.int32)
+        t0s = np.array([int(s[2]) for s in segs], np.int64)
+        sums = np.zeros((int(Ts.sum()), 2), np.uint64)
+        check(self._eng.lib.mdb_noise_sums_dev(self._eng.handle, len(segs), C.cast(ptrs, C.c_void_p), _ptr(Ts), _ptr(t0s),
+                                               _ptr(sums)), "noise_sums_device")
+        offs = np.concatenate(([0], np.cumsum(Ts)))
+        return [sums[offs[k]:offs[k + 1]] for k in range(len(segs))]
+
     def collect(self, want_lines: bool = True):
         """Waits for the oldest submitted batch (mdb_collect_batch); returns its list of
         (lines, cls_pred), or None with want_lines=False (scalars of the last frame still update)."""

@@ -243,3 +243,120 @@ def detect_sharded(engine, frames: np.ndarray, shard: Shard, total_frames: int, 
         dst = dst[skip:]
     records = gather_lines(res, shard.start, group, device)
     return res, dst, records, (thr[shard.start:shard.end], thr_f[shard.start:shard.end], snr[shard.start:shard.end])
+
+
+# ---------------------------------------------------------------------------------------------
+# Device-resident chunks on the product pipeline (what bench.py --gpus N runs)
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class Segment:
+    """T frames, contiguous in device memory at `ptr`, global index of the first one `t0`; `history` frames of the
+    stream lie in memory right in front of ptr (needed by noise windows that start before the segment)."""
+    ptr: int
+    T: int
+    t0: int
+    history: int = 0
+
+
+def chunk_noise_samples(det, segments: Sequence[Segment], n: int, interval: int, start: int, end: int, frame_bytes: int):
+    """(timer, sum d, sum d^2) of the noise samples with timers in (start, end], from device frames: one
+    mdb_noise_sums_dev call for all segments, on the detector's own stream and buffers."""
+    calls, wanted = [], []
+    for sg in segments:
+        lo, hi = max(sg.t0, start), min(sg.t0 + sg.T, end)
+        taus = [tau for tau in range(lo + 1, hi + 1) if is_noise_sample(tau, n, interval)]
+        if not taus:
+            continue
+        back = min(sg.history, n - 1) if sg.t0 > 0 else 0
+        first = sg.t0 - back
+        for tau in taus:
+            if first > 0 and tau - n < first:
+                raise ValueError(f"noise sample {tau}: its window starts before the frames of the segment")
+        calls.append((sg.ptr - back * frame_bytes, sg.T + back, first))
+        wanted.append((first, taus))
+    out = []
+    for (first, taus), sums in zip(wanted, det.noise_sums_device(calls)):
+        for tau in taus:
+            i = tau - 1 - first
+            out.append((tau, int(sums[i, 0]), int(sums[i, 1])))
+    return out
+
+
+def replay_thresholds_native(samples: Sequence[tuple], roi_pixels: int, n: int, t_begin: int, t_end: int, *, adaptive: bool,
+                             init_value: int, sensitivity: str, interval: int):
+    """replay_thresholds in the library's host code (mdb_replay_thresholds): (timer, s1, s2) triples sorted by timer ->
+    (thr int32, thr_float f64, snr f64) for frames t_begin .. t_end-1.  Same arithmetic as the device recurrence."""
+    from . import _lib
+    lib = _lib.load()
+    smp = sorted(samples)
+    timers = np.array([s[0] for s in smp], np.int64)
+    sums = np.array([[s[1], s[2]] for s in smp], np.uint64).reshape(-1, 2)
+    m = t_end - t_begin
+    thr, thr_f, snr = np.empty(m, np.int32), np.empty(m, np.float64), np.empty(m, np.float64)
+    _lib.check(lib.mdb_replay_thresholds(len(smp), timers.ctypes.data, sums.ctypes.data, int(roi_pixels), int(n),
+                                         int(interval), int(bool(adaptive)), int(init_value),
+                                         {"low": 0, "normal": 1, "high": 2}[sensitivity], int(t_begin), int(t_end),
+                                         thr.ctypes.data, thr_f.ctypes.data, snr.ctypes.data), "mdb_replay_thresholds")
+    return thr, thr_f, snr
+
+
+def pack_line_records(det, T: int, first_frame: int, out: np.ndarray) -> int:
+    """Line records (frame, x1, y1, x2, y2, nonline_prob) of the batch collected last into out[:k] (float64 rows),
+    without a per-frame Python loop.  Returns k (clipped to len(out))."""
+    eng = det._eng
+    nl = det.last_infos["n_lines"][:T]
+    k = min(int(nl.sum()), len(out))
+    if k:
+        sel = np.arange(eng.lines.shape[1])[None, :] < nl[:, None]
+        out[:k, 0] = (first_frame + np.repeat(np.arange(T), nl))[:k]
+        out[:k, 1:5] = eng.lines[:T][sel][:k]
+        out[:k, 5] = eng.prob[:T][sel][:k]
+    return k
+
+
+def batch_digest(det, T: int) -> bytes:
+    """8-byte digest of a collected batch: per-frame threshold, on-pixel count, raw segment count and the raw Hough
+    segments themselves.  Two runs that agree on every digest produced the same masks' statistics and lines."""
+    import hashlib
+    eng = det._eng
+    info = det.last_infos[:T]
+    h = hashlib.blake2b(digest_size=8)
+    h.update(np.ascontiguousarray(info["bi_threshold"]).tobytes())
+    h.update(np.ascontiguousarray(info["n_on"]).tobytes())
+    h.update(np.ascontiguousarray(info["lines_num"]).tobytes())
+    nraw = info["n_raw"]
+    if nraw.any():
+        sel = np.arange(eng.raw.shape[1])[None, :] < nraw[:, None]
+        h.update(np.ascontiguousarray(eng.raw[:T][sel]).tobytes())
+    return h.digest()
+
+
+def run_chunk(det, segments: Sequence[Segment], shard: Shard, thr, thr_f, snr, *, thr_base: int = 0, on_batch=None,
+              in_flight: int = 3):
+    """One rank's chunk on the product pipeline: mdb_reset + mdb_seek(halo_start), then every segment with the
+    replayed thresholds (mdb_submit_batch_thr), `in_flight` batches submitted ahead.  `segments` cover
+    [halo_start, end) in order; segments that end at or before shard.start are halo (results dropped).
+    thr[i] belongs to global frame thr_base + i.  on_batch(det, seg) is called after each collected non-halo batch
+    (det.last_infos etc. describe it)."""
+    det.reset()
+    det.seek(shard.halo_start)
+    segs = list(segments)
+    if segs and segs[0].t0 != shard.halo_start:
+        raise ValueError("segments must start at the shard's halo_start")
+    nxt = 0
+
+    def submit(sg):
+        a, b = sg.t0 - thr_base, sg.t0 - thr_base + sg.T
+        det.submit_thr(sg.ptr, sg.T, True, thr[a:b], thr_f[a:b], snr[a:b])
+
+    for k in range(min(in_flight - 1, len(segs))):
+        submit(segs[nxt])
+        nxt += 1
+    for i, sg in enumerate(segs):
+        if nxt < len(segs):
+            submit(segs[nxt])
+            nxt += 1
+        halo = sg.t0 + sg.T <= shard.start
+        det.collect(want_lines=not halo)
+        if not halo and on_batch is not None:
+            on_batch(det, sg)

@@ -412,3 +412,66 @@ def test_time_sharded_equals_reference_golden(name, world):
             refc = ragged_get(g["cls_pred"], g["nms_offs"], t)
             raw = ragged_get(g["raw_lines"], g["raw_offs"], t)
             assert_nms_equivalent(lines, np.asarray(cls).reshape(-1, 10)[:, -1], ref, refc[:, -1], raw, t)
+
+
+@pytest.mark.parametrize("name,world,batch", [("synth_384x216_n12_dyon_mask", 3, 16), ("clip_192x144_n25", 2, 32),
+                                              ("synth_320x240_n5_dyoff", 4, 7)])
+def test_device_chunk_pipeline_equals_reference_golden(name, world, batch):
+    """The multi-GPU path of bench.py with `world` virtual ranks on one GPU, frames resident on the device: noise sums of
+    every rank's chunk (mdb_noise_sums_dev), native threshold replay (mdb_replay_thresholds), then mdb_reset + mdb_seek
+    + a halo batch + the chunk with three batches in flight (sharding.run_chunk).  Thresholds, on-pixel counts, raw
+    Hough segments and NMS lines of every frame must equal the reference's sequential run."""
+    import torch
+    from metdetpy_b200 import sharding as S
+    from metdetpy_b200.detector import M3Detector
+    g = load_det_case(name)
+    cfg, n, T = _cfg(g["cfg"]), g["n"], len(g["frames"])
+    H, W = g["frames"].shape[1:]
+    dev_frames = torch.from_numpy(g["frames"]).cuda().contiguous()
+    base, fb = dev_frames.data_ptr(), H * W
+    det = M3Detector(n / g["fps"] + 1e-9, g["fps"], g["mask"], 10, cfg, None, max_batch=batch)
+    shards = S.plan_shards(T, world, n)
+    c = g["cfg"]
+
+    def pieces(lo, hi):
+        return [S.Segment(base + t * fb, min(batch, hi - t), t, history=t) for t in range(lo, hi, batch)]
+
+    samples = []
+    for sh in shards:
+        samples += S.chunk_noise_samples(det, pieces(sh.start, sh.end), n, c["interval"], sh.start, sh.end, fb)
+    roi = det.stack.std_roi
+    roi_px = (roi[2] - roi[0]) * (roi[3] - roi[1])
+    thr, thr_f, snr = S.replay_thresholds_native(samples, roi_px, n, 0, T, adaptive=c["adaptive"], init_value=c["init_value"],
+                                                 sensitivity=c["sensitivity"], interval=c["interval"])
+    assert np.array_equal(thr, g["bi_threshold"])
+    assert np.allclose(snr, g["snr"], rtol=1e-12, atol=0)
+    seen = 0
+    for sh in shards:
+        segs = ([S.Segment(base + sh.halo_start * fb, sh.start - sh.halo_start, sh.halo_start)] if sh.start > sh.halo_start else [])
+        if segs and segs[0].T > batch:  # a halo longer than a batch goes in pieces
+            segs = pieces(sh.halo_start, sh.start)
+        segs += pieces(sh.start, sh.end)
+        got = []
+
+        def on_batch(d, sg):
+            for i in range(sg.T):
+                info = d.last_infos[i]
+                k = int(info["n_raw"])
+                got.append((sg.t0 + i, int(info["bi_threshold"]), int(info["n_on"]), int(info["lines_num"]),
+                            d._eng.raw[i, :k].copy(), d._eng.lines[i, :int(info["n_lines"])].copy(),
+                            d._eng.prob[i, :int(info["n_lines"])].copy()))
+        S.run_chunk(det, segs, sh, thr, thr_f, snr, on_batch=on_batch)
+        assert [x[0] for x in got] == list(range(sh.start, sh.end))
+        for t, bt, non, ln, raw, lines, prob in got:
+            assert bt == g["bi_threshold"][t], t
+            assert non == int(np.count_nonzero(g["dst"][t])), t
+            assert ln == g["lines_num"][t], t
+            rraw = ragged_get(g["raw_lines"], g["raw_offs"], t)
+            if ln <= 500:
+                assert np.array_equal(raw, rraw), t
+            ref = ragged_get(g["nms_lines"], g["nms_offs"], t)
+            refc = ragged_get(g["cls_pred"], g["nms_offs"], t)
+            assert_nms_equivalent(lines, prob, ref, refc[:, -1], rraw, t)
+            seen += 1
+    assert seen == T
+    det.close()

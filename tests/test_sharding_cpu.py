@@ -91,3 +91,33 @@ def test_two_rank_gloo_equals_sequential():
     rec = out[0]["records"]  # gathered to rank 0, in frame order
     flat = [[t, *row.tolist()] for t, (l, _) in enumerate(lines_ref) for row in l]
     assert [r[:5] for r in rec] == flat and n_lines == len(flat) and n_lines > 0
+
+
+@pytest.mark.parametrize("n,interval,sens,adaptive", [(5, 1, "normal", True), (12, 2, "high", True), (30, 2, "low", True),
+                                                      (7, 3, "normal", False)])
+def test_native_replay_equals_python_replay(n, interval, sens, adaptive):
+    """mdb_replay_thresholds (host C++ in the library, what the multi-GPU path uses) against the Python statement of
+    the recurrence: identical thresholds, bit-identical doubles; sub-ranges; a missing sample is an error."""
+    rng = np.random.default_rng(n)
+    T, roi_px = 700, 37 * 53
+    samples = []
+    for tau in range(1, T + 1):
+        if S.is_noise_sample(tau, n, interval):
+            L = min(n, tau)
+            N_ = L * roi_px
+            mean = rng.uniform(0, 3)
+            s1 = int(mean * N_)
+            s2 = int((mean * mean + rng.uniform(0.5, 9)) * N_)
+            samples.append((tau, s1, s2))
+    sig = {tau: S.sigma_from_sums(s1, s2, min(n, tau), roi_px) for tau, s1, s2 in samples}
+    thr, thr_f, snr = S.replay_thresholds(sig, T, n, adaptive=adaptive, init_value=6, sensitivity=sens, interval=interval)
+    a, b, c = S.replay_thresholds_native(samples, roi_px, n, 0, T, adaptive=adaptive, init_value=6, sensitivity=sens,
+                                         interval=interval)
+    assert np.array_equal(a, thr) and np.array_equal(b, thr_f) and np.array_equal(c, snr)
+    a, b, c = S.replay_thresholds_native(samples, roi_px, n, 123, 611, adaptive=adaptive, init_value=6, sensitivity=sens,
+                                         interval=interval)
+    assert np.array_equal(a, thr[123:611]) and np.array_equal(b, thr_f[123:611]) and np.array_equal(c, snr[123:611])
+    if len(samples) > 3:
+        with pytest.raises(ValueError):
+            S.replay_thresholds_native(samples[:2] + samples[3:], roi_px, n, 0, T, adaptive=adaptive, init_value=6,
+                                       sensitivity=sens, interval=interval)
