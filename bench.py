@@ -441,32 +441,33 @@ def main_ours(a):
     def sharded_job(steps, vrank=rank, vworld=world, gather=None, digests=None, timed=False, group_exchange=True):
         C = steps * bps * B                       # frames per rank
         sh = S.Shard(vrank, vrank * C, (vrank + 1) * C, max(0, vrank * C - pad))
+        tp = [time.perf_counter()]
         # phase A: integer noise sums of the sample timers of this rank's chunk
         segs = [S.Segment(stream.ptr(t), B, t, history=pad) for t in range(sh.start, sh.end, B)]
         mine = S.chunk_noise_samples(det, segs, n, interval, sh.start, sh.end, HW)
+        tp.append(time.perf_counter())
         # phase B: all-gather of the triples (one packed int64 tensor; every rank owns the same number of samples +-1)
         if group_exchange and world > 1:
             cap = C // (interval * n) + n + 2
             buf = torch.zeros((cap, 3), dtype=torch.int64)
             buf[0, 0] = len(mine)
-            if mine:
-                buf[1:1 + len(mine)] = torch.tensor(mine, dtype=torch.int64)
-            dbuf = buf.to(dev, non_blocking=False)
+            buf[1:1 + len(mine)] = torch.from_numpy(mine)
             allb = torch.zeros((world * cap, 3), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(allb, dbuf)
+            dist.all_gather_into_tensor(allb, buf.to(dev))
             allh = allb.cpu().view(world, cap, 3).numpy()
-            samples = []
-            for r in range(vrank + 1):  # later ranks' samples are not needed for this rank's thresholds
-                k = int(allh[r, 0, 0])
-                samples += [tuple(int(v) for v in row) for row in allh[r, 1:1 + k]]
+            # later ranks' samples are not needed for this rank's thresholds
+            samples = np.concatenate([allh[r, 1:1 + int(allh[r, 0, 0])] for r in range(vrank + 1)])
         else:
-            samples = list(mine)
+            parts = []
             for r in range(vrank):      # virtual ranks on one GPU: compute the earlier chunks' samples here
                 segs_r = [S.Segment(stream.ptr(t), B, t, history=pad) for t in range(r * C, (r + 1) * C, B)]
-                samples += S.chunk_noise_samples(det, segs_r, n, interval, r * C, (r + 1) * C, HW)
+                parts.append(S.chunk_noise_samples(det, segs_r, n, interval, r * C, (r + 1) * C, HW))
+            samples = np.concatenate(parts + [mine])
+        tp.append(time.perf_counter())
         # phase C: bit-identical threshold replay for the frames this rank ingests
         thr, thr_f, snr = S.replay_thresholds_native(samples, roi_px, n, sh.halo_start, sh.end, adaptive=True, init_value=7,
                                                      sensitivity="normal", interval=interval)
+        tp.append(time.perf_counter())
         # phase D: seek + halo batch + chunk, three batches in flight; line records shipped once per step
         run = ([S.Segment(stream.ptr(sh.halo_start), sh.start - sh.halo_start, sh.halo_start)] if sh.start > sh.halo_start else []) + segs
         state = {"k": 0}
@@ -487,6 +488,11 @@ def main_ours(a):
             if trace is not None and timed and state["k"] % bps == 0:
                 trace.append(time.perf_counter())
         S.run_chunk(det, run, sh, thr, thr_f, snr, thr_base=sh.halo_start, on_batch=on_batch)
+        tp.append(time.perf_counter())
+        if trace is not None and timed:
+            d = np.diff(tp) * 1e3
+            print(f"rank {rank} phases (ms): noise sums {d[0]:.2f}, all-gather {d[1]:.2f}, replay {d[2]:.2f}, "
+                  f"seek + halo + chunk {d[3]:.2f} ({len(mine)} own samples, {len(samples)} replayed)", file=sys.stderr)
         return sh
 
     # ---- warm-up + timed region ------------------------------------------------------------------------------------

@@ -129,6 +129,14 @@ int mdb_collect_batch(mdb_handle h, mdb_frame_info *infos, int32_t *lines, doubl
  *                  the host over the samples of all chunks.
  *  mdb_submit_batch_thr  mdb_submit_batch with per-frame thresholds supplied by the caller instead of
  *                  the handle's own recurrence. */
+/* mdb_submit_batch / mdb_submit_batch_thr (thr arrays NULL: the handle's own recurrence) with flags:
+ *  MDB_SUBMIT_HALO  the frames are the look-back halo of a time-sharded chunk: they only fill the window and the
+ *                   dynamic-mask history (temporal pass + median/close); no mask bytes, no Hough; the collected
+ *                   frame infos carry the thresholds, n_on = 0 and no lines.  (After mdb_seek the first frames see
+ *                   an empty window and would otherwise produce full-frame masks.) */
+#define MDB_SUBMIT_HALO 1
+int mdb_submit_batch_ex(mdb_handle h, const uint8_t *frames, int T, int on_device, const int32_t *thr,
+                        const double *thr_float, const double *snr, int flags);
 int mdb_seek(mdb_handle h, int64_t timer);
 int mdb_noise_sums(const uint8_t *frames, int T, int on_device, int64_t t0, int width, int height,
                    int window, int nz_interval, const int32_t *roi, const uint8_t *mask,

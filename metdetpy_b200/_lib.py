@@ -63,6 +63,7 @@ SYMBOLS = {
     "mdb_seek": (_I, [_VP, C.c_int64]),
     "mdb_noise_sums": (_I, [_VP, _I, _I, C.c_int64, _I, _I, _I, _I, _VP, _VP, _VP, _I]),
     "mdb_submit_batch_thr": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP]),
+    "mdb_submit_batch_ex": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _I]),
     "mdb_gauss_stack": (_I, [_VP, _I, _SZ, _VP, _VP, _I, _I, _I, _I]),
     "mdb_preproc_create": (_I, [_I, _I, _I, _I, _I, _I, _VP, _I, _I, _I, C.POINTER(_VP)]),
     "mdb_preproc_run": (_I, [_VP, _VP, _I, _I, _VP, _I, C.POINTER(C.c_int32)]),

@@ -63,13 +63,13 @@ noise_sample_kernel(FrameSrc src, int W, int n, long long timer0, long long std_
     }
 }
 
-// Same sums, four pixels per 32-bit load (W % 4 == 0, n <= 128): the ROI rows are widened to 4-pixel alignment and the
-// pixels outside [c0, c0 + rw) are masked out.  Per word and frame: sum of squares of the four bytes by one IDP.4A
-// (it only enters d2 summed over pixels), per-pixel sums as u16x2 pairs of the even and the odd bytes.  The loads of a
-// window's frames are independent, so a thread keeps several in flight.
+// Same sums, sixteen pixels per 16-byte load (W % 16 == 0, n <= 128, 16-byte aligned frames): the ROI rows are widened
+// to 16-pixel alignment and the pixels outside [c0, c0 + rw) are masked out.  Per 32-bit word and frame: sum of squares
+// of the four bytes by one IDP.4A (it only enters d2 summed over pixels), per-pixel sums as u16x2 pairs of the even and
+// the odd bytes.  The loads of a window's frames are independent, so a thread keeps several in flight.
 __global__ void __launch_bounds__(256)
-noise_sample4_kernel(FrameSrc src, int W, int n, long long timer0, long long std_interval, int r0, int c0, int rh,
-                     int rw, unsigned long long *acc, long long min_tau, const __grid_constant__ SampleList sl) {
+noise_sample16_kernel(FrameSrc src, int W, int n, long long timer0, long long std_interval, int r0, int c0, int rh,
+                      int rw, unsigned long long *acc, long long min_tau, const __grid_constant__ SampleList sl) {
     const int i = sl.count < 0 ? blockIdx.y : sl.idx[blockIdx.y];
     const long long tau = timer0 + i + 1;
     if (tau < min_tau || !is_noise_sample(tau, n, std_interval)) return;
@@ -78,34 +78,50 @@ noise_sample4_kernel(FrameSrc src, int W, int n, long long timer0, long long std
     __shared__ const uint8_t *fp[128];
     for (int k = threadIdx.x; k < L; k += blockDim.x) fp[k] = src.frame(t - k);
     __syncthreads();
-    const int c0a = c0 & ~3, c1a = (c0 + rw + 3) & ~3;
-    const int wpr = (c1a - c0a) >> 2;  // words per ROI row
-    const int total = rh * wpr;
+    const int c0a = c0 & ~15, c1a = (c0 + rw + 15) & ~15;
+    const int gpr = (c1a - c0a) >> 4;  // 16-pixel groups per ROI row
+    const int total = rh * gpr;
     unsigned long long d1 = 0, d2 = 0;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
-        const int y = r0 + q / wpr, x = c0a + ((q % wpr) << 2);
+        const int y = r0 + q / gpr, x = c0a + ((q % gpr) << 4);
         const size_t p = (size_t)y * W + x;
-        unsigned keep = 0u;  // 0xff for the bytes of this word that are ROI pixels (and unmasked)
+        unsigned keep[4];  // 0xff for the bytes that are ROI pixels (and unmasked)
 #pragma unroll
-        for (int b = 0; b < 4; b++)
-            if (x + b >= c0 && x + b < c0 + rw) keep |= 0xffu << (8 * b);
-        if (src.mask) keep &= *reinterpret_cast<const unsigned *>(src.mask + p) * 0xffu;
-        unsigned se = 0, so = 0, sq = 0;  // even / odd byte sums (u16x2), sum of squares of all four bytes
-#pragma unroll 6
+        for (int w = 0; w < 4; w++) {
+            keep[w] = 0u;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int xx = x + 4 * w + b;
+                if (xx >= c0 && xx < c0 + rw) keep[w] |= 0xffu << (8 * b);
+            }
+        }
+        if (src.mask) {
+            const uint4 m = *reinterpret_cast<const uint4 *>(src.mask + p);
+            keep[0] &= m.x * 0xffu; keep[1] &= m.y * 0xffu; keep[2] &= m.z * 0xffu; keep[3] &= m.w * 0xffu;
+        }
+        unsigned se[4] = {0, 0, 0, 0}, so[4] = {0, 0, 0, 0}, sq = 0;
+#pragma unroll 5
         for (int k = 0; k < L; k++) {
-            const unsigned v = __ldg(reinterpret_cast<const unsigned *>(fp[k] + p)) & keep;
-            se += v & 0x00ff00ffu;
-            so += (v >> 8) & 0x00ff00ffu;
-            sq = __dp4a(v, v, sq);
+            const uint4 v4 = __ldg(reinterpret_cast<const uint4 *>(fp[k] + p));
+            const unsigned v[4] = {v4.x & keep[0], v4.y & keep[1], v4.z & keep[2], v4.w & keep[3]};
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                se[w] += v[w] & 0x00ff00ffu;
+                so[w] += (v[w] >> 8) & 0x00ff00ffu;
+                sq = __dp4a(v[w], v[w], sq);  // 16 * 128 * 255^2 < 2^32
+            }
         }
         d2 += sq;
-        const unsigned sx4[4] = {se & 0xffffu, so & 0xffffu, se >> 16, so >> 16};
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const unsigned sx = sx4[b], m = sx / (unsigned)L;
-            d1 += sx - (unsigned)L * m;
-            // sum of d^2 = sxx - 2 m sx + L m^2; the sxx part is already in; a masked-out pixel has sx = m = 0
-            d2 += (unsigned long long)((long long)L * m * m - 2ll * m * sx);
+        for (int w = 0; w < 4; w++) {
+            const unsigned sx4[4] = {se[w] & 0xffffu, so[w] & 0xffffu, se[w] >> 16, so[w] >> 16};
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const unsigned sx = sx4[b], m = sx / (unsigned)L;
+                d1 += sx - (unsigned)L * m;
+                // sum of d^2 = sxx - 2 m sx + L m^2; the sxx part is already in; a masked-out pixel has sx = m = 0
+                d2 += (unsigned long long)((long long)L * m * m - 2ll * m * sx);
+            }
         }
     }
     for (int o = 16; o; o >>= 1) {
@@ -128,13 +144,13 @@ static inline void launch_noise_samples(const FrameSrc &src, int W, int n, long 
                                         int T, cudaStream_t st) {
     const int rh = roi[2] - roi[0], rw = roi[3] - roi[1];
     const int rows = sl.count < 0 ? T : sl.count;
-    const bool mask_ok = !src.mask || ((uintptr_t)src.mask & 3) == 0;
-    const bool base_ok = ((uintptr_t)src.ring & 3) == 0 && ((uintptr_t)src.cur & 3) == 0 && (src.HW & 3) == 0;
-    if (W % 4 == 0 && n <= 128 && mask_ok && base_ok) {
-        const int words = rh * ((((roi[1] + rw + 3) & ~3) - (roi[1] & ~3)) >> 2);
-        const int gx = std::max(1, std::min((words + 255) / 256, 1184));
-        noise_sample4_kernel<<<dim3(gx, rows), 256, 0, st>>>(src, W, n, timer0, std_interval, roi[0], roi[1], rh, rw, acc,
-                                                           min_tau, sl);
+    const bool mask_ok = !src.mask || ((uintptr_t)src.mask & 15) == 0;
+    const bool base_ok = ((uintptr_t)src.ring & 15) == 0 && ((uintptr_t)src.cur & 15) == 0 && (src.HW & 15) == 0;
+    if (W % 16 == 0 && n <= 128 && mask_ok && base_ok) {
+        const int groups = rh * ((((roi[1] + rw + 15) & ~15) - (roi[1] & ~15)) >> 4);
+        const int gx = std::max(1, std::min((groups + 255) / 256, 1184));
+        noise_sample16_kernel<<<dim3(gx, rows), 256, 0, st>>>(src, W, n, timer0, std_interval, roi[0], roi[1], rh, rw, acc,
+                                                            min_tau, sl);
     } else {
         const int gx = std::max(1, std::min((rh * rw + 255) / 256, 592));
         noise_sample_kernel<<<dim3(gx, rows), 256, 0, st>>>(src, W, n, timer0, std_interval, roi[0], roi[1], rh, rw, acc,

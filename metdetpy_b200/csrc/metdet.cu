@@ -70,6 +70,7 @@ struct BatchCtx {
     cudaEvent_t tl[12] = {};         // optional timeline marks (debug)
     int T = 0;  // 0: free
     int bits_parity = 0;  // which predicate-bit buffer this batch uses
+    bool halo = false;    // results not wanted (look-back frames of a time-sharded run): no dst, no Hough
     long long timer0 = 0;
     long long seq = 0;
 };
@@ -462,7 +463,7 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
         sl.alist = c.d_alist; sl.acount = c.d_acount; sl.wlist = c.d_wlist; sl.wcount = c.d_wcount; sl.dense = c.d_dense;
         int rc = stream_kernel_launch(h->sk, src, timer0, dy0, T, h->cfg.dy_mask, c.d_thr, act_ring(h),
                                       c.d_dst, c.d_dstbits, c.d_npoints, c.d_points, MDB_POINT_CAP, sl, h->stream,
-                                      h->stream2, c.ev_f1, c.ev_d0, (int)(c.bits_parity & 1), &nl);
+                                      h->stream2, c.ev_f1, c.ev_d0, (int)(c.bits_parity & 1), &nl, c.halo);
         if (rc != 0) return fail(MDB_ERR_CUDA, "stream kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
         // generic per-frame kernel: the whole chain runs on the back stream, after the front stream's thresholds
@@ -491,6 +492,17 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
 
 static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
     CK(cudaStreamWaitEvent(h->stream3, c.ev_d1, 0));  // dst (stream2) has produced the on-pixel lists
+    if (c.halo) {  // no results wanted: empty masks, no lines
+        CK(cudaMemsetAsync(c.d_npoints, 0, T * sizeof(unsigned), h->stream3));
+        CK(cudaMemsetAsync(c.d_nlines, 0, T * sizeof(int), h->stream3));
+        CK(cudaMemcpyAsync(c.h_thr, c.d_thr, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream3));
+        CK(cudaMemcpyAsync(c.h_thrf, c.d_thrf, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream3));
+        CK(cudaMemcpyAsync(c.h_snr, c.d_snr, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream3));
+        CK(cudaMemcpyAsync(c.h_npoints, c.d_npoints, T * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream3));
+        CK(cudaMemcpyAsync(c.h_nlines, c.d_nlines, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream3));
+        CK(cudaEventRecord(c.ev_done, h->stream3));
+        return MDB_OK;
+    }
     CK(cudaMemsetAsync(c.d_queue, 0, 4 * sizeof(unsigned), h->stream3));
     TL(c, 4, h->stream3);
     ppht_order_kernel<<<T, 32, HOUGH_ORDER_CAP * 2, h->stream3>>>(T, HOUGH_ORDER_CAP, c.d_npoints, c.d_order);
@@ -649,6 +661,7 @@ extern "C" int mdb_detect(mdb_handle h, mdb_frame_info *info, int32_t *lines, do
     BatchCtx &c = h->ctx[0];
     int rc = front_after_scalar(h);  // the history copy of the last batch runs on the scalar stream
     if (rc) return rc;
+    c.halo = false;
     rc = launch_fused(h, c, frame_src(h, nullptr, 0), 1, h->timer - 1, h->dy_timer);
     if (rc) return rc;
     rc = launch_hough_and_copy(h, c, 1);
@@ -673,7 +686,7 @@ extern "C" int mdb_detect(mdb_handle h, mdb_frame_info *info, int32_t *lines, do
 
 // ---- batched API -----------------------------------------------------------------------------
 static int submit_impl(mdb_handle h, const uint8_t *frames, int T, int on_device, const int32_t *thr,
-                       const double *thrf, const double *snr) {
+                       const double *thrf, const double *snr, int flags = 0) {
     if (!h || !frames) return fail(MDB_ERR_INVALID, "mdb_submit_batch: null argument");
     if (T < 1 || T > h->cfg.max_batch)
         return fail(MDB_ERR_INVALID, "mdb_submit_batch: T=%d outside 1..max_batch=%d", T, h->cfg.max_batch);
@@ -757,6 +770,7 @@ static int submit_impl(mdb_handle h, const uint8_t *frames, int T, int on_device
     CK(cudaEventRecord(c.ev_src, h->sstream));
     CK(cudaStreamWaitEvent(h->stream, c.ev_thr, 0));
     c.bits_parity = (int)(h->submitted & 1);
+    c.halo = (flags & MDB_SUBMIT_HALO) != 0;
     rc = launch_fused(h, c, src, T, timer0, h->dy_timer);
     if (rc) return rc;
     rc = launch_hough_and_copy(h, c, T);
@@ -778,6 +792,14 @@ extern "C" int mdb_submit_batch_thr(mdb_handle h, const uint8_t *frames, int T, 
                                     const int32_t *thr, const double *thr_float, const double *snr) {
     if (!thr || !thr_float || !snr) return fail(MDB_ERR_INVALID, "mdb_submit_batch_thr: null threshold arrays");
     return submit_impl(h, frames, T, on_device, thr, thr_float, snr);
+}
+
+extern "C" int mdb_submit_batch_ex(mdb_handle h, const uint8_t *frames, int T, int on_device, const int32_t *thr,
+                                   const double *thr_float, const double *snr, int flags) {
+    if ((thr || thr_float || snr) && !(thr && thr_float && snr))
+        return fail(MDB_ERR_INVALID, "mdb_submit_batch_ex: all three threshold arrays or none");
+    if (flags & ~MDB_SUBMIT_HALO) return fail(MDB_ERR_INVALID, "mdb_submit_batch_ex: unknown flags 0x%x", flags);
+    return submit_impl(h, frames, T, on_device, thr, thr_float, snr, flags);
 }
 
 extern "C" int mdb_seek(mdb_handle h, int64_t timer) {

@@ -354,7 +354,7 @@ static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long t
                                        int dy_on, const int *d_thr, ActRing ring, uint8_t *dst, uint32_t *dstbits,
                                        unsigned *npoints, uint32_t *points, int cap, SparseLists sl, cudaStream_t st1,
                                        cudaStream_t st2, cudaEvent_t ev_f1, cudaEvent_t ev_d0, int parity,
-                                       int *launches) {
+                                       int *launches, bool act_only = false) {
     uint32_t *const bits = parity ? s.d_bits2 : s.d_bits;
     const int HWG = (int)((size_t)s.W * s.H / (4 * s.t_wpt));  // pixel groups = threads
     const int nt = s.t_threads;
@@ -408,6 +408,10 @@ static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long t
         act_kernel<<<g, SP_WARPS * 32, 0, st2>>>(bits, s.W, s.H, T, s.sp_rows, strips, bands, ring, dy0, sl);
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
+    if (act_only) {  // halo frames of a time-sharded run: only the window and the act history are wanted
+        *launches = 2;
+        return 0;
+    }
     if (cudaMemsetAsync(sl.dense, 0, sizeof(unsigned), st2) != cudaSuccess) return -1;
     if (s.force_dense) {  // test hook: every frame takes the full-scan path
         dst_force_dense_kernel<<<(T + 127) / 128, 128, 0, st2>>>(T, sl);

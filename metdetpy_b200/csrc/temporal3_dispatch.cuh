@@ -89,6 +89,19 @@ static inline int temporal3_launch(int n, int variant, const FrameSrc &src, long
             default: break;
         }
     }
+    if (n == 60 && variant) {
+        switch (variant) {
+            T3_CASE(1, 30, 10, 2, 10, 3)
+            T3_CASE(2, 30, 10, 2, 15, 3)
+            T3_CASE(3, 30, 15, 2, 15, 3)
+            T3_CASE(4, 30, 15, 2, 10, 3)
+            T3_CASE(5, 20, 10, 3, 10, 3)
+            T3_CASE(6, 15, 15, 4, 15, 2)
+            T3_CASE(7, 20, 20, 3, 10, 2)
+            T3_CASE(8, 30, 10, 2, 6, 3)
+            default: break;
+        }
+    }
     switch (n) {
         T3_CASE(2, 2, 2, 1, 2, 6)
         T3_CASE(3, 3, 3, 1, 3, 6)
@@ -113,12 +126,14 @@ static inline int temporal3_launch(int n, int variant, const FrameSrc &src, long
         T3_CASE(28, 14, 14, 2, 14, 4)
         T3_CASE(30, 15, 15, 2, 15, 4)
         T3_CASE(32, 16, 16, 2, 16, 4)
-        T3_CASE(36, 18, 9, 2, 6, 3)
-        T3_CASE(40, 20, 10, 2, 5, 3)
-        T3_CASE(48, 24, 12, 2, 6, 3)
+        // long windows: 3 CTAs per SM (the 60-frame ring is half registers, half page); half a body of frames in flight
+        // (4K n = 60: 2.45 -> 1.59 ms against the second generation)
+        T3_CASE(36, 18, 9, 2, 9, 3)
+        T3_CASE(40, 20, 10, 2, 10, 3)
+        T3_CASE(48, 24, 12, 2, 12, 3)
         T3_CASE(50, 25, 5, 2, 5, 3)
-        T3_CASE(60, 30, 10, 2, 6, 3)
-        T3_CASE(64, 32, 16, 2, 8, 3)
+        T3_CASE(60, 30, 15, 2, 15, 3)
+        T3_CASE(64, 32, 16, 2, 16, 3)
         default: return -2;
     }
 #undef T3_CASE

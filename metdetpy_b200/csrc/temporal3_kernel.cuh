@@ -149,7 +149,7 @@ struct Layout {
     static constexpr int N = U * P;     // window length
     static constexpr int KD = N / BL;   // blocks per window
     static constexpr int NB = U / BL;   // blocks per unrolled body
-    static_assert(U % BL == 0 && BL >= 2 && (P == 1 || P == 2), "bad temporal3 shape");
+    static_assert(U % BL == 0 && BL >= 2 && P >= 1 && P <= 4, "bad temporal3 shape");
     // shared memory of a CTA: suffix max [BL][NT] uint4 | block maxima [KD][NT] uint4 | page [(P-1)*U][NT] uint2 | table [T] uint2
     static constexpr size_t suf_bytes = (size_t)BL * T3_NT * 16;
     static constexpr size_t fifo_bytes = (size_t)KD * T3_NT * 16;
@@ -310,6 +310,10 @@ T3_HD void thread_main(const FrameSrc &src, long long t0, int T, int g, int tid,
 
     unsigned parity = 0;  // FEED 1: body number & 1
     int fbase = 0;        // FEED 1: first frame of the body
+    // P > 1: the page holds the (P-1)*U frames younger than the registers' as P-1 sub-pages of U frames; the sub-page of
+    // body b mod (P-1) holds the oldest of them, which this body moves into the registers and replaces by its own frames
+    uint2 *subpage = page;
+    int sp = 0;
     for (int rem = T + nz; rem > 0; rem -= U) {
 #pragma unroll
         for (int j = 0; j < U; j++) {
@@ -341,9 +345,9 @@ T3_HD void thread_main(const FrameSrc &src, long long t0, int T, int g, int tid,
             const unsigned o0 = r0[j], o1 = r1[j];  // frame t-N leaves the window
             if (P == 1) { r0[j] = x0; r1[j] = x1; }
             else {
-                const uint2 pg = page[j * T3_NT];   // frame t-U moves from the page into the registers
+                const uint2 pg = subpage[j * T3_NT];   // frame t-(P-1)*U moves from the page into the registers
                 r0[j] = pg.x; r1[j] = pg.y;
-                page[j * T3_NT] = make_uint2(x0, x1);
+                subpage[j * T3_NT] = make_uint2(x0, x1);
             }
             const uint4 s = suf[jj * T3_NT];  // oldest block, positions jj+1 .. BL-1, and the whole blocks in between
             const uint2 tl = tb[j];
@@ -415,6 +419,10 @@ T3_HD void thread_main(const FrameSrc &src, long long t0, int T, int g, int tid,
         tb += U;
         parity ^= 1u;
         fbase += U;
+        if (P > 2) {
+            sp = sp + 1 == P - 1 ? 0 : sp + 1;
+            subpage = page + sp * (U * T3_NT);
+        }
     }
 }
 

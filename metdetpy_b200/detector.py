@@ -552,9 +552,10 @@ class M3Detector(LineDetector):
         self._timer += T
         self._dst_cache = None
         res = self._unpack_all(T)  # also sets last_infos (structured array, one record per frame)
-        nraw = self.last_infos["n_raw"]
-        sel = np.arange(MAX_LINES)[None, :] < nraw[:, None]
-        self.last_raw = _RaggedRows(eng.raw[:T][sel].reshape(-1, 4), np.concatenate(([0], np.cumsum(nraw))))
+        nraw = self.last_infos["n_raw"].astype(np.int64)
+        rows = np.repeat(np.arange(T), nraw)
+        cols = np.arange(int(nraw.sum())) - np.repeat(np.cumsum(nraw) - nraw, nraw)
+        self.last_raw = _RaggedRows(eng.raw[rows, cols].reshape(-1, 4), np.concatenate(([0], np.cumsum(nraw))))
         if dst_out is not None:
             return res, dst_out
         return res
@@ -570,17 +571,19 @@ class M3Detector(LineDetector):
             self._pending = []
         self._pending.append(T)
 
-    def submit_thr(self, ptr: int, T: int, on_device: bool, thr: np.ndarray, thr_f: np.ndarray, snr: np.ndarray):
+    def submit_thr(self, ptr: int, T: int, on_device: bool, thr: np.ndarray, thr_f: np.ndarray, snr: np.ndarray,
+                   halo: bool = False):
         """submit() with the per-frame thresholds supplied by the caller instead of the detector's own noise / EMA
         recurrence (mdb_submit_batch_thr): the form a rank of a time-sharded run uses (sharding.py).  The three
-        arrays (int32, float64, float64; T entries) are copied before the call returns."""
+        arrays (int32, float64, float64; T entries) are copied before the call returns.  halo=True marks look-back
+        frames whose results are not wanted (MDB_SUBMIT_HALO: window and dynamic-mask history only)."""
         thr = np.ascontiguousarray(thr, np.int32)
         thr_f = np.ascontiguousarray(thr_f, np.float64)
         snr = np.ascontiguousarray(snr, np.float64)
         if not (len(thr) == len(thr_f) == len(snr) == T):
             raise ValueError("threshold arrays must have T entries")
-        check(self._eng.lib.mdb_submit_batch_thr(self._eng.handle, ptr, T, int(on_device), _ptr(thr), _ptr(thr_f),
-                                                 _ptr(snr)), "submit_thr")
+        check(self._eng.lib.mdb_submit_batch_ex(self._eng.handle, ptr, T, int(on_device), _ptr(thr), _ptr(thr_f),
+                                                _ptr(snr), 1 if halo else 0), "submit_thr")
         self._timer += T
         if not hasattr(self, "_pending"):
             self._pending = []

@@ -112,36 +112,51 @@ class CudaEngine:
         self.roi_pixels = (self.roi[2] - self.roi[0]) * (self.roi[3] - self.roi[1])
 
     def noise_sums(self, frames: np.ndarray, t0: int) -> np.ndarray:
-        """(T,2) uint64 integer sums for the frames' sample timers (mdb_noise_sums)."""
+        """(T,2) uint64 integer sums for the frames' sample timers (mdb_noise_sums), uploaded in pieces of at most
+        max_batch frames plus the n-1 frames of look-back a sample window needs."""
         frames = np.ascontiguousarray(frames, np.uint8)
         T, H, W = frames.shape
         sums = np.zeros((T, 2), np.uint64)
         roi = (C.c_int32 * 4)(*self.roi)
-        self._lib.check(self.lib.mdb_noise_sums(frames.ctypes.data, T, 0, t0, W, H, self.n,
-                                                int(self.cfg.binary.interval), roi,
-                                                self.mask.ctypes.data if self.apply_mask else None,
-                                                sums.ctypes.data, self.device), "mdb_noise_sums")
+        step = max(self.max_batch, 1)
+        for a in range(0, T, step):
+            b = min(T, a + step)
+            lo = max(0, a - (self.n - 1))
+            piece = frames[lo:b]
+            part = np.zeros((b - lo, 2), np.uint64)
+            self._lib.check(self.lib.mdb_noise_sums(piece.ctypes.data, b - lo, 0, t0 + lo, W, H, self.n,
+                                                    int(self.cfg.binary.interval), roi,
+                                                    self.mask.ctypes.data if self.apply_mask else None,
+                                                    part.ctypes.data, self.device), "mdb_noise_sums")
+            sums[a:b] = part[a - lo:]
         return sums
 
-    def detect_chunk(self, frames: np.ndarray, t0: int, thr, thr_f, snr, want_dst: bool = False):
-        """Run frames (global index of frames[0] = t0) with the given per-frame thresholds.
-        Returns per-frame (lines, cls_pred) and, optionally, the masks."""
+    def _detector(self):
         from .detector import M3Detector
-        det = M3Detector(self.n / self.fps + 1e-9, self.fps, self.mask, 10, self.cfg, None, device=self.device,
-                         max_batch=self.max_batch, apply_mask=self.apply_mask)
+        if getattr(self, "_det", None) is None:
+            self._det = M3Detector(self.n / self.fps + 1e-9, self.fps, self.mask, 10, self.cfg, None, device=self.device,
+                                   max_batch=self.max_batch, apply_mask=self.apply_mask)
+        return self._det
+
+    def close(self):
+        if getattr(self, "_det", None) is not None:
+            self._det.close()
+            self._det = None
+
+    def detect_chunk(self, frames: np.ndarray, t0: int, thr, thr_f, snr, want_dst: bool = False, num_cls: int = 10):
+        """Run host frames (global index of frames[0] = t0) with the given per-frame thresholds on one detector that
+        is reset and re-seeked per call, batch by batch.  Returns per-frame (lines, cls_pred) and, optionally, the masks."""
+        det = self._detector()
+        det.num_cls = num_cls
         eng = det._eng
-        self._lib.check(self.lib.mdb_seek(eng.handle, t0), "mdb_seek")
+        det.reset()
+        det.seek(t0)
         frames = np.ascontiguousarray(frames, np.uint8)
         res, dsts = [], []
-        thr = np.ascontiguousarray(thr, np.int32)
-        thr_f = np.ascontiguousarray(thr_f, np.float64)
-        snr = np.ascontiguousarray(snr, np.float64)
         for s in range(0, len(frames), self.max_batch):
             T = min(self.max_batch, len(frames) - s)
-            self._lib.check(self.lib.mdb_submit_batch_thr(eng.handle, frames[s:s + T].ctypes.data, T, 0,
-                                                          thr[s:s + T].ctypes.data, thr_f[s:s + T].ctypes.data,
-                                                          snr[s:s + T].ctypes.data), "mdb_submit_batch_thr")
-            det._pending = [T]
+            det.submit_thr(frames[s:s + T].ctypes.data, T, False, thr[s:s + T], thr_f[s:s + T], snr[s:s + T])
+            det._pending.pop()
             dst = np.empty((T,) + frames.shape[1:], np.uint8) if want_dst else None
             self._lib.check(self.lib.mdb_collect_batch(eng.handle, C.byref(eng.infos), eng.lines.ctypes.data,
                                                        eng.prob.ctypes.data, eng.raw.ctypes.data,
@@ -149,7 +164,6 @@ class CudaEngine:
             res += [det._unpack(i) for i in range(T)]
             if want_dst:
                 dsts.append(dst)
-        det.close()
         return res, (np.concatenate(dsts) if want_dst else None)
 
 
@@ -258,39 +272,54 @@ class Segment:
     history: int = 0
 
 
+def sample_timers(lo: int, hi: int, n: int, interval: int) -> np.ndarray:
+    """The noise-sample timers tau with lo < tau <= hi (SNR_SW.update's schedule, Detector.py:82-91), ascending."""
+    parts = [np.arange(max(lo + 1, 2), min(hi, n) + 1, dtype=np.int64)]
+    si = interval * n
+    if si > 0:
+        first = max(lo + 1, n + 1)
+        parts.append(np.arange(-(-first // si) * si, hi + 1, si, dtype=np.int64))
+    return np.concatenate(parts)
+
+
 def chunk_noise_samples(det, segments: Sequence[Segment], n: int, interval: int, start: int, end: int, frame_bytes: int):
-    """(timer, sum d, sum d^2) of the noise samples with timers in (start, end], from device frames: one
-    mdb_noise_sums_dev call for all segments, on the detector's own stream and buffers."""
+    """(timer, sum d, sum d^2) rows (int64 array, ascending timers) of the noise samples with timers in (start, end],
+    from device frames: one mdb_noise_sums_dev call for all segments, on the detector's own stream and buffers."""
+    taus_all = sample_timers(start, end, n, interval)
     calls, wanted = [], []
     for sg in segments:
         lo, hi = max(sg.t0, start), min(sg.t0 + sg.T, end)
-        taus = [tau for tau in range(lo + 1, hi + 1) if is_noise_sample(tau, n, interval)]
-        if not taus:
+        if hi <= lo:
+            continue
+        taus = taus_all[np.searchsorted(taus_all, lo, side="right"):np.searchsorted(taus_all, hi, side="right")]
+        if len(taus) == 0:
             continue
         back = min(sg.history, n - 1) if sg.t0 > 0 else 0
         first = sg.t0 - back
-        for tau in taus:
-            if first > 0 and tau - n < first:
-                raise ValueError(f"noise sample {tau}: its window starts before the frames of the segment")
+        if first > 0 and int(taus[0]) - n < first:
+            raise ValueError(f"noise sample {int(taus[0])}: its window starts before the frames of the segment")
         calls.append((sg.ptr - back * frame_bytes, sg.T + back, first))
         wanted.append((first, taus))
-    out = []
+    out = [np.zeros((0, 3), np.int64)]
     for (first, taus), sums in zip(wanted, det.noise_sums_device(calls)):
-        for tau in taus:
-            i = tau - 1 - first
-            out.append((tau, int(sums[i, 0]), int(sums[i, 1])))
-    return out
+        rows = np.empty((len(taus), 3), np.int64)
+        rows[:, 0] = taus
+        rows[:, 1:] = sums[taus - 1 - first].astype(np.int64)
+        out.append(rows)
+    return np.concatenate(out)
 
 
 def replay_thresholds_native(samples: Sequence[tuple], roi_pixels: int, n: int, t_begin: int, t_end: int, *, adaptive: bool,
                              init_value: int, sensitivity: str, interval: int):
-    """replay_thresholds in the library's host code (mdb_replay_thresholds): (timer, s1, s2) triples sorted by timer ->
+    """replay_thresholds in the library's host code (mdb_replay_thresholds): (timer, s1, s2) rows (any order) ->
     (thr int32, thr_float f64, snr f64) for frames t_begin .. t_end-1.  Same arithmetic as the device recurrence."""
     from . import _lib
     lib = _lib.load()
-    smp = sorted(samples)
-    timers = np.array([s[0] for s in smp], np.int64)
-    sums = np.array([[s[1], s[2]] for s in smp], np.uint64).reshape(-1, 2)
+    smp = np.asarray(samples, np.int64).reshape(-1, 3)
+    if len(smp) > 1 and np.any(np.diff(smp[:, 0]) < 0):
+        smp = smp[np.argsort(smp[:, 0], kind="stable")]
+    timers = np.ascontiguousarray(smp[:, 0])
+    sums = np.ascontiguousarray(smp[:, 1:]).astype(np.uint64)
     m = t_end - t_begin
     thr, thr_f, snr = np.empty(m, np.int32), np.empty(m, np.float64), np.empty(m, np.float64)
     _lib.check(lib.mdb_replay_thresholds(len(smp), timers.ctypes.data, sums.ctypes.data, int(roi_pixels), int(n),
@@ -300,17 +329,28 @@ def replay_thresholds_native(samples: Sequence[tuple], roi_pixels: int, n: int, 
     return thr, thr_f, snr
 
 
+def ragged_index(counts: np.ndarray):
+    """(row, column) index arrays that enumerate the first counts[i] entries of every row i, row-major: gathers the
+    used part of a padded [T][cap] result array without touching the padding."""
+    counts = np.asarray(counts, np.int64)
+    total = int(counts.sum())
+    rows = np.repeat(np.arange(len(counts)), counts)
+    starts = np.cumsum(counts) - counts
+    cols = np.arange(total) - np.repeat(starts, counts)
+    return rows, cols
+
+
 def pack_line_records(det, T: int, first_frame: int, out: np.ndarray) -> int:
     """Line records (frame, x1, y1, x2, y2, nonline_prob) of the batch collected last into out[:k] (float64 rows),
     without a per-frame Python loop.  Returns k (clipped to len(out))."""
     eng = det._eng
     nl = det.last_infos["n_lines"][:T]
-    k = min(int(nl.sum()), len(out))
+    rows, cols = ragged_index(nl)
+    k = min(len(rows), len(out))
     if k:
-        sel = np.arange(eng.lines.shape[1])[None, :] < nl[:, None]
-        out[:k, 0] = (first_frame + np.repeat(np.arange(T), nl))[:k]
-        out[:k, 1:5] = eng.lines[:T][sel][:k]
-        out[:k, 5] = eng.prob[:T][sel][:k]
+        out[:k, 0] = first_frame + rows[:k]
+        out[:k, 1:5] = eng.lines[rows[:k], cols[:k]]
+        out[:k, 5] = eng.prob[rows[:k], cols[:k]]
     return k
 
 
@@ -326,8 +366,8 @@ def batch_digest(det, T: int) -> bytes:
     h.update(np.ascontiguousarray(info["lines_num"]).tobytes())
     nraw = info["n_raw"]
     if nraw.any():
-        sel = np.arange(eng.raw.shape[1])[None, :] < nraw[:, None]
-        h.update(np.ascontiguousarray(eng.raw[:T][sel]).tobytes())
+        rows, cols = ragged_index(nraw)
+        h.update(np.ascontiguousarray(eng.raw[rows, cols]).tobytes())
     return h.digest()
 
 
@@ -347,7 +387,7 @@ def run_chunk(det, segments: Sequence[Segment], shard: Shard, thr, thr_f, snr, *
 
     def submit(sg):
         a, b = sg.t0 - thr_base, sg.t0 - thr_base + sg.T
-        det.submit_thr(sg.ptr, sg.T, True, thr[a:b], thr_f[a:b], snr[a:b])
+        det.submit_thr(sg.ptr, sg.T, True, thr[a:b], thr_f[a:b], snr[a:b], halo=sg.t0 + sg.T <= shard.start)
 
     for k in range(min(in_flight - 1, len(segs))):
         submit(segs[nxt])

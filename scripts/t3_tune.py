@@ -41,6 +41,11 @@ if only:
     sys.exit(0)
 run("temporal2 (round 1)", {"temporal_version": 2})
 run("temporal3 default", {"temporal_version": 3, "t3_variant": 0})
+if n == 60:
+    for v, name in [(1, "U30 P2 BL10 K10 minb3"), (2, "U30 P2 BL10 K15 minb3"), (3, "U30 P2 BL15 K15 minb3"),
+                    (4, "U30 P2 BL15 K10 minb3"), (5, "U20 P3 BL10 K10 minb3"), (6, "U15 P4 BL15 K15 minb2"),
+                    (7, "U20 P3 BL20 K10 minb2"), (8, "U30 P2 BL10 K6 minb3")]:
+        run(f"temporal3 variant {v}: {name}", {"temporal_version": 3, "t3_variant": v})
 if n == 30:
     for v, name in [(1, "BL15 K5 minb4"), (2, "BL10 K6 minb3"), (3, "BL10 K5 minb4"), (4, "BL15 K6 minb3"),
                     (5, "BL10 K10 minb3"), (6, "BL6 K6 minb4"), (7, "bulk BL10 K5 minb4"), (8, "bulk BL10 K5 minb3"),

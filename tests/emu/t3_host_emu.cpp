@@ -105,6 +105,9 @@ int main() {
     bad += run_shape<25, 5, 1, 5>();
     bad += run_shape<12, 4, 2, 4>();
     bad += run_shape<2, 2, 1, 2>();
+    bad += run_shape<15, 15, 4, 15>();
+    bad += run_shape<20, 10, 3, 10>();
+    bad += run_shape<6, 3, 4, 3>();
     bad += run_shape<30, 10, 1, 5, 1>();
     bad += run_shape<30, 10, 2, 5, 1>();
     bad += run_shape<24, 12, 1, 6, 1>();

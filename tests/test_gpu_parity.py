@@ -436,9 +436,8 @@ def test_device_chunk_pipeline_equals_reference_golden(name, world, batch):
     def pieces(lo, hi):
         return [S.Segment(base + t * fb, min(batch, hi - t), t, history=t) for t in range(lo, hi, batch)]
 
-    samples = []
-    for sh in shards:
-        samples += S.chunk_noise_samples(det, pieces(sh.start, sh.end), n, c["interval"], sh.start, sh.end, fb)
+    samples = np.concatenate([S.chunk_noise_samples(det, pieces(sh.start, sh.end), n, c["interval"], sh.start, sh.end, fb)
+                              for sh in shards])
     roi = det.stack.std_roi
     roi_px = (roi[2] - roi[0]) * (roi[3] - roi[1])
     thr, thr_f, snr = S.replay_thresholds_native(samples, roi_px, n, 0, T, adaptive=c["adaptive"], init_value=c["init_value"],
