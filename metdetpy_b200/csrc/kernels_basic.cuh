@@ -100,7 +100,7 @@ noise_sample16_kernel(FrameSrc src, int W, int n, long long timer0, long long st
             keep[0] &= m.x * 0xffu; keep[1] &= m.y * 0xffu; keep[2] &= m.z * 0xffu; keep[3] &= m.w * 0xffu;
         }
         unsigned se[4] = {0, 0, 0, 0}, so[4] = {0, 0, 0, 0}, sq = 0;
-#pragma unroll 5
+#pragma unroll 10
         for (int k = 0; k < L; k++) {
             const uint4 v4 = __ldg(reinterpret_cast<const uint4 *>(fp[k] + p));
             const unsigned v[4] = {v4.x & keep[0], v4.y & keep[1], v4.z & keep[2], v4.w & keep[3]};

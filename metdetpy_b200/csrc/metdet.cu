@@ -838,14 +838,15 @@ extern "C" int mdb_noise_sums_dev(mdb_handle h, int nseg, const uint8_t *const *
         total += (size_t)T[k];
     }
     CK(cudaSetDevice(h->cfg.device));
-    if (h->noise2_cap < total) {
+    if (h->noise2_cap < total) {  // grown generously: reallocating costs milliseconds (pinned memory, implicit syncs)
         if (h->d_noise2) CK(cudaFree(h->d_noise2));
         if (h->h_noise2) CK(cudaFreeHost(h->h_noise2));
         h->d_noise2 = h->h_noise2 = nullptr;
         h->noise2_cap = 0;
-        CK(cudaMalloc((void **)&h->d_noise2, total * 16));
-        CK(cudaHostAlloc((void **)&h->h_noise2, total * 16, cudaHostAllocDefault));
-        h->noise2_cap = total;
+        const size_t cap = std::max<size_t>(2 * total, (size_t)1 << 20);
+        CK(cudaMalloc((void **)&h->d_noise2, cap * 16));
+        CK(cudaHostAlloc((void **)&h->h_noise2, cap * 16, cudaHostAllocDefault));
+        h->noise2_cap = cap;
     }
     const mdb_config &c = h->cfg;
     const long long std_interval = (long long)c.nz_interval * h->n;
