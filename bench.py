@@ -755,10 +755,10 @@ def measure_dense(a, stream, dev):
     import torch
     from metdetpy_b200.detector import M3Detector
     W, H, n = a.width, a.height, a.window
-    T = 64
+    T = 128
     mask = np.ones((H, W), np.uint8)
     out = None
-    for thr in (6, 5):
+    for thr in (5,):
         det = M3Detector(n / a.fps + 1e-9, a.fps, mask, 10, make_cfg(dy=True, adaptive=False, init_value=thr), None,
                          device=dev.index or 0, max_batch=T)
         det.detect_many((stream.ptr(0), T), on_device=True)          # fills the window

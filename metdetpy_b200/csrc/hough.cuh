@@ -701,58 +701,113 @@ hough_tier2_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
 }
 
 // ------------------------------------------------------------------------------------------
-// Tier 3 (overflow path): dense masks beyond the shared-memory capacity.  One CTA walks the flagged
-// frames of the batch: ordered compaction of the frame's dst mask into a global point list (row-major
-// == sorted), visiting order and pixel bitmap in global memory, sequential walks.  Slow, rare, and
-// entirely on the device (no host round trip, so batches can stay pipelined).
+// Tier 3: dense masks beyond the point capacity of tier 2 (sensor noise above the threshold, clouds, dawn: tens of
+// thousands of on-pixels).  Same exact-order algorithm with tier 2's parallel machinery -- votes of four points per
+// barrier with the cell reads in flight together, 256-step ballot walks, fire-and-forget un-votes -- but nothing
+// frame-sized lives in shared memory: the row-major point list and the visiting order are in global memory and are
+// staged 256 visits at a time, "is this pixel still on" is a per-slot pixel bitmap in global memory (L2).  One CTA per
+// scratch slot; the CTAs claim the dense frames of the batch from a queue, so up to `slots3` frames are worked on side
+// by side.  Entirely on the device (no host round trip: batches stay pipelined).
 // ------------------------------------------------------------------------------------------
-__device__ int compact_ordered(const uint8_t *dst, int W, int H, uint32_t *keys) {
-    __shared__ unsigned c_wsum[HOUGH_THREADS / 32];
-    __shared__ unsigned c_base;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) c_base = 0;
-    __syncthreads();
-    const size_t HW = (size_t)W * H;
-    for (size_t start = 0; start < HW; start += HOUGH_THREADS * 8) {
-        const size_t p0 = start + (size_t)tid * 8;
-        unsigned bits = 0;
-        for (int k = 0; k < 8; k++)
-            if (p0 + k < HW && dst[p0 + k]) bits |= 1u << k;
-        const unsigned c = __popc(bits);
-        unsigned inc = c;
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        if (lane == 31) c_wsum[w] = inc;
-        __syncthreads();
-        unsigned woff = 0, tot = 0;
-        for (int k = 0; k < HOUGH_THREADS / 32; k++) {
-            if (k < w) woff += c_wsum[k];
-            tot += c_wsum[k];
-        }
-        unsigned off = c_base + woff + inc - c;
-        for (int k = 0; k < 8; k++)
-            if (bits >> k & 1) {
-                const size_t p = p0 + k;
-                keys[off++] = ((unsigned)(p / W) << 16) | (unsigned)(p % W);
+#define H3_STAGE 256          // visits staged per round (= HOUGH_THREADS)
+#define H3_ORDER_CAP 98304    // most points whose visiting order is shuffled in shared memory (u16 + one high bit each)
+#define H3_ORDER_SMEM (H3_ORDER_CAP * 2 + H3_ORDER_CAP / 8)
+
+// Row-major list of the on-pixels of one mask: per-row counts, a scan over the rows, then every warp writes its rows in
+// order.  row_off: global scratch of at least H + 1 words.  Returns the number of points.
+__device__ int compact_rows(const uint8_t *dst, int W, int H, uint32_t *keys, uint32_t *row_off) {
+    __shared__ unsigned c_part[HOUGH_THREADS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool vec = (W & 15) == 0 && ((uintptr_t)dst & 15) == 0;
+    // pass 1: on-pixels per row
+    for (int y = warp; y < H; y += HOUGH_THREADS / 32) {
+        const uint8_t *row = dst + (size_t)y * W;
+        unsigned c = 0;
+        if (vec) {
+            for (int x = lane * 16; x < W; x += 512) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(row + x);
+                // mask bytes are 0 or 255: the top bit of every byte
+                c += __popc(v.x & 0x80808080u) + __popc(v.y & 0x80808080u) + __popc(v.z & 0x80808080u) + __popc(v.w & 0x80808080u);
             }
-        __syncthreads();
-        if (tid == 0) c_base += tot;
-        __syncthreads();
+        } else {
+            for (int x = lane; x < W; x += 32) c += row[x] != 0;
+        }
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) row_off[y] = c;
     }
-    return (int)c_base;
+    __syncthreads();
+    // exclusive scan over the rows: every thread owns a contiguous range of rows
+    const int per = (H + HOUGH_THREADS - 1) / HOUGH_THREADS;
+    const int y0 = min(tid * per, H), y1 = min(y0 + per, H);
+    unsigned sum = 0;
+    for (int y = y0; y < y1; y++) sum += row_off[y];
+    c_part[tid] = sum;
+    __syncthreads();
+    unsigned base = 0, total = 0;
+    for (int k = 0; k < HOUGH_THREADS; k++) {
+        if (k < tid) base += c_part[k];
+        total += c_part[k];
+    }
+    for (int y = y0; y < y1; y++) {
+        const unsigned c = row_off[y];
+        row_off[y] = base;
+        base += c;
+    }
+    __syncthreads();
+    // pass 2: write the keys of every row in x order
+    for (int y = warp; y < H; y += HOUGH_THREADS / 32) {
+        const uint8_t *row = dst + (size_t)y * W;
+        unsigned off = row_off[y];
+        const int step = vec ? 512 : 32;
+        for (int xb = 0; xb < W; xb += step) {
+            unsigned bits = 0;  // this lane's on-pixels of the chunk (16 consecutive pixels, or one)
+            if (vec) {
+                const int x = xb + lane * 16;
+                if (x < W) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(row + x);
+                    const unsigned w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+#pragma unroll
+                        for (int b = 0; b < 4; b++)
+                            if (w4[q] >> (8 * b + 7) & 1u) bits |= 1u << (4 * q + b);
+                }
+            } else {
+                const int x = xb + lane;
+                if (x < W && row[x]) bits = 1u;
+            }
+            const unsigned c = __popc(bits);
+            unsigned inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            unsigned w = off + inc - c;
+            const int x0 = vec ? xb + lane * 16 : xb + lane;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                keys[w++] = ((unsigned)y << 16) | (unsigned)(x0 + b);
+            }
+            off += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    __syncthreads();
+    return (int)total;
 }
 
 __global__ void __launch_bounds__(HOUGH_THREADS)
 hough_tier3_kernel(HoughParams P, int T, const uint8_t *dst, uint32_t *keys, uint32_t *idx, int32_t *accum,
-                   uint32_t *bitmap, uint32_t *walk, int32_t *lines_all, int *nlines_all, unsigned *queue) {
-    // one CTA per scratch slot (point list, visiting order, accumulator, pixel bitmap, walk buffer); the CTAs
-    // claim frame indices from a queue, so the dense frames of a batch are worked on side by side
-    __shared__ int s_red[HOUGH_THREADS / 32];
+                   uint32_t *bitmap, uint32_t *walk, int32_t *lines_all, int *nlines_all, unsigned *queue, long long *prof) {
+    extern __shared__ uint32_t h_sm[];  // order shuffle: u16 [H3_ORDER_CAP] + high bits
+    __shared__ int s_red[2][HOUGH_THREADS / 32][HOUGH_SPEC];
+    __shared__ unsigned s_on[HOUGH_THREADS / 32], s_inb[HOUGH_THREADS / 32];
     __shared__ int s_ctl[8];
-    __shared__ int s_next;
-    const int tid = threadIdx.x;
+    __shared__ int s_next, s_any;
+    __shared__ uint32_t st_key[H3_STAGE];
+    __shared__ unsigned st_alive[H3_STAGE / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = P.W, H = P.H, numrho = P.numrho, half = (numrho - 1) / 2;
     {
         const size_t HWs = (size_t)W * H;
@@ -763,8 +818,7 @@ hough_tier3_kernel(HoughParams P, int T, const uint8_t *dst, uint32_t *keys, uin
         walk += (size_t)blockIdx.x * P.walk_cap;
     }
     const float my_c = c_trig[2 * (tid < MDB_HOUGH_ANGLES ? tid : 0)], my_s = c_trig[2 * (tid < MDB_HOUGH_ANGLES ? tid : 0) + 1];
-    volatile uint32_t *vbitmap = bitmap;
-    __shared__ int s_any;
+    int32_t *myrow = accum + (size_t)(tid < MDB_HOUGH_ANGLES ? tid : 0) * numrho + half;
     if (tid == 0) s_any = 0;
     __syncthreads();
     for (int t = tid; t < T; t += HOUGH_THREADS)
@@ -772,119 +826,372 @@ hough_tier3_kernel(HoughParams P, int T, const uint8_t *dst, uint32_t *keys, uin
     __syncthreads();
     if (!s_any) return;  // the usual case: no dense frame in this batch
     for (;;) {
-    __syncthreads();
-    if (tid == 0) s_next = (int)atomicAdd(queue, 1u);
-    __syncthreads();
-    const int t = s_next;
-    if (t >= T) break;
-    if (nlines_all[t] != -1) continue;  // (only the CTA that claimed t ever writes nlines_all[t])
-    int32_t *lines_out = lines_all + (size_t)t * P.max_lines * 4;
-    const int N = compact_ordered(dst + (size_t)t * W * H, W, H, keys);
-    if (N == 0) { if (tid == 0) nlines_all[t] = 0; continue; }
-    const int line_gap = line_gap_of(P, (unsigned)N);
-    for (int i = tid; i < N; i += HOUGH_THREADS) {
-        idx[i] = i;
-        const uint32_t k = keys[i];
-        const size_t p = (size_t)(k >> 16) * W + (k & 0xffffu);
-        atomicOr(&bitmap[p >> 5], 1u << (p & 31));
-    }
-    if (tid == 0) s_ctl[2] = 0;
-    __syncthreads();
-    if (tid == 0) {
-        unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
-        for (int count = N; count > 0; count--) {
-            state = (unsigned long long)(unsigned)state * 4164903690ull + (unsigned)(state >> 32);
-            const unsigned r = (unsigned)state % (unsigned)count;
-            const uint32_t a = idx[r], b = idx[count - 1];
-            idx[r] = b;
-            idx[count - 1] = a;
-        }
-    }
-    __syncthreads();
-    int32_t *myrow = accum + (size_t)(tid < MDB_HOUGH_ANGLES ? tid : 0) * numrho + half;
-    for (int s = N - 1; s >= 0; s--) {
-        const uint32_t key = keys[idx[s]];
-        const int x = key & 0xffffu, y = key >> 16;
-        const size_t p = (size_t)y * W + x;
-        if (!((vbitmap[p >> 5] >> (p & 31)) & 1u)) continue;
-        int best = INT_MIN;
-        if (tid < MDB_HOUGH_ANGLES) {
-            const int r = rho_cs(x, y, my_c, my_s);
-            const int v = myrow[r] + 1;
-            myrow[r] = v;
-            best = v * 256 + (255 - tid);
-        }
-        best = __reduce_max_sync(0xffffffffu, best);
-        if ((tid & 31) == 0) s_red[tid >> 5] = best;
         __syncthreads();
-        best = s_red[0];
-#pragma unroll
-        for (int k = 1; k < HOUGH_THREADS / 32; k++) best = max(best, s_red[k]);
-        if ((best >> 8) < P.threshold) { __syncthreads(); continue; }
-        const int max_n = 255 - (best & 255);
-        if (tid == 0) {
-            Walk wk;
-            wk.init(x, y, max_n);
-            int ends[2] = {0, 0};
-            for (int k = 0; k < 2; k++) {
-                int gap = 0;
-                for (int i = 0;; i++) {
-                    int j1, i1;
-                    wk.at(k, i, j1, i1);
-                    if (j1 < 0 || j1 >= W || i1 < 0 || i1 >= H) break;
-                    const size_t q = (size_t)i1 * W + j1;
-                    if ((vbitmap[q >> 5] >> (q & 31)) & 1u) { gap = 0; ends[k] = i; }
-                    else if (++gap > line_gap) break;
-                }
+        if (tid == 0) s_next = (int)atomicAdd(queue, 1u);
+        __syncthreads();
+        const int t = s_next;
+        if (t >= T) break;
+        if (nlines_all[t] != -1) continue;  // (only the CTA that claimed t ever writes nlines_all[t])
+        int32_t *lines = lines_all + (size_t)t * P.max_lines * 4;
+        const long long pc0 = clock64();
+        long long p_setup = 0, p_vote = 0, p_walk = 0, p_unvote = 0, p_stage = 0, n_vote = 0, n_line = 0, n_iso = 0;
+        const int N = compact_rows(dst + (size_t)t * W * H, W, H, keys, walk);
+        if (N == 0) { if (tid == 0) nlines_all[t] = 0; continue; }
+        const int line_gap = line_gap_of(P, (unsigned)N);
+        for (int i = tid; i < N; i += HOUGH_THREADS) {
+            const uint32_t k = keys[i];
+            const size_t p = (size_t)(k >> 16) * W + (k & 0xffffu);
+            atomicOr(&bitmap[p >> 5], 1u << (p & 31));
+        }
+        // ---- visiting order: Fisher-Yates with OpenCV's RNG; idx[N-1], idx[N-2], ... is the visit sequence ----------
+        if (N <= H3_ORDER_CAP) {
+            uint16_t *lo = reinterpret_cast<uint16_t *>(h_sm);
+            uint32_t *hi = h_sm + H3_ORDER_CAP / 2;  // bit i = bit 16 of entry i
+            for (int i = tid; i < N; i += HOUGH_THREADS) lo[i] = (uint16_t)i;
+            for (int i = tid; i < (N + 31) / 32; i += HOUGH_THREADS) {
+                // entries 65536 .. N-1 start with their high bit set
+                unsigned m = 0;
+                if (i * 32 >= 65536) m = 0xffffffffu;
+                hi[i] = m;
             }
-            int ex0, ey0, ex1, ey1;
-            wk.at(0, ends[0], ex0, ey0);
-            wk.at(1, ends[1], ex1, ey1);
-            const int good = abs(ex1 - ex0) >= P.min_len || abs(ey1 - ey0) >= P.min_len;
-            int nw = 0;
-            for (int k = 0; k < 2; k++)
-                for (int i = 0; i <= ends[k]; i++) {
-                    int j1, i1;
-                    wk.at(k, i, j1, i1);
-                    const size_t q = (size_t)i1 * W + j1;
-                    const uint32_t wv = vbitmap[q >> 5];
-                    if ((wv >> (q & 31)) & 1u) {
-                        if (good && nw < P.walk_cap) walk[nw++] = ((unsigned)i1 << 16) | (unsigned)j1;
-                        vbitmap[q >> 5] = wv & ~(1u << (q & 31));
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
+                for (int count = N; count > 0; count--) {
+                    state = (unsigned long long)(unsigned)state * 4164903690ull + (unsigned)(state >> 32);
+                    const unsigned r = (unsigned)state % (unsigned)count, c = (unsigned)count - 1;
+                    const uint16_t a = lo[r], b = lo[c];
+                    lo[r] = b; lo[c] = a;
+                    if (N > 65536) {
+                        const unsigned ha = (hi[r >> 5] >> (r & 31)) & 1u, hb = (hi[c >> 5] >> (c & 31)) & 1u;
+                        if (ha != hb) { hi[r >> 5] ^= 1u << (r & 31); hi[c >> 5] ^= 1u << (c & 31); }
                     }
                 }
-            if (good) {
-                const int li = s_ctl[2];
-                if (li < P.max_lines) {
-                    lines_out[4 * li] = ex0; lines_out[4 * li + 1] = ey0;
-                    lines_out[4 * li + 2] = ex1; lines_out[4 * li + 3] = ey1;
+            }
+            __syncthreads();
+            for (int i = tid; i < N; i += HOUGH_THREADS) idx[i] = (uint32_t)lo[i] | (((hi[i >> 5] >> (i & 31)) & 1u) << 16);
+        } else {
+            for (int i = tid; i < N; i += HOUGH_THREADS) idx[i] = i;
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long state = 0xFFFFFFFFFFFFFFFFull;
+                for (int count = N; count > 0; count--) {
+                    state = (unsigned long long)(unsigned)state * 4164903690ull + (unsigned)(state >> 32);
+                    const unsigned r = (unsigned)state % (unsigned)count;
+                    const uint32_t a = idx[r], b = idx[count - 1];
+                    idx[r] = b;
+                    idx[count - 1] = a;
                 }
-                s_ctl[2] = li + 1;
-            }
-            s_ctl[0] = good;
-            s_ctl[1] = nw;
-            __threadfence_block();
-        }
-        __syncthreads();
-        if (s_ctl[0] && tid < MDB_HOUGH_ANGLES) {
-            const int nw = s_ctl[1];
-            volatile uint32_t *vwalk = walk;
-            for (int k = 0; k < nw; k++) {
-                const uint32_t wk2 = vwalk[k];
-                myrow[rho_cs(wk2 & 0xffffu, wk2 >> 16, my_c, my_s)]--;
             }
         }
+        if (tid == 0) s_ctl[2] = 0;
         __syncthreads();
-    }
-    // dense frame: its points project onto (nearly) the whole accumulator -- clear the slot with coalesced stores
-    for (size_t q = tid; q < (size_t)MDB_HOUGH_ANGLES * numrho; q += HOUGH_THREADS) accum[q] = 0;
-    for (int i = tid; i < N; i += HOUGH_THREADS) {
-        const uint32_t k = keys[i];
-        const size_t p = (size_t)(k >> 16) * W + (k & 0xffffu);
-        bitmap[p >> 5] = 0;
-    }
-    __syncthreads();
-    if (tid == 0) nlines_all[t] = s_ctl[2];
-    __syncthreads();
+        __threadfence_block();
+
+        int par = 0;
+        bool hot = false;  // the last point looked at yielded a line
+        p_setup = clock64() - pc0;
+        // ---- visits, H3_STAGE at a time -----------------------------------------------------------------------
+        for (int top = N - 1; top >= 0; top -= H3_STAGE) {
+            const int cnt_stage = min(H3_STAGE, top + 1);
+            long long c0 = clock64();
+            // stage: keys of visits top, top-1, ... and whether their pixels are still on
+            auto refresh = [&](int from) {  // alive bits of staged positions >= from (others cleared)
+                bool on = false;
+                if (tid >= from && tid < cnt_stage) {
+                    const uint32_t k = st_key[tid];
+                    const size_t p = (size_t)(k >> 16) * W + (k & 0xffffu);
+                    on = (__ldcg(&bitmap[p >> 5]) >> (p & 31)) & 1u;
+                }
+                const unsigned b = __ballot_sync(0xffffffffu, on);
+                if (lane == 0) st_alive[warp] = b;
+            };
+            if (tid < cnt_stage) st_key[tid] = keys[idx[top - tid]];
+            __syncthreads();
+            refresh(0);
+            // warm the cells of the staged points (L2)
+            if (tid < MDB_HOUGH_ANGLES)
+                for (int j = 0; j < cnt_stage; j++) {
+                    const uint32_t k = st_key[j];
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(myrow + rho_cs(k & 0xffffu, k >> 16, my_c, my_s)));
+                }
+            __syncthreads();
+            int j0 = 0;  // next staged position to look at
+            p_stage += clock64() - c0;
+            for (;;) {
+                c0 = clock64();
+                // the next (up to HOUGH_SPEC) staged points whose pixels are still on: uniform scan of the alive bits.
+                // Right after a point that yielded a line only one is taken: in saturated accumulators (dense noise)
+                // nearly every point yields one, and votes taken ahead would only have to be taken back.
+                const int spec = hot ? 1 : HOUGH_SPEC;
+                hot = false;
+                int cs[HOUGH_SPEC], cnt = 0;
+                uint32_t ck[HOUGH_SPEC];
+#pragma unroll
+                for (int j = 0; j < HOUGH_SPEC; j++) { cs[j] = -1; ck[j] = 0; }
+                while (cnt < spec && j0 < cnt_stage) {
+                    unsigned m = st_alive[j0 >> 5] & (0xffffffffu << (j0 & 31));
+                    const int wbase = j0 & ~31;
+                    while (m && cnt < spec) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+#pragma unroll
+                        for (int j = 0; j < HOUGH_SPEC; j++)
+                            if (j == cnt) cs[j] = wbase + b;
+                        cnt++;
+                        j0 = wbase + b + 1;
+                    }
+                    if (!m && cnt < spec) j0 = max(j0, wbase + 32);
+                }
+                if (cnt == 0) break;
+#pragma unroll
+                for (int j = 0; j < HOUGH_SPEC; j++)
+                    if (j < cnt) ck[j] = st_key[cs[j]];
+                int bj[HOUGH_SPEC], rj[HOUGH_SPEC], vj[HOUGH_SPEC];
+#pragma unroll
+                for (int j = 0; j < HOUGH_SPEC; j++) { bj[j] = INT_MIN; rj[j] = 0; vj[j] = 0; }
+                if (tid < MDB_HOUGH_ANGLES) {
+#pragma unroll
+                    for (int j = 0; j < HOUGH_SPEC; j++)
+                        if (j < cnt) rj[j] = rho_cs(ck[j] & 0xffffu, ck[j] >> 16, my_c, my_s);
+#pragma unroll
+                    for (int j = 0; j < HOUGH_SPEC; j++)
+                        if (j < cnt) vj[j] = __ldcg(myrow + rj[j]);  // L2 only: cells are also updated by REDs
+                    // maxLineGap 0 (every mask this dense): a walk ends at the first off pixel, so a point whose two
+                    // neighbours along the winning angle are off is an isolated pixel.  Thread n looks at the neighbours
+                    // along ITS angle while its cell read is in flight; the flag rides in the low bit of the arg-max key
+                    // and the usual outcome in noise -- isolated -- costs no further round trip.
+                    unsigned nbj = 0xfu;
+                    if (line_gap == 0) {
+                        nbj = 0u;
+#pragma unroll
+                        for (int j = 0; j < HOUGH_SPEC; j++)
+                            if (j < cnt) {
+                                Walk wn;
+                                wn.init(ck[j] & 0xffffu, ck[j] >> 16, tid);
+#pragma unroll
+                                for (int k = 0; k < 2; k++) {
+                                    int j1, i1;
+                                    wn.at(k, 1, j1, i1);
+                                    if (j1 >= 0 && j1 < W && i1 >= 0 && i1 < H) {
+                                        const size_t q = (size_t)i1 * W + j1;
+                                        nbj |= ((__ldcg(&bitmap[q >> 5]) >> (q & 31)) & 1u) << j;
+                                    }
+                                }
+                            }
+                    }
+#pragma unroll
+                    for (int j = 0; j < HOUGH_SPEC; j++)
+                        if (j < cnt) {
+                            int base = vj[j];
+#pragma unroll
+                            for (int i = 0; i < j; i++)
+                                if (rj[i] == rj[j]) base = vj[i];  // the latest earlier vote for the same cell wins
+                            vj[j] = base + 1;
+                            // max value first, lowest angle on ties; bit 0: this angle's walk would find a neighbour
+                            bj[j] = (vj[j] * 256 + (255 - tid)) * 2 + (int)((nbj >> j) & 1u);
+                        }
+#pragma unroll
+                    for (int j = 0; j < HOUGH_SPEC; j++)
+                        if (j < cnt) __stcg(myrow + rj[j], vj[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < HOUGH_SPEC; j++) {
+                    bj[j] = __reduce_max_sync(0xffffffffu, bj[j]);
+                    if (lane == 0) s_red[par][warp][j] = bj[j];
+                }
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < HOUGH_SPEC; j++)
+#pragma unroll
+                    for (int k = 0; k < HOUGH_THREADS / 32; k++) bj[j] = max(bj[j], s_red[par][k][j]);
+                par ^= 1;
+                int trig = -1;
+#pragma unroll
+                for (int j = 0; j < HOUGH_SPEC; j++)
+                    if (trig < 0 && j < cnt && (bj[j] >> 9) >= P.threshold) trig = j;
+                p_vote += clock64() - c0; n_vote += trig < 0 ? cnt : trig + 1;
+                if (trig < 0) continue;
+                c0 = clock64(); n_line++;
+                uint32_t key = 0;
+                int best = 0;
+                bool lonely = false;
+#pragma unroll
+                for (int j = 0; j < HOUGH_SPEC; j++) {
+                    if (j == trig) { key = ck[j]; best = bj[j] >> 1; lonely = !(bj[j] & 1); j0 = cs[j] + 1; }
+                    // take back the votes of the points behind the one that yielded a line
+                    if (j > trig && j < cnt && tid < MDB_HOUGH_ANGLES) __stcg(myrow + rj[j], __ldcg(myrow + rj[j]) - 1);
+                }
+                const int x = key & 0xffffu, y = key >> 16;
+                const int max_n = 255 - (best & 255);
+                if (lonely) {
+                    // an isolated pixel (known from the neighbour flag): only the start pixel leaves the mask
+                    if (tid == 0) {
+                        const size_t q = (size_t)y * W + x;
+                        atomicAnd(&bitmap[q >> 5], ~(1u << (q & 31)));
+                    }
+                    hot = true;
+                    p_walk += clock64() - c0; n_iso++;
+                    continue;  // the next vote round's barrier orders the bitmap update before any later probe
+                }
+                // ---- line: find both ends (mask unchanged meanwhile) -----------------------------------------
+                Walk wk;
+                wk.init(x, y, max_n);
+                int ends[2];
+                bool slow[2];
+                {
+                    // first round: warp k probes steps 1 .. 32 of direction k (dense masks have maxLineGap 0 or close to
+                    // it: nearly every walk ends here, after one barrier)
+                    if (warp < 2) {
+                        int j1, i1;
+                        wk.at(warp, lane + 1, j1, i1);
+                        const bool inb = j1 >= 0 && j1 < W && i1 >= 0 && i1 < H;
+                        bool on = false;
+                        if (inb) {
+                            const size_t q = (size_t)i1 * W + j1;
+                            on = (__ldcg(&bitmap[q >> 5]) >> (q & 31)) & 1u;
+                        }
+                        const unsigned bo = __ballot_sync(0xffffffffu, on), bi = __ballot_sync(0xffffffffu, inb);
+                        if (lane == 0) { s_on[warp] = bo; s_inb[warp] = bi; }
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        unsigned onw = s_on[k];
+                        const unsigned inw = s_inb[k];
+                        int last_on = 0;
+                        bool done = false;
+                        const int ob = inw == 0xffffffffu ? INT_MAX : __ffs(~inw);  // first out-of-bounds step (bit b = step b+1)
+                        while (onw) {
+                            const int io = __ffs(onw);
+                            onw &= onw - 1;
+                            if (io - last_on - 1 > line_gap) { done = true; break; }
+                            last_on = io;
+                        }
+                        if (!done) {
+                            const int wend = min(32, ob == INT_MAX ? INT_MAX : ob - 1);  // last in-bounds step seen
+                            if (ob != INT_MAX || wend - last_on > line_gap) done = true;
+                        }
+                        ends[k] = last_on;
+                        slow[k] = !done;
+                    }
+                    __syncthreads();
+                }
+                for (int k = 0; k < 2; k++) {
+                    if (!slow[k]) continue;  // uniform
+                    int last_on = 0;  // step 0 is the start pixel, which is on
+                    bool done = false;
+                    for (int base = 0; !done; base += HOUGH_THREADS) {
+                        const int i = base + tid;
+                        int j1, i1;
+                        wk.at(k, i, j1, i1);
+                        const bool inb = j1 >= 0 && j1 < W && i1 >= 0 && i1 < H;
+                        bool on = false;
+                        if (inb) {
+                            const size_t q = (size_t)i1 * W + j1;
+                            on = (__ldcg(&bitmap[q >> 5]) >> (q & 31)) & 1u;
+                        }
+                        const unsigned bo = __ballot_sync(0xffffffffu, on), bi = __ballot_sync(0xffffffffu, inb);
+                        if (lane == 0) { s_on[warp] = bo; s_inb[warp] = bi; }
+                        __syncthreads();
+                        for (int w = 0; w < HOUGH_THREADS / 32 && !done; w++) {
+                            unsigned onw = s_on[w];
+                            const unsigned inw = s_inb[w];
+                            const int wbase = base + w * 32;
+                            const int ob = inw == 0xffffffffu ? INT_MAX : wbase + __ffs(~inw) - 1;
+                            while (onw) {
+                                const int io = wbase + __ffs(onw) - 1;
+                                onw &= onw - 1;
+                                if (io - last_on - 1 > line_gap) { done = true; break; }
+                                last_on = io;
+                            }
+                            if (!done) {
+                                const int wend = min(wbase + 31, ob == INT_MAX ? INT_MAX : ob - 1);
+                                if (ob != INT_MAX || wend - last_on > line_gap) done = true;
+                            }
+                        }
+                        __syncthreads();
+                    }
+                    ends[k] = last_on;
+                }
+                if (ends[0] == 0 && ends[1] == 0) {
+                    // an isolated pixel (the usual outcome in noise): only the start pixel leaves the mask, nothing to
+                    // un-vote (a zero-length segment never counts), no other staged point is affected
+                    if (tid == 0) {
+                        const size_t q = (size_t)y * W + x;
+                        atomicAnd(&bitmap[q >> 5], ~(1u << (q & 31)));
+                    }
+                    hot = true;
+                    p_walk += clock64() - c0; n_iso++;
+                    continue;  // the next vote round's barrier orders the bitmap update before any later probe
+                }
+                int ex0, ey0, ex1, ey1;
+                wk.at(0, ends[0], ex0, ey0);
+                wk.at(1, ends[1], ex1, ey1);
+                const bool good = abs(ex1 - ex0) >= P.min_len || abs(ey1 - ey0) >= P.min_len;
+                p_walk += clock64() - c0; c0 = clock64();
+                // ---- second pass: clear the on-pixels up to both ends; un-vote them if the line counts
+                if (tid == 0) s_ctl[1] = 0;
+                __syncthreads();
+                for (int k = 0; k < 2; k++)
+                    for (int i = tid + k; i <= ends[k]; i += HOUGH_THREADS) {  // k=1 skips the shared start pixel
+                        int j1, i1;
+                        wk.at(k, i, j1, i1);
+                        const size_t q = (size_t)i1 * W + j1;
+                        const unsigned bit = 1u << (q & 31);
+                        if (__ldcg(&bitmap[q >> 5]) & bit) {
+                            atomicAnd(&bitmap[q >> 5], ~bit);
+                            if (good) {
+                                const int wi = atomicAdd(&s_ctl[1], 1);
+                                if (wi < P.walk_cap) walk[wi] = ((unsigned)i1 << 16) | (unsigned)j1;
+                            }
+                        }
+                    }
+                __syncthreads();
+                __threadfence_block();
+                if (good) {
+                    const int nw = min(s_ctl[1], P.walk_cap);
+                    if (tid < MDB_HOUGH_ANGLES)
+                        for (int q = 0; q < nw; q++) {
+                            const uint32_t k2 = __ldcg(&walk[q]);
+                            atomicAdd(myrow + rho_cs(k2 & 0xffffu, k2 >> 16, my_c, my_s), -1);  // RED, no return
+                        }
+                    if (tid == 0) {
+                        const int li = s_ctl[2];
+                        if (li < P.max_lines) {
+                            lines[4 * li] = ex0; lines[4 * li + 1] = ey0;
+                            lines[4 * li + 2] = ex1; lines[4 * li + 3] = ey1;
+                        }
+                        s_ctl[2] = li + 1;
+                    }
+                }
+                hot = true;
+                __syncthreads();
+                refresh(j0);  // the line may have removed pixels of points staged behind this one
+                __syncthreads();
+                p_unvote += clock64() - c0;
+            }
+            __syncthreads();
+        }
+        // dense frame: its points project onto (nearly) the whole accumulator -- clear the slot with coalesced stores
+        {
+            int4 *a4 = reinterpret_cast<int4 *>(accum);
+            const size_t cells = (size_t)MDB_HOUGH_ANGLES * numrho, n4 = cells / 4;
+            for (size_t q = tid; q < n4; q += HOUGH_THREADS) __stcg(a4 + q, make_int4(0, 0, 0, 0));
+            for (size_t q = n4 * 4 + tid; q < cells; q += HOUGH_THREADS) accum[q] = 0;
+        }
+        for (int i = tid; i < N; i += HOUGH_THREADS) {
+            const uint32_t k = keys[i];
+            const size_t p = (size_t)(k >> 16) * W + (k & 0xffffu);
+            bitmap[p >> 5] = 0;
+        }
+        __syncthreads();
+        if (tid == 0) nlines_all[t] = s_ctl[2];
+        if (prof && tid == 0) {
+            long long *o = prof + (size_t)t * 10;
+            o[0] = N; o[1] = p_setup; o[2] = p_vote; o[3] = p_walk; o[4] = p_unvote; o[5] = p_stage;
+            o[6] = n_vote; o[7] = n_line; o[8] = clock64() - pc0; o[9] = n_iso;
+        }
+        __syncthreads();
     }
 }

@@ -326,7 +326,8 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     }
     if (cfg->detector == 1) ALLOC(h->d_cbits, (size_t)3 * T * h->H * h->Wb * sizeof(uint32_t));
     ALLOC(h->d_accum, (size_t)h->slots * MDB_HOUGH_ANGLES * hp.numrho * sizeof(int32_t));
-    h->slots3 = std::max(1, std::min(std::min(h->slots, T), 8));
+    // tier-3 scratch slots: point list + visiting order (2 x HW words each), 6 GB at most
+    h->slots3 = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(std::min(h->slots, T), (size_t)h->sm_count), (12ull << 30) / (h->HW * 8)));
     ALLOC(h->d_bitmap, (size_t)h->slots3 * bm_words * sizeof(uint32_t));
     ALLOC(h->d_walk, (size_t)h->slots3 * hp.walk_cap * sizeof(uint32_t));
     CKH(cudaMemsetAsync(h->d_ring, 0, (size_t)h->R * h->HW, h->stream));
@@ -365,6 +366,7 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
                              HOUGH_SMEM_BYTES));
     CKH(cudaFuncSetAttribute(hough_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              HOUGH_SMEM_LARGE + HOUGH_TABLE_BYTES));
+    CKH(cudaFuncSetAttribute(hough_tier3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H3_ORDER_SMEM));
     CKH(cudaStreamSynchronize(h->stream));
     {
         int rc = cfg->detector == 1 ? 0 : stream_state_init(h->sk, h->W, h->H, h->n, cfg->device, cfg->max_batch);
@@ -521,9 +523,9 @@ static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
             cudaMalloc((void **)&h->d_oidx, (size_t)h->slots3 * h->HW * sizeof(uint32_t)) != cudaSuccess)
             return fail(MDB_ERR_NOMEM, "tier-3 scratch: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    hough_tier3_kernel<<<h->slots3, HOUGH_THREADS, 0, h->stream3>>>(h->hp, T, c.d_dst, h->d_okeys, h->d_oidx, h->d_accum,
+    hough_tier3_kernel<<<h->slots3, HOUGH_THREADS, H3_ORDER_SMEM, h->stream3>>>(h->hp, T, c.d_dst, h->d_okeys, h->d_oidx, h->d_accum,
                                                                    h->d_bitmap, h->d_walk, c.d_lines, c.d_nlines,
-                                                                   c.d_queue + 2);
+                                                                   c.d_queue + 2, h->d_prof);
     h->launches += 5;
     TL(c, 6, h->stream3);
     CK(cudaGetLastError());
