@@ -399,7 +399,7 @@ def main_ours(a):
             det._eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     ext = torch.cuda.ExternalStream(det._eng.stream_ptr(), device=dev)
     pad = 2 * n - 2
-    stream = Stream(B, W, H, a.fps, dev, pad, quiet=n)
+    stream = Stream(B, W, H, a.fps, dev, pad)
     _VIEWS["main"] = stream
     interval = 2
     roi = det.stack.std_roi
@@ -522,6 +522,7 @@ def main_ours(a):
     wall = time.perf_counter() - t0
     sampler.stop()
     launches = det._eng.launch_count() - l0
+    tiers = {k: int(det._eng.info(k + "_total")) for k in ("hough_tier1a", "hough_tier1b", "hough_tier2", "hough_tier3")}
     wall_max = allmax(wall)
     value = world * a.steps * bps * B / wall_max
     dev_ms = e0.elapsed_time(e1)
@@ -693,6 +694,7 @@ def main_ours(a):
                                         "and the next batch's temporal pass (three batches in flight): elapsed, not busy, time",
                          "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s"},
             "clocks": sampler.summary(), "nms_lines_total": nlines_total,
+            "ppht_tiers_rank0": tiers,
         }
         if gather is not None and gather.dropped:
             out["line_records_dropped"] = gather.dropped
@@ -768,11 +770,11 @@ def measure_dense(a, stream, dev):
         dt = time.perf_counter() - t0
         non = det.last_infos["n_on"].astype(np.float64)
         raw = det.last_infos["lines_num"].astype(np.float64)
+        det_info = {k: det._eng.info(k) for k in ("hough_tier1a", "hough_tier1b", "hough_tier2", "hough_tier3")}
         det.close()
         out = {"threshold": thr, "frames": T, "value": T / dt, "unit": UNIT, "on_pixels_mean": float(non.mean()),
                "on_pixels_max": float(non.max()), "raw_segments_mean": float(raw.mean()),
-               "tiers": {"<=2048 (1a)": int((non <= 2048).sum()), "<=4096 (1b)": int(((non > 2048) & (non <= 4096)).sum()),
-                         "<=16384 (2)": int(((non > 4096) & (non <= 16384)).sum()), ">16384 (3)": int((non > 16384).sum())}}
+               "ppht_tiers": {k: int(det_info[k]) for k in ("hough_tier1a", "hough_tier1b", "hough_tier2", "hough_tier3")}}
         if non.mean() >= 5000:
             break
     # CPU arm on a few of the same frames
@@ -807,7 +809,7 @@ def measure_configs(a, dev, peak):
             mask, note = load_bench_mask(W, H)
         det = M3Detector(n / fps + 1e-9, fps, mask, 10, make_cfg(dy=dy), None, device=dev.index or 0, max_batch=B,
                          apply_mask=mk is not None)
-        st = Stream(B, W, H, fps, dev, 0, distinct=2, quiet=n)
+        st = Stream(B, W, H, fps, dev, 0, distinct=2)
         nb = 10
         for s in range(3):
             det.submit(st.ptr(s * B), B, True); det.collect()

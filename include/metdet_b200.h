@@ -181,7 +181,9 @@ int mdb_replay_thresholds(int nsamples, const int64_t *timers, const uint64_t *s
 /* Read-only counters / timings of the most recent batch by name: "temporal_ms" (stack->diff->threshold pass),
  * "spatial_ms" (median + close + dy-mask + mask bytes), "temporal_generation" (which temporal kernel ran: 3 =
  * register ring, 2 = shared-memory ring, 1 = first generation, 0 = none), "stream_kernel" (1 if the time-tiled
- * streaming path serves this handle).  Unknown names return MDB_ERR_INVALID. */
+ * streaming path serves this handle), "hough_tier1a" / "hough_tier1b" / "hough_tier2" / "hough_tier3" (frames of the
+ * batch collected last that each PPHT tier resolved; "..._total": since creation).  Unknown names return
+ * MDB_ERR_INVALID. */
 int mdb_get_info(mdb_handle h, const char *name, double *value);
 /* Tuning / test knobs by name (the parity tests force every kernel variant through these): "stream_kernel" (0 = the
  * generic per-frame kernel), "temporal_version" (1, 2, 3), "t3_variant", "temporal_wpt", "temporal_nt", "temporal_kdiv",

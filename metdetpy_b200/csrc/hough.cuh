@@ -234,14 +234,57 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
             for (int k = 1; k <= MDB_HOUGH_ANGLES; k++) { acc += s_base[k]; s_base[k] = acc; }
         }
         __syncthreads();
-        const int total = s_base[MDB_HOUGH_ANGLES];
+        int total = s_base[MDB_HOUGH_ANGLES];
+        // rho >= gap_b lies gap_skip cells further down the row: rows are ONE interval [mn, mx] by default
+        int gap_b = INT_MAX, gap_skip = 0;
+        if (total > table_bytes / 2) {
+            // Two far-apart objects in one window: per angle the points project onto two clusters with a long empty
+            // stretch in between.  Each thread looks for the longest empty run of its row on a 64-bin occupancy mask
+            // (thread-private: thread n owns angle n) and leaves it out of the table: the row becomes two intervals.
+            __syncthreads();
+            if (tid < MDB_HOUGH_ANGLES) {
+                const int range = mx - mn + 1;
+                unsigned long long occ = 0ull;
+#pragma unroll 4
+                for (int i = 0; i < N; i++) {
+                    const uint32_t k = keys[i];
+                    const int r = rho_cs(k & 0xffffu, k >> 16, my_c, my_s);
+                    occ |= 1ull << (unsigned)(((long long)(r - mn) * 64) / range);
+                }
+                // longest run of empty bins between occupied ones (bins 0 and 63 are occupied: they hold mn and mx)
+                int best_len = 0, best_start = 0, run = 0;
+                for (int bnum = 0; bnum < 64; bnum++) {
+                    if ((occ >> bnum) & 1ull) run = 0;
+                    else if (++run > best_len) { best_len = run; best_start = bnum - run + 1; }
+                }
+                if (best_len >= 2) {
+                    // a = largest rho whose bin is below the run, b = smallest rho whose bin is at or behind its end
+                    const long long gs = best_start, ge = best_start + best_len;
+                    const int a = mn + (int)((gs * range + 63) / 64) - 1;
+                    const int b = mn + (int)((ge * range + 63) / 64);
+                    gap_b = b;
+                    gap_skip = b - a - 1;
+                }
+                s_base[tid + 1] = ((((range - gap_skip) + 1) >> 1) | 1) << 1;
+            }
+            if (tid == 0) s_base[0] = 0;
+            __syncthreads();
+            if (tid == 0) {
+                int acc = 0;
+                for (int k = 1; k <= MDB_HOUGH_ANGLES; k++) { acc += s_base[k]; s_base[k] = acc; }
+            }
+            __syncthreads();
+            total = s_base[MDB_HOUGH_ANGLES];
+        }
         if (total > table_bytes / 2) {  // does not fit in this tier's table: next tier
             if (tid == 0) nlines_out[t] = fail_flag;
             __syncthreads();
             continue;
         }
         for (int i = tid; i < (total + 1) / 2; i += HOUGH_THREADS) reinterpret_cast<uint32_t *>(table)[i] = 0;
-        int16_t *myrow = table + (tid < MDB_HOUGH_ANGLES ? s_base[tid] - mn : 0);
+        int16_t *myrow0 = table + (tid < MDB_HOUGH_ANGLES ? s_base[tid] - mn : 0);
+        // cell of rho r in this thread's row
+#define H1_CELL(r) (myrow0[(r) - ((r) >= gap_b ? gap_skip : 0)])
         __syncthreads();
 
         int par = 0;
@@ -287,8 +330,8 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
                 for (int j = 0; j < HOUGH_SPEC; j++)
                     if (j < cnt) {
                         const int r = rho_cs(ck[j] & 0xffffu, ck[j] >> 16, my_c, my_s);
-                        const int v = (int)myrow[r] + 1;
-                        myrow[r] = (int16_t)v;
+                        const int v = (int)H1_CELL(r) + 1;
+                        H1_CELL(r) = (int16_t)v;
                         sat |= v >= 32767;
                         bj[j] = v * 256 + (255 - tid);  // max value first, lowest angle on ties
                         rj[j] = r;
@@ -317,7 +360,7 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
 #pragma unroll
             for (int j = 0; j < HOUGH_SPEC; j++) {
                 if (j == trig) { key = ck[j]; best = bj[j]; s = cs[j] - 1; }
-                if (j > trig && j < cnt && tid < MDB_HOUGH_ANGLES) myrow[rj[j]] = (int16_t)((int)myrow[rj[j]] - 1);
+                if (j > trig && j < cnt && tid < MDB_HOUGH_ANGLES) H1_CELL(rj[j]) = (int16_t)((int)H1_CELL(rj[j]) - 1);
             }
             const int x = key & 0xffffu, y = key >> 16;
             const int max_n = 255 - (best & 255);
@@ -397,22 +440,22 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
                             r[u] = rho_cs(k2 & 0xffffu, k2 >> 16, my_c, my_s);
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; u++) v[u] = (int)myrow[r[u]];
+                        for (int u = 0; u < 4; u++) v[u] = (int)H1_CELL(r[u]);
                         v[0] -= 1;
                         v[1] = (r[1] == r[0] ? v[0] : v[1]) - 1;
                         v[2] = (r[2] == r[1] ? v[1] : (r[2] == r[0] ? v[0] : v[2])) - 1;
                         v[3] = (r[3] == r[2] ? v[2] : (r[3] == r[1] ? v[1] : (r[3] == r[0] ? v[0] : v[3]))) - 1;
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
-                            myrow[r[u]] = (int16_t)v[u];
+                            H1_CELL(r[u]) = (int16_t)v[u];
                             sat |= v[u] <= -32768;
                         }
                     }
                     for (; q < nw; q++) {
                         const uint32_t k2 = keys[wl[q]];
                         const int rc = rho_cs(k2 & 0xffffu, k2 >> 16, my_c, my_s);
-                        const int v1 = (int)myrow[rc] - 1;
-                        myrow[rc] = (int16_t)v1;
+                        const int v1 = (int)H1_CELL(rc) - 1;
+                        H1_CELL(rc) = (int16_t)v1;
                         sat |= v1 <= -32768;
                     }
                 }
@@ -435,18 +478,22 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
         }
         if (sat) s_ctl[3] = 1;
         __syncthreads();
-        if (tid == 0) nlines_out[t] = s_ctl[3] ? -3 : s_ctl[2];  // a saturated cell (impossible for N <= cap): tier 2
+        if (tid == 0) {
+            nlines_out[t] = s_ctl[3] ? -3 : s_ctl[2];  // a saturated cell (impossible for N <= cap): tier 2
+            if (!s_ctl[3]) atomicAdd(queue + 4, 1u);  // frames this tier resolved (statistics)
+        }
         __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------------------------------
+#undef H1_CELL
 // Tier 2: same algorithm with the accumulator in global memory ([180][numrho] int32 per slot)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(HOUGH_THREADS)
 hough_tier2_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
                    const uint32_t *__restrict__ points, int32_t *accum_slots, int32_t *lines_out,
-                   int *nlines_out, long long *prof) {
+                   int *nlines_out, long long *prof, unsigned *tier_count) {
     extern __shared__ uint32_t h_sm[];
     uint32_t *keys = h_sm;                                            // [cap]
     uint16_t *idx = reinterpret_cast<uint16_t *>(keys + P.cap);       // [cap] visiting order
@@ -690,7 +737,7 @@ hough_tier2_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
         }
         __syncthreads();
         p_reset = clock64() - c1;
-        if (tid == 0) nlines_out[t] = s_ctl[2];
+        if (tid == 0) { nlines_out[t] = s_ctl[2]; atomicAdd(tier_count, 1u); }
         if (prof && tid == 0) {
             long long *o = prof + (size_t)t * 10;
             o[0] = N; o[1] = p_setup; o[2] = p_vote; o[3] = p_walk; o[4] = p_unvote; o[5] = p_reset;
@@ -996,15 +1043,18 @@ hough_tier3_kernel(HoughParams P, int T, const uint8_t *dst, uint32_t *keys, uin
                         if (j < cnt) __stcg(myrow + rj[j], vj[j]);
                 }
 #pragma unroll
-                for (int j = 0; j < HOUGH_SPEC; j++) {
-                    bj[j] = __reduce_max_sync(0xffffffffu, bj[j]);
-                    if (lane == 0) s_red[par][warp][j] = bj[j];
-                }
+                for (int j = 0; j < HOUGH_SPEC; j++)
+                    if (j < cnt) {  // uniform
+                        bj[j] = __reduce_max_sync(0xffffffffu, bj[j]);
+                        if (lane == 0) s_red[par][warp][j] = bj[j];
+                    }
                 __syncthreads();
 #pragma unroll
                 for (int j = 0; j < HOUGH_SPEC; j++)
+                    if (j < cnt) {
 #pragma unroll
-                    for (int k = 0; k < HOUGH_THREADS / 32; k++) bj[j] = max(bj[j], s_red[par][k][j]);
+                        for (int k = 0; k < HOUGH_THREADS / 32; k++) bj[j] = max(bj[j], s_red[par][k][j]);
+                    }
                 par ^= 1;
                 int trig = -1;
 #pragma unroll
@@ -1186,7 +1236,7 @@ hough_tier3_kernel(HoughParams P, int T, const uint8_t *dst, uint32_t *keys, uin
             bitmap[p >> 5] = 0;
         }
         __syncthreads();
-        if (tid == 0) nlines_all[t] = s_ctl[2];
+        if (tid == 0) { nlines_all[t] = s_ctl[2]; atomicAdd(queue + 4, 1u); }
         if (prof && tid == 0) {
             long long *o = prof + (size_t)t * 10;
             o[0] = N; o[1] = p_setup; o[2] = p_vote; o[3] = p_walk; o[4] = p_unvote; o[5] = p_stage;

@@ -46,6 +46,7 @@ struct BatchCtx {
     int *h_thr = nullptr, *h_nlines = nullptr;
     double *h_thrf = nullptr, *h_snr = nullptr;
     unsigned *h_npoints = nullptr;
+    unsigned *h_tiers = nullptr;     // [4] frames resolved by PPHT tiers 1a, 1b, 3, 2
     int32_t *h_lines = nullptr;
     int *d_thr = nullptr;            // per-frame thresholds of this batch (device)
     double *d_thrf = nullptr, *d_snr = nullptr;
@@ -112,6 +113,8 @@ struct mdb_detector {
     int last_T = 0;                           // frames in the most recently finished batch
     int last_ctx = 0;                         // ... and which context holds its dst
     float fused_ms = 0.f, temporal_ms = 0.f, spatial_ms = 0.f;
+    unsigned tiers_last[4] = {0, 0, 0, 0};        // PPHT tier statistics of the batch collected last (1a, 1b, 3, 2)
+    unsigned long long tiers_total[4] = {0, 0, 0, 0};
     int fused_launches = 0, last_fused_launches = 0;
     HoughParams hp;
     int use_stream_kernel = 1;
@@ -173,7 +176,7 @@ static void free_all(mdb_detector *h) {
     }
     stream_state_free(h->sk);
     for (BatchCtx &c : h->ctx) {
-        void *pin[] = {c.h_thr, c.h_nlines, c.h_thrf, c.h_snr, c.h_npoints, c.h_lines};
+        void *pin[] = {c.h_thr, c.h_nlines, c.h_thrf, c.h_snr, c.h_npoints, c.h_lines, c.h_tiers};
         for (void *p : pin)
             if (p) cudaFreeHost(p);
         if (c.ev_f0) cudaEventDestroy(c.ev_f0);
@@ -309,7 +312,7 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
         ALLOC(c.d_npoints, T * sizeof(unsigned));
         ALLOC(c.d_points, (size_t)T * MDB_POINT_CAP * sizeof(uint32_t));
         ALLOC(c.d_order, (size_t)T * HOUGH_ORDER_CAP * sizeof(uint16_t));
-        ALLOC(c.d_queue, 4 * sizeof(unsigned));
+        ALLOC(c.d_queue, 8 * sizeof(unsigned));  // [0..2] work-queue heads of tiers 1a, 1b, 3; [4..7] frames resolved by tiers 1a, 1b, 3, 2
         ALLOC(c.d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t));
         ALLOC(c.d_nlines, T * sizeof(int));
         CKH(cudaMemsetAsync(c.d_dst, 0, (size_t)T * h->HW, h->stream));
@@ -341,6 +344,8 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
         CKH(cudaHostAlloc((void **)&c.h_thrf, T * sizeof(double), cudaHostAllocDefault));
         CKH(cudaHostAlloc((void **)&c.h_snr, T * sizeof(double), cudaHostAllocDefault));
         CKH(cudaHostAlloc((void **)&c.h_npoints, T * sizeof(unsigned), cudaHostAllocDefault));
+        CKH(cudaHostAlloc((void **)&c.h_tiers, 4 * sizeof(unsigned), cudaHostAllocDefault));
+        memset(c.h_tiers, 0, 4 * sizeof(unsigned));
         CKH(cudaHostAlloc((void **)&c.h_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t), cudaHostAllocDefault));
         CKH(cudaEventCreate(&c.ev_f0));
         CKH(cudaEventCreate(&c.ev_f1));
@@ -495,6 +500,7 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
 static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
     CK(cudaStreamWaitEvent(h->stream3, c.ev_d1, 0));  // dst (stream2) has produced the on-pixel lists
     if (c.halo) {  // no results wanted: empty masks, no lines
+        memset(c.h_tiers, 0, 4 * sizeof(unsigned));
         CK(cudaMemsetAsync(c.d_npoints, 0, T * sizeof(unsigned), h->stream3));
         CK(cudaMemsetAsync(c.d_nlines, 0, T * sizeof(int), h->stream3));
         CK(cudaMemcpyAsync(c.h_thr, c.d_thr, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream3));
@@ -505,7 +511,7 @@ static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
         CK(cudaEventRecord(c.ev_done, h->stream3));
         return MDB_OK;
     }
-    CK(cudaMemsetAsync(c.d_queue, 0, 4 * sizeof(unsigned), h->stream3));
+    CK(cudaMemsetAsync(c.d_queue, 0, 8 * sizeof(unsigned), h->stream3));
     TL(c, 4, h->stream3);
     ppht_order_kernel<<<T, 32, HOUGH_ORDER_CAP * 2, h->stream3>>>(T, HOUGH_ORDER_CAP, c.d_npoints, c.d_order);
     // tier 1a: 2 CTAs/SM (2048 points, 90 KB table); tier 1b: 1 CTA/SM (4096 points, 184 KB table)
@@ -517,7 +523,7 @@ static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
         HOUGH_CAP_LARGE, HOUGH_TABLE_BYTES, 1);
     TL(c, 5, h->stream3);
     hough_tier2_kernel<<<std::min(T, h->slots), HOUGH_THREADS, HOUGH_SMEM_BYTES, h->stream3>>>(
-        h->hp, T, c.d_npoints, c.d_points, h->d_accum, c.d_lines, c.d_nlines, h->d_prof);
+        h->hp, T, c.d_npoints, c.d_points, h->d_accum, c.d_lines, c.d_nlines, h->d_prof, c.d_queue + 7);
     if (!h->d_okeys) {  // tier-3 scratch, allocated once
         if (cudaMalloc((void **)&h->d_okeys, (size_t)h->slots3 * h->HW * sizeof(uint32_t)) != cudaSuccess ||
             cudaMalloc((void **)&h->d_oidx, (size_t)h->slots3 * h->HW * sizeof(uint32_t)) != cudaSuccess)
@@ -532,6 +538,7 @@ static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
     CK(cudaMemcpyAsync(c.h_thr, c.d_thr, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream3));
     CK(cudaMemcpyAsync(c.h_thrf, c.d_thrf, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream3));
     CK(cudaMemcpyAsync(c.h_snr, c.d_snr, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream3));
+    CK(cudaMemcpyAsync(c.h_tiers, c.d_queue + 4, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream3));
     CK(cudaMemcpyAsync(c.h_npoints, c.d_npoints, T * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream3));
     CK(cudaMemcpyAsync(c.h_nlines, c.d_nlines, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream3));
     CK(cudaMemcpyAsync(c.h_lines, c.d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t),
@@ -1020,6 +1027,7 @@ extern "C" int mdb_collect_batch(mdb_handle h, mdb_frame_info *infos, int32_t *l
         h->temporal_ms = a; h->spatial_ms = b;
     }
     h->last_fused_launches = h->fused_launches;
+    for (int k = 0; k < 4; k++) { h->tiers_last[k] = c.h_tiers[k]; h->tiers_total[k] += c.h_tiers[k]; }
     int rc = finish_batch(h, c, infos, lines, nonline_prob, raw_lines);
     h->last_T = T;
     h->last_ctx = (int)(h->collected % NCTX);
@@ -1107,6 +1115,14 @@ extern "C" int mdb_get_info(mdb_handle h, const char *name, double *value) {
     if (!strcmp(name, "temporal_ms")) { *value = h->temporal_ms; return MDB_OK; }
     if (!strcmp(name, "spatial_ms")) { *value = h->spatial_ms; return MDB_OK; }
     if (!strcmp(name, "stream_kernel")) { *value = h->sk.ok && h->use_stream_kernel; return MDB_OK; }
+    {   // frames resolved by each PPHT tier: in the batch collected last / since creation ("..._total")
+        static const char *tn[4] = {"hough_tier1a", "hough_tier1b", "hough_tier3", "hough_tier2"};
+        for (int k = 0; k < 4; k++) {
+            if (!strcmp(name, tn[k])) { *value = h->tiers_last[k]; return MDB_OK; }
+            const size_t ln = strlen(tn[k]);
+            if (!strncmp(name, tn[k], ln) && !strcmp(name + ln, "_total")) { *value = (double)h->tiers_total[k]; return MDB_OK; }
+        }
+    }
     return fail(MDB_ERR_INVALID, "mdb_get_info: unknown name %s", name);
 }
 

@@ -72,9 +72,8 @@ def make_stream_device(T: int, W: int, H: int, FPS: float, device, seed: int = 1
     parity runs use the host generator). Returns a (T,H,W) uint8 CUDA tensor.
 
     loop > 0 makes the stream cyclic with period `loop` frames (a benchmark replays a few resident
-    batches): a streak that would still be inside the detector's window (`quiet` frames) when the
-    stream jumps back to frame 0 is left out, so the replayed stream never shows two streaks in one
-    window -- which the continuous stream (one streak every 2 s, 0.5 s long) cannot do either."""
+    batches).  quiet > 0 (not used by bench.py any more) leaves out a streak that would still be inside
+    the detector's window (`quiet` frames) when the stream jumps back to frame 0."""
     import torch
     sky = torch.from_numpy(make_sky(W, H, seed)).to(device)
     out = torch.empty((T, H, W), dtype=torch.uint8, device=device)

@@ -112,3 +112,41 @@ def test_4k_streaming_vs_generic_kernel_and_batch_split_invariance():
             assert np.array_equal(a[t][3], other[t][3]) and np.array_equal(a[t][4], other[t][4]), t
         lit += a[t][2] > 0
     assert lit > 10
+
+
+def test_4k_two_far_apart_objects_stay_on_chip_and_equal_cv2():
+    """Two streaks far apart in one window (plus a dense-noise frame): per angle their points project onto two rho
+    clusters, so the shared-memory PPHT tier keeps TWO intervals per row instead of handing the frame to the
+    global-memory tier.  Raw segments must equal cv2.HoughLinesP on the device's own masks, and the tier statistics
+    must show the frames on chip."""
+    import cv2
+    from metdetpy_b200 import BinaryCfg, BinaryCoreCfg, DynamicCfg, HoughLineCfg
+    from metdetpy_b200.detector import M3Detector
+    W, H, n, T = 3840, 2160, 5, 24
+    rng = np.random.default_rng(21)
+    frames = np.clip(48 + rng.normal(0, 2.0, (T, H, W)), 0, 255).astype(np.uint8)
+    for t in range(4, T):  # two objects, ~3000 px apart, moving in different directions
+        for (x0, y0, dx, dy) in ((300, 250, 14, 5), (3400, 1900, -9, -12)):
+            m = np.zeros((H, W), np.uint8)
+            p1 = (int(x0 + dx * (t - 4)), int(y0 + dy * (t - 4)))
+            p2 = (int(x0 + dx * (t - 3)), int(y0 + dy * (t - 3)))
+            cv2.line(m, p1, p2, 70, 3, cv2.LINE_AA)
+            frames[t] = np.clip(frames[t].astype(np.int32) + m, 0, 255).astype(np.uint8)
+    mask = np.ones((H, W), np.uint8)
+    cfg = BinaryCfg(BinaryCoreCfg(False, 12, "normal", 0.1, 2), HoughLineCfg(10, 10, 10), DynamicCfg(True, 5))
+    det = M3Detector(n / 30 + 1e-9, 30, mask, 10, cfg, None, max_batch=T)
+    res, dst = det.detect_many(frames, return_dst=True)
+    both = 0
+    for t in range(T):
+        info = det.last_infos[t]
+        ref = cv2.HoughLinesP(dst[t], 1, np.pi / 180, 10, minLineLength=10, maxLineGap=float(info["gap"]))
+        ref = np.zeros((0, 4), np.int32) if ref is None else ref.reshape(-1, 4)
+        assert info["lines_num"] == len(ref), (t, info["lines_num"], len(ref))
+        assert np.array_equal(det.last_raw[t].reshape(-1, 4), ref), t
+        ys, xs = np.nonzero(dst[t])
+        both += int(len(xs) > 0 and xs.min() < 1500 and xs.max() > 2500)
+    assert both >= 10, "the two objects were not in the masks together"
+    on_chip = det._eng.info("hough_tier1a") + det._eng.info("hough_tier1b")
+    assert det._eng.info("hough_tier2") == 0 and det._eng.info("hough_tier3") == 0, "a frame left the shared-memory tiers"
+    assert on_chip >= both
+    det.close()
