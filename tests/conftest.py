@@ -10,7 +10,9 @@ if REPO not in sys.path:
 GOLDEN = os.path.join(REPO, "tests", "golden")
 
 DET_CASES = ["synth_320x240_n5_dyoff", "synth_384x216_n12_dyon_mask", "synth_203x157_n3_high",
-             "synth_256x160_n6_fixed3_dense", "synth_300x200_n7_low", "clip_192x144_n25"]
+             "synth_256x160_n6_fixed3_dense", "synth_300x200_n7_low", "clip_192x144_n25",
+             # BASELINE config 1: the bundled clip as detect_video feeds it (real mask, exp_frame = 4 merge, n = 6)
+             "clip_cfg1_480x270_n6", "clip_cfg1_960x540_n6_range"]
 
 
 def pytest_configure(config):

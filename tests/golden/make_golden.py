@@ -337,7 +337,53 @@ def case_preproc():
     np.savez_compressed(os.path.join(HERE, "preproc.npz"), names=np.array([c[0] for c in cases]), **out)
 
 
-CASES = dict(preproc=case_preproc, gauss=case_gauss_stack, classic=case_classic, synth_small=case_synth_small, synth_dy_mask=case_synth_dy_mask, odd=case_odd_size,
+def _clip_config1_frames(W, H):
+    """The bundled clip exactly as MetDetPy.detect_video feeds it to the detector with config/m3det_normal.json
+    (BASELINE config 1): cv2/FFmpeg decode -> resize (W, H) INTER_LINEAR -> BGR2GRAY -> x mask (test/mask-east.jpg
+    through the reference's own fileio.load_mask) -> MergeFunction.max over exp_frame = 4 decoded frames
+    (videoloader.py:300-308, :388; utils.py:203-204).  eq_fps = 25 / 4 = 6.25, window n = int(1 * 6.25) = 6."""
+    from MetLib.fileio import load_mask
+    from MetLib.utils import MergeFunction
+    mask = load_mask("/root/reference/test/mask-east.jpg", [W, H], grayscale=True)
+    assert mask.shape == (H, W) and set(np.unique(mask)) <= {0, 1}
+    cap = cv2.VideoCapture("/root/reference/test/20220413Red.mp4")
+    merged, group = [], []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        f = cv2.resize(f, (W, H), interpolation=cv2.INTER_LINEAR)
+        g = cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) * mask
+        group.append(g)
+        if len(group) == 4:
+            merged.append(MergeFunction.max(group)); group = []
+    if group:
+        merged.append(MergeFunction.max(group))
+    return np.stack(merged).astype(np.uint8), mask
+
+
+def case_clip_config1():
+    """BASELINE config 1 through the real M3Detector: the whole clip at 480x270 (80 detector iterations) and the
+    stretch around the annotated meteor (test/20220413_annotation.json: 2.4 s .. 4.4 s) at the runtime size 960x540."""
+    fr, mask = _clip_config1_frames(480, 270)
+    run_detector_case("clip_cfg1_480x270_n6", fr, mask, 6, 6.25, NORMAL, dy=True)
+    fr, mask = _clip_config1_frames(960, 540)
+    run_detector_case("clip_cfg1_960x540_n6_range", fr[8:30], mask, 6, 6.25, NORMAL, dy=True)
+
+
+def case_masks():
+    """test/mask-east.jpg through fileio.load_mask (fileio.py:250-292) at the sizes the benchmark and the tests use,
+    bit-packed."""
+    from MetLib.fileio import load_mask
+    for W, H in ((3840, 2160), (960, 540), (480, 270)):
+        m = load_mask("/root/reference/test/mask-east.jpg", [W, H], grayscale=True)
+        assert m.shape == (H, W) and m.dtype == np.uint8 and set(np.unique(m)) <= {0, 1}
+        path = os.path.join(HERE, f"mask_east_{W}x{H}.npz")
+        np.savez_compressed(path, bits=np.packbits(m, axis=None), shape=np.array([H, W]))
+        print(f"mask_east {W}x{H}: open share {m.mean():.4f} -> {os.path.getsize(path) / 1e3:.1f} KB")
+
+
+CASES = dict(clip_cfg1=case_clip_config1, masks=case_masks, preproc=case_preproc, gauss=case_gauss_stack, classic=case_classic, synth_small=case_synth_small, synth_dy_mask=case_synth_dy_mask, odd=case_odd_size,
              dense=case_fixed_thr_dense, low=case_low_sens, clip=case_real_clip, nms=case_nms,
              sw=case_sliding_window, hough=case_hough)
 

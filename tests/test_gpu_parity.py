@@ -474,3 +474,49 @@ def test_device_chunk_pipeline_equals_reference_golden(name, world, batch):
             seen += 1
     assert seen == T
     det.close()
+
+
+def test_config1_bundled_clip_through_the_cuda_class():
+    """BASELINE config 1 (test/20220413Red.mp4 with config/m3det_normal.json and test/mask-east.jpg) through the
+    CUDA M3Detector with the reference's own call pattern (MetDetPy.py:197-198): the frames are what detect_video
+    hands to the detector (resize, gray, real mask, max-merge of exp_frame = 4 decoded frames; window n = 6), the
+    golden trajectory is the live reference's.  Spot values of SURVEY 8(c): threshold 5 -> 4, mask_area 474728 and
+    std_roi (185,328,355,631) at 960x540, and the one annotated meteor (test/20220413_annotation.json: 2.4 s .. 4.4 s,
+    (433,147)-(374,222) on a 1168x655 canvas) is found inside its time span, on its line."""
+    from metdetpy_b200.detector import M3Detector
+    g = load_det_case("clip_cfg1_480x270_n6")
+    H, W = g["frames"].shape[1:]
+    det = M3Detector(g["n"] / g["fps"] + 1e-9, g["fps"], g["mask"], 10, _cfg(g["cfg"]), None)
+    assert det.stack_maxsize == 6
+    hits = []
+    for t in range(len(g["frames"])):
+        det.update(g["frames"][t])
+        lines, cls = det.detect()
+        _check_frame(det, g, t, lines, cls, det.dst)
+        if len(lines):
+            hits.append((t, np.asarray(lines)))
+    det.close()
+    assert g["bi_threshold"][0] == 5 and set(g["bi_threshold"][1:].tolist()) == {4}
+    assert hits and hits[0][0] == 20
+    eq_fps = 25 / 4
+    for t, lines in hits:  # a window of n merged frames ends at frame t
+        assert 2.4 - 0.2 <= t / eq_fps <= 4.4 + 6 / eq_fps, t
+    # the annotated segment, scaled to this frame size
+    sx, sy = W / 1168, H / 655
+    p1, p2 = np.array([433 * sx, 147 * sy]), np.array([374 * sx, 222 * sy])
+    d = (p2 - p1) / np.linalg.norm(p2 - p1)
+    for t, lines in hits:
+        for x1, y1, x2, y2 in lines:
+            for q in (np.array([x1, y1], float), np.array([x2, y2], float)):
+                off = q - p1
+                assert abs(off[0] * d[1] - off[1] * d[0]) < 6, (t, lines)          # distance from the annotated line
+                assert -10 <= off @ d <= np.linalg.norm(p2 - p1) + 10, (t, lines)  # within its extent
+    g2 = load_det_case("clip_cfg1_960x540_n6_range")
+    assert int(g2["mask_area"]) == 474728 and tuple(g2["std_roi"]) == (185, 328, 355, 631)
+    det = M3Detector(g2["n"] / g2["fps"] + 1e-9, g2["fps"], g2["mask"], 10, _cfg(g2["cfg"]), None, max_batch=22)
+    assert tuple(det.stack.std_roi) == (185, 328, 355, 631) and int(det.mask_area) == 474728
+    res, dst = det.detect_many(g2["frames"], return_dst=True)
+    for t, (lines, cls) in enumerate(res):
+        _check_frame(det, g2, t, lines, cls, dst[t], det.last_infos[t])
+    assert np.array_equal(np.asarray(res[12][0]), [[337, 152, 351, 126]])
+    det.close()
