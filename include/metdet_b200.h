@@ -205,6 +205,12 @@ int mdb_max_stack(const uint8_t *frames, int T, size_t frame_bytes, uint8_t *out
  * input index (what np.argsort(...)[::-1] yields for the n <= 16 insertion-sort regime). */
 int mdb_lineset_nms(const int32_t *lines_in, int n, int32_t *lines_out, double *prob_out,
                     int32_t *n_out);
+/* Same greedy pass over a visiting order supplied by the caller (a permutation of 0..n-1, longest first).  The
+ * reference orders with np.argsort(len^2)[::-1] (MetLib/utils.py:804), whose order among EQUAL lengths is numpy's
+ * business for n > 16; the Python layer passes numpy's own order here whenever lengths tie, so the kept lines are the
+ * reference's on the same host. */
+int mdb_lineset_nms_ordered(const int32_t *lines_in, int n, const int32_t *order, int32_t *lines_out,
+                            double *prob_out, int32_t *n_out);
 
 /* FastGaussianContainer.append over T frames (MetLib/stacker.py:52-59; FastGaussianParam.__init__/__add__,
  * MetLib/utils.py:435-452, :485-493): per element sum_out = sum of the frames as uint16 and sq_out = sum of

@@ -549,7 +549,7 @@ static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
 }
 
 // ---- lineset_nms on the host (MetLib/utils.py:780-839) --------------------------------------
-static int nms_host(const int32_t *in, int n, int32_t *out, double *prob) {
+static int nms_host(const int32_t *in, int n, int32_t *out, double *prob, const int32_t *given_order = nullptr) {
     std::vector<long long> len2(n), A(n), B(n), C(n), cx(n), cy(n);
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) {
@@ -561,10 +561,14 @@ static int nms_host(const int32_t *in, int n, int32_t *out, double *prob) {
         cy[i] = (y2 + y1) >= 0 ? (y2 + y1) / 2 : -((-(y2 + y1) + 1) / 2);
         order[i] = i;
     }
-    std::sort(order.begin(), order.end(), [&](int a, int b) {
-        if (len2[a] != len2[b]) return len2[a] > len2[b];
-        return a > b;
-    });
+    if (given_order) {
+        for (int i = 0; i < n; i++) order[i] = given_order[i];
+    } else {
+        std::sort(order.begin(), order.end(), [&](int a, int b) {
+            if (len2[a] != len2[b]) return len2[a] > len2[b];
+            return a > b;
+        });
+    }
     std::vector<char> taken(n, 0);
     int k = 0;
     for (int i = 0; i < n; i++) {
@@ -596,6 +600,20 @@ extern "C" int mdb_lineset_nms(const int32_t *lines_in, int n, int32_t *lines_ou
     if (n < 0 || (n > 0 && (!lines_in || !lines_out || !prob_out)) || !n_out)
         return fail(MDB_ERR_INVALID, "mdb_lineset_nms: bad arguments");
     *n_out = n ? nms_host(lines_in, n, lines_out, prob_out) : 0;
+    return MDB_OK;
+}
+
+extern "C" int mdb_lineset_nms_ordered(const int32_t *lines_in, int n, const int32_t *order, int32_t *lines_out,
+                                       double *prob_out, int32_t *n_out) {
+    if (n < 0 || (n > 0 && (!lines_in || !order || !lines_out || !prob_out)) || !n_out)
+        return fail(MDB_ERR_INVALID, "mdb_lineset_nms_ordered: bad arguments");
+    std::vector<char> seen(n, 0);
+    for (int i = 0; i < n; i++) {
+        if (order[i] < 0 || order[i] >= n || seen[order[i]])
+            return fail(MDB_ERR_INVALID, "mdb_lineset_nms_ordered: order is not a permutation of 0..%d", n - 1);
+        seen[order[i]] = 1;
+    }
+    *n_out = n ? nms_host(lines_in, n, lines_out, prob_out, order) : 0;
     return MDB_OK;
 }
 

@@ -56,14 +56,24 @@ def select_subarea(mask: np.ndarray, area: float) -> tuple[int, int, int, int]:
     return (r0, c0, r0 + sub_h, c0 + sub_w)
 
 
+def _len2_ties(lines: np.ndarray) -> bool:
+    d = lines[:, 2:].astype(np.int64) - lines[:, :2]
+    l2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]
+    return len(np.unique(l2)) != len(l2)
+
+
 def lineset_nms(lines: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
-    """lineset_nms (MetLib/utils.py:780-839) -- runs in the library's host C++ (mdb_lineset_nms)."""
+    """lineset_nms (MetLib/utils.py:780-839): the greedy pass runs in the library's host C++; the visiting order is the
+    reference's own `np.argsort(length_sqr)[::-1]` (utils.py:804), evaluated by numpy on this host on the same int32
+    values, so that equal lengths are ordered exactly as the reference orders them here."""
     lines = np.ascontiguousarray(lines, np.int32).reshape(-1, 4)
     n = len(lines)
     out = np.empty((max(n, 1), 4), np.int32)
     prob = np.empty(max(n, 1), np.float64)
     k = C.c_int32(0)
-    check(_lib.load().mdb_lineset_nms(_ptr(lines), n, _ptr(out), _ptr(prob), C.byref(k)), "lineset_nms")
+    length_sqr = np.power((lines[:, 3] - lines[:, 1]), 2) + np.power((lines[:, 2] - lines[:, 0]), 2)
+    order = np.ascontiguousarray(np.argsort(length_sqr)[::-1], np.int32)
+    check(_lib.load().mdb_lineset_nms_ordered(_ptr(lines), n, _ptr(order), _ptr(out), _ptr(prob), C.byref(k)), "lineset_nms")
     return out[:k.value].copy(), prob[:k.value].copy()
 
 
@@ -476,6 +486,8 @@ class M3Detector(LineDetector):
         out = [empty] * T
         for i in np.nonzero(nl)[0]:
             k = int(nl[i])
+            self._renms_if_tied(i, info)
+            k = int(info["n_lines"][i])
             cls_pred = np.zeros((k, self.num_cls))
             p = eng.prob[i, :k]
             cls_pred[:, -1] = p
@@ -485,8 +497,28 @@ class M3Detector(LineDetector):
         self.last_infos = info.copy()
         return out
 
+    def _renms_if_tied(self, i: int, info=None):
+        """The library orders equal-length segments by descending index, which is what np.argsort(...)[::-1] yields
+        up to 16 segments (insertion sort).  Beyond that numpy's order among ties is its own: redo the NMS of such a
+        frame with numpy's order (lineset_nms above) so that the result is the reference's on this host."""
+        eng = self._eng
+        fi = eng.infos[i]
+        if fi.n_raw <= 16 or fi.n_lines == 0:
+            return
+        raw = eng.raw[i, :fi.n_raw]
+        if not _len2_ties(raw):
+            return
+        lines, prob = lineset_nms(raw)
+        k = len(lines)
+        eng.lines[i, :k] = lines
+        eng.prob[i, :k] = prob
+        fi.n_lines = k
+        if info is not None:
+            info["n_lines"][i] = k
+
     def _unpack(self, i: int):
         eng = self._eng
+        self._renms_if_tied(i)
         fi = eng.infos[i]
         self.bi_threshold = fi.bi_threshold
         self.bi_threshold_float = fi.bi_threshold_float

@@ -49,20 +49,23 @@ def golden_dir():
 
 
 def assert_nms_equivalent(got_lines, got_prob, ref_lines, ref_prob, raw_lines, ctx=""):
-    """NMS output check. Without length ties among the raw segments the result must be identical
-    (rows, order, probabilities to 1e-12). With ties the reference's own order comes from an
-    unstable np.argsort (MetLib/utils.py:804) and depends on numpy's CPU dispatch, so the kept
-    segments are compared as a set and, failing that (a tie decided which of two mutually
-    absorbing segments survives), by count."""
+    """NMS output check: identical rows, order and probabilities (1e-12).  The reference orders the raw segments with
+    np.argsort(len^2)[::-1] (MetLib/utils.py:804); among EQUAL lengths that order is deterministic up to 16 segments
+    (insertion sort) and numpy's / the CPU's business beyond.  For such a frame (rare: 2 of the 135 golden frames with
+    lines) the expected result is recomputed on THIS host from the golden raw segments with the CPU checker's NMS,
+    which calls numpy's argsort exactly like the reference -- and the comparison is exact again."""
     got = np.asarray(got_lines).reshape(-1, 4)
     ref = np.asarray(ref_lines).reshape(-1, 4)
     raw = np.asarray(raw_lines).reshape(-1, 4)
-    if not has_len2_ties(raw):
-        assert np.array_equal(got, ref), (ctx, got, ref)
-        if got_prob is not None and ref_prob is not None:
-            assert np.allclose(np.asarray(got_prob).ravel(), np.asarray(ref_prob).ravel(), rtol=1e-12, atol=0), ctx
-        return
-    a = sorted(map(tuple, got.tolist()))
-    b = sorted(map(tuple, ref.tolist()))
-    if a != b:
-        assert abs(len(a) - len(b)) <= 2, (ctx, got, ref)
+    if len(raw) > 16 and has_len2_ties(raw):
+        from oracle import m3_oracle as O
+        ref, ref_prob = O.lineset_nms(raw.astype(np.int32))
+        NMS_BRANCHES["recomputed_on_host"] += 1
+    else:
+        NMS_BRANCHES["golden_exact"] += 1
+    assert np.array_equal(got, np.asarray(ref).reshape(-1, 4)), (ctx, got, ref)
+    if got_prob is not None and ref_prob is not None:
+        assert np.allclose(np.asarray(got_prob).ravel(), np.asarray(ref_prob).ravel(), rtol=1e-12, atol=0), ctx
+
+
+NMS_BRANCHES = {"golden_exact": 0, "recomputed_on_host": 0}
