@@ -36,6 +36,7 @@ extern "C" {
 
 #define MDB_NUM_LINES_TOOMUCH 500 /* MetLib/Detector.py:30 */
 #define MDB_MAX_LINES 512         /* per-frame capacity of the raw / NMS line outputs (> 500) */
+#define MDB_MAX_WINDOW 4096       /* longest window n (the streaming kernels serve n <= 128, the generic kernel the rest) */
 
 #define MDB_SENS_LOW 0
 #define MDB_SENS_NORMAL 1
@@ -45,7 +46,7 @@ extern "C" {
  * after the host has evaluated the pure-Python parts (int(window_sec*fps), select_subarea). */
 typedef struct mdb_config {
     int32_t width, height;
-    int32_t window;          /* n = int(window_sec * fps), 1 <= n <= 255        Detector.py:197 */
+    int32_t window;          /* n = int(window_sec * fps), 1 <= n <= MDB_MAX_WINDOW  Detector.py:197 */
     int32_t adaptive;        /* cfg.binary.adaptive_bi_thre                     Detector.py:204 */
     int32_t init_value;      /* cfg.binary.init_value (used when !adaptive)     Detector.py:208 */
     int32_t sensitivity;     /* MDB_SENS_*  (cfg.binary.sensitivity)            Detector.py:177-183 */
@@ -77,7 +78,10 @@ typedef struct mdb_frame_info {
     int32_t lines_num;         /* M3Detector.lines_num (raw HoughLinesP count)  Detector.py:357 */
     int32_t n_raw;             /* rows valid in raw_lines (0 when lines_num > 500, :358-360) */
     int32_t n_lines;           /* M3Detector.filtered_line_num (after NMS)      Detector.py:373 */
-    int32_t reserved;
+    int32_t len_ties;          /* != 0: two raw segments have the same length; the NMS order among them (numpy's
+                                  unstable argsort, utils.py:804) is then the host's business: the library used
+                                  "descending index", a caller that wants numpy's order on its machine redoes the frame
+                                  with mdb_lineset_nms_ordered */
 } mdb_frame_info;
 
 typedef struct mdb_detector *mdb_handle;
@@ -152,6 +156,16 @@ int mdb_get_dst_device(mdb_handle h, const uint8_t **ptr);
 /* SlidingWindow.max / .mean / .sum (utils.py:288-300) of the detector's main window. Any output
  * may be NULL. Host buffers of H*W elements. */
 int mdb_get_stack(mdb_handle h, uint8_t *max_out, uint8_t *mean_out, uint32_t *sum_out);
+/* SlidingWindow.sliding_window (MetLib/utils.py:263-265): out[n][H][W], the ring in the reference's slot order (slot i =
+ * newest frame whose 0-based index is congruent to i modulo n; never-written slots are zero). */
+int mdb_get_window(mdb_handle h, uint8_t *out, int on_device);
+/* SlidingWindow.std in the uint8 / force_int mode (MetLib/utils.py:309-321): sqrt(mean((sum(x^2) - sum(x)^2 // L) // L))
+ * with numpy's uint32 arithmetic per pixel; exact integer total on the device. */
+int mdb_get_std(mdb_handle h, double *std_out);
+/* Every raw Hough segment of frame `frame` (0-based) of the batch collected last, without the MDB_MAX_LINES cap of the
+ * batched outputs: ClassicDetector returns all of them (Detector.py:282-292).  *n_out = the count; with cap == 0 only the
+ * count is returned; cap < count is an error. */
+int mdb_get_raw_lines(mdb_handle h, int frame, int32_t *out, int cap, int32_t *n_out);
 
 /* The handle's CUDA stream (cudaStream_t) -- for callers that time with CUDA events. */
 int mdb_get_stream(mdb_handle h, void **stream);

@@ -7,11 +7,13 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import warnings
 
 from . import build as _build
 
 MAX_LINES = 512
 NUM_LINES_TOOMUCH = 500
+ABI_VERSION = 102  # mdb_version() of the library this binding was written against
 
 
 class Config(C.Structure):
@@ -27,7 +29,7 @@ class FrameInfo(C.Structure):
     _fields_ = [("timer", C.c_int64), ("bi_threshold", C.c_int32), ("n_on", C.c_int32),
                 ("bi_threshold_float", C.c_double), ("snr", C.c_double), ("dst_sum", C.c_double),
                 ("gap", C.c_double), ("lines_num", C.c_int32), ("n_raw", C.c_int32),
-                ("n_lines", C.c_int32), ("reserved", C.c_int32)]
+                ("n_lines", C.c_int32), ("len_ties", C.c_int32)]
 
 
 # every symbol include/metdet_b200.h declares: (restype, argtypes)
@@ -46,6 +48,9 @@ SYMBOLS = {
     "mdb_get_dst": (_I, [_VP, _VP, _I]),
     "mdb_get_dst_device": (_I, [_VP, C.POINTER(_VP)]),
     "mdb_get_stack": (_I, [_VP, _VP, _VP, _VP]),
+    "mdb_get_window": (_I, [_VP, _VP, _I]),
+    "mdb_get_std": (_I, [_VP, C.POINTER(C.c_double)]),
+    "mdb_get_raw_lines": (_I, [_VP, _I, _VP, _I, C.POINTER(C.c_int32)]),
     "mdb_get_stream": (_I, [_VP, C.POINTER(_VP)]),
     "mdb_get_launch_count": (_I, [_VP, C.POINTER(C.c_int64)]),
     "mdb_get_fused_time": (_I, [_VP, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
@@ -95,9 +100,19 @@ def load():
                 raise RuntimeError(
                     "libmetdet_b200.so is missing and could not be built with nvcc "
                     f"({e}); metdetpy_b200 has no CPU fallback") from e
+            # an older binary exists: it is only usable if it still speaks this binding's ABI (checked below)
+            warnings.warn(f"libmetdet_b200.so is older than its sources and the rebuild failed ({e}); "
+                          "loading the existing binary", RuntimeWarning, stacklevel=2)
     lib = C.CDLL(path)
+    lib.mdb_version.restype = _I
+    ver = lib.mdb_version()
+    if ver != ABI_VERSION:
+        raise RuntimeError(f"{path} reports ABI version {ver}, this binding needs {ABI_VERSION}: rebuild it "
+                           "(python -m metdetpy_b200.build --force)")
     for name, (res, args) in SYMBOLS.items():
-        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn = getattr(lib, name, None)
+        if fn is None:
+            raise RuntimeError(f"{path} does not export {name} (declared in include/metdet_b200.h): stale build")
         fn.restype = res
         fn.argtypes = args
     _lib = lib

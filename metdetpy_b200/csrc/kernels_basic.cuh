@@ -27,8 +27,9 @@ noise_sample_kernel(FrameSrc src, int W, int n, long long timer0, long long std_
     if (tau < min_tau || !is_noise_sample(tau, n, std_interval)) return;
     const int L = (int)(tau < n ? tau : n);
     const long long t = tau - 1;
-    __shared__ const uint8_t *fp[256];  // window frame pointers (n <= 255), resolved once per block
-    for (int k = threadIdx.x; k < L; k += blockDim.x) fp[k] = src.frame(t - k);
+    __shared__ const uint8_t *fp[256];  // window frame pointers, resolved once per block (longer windows resolve inline)
+    const bool big = L > 256;
+    for (int k = threadIdx.x; k < min(L, 256); k += blockDim.x) fp[k] = src.frame(t - k);
     __syncthreads();
     unsigned long long d1 = 0, d2 = 0;
     const int total = rh * rw;
@@ -39,7 +40,7 @@ noise_sample_kernel(FrameSrc src, int W, int n, long long timer0, long long std_
         unsigned sx = 0, sxx = 0;
 #pragma unroll 4
         for (int k = 0; k < L; k++) {
-            const unsigned v = fp[k][p] * mk;
+            const unsigned v = (big ? src.frame(t - k) : fp[k])[p] * mk;
             sx += v;
             sxx += v * v;
         }
@@ -246,8 +247,9 @@ fused_frame_kernel(FrameSrc src, int W, int H, int n, long long t, int L, long l
     const int x0 = blockIdx.x * V1_TW - 4, y0 = blockIdx.y * V1_TH - 4;
     const int thr = *thr_ptr;
     const int nwin = (int)((t + 1) < n ? (t + 1) : n);  // frames that exist in the window
-    __shared__ const uint8_t *fp[256];  // window frame pointers, resolved once per block
-    for (int k = tid; k < nwin; k += 256) fp[k] = src.frame(t - k);
+    __shared__ const uint8_t *fp[256];  // window frame pointers, resolved once per block (longer windows resolve inline)
+    const bool big = nwin > 256;
+    for (int k = tid; k < min(nwin, 256); k += 256) fp[k] = src.frame(t - k);
     __syncthreads();
     // stage 0: diff on the whole region, replicated border (medianBlur's border mode)
     for (int q = tid; q < V1_RW * V1_RH; q += 256) {
@@ -258,7 +260,7 @@ fused_frame_kernel(FrameSrc src, int W, int H, int n, long long t, int L, long l
         unsigned mx = 0, sm = 0;
 #pragma unroll 4
         for (int k = 0; k < nwin; k++) {
-            const unsigned v = fp[k][p] * mk;
+            const unsigned v = (big ? src.frame(t - k) : fp[k])[p] * mk;
             mx = max(mx, v);
             sm += v;
         }
@@ -352,14 +354,15 @@ __global__ void stack_readback_kernel(FrameSrc src, size_t HW, int n, long long 
                                       uint8_t *mx_out, uint8_t *mean_out, uint32_t *sum_out) {
     const int nwin = (int)((t + 1) < n ? (t + 1) : n);
     __shared__ const uint8_t *fp[256];
-    for (int k = threadIdx.x; k < nwin; k += blockDim.x) fp[k] = src.frame(t - k);
+    const bool big = nwin > 256;
+    for (int k = threadIdx.x; k < min(nwin, 256); k += blockDim.x) fp[k] = src.frame(t - k);
     __syncthreads();
     for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < HW;
          p += (size_t)gridDim.x * blockDim.x) {
         const unsigned mk = src.mask ? src.mask[p] : 1u;
         unsigned mx = 0, sm = 0;
         for (int k = 0; k < nwin; k++) {
-            const unsigned v = fp[k][p] * mk;
+            const unsigned v = (big ? src.frame(t - k) : fp[k])[p] * mk;
             mx = max(mx, v);
             sm += v;
         }
@@ -367,6 +370,36 @@ __global__ void stack_readback_kernel(FrameSrc src, size_t HW, int n, long long 
         if (mean_out) mean_out[p] = (uint8_t)(sm / (unsigned)L);
         if (sum_out) sum_out[p] = sm;
     }
+}
+
+// one ring frame as the reference's window holds it (masked when the library does the loader's mask_with)
+__global__ void window_frame_kernel(const uint8_t *frame, const uint8_t *mask, size_t HW, uint8_t *out) {
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < HW; p += (size_t)gridDim.x * blockDim.x)
+        out[p] = (uint8_t)(frame[p] * mask[p]);
+}
+
+// SlidingWindow.std with calc_std=True, force_int=True, dtype=uint8 (MetLib/utils.py:309-321):
+// sqrt(mean((square_sum - square(sum) // L) // L)) in numpy's uint32 arithmetic; this kernel leaves the exact integer total
+// of the per-pixel terms in *total (the mean and the square root are two double operations on the host side of the ABI).
+__global__ void stack_std_kernel(FrameSrc src, size_t HW, int n, long long t, int L, unsigned long long *total) {
+    const int nwin = (int)((t + 1) < n ? (t + 1) : n);
+    __shared__ const uint8_t *fp[256];
+    const bool big = nwin > 256;
+    for (int k = threadIdx.x; k < min(nwin, 256); k += blockDim.x) fp[k] = src.frame(t - k);
+    __syncthreads();
+    unsigned long long acc = 0;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < HW; p += (size_t)gridDim.x * blockDim.x) {
+        const unsigned mk = src.mask ? src.mask[p] : 1u;
+        unsigned sm = 0, sq = 0;
+        for (int k = 0; k < nwin; k++) {
+            const unsigned v = (big ? src.frame(t - k) : fp[k])[p] * mk;
+            sm += v;
+            sq += v * v;
+        }
+        acc += (unsigned)(sq - (unsigned)(sm * sm) / (unsigned)L) / (unsigned)L;  // uint32 wrap-around as in numpy
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(total, acc);
 }
 
 // Ordered (row-major) compaction of one dst mask into keys (y<<16|x): the overflow path for

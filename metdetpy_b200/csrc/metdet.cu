@@ -128,7 +128,7 @@ struct mdb_detector {
     } while (0)
 
 extern "C" const char *mdb_last_error(void) { return g_err; }
-extern "C" int mdb_version(void) { return 101; }
+extern "C" int mdb_version(void) { return 102; }
 extern "C" int mdb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -216,8 +216,8 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     *out = nullptr;
     if (cfg->width < 1 || cfg->height < 1 || cfg->width > 65535 || cfg->height > 65535)
         return fail(MDB_ERR_INVALID, "mdb_create: unsupported frame size %dx%d", cfg->width, cfg->height);
-    if (cfg->window < 1 || cfg->window > 255)
-        return fail(MDB_ERR_INVALID, "mdb_create: window n=%d outside 1..255", cfg->window);
+    if (cfg->window < 1 || cfg->window > MDB_MAX_WINDOW)
+        return fail(MDB_ERR_INVALID, "mdb_create: window n=%d outside 1..%d", cfg->window, MDB_MAX_WINDOW);
     if (cfg->max_batch < 1) return fail(MDB_ERR_INVALID, "mdb_create: max_batch must be >= 1");
     if (cfg->sensitivity < 0 || cfg->sensitivity > 2)
         return fail(MDB_ERR_INVALID, "mdb_create: bad sensitivity %d", cfg->sensitivity);
@@ -497,6 +497,36 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
     return MDB_OK;
 }
 
+// the PPHT tiers over frames 0..T-1 whose on-pixel lists / masks start at the given pointers; `hp.max_lines` rows of
+// `d_lines` per frame.  tl (may be null): batch context whose timeline events are recorded.
+static int launch_hough_kernels(mdb_detector *h, BatchCtx *tl, const HoughParams &hp, int T, const unsigned *d_npoints,
+                                const uint32_t *d_points, uint16_t *d_order, const uint8_t *d_dst, int32_t *d_lines,
+                                int *d_nlines, unsigned *d_queue, cudaStream_t st) {
+    CK(cudaMemsetAsync(d_queue, 0, 8 * sizeof(unsigned), st));
+    if (tl) TL(*tl, 4, st);
+    ppht_order_kernel<<<T, 32, HOUGH_ORDER_CAP * 2, st>>>(T, HOUGH_ORDER_CAP, d_npoints, d_order);
+    // tier 1a: 2 CTAs/SM (2048 points, 90 KB table); tier 1b: 1 CTA/SM (4096 points, 184 KB table)
+    hough_smem_kernel<<<std::min(T, 2 * h->sm_count), HOUGH_THREADS, HOUGH_SMEM_SMALL + HOUGH_TABLE_BYTES_SMALL, st>>>(
+        hp, T, d_npoints, d_points, d_order, d_lines, d_nlines, d_queue, h->d_prof,
+        HOUGH_CAP_SMALL, HOUGH_TABLE_BYTES_SMALL, 0);
+    hough_smem_kernel<<<std::min(T, h->sm_count), HOUGH_THREADS, HOUGH_SMEM_LARGE + HOUGH_TABLE_BYTES, st>>>(
+        hp, T, d_npoints, d_points, d_order, d_lines, d_nlines, d_queue + 1, h->d_prof,
+        HOUGH_CAP_LARGE, HOUGH_TABLE_BYTES, 1);
+    if (tl) TL(*tl, 5, st);
+    hough_tier2_kernel<<<std::min(T, h->slots), HOUGH_THREADS, HOUGH_SMEM_BYTES, st>>>(
+        hp, T, d_npoints, d_points, h->d_accum, d_lines, d_nlines, h->d_prof, d_queue + 7);
+    if (!h->d_okeys) {  // tier-3 scratch, allocated once
+        if (cudaMalloc((void **)&h->d_okeys, (size_t)h->slots3 * h->HW * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMalloc((void **)&h->d_oidx, (size_t)h->slots3 * h->HW * sizeof(uint32_t)) != cudaSuccess)
+            return fail(MDB_ERR_NOMEM, "tier-3 scratch: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    hough_tier3_kernel<<<h->slots3, HOUGH_THREADS, H3_ORDER_SMEM, st>>>(hp, T, d_dst, h->d_okeys, h->d_oidx, h->d_accum,
+                                                                        h->d_bitmap, h->d_walk, d_lines, d_nlines,
+                                                                        d_queue + 2, h->d_prof);
+    CK(cudaGetLastError());
+    return MDB_OK;
+}
+
 static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
     CK(cudaStreamWaitEvent(h->stream3, c.ev_d1, 0));  // dst (stream2) has produced the on-pixel lists
     if (c.halo) {  // no results wanted: empty masks, no lines
@@ -511,27 +541,9 @@ static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
         CK(cudaEventRecord(c.ev_done, h->stream3));
         return MDB_OK;
     }
-    CK(cudaMemsetAsync(c.d_queue, 0, 8 * sizeof(unsigned), h->stream3));
-    TL(c, 4, h->stream3);
-    ppht_order_kernel<<<T, 32, HOUGH_ORDER_CAP * 2, h->stream3>>>(T, HOUGH_ORDER_CAP, c.d_npoints, c.d_order);
-    // tier 1a: 2 CTAs/SM (2048 points, 90 KB table); tier 1b: 1 CTA/SM (4096 points, 184 KB table)
-    hough_smem_kernel<<<std::min(T, 2 * h->sm_count), HOUGH_THREADS, HOUGH_SMEM_SMALL + HOUGH_TABLE_BYTES_SMALL, h->stream3>>>(
-        h->hp, T, c.d_npoints, c.d_points, c.d_order, c.d_lines, c.d_nlines, c.d_queue, h->d_prof,
-        HOUGH_CAP_SMALL, HOUGH_TABLE_BYTES_SMALL, 0);
-    hough_smem_kernel<<<std::min(T, h->sm_count), HOUGH_THREADS, HOUGH_SMEM_LARGE + HOUGH_TABLE_BYTES, h->stream3>>>(
-        h->hp, T, c.d_npoints, c.d_points, c.d_order, c.d_lines, c.d_nlines, c.d_queue + 1, h->d_prof,
-        HOUGH_CAP_LARGE, HOUGH_TABLE_BYTES, 1);
-    TL(c, 5, h->stream3);
-    hough_tier2_kernel<<<std::min(T, h->slots), HOUGH_THREADS, HOUGH_SMEM_BYTES, h->stream3>>>(
-        h->hp, T, c.d_npoints, c.d_points, h->d_accum, c.d_lines, c.d_nlines, h->d_prof, c.d_queue + 7);
-    if (!h->d_okeys) {  // tier-3 scratch, allocated once
-        if (cudaMalloc((void **)&h->d_okeys, (size_t)h->slots3 * h->HW * sizeof(uint32_t)) != cudaSuccess ||
-            cudaMalloc((void **)&h->d_oidx, (size_t)h->slots3 * h->HW * sizeof(uint32_t)) != cudaSuccess)
-            return fail(MDB_ERR_NOMEM, "tier-3 scratch: %s", cudaGetErrorString(cudaGetLastError()));
-    }
-    hough_tier3_kernel<<<h->slots3, HOUGH_THREADS, H3_ORDER_SMEM, h->stream3>>>(h->hp, T, c.d_dst, h->d_okeys, h->d_oidx, h->d_accum,
-                                                                   h->d_bitmap, h->d_walk, c.d_lines, c.d_nlines,
-                                                                   c.d_queue + 2, h->d_prof);
+    int rc = launch_hough_kernels(h, &c, h->hp, T, c.d_npoints, c.d_points, c.d_order, c.d_dst, c.d_lines, c.d_nlines, c.d_queue,
+                                  h->stream3);
+    if (rc) return rc;
     h->launches += 5;
     TL(c, 6, h->stream3);
     CK(cudaGetLastError());
@@ -549,7 +561,8 @@ static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
 }
 
 // ---- lineset_nms on the host (MetLib/utils.py:780-839) --------------------------------------
-static int nms_host(const int32_t *in, int n, int32_t *out, double *prob, const int32_t *given_order = nullptr) {
+static int nms_host(const int32_t *in, int n, int32_t *out, double *prob, const int32_t *given_order = nullptr,
+                    int *ties = nullptr) {
     std::vector<long long> len2(n), A(n), B(n), C(n), cx(n), cy(n);
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) {
@@ -568,6 +581,16 @@ static int nms_host(const int32_t *in, int n, int32_t *out, double *prob, const 
             if (len2[a] != len2[b]) return len2[a] > len2[b];
             return a > b;
         });
+    }
+    if (ties) {
+        *ties = 0;
+        if (given_order) {
+            std::vector<long long> l(len2);
+            std::sort(l.begin(), l.end());
+            for (int i = 1; i < n; i++) *ties |= l[i] == l[i - 1];
+        } else {
+            for (int i = 1; i < n; i++) *ties |= len2[order[i]] == len2[order[i - 1]];
+        }
     }
     std::vector<char> taken(n, 0);
     int k = 0;
@@ -645,8 +668,11 @@ static int finish_batch(mdb_detector *h, const BatchCtx &c, mdb_frame_info *info
         fi.n_raw = nraw;
         if (raw_lines && nraw) memcpy(raw_lines + (size_t)i * MDB_MAX_LINES * 4, src, (size_t)nraw * 16);
         fi.n_lines = 0;
-        if (nraw && lines && prob && h->cfg.detector == 0)
-            fi.n_lines = nms_host(src, nraw, lines + (size_t)i * MDB_MAX_LINES * 4, prob + (size_t)i * MDB_MAX_LINES);
+        if (nraw && lines && prob && h->cfg.detector == 0) {
+            int ties = 0;
+            fi.n_lines = nms_host(src, nraw, lines + (size_t)i * MDB_MAX_LINES * 4, prob + (size_t)i * MDB_MAX_LINES, nullptr, &ties);
+            fi.len_ties = ties;
+        }
         if (infos) infos[i] = fi;
     }
     return MDB_OK;
@@ -1104,6 +1130,117 @@ extern "C" int mdb_get_stack(mdb_handle h, uint8_t *max_out, uint8_t *mean_out, 
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(dmx); cudaFree(dmean); cudaFree(dsum);
     if (e != cudaSuccess) return fail(MDB_ERR_CUDA, "mdb_get_stack: %s", cudaGetErrorString(e));
+    return MDB_OK;
+}
+
+// SlidingWindow.sliding_window (MetLib/utils.py:263-265): the n ring slots in the reference's own slot order (slot i holds
+// the newest frame whose 0-based index is congruent to i modulo n; slots never written are zero).
+extern "C" int mdb_get_window(mdb_handle h, uint8_t *out, int on_device) {
+    if (!h || !out) return fail(MDB_ERR_INVALID, "mdb_get_window: null argument");
+    if (in_flight(h)) return fail(MDB_ERR_STATE, "mdb_get_window: a batch is in flight");
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = front_after_scalar(h);
+    if (rc) return rc;
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    uint8_t *tmp = nullptr;
+    for (int i = 0; i < h->n; i++) {
+        // newest frame index t <= timer-1 with t % n == i
+        long long t = h->timer - 1 - (((h->timer - 1 - i) % h->n + h->n) % h->n);
+        uint8_t *dst = out + (size_t)i * h->HW;
+        if (h->timer == 0 || t < 0) {
+            if (on_device) CK(cudaMemsetAsync(dst, 0, h->HW, h->stream));
+            else memset(dst, 0, h->HW);
+            continue;
+        }
+        const uint8_t *src = h->d_ring + (size_t)(t % h->R) * h->HW;
+        if (h->cfg.apply_mask) {
+            if (!tmp && !on_device) CK(cudaMalloc((void **)&tmp, h->HW));
+            uint8_t *m = on_device ? dst : tmp;
+            window_frame_kernel<<<592, 256, 0, h->stream>>>(src, h->d_mask, h->HW, m);
+            h->launches += 1;
+            src = m;
+        }
+        if (src != dst) {
+            cudaError_t e = cudaMemcpyAsync(dst, src, h->HW, kind, h->stream);
+            if (e != cudaSuccess) { cudaFree(tmp); return fail(MDB_ERR_CUDA, "mdb_get_window: %s", cudaGetErrorString(e)); }
+            if (tmp) cudaStreamSynchronize(h->stream);  // tmp is reused by the next slot
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(MDB_ERR_CUDA, "mdb_get_window: %s", cudaGetErrorString(e));
+    return MDB_OK;
+}
+
+// SlidingWindow.std for the uint8 / force_int mode (MetLib/utils.py:309-321)
+extern "C" int mdb_get_std(mdb_handle h, double *std_out) {
+    if (!h || !std_out) return fail(MDB_ERR_INVALID, "mdb_get_std: null argument");
+    if (h->timer == 0) return fail(MDB_ERR_STATE, "mdb_get_std: empty window");
+    if (in_flight(h)) return fail(MDB_ERR_STATE, "mdb_get_std: a batch is in flight");
+    CK(cudaSetDevice(h->cfg.device));
+    unsigned long long *d_tot = nullptr, tot = 0;
+    CK(cudaMalloc((void **)&d_tot, sizeof tot));
+    int rc = front_after_scalar(h);
+    cudaError_t e = rc ? cudaErrorUnknown : cudaMemsetAsync(d_tot, 0, sizeof tot, h->stream);
+    const int L = (int)std::min<long long>(h->n, h->timer);
+    if (e == cudaSuccess) {
+        // the reference's window holds unmasked frames unless the caller masked them: same source as mdb_get_stack
+        stack_std_kernel<<<592, 256, 0, h->stream>>>(frame_src(h, nullptr, 0), h->HW, h->n, h->timer - 1, L, d_tot);
+        h->launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_tot);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(MDB_ERR_CUDA, "mdb_get_std: %s", cudaGetErrorString(e));
+    volatile double mean = (double)tot / (double)h->HW;
+    *std_out = std::sqrt(mean);
+    return MDB_OK;
+}
+
+// every raw Hough segment of frame `frame` of the batch collected last.  The batched outputs hold MDB_MAX_LINES rows per
+// frame; ClassicDetector returns every segment without a cap (Detector.py:282-292), so a frame with more is resolved
+// here: its PPHT is run again (masks and on-pixel lists of the last batch are still on the device, the transform is
+// deterministic) into a buffer of the size the first pass counted.
+extern "C" int mdb_get_raw_lines(mdb_handle h, int frame, int32_t *out, int cap, int32_t *n_out) {
+    if (!h || !n_out || cap < 0 || (cap > 0 && !out)) return fail(MDB_ERR_INVALID, "mdb_get_raw_lines: bad arguments");
+    if (h->last_T < 1) return fail(MDB_ERR_STATE, "mdb_get_raw_lines: no detect has run yet");
+    if (in_flight(h)) return fail(MDB_ERR_STATE, "mdb_get_raw_lines: a batch is in flight");
+    if (frame < 0 || frame >= h->last_T) return fail(MDB_ERR_INVALID, "mdb_get_raw_lines: frame %d outside 0..%d", frame, h->last_T - 1);
+    BatchCtx &c = h->ctx[h->last_ctx];
+    const int nl = c.h_nlines[frame];
+    *n_out = nl;
+    if (nl <= 0 || cap == 0) return MDB_OK;
+    if (cap < nl) return fail(MDB_ERR_INVALID, "mdb_get_raw_lines: %d segments, room for %d", nl, cap);
+    if (nl <= MDB_MAX_LINES) {
+        memcpy(out, c.h_lines + (size_t)frame * MDB_MAX_LINES * 4, (size_t)nl * 16);
+        return MDB_OK;
+    }
+    CK(cudaSetDevice(h->cfg.device));
+    int32_t *d_l = nullptr;
+    int *d_n = nullptr;
+    unsigned *d_q = nullptr;
+    int got = 0;
+    cudaError_t e = cudaMalloc((void **)&d_l, (size_t)nl * 16);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_n, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_q, 8 * sizeof(unsigned));
+    int rc = MDB_OK;
+    if (e == cudaSuccess) {
+        HoughParams hp = h->hp;
+        hp.max_lines = nl;
+        rc = launch_hough_kernels(h, nullptr, hp, 1, c.d_npoints + frame, c.d_points + (size_t)frame * MDB_POINT_CAP,
+                                  c.d_order + (size_t)frame * HOUGH_ORDER_CAP, c.d_dst + (size_t)frame * h->HW, d_l, d_n, d_q,
+                                  h->stream3);
+        h->launches += 5;
+        if (!rc) e = cudaMemcpyAsync(out, d_l, (size_t)nl * 16, cudaMemcpyDeviceToHost, h->stream3);
+        if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(&got, d_n, sizeof got, cudaMemcpyDeviceToHost, h->stream3);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream3);
+    }
+    cudaFree(d_l); cudaFree(d_n); cudaFree(d_q);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(MDB_ERR_CUDA, "mdb_get_raw_lines: %s", cudaGetErrorString(e));
+    if (got != nl) return fail(MDB_ERR_STATE, "internal: second PPHT pass found %d segments, first pass %d", got, nl);
     return MDB_OK;
 }
 

@@ -25,7 +25,7 @@ PI = np.pi / 180.0  # MetLib/utils.py:22
 _SENS_CODE = {"low": 0, "normal": 1, "high": 2}
 _INFO_DTYPE = np.dtype([("timer", "<i8"), ("bi_threshold", "<i4"), ("n_on", "<i4"), ("bi_threshold_float", "<f8"),
                         ("snr", "<f8"), ("dst_sum", "<f8"), ("gap", "<f8"), ("lines_num", "<i4"), ("n_raw", "<i4"),
-                        ("n_lines", "<i4"), ("reserved", "<i4")])
+                        ("n_lines", "<i4"), ("len_ties", "<i4")])
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -54,12 +54,6 @@ def select_subarea(mask: np.ndarray, area: float) -> tuple[int, int, int, int]:
             break
         ratio = new_ratio
     return (r0, c0, r0 + sub_h, c0 + sub_w)
-
-
-def _len2_ties(lines: np.ndarray) -> bool:
-    d = lines[:, 2:].astype(np.int64) - lines[:, :2]
-    l2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]
-    return len(np.unique(l2)) != len(l2)
 
 
 def lineset_nms(lines: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
@@ -198,15 +192,17 @@ class _Engine:
 
 class SlidingWindow(object):
     """SlidingWindow (MetLib/utils.py:225-321) for uint8 frames, backed by the device frame ring:
-    `update`, `max`, `mean`, `sum`, `length`, `timer`, `cur_index`, `refresh_max`.
-    Only the reference's `dtype=np.uint8, force_int=True` mode (the one the detectors use,
-    Detector.py:53-57, :212-215) exists; anything else raises."""
+    `update`, `max`, `mean`, `sum`, `length`, `timer`, `cur_index`, `refresh_max`, `sliding_window`, `std`
+    (with `calc_std=True`).  Only the reference's `dtype=np.uint8, force_int=True` mode (the one the detectors
+    use, Detector.py:53-57, :212-215) exists; anything else raises."""
 
     def __init__(self, n: int, size: Sequence[int], dtype: type = np.uint8, force_int: bool = True,
                  calc_std: bool = False, device: int = 0) -> None:
-        if np.dtype(dtype) != np.uint8 or not force_int or calc_std:
-            raise NotImplementedError("device SlidingWindow supports dtype=uint8, force_int=True, "
-                                      "calc_std=False (the detector configuration)")
+        if np.dtype(dtype) != np.uint8 or not force_int:
+            # utils.py:248-252: other element types switch the sums to float64; every SlidingWindow the reference
+            # constructs (Detector.py:53-57, :67-71, :213-216, :536-539) is dtype=np.uint8, force_int=True
+            raise NotImplementedError("device SlidingWindow supports dtype=uint8, force_int=True (the mode of every "
+                                      "SlidingWindow the reference constructs); MetLib/utils.py:248-252 float mode is not built")
         if len(size) != 2:
             raise ValueError("size must be (H, W)")
         self.n = n
@@ -256,6 +252,25 @@ class SlidingWindow(object):
     def refresh_max(self) -> np.ndarray:
         return self.max
 
+    @property
+    def sliding_window(self) -> np.ndarray:
+        """The (n, H, W) ring in the reference's slot order (utils.py:263-265, :276-281); a read-back copy."""
+        return _window(self._eng, self.n)
+
+    @property
+    def std(self) -> float:
+        """utils.py:309-321, force_int branch."""
+        assert self.calc_std, "calc_std should be applied when initialized."
+        v = C.c_double()
+        check(self._eng.lib.mdb_get_std(self._eng.handle, C.byref(v)), "SlidingWindow.std")
+        return np.float64(v.value)
+
+
+def _window(eng: "_Engine", n: int) -> np.ndarray:
+    out = np.empty((n, eng.H, eng.W), np.uint8)
+    check(eng.lib.mdb_get_window(eng.handle, _ptr(out), 0), "sliding_window")
+    return out
+
 
 class SNR_SW(object):
     """View of the detector's main window with the attributes of SNR_SW (MetLib/Detector.py:34-127)
@@ -300,6 +315,11 @@ class SNR_SW(object):
     @property
     def sum(self):
         return self._stack(2)
+
+    @property
+    def sliding_window(self) -> np.ndarray:
+        """utils.py:263-265: the (n, H, W) ring in the reference's slot order (a read-back copy)."""
+        return _window(self._det._eng, self.n)
 
 
 class BaseDetector(metaclass=ABCMeta):
@@ -393,14 +413,18 @@ class ClassicDetector(LineDetector):
     def _result(self, i: int):
         eng = self._eng
         fi = eng.infos[i]
-        if fi.lines_num > MAX_LINES:
-            raise _lib.MetDetError(f"{fi.lines_num} Hough segments in one frame exceed the library's capacity of {MAX_LINES}")
         self.bi_threshold = fi.bi_threshold
         self.bi_threshold_float = fi.bi_threshold_float
         self._snr = fi.snr
         if fi.timer < self.stack_maxsize:
             return [], []  # fewer than four frames: LineDetector.detect() (Detector.py:222-223, :264-265)
-        lines = eng.raw[i, :fi.n_raw].copy() if fi.n_raw else []
+        if fi.lines_num > MAX_LINES:
+            # the reference returns every segment (Detector.py:282-292): fetch the frame's full list
+            lines = np.empty((fi.lines_num, 4), np.int32)
+            got = C.c_int32()
+            check(eng.lib.mdb_get_raw_lines(eng.handle, i, _ptr(lines), fi.lines_num, C.byref(got)), "raw lines")
+        else:
+            lines = eng.raw[i, :fi.n_raw].copy() if fi.n_raw else []
         cls_pred = np.zeros((len(lines), self.num_cls))
         cls_pred[:, 0] = 1
         return lines, cls_pred
@@ -498,16 +522,17 @@ class M3Detector(LineDetector):
         return out
 
     def _renms_if_tied(self, i: int, info=None):
-        """The library orders equal-length segments by descending index, which is what np.argsort(...)[::-1] yields
-        up to 16 segments (insertion sort).  Beyond that numpy's order among ties is its own: redo the NMS of such a
-        frame with numpy's order (lineset_nms above) so that the result is the reference's on this host."""
+        """The library orders equal-length segments by descending index.  The reference's order is
+        `np.argsort(length_sqr)[::-1]` (utils.py:804), and among EQUAL lengths numpy's result is its own business: an
+        insertion sort (descending index after the reversal) on some builds / CPUs, a SIMD sorting network with another
+        tie order on others (x86-simd-sort on AVX-512 / AVX2 hosts), whatever the segment count.  So every frame whose
+        raw segments tie in length has its NMS redone with numpy's order on this host (lineset_nms above): the result
+        is what the reference returns on the machine it runs on."""
         eng = self._eng
         fi = eng.infos[i]
-        if fi.n_raw <= 16 or fi.n_lines == 0:
+        if not fi.len_ties:  # set by the library's NMS pass (mdb_frame_info.len_ties)
             return
         raw = eng.raw[i, :fi.n_raw]
-        if not _len2_ties(raw):
-            return
         lines, prob = lineset_nms(raw)
         k = len(lines)
         eng.lines[i, :k] = lines

@@ -9,12 +9,12 @@ W, H, FPS, n, T = 256, 96, 30, 5, 24
 frames = synth.make_stream(T, W, H, FPS, speed_scale=3.0, thickness=2)
 mask = np.ones((H, W), np.uint8); mask[80:, :] = 0
 cfg = BinaryCfg(BinaryCoreCfg(True, 7, "normal", 0.2, 1), HoughLineCfg(8, 8, 6), DynamicCfg(True, 5))
-for mode in ("stream", "stream_dense_dst", "stream_strip_act", "temporal_v1", "generic"):
+for mode in ("stream", "temporal_v3", "stream_dense_dst", "stream_strip_act", "temporal_v1", "generic"):
     det = M3Detector(n / FPS + 1e-9, FPS, mask, 10, cfg, None, max_batch=8, apply_mask=True)
     det._eng.set_option("stream_kernel", int(mode != "generic"))
     det._eng.set_option("force_dense", int(mode == "stream_dense_dst"))
     det._eng.set_option("force_strip", int(mode == "stream_strip_act"))
-    det._eng.set_option("temporal_version", 1 if mode == "temporal_v1" else 2)
+    det._eng.set_option("temporal_version", 1 if mode == "temporal_v1" else 3 if mode == "temporal_v3" else 2)
     tot = 0
     for s in range(0, T, 8):
         res, dst = det.detect_many(frames[s:s + 8], return_dst=True)
@@ -30,6 +30,13 @@ det = M3Detector(n / FPS + 1e-9, FPS, mask, 10, cfg, None)
 for t in range(8):
     det.update(frames[t] * mask); det.detect()
 _ = det.dst, det.stack.max
+# temporal3 shapes: paged shared-memory ring (n = 30), long window (n = 60), two far-apart objects (two rho intervals)
+for nn in (30, 60):
+    fr = synth.make_stream(80, W, H, FPS, speed_scale=3.0, thickness=2)
+    d3 = M3Detector(nn / FPS + 1e-9, FPS, mask, 10, cfg, None, max_batch=40, apply_mask=True)
+    print("temporal3 n", nn, "lines", sum(len(r[0]) for s in range(0, 80, 40) for r in d3.detect_many(fr[s:s + 40])),
+          "generation", int(d3._eng.info("temporal_generation")))
+    d3.close()
 # dense frame -> tier 3
 rng = np.random.default_rng(0)
 dense = rng.integers(0, 60, (6, H, W)).astype(np.uint8)

@@ -173,10 +173,13 @@ def case_sliding_window():
     n, shape, T = 4, (5, 7), 11
     sw = SlidingWindow(n, shape, np.uint8, force_int=True)
     xs = rng.integers(0, 256, (T,) + shape, dtype=np.uint8)
-    means, maxs, sums, lens = [], [], [], []
+    sw_std = SlidingWindow(n, shape, np.uint8, force_int=True, calc_std=True)  # utils.py:309-321, integer branch
+    means, maxs, sums, lens, rings, stds = [], [], [], [], [], []
     for t in range(T):
         sw.update(xs[t])
+        sw_std.update(xs[t])
         means.append(sw.mean.copy()); maxs.append(sw.max.copy()); sums.append(sw.sum.copy()); lens.append(sw.length)
+        rings.append(sw.sliding_window.copy()); stds.append(float(sw_std.std))
     e = EMA(momentum=1 - 2 / 60, warmup_speed=25)
     vals = rng.uniform(0.2, 3, 40)
     ev = []
@@ -198,6 +201,7 @@ def case_sliding_window():
         masks.append(np.packbits(m, axis=None))
     np.savez_compressed(os.path.join(HERE, "sliding_window.npz"), xs=xs, n=n, mean=np.stack(means),
                         max=np.stack(maxs), sum=np.stack(sums), length=np.array(lens),
+                        ring=np.stack(rings), std=np.array(stds),
                         ema_in=vals, ema_out=np.array(ev), ema_momentum=1 - 2 / 60, ema_warmup=25,
                         rois=np.stack(rois), roi_mask_shapes=np.array([(120 + 17 * k, 200 + 31 * k) for k in range(4)]),
                         roi_areas=np.array([0.1 + 0.05 * k for k in range(4)]),

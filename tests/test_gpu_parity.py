@@ -324,15 +324,49 @@ def test_dense_mask_overflow_path_and_too_many_lines(thr, lo, hi):
 def test_sliding_window_class_golden():
     from metdetpy_b200.detector import SlidingWindow
     g = np.load(os.path.join(GOLDEN, "sliding_window.npz"))
-    sw = SlidingWindow(int(g["n"]), g["xs"].shape[1:], np.uint8, force_int=True)
+    sw = SlidingWindow(int(g["n"]), g["xs"].shape[1:], np.uint8, force_int=True, calc_std=True)
+    assert np.array_equal(sw.sliding_window, np.zeros_like(g["ring"][0]))
     for t, x in enumerate(g["xs"]):
         sw.update(x)
         assert sw.length == g["length"][t] and sw.timer == t + 1
         assert np.array_equal(sw.mean, g["mean"][t]) and sw.mean.dtype == np.uint8
         assert np.array_equal(sw.max, g["max"][t])
         assert np.array_equal(sw.sum, g["sum"][t])
+        assert np.array_equal(sw.sliding_window, g["ring"][t])  # utils.py:263-265, the reference's slot order
+        assert sw.std == g["std"][t]                            # utils.py:309-321, integer branch
     with pytest.raises(NotImplementedError):
         SlidingWindow(3, (4, 4), float)
+    with pytest.raises(AssertionError):
+        SlidingWindow(3, (4, 4), np.uint8).std
+
+
+def test_window_longer_than_255_frames_against_oracle():
+    """The reference has no limit on int(window_sec * fps) (Detector.py:197): n = 300 runs the generic kernel."""
+    from metdetpy_b200 import BinaryCfg, BinaryCoreCfg, DynamicCfg, HoughLineCfg, synth
+    from metdetpy_b200.detector import M3Detector
+    from oracle import m3_oracle as O
+    W, H, n, T, B = 64, 48, 300, 340, 64
+    frames = synth.make_stream(T, W, H, 30.0, speed_scale=2.0, thickness=2)
+    mask = np.ones((H, W), np.uint8)
+    kw = dict(adaptive=True, init_value=7, sensitivity="normal", area=0.2, interval=2, hough=(6, 6, 4), dy_mask=True)
+    ref = O.M3DetectorOracle(n / 30.0 + 1e-9, 30.0, mask, 10, backend="numpy", **kw)
+    cfg = BinaryCfg(BinaryCoreCfg(True, 7, "normal", 0.2, 2), HoughLineCfg(6, 6, 4), DynamicCfg(True, 5))
+    det = M3Detector(n / 30.0 + 1e-9, 30.0, mask, 10, cfg, None, max_batch=B)
+    assert det.stack_maxsize == n
+    for s0 in range(0, T, B):
+        res, dst = det.detect_many(frames[s0:s0 + B], return_dst=True)
+        for i in range(len(res)):
+            t = s0 + i
+            ref.update(frames[t]); rl, rc = ref.detect()
+            info = det.last_infos[i]
+            assert info["bi_threshold"] == ref.bi_threshold, t
+            assert info["snr"] == pytest.approx(float(ref.stack.snr), rel=1e-12, abs=0), t
+            assert np.array_equal(dst[i], ref.dst), (t, int(np.count_nonzero(dst[i] != ref.dst)))
+            raw = np.asarray(ref.linesp_ext).reshape(-1, 4)
+            assert_nms_equivalent(res[i][0], res[i][1][:, -1], rl, rc[:, -1], raw, t)
+    assert np.array_equal(det.stack.max, ref.stack.max) and np.array_equal(det.stack.mean, ref.stack.mean)
+    assert np.array_equal(det.stack.sliding_window, ref.stack.sliding_window)
+    det.close()
 
 
 def test_max_stack_and_merge():

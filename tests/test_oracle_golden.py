@@ -112,6 +112,8 @@ def test_sliding_window_ema_roi_golden():
         assert np.array_equal(sw.mean, g["mean"][t]) and sw.mean.dtype == np.uint8
         assert np.array_equal(sw.max, g["max"][t])
         assert np.array_equal(sw.sum, g["sum"][t])
+        assert np.array_equal(sw.sliding_window, g["ring"][t])
+        assert sw.std == g["std"][t]
     e = O.EMA(float(g["ema_momentum"]), float(g["ema_warmup"]))
     for v, r in zip(g["ema_in"], g["ema_out"]):
         e.update(v)
