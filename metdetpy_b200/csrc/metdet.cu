@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "hough.cuh"
 #include "classic.cuh"
+#include "perframe_kernel.cuh"
 #include "kernels_basic.cuh"
 #include "preproc.cuh"
 #include "stream_kernel.cuh"
@@ -69,6 +70,10 @@ struct BatchCtx {
     cudaEvent_t ev_thr = nullptr;    // thresholds of this batch are on the device (scalar stream)
     cudaEvent_t ev_src = nullptr;    // the scalar stream is done with this batch's frames (noise samples, history copy)
     cudaEvent_t tl[12] = {};         // optional timeline marks (debug)
+    // thr_float | snr | thr | nlines | npoints | queue | lines live in ONE device block and one pinned mirror, so that a
+    // batch's results come back in a single copy (the pointers above point into these)
+    uint8_t *d_res = nullptr, *h_res = nullptr;
+    size_t res_head = 0;  // bytes in front of the line rows
     int T = 0;  // 0: free
     int bits_parity = 0;  // which predicate-bit buffer this batch uses
     bool halo = false;    // results not wanted (look-back frames of a time-sharded run): no dst, no Hough
@@ -118,6 +123,13 @@ struct mdb_detector {
     int fused_launches = 0, last_fused_launches = 0;
     HoughParams hp;
     int use_stream_kernel = 1;
+    // per-frame O(1) path (perframe_kernel.cuh): resident window state, valid for `pf_timer` frames seen
+    int per_frame_fast = 1;
+    uint16_t *d_pf_sum = nullptr;
+    uint8_t *d_pf_pmax = nullptr, *d_pf_suf = nullptr, *d_pf_stage = nullptr;
+    long long pf_timer = -1;         // frames the state has absorbed (-1: rebuild from the ring before use)
+    long long pf_bits_timer = -1;    // the predicate bits in sk.d_bits belong to frame pf_bits_timer - 1
+    bool pf_suffix_pending = false;  // the block that just ended still needs its suffix planes
     int timeline = 0;                // debug: record per-kernel timeline events
     cudaEvent_t tl_base = nullptr;
 };
@@ -165,18 +177,19 @@ static void free_all(mdb_detector *h) {
     if (h->sstream) cudaStreamSynchronize(h->sstream);
     if (h->h_noise2) cudaFreeHost(h->h_noise2);
     void *dev[] = {h->d_ring, h->d_mask, h->d_stage[0], h->d_stage[1], h->d_act, h->d_state, h->d_noise, h->d_noise2, h->d_accum,
-                   h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_prof, h->d_cbits};
+                   h->d_bitmap, h->d_walk, h->d_okeys, h->d_oidx, h->d_prof, h->d_cbits, h->d_pf_sum, h->d_pf_pmax, h->d_pf_suf,
+                   h->d_pf_stage};
     for (void *p : dev)
         if (p) cudaFree(p);
     for (BatchCtx &c : h->ctx) {
-        void *cd[] = {c.d_thr, c.d_thrf, c.d_snr, c.d_dst, c.d_dstbits, c.d_npoints, c.d_points, c.d_order, c.d_queue,
-                      c.d_lines, c.d_nlines, c.d_alist, c.d_acount, c.d_wlist, c.d_wcount, c.d_dense};
+        void *cd[] = {c.d_res, c.d_dst, c.d_dstbits, c.d_points, c.d_order, c.d_alist, c.d_acount, c.d_wlist, c.d_wcount,
+                      c.d_dense};
         for (void *p : cd)
             if (p) cudaFree(p);
     }
     stream_state_free(h->sk);
     for (BatchCtx &c : h->ctx) {
-        void *pin[] = {c.h_thr, c.h_nlines, c.h_thrf, c.h_snr, c.h_npoints, c.h_lines, c.h_tiers};
+        void *pin[] = {c.h_res};
         for (void *p : pin)
             if (p) cudaFreeHost(p);
         if (c.ev_f0) cudaEventDestroy(c.ev_f0);
@@ -305,16 +318,27 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     ALLOC(h->d_noise, (size_t)T * 2 * sizeof(unsigned long long));
     for (int k = 0; k < NCTX; k++) {
         BatchCtx &c = h->ctx[k];
-        ALLOC(c.d_thr, T * sizeof(int));
-        ALLOC(c.d_thrf, T * sizeof(double));
-        ALLOC(c.d_snr, T * sizeof(double));
         ALLOC(c.d_dst, (size_t)T * h->HW);
-        ALLOC(c.d_npoints, T * sizeof(unsigned));
         ALLOC(c.d_points, (size_t)T * MDB_POINT_CAP * sizeof(uint32_t));
         ALLOC(c.d_order, (size_t)T * HOUGH_ORDER_CAP * sizeof(uint16_t));
-        ALLOC(c.d_queue, 8 * sizeof(unsigned));  // [0..2] work-queue heads of tiers 1a, 1b, 3; [4..7] frames resolved by tiers 1a, 1b, 3, 2
-        ALLOC(c.d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t));
-        ALLOC(c.d_nlines, T * sizeof(int));
+        {   // result block: [thr_float T][snr T][thr T][nlines T][npoints T][queue 8][pad][lines T*MDB_MAX_LINES*4]
+            const size_t o_thrf = 0, o_snr = o_thrf + (size_t)T * 8, o_thr = o_snr + (size_t)T * 8, o_nl = o_thr + (size_t)T * 4,
+                         o_np = o_nl + (size_t)T * 4, o_q = o_np + (size_t)T * 4;
+            c.res_head = (o_q + 8 * sizeof(unsigned) + 15) / 16 * 16;
+            const size_t total = c.res_head + (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t);
+            ALLOC(c.d_res, total);
+            CKH(cudaMemsetAsync(c.d_res, 0, total, h->stream));
+            CKH(cudaHostAlloc((void **)&c.h_res, total, cudaHostAllocDefault));
+            memset(c.h_res, 0, total);
+            c.d_thrf = (double *)(c.d_res + o_thrf); c.h_thrf = (double *)(c.h_res + o_thrf);
+            c.d_snr = (double *)(c.d_res + o_snr);   c.h_snr = (double *)(c.h_res + o_snr);
+            c.d_thr = (int *)(c.d_res + o_thr);      c.h_thr = (int *)(c.h_res + o_thr);
+            c.d_nlines = (int *)(c.d_res + o_nl);    c.h_nlines = (int *)(c.h_res + o_nl);
+            c.d_npoints = (unsigned *)(c.d_res + o_np); c.h_npoints = (unsigned *)(c.h_res + o_np);
+            // queue: [0..2] work-queue heads of tiers 1a, 1b, 3; [4..7] frames resolved by tiers 1a, 1b, 3, 2
+            c.d_queue = (unsigned *)(c.d_res + o_q);  c.h_tiers = (unsigned *)(c.h_res + o_q) + 4;
+            c.d_lines = (int32_t *)(c.d_res + c.res_head); c.h_lines = (int32_t *)(c.h_res + c.res_head);
+        }
         CKH(cudaMemsetAsync(c.d_dst, 0, (size_t)T * h->HW, h->stream));
         ALLOC(c.d_dstbits, (size_t)T * h->H * h->Wb * sizeof(uint32_t));
         CKH(cudaMemsetAsync(c.d_dstbits, 0, (size_t)T * h->H * h->Wb * sizeof(uint32_t), h->stream));
@@ -339,14 +363,6 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     CKH(cudaMemsetAsync(h->d_bitmap, 0, (size_t)h->slots3 * bm_words * sizeof(uint32_t), h->stream));
     CKH(cudaMemcpyAsync(h->d_mask, mask, h->HW, cudaMemcpyHostToDevice, h->stream));
     for (BatchCtx &c : h->ctx) {
-        CKH(cudaHostAlloc((void **)&c.h_thr, T * sizeof(int), cudaHostAllocDefault));
-        CKH(cudaHostAlloc((void **)&c.h_nlines, T * sizeof(int), cudaHostAllocDefault));
-        CKH(cudaHostAlloc((void **)&c.h_thrf, T * sizeof(double), cudaHostAllocDefault));
-        CKH(cudaHostAlloc((void **)&c.h_snr, T * sizeof(double), cudaHostAllocDefault));
-        CKH(cudaHostAlloc((void **)&c.h_npoints, T * sizeof(unsigned), cudaHostAllocDefault));
-        CKH(cudaHostAlloc((void **)&c.h_tiers, 4 * sizeof(unsigned), cudaHostAllocDefault));
-        memset(c.h_tiers, 0, 4 * sizeof(unsigned));
-        CKH(cudaHostAlloc((void **)&c.h_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t), cudaHostAllocDefault));
         CKH(cudaEventCreate(&c.ev_f0));
         CKH(cudaEventCreate(&c.ev_f1));
         CKH(cudaEventCreate(&c.ev_d0));
@@ -431,7 +447,8 @@ static int launch_noise_thr(mdb_detector *h, BatchCtx &bc, const FrameSrc &src, 
 
 // fused mask chain for frames i = 0..T-1 of the batch (global index timer0 + i): temporal pass on the
 // front stream, dst on the back stream
-static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T, long long timer0, long long dy0) {
+static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T, long long timer0, long long dy0,
+                        bool bits_ready = false) {
     CK(cudaMemsetAsync(c.d_npoints, 0, T * sizeof(unsigned), h->stream2));
     CK(cudaEventRecord(c.ev_f0, h->stream));
     int nl = 0;
@@ -470,7 +487,8 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
         sl.alist = c.d_alist; sl.acount = c.d_acount; sl.wlist = c.d_wlist; sl.wcount = c.d_wcount; sl.dense = c.d_dense;
         int rc = stream_kernel_launch(h->sk, src, timer0, dy0, T, h->cfg.dy_mask, c.d_thr, act_ring(h),
                                       c.d_dst, c.d_dstbits, c.d_npoints, c.d_points, MDB_POINT_CAP, sl, h->stream,
-                                      h->stream2, c.ev_f1, c.ev_d0, (int)(c.bits_parity & 1), &nl, c.halo);
+                                      h->stream2, c.ev_f1, c.ev_d0, bits_ready ? 0 : (int)(c.bits_parity & 1), &nl, c.halo,
+                                      bits_ready);
         if (rc != 0) return fail(MDB_ERR_CUDA, "stream kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
         // generic per-frame kernel: the whole chain runs on the back stream, after the front stream's thresholds
@@ -533,11 +551,8 @@ static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
         memset(c.h_tiers, 0, 4 * sizeof(unsigned));
         CK(cudaMemsetAsync(c.d_npoints, 0, T * sizeof(unsigned), h->stream3));
         CK(cudaMemsetAsync(c.d_nlines, 0, T * sizeof(int), h->stream3));
-        CK(cudaMemcpyAsync(c.h_thr, c.d_thr, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream3));
-        CK(cudaMemcpyAsync(c.h_thrf, c.d_thrf, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream3));
-        CK(cudaMemcpyAsync(c.h_snr, c.d_snr, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream3));
-        CK(cudaMemcpyAsync(c.h_npoints, c.d_npoints, T * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream3));
-        CK(cudaMemcpyAsync(c.h_nlines, c.d_nlines, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream3));
+        CK(cudaMemsetAsync(c.d_queue, 0, 8 * sizeof(unsigned), h->stream3));
+        CK(cudaMemcpyAsync(c.h_res, c.d_res, c.res_head, cudaMemcpyDeviceToHost, h->stream3));  // scalars only
         CK(cudaEventRecord(c.ev_done, h->stream3));
         return MDB_OK;
     }
@@ -547,14 +562,9 @@ static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
     h->launches += 5;
     TL(c, 6, h->stream3);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c.h_thr, c.d_thr, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream3));
-    CK(cudaMemcpyAsync(c.h_thrf, c.d_thrf, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream3));
-    CK(cudaMemcpyAsync(c.h_snr, c.d_snr, T * sizeof(double), cudaMemcpyDeviceToHost, h->stream3));
-    CK(cudaMemcpyAsync(c.h_tiers, c.d_queue + 4, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream3));
-    CK(cudaMemcpyAsync(c.h_npoints, c.d_npoints, T * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream3));
-    CK(cudaMemcpyAsync(c.h_nlines, c.d_nlines, T * sizeof(int), cudaMemcpyDeviceToHost, h->stream3));
-    CK(cudaMemcpyAsync(c.h_lines, c.d_lines, (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t),
-                       cudaMemcpyDeviceToHost, h->stream3));
+    // one copy brings back the scalars of the whole batch and the line rows of its T frames
+    CK(cudaMemcpyAsync(c.h_res, c.d_res, c.res_head + (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                       h->stream3));
     CK(cudaEventRecord(c.ev_done, h->stream3));
     TL(c, 7, h->stream3);
     return MDB_OK;
@@ -689,12 +699,84 @@ static int front_after_scalar(mdb_detector *h) {
 }
 
 // ---- per-frame API ---------------------------------------------------------------------------
+// the per-frame O(1) path serves M3 handles the streaming kernels serve (W % 32 == 0, 2 <= n <= 128)
+static bool pf_usable(const mdb_detector *h) {
+    return h->per_frame_fast && h->cfg.detector == 0 && h->sk.ok && h->use_stream_kernel;
+}
+
+static int pf_launch_suffix(mdb_detector *h) {
+    // block b .. b+n-1 just ended (timer = b + n): SUF[j] = max(x[b+j .. b+n-1]), j = n-1 .. 1
+    const size_t groups = h->HW / 16;
+    const unsigned grid = (unsigned)((groups + PF_THREADS - 1) / PF_THREADS);
+    const long long hi = h->timer - 1, lo = h->timer - h->n + 1;
+    const FrameSrc src = frame_src(h, nullptr, 0);
+    if (src.mask) pf_suffix_kernel<true><<<grid, PF_THREADS, 0, h->stream>>>(src, hi, lo, h->n - 1, h->d_pf_suf, groups);
+    else pf_suffix_kernel<false><<<grid, PF_THREADS, 0, h->stream>>>(src, hi, lo, h->n - 1, h->d_pf_suf, groups);
+    h->launches += 1;
+    h->pf_suffix_pending = false;
+    CK(cudaGetLastError());
+    return MDB_OK;
+}
+
+static int pf_update(mdb_detector *h, const uint8_t *frame, int on_device) {
+    const size_t groups = h->HW / 16;
+    const unsigned grid = (unsigned)((groups + PF_THREADS - 1) / PF_THREADS);
+    if (!h->d_pf_sum) {
+        if (cudaMalloc((void **)&h->d_pf_sum, h->HW * sizeof(uint16_t)) != cudaSuccess ||
+            cudaMalloc((void **)&h->d_pf_pmax, h->HW) != cudaSuccess ||
+            cudaMalloc((void **)&h->d_pf_suf, (size_t)h->n * h->HW) != cudaSuccess ||
+            cudaMalloc((void **)&h->d_pf_stage, h->HW) != cudaSuccess)
+            return fail(MDB_ERR_NOMEM, "per-frame window state: %s", cudaGetErrorString(cudaGetLastError()));
+        h->pf_timer = -1;
+    }
+    if (h->pf_suffix_pending && h->pf_timer == h->timer) {
+        int rc = pf_launch_suffix(h);
+        if (rc) return rc;
+    }
+    if (h->pf_timer != h->timer) {  // batched calls, reset or seek moved the stream on: rebuild from the ring
+        const FrameSrc src = frame_src(h, nullptr, 0);
+        if (src.mask) pf_rebuild_kernel<true><<<grid, PF_THREADS, 0, h->stream>>>(src, h->timer, h->n, h->d_pf_sum, h->d_pf_pmax, h->d_pf_suf, groups);
+        else pf_rebuild_kernel<false><<<grid, PF_THREADS, 0, h->stream>>>(src, h->timer, h->n, h->d_pf_sum, h->d_pf_pmax, h->d_pf_suf, groups);
+        h->launches += 1;
+        h->pf_suffix_pending = false;
+        CK(cudaGetLastError());
+    }
+    const long long t = h->timer;
+    CK(cudaMemcpyAsync(h->d_pf_stage, frame, h->HW, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    // noise sample + threshold of this frame: newest frame from the staging buffer, older ones from the ring
+    int rc = launch_noise_thr(h, h->ctx[0], frame_src(h, h->d_pf_stage, t), 1, t, h->stream);
+    if (rc) return rc;
+    const int pos = (int)(t % h->n);
+    const int L = (int)std::min<long long>(h->n, t + 1);
+    uint8_t *slot = h->d_ring + (size_t)(t % h->R) * h->HW;
+    const uint8_t *old = t >= h->n ? h->d_ring + (size_t)((t - h->n) % h->R) * h->HW : nullptr;
+    // window = prefix of the current block + suffix [pos+1 ..] of the previous one (none for the block's last frame)
+    const uint8_t *suf = (pos < h->n - 1) ? h->d_pf_suf + (size_t)(pos + 1) * h->HW : nullptr;
+    uint16_t *bits = reinterpret_cast<uint16_t *>(h->sk.d_bits);
+    if (h->cfg.apply_mask)
+        pf_update_kernel<true><<<grid, PF_THREADS, 0, h->stream>>>(h->d_pf_stage, slot, old, h->d_mask, h->d_pf_sum, h->d_pf_pmax, suf,
+                                                                  pos == 0, L, h->ctx[0].d_thr, groups, bits);
+    else
+        pf_update_kernel<false><<<grid, PF_THREADS, 0, h->stream>>>(h->d_pf_stage, slot, old, nullptr, h->d_pf_sum, h->d_pf_pmax, suf,
+                                                                   pos == 0, L, h->ctx[0].d_thr, groups, bits);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    h->timer += 1;
+    h->pf_timer = h->pf_bits_timer = h->timer;
+    h->pf_suffix_pending = pos == h->n - 1;
+    h->front_dirty = true;
+    return MDB_OK;
+}
+
 extern "C" int mdb_update(mdb_handle h, const uint8_t *frame, int on_device) {
     if (!h || !frame) return fail(MDB_ERR_INVALID, "mdb_update: null argument");
     if (in_flight(h)) return fail(MDB_ERR_STATE, "mdb_update: a submitted batch has not been collected");
     CK(cudaSetDevice(h->cfg.device));
     int rc = front_after_scalar(h);
     if (rc) return rc;
+    // O(1) path: the copy is asynchronous.  A pageable source has been consumed when cudaMemcpyAsync returns (the
+    // runtime stages it); a pinned source must stay untouched until the next detect() / update() returns.
+    if (pf_usable(h)) return pf_update(h, frame, on_device);
     rc = copy_to_ring(h, frame, 0, 1, h->timer, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream);
     if (rc) return rc;
     rc = launch_noise_thr(h, h->ctx[0], frame_src(h, nullptr, 0), 1, h->timer, h->stream);
@@ -715,10 +797,16 @@ extern "C" int mdb_detect(mdb_handle h, mdb_frame_info *info, int32_t *lines, do
     int rc = front_after_scalar(h);  // the history copy of the last batch runs on the scalar stream
     if (rc) return rc;
     c.halo = false;
-    rc = launch_fused(h, c, frame_src(h, nullptr, 0), 1, h->timer - 1, h->dy_timer);
+    // update() of this frame already left its predicate bits behind (per-frame O(1) path): spatial passes only
+    const bool bits_ready = pf_usable(h) && h->pf_bits_timer == h->timer;
+    rc = launch_fused(h, c, frame_src(h, nullptr, 0), 1, h->timer - 1, h->dy_timer, bits_ready);
     if (rc) return rc;
     rc = launch_hough_and_copy(h, c, 1);
     if (rc) return rc;
+    if (h->pf_suffix_pending && h->pf_timer == h->timer) {  // behind this frame's chain, beside its Hough pass
+        rc = pf_launch_suffix(h);
+        if (rc) return rc;
+    }
     CK(cudaStreamSynchronize(h->stream3));
     {
         float a = 0.f, b = 0.f;
@@ -1287,7 +1375,7 @@ extern "C" int mdb_get_info(mdb_handle h, const char *name, double *value) {
 // [8] = ev_d0 (dst start)
 extern "C" int mdb_debug_timeline(mdb_handle h, float *out) {
     if (!h || !out || !h->timeline) return fail(MDB_ERR_INVALID, "mdb_debug_timeline: not enabled");
-    BatchCtx &c = h->ctx[(h->collected + NCTX - 1) % NCTX];
+    BatchCtx &c = h->ctx[h->last_ctx];  // the batch collected last / the per-frame context
     cudaEvent_t ev[9] = {c.tl[0], c.tl[1], c.ev_f0, c.ev_f1, c.tl[4], c.tl[5], c.tl[6], c.tl[7], c.ev_d0};
     for (int i = 0; i < 9; i++)
         if (cudaEventElapsedTime(&out[i], h->tl_base, ev[i]) != cudaSuccess) { cudaGetLastError(); out[i] = -1.f; }
@@ -1311,6 +1399,7 @@ extern "C" int mdb_set_option(mdb_handle h, const char *name, int value) {
         return MDB_OK;
     }
     if (!strcmp(name, "stream_kernel")) { h->use_stream_kernel = value; return MDB_OK; }
+    if (!strcmp(name, "per_frame_fast")) { h->per_frame_fast = value; h->pf_timer = h->pf_bits_timer = -1; return MDB_OK; }
     if (!strcmp(name, "timeline")) {
         if (value && !h->tl_base) {
             for (BatchCtx &c : h->ctx)
@@ -1338,6 +1427,8 @@ extern "C" int mdb_set_option(mdb_handle h, const char *name, int value) {
     if (!strcmp(name, "force_strip")) { h->sk.force_strip = value; return MDB_OK; }
     if (!strcmp(name, "sp_rows")) { h->sk.sp_rows = value; return MDB_OK; }
     if (!strcmp(name, "dst_rows")) { h->sk.dst_rows = value; return MDB_OK; }
+    if (!strcmp(name, "sp_rows_single")) { h->sk.sp_rows_single = value > 0 ? value : 8; return MDB_OK; }
+    if (!strcmp(name, "single_dense")) { h->sk.single_dense = value; return MDB_OK; }
     if (!strcmp(name, "temporal_wpt")) {
         if (!h->sk.ok || stream_state_config(h->sk, value) != 0)
             return fail(MDB_ERR_INVALID, "mdb_set_option: temporal_wpt=%d not possible here", value);

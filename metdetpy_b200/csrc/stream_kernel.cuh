@@ -38,6 +38,8 @@ struct StreamState {
     int t_kdiv = 1;         // temporal2: sub-blocks per window (divides n)
     int t_kdiv_req = 0;     // test hook: force this many sub-blocks (0 = choose)
     int dst_rows = 32;      // output rows per warp strip in dst_dense_kernel
+    int sp_rows_single = 8; // act4 band height when the batch is one frame
+    int single_dense = 0;   // one-frame batches take the full-scan dst kernel (measured slower than the list walk: off)
     int force_dense = 0;    // test hook: dst of every frame by the full-scan kernel
     int force_strip = 0;    // test hook: act by the warp-strip kernel even when W % 128 == 0
     size_t t_smem_per_thread = 0;
@@ -354,7 +356,7 @@ static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long t
                                        int dy_on, const int *d_thr, ActRing ring, uint8_t *dst, uint32_t *dstbits,
                                        unsigned *npoints, uint32_t *points, int cap, SparseLists sl, cudaStream_t st1,
                                        cudaStream_t st2, cudaEvent_t ev_f1, cudaEvent_t ev_d0, int parity,
-                                       int *launches, bool act_only = false) {
+                                       int *launches, bool act_only = false, bool skip_temporal = false) {
     uint32_t *const bits = parity ? s.d_bits2 : s.d_bits;
     const int HWG = (int)((size_t)s.W * s.H / (4 * s.t_wpt));  // pixel groups = threads
     const int nt = s.t_threads;
@@ -362,11 +364,13 @@ static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long t
     const int grid = (HWG + nt - 1) / nt;
     uint8_t *bits8 = reinterpret_cast<uint8_t *>(bits);
     int t3rc = -2;
-    if (s.t_version == 3) {
+    if (skip_temporal) {  // the predicate bits are already in the buffer (per-frame O(1) path, perframe_kernel.cuh)
+        t3rc = 0;
+    } else if (s.t_version == 3) {
         t3rc = temporal3_launch(s.n, s.t3_variant, src, timer0, T, (int)((size_t)s.W * s.H / 8), d_thr, bits8, s.t3tab, parity, st1);
         if (t3rc == -1) return -1;
     }
-    s.t_last = t3rc == 0 ? 3 : (s.t_version == 1 ? 1 : 2);
+    s.t_last = skip_temporal ? 4 : t3rc == 0 ? 3 : (s.t_version == 1 ? 1 : 2);
     if (t3rc == 0) {
     } else if (s.t_version != 1) {
 #define T2_LAUNCH(M, WP, NT)                                                                                            \
@@ -399,9 +403,11 @@ static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long t
     const int Wb = s.W / 32;
     const int strips = (Wb + SP_USE - 1) / SP_USE;
     if (Wb % 4 == 0 && !s.force_strip) {
-        const int chunks = Wb / 4, bands = (s.H + s.sp_rows - 1) / s.sp_rows;
+        // a single frame (per-frame API) is latency-bound: short bands give the one frame enough CTAs to cover the SMs
+        const int rows = T == 1 ? s.sp_rows_single : s.sp_rows;
+        const int chunks = Wb / 4, bands = (s.H + rows - 1) / rows;
         dim3 g((chunks * bands + A4_THREADS - 1) / A4_THREADS, T);
-        act4_kernel<<<g, A4_THREADS, 0, st2>>>(bits, s.H, Wb, s.sp_rows, chunks, bands, ring, dy0, sl);
+        act4_kernel<<<g, A4_THREADS, 0, st2>>>(bits, s.H, Wb, rows, chunks, bands, ring, dy0, sl);
     } else {
         const int bands = (s.H + s.sp_rows - 1) / s.sp_rows;
         dim3 g((strips * bands + SP_WARPS - 1) / SP_WARPS, T);
@@ -413,7 +419,7 @@ static inline int stream_kernel_launch(StreamState &s, FrameSrc src, long long t
         return 0;
     }
     if (cudaMemsetAsync(sl.dense, 0, sizeof(unsigned), st2) != cudaSuccess) return -1;
-    if (s.force_dense) {  // test hook: every frame takes the full-scan path
+    if (s.force_dense || (T == 1 && s.single_dense)) {  // test hooks: every frame takes the full-scan path
         dst_force_dense_kernel<<<(T + 127) / 128, 128, 0, st2>>>(T, sl);
     } else {
         dst_sparse_kernel<<<T, 256, 0, st2>>>(ring, s.W, s.H, s.n, dy0, dy_on, dst, dstbits, npoints, points, cap, sl);

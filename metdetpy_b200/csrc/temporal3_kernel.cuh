@@ -69,6 +69,10 @@ T3_HD const uint8_t *addr(const uint8_t *base, unsigned idx, unsigned stride) {
 T3_HD unsigned bits8(unsigned m0, unsigned m1) {
     return (unsigned)__dp4a((int)m1, (int)0x80C0E0F0, __dp4a((int)m0, (int)0xF8FCFEFF, 0));
 }
+// the same with per-thread weights (a weight of 0 drops a masked-out pixel)
+T3_HD unsigned bits8w(unsigned m0, unsigned m1, unsigned w0, unsigned w1) {
+    return (unsigned)__dp4a((int)m1, (int)w1, __dp4a((int)m0, (int)w0, 0));
+}
 // ---- bulk-copy feed (FEED = 1): cp.async.bulk global -> shared, completion on an mbarrier (UBLKCP + SYNCS in SASS)
 T3_HD uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 T3_HD void mbar_init(uint32_t bar, unsigned count) {
@@ -127,6 +131,14 @@ T3_HD unsigned bits8(unsigned m0, unsigned m1) {
     for (int k = 0; k < 4; k++) {
         if ((m0 >> (8 * k)) & 0x80) r |= 1u << k;
         if ((m1 >> (8 * k)) & 0x80) r |= 16u << k;
+    }
+    return r;
+}
+T3_HD unsigned bits8w(unsigned m0, unsigned m1, unsigned w0, unsigned w1) {
+    unsigned r = 0;
+    for (int k = 0; k < 4; k++) {
+        if (((m0 >> (8 * k)) & 0x80) && ((w0 >> (8 * k)) & 0xff)) r |= 1u << k;
+        if (((m1 >> (8 * k)) & 0x80) && ((w1 >> (8 * k)) & 0xff)) r |= 16u << k;
     }
     return r;
 }
@@ -194,11 +206,15 @@ T3_HD void thread_main(const FrameSrc &src, long long t0, int T, int g, int tid,
     const size_t off = (size_t)g * 8;
     const size_t HW = src.HW;
 
-    unsigned mk0 = ~0u, mk1 = ~0u;
+    // frame * mask (imgproc.py:96-101) with mask in {0,1}: a masked-out pixel has max = mean = 0 over any window, so its
+    // predicate max*L - sum > thr*L is false (thr >= 0) whatever the window holds -- the mask is applied to the eight
+    // output bits instead of to every loaded frame
+    // ... by zeroing that pixel's weight in the two dot products that gather the eight bits (bits8w): no per-frame cost
+    unsigned w0 = 0xF8FCFEFFu, w1 = 0x80C0E0F0u;
     if (MASKED) {
         const uint2 m = ldg8(src.mask + off);
-        mk0 = m.x * 0xffu;  // {0,1} -> {0x00,0xff}
-        mk1 = m.y * 0xffu;
+        w0 &= m.x * 0xffu;  // {0,1} -> {0x00,0xff}
+        w1 &= m.y * 0xffu;
     }
 
     // ---- history: ring position p (1 .. N-1) = frame t0-N+p; position 0 ("frame t0-N") counts as zeros -------
@@ -220,8 +236,8 @@ T3_HD void thread_main(const FrameSrc &src, long long t0, int T, int g, int tid,
                     if (th >= 0) { s = slot + p; if (s >= src.R) s -= src.R; }  // N <= R: one wrap at most
                     else s = (int)(th + p);                                      // frame th+p < N <= R
                     const uint2 v = ldg8(src.ring + (size_t)s * HW + off);
-                    h0[jj] = v.x & mk0;
-                    h1[jj] = v.y & mk1;
+                    h0[jj] = v.x;
+                    h1[jj] = v.y;
                 }
             }
             Acc bm = {0, 0, 0, 0};
@@ -341,7 +357,6 @@ T3_HD void thread_main(const FrameSrc &src, long long t0, int T, int g, int tid,
                 ldg8_if(pf0[j % KR], pf1[j % KR], gp, j + K, rem);
                 gp += HW;
             }
-            if (MASKED) { x0 &= mk0; x1 &= mk1; }
             const unsigned o0 = r0[j], o1 = r1[j];  // frame t-N leaves the window
             if (P == 1) { r0[j] = x0; r1[j] = x1; }
             else {
@@ -368,7 +383,7 @@ T3_HD void thread_main(const FrameSrc &src, long long t0, int T, int g, int tid,
             const unsigned va1 = wa1 * Lu + cpk - SA1, vb1 = wb1 * Lu + cpk - SB1;
             const unsigned M0 = prmt(va0, vb0, 0xFBD9u);  // sign-replicate bytes 1,5,3,7 -> 0x00/0xff per pixel
             const unsigned M1 = prmt(va1, vb1, 0xFBD9u);
-            *const_cast<uint8_t *>(bo) = (uint8_t)bits8(M0, M1);
+            *const_cast<uint8_t *>(bo) = (uint8_t)(MASKED ? bits8w(M0, M1, w0, w1) : bits8(M0, M1));
             bo += bstride;
             if (FEED == 1 && j % K == K - 1) {
                 // stage consumed.  Its data was read into registers above; the arrive orders those reads before the

@@ -134,6 +134,42 @@ def test_gpu_seeded_streams_against_oracle(W, H, apply_mask):
 
 
 @pytest.mark.gpu
+def test_gpu_more_than_512_segments_are_all_returned():
+    """The reference returns every HoughLinesP segment without a cap (Detector.py:282-292); the library's batched
+    outputs hold 512 rows per frame, the rest comes from a second PPHT pass (mdb_get_raw_lines)."""
+    from metdetpy_b200 import BinaryCfg, BinaryCoreCfg, DynamicCfg, HoughLineCfg
+    from metdetpy_b200.detector import ClassicDetector
+    W, H, T, FPS = 640, 360, 7, 30
+    rng = np.random.default_rng(5)
+    frames = np.full((T, H, W), 20, np.uint8)
+    for t in range(T):  # a field of short dashes that jumps from frame to frame: hundreds of separate segments
+        ys = rng.integers(2, H - 2, 900)
+        xs = rng.integers(2, W - 14, 900)
+        for y, x in zip(ys, xs):
+            frames[t, y, x:x + 9] = 200
+    mask = np.ones((H, W), np.uint8)
+    ref = CO.ClassicDetectorOracle(1.0, FPS, mask, 10, adaptive=False, init_value=40, sensitivity="normal", area=0.2,
+                                   interval=1, hough=(6, 6, 1), backend="cv2")
+    cfg = BinaryCfg(BinaryCoreCfg(False, 40, "normal", 0.2, 1), HoughLineCfg(6, 6, 1), DynamicCfg(False, 5))
+    det = ClassicDetector(1.0, FPS, mask, 10, cfg, None, max_batch=4)
+    det1 = ClassicDetector(1.0, FPS, mask, 10, cfg, None)
+    got = []
+    for s in range(0, T, 4):
+        got += det.detect_many(frames[s:s + 4])
+    most = 0
+    for t in range(T):
+        ref.update(frames[t]); rl, rc = ref.detect()
+        det1.update(frames[t]); l1, c1 = det1.detect()
+        rl = np.asarray(rl, np.int32).reshape(-1, 4)
+        most = max(most, len(rl))
+        assert np.array_equal(np.asarray(got[t][0], np.int32).reshape(-1, 4), rl), (t, len(got[t][0]), len(rl))
+        assert np.array_equal(np.asarray(l1, np.int32).reshape(-1, 4), rl), t
+        if len(rl):
+            assert np.asarray(got[t][1]).shape == (len(rl), 10) and np.asarray(c1).shape == (len(rl), 10)
+    assert most > 512, most
+
+
+@pytest.mark.gpu
 def test_gpu_exotic_fps_is_refused():
     from metdetpy_b200 import BinaryCfg
     from metdetpy_b200.detector import ClassicDetector

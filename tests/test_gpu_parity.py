@@ -340,6 +340,92 @@ def test_sliding_window_class_golden():
         SlidingWindow(3, (4, 4), np.uint8).std
 
 
+@pytest.mark.parametrize("n,apply_mask,W,H", [(2, False, 64, 40), (5, True, 96, 64), (12, False, 128, 48), (30, True, 160, 96)])
+def test_per_frame_resident_window_state_against_oracle(n, apply_mask, W, H):
+    """update()/detect() on the O(1) path (csrc/perframe_kernel.cuh: running sum, prefix max and suffix planes resident
+    in HBM) against the CPU oracle, with detect() skipped on some frames, a batched call in the middle (state rebuilt from
+    the ring) and the slow path (per_frame_fast = 0: window re-read) beside it."""
+    from metdetpy_b200 import BinaryCfg, BinaryCoreCfg, DynamicCfg, HoughLineCfg
+    from metdetpy_b200.detector import M3Detector
+    from oracle import m3_oracle as O
+    rng = np.random.default_rng(100 + n)
+    T = 4 * n + 9
+    base = rng.integers(20, 60, (H, W))
+    frames = np.clip(base[None] + rng.normal(0, 2.5, (T, H, W)), 0, 255).astype(np.uint8)
+    for t in range(T):
+        x, y = (7 * t) % (W - 14), (3 * t) % (H - 3)
+        frames[t, y:y + 2, x:x + 12] = 210
+        frames[t, H // 3:H // 3 + 3, W // 4:W // 4 + 3] = 255 if t % 3 else 40
+    mask = np.ones((H, W), np.uint8)
+    mask[: H // 6, : W // 3] = 0
+    kw = dict(adaptive=True, init_value=7, sensitivity="high", area=0.2, interval=1, hough=(6, 6, 4), dy_mask=True)
+    ref = O.M3DetectorOracle(n / 10 + 1e-9, 10, mask, 10, backend="numpy", **kw)
+    cfg = BinaryCfg(BinaryCoreCfg(True, 7, "high", 0.2, 1), HoughLineCfg(6, 6, 4), DynamicCfg(True, 5))
+    fast = M3Detector(n / 10 + 1e-9, 10, mask, 10, cfg, None, max_batch=7, apply_mask=apply_mask)
+    slow = M3Detector(n / 10 + 1e-9, 10, mask, 10, cfg, None, max_batch=7, apply_mask=apply_mask)
+    slow._eng.set_option("per_frame_fast", 0)
+    feed = frames if apply_mask else frames * mask[None]
+    t = 0
+    used_fast = False
+    while t < T:
+        if t == 2 * n + 3:  # a batched call in the middle: the resident state has to be rebuilt afterwards
+            for d in (fast, slow):
+                res = d.detect_many(feed[t:t + 7])
+            for i in range(7):
+                ref.update(frames[t + i] * mask); rl, rc = ref.detect()
+            assert fast.last_infos[-1]["bi_threshold"] == ref.bi_threshold
+            t += 7
+            continue
+        ref.update(frames[t] * mask)
+        fast.update(feed[t]); slow.update(feed[t])
+        if t % 5 != 3:  # every fifth frame is pushed without a detect()
+            rl, rc = ref.detect()
+            lf, cf = fast.detect()
+            used_fast |= int(fast._eng.info("temporal_generation")) == 4
+            ls, cs = slow.detect()
+            assert int(slow._eng.info("temporal_generation")) != 4
+            assert fast.bi_threshold == slow.bi_threshold == ref.bi_threshold, t
+            assert np.array_equal(fast.dst, ref.dst), (t, int(np.count_nonzero(fast.dst != ref.dst)))
+            assert np.array_equal(slow.dst, ref.dst), t
+            raw = np.asarray(ref.linesp_ext).reshape(-1, 4)
+            assert np.array_equal(np.asarray(fast.linesp_ext).reshape(-1, 4), raw), t
+            assert_nms_equivalent(lf, cf[:, -1], rl, rc[:, -1], raw, t)
+        if t in (n - 1, n, 2 * n + 1, T - 1):
+            assert np.array_equal(fast.stack.max, ref.stack.max) and np.array_equal(fast.stack.mean, ref.stack.mean), t
+            assert np.array_equal(fast.stack.sliding_window, ref.stack.sliding_window), t
+        t += 1
+    assert used_fast
+    fast.close(); slow.close()
+
+
+def test_per_frame_4k_device_frames_equal_the_batched_path():
+    """4K, n = 30: update(on-device frame) + detect() frame by frame == one detect_many over the same frames."""
+    import torch
+    from metdetpy_b200 import BinaryCfg, BinaryCoreCfg, DynamicCfg, HoughLineCfg, synth
+    from metdetpy_b200.detector import M3Detector
+    W, H, n, T = 3840, 2160, 30, 75
+    dev = torch.device("cuda", 0)
+    fr = synth.make_stream_device(T, W, H, 30.0, dev, t0=0, loop=4 * T)
+    torch.cuda.synchronize()
+    cfg = BinaryCfg(BinaryCoreCfg(True, 7, "normal", 0.1, 2), HoughLineCfg(10, 10, 10), DynamicCfg(True, 5))
+    mask = np.ones((H, W), np.uint8)
+    one = M3Detector(n / 30.0 + 1e-9, 30.0, mask, 10, cfg, None)
+    many = M3Detector(n / 30.0 + 1e-9, 30.0, mask, 10, cfg, None, max_batch=T)
+    res, dst = many.detect_many((fr.data_ptr(), T), on_device=True, return_dst=True)
+    lib = one._eng.lib
+    from metdetpy_b200._lib import check
+    for t in range(T):
+        check(lib.mdb_update(one._eng.handle, fr[t].data_ptr(), 1), "update")
+        one._timer += 1
+        lines, cls = one.detect()
+        assert int(one._eng.info("temporal_generation")) == 4
+        assert one.bi_threshold == many.last_infos[t]["bi_threshold"], t
+        assert np.array_equal(np.asarray(one.linesp_ext).reshape(-1, 4), many.last_raw[t].reshape(-1, 4)), t
+        if t % 6 == 0 or t >= T - 2:
+            assert np.array_equal(one.dst, dst[t]), t
+    one.close(); many.close()
+
+
 def test_window_longer_than_255_frames_against_oracle():
     """The reference has no limit on int(window_sec * fps) (Detector.py:197): n = 300 runs the generic kernel."""
     from metdetpy_b200 import BinaryCfg, BinaryCoreCfg, DynamicCfg, HoughLineCfg, synth
@@ -411,7 +497,7 @@ def test_error_behaviour():
     lines, cls = det.detect()  # first frame: empty result, reference shapes
     assert len(lines) == 0 and cls.shape == (0, 10)
     with pytest.raises(ValueError):
-        M3Detector(100, 30, np.ones((8, 8), np.uint8), 10, BinaryCfg())  # window 3000 > 255
+        M3Detector(200, 30, np.ones((8, 8), np.uint8), 10, BinaryCfg())  # window 6000 > MDB_MAX_WINDOW
 
 
 @pytest.mark.parametrize("name,world", [("synth_384x216_n12_dyon_mask", 3), ("clip_192x144_n25", 2),
