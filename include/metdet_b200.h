@@ -233,6 +233,32 @@ int mdb_lineset_nms_ordered(const int32_t *lines_in, int n, const int32_t *order
 int mdb_gauss_stack(const uint8_t *frames, int T, size_t frame_bytes, uint16_t *sum_out, uint32_t *sq_out,
                     int frames_on_device, int out_on_device, int accumulate, int device);
 
+/* ---- MFNR mix stacker on the device (second half) ---------------------
+ * mfnr_mix_stacker, MetLib/stacker.py:296-403, for connect_lines.switch == false and the background algorithms "mean"
+ * (:339-342) and "sigma-clipping" (:333-338, single_sigma_clipping :94-115).  Frames ((H, W, C) uint8, any C <= 4) are
+ * appended as the loader delivers them (what _batch_stacker, :146-175, feeds MaxImgContainer / AllImgContainer /
+ * FastGaussianContainer); with keep_frames they stay resident on the device for the clipping pass.  The finishing
+ * passes run in float64 like the reference; the two global means are reduced in a fixed order that is not numpy's
+ * pairwise one, so the result equals the reference's up to the last ulp of those scalars: a mixed pixel may differ by
+ * one grey level where it sits on a rounding boundary (tests hold <= 1 level on <= 1e-4 of the elements).
+ * Not built: bg_algorithm "median" / "med-of-med" (:343-349) and connect_highlight_area (:239-294). */
+typedef struct mdb_mfnr *mdb_mfnr_handle;
+typedef struct mdb_mfnr_params {
+    double highlight_preserve; /* DenoiseOption.highlight_preserve                      stacker.py:313 */
+    int32_t blur_ksize;        /* DenoiseOption.blur_ksize (odd)                        stacker.py:368 */
+    int32_t bg_algorithm;      /* 0 = "mean", 1 = "sigma-clipping"                      stacker.py:333-342 */
+    double blur_sigma;         /* 3 in the reference (sigmaX=3); <= 0: 3                stacker.py:370 */
+    double sigma_high;         /* single_sigma_clipping arguments (the reference passes 3.0, 3.0: :335-336) */
+    double sigma_low;
+    double bg_fix_factor;      /* MFNRDenoiseParam.bg_fix_factor                        stacker.py:353 */
+    double gumbel_mean;        /* get_gumbel_mean(n) as the caller computed it, or <= 0 to have it computed here */
+} mdb_mfnr_params;
+int mdb_mfnr_create(int height, int width, int channels, int keep_frames, int device, mdb_mfnr_handle *out);
+int mdb_mfnr_append(mdb_mfnr_handle m, const uint8_t *frames, int T, int on_device);
+/* out: (H, W, C) uint8; stats (optional, 4 doubles): est_bg_var, gumbel mean, highlight_avg_diff, count of positive diffs */
+int mdb_mfnr_finish(mdb_mfnr_handle m, const mdb_mfnr_params *params, uint8_t *out, int out_on_device, double *stats);
+int mdb_mfnr_destroy(mdb_mfnr_handle m);
+
 /* ---- loader preprocessing on the device ---------------------------
  * Replaces, for uint8 frames, what the reference's video loader applies to every decoded frame:
  *   Transform.opencv_resize   = cv2.resize(img, dsize, INTER_LINEAR)   MetLib/imgproc.py:82-85

@@ -25,6 +25,12 @@ class Config(C.Structure):
                 ("detector", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
+class MfnrParams(C.Structure):
+    _fields_ = [("highlight_preserve", C.c_double), ("blur_ksize", C.c_int32), ("bg_algorithm", C.c_int32),
+                ("blur_sigma", C.c_double), ("sigma_high", C.c_double), ("sigma_low", C.c_double),
+                ("bg_fix_factor", C.c_double), ("gumbel_mean", C.c_double)]
+
+
 class FrameInfo(C.Structure):
     _fields_ = [("timer", C.c_int64), ("bi_threshold", C.c_int32), ("n_on", C.c_int32),
                 ("bi_threshold_float", C.c_double), ("snr", C.c_double), ("dst_sum", C.c_double),
@@ -71,6 +77,10 @@ SYMBOLS = {
     "mdb_submit_batch_thr": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP]),
     "mdb_submit_batch_ex": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _I]),
     "mdb_gauss_stack": (_I, [_VP, _I, _SZ, _VP, _VP, _I, _I, _I, _I]),
+    "mdb_mfnr_create": (_I, [_I, _I, _I, _I, _I, C.POINTER(_VP)]),
+    "mdb_mfnr_append": (_I, [_VP, _VP, _I, _I]),
+    "mdb_mfnr_finish": (_I, [_VP, C.POINTER(MfnrParams), _VP, _I, _VP]),
+    "mdb_mfnr_destroy": (_I, [_VP]),
     "mdb_preproc_create": (_I, [_I, _I, _I, _I, _I, _I, _VP, _I, _I, _I, C.POINTER(_VP)]),
     "mdb_preproc_run": (_I, [_VP, _VP, _I, _I, _VP, _I, C.POINTER(C.c_int32)]),
     "mdb_preproc_output": (_I, [_VP, C.POINTER(_VP)]),

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmetdet_b200.so")
 SOURCES = ["metdet.cu"]
 DEPS = ["metdet.cu", "common.cuh", "hough.cuh", "kernels_basic.cuh", "stream_kernel.cuh", "spatial_kernel.cuh", "temporal_kernel.cuh", "temporal3_kernel.cuh",
-        "temporal3_dispatch.cuh", "preproc.cuh", "classic.cuh", "perframe_kernel.cuh",
+        "temporal3_dispatch.cuh", "preproc.cuh", "classic.cuh", "perframe_kernel.cuh", "mfnr.cuh",
         os.path.join("..", "..", "include", "metdet_b200.h")]
 
 

@@ -13,6 +13,7 @@
 #include "hough.cuh"
 #include "classic.cuh"
 #include "perframe_kernel.cuh"
+#include "mfnr.cuh"
 #include "kernels_basic.cuh"
 #include "preproc.cuh"
 #include "stream_kernel.cuh"
@@ -1385,6 +1386,204 @@ extern "C" int mdb_debug_timeline(mdb_handle h, float *out) {
 extern "C" int mdb_debug_hough_profile(mdb_handle h, long long *out, int T) {
     if (!h || !out || !h->d_prof) return fail(MDB_ERR_INVALID, "mdb_debug_hough_profile: not enabled");
     CK(cudaMemcpy(out, h->d_prof, (size_t)T * 10 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return MDB_OK;
+}
+
+// ---- MFNR mix stacker (MetLib/stacker.py:296-403; kernels in mfnr.cuh) ------------------------------------------------
+struct mdb_mfnr {
+    int H = 0, W = 0, C = 0, device = 0, keep = 0;
+    size_t E = 0, P = 0;
+    long long n_frames = 0;
+    uint8_t *d_max = nullptr;
+    uint16_t *d_sum = nullptr;
+    uint32_t *d_sq = nullptr;
+    std::vector<uint8_t *> chunks;  // retained frames (keep) or one reusable staging buffer
+    std::vector<int> counts;
+    size_t stage_cap = 0;
+    cudaStream_t st = nullptr;
+};
+
+static void mfnr_free(mdb_mfnr *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->st) cudaStreamSynchronize(m->st);
+    for (uint8_t *p : m->chunks) cudaFree(p);
+    cudaFree(m->d_max); cudaFree(m->d_sum); cudaFree(m->d_sq);
+    if (m->st) cudaStreamDestroy(m->st);
+    delete m;
+}
+
+extern "C" int mdb_mfnr_create(int height, int width, int channels, int keep_frames, int device, mdb_mfnr_handle *out) {
+    if (!out) return fail(MDB_ERR_INVALID, "mdb_mfnr_create: null argument");
+    *out = nullptr;
+    if (height < 1 || width < 1 || channels < 1 || channels > 4)
+        return fail(MDB_ERR_INVALID, "mdb_mfnr_create: unsupported frame shape %dx%dx%d", height, width, channels);
+    const int ndev = mdb_device_count();
+    if (ndev == 0) return fail(MDB_ERR_CUDA, "mdb_mfnr_create: no CUDA device -- this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(MDB_ERR_INVALID, "mdb_mfnr_create: device %d of %d", device, ndev);
+    CK(cudaSetDevice(device));
+    mdb_mfnr *m = new (std::nothrow) mdb_mfnr();
+    if (!m) return fail(MDB_ERR_NOMEM, "mdb_mfnr_create: out of host memory");
+    m->H = height; m->W = width; m->C = channels; m->device = device; m->keep = keep_frames;
+    m->P = (size_t)height * width; m->E = m->P * channels;
+    if (cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc((void **)&m->d_max, m->E) != cudaSuccess || cudaMalloc((void **)&m->d_sum, m->E * 2) != cudaSuccess ||
+        cudaMalloc((void **)&m->d_sq, m->E * 4) != cudaSuccess) {
+        const int rc = fail(MDB_ERR_NOMEM, "mdb_mfnr_create: %s", cudaGetErrorString(cudaGetLastError()));
+        mfnr_free(m);
+        return rc;
+    }
+    *out = m;
+    return MDB_OK;
+}
+
+extern "C" int mdb_mfnr_destroy(mdb_mfnr_handle m) {
+    mfnr_free(m);
+    return MDB_OK;
+}
+
+extern "C" int mdb_mfnr_append(mdb_mfnr_handle m, const uint8_t *frames, int T, int on_device) {
+    if (!m || !frames || T < 1) return fail(MDB_ERR_INVALID, "mdb_mfnr_append: bad arguments");
+    if (m->n_frames + T > 32767) return fail(MDB_ERR_INVALID, "mdb_mfnr_append: more than 32767 frames (the reference's int16 count)");
+    CK(cudaSetDevice(m->device));
+    const size_t bytes = (size_t)T * m->E;
+    uint8_t *buf = nullptr;
+    if (m->keep || m->chunks.empty() || m->stage_cap < bytes) {
+        if (!m->keep && !m->chunks.empty()) {  // grow the staging buffer
+            CK(cudaStreamSynchronize(m->st));
+            cudaFree(m->chunks[0]);
+            m->chunks.clear(); m->counts.clear();
+        }
+        if (cudaMalloc((void **)&buf, bytes) != cudaSuccess)
+            return fail(MDB_ERR_NOMEM, "mdb_mfnr_append: %zu bytes for %d frames: %s", bytes, T, cudaGetErrorString(cudaGetLastError()));
+        m->chunks.push_back(buf);
+        m->counts.push_back(T);
+        m->stage_cap = bytes;
+    } else {
+        buf = m->chunks[0];
+        m->counts[0] = T;
+    }
+    CK(cudaMemcpyAsync(buf, frames, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, m->st));
+    const int first = m->n_frames == 0;
+    if (m->E % 4 == 0) {
+        const size_t thr = m->E / 4;
+        mfnr_accum_kernel<4><<<(unsigned)((thr + MF_THREADS - 1) / MF_THREADS), MF_THREADS, 0, m->st>>>(buf, T, m->E, m->d_max, m->d_sum, m->d_sq, first);
+    } else {
+        mfnr_accum_kernel<1><<<(unsigned)((m->E + MF_THREADS - 1) / MF_THREADS), MF_THREADS, 0, m->st>>>(buf, T, m->E, m->d_max, m->d_sum, m->d_sq, first);
+    }
+    CK(cudaGetLastError());
+    if (!on_device) CK(cudaStreamSynchronize(m->st));  // the caller may reuse its buffer
+    m->n_frames += T;
+    return MDB_OK;
+}
+
+extern "C" int mdb_mfnr_finish(mdb_mfnr_handle m, const mdb_mfnr_params *prm, uint8_t *out, int out_on_device, double *stats) {
+    if (!m || !prm || !out) return fail(MDB_ERR_INVALID, "mdb_mfnr_finish: null argument");
+    if (m->n_frames < 2) return fail(MDB_ERR_STATE, "mdb_mfnr_finish: %lld frames appended, at least 2 are needed", m->n_frames);
+    if (prm->blur_ksize < 1 || prm->blur_ksize % 2 == 0 || prm->blur_ksize > 255)
+        return fail(MDB_ERR_INVALID, "mdb_mfnr_finish: blur_ksize %d must be odd and in 1..255", prm->blur_ksize);
+    if (prm->bg_algorithm != 0 && prm->bg_algorithm != 1)
+        return fail(MDB_ERR_INVALID, "mdb_mfnr_finish: bg_algorithm %d (0 = mean, 1 = sigma-clipping)", prm->bg_algorithm);
+    if (prm->bg_algorithm == 1 && !m->keep)
+        return fail(MDB_ERR_STATE, "mdb_mfnr_finish: sigma clipping needs the frames (create with keep_frames = 1)");
+    CK(cudaSetDevice(m->device));
+    const int N = (int)m->n_frames, ks = prm->blur_ksize;
+    const size_t E = m->E, P = m->P;
+    // scratch: clipped sums, partials, mask, blur planes, kernel taps, output
+    uint16_t *d_sum2 = nullptr; uint32_t *d_sq2 = nullptr; int32_t *d_n2 = nullptr;
+    double *d_pv = nullptr, *d_tot = nullptr, *d_row = nullptr, *d_blur = nullptr, *d_k = nullptr;
+    unsigned long long *d_pc = nullptr, *d_cnt = nullptr;
+    uint8_t *d_fg = nullptr, *d_out = nullptr;
+    const uint8_t **d_cptr = nullptr; int *d_ccnt = nullptr;
+    std::vector<void *> scratch;
+    auto alloc = [&](void **p, size_t bytes) { cudaError_t e = cudaMalloc(p, bytes); if (e == cudaSuccess) scratch.push_back(*p); return e; };
+    auto cleanup = [&]() { for (void *p : scratch) cudaFree(p); };
+#define MF_TRY(expr)                                                                      \
+    do {                                                                                  \
+        cudaError_t e_ = (expr);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            cudaStreamSynchronize(m->st);                                                 \
+            cleanup();                                                                    \
+            return fail(MDB_ERR_CUDA, "mdb_mfnr_finish: %s", cudaGetErrorString(e_));      \
+        }                                                                                 \
+    } while (0)
+    MF_TRY(alloc((void **)&d_pv, MF_PARTS * sizeof(double)));
+    MF_TRY(alloc((void **)&d_pc, MF_PARTS * sizeof(unsigned long long)));
+    MF_TRY(alloc((void **)&d_tot, sizeof(double)));
+    MF_TRY(alloc((void **)&d_cnt, sizeof(unsigned long long)));
+    MF_TRY(alloc((void **)&d_fg, P));
+    MF_TRY(alloc((void **)&d_row, P * sizeof(double)));
+    MF_TRY(alloc((void **)&d_blur, P * sizeof(double)));
+    MF_TRY(alloc((void **)&d_k, ks * sizeof(double)));
+    if (!out_on_device) MF_TRY(alloc((void **)&d_out, E));
+    const unsigned gE = (unsigned)((E + MF_THREADS - 1) / MF_THREADS), gP = (unsigned)((P + MF_THREADS - 1) / MF_THREADS);
+    const uint16_t *sum = m->d_sum;
+    const int32_t *n_arr = nullptr;
+    if (prm->bg_algorithm == 1) {
+        MF_TRY(alloc((void **)&d_sum2, E * 2));
+        MF_TRY(alloc((void **)&d_sq2, E * 4));
+        MF_TRY(alloc((void **)&d_n2, E * 4));
+        MF_TRY(alloc((void **)&d_cptr, m->chunks.size() * sizeof(uint8_t *)));
+        MF_TRY(alloc((void **)&d_ccnt, m->chunks.size() * sizeof(int)));
+        MF_TRY(cudaMemcpyAsync(d_cptr, m->chunks.data(), m->chunks.size() * sizeof(uint8_t *), cudaMemcpyHostToDevice, m->st));
+        MF_TRY(cudaMemcpyAsync(d_ccnt, m->counts.data(), m->counts.size() * sizeof(int), cudaMemcpyHostToDevice, m->st));
+        MfnrChunks ch;
+        ch.ptr = d_cptr; ch.count = d_ccnt; ch.n = (int)m->chunks.size();
+        // stacker.py:333-336 passes sigma_high = sigma_low = 3.0 whatever the configuration holds; the caller decides
+        mfnr_sigma_kernel<<<gE, MF_THREADS, 0, m->st>>>(ch, E, N, prm->sigma_high, prm->sigma_low, m->d_sum, m->d_sq, d_sum2, d_sq2, d_n2);
+        MF_TRY(cudaGetLastError());
+        sum = d_sum2;
+        n_arr = d_n2;
+    }
+    const uint32_t *sq = prm->bg_algorithm == 1 ? d_sq2 : m->d_sq;
+    double tot = 0.0;
+    unsigned long long cnt = 0;
+    mfnr_sqrtvar_kernel<<<MF_PARTS, MF_THREADS, 0, m->st>>>(E, N, sum, sq, n_arr, d_pv, d_pc);
+    mfnr_final_reduce_kernel<<<1, 32, 0, m->st>>>(MF_PARTS, d_pv, d_pc, d_tot, d_cnt);
+    MF_TRY(cudaGetLastError());
+    MF_TRY(cudaMemcpyAsync(&tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, m->st));
+    MF_TRY(cudaStreamSynchronize(m->st));
+    const double est_bg_var = tot / (double)E;
+    // get_gumbel_mean (stacker.py:118-126): the caller may hand in the value its own numpy computed
+    double g = prm->gumbel_mean;
+    if (!(g > 0.0)) {
+        const double s2 = std::sqrt(2.0 * std::log((double)N));
+        g = s2 - (std::log(std::log((double)N)) + std::log(4.0 * 3.141592653589793)) / (2.0 * s2) + 0.5772 / s2;
+    }
+    volatile double c2v = est_bg_var * g;            // (est_bg_var * gumble_mean)
+    volatile double c1v = c2v * prm->bg_fix_factor;  // est_bg_var * gumble_mean * bg_fix_factor, left to right
+    const double c1 = c1v, c2 = c2v;
+    mfnr_diffpos_kernel<<<MF_PARTS, MF_THREADS, 0, m->st>>>(E, N, c1, m->d_max, sum, n_arr, d_pv, d_pc);
+    mfnr_final_reduce_kernel<<<1, 32, 0, m->st>>>(MF_PARTS, d_pv, d_pc, d_tot, d_cnt);
+    MF_TRY(cudaGetLastError());
+    MF_TRY(cudaMemcpyAsync(&tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, m->st));
+    MF_TRY(cudaMemcpyAsync(&cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, m->st));
+    MF_TRY(cudaStreamSynchronize(m->st));
+    const double avg = tot / (double)cnt;  // np.average of an empty selection is NaN there too
+    std::vector<double> taps(ks);
+    {   // cv2.getGaussianKernel(ksize, sigma, CV_64F), computed branch
+        const double sigma = prm->blur_sigma > 0 ? prm->blur_sigma : 3.0;
+        double ssum = 0.0;
+        for (int i = 0; i < ks; i++) {
+            const double x = i - (ks - 1) * 0.5;
+            taps[i] = std::exp(-(x * x) / (2.0 * sigma * sigma));
+            ssum += taps[i];
+        }
+        for (int i = 0; i < ks; i++) taps[i] = taps[i] / ssum;
+    }
+    MF_TRY(cudaMemcpyAsync(d_k, taps.data(), ks * sizeof(double), cudaMemcpyHostToDevice, m->st));
+    volatile double hl = 255.0 * prm->highlight_preserve, omh = 1.0 - prm->highlight_preserve;
+    mfnr_mask_kernel<<<gP, MF_THREADS, 0, m->st>>>(P, m->C, N, c1, avg, hl, m->d_max, sum, n_arr, d_fg);
+    mfnr_blur_row_kernel<<<gP, MF_THREADS, 0, m->st>>>(m->H, m->W, ks, d_k, d_fg, d_row);
+    mfnr_blur_col_kernel<<<gP, MF_THREADS, 0, m->st>>>(m->H, m->W, ks, d_k, d_row, d_blur);
+    uint8_t *dst = out_on_device ? out : d_out;
+    mfnr_mix_kernel<<<gE, MF_THREADS, 0, m->st>>>(E, m->C, N, c2, prm->highlight_preserve, omh, m->d_max, sum, n_arr, d_blur, dst);
+    MF_TRY(cudaGetLastError());
+    if (!out_on_device) MF_TRY(cudaMemcpyAsync(out, d_out, E, cudaMemcpyDeviceToHost, m->st));
+    MF_TRY(cudaStreamSynchronize(m->st));
+#undef MF_TRY
+    cleanup();
+    if (stats) { stats[0] = est_bg_var; stats[1] = g; stats[2] = avg; stats[3] = (double)cnt; }
     return MDB_OK;
 }
 

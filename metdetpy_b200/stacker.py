@@ -156,3 +156,122 @@ def max_stacker(video_loader: Any, start_frame: Optional[int] = None, end_frame:
     finally:
         video_loader.stop()
     return box.container
+
+
+SUPPORT_BG_ALGO = ["median", "med-of-med", "sigma-clipping", "mean"]  # MetLib/stacker.py:13
+_BG_ON_DEVICE = {"mean": 0, "sigma-clipping": 1}
+EULER_CONSTANT = 0.5772  # MetLib/utils.py:24
+
+
+def get_gumbel_mean(n: int) -> float:
+    """MetLib/stacker.py:118-126."""
+    sqrt2logn = np.sqrt(2 * np.log(n))
+    return (sqrt2logn - (np.log(np.log(n)) + np.log(4 * np.pi)) / (2 * sqrt2logn) + EULER_CONSTANT / sqrt2logn)
+
+
+class MfnrMixContainer:
+    """What mfnr_mix_stacker builds with MaxImgContainer + AllImgContainer + FastGaussianContainer
+    (MetLib/stacker.py:316-319), kept on the device: `append(frame)` per loader frame, `export(denoise_cfg)` for the
+    mixed image.  Frames are shipped in chunks; for sigma clipping they stay resident in HBM for the second pass."""
+
+    def __init__(self, keep_frames: bool, chunk: int = 16, device: int = 0):
+        self._buf: list[np.ndarray] = []
+        self._h = None
+        self._keep, self._chunk, self._device = bool(keep_frames), chunk, device
+        self.shape = None
+        self.count = 0
+        self.stats = None
+
+    def append(self, new_frame: np.ndarray) -> None:
+        f = np.ascontiguousarray(new_frame)
+        if f.dtype != np.uint8:
+            raise ValueError(f"uint8 frames expected, got {f.dtype}")
+        if self.shape is None:
+            if f.ndim not in (2, 3):
+                raise ValueError("frames must be (H, W) or (H, W, C)")
+            self.shape = f.shape
+            import ctypes as C
+            h = C.c_void_p()
+            ch = 1 if f.ndim == 2 else f.shape[2]
+            check(_lib.load().mdb_mfnr_create(f.shape[0], f.shape[1], ch, int(self._keep), self._device, C.byref(h)),
+                  "mfnr create")
+            self._h = h
+        elif f.shape != self.shape:
+            raise ValueError(f"Expect new frame has the same shape as the base frame {self.shape}, got {f.shape}.")
+        self._buf.append(f)
+        if len(self._buf) >= self._chunk:
+            self._flush()
+
+    def _flush(self):
+        if self._buf:
+            arr = np.ascontiguousarray(np.stack(self._buf))
+            check(_lib.load().mdb_mfnr_append(self._h, arr.ctypes.data, len(arr), 0), "mfnr append")
+            self.count += len(arr)
+            self._buf = []
+
+    def export(self, highlight_preserve: float, blur_ksize: int, bg_algorithm: str, bg_fix_factor: float,
+               sigma_high: float = 3.0, sigma_low: float = 3.0) -> np.ndarray:
+        import ctypes as C
+        self._flush()
+        prm = _lib.MfnrParams()
+        prm.highlight_preserve, prm.blur_ksize, prm.blur_sigma = float(highlight_preserve), int(blur_ksize), 3.0
+        prm.bg_algorithm = _BG_ON_DEVICE[bg_algorithm]
+        prm.sigma_high, prm.sigma_low, prm.bg_fix_factor = float(sigma_high), float(sigma_low), float(bg_fix_factor)
+        with np.errstate(all="ignore"):
+            prm.gumbel_mean = float(get_gumbel_mean(self.count))
+        out = np.empty(self.shape, np.uint8)
+        st = (C.c_double * 4)()
+        check(_lib.load().mdb_mfnr_finish(self._h, C.byref(prm), out.ctypes.data, 0, st), "mfnr finish")
+        self.stats = dict(est_bg_var=st[0], gumbel=st[1], highlight_avg_diff=st[2], positive_diffs=int(st[3]))
+        return out
+
+    def close(self):
+        if self._h is not None:
+            _lib.load().mdb_mfnr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def mfnr_mix_stacker(video_loader: Any, denoise_cfg: Any, start_frame: Optional[int] = None,
+                     end_frame: Optional[int] = None, logger: Any = None) -> Optional[np.ndarray]:
+    """mfnr_mix_stacker (MetLib/stacker.py:296-403) on the device, same signature; `denoise_cfg` is the reference's
+    DenoiseOption (or anything with its fields).  Built: connect_lines.switch == False with bg_algorithm "mean" or
+    "sigma-clipping".  Refused (NotImplementedError): "median" / "med-of-med" (:343-349) and connect_highlight_area
+    (:239-294: Lab round trips, Otsu, circular-kernel morphology, contour filling)."""
+    algo = denoise_cfg.mfnr_param.bg_algorithm
+    assert algo in SUPPORT_BG_ALGO, f"unsupported bg algo! select from {SUPPORT_BG_ALGO}, but {algo} got."
+    if algo not in _BG_ON_DEVICE:
+        raise NotImplementedError(f"bg_algorithm {algo!r} (MetLib/stacker.py:343-349) is not built on the device")
+    if denoise_cfg.connect_lines.switch:
+        raise NotImplementedError("connect_lines (connect_highlight_area, MetLib/stacker.py:239-294) is not built on the device")
+    box = MfnrMixContainer(keep_frames=algo == "sigma-clipping")
+    try:
+        try:
+            if start_frame is not None or end_frame is not None:
+                video_loader.reset(start_frame=start_frame, end_frame=end_frame)
+            video_loader.start()
+            for _ in range(video_loader.iterations):
+                img = video_loader.pop()
+                if img is None:
+                    break
+                box.append(img)
+        except Exception as e:  # the reference logs and goes on with what it has (stacker.py:169-171)
+            if logger is not None:
+                logger.error(e.__repr__())
+        finally:
+            video_loader.stop()
+        box._flush()
+        if box.count == 0:
+            return None
+        # stacker.py:333-336: single_sigma_clipping is always called with sigma 3.0 / 3.0
+        out = box.export(denoise_cfg.highlight_preserve, denoise_cfg.blur_ksize, algo, denoise_cfg.mfnr_param.bg_fix_factor)
+        if logger is not None and hasattr(logger, "debug"):
+            logger.debug(f"highlight fix factor = {box.stats['est_bg_var'] * box.stats['gumbel'] * denoise_cfg.mfnr_param.bg_fix_factor:.4f}")
+        return out
+    finally:
+        box.close()

@@ -307,6 +307,56 @@ def case_gauss_stack():
     np.savez_compressed(os.path.join(HERE, "gauss_stack.npz"), names=np.array(["rgb40", "wrap300"]), **out)
 
 
+def case_mfnr():
+    """mfnr_mix_stacker (MetLib/stacker.py:296-403) of the live reference through a loader stub, connect_lines off,
+    background algorithms "mean" and "sigma-clipping"."""
+    from MetLib.stacker import mfnr_mix_stacker
+    from MetLib.metstruct import ConnectParam, DenoiseOption, MFNRDenoiseParam, SimpleDenoiseParam
+
+    class Loader:  # the protocol _batch_stacker drives (stacker.py:146-175)
+        def __init__(self, frames):
+            self.frames, self.i = frames, 0
+            self.iterations = len(frames)
+
+        def reset(self, start_frame=None, end_frame=None):
+            self.i = 0
+
+        def start(self):
+            self.i = 0
+
+        def pop(self):
+            f = self.frames[self.i]; self.i += 1
+            return f
+
+        def stop(self):
+            pass
+
+    rng = np.random.default_rng(21)
+    out = {}
+    for name, T, H, W in [("clip24", 24, 72, 104), ("clip50", 50, 48, 64)]:
+        base = rng.integers(15, 70, (H, W, 3))
+        frames = np.clip(base[None] + rng.normal(0, 4.0, (T, H, W, 3)), 0, 255).astype(np.uint8)
+        for t in range(T):  # a moving streak, a saturated lamp, a hot pixel that flickers
+            x = 5 + 3 * t
+            if x + 8 < W:
+                frames[t, H // 2 + t // 3, x:x + 8] = (230, 240, 250)
+            frames[t, 6:10, 8:12] = 255
+            if t % 7 == 0:
+                frames[t, H - 9, W - 12] = (90, 200, 120)
+        out[f"{name}_frames"] = frames
+        for algo in ("mean", "sigma-clipping"):
+            cfg = DenoiseOption(switch=True, highlight_preserve=0.9, algorithm="mfnr-mix", blur_ksize=31,
+                                connect_lines=ConnectParam(switch=False, ksize_multiplier=1.5, gamma=1.0, threshold=30),
+                                simple_param=SimpleDenoiseParam(10, 20, 10, 15, 6),
+                                mfnr_param=MFNRDenoiseParam(bg_algorithm=algo, sigma_high=3.0, sigma_low=3.0, bg_fix_factor=1.5))
+            with np.errstate(all="ignore"):
+                mix = mfnr_mix_stacker(Loader(list(frames)), cfg, None, None, BaseMetLog())
+            assert mix is not None and mix.dtype == np.uint8 and mix.shape == (H, W, 3)
+            out[f"{name}_{algo}"] = mix
+            print("mfnr", name, algo, mix.shape, int(mix.mean() * 1000) / 1000, int((mix != frames.max(0)).sum()))
+    np.savez_compressed(os.path.join(HERE, "mfnr.npz"), names=np.array(["clip24", "clip50"]), **out)
+
+
 def case_preproc():
     """Loader preprocessing by the reference's own Transform (MetLib/imgproc.py:70-139) and
     MergeFunction.max (MetLib/utils.py:203-204): resize -> BGR2GRAY -> mask, exp_frame merge."""
@@ -387,7 +437,7 @@ def case_masks():
         print(f"mask_east {W}x{H}: open share {m.mean():.4f} -> {os.path.getsize(path) / 1e3:.1f} KB")
 
 
-CASES = dict(clip_cfg1=case_clip_config1, masks=case_masks, preproc=case_preproc, gauss=case_gauss_stack, classic=case_classic, synth_small=case_synth_small, synth_dy_mask=case_synth_dy_mask, odd=case_odd_size,
+CASES = dict(mfnr=case_mfnr, clip_cfg1=case_clip_config1, masks=case_masks, preproc=case_preproc, gauss=case_gauss_stack, classic=case_classic, synth_small=case_synth_small, synth_dy_mask=case_synth_dy_mask, odd=case_odd_size,
              dense=case_fixed_thr_dense, low=case_low_sens, clip=case_real_clip, nms=case_nms,
              sw=case_sliding_window, hough=case_hough)
 
