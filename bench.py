@@ -263,7 +263,120 @@ def measure_next_rows(a, batch0_ptr, dev, peak):
                                "cpu_baseline": {"value": cpu, "unit": "frames/s", "kind": "port", "cores": cv2.getNumThreads(),
                                                 "sample": "8 frames, oracle cv2 backend = the reference's numpy+cv2 calls"}}
     det.close()
+    # ---- row 3: MFNR mix stacker (stacker.py:296-403), sigma clipping, device-resident colour clip ------------------
+    try:
+        import ctypes as C
+        from metdetpy_b200 import _lib, stacker
+        from metdetpy_b200._lib import check
+        from oracle import mfnr_oracle as MO
+        Tm, Hm, Wm = 48, 2160, 3840
+        g = torch.Generator(device=dev); g.manual_seed(3)
+        clip = (torch.randn((Tm, Hm, Wm, 3), device=dev, generator=g) * 5.0 + 50.0).clamp_(0, 255).to(torch.uint8)
+        clip[:, 1000:1003, 500:2500] = 240
+        torch.cuda.synchronize()
+        lib = _lib.load()
+        times = []
+        for rep in range(3):
+            h = C.c_void_p()
+            check(lib.mdb_mfnr_create(Hm, Wm, 3, 1, dev.index or 0, C.byref(h)), "mfnr")
+            prm = _lib.MfnrParams()
+            prm.highlight_preserve, prm.blur_ksize, prm.blur_sigma, prm.bg_algorithm = 0.9, 31, 3.0, 1
+            prm.sigma_high = prm.sigma_low = 3.0
+            prm.bg_fix_factor, prm.gumbel_mean = 1.5, float(stacker.get_gumbel_mean(Tm))
+            outb = torch.empty((Hm, Wm, 3), dtype=torch.uint8, device=dev)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for s0 in range(0, Tm, 16):
+                check(lib.mdb_mfnr_append(h, clip[s0:s0 + 16].data_ptr(), 16, 1), "mfnr")
+            check(lib.mdb_mfnr_finish(h, C.byref(prm), outb.data_ptr(), 1, None), "mfnr")
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+            lib.mdb_mfnr_destroy(h)
+        dt = float(np.median(times))
+        small = clip[:, 540:1080, 960:1920].cpu().numpy()  # a quarter-HD crop of the same clip for the CPU arm
+        t0 = time.perf_counter()
+        with np.errstate(all="ignore"):
+            MO.mfnr_mix(small, bg_algorithm="sigma-clipping", backend="cv2")
+        cpu_dt = (time.perf_counter() - t0) * (Hm * Wm) / (540 * 960)
+        out["mfnr_mix_stacker"] = {"workload": f"{Tm} device-resident {Wm}x{Hm} BGR frames, bg sigma-clipping, blur 31 (stacker.py:296-403, connect_lines off)",
+                                   "frames_per_s": Tm / dt, "ms_per_clip": dt * 1e3,
+                                   "roofline": {"bound": "hbm", "achieved": 3.0 * Tm * Hm * Wm * 3 / dt / 1e9, "peak": peak, "unit": "GB/s",
+                                                "frac": 3.0 * Tm * Hm * Wm * 3 / dt / 1e9 / peak,
+                                                "bytes": "every frame byte read by the accumulation and by the clipping pass, written once into the resident copy"},
+                                   "cpu_baseline": {"value": Tm / cpu_dt, "unit": "frames/s", "kind": "port", "cores": 1,
+                                                    "sample": "960x540 crop of the same clip through the oracle (numpy + cv2.GaussianBlur), time scaled by the pixel ratio"}}
+        del clip, outb
+    except Exception as e:
+        out["mfnr_mix_stacker"] = {"error": repr(e)}
+    # ---- loader leg: host BGR frames -> Transform chain -> detector, end to end (the reference's main loop from decoded frames)
+    try:
+        out["loader_leg"] = measure_loader_leg(dev)
+    except Exception as e:
+        out["loader_leg"] = {"error": repr(e)}
     return out
+
+
+def measure_loader_leg(dev):
+    """What MetDetPy.detect_video does per frame once the decoder has produced it (videoloader.py:300-308, 388;
+    MetDetPy.py:192-198): resize -> gray -> mask -> detector.  Source: 4K BGR frames in pinned host memory (NVDEC is not
+    reachable from this container: profiles/r02_nvdec_probe2.txt), detector at the reference's 960x540 working size.
+    Two preprocessing handles alternate so that the detector of chunk k runs beside the H2D copy of chunk k + 1."""
+    import cv2
+    import torch
+    from metdetpy_b200.detector import M3Detector
+    from metdetpy_b200.imgproc import Transform
+    W0, H0, W, H, T, n, fps = 3840, 2160, 960, 540, 32, 30, 30.0
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    hosts = []
+    for k in range(2):
+        d = (torch.randn((T, H0, W0, 3), device=dev, generator=g) * 4.0 + 45.0).clamp_(0, 255).to(torch.uint8)
+        d[:, 700 + 40 * k:704 + 40 * k, 300:1500] = 230
+        hb = torch.empty((T, H0, W0, 3), dtype=torch.uint8).pin_memory()
+        hb.copy_(d)
+        hosts.append(hb)
+        del d
+    mask = np.ones((H, W), np.uint8)
+    trs = []
+    for k in range(2):
+        tr = Transform(device=dev.index or 0)
+        tr.opencv_resize([W, H]); tr.opencv_BGR2GRAY(); tr.mask_with(mask)
+        trs.append(tr)
+    det = M3Detector(n / fps + 1e-9, fps, mask, 10, make_cfg(), None, device=dev.index or 0, max_batch=T)
+    arrs = [h.numpy() for h in hosts]
+
+    def run(nb):
+        pending = 0
+        for k in range(nb):
+            df = trs[k % 2].exec_transform_many(arrs[k % 2], 1, keep_on_device=True)
+            det.submit(df.ptr, T, True)
+            pending += 1
+            if pending == 2:
+                det.collect(); pending -= 1
+        while pending:
+            det.collect(); pending -= 1
+    run(3)
+    torch.cuda.synchronize()
+    nb = 10
+    t0 = time.perf_counter()
+    run(nb)
+    dt = time.perf_counter() - t0
+    for tr in trs:
+        tr.close()
+    det.close()
+    # CPU arm: the reference's own calls on the same frames
+    cdet, threads = cpu_reference_detector(W, H, n, fps)
+    src = arrs[0][:12]
+    for f in src[:4]:
+        cdet.update(cv2.cvtColor(cv2.resize(f, (W, H), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY) * mask); cdet.detect()
+    t0 = time.perf_counter()
+    for f in src[4:]:
+        cdet.update(cv2.cvtColor(cv2.resize(f, (W, H), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY) * mask); cdet.detect()
+    cpu = 8 / (time.perf_counter() - t0)
+    return {"workload": f"{W0}x{H0} BGR frames in pinned host memory -> resize {W}x{H} -> gray -> mask -> M3Detector(window {n}), {T} frames per call",
+            "frames_per_s": nb * T / dt, "h2d_gbs": nb * T * H0 * W0 * 3 / dt / 1e9, "h2d_bytes_per_frame": H0 * W0 * 3,
+            "bound": "PCIe: every source frame is 24.9 MB",
+            "cpu_baseline": {"value": cpu, "unit": "frames/s", "kind": "port", "cores": threads,
+                             "sample": "8 frames: cv2.resize + cv2.cvtColor + the oracle's cv2 backend at 960x540 (window not full: its cost does not depend on that)"}}
 
 
 _VIEWS = {}
@@ -721,6 +834,9 @@ def main_ours(a):
                          "frac_inside_timed_region": (in_step / peak) if in_step else None,
                          "inside_note": "same events during the timed region, where the chain shares the SMs with the Hough pass "
                                         "and the next batch's temporal pass (three batches in flight): elapsed, not busy, time",
+                         "frac_whole_step": 2.0 * HW * B * bps / (dev_ms / a.steps * 1e-3) / 1e9 / peak if dev_ms else None,
+                         "whole_step_note": "algorithmic bytes of a step / the device time of the step (every kernel of the path: noise, "
+                                            "thresholds, mask chain, PPHT, result copies; three batches in flight) against the same peak",
                          "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s"},
             "clocks": sampler.summary(), "nms_lines_total": nlines_total,
             "ppht_tiers_rank0": tiers,

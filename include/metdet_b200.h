@@ -225,6 +225,12 @@ int mdb_lineset_nms(const int32_t *lines_in, int n, int32_t *lines_out, double *
  * reference's on the same host. */
 int mdb_lineset_nms_ordered(const int32_t *lines_in, int n, const int32_t *order, int32_t *lines_out,
                             double *prob_out, int32_t *n_out);
+/* The same for several frames of a finished batch at once (the frames whose mdb_frame_info.len_ties is set): frames[j]
+ * indexes infos / raw_lines / lines / nonline_prob as mdb_collect_batch / mdb_detect_batch filled them; orders holds one
+ * permutation of 0..n_raw-1 per frame, back to back (order_off[j] .. order_off[j+1]).  Rewrites lines, nonline_prob and
+ * infos[].n_lines of those frames. */
+int mdb_lineset_nms_frames(int k, const int32_t *frames, const int32_t *orders, const int64_t *order_off,
+                           const int32_t *raw_lines, mdb_frame_info *infos, int32_t *lines, double *nonline_prob);
 
 /* FastGaussianContainer.append over T frames (MetLib/stacker.py:52-59; FastGaussianParam.__init__/__add__,
  * MetLib/utils.py:435-452, :485-493): per element sum_out = sum of the frames as uint16 and sq_out = sum of

@@ -63,6 +63,7 @@ SYMBOLS = {
     "mdb_max_stack": (_I, [_VP, _I, _SZ, _VP, _I, _I, _I]),
     "mdb_lineset_nms": (_I, [_VP, _I, _VP, _VP, C.POINTER(C.c_int32)]),
     "mdb_lineset_nms_ordered": (_I, [_VP, _I, _VP, _VP, _VP, C.POINTER(C.c_int32)]),
+    "mdb_lineset_nms_frames": (_I, [_I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mdb_alloc_pinned": (_I, [_SZ, C.POINTER(_VP)]),
     "mdb_free_pinned": (_I, [_VP]),
     "mdb_set_option": (_I, [_VP, C.c_char_p, _I]),

@@ -651,6 +651,34 @@ extern "C" int mdb_lineset_nms_ordered(const int32_t *lines_in, int n, const int
     return MDB_OK;
 }
 
+// lineset_nms redone for some frames of a finished batch with a caller-supplied visiting order per frame (numpy's
+// argsort of the squared lengths on the caller's machine, utils.py:804): frames[j] indexes infos / raw_lines / lines /
+// prob as mdb_collect_batch filled them; orders holds the permutations back to back, order_off[j] .. order_off[j+1].
+extern "C" int mdb_lineset_nms_frames(int k, const int32_t *frames, const int32_t *orders, const int64_t *order_off,
+                                      const int32_t *raw_lines, mdb_frame_info *infos, int32_t *lines, double *prob) {
+    if (k < 0 || (k > 0 && (!frames || !orders || !order_off || !raw_lines || !infos || !lines || !prob)))
+        return fail(MDB_ERR_INVALID, "mdb_lineset_nms_frames: bad arguments");
+    std::vector<char> seen;
+    for (int j = 0; j < k; j++) {
+        const int i = frames[j];
+        if (i < 0) return fail(MDB_ERR_INVALID, "mdb_lineset_nms_frames: negative frame index");
+        const int n = infos[i].n_raw;
+        const int32_t *ord = orders + order_off[j];
+        if (order_off[j + 1] - order_off[j] != n || n < 1 || n > MDB_MAX_LINES)
+            return fail(MDB_ERR_INVALID, "mdb_lineset_nms_frames: frame %d has %d raw segments, order has %lld entries", i, n,
+                        (long long)(order_off[j + 1] - order_off[j]));
+        seen.assign(n, 0);
+        for (int q = 0; q < n; q++) {
+            if (ord[q] < 0 || ord[q] >= n || seen[ord[q]])
+                return fail(MDB_ERR_INVALID, "mdb_lineset_nms_frames: order of frame %d is not a permutation", i);
+            seen[ord[q]] = 1;
+        }
+        infos[i].n_lines = nms_host(raw_lines + (size_t)i * MDB_MAX_LINES * 4, n, lines + (size_t)i * MDB_MAX_LINES * 4,
+                                    prob + (size_t)i * MDB_MAX_LINES, ord);
+    }
+    return MDB_OK;
+}
+
 // fill infos / line outputs for frames 0..T-1 of a finished batch (pure host work)
 static int finish_batch(mdb_detector *h, const BatchCtx &c, mdb_frame_info *infos, int32_t *lines,
                         double *prob, int32_t *raw_lines) {

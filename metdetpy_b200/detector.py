@@ -505,13 +505,14 @@ class M3Detector(LineDetector):
         cost any per-frame Python work."""
         eng = self._eng
         info = np.frombuffer(eng.infos, dtype=_INFO_DTYPE, count=T)
+        tied = np.nonzero(info["len_ties"])[0]
+        if len(tied):
+            self._renms_tied(info, tied)
         nl = info["n_lines"]
         empty = (np.array([]), np.zeros((0, self.num_cls)))
         out = [empty] * T
         for i in np.nonzero(nl)[0]:
             k = int(nl[i])
-            self._renms_if_tied(i, info)
-            k = int(info["n_lines"][i])
             cls_pred = np.zeros((k, self.num_cls))
             p = eng.prob[i, :k]
             cls_pred[:, -1] = p
@@ -520,6 +521,25 @@ class M3Detector(LineDetector):
         self._unpack(T - 1)
         self.last_infos = info.copy()
         return out
+
+    def _renms_tied(self, info, tied):
+        """Batch form of _renms_if_tied: the squared lengths of all tied frames' segments in one pass (the reference's
+        int32 expression, utils.py:802-803), one np.argsort per frame on exactly the array the reference would sort,
+        one library call for the greedy passes."""
+        eng = self._eng
+        nraw = info["n_raw"][tied].astype(np.int64)
+        off = np.concatenate(([0], np.cumsum(nraw)))
+        rows = np.repeat(tied, nraw)
+        cols = np.arange(int(off[-1])) - np.repeat(off[:-1], nraw)
+        seg = eng.raw[rows, cols]
+        l2 = np.power(seg[:, 3] - seg[:, 1], 2) + np.power(seg[:, 2] - seg[:, 0], 2)
+        orders = np.empty(len(l2), np.int32)
+        for j in range(len(tied)):
+            a, b = off[j], off[j + 1]
+            orders[a:b] = np.argsort(l2[a:b])[::-1]
+        fr = np.ascontiguousarray(tied, np.int32)
+        check(eng.lib.mdb_lineset_nms_frames(len(fr), _ptr(fr), _ptr(orders), _ptr(off), _ptr(eng.raw), C.byref(eng.infos),
+                                             _ptr(eng.lines), _ptr(eng.prob)), "lineset_nms")
 
     def _renms_if_tied(self, i: int, info=None):
         """The library orders equal-length segments by descending index.  The reference's order is

@@ -93,3 +93,42 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(root, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|oracle/|liboracle", src, re.M), \
                     f"{f} reaches into oracle/"
+
+
+def test_batched_tie_renms_equals_the_checker_frame_by_frame():
+    """mdb_lineset_nms_frames with numpy's own argsort order per frame == the CPU checker's lineset_nms (which calls
+    np.argsort like the reference, utils.py:804) on tie-heavy segment sets of every size up to 40."""
+    import ctypes as C
+    from metdetpy_b200 import _lib
+    from oracle import m3_oracle as O
+    lib = _lib.load()
+    rng = np.random.default_rng(9)
+    T, M = 64, _lib.MAX_LINES
+    infos = (_lib.FrameInfo * T)()
+    raw = np.zeros((T, M, 4), np.int32)
+    lines = np.zeros((T, M, 4), np.int32)
+    prob = np.zeros((T, M), np.float64)
+    for i in range(T):
+        n = 1 + i % 40
+        p0 = rng.integers(0, 60, (n, 2))
+        d = rng.integers(-6, 7, (n, 2)) * 3          # few distinct lengths: many ties
+        raw[i, :n] = np.concatenate([p0, p0 + d], 1)
+        infos[i].n_raw = n
+    fr = np.arange(T, dtype=np.int32)
+    off = np.concatenate(([0], np.cumsum([infos[i].n_raw for i in range(T)]))).astype(np.int64)
+    orders = np.empty(off[-1], np.int32)
+    for i in range(T):
+        seg = raw[i, :infos[i].n_raw]
+        l2 = np.power(seg[:, 3] - seg[:, 1], 2) + np.power(seg[:, 2] - seg[:, 0], 2)
+        orders[off[i]:off[i + 1]] = np.argsort(l2)[::-1]
+    rc = lib.mdb_lineset_nms_frames(T, fr.ctypes.data, orders.ctypes.data, off.ctypes.data, raw.ctypes.data, C.byref(infos),
+                                    lines.ctypes.data, prob.ctypes.data)
+    assert rc == 0, lib.mdb_last_error()
+    for i in range(T):
+        ref, rp = O.lineset_nms(raw[i, :infos[i].n_raw].copy())
+        k = infos[i].n_lines
+        assert k == len(ref) and np.array_equal(lines[i, :k], np.asarray(ref).reshape(-1, 4)), i
+        assert np.allclose(prob[i, :k], rp, rtol=1e-12, atol=0, equal_nan=True), i
+    bad = orders.copy(); bad[off[5]] = bad[off[5] + 1]
+    assert lib.mdb_lineset_nms_frames(T, fr.ctypes.data, bad.ctypes.data, off.ctypes.data, raw.ctypes.data, C.byref(infos),
+                                      lines.ctypes.data, prob.ctypes.data) != 0
