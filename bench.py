@@ -958,7 +958,7 @@ def measure_configs(a, dev, peak):
     res = {}
     cases = [("config2_1080p_n5", 1920, 1080, 30.0, 5, False, None, 2048),
              ("config4_4k60_n60_mask", 3840, 2160, 60.0, 60, True, "mask-east", 512),
-             ("config5_8k_n30", 7680, 4320, 30.0, 30, True, None, 128)]
+             ("config5_8k_n30", 7680, 4320, 30.0, 30, True, None, 256)]
     for name, W, H, fps, n, dy, mk, B in cases:
         HW = W * H
         mask = np.ones((H, W), np.uint8)

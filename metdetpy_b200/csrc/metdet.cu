@@ -125,6 +125,7 @@ struct mdb_detector {
     HoughParams hp;
     int use_stream_kernel = 1;
     // per-frame O(1) path (perframe_kernel.cuh): resident window state, valid for `pf_timer` frames seen
+    int hough_ctas = 0;              // > 0: grid cap of the shared-memory PPHT tiers
     int per_frame_fast = 1;
     uint16_t *d_pf_sum = nullptr;
     uint8_t *d_pf_pmax = nullptr, *d_pf_suf = nullptr, *d_pf_stage = nullptr;
@@ -525,10 +526,13 @@ static int launch_hough_kernels(mdb_detector *h, BatchCtx *tl, const HoughParams
     if (tl) TL(*tl, 4, st);
     ppht_order_kernel<<<T, 32, HOUGH_ORDER_CAP * 2, st>>>(T, HOUGH_ORDER_CAP, d_npoints, d_order);
     // tier 1a: 2 CTAs/SM (2048 points, 90 KB table); tier 1b: 1 CTA/SM (4096 points, 184 KB table)
-    hough_smem_kernel<<<std::min(T, 2 * h->sm_count), HOUGH_THREADS, HOUGH_SMEM_SMALL + HOUGH_TABLE_BYTES_SMALL, st>>>(
+    // the CTAs take frames from a queue, so the grid only sets how much of the GPU the (latency-bound, shared-memory
+    // hungry) PPHT occupies beside the next batch's temporal pass: hough_ctas = 0 keeps one wave on every SM
+    const int cap_a = h->hough_ctas > 0 ? h->hough_ctas : 2 * h->sm_count, cap_b = h->hough_ctas > 0 ? h->hough_ctas : h->sm_count;
+    hough_smem_kernel<<<std::min(T, cap_a), HOUGH_THREADS, HOUGH_SMEM_SMALL + HOUGH_TABLE_BYTES_SMALL, st>>>(
         hp, T, d_npoints, d_points, d_order, d_lines, d_nlines, d_queue, h->d_prof,
         HOUGH_CAP_SMALL, HOUGH_TABLE_BYTES_SMALL, 0);
-    hough_smem_kernel<<<std::min(T, h->sm_count), HOUGH_THREADS, HOUGH_SMEM_LARGE + HOUGH_TABLE_BYTES, st>>>(
+    hough_smem_kernel<<<std::min(T, cap_b), HOUGH_THREADS, HOUGH_SMEM_LARGE + HOUGH_TABLE_BYTES, st>>>(
         hp, T, d_npoints, d_points, d_order, d_lines, d_nlines, d_queue + 1, h->d_prof,
         HOUGH_CAP_LARGE, HOUGH_TABLE_BYTES, 1);
     if (tl) TL(*tl, 5, st);
@@ -1626,6 +1630,7 @@ extern "C" int mdb_set_option(mdb_handle h, const char *name, int value) {
         return MDB_OK;
     }
     if (!strcmp(name, "stream_kernel")) { h->use_stream_kernel = value; return MDB_OK; }
+    if (!strcmp(name, "hough_ctas")) { h->hough_ctas = value; return MDB_OK; }
     if (!strcmp(name, "per_frame_fast")) { h->per_frame_fast = value; h->pf_timer = h->pf_bits_timer = -1; return MDB_OK; }
     if (!strcmp(name, "timeline")) {
         if (value && !h->tl_base) {
