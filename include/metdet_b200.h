@@ -263,6 +263,9 @@ int mdb_mfnr_create(int height, int width, int channels, int keep_frames, int de
 int mdb_mfnr_append(mdb_mfnr_handle m, const uint8_t *frames, int T, int on_device);
 /* out: (H, W, C) uint8; stats (optional, 4 doubles): est_bg_var, gumbel mean, highlight_avg_diff, count of positive diffs */
 int mdb_mfnr_finish(mdb_mfnr_handle m, const mdb_mfnr_params *params, uint8_t *out, int out_on_device, double *stats);
+/* the running statistics as the reference's containers hold them (stacker.py:43-59): max (uint8), sum (uint16, wrapping),
+ * sum of squares (uint32, wrapping) of the frames appended so far; any output may be NULL; n_frames optional */
+int mdb_mfnr_stats(mdb_mfnr_handle m, uint8_t *max_out, uint16_t *sum_out, uint32_t *sq_out, int64_t *n_frames);
 int mdb_mfnr_destroy(mdb_mfnr_handle m);
 
 /* ---- loader preprocessing on the device ---------------------------

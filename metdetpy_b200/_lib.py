@@ -81,6 +81,7 @@ SYMBOLS = {
     "mdb_mfnr_create": (_I, [_I, _I, _I, _I, _I, C.POINTER(_VP)]),
     "mdb_mfnr_append": (_I, [_VP, _VP, _I, _I]),
     "mdb_mfnr_finish": (_I, [_VP, C.POINTER(MfnrParams), _VP, _I, _VP]),
+    "mdb_mfnr_stats": (_I, [_VP, _VP, _VP, _VP, C.POINTER(C.c_int64)]),
     "mdb_mfnr_destroy": (_I, [_VP]),
     "mdb_preproc_create": (_I, [_I, _I, _I, _I, _I, _I, _VP, _I, _I, _I, C.POINTER(_VP)]),
     "mdb_preproc_run": (_I, [_VP, _VP, _I, _I, _VP, _I, C.POINTER(C.c_int32)]),

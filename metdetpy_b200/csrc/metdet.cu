@@ -1476,7 +1476,6 @@ extern "C" int mdb_mfnr_destroy(mdb_mfnr_handle m) {
 
 extern "C" int mdb_mfnr_append(mdb_mfnr_handle m, const uint8_t *frames, int T, int on_device) {
     if (!m || !frames || T < 1) return fail(MDB_ERR_INVALID, "mdb_mfnr_append: bad arguments");
-    if (m->n_frames + T > 32767) return fail(MDB_ERR_INVALID, "mdb_mfnr_append: more than 32767 frames (the reference's int16 count)");
     CK(cudaSetDevice(m->device));
     const size_t bytes = (size_t)T * m->E;
     uint8_t *buf = nullptr;
@@ -1509,9 +1508,24 @@ extern "C" int mdb_mfnr_append(mdb_mfnr_handle m, const uint8_t *frames, int T, 
     return MDB_OK;
 }
 
+// the running statistics as the reference's containers hold them: MaxImgContainer.container (uint8 max),
+// FastGaussianContainer.container.sum_mu (uint16) / .square_sum (uint32); any of the three may be NULL
+extern "C" int mdb_mfnr_stats(mdb_mfnr_handle m, uint8_t *max_out, uint16_t *sum_out, uint32_t *sq_out, int64_t *n_frames) {
+    if (!m) return fail(MDB_ERR_INVALID, "mdb_mfnr_stats: null handle");
+    if (n_frames) *n_frames = m->n_frames;
+    if (m->n_frames == 0) return (max_out || sum_out || sq_out) ? fail(MDB_ERR_STATE, "mdb_mfnr_stats: no frame appended yet") : MDB_OK;
+    CK(cudaSetDevice(m->device));
+    if (max_out) CK(cudaMemcpyAsync(max_out, m->d_max, m->E, cudaMemcpyDeviceToHost, m->st));
+    if (sum_out) CK(cudaMemcpyAsync(sum_out, m->d_sum, m->E * 2, cudaMemcpyDeviceToHost, m->st));
+    if (sq_out) CK(cudaMemcpyAsync(sq_out, m->d_sq, m->E * 4, cudaMemcpyDeviceToHost, m->st));
+    CK(cudaStreamSynchronize(m->st));
+    return MDB_OK;
+}
+
 extern "C" int mdb_mfnr_finish(mdb_mfnr_handle m, const mdb_mfnr_params *prm, uint8_t *out, int out_on_device, double *stats) {
     if (!m || !prm || !out) return fail(MDB_ERR_INVALID, "mdb_mfnr_finish: null argument");
     if (m->n_frames < 2) return fail(MDB_ERR_STATE, "mdb_mfnr_finish: %lld frames appended, at least 2 are needed", m->n_frames);
+    if (m->n_frames > 32767) return fail(MDB_ERR_INVALID, "mdb_mfnr_finish: %lld frames: the reference's int16 frame count wraps beyond 32767", m->n_frames);
     if (prm->blur_ksize < 1 || prm->blur_ksize % 2 == 0 || prm->blur_ksize > 255)
         return fail(MDB_ERR_INVALID, "mdb_mfnr_finish: blur_ksize %d must be odd and in 1..255", prm->blur_ksize);
     if (prm->bg_algorithm != 0 && prm->bg_algorithm != 1)

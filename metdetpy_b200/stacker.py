@@ -24,38 +24,76 @@ def merge_max(image_stack: Sequence[np.ndarray], device: int = 0) -> np.ndarray:
     return out
 
 
-class MaxImgContainer:
-    """Running max of appended frames (MetLib/stacker.py:43-49). Frames are buffered and reduced on
-    the device in chunks; `container` / `export()` give the current result."""
+class _DeviceAccumulator:
+    """Frames are shipped in chunks to a device-resident accumulator (max, uint16 sum, uint32 sum of squares per element:
+    `mdb_mfnr_append`); nothing but the new frames crosses PCIe, the running result is read back on demand."""
 
-    def __init__(self, chunk: int = 32, device: int = 0):
+    def __init__(self, chunk: int, device: int):
         self._buf: list[np.ndarray] = []
-        self._acc: Optional[np.ndarray] = None
-        self._chunk = chunk
-        self._device = device
+        self._h = None
+        self._chunk, self._device = chunk, device
+        self.shape = None
+        self.count = 0
 
     def append(self, new_frame: np.ndarray) -> None:
-        if self._acc is not None and new_frame.shape != self._acc.shape:
-            raise ValueError(f"Expect new frame has the same shape as the base frame "
-                             f"{self._acc.shape}, got {new_frame.shape}.")
-        if self._buf and new_frame.shape != self._buf[0].shape:
-            raise ValueError(f"Expect new frame has the same shape as the base frame "
-                             f"{self._buf[0].shape}, got {new_frame.shape}.")
-        self._buf.append(np.ascontiguousarray(new_frame, np.uint8))
+        f = np.asarray(new_frame)
+        if f.dtype != np.uint8:
+            raise ValueError(f"uint8 frames expected, got {f.dtype}")
+        if self.shape is None:
+            import ctypes as C
+            if f.ndim not in (2, 3) or (f.ndim == 3 and f.shape[2] > 4):
+                raise ValueError("frames must be (H, W) or (H, W, C <= 4)")
+            self.shape = f.shape
+            h = C.c_void_p()
+            check(_lib.load().mdb_mfnr_create(f.shape[0], f.shape[1], 1 if f.ndim == 2 else f.shape[2], 0, self._device,
+                                              C.byref(h)), "stack accumulator")
+            self._h = h
+        elif f.shape != self.shape:
+            raise ValueError(f"Expect new frame has the same shape as the base frame {self.shape}, got {f.shape}.")
+        self._buf.append(np.ascontiguousarray(f))
         if len(self._buf) >= self._chunk:
             self._flush()
 
     def _flush(self):
-        if not self._buf:
-            return
-        frames = self._buf if self._acc is None else [self._acc] + self._buf
-        self._acc = merge_max(frames, self._device)
-        self._buf = []
+        if self._buf:
+            arr = np.ascontiguousarray(np.stack(self._buf))
+            check(_lib.load().mdb_mfnr_append(self._h, arr.ctypes.data, len(arr), 0), "stack accumulator")
+            self.count += len(arr)
+            self._buf = []
+
+    def _read(self, want_max=False, want_sums=False):
+        self._flush()
+        if self.count == 0:
+            return None, None, None
+        mx = np.empty(self.shape, np.uint8) if want_max else None
+        sm = np.empty(self.shape, np.uint16) if want_sums else None
+        sq = np.empty(self.shape, np.uint32) if want_sums else None
+        p = lambda a: None if a is None else a.ctypes.data
+        check(_lib.load().mdb_mfnr_stats(self._h, p(mx), p(sm), p(sq), None), "stack accumulator")
+        return mx, sm, sq
+
+    def close(self):
+        if self._h is not None:
+            _lib.load().mdb_mfnr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MaxImgContainer(_DeviceAccumulator):
+    """Running max of appended frames (MetLib/stacker.py:43-49), accumulated on the device; `container` / `export()`
+    give the current result."""
+
+    def __init__(self, chunk: int = 32, device: int = 0):
+        super().__init__(chunk, device)
 
     @property
     def container(self) -> Optional[np.ndarray]:
-        self._flush()
-        return self._acc
+        return self._read(want_max=True)[0]
 
     def export(self):
         return self.container
@@ -82,48 +120,52 @@ class FastGaussianParam:
     def shape(self):
         return self.sum_mu.shape
 
+    # arithmetic of the reference class (utils.py:485-509), numpy dtypes and wrap-around as there; host-side result
+    # objects only -- the accumulation itself runs on the device
+    def __add__(self, g2: "FastGaussianParam") -> "FastGaussianParam":
+        assert isinstance(g2, FastGaussianParam), "unacceptable object"
+        assert self.ddof == g2.ddof, "unmatched var calculation!"
+        return FastGaussianParam(self.sum_mu + g2.sum_mu, self.square_sum + g2.square_sum, self.n + g2.n, self.ddof)
 
-class FastGaussianContainer:
+    def __sub__(self, g2: "FastGaussianParam") -> "FastGaussianParam":
+        assert isinstance(g2, FastGaussianParam), "unacceptable object"
+        assert self.ddof == g2.ddof, "unmatched var calculation!"
+        assert (self.n - g2.n).any() >= 0, "generate n<0 fistribution!"
+        return FastGaussianParam(self.sum_mu - g2.sum_mu, self.square_sum - g2.square_sum, self.n - g2.n, self.ddof)
+
+    def mask(self, mask_pos: np.ndarray) -> None:
+        assert mask_pos.dtype == np.dtype("bool"), "Invalid mask!"
+        self.sum_mu *= mask_pos
+        self.square_sum *= mask_pos
+        self.n = np.array(mask_pos, dtype=np.uint16)
+
+    def apply_zero_var(self, full_img: "FastGaussianParam") -> None:
+        zero_pos = (self.n == 0)
+        self.n[zero_pos] = full_img.n[zero_pos]
+        self.sum_mu[zero_pos] = full_img.sum_mu[zero_pos]
+        self.square_sum[zero_pos] = full_img.square_sum[zero_pos]
+
+    def upscale(self) -> None:
+        up = {np.dtype("uint8"): np.dtype("uint16"), np.dtype("uint16"): np.dtype("uint32"), np.dtype("uint32"): np.dtype("uint64")}
+        self.sum_mu = np.array(self.sum_mu, dtype=up.get(self.sum_mu.dtype, float))
+        self.square_sum = np.array(self.square_sum, dtype=up.get(self.square_sum.dtype, float))
+
+
+class FastGaussianContainer(_DeviceAccumulator):
     """FastGaussianContainer (MetLib/stacker.py:52-59): `append(frame)` adds the frame to the running
-    per-element sum / sum of squares.  Frames are buffered and reduced on the device in chunks."""
+    per-element sum / sum of squares, accumulated on the device."""
 
     def __init__(self, chunk: int = 32, device: int = 0):
-        self._buf: list[np.ndarray] = []
-        self._sum: Optional[np.ndarray] = None
-        self._sq: Optional[np.ndarray] = None
-        self._count = 0
-        self._chunk = chunk
-        self._device = device
-
-    def append(self, new_frame: np.ndarray) -> None:
-        if self._buf and new_frame.shape != self._buf[0].shape or \
-                self._sum is not None and new_frame.shape != self._sum.shape:
-            raise ValueError("Expect new frame has the same shape as the base frame")
-        self._buf.append(np.ascontiguousarray(new_frame, np.uint8))
-        if len(self._buf) >= self._chunk:
-            self._flush()
-
-    def _flush(self):
-        if not self._buf:
-            return
-        arr = np.ascontiguousarray(np.stack(self._buf))
-        acc = self._sum is not None
-        if not acc:
-            self._sum = np.empty(arr.shape[1:], np.uint16)
-            self._sq = np.empty(arr.shape[1:], np.uint32)
-        check(_lib.load().mdb_gauss_stack(arr.ctypes.data, len(arr), arr[0].nbytes, self._sum.ctypes.data,
-                                          self._sq.ctypes.data, 0, 0, int(acc), self._device), "FastGaussianContainer")
-        self._count += len(arr)
-        self._buf = []
+        super().__init__(chunk, device)
 
     @property
     def container(self) -> Optional[FastGaussianParam]:
-        self._flush()
-        if self._sum is None:
+        _, sm, sq = self._read(want_sums=True)
+        if sm is None:
             return None
         # n: np.ones_like(sum_mu, dtype=int16) added once per frame (utils.py:450-451, :490-493): wraps at 2^15
-        n = np.full(self._sum.shape, np.array(self._count).astype(np.int64).astype(np.int16), np.int16)
-        return FastGaussianParam(self._sum, self._sq, n)
+        n = np.full(sm.shape, np.array(self.count).astype(np.int64).astype(np.int16), np.int16)
+        return FastGaussianParam(sm, sq, n)
 
     def export(self):
         return self.container
