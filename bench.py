@@ -286,6 +286,7 @@ def measure_next_rows(a, batch0_ptr, dev, peak):
             outb = torch.empty((Hm, Wm, 3), dtype=torch.uint8, device=dev)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
+            check(lib.mdb_mfnr_reserve(h, Tm), "mfnr")
             for s0 in range(0, Tm, 16):
                 check(lib.mdb_mfnr_append(h, clip[s0:s0 + 16].data_ptr(), 16, 1), "mfnr")
             check(lib.mdb_mfnr_finish(h, C.byref(prm), outb.data_ptr(), 1, None), "mfnr")

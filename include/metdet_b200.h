@@ -260,6 +260,8 @@ typedef struct mdb_mfnr_params {
     double gumbel_mean;        /* get_gumbel_mean(n) as the caller computed it, or <= 0 to have it computed here */
 } mdb_mfnr_params;
 int mdb_mfnr_create(int height, int width, int channels, int keep_frames, int device, mdb_mfnr_handle *out);
+/* optional: device memory for `frames` more retained frames in one allocation (keep_frames handles only) */
+int mdb_mfnr_reserve(mdb_mfnr_handle m, int frames);
 int mdb_mfnr_append(mdb_mfnr_handle m, const uint8_t *frames, int T, int on_device);
 /* out: (H, W, C) uint8; stats (optional, 4 doubles): est_bg_var, gumbel mean, highlight_avg_diff, count of positive diffs */
 int mdb_mfnr_finish(mdb_mfnr_handle m, const mdb_mfnr_params *params, uint8_t *out, int out_on_device, double *stats);

@@ -79,6 +79,7 @@ SYMBOLS = {
     "mdb_submit_batch_ex": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP, _I]),
     "mdb_gauss_stack": (_I, [_VP, _I, _SZ, _VP, _VP, _I, _I, _I, _I]),
     "mdb_mfnr_create": (_I, [_I, _I, _I, _I, _I, C.POINTER(_VP)]),
+    "mdb_mfnr_reserve": (_I, [_VP, _I]),
     "mdb_mfnr_append": (_I, [_VP, _VP, _I, _I]),
     "mdb_mfnr_finish": (_I, [_VP, C.POINTER(MfnrParams), _VP, _I, _VP]),
     "mdb_mfnr_stats": (_I, [_VP, _VP, _VP, _VP, C.POINTER(C.c_int64)]),

@@ -4,20 +4,22 @@
 // MWC RNG seeded per call), its float32 rho rounding and its in-loop un-voting, so the emitted
 // segments are identical.
 //
-// Batch path (frames with <= MDB_POINT_CAP on-pixels; shared-memory tiers up to HOUGH_CAP_LARGE):
-//   * the frame's on-pixels are sorted in shared memory (row-major == cv2's nzloc order); the image
-//     mask itself is never touched again: "is pixel q still on" = binary search in the sorted keys
-//     + a removed-bit per point, all in shared memory;
-//   * thread n < 180 owns accumulator row n of this CTA's slot ([180][numrho] int32 in global
-//     memory), so votes need no atomics; the cells of the points that will be visited next are
-//     prefetched into L2 a few visits ahead (the visiting order is known up front);
-//   * arg-max over angles = warp REDUX + one shared-memory hop (double-buffered, one barrier);
-//   * line walks are evaluated 256 steps at a time by the whole CTA (warp ballots), un-voting is a
-//     fire-and-forget RED per (pixel, angle);
-//   * accumulators are never memset: every cell a point of the frame can touch is zeroed by
-//     replaying the point list at the end.
-// Overflow path (hough_global_kernel): same algorithm, sequential walks, point list / visit order /
-// pixel bitmap in global memory -- for dense masks beyond the shared-memory capacity.
+// Tiers (a frame takes the first one it fits; the choice never changes the result):
+//   1a / 1b  hough_smem_kernel: the frame's whole PPHT on chip.  On-pixels sorted in shared memory (row-major == cv2's
+//            nzloc order); "is pixel q still on" = binary search in the sorted keys + a removed-bit per point; the
+//            accumulator is a shared-memory table of per-angle rho INTERVALS (int16 cells; two intervals per angle when
+//            one does not fit: two far-apart objects); thread n < 180 owns angle n, so votes need no atomics; votes of
+//            four points per barrier (exact: a thread reads its cell right after its own increment, votes behind a
+//            line-yielding point are rolled back); arg-max = warp REDUX + one shared-memory hop; line walks 256 steps
+//            at a time by the whole CTA (ballots).  1a: <= 2048 points, 90 KB table, two CTAs per SM; 1b: <= 4096
+//            points, 184 KB table.  CTAs take frames from a queue.
+//   2        hough_tier2_kernel: frames of up to MDB_POINT_CAP points whose intervals do not fit on chip (8K streaks):
+//            same scheme with the accumulator rows in global memory ([180][numrho] int32 per slot), cells of the next
+//            visits prefetched into L2, accumulator cleared by per-angle rho intervals.
+//   3        hough_tier3_kernel: dense masks beyond MDB_POINT_CAP.  Ordered row-wise compaction of the mask into a
+//            global point list, visiting order shuffled in shared memory (up to H3_ORDER_CAP points), visits staged
+//            256 at a time, four votes per barrier, ballot walks on a pixel bitmap, isolated pixels skipped by a
+//            neighbour flag; up to one CTA per SM, each with its own scratch slot.
 #pragma once
 #include <limits.h>
 

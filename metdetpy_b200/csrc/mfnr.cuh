@@ -13,6 +13,23 @@
 #define MF_THREADS 256
 #define MF_PARTS 1024  // blocks of the reduction kernels = partial sums
 
+// V consecutive bytes at p (V = 1, 4 or 16; p aligned to V) as V unsigned values
+template <int V>
+__device__ __forceinline__ void mf_load(const uint8_t *p, unsigned (&x)[V]) {
+    if (V == 16) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(p));
+        const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int v = 0; v < V; v++) x[v] = (ws[v >> 2] >> (8 * (v & 3))) & 0xffu;
+    } else if (V == 4) {
+        const unsigned w = __ldg(reinterpret_cast<const unsigned *>(p));
+#pragma unroll
+        for (int v = 0; v < V; v++) x[v] = (w >> (8 * v)) & 0xffu;
+    } else {
+        x[0] = __ldg(p);
+    }
+}
+
 struct MfnrChunks {  // frames retained on the device, chunk by chunk
     const uint8_t *const *ptr;
     const int *count;
@@ -32,15 +49,10 @@ mfnr_accum_kernel(const uint8_t *__restrict__ frames, int T, size_t E, uint8_t *
         s[v] = first ? 0u : sum[i0 + v];
         q[v] = first ? 0u : sq[i0 + v];
     }
+#pragma unroll 4
     for (int t = 0; t < T; t++) {
         unsigned x[V];
-        if (V == 4) {
-            const unsigned w = __ldg(reinterpret_cast<const unsigned *>(frames + (size_t)t * E + i0));
-#pragma unroll
-            for (int v = 0; v < V; v++) x[v] = (w >> (8 * v)) & 0xffu;
-        } else {
-            x[0] = __ldg(frames + (size_t)t * E + i0);
-        }
+        mf_load<V>(frames + (size_t)t * E + i0, x);
 #pragma unroll
         for (int v = 0; v < V; v++) {
             m[v] = max(m[v], x[v]);
@@ -67,27 +79,42 @@ __device__ __forceinline__ uint8_t mf_u8(double v) {  // np.round(v).clip(0, 255
     return (uint8_t)r;
 }
 
-// single_sigma_clipping (stacker.py:94-115): subtract the clipped frames' contributions; n becomes per-element
+// single_sigma_clipping (stacker.py:94-115): subtract the clipped frames' contributions; n becomes per-element.
+// V = 4: four elements per thread, one 32-bit load per frame (E and every chunk base are multiples of 4 / 256-byte aligned)
+template <int V>
 __global__ void __launch_bounds__(MF_THREADS)
 mfnr_sigma_kernel(MfnrChunks ch, size_t E, int N, double sigma_high, double sigma_low, const uint16_t *sum, const uint32_t *sq,
                   uint16_t *sum_out, uint32_t *sq_out, int32_t *n_out) {
-    const size_t i = blockIdx.x * (size_t)MF_THREADS + threadIdx.x;
-    if (i >= E) return;
-    const unsigned s = sum[i], q = sq[i];
+    const size_t i0 = (blockIdx.x * (size_t)MF_THREADS + threadIdx.x) * V;
+    if (i0 >= E) return;
     const int n16 = (int)(int16_t)N;  // n is an int16 array in the reference (utils.py:450-451)
-    const double mu = mf_mu(s, n16), sd = sqrt(mf_var(s, q, n16));
-    const unsigned hi = mf_u8(mu + sigma_high * sd), lo = mf_u8(mu - sigma_low * sd);
-    unsigned cs = 0, cq = 0, cn = 0;
+    unsigned s[V], q[V], hi[V], lo[V], cs[V], cq[V], cn[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+        s[v] = sum[i0 + v]; q[v] = sq[i0 + v];
+        const double mu = mf_mu(s[v], n16), sd = sqrt(mf_var(s[v], q[v], n16));
+        hi[v] = mf_u8(mu + sigma_high * sd);
+        lo[v] = mf_u8(mu - sigma_low * sd);
+        cs[v] = cq[v] = cn[v] = 0;
+    }
     for (int c = 0; c < ch.n; c++) {
-        const uint8_t *p = ch.ptr[c] + i;
-        for (int t = 0; t < ch.count[c]; t++, p += E) {
-            const unsigned x = __ldg(p);
-            if (x > hi || x < lo) { cs += x; cq += x * x; cn += 1; }
+        const uint8_t *p = ch.ptr[c] + i0;
+        const int cnt = ch.count[c];
+#pragma unroll 4
+        for (int t = 0; t < cnt; t++, p += E) {
+            unsigned x[V];
+            mf_load<V>(p, x);
+#pragma unroll
+            for (int v = 0; v < V; v++)
+                if (x[v] > hi[v] || x[v] < lo[v]) { cs[v] += x[v]; cq[v] += x[v] * x[v]; cn[v] += 1; }
         }
     }
-    sum_out[i] = (uint16_t)(s - (uint16_t)cs);
-    sq_out[i] = q - cq;
-    n_out[i] = n16 - (int)(uint16_t)cn;  // int16 - uint16 -> int32 in numpy
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+        sum_out[i0 + v] = (uint16_t)(s[v] - (uint16_t)cs[v]);
+        sq_out[i0 + v] = q[v] - cq[v];
+        n_out[i0 + v] = n16 - (int)(uint16_t)cn[v];  // int16 - uint16 -> int32 in numpy
+    }
 }
 
 // block-level deterministic sum of (value, count): partial[blockIdx.x]
@@ -134,14 +161,18 @@ mfnr_diffpos_kernel(size_t E, int N, double c1, const uint8_t *mx, const uint16_
     mf_block_reduce(acc, cnt, part_v, part_c);
 }
 
+// one warp, fixed order: lane l sums partials l, l+32, ...; then a shuffle tree
 __global__ void mfnr_final_reduce_kernel(int parts, const double *part_v, const unsigned long long *part_c, double *out_v,
                                          unsigned long long *out_c) {
-    if (threadIdx.x || blockIdx.x) return;
+    if (blockIdx.x || threadIdx.x >= 32) return;
     double v = 0.0;
     unsigned long long c = 0;
-    for (int k = 0; k < parts; k++) { v += part_v[k]; c += part_c[k]; }
-    *out_v = v;
-    *out_c = c;
+    for (int k = threadIdx.x; k < parts; k += 32) { v += part_v[k]; c += part_c[k]; }
+    for (int o = 16; o; o >>= 1) {
+        v += __shfl_down_sync(0xffffffffu, v, o);
+        c += __shfl_down_sync(0xffffffffu, c, o);
+    }
+    if (threadIdx.x == 0) { *out_v = v; *out_c = c; }
 }
 
 // fg_mask (stacker.py:358-365): a pixel is foreground when any of its channels is an outlier or a highlight
@@ -173,8 +204,15 @@ mfnr_blur_row_kernel(int H, int W, int ksize, const double *__restrict__ k, cons
     if (p >= (size_t)H * W) return;
     const int y = (int)(p / W), x = (int)(p % W), r = ksize / 2;
     const uint8_t *src = fg + (size_t)y * W;
-    double s = k[0] * (double)src[mf_reflect101(x - r, W)];
-    for (int j = 1; j < ksize; j++) s += k[j] * (double)src[mf_reflect101(x - r + j, W)];
+    double s;
+    if (x >= r && x + r < W) {  // interior: no border arithmetic (same taps, same order)
+        const uint8_t *q = src + x - r;
+        s = k[0] * (double)q[0];
+        for (int j = 1; j < ksize; j++) s += k[j] * (double)q[j];
+    } else {
+        s = k[0] * (double)src[mf_reflect101(x - r, W)];
+        for (int j = 1; j < ksize; j++) s += k[j] * (double)src[mf_reflect101(x - r + j, W)];
+    }
     row[p] = s;
 }
 
@@ -185,8 +223,12 @@ mfnr_blur_col_kernel(int H, int W, int ksize, const double *__restrict__ k, cons
     if (p >= (size_t)H * W) return;
     const int y = (int)(p / W), x = (int)(p % W), r = ksize / 2;
     double s = k[r] * row[p];
-    for (int j = 1; j <= r; j++)
-        s += k[r + j] * (row[(size_t)mf_reflect101(y + j, H) * W + x] + row[(size_t)mf_reflect101(y - j, H) * W + x]);
+    if (y >= r && y + r < H) {
+        for (int j = 1; j <= r; j++) s += k[r + j] * (row[p + (size_t)j * W] + row[p - (size_t)j * W]);
+    } else {
+        for (int j = 1; j <= r; j++)
+            s += k[r + j] * (row[(size_t)mf_reflect101(y + j, H) * W + x] + row[(size_t)mf_reflect101(y - j, H) * W + x]);
+    }
     out[p] = s;
 }
 

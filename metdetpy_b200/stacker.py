@@ -244,9 +244,15 @@ class MfnrMixContainer:
         if len(self._buf) >= self._chunk:
             self._flush()
 
+    def expect(self, frames: int) -> None:
+        """How many frames the clip will deliver: the device memory for them is then reserved in one piece."""
+        self._expect = max(0, int(frames))
+
     def _flush(self):
         if self._buf:
             arr = np.ascontiguousarray(np.stack(self._buf))
+            if self._keep and self.count == 0 and getattr(self, "_expect", 0):
+                check(_lib.load().mdb_mfnr_reserve(self._h, self._expect), "mfnr reserve")
             check(_lib.load().mdb_mfnr_append(self._h, arr.ctypes.data, len(arr), 0), "mfnr append")
             self.count += len(arr)
             self._buf = []
@@ -297,6 +303,7 @@ def mfnr_mix_stacker(video_loader: Any, denoise_cfg: Any, start_frame: Optional[
             if start_frame is not None or end_frame is not None:
                 video_loader.reset(start_frame=start_frame, end_frame=end_frame)
             video_loader.start()
+            box.expect(int(video_loader.iterations))
             for _ in range(video_loader.iterations):
                 img = video_loader.pop()
                 if img is None:

@@ -6,10 +6,12 @@
     kernel (two independent implementations) agree bit for bit; splitting the stream into different
     batch sizes changes nothing; `on-pixel count == popcount(dst)`; dst is {0,255}; zero-copy device
     input == host input."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import assert_nms_equivalent
+from conftest import GOLDEN, assert_nms_equivalent
 
 pytestmark = pytest.mark.gpu
 
@@ -19,15 +21,11 @@ def _cfg(dy=True):
     return BinaryCfg(BinaryCoreCfg(True, 7, "normal", 0.1, 2), HoughLineCfg(10, 10, 10), DynamicCfg(dy, 5))
 
 
-def _synthetic_mask(H, W):
-    """Stand-in for test/mask-east.jpg (not shipped to the GPU box): ground + a tree line, ~90 % open."""
-    m = np.ones((H, W), np.uint8)
-    m[int(H * 0.93):, :] = 0
-    xs = np.arange(W)
-    ridge = (H * 0.93 - H * 0.05 * (1 + np.sin(xs / W * 9.0))).astype(int)
-    for x in range(0, W, 1):
-        m[ridge[x]:, x] = 0
-    return m
+def _real_mask(H, W):
+    """test/mask-east.jpg of the reference through fileio.load_mask (MetLib/fileio.py:250-292) at this size, committed
+    bit-packed by tests/golden/make_golden.py (the reference tree does not exist on the GPU box)."""
+    z = np.load(os.path.join(GOLDEN, f"mask_east_{W}x{H}.npz"))
+    return np.unpackbits(z["bits"])[:H * W].reshape(H, W).astype(np.uint8)
 
 
 @pytest.mark.parametrize("name,W,H,fps,n,dy,masked,T", [
@@ -41,7 +39,7 @@ def test_baseline_config_against_oracle(name, W, H, fps, n, dy, masked, T):
     from metdetpy_b200.detector import M3Detector
     from oracle import m3_oracle as O
     frames = synth.make_stream(T, W, H, fps)
-    mask = _synthetic_mask(H, W) if masked else np.ones((H, W), np.uint8)
+    mask = _real_mask(H, W) if masked else np.ones((H, W), np.uint8)
     ref = O.M3DetectorOracle(n / fps + 1e-9, fps, mask, 10, adaptive=True, init_value=7, sensitivity="normal",
                              area=0.1, interval=2, hough=(10, 10, 10), dy_mask=dy,
                              backend="cv2" if O.cv2 is not None else "numpy")
