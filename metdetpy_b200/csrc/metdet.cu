@@ -125,6 +125,9 @@ struct mdb_detector {
     HoughParams hp;
     int use_stream_kernel = 1;
     // per-frame O(1) path (perframe_kernel.cuh): resident window state, valid for `pf_timer` frames seen
+    bool single_stream = false;      // set around the per-frame chain: everything on the front stream
+    cudaEvent_t ev_suffix = nullptr; // the suffix planes of the block that just ended are rebuilt (back stream)
+    cudaEvent_t ev_pf_a = nullptr, ev_pf_b = nullptr, ev_pf_done = nullptr;  // per-frame copy halves / staging buffer free
     int hough_ctas = 0;              // > 0: grid cap of the shared-memory PPHT tiers
     int per_frame_fast = 1;
     uint16_t *d_pf_sum = nullptr;
@@ -132,6 +135,7 @@ struct mdb_detector {
     long long pf_timer = -1;         // frames the state has absorbed (-1: rebuild from the ring before use)
     long long pf_bits_timer = -1;    // the predicate bits in sk.d_bits belong to frame pf_bits_timer - 1
     bool pf_suffix_pending = false;  // the block that just ended still needs its suffix planes
+    bool pf_suffix_wait = false;     // ... they are being rebuilt: the next update kernel waits for ev_suffix
     int timeline = 0;                // debug: record per-kernel timeline events
     cudaEvent_t tl_base = nullptr;
 };
@@ -204,6 +208,9 @@ static void free_all(mdb_detector *h) {
     }
     if (h->ev_copy) cudaEventDestroy(h->ev_copy);
     if (h->ev_front) cudaEventDestroy(h->ev_front);
+    if (h->ev_suffix) cudaEventDestroy(h->ev_suffix);
+    for (cudaEvent_t e : {h->ev_pf_a, h->ev_pf_b, h->ev_pf_done})
+        if (e) cudaEventDestroy(e);
     if (h->sstream) cudaStreamDestroy(h->sstream);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream2) cudaStreamDestroy(h->stream2);
@@ -310,6 +317,10 @@ extern "C" int mdb_create(const mdb_config *cfg, const uint8_t *mask, mdb_handle
     }
     CKH(cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming));
     CKH(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+    CKH(cudaEventCreateWithFlags(&h->ev_suffix, cudaEventDisableTiming));
+    CKH(cudaEventCreateWithFlags(&h->ev_pf_a, cudaEventDisableTiming));
+    CKH(cudaEventCreateWithFlags(&h->ev_pf_b, cudaEventDisableTiming));
+    CKH(cudaEventCreateWithFlags(&h->ev_pf_done, cudaEventDisableTiming));
     const size_t bm_words = (h->HW + 31) / 32;
     h->Wb = (h->W + 31) / 32;
     h->RA = h->n - 1 + (T > 1 ? 2 * T : 1);  // two batches: act of batch k+1 is written while dst of batch k reads
@@ -451,7 +462,9 @@ static int launch_noise_thr(mdb_detector *h, BatchCtx &bc, const FrameSrc &src, 
 // front stream, dst on the back stream
 static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T, long long timer0, long long dy0,
                         bool bits_ready = false) {
-    CK(cudaMemsetAsync(c.d_npoints, 0, T * sizeof(unsigned), h->stream2));
+    // per-frame calls (single_stream) keep the whole chain on the front stream: no cross-stream hand-overs on the latency path
+    cudaStream_t s2 = h->single_stream ? h->stream : h->stream2;
+    CK(cudaMemsetAsync(c.d_npoints, 0, T * sizeof(unsigned), s2));
     CK(cudaEventRecord(c.ev_f0, h->stream));
     int nl = 0;
     if (h->cfg.detector == 1) {
@@ -468,49 +481,49 @@ static int launch_fused(mdb_detector *h, BatchCtx &c, const FrameSrc &src, int T
             ab, bb, h->H, h->Wb, rows, strips, bands, db);
         CK(cudaGetLastError());
         CK(cudaEventRecord(c.ev_f1, h->stream));
-        CK(cudaStreamWaitEvent(h->stream2, c.ev_f1, 0));
-        CK(cudaEventRecord(c.ev_d0, h->stream2));
+        CK(cudaStreamWaitEvent(s2, c.ev_f1, 0));
+        CK(cudaEventRecord(c.ev_d0, s2));
         c.dst_dirty = true;
         if (h->W % 16 == 0)
-            classic_expand_kernel<true><<<dim3((nthreads + 255) / 256, T), 256, 0, h->stream2>>>(
+            classic_expand_kernel<true><<<dim3((nthreads + 255) / 256, T), 256, 0, s2>>>(
                 db, h->W, h->H, h->Wb, c.d_dst, c.d_npoints, c.d_points, MDB_POINT_CAP);
         else
-            classic_expand_kernel<false><<<dim3((nthreads + 255) / 256, T), 256, 0, h->stream2>>>(
+            classic_expand_kernel<false><<<dim3((nthreads + 255) / 256, T), 256, 0, s2>>>(
                 db, h->W, h->H, h->Wb, c.d_dst, c.d_npoints, c.d_points, MDB_POINT_CAP);
         nl = 3;
     } else if (h->use_stream_kernel && stream_kernel_supported(h->sk, T)) {
         if (c.dst_dirty) {  // the generic kernel wrote this buffer last: resynchronise buffer and bitmap
-            CK(cudaMemsetAsync(c.d_dst, 0, (size_t)h->cfg.max_batch * h->HW, h->stream2));
-            CK(cudaMemsetAsync(c.d_dstbits, 0, (size_t)h->cfg.max_batch * h->H * h->Wb * sizeof(uint32_t), h->stream2));
-            CK(cudaMemsetAsync(c.d_wcount, 0, (size_t)h->cfg.max_batch * sizeof(unsigned), h->stream2));
+            CK(cudaMemsetAsync(c.d_dst, 0, (size_t)h->cfg.max_batch * h->HW, s2));
+            CK(cudaMemsetAsync(c.d_dstbits, 0, (size_t)h->cfg.max_batch * h->H * h->Wb * sizeof(uint32_t), s2));
+            CK(cudaMemsetAsync(c.d_wcount, 0, (size_t)h->cfg.max_batch * sizeof(unsigned), s2));
             c.dst_dirty = false;
         }
         SparseLists sl;
         sl.alist = c.d_alist; sl.acount = c.d_acount; sl.wlist = c.d_wlist; sl.wcount = c.d_wcount; sl.dense = c.d_dense;
         int rc = stream_kernel_launch(h->sk, src, timer0, dy0, T, h->cfg.dy_mask, c.d_thr, act_ring(h),
                                       c.d_dst, c.d_dstbits, c.d_npoints, c.d_points, MDB_POINT_CAP, sl, h->stream,
-                                      h->stream2, c.ev_f1, c.ev_d0, bits_ready ? 0 : (int)(c.bits_parity & 1), &nl, c.halo,
+                                      s2, c.ev_f1, c.ev_d0, bits_ready ? 0 : (int)(c.bits_parity & 1), &nl, c.halo,
                                       bits_ready);
         if (rc != 0) return fail(MDB_ERR_CUDA, "stream kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
         // generic per-frame kernel: the whole chain runs on the back stream, after the front stream's thresholds
         CK(cudaEventRecord(c.ev_f1, h->stream));
-        CK(cudaStreamWaitEvent(h->stream2, c.ev_f1, 0));
-        CK(cudaEventRecord(c.ev_d0, h->stream2));
+        CK(cudaStreamWaitEvent(s2, c.ev_f1, 0));
+        CK(cudaEventRecord(c.ev_d0, s2));
         c.dst_dirty = true;
         dim3 grid((h->W + V1_TW - 1) / V1_TW, (h->H + V1_TH - 1) / V1_TH);
         for (int i = 0; i < T; i++) {
             const long long t = timer0 + i;
             const int L = (int)std::min<long long>(h->n, t + 1);
             const int Ldy = (int)std::min<long long>(h->n, dy0 + i + 1);
-            fused_frame_kernel<<<grid, 256, 0, h->stream2>>>(
+            fused_frame_kernel<<<grid, 256, 0, s2>>>(
                 src, h->W, h->H, h->n, t, L, dy0 + i, Ldy, h->cfg.dy_mask, c.d_thr + i, act_ring(h),
                 c.d_dst + (size_t)i * h->HW, c.d_npoints + i, c.d_points + (size_t)i * MDB_POINT_CAP,
                 MDB_POINT_CAP);
             nl++;
         }
     }
-    CK(cudaEventRecord(c.ev_d1, h->stream2));
+    CK(cudaEventRecord(c.ev_d1, s2));
     h->fused_launches = nl;
     h->launches += nl;
     CK(cudaGetLastError());
@@ -551,27 +564,28 @@ static int launch_hough_kernels(mdb_detector *h, BatchCtx *tl, const HoughParams
 }
 
 static int launch_hough_and_copy(mdb_detector *h, BatchCtx &c, int T) {
-    CK(cudaStreamWaitEvent(h->stream3, c.ev_d1, 0));  // dst (stream2) has produced the on-pixel lists
+    cudaStream_t s3 = h->single_stream ? h->stream : h->stream3;
+    CK(cudaStreamWaitEvent(s3, c.ev_d1, 0));  // dst (stream2) has produced the on-pixel lists
     if (c.halo) {  // no results wanted: empty masks, no lines
         memset(c.h_tiers, 0, 4 * sizeof(unsigned));
-        CK(cudaMemsetAsync(c.d_npoints, 0, T * sizeof(unsigned), h->stream3));
-        CK(cudaMemsetAsync(c.d_nlines, 0, T * sizeof(int), h->stream3));
-        CK(cudaMemsetAsync(c.d_queue, 0, 8 * sizeof(unsigned), h->stream3));
-        CK(cudaMemcpyAsync(c.h_res, c.d_res, c.res_head, cudaMemcpyDeviceToHost, h->stream3));  // scalars only
-        CK(cudaEventRecord(c.ev_done, h->stream3));
+        CK(cudaMemsetAsync(c.d_npoints, 0, T * sizeof(unsigned), s3));
+        CK(cudaMemsetAsync(c.d_nlines, 0, T * sizeof(int), s3));
+        CK(cudaMemsetAsync(c.d_queue, 0, 8 * sizeof(unsigned), s3));
+        CK(cudaMemcpyAsync(c.h_res, c.d_res, c.res_head, cudaMemcpyDeviceToHost, s3));  // scalars only
+        CK(cudaEventRecord(c.ev_done, s3));
         return MDB_OK;
     }
     int rc = launch_hough_kernels(h, &c, h->hp, T, c.d_npoints, c.d_points, c.d_order, c.d_dst, c.d_lines, c.d_nlines, c.d_queue,
-                                  h->stream3);
+                                  s3);
     if (rc) return rc;
     h->launches += 5;
-    TL(c, 6, h->stream3);
+    TL(c, 6, s3);
     CK(cudaGetLastError());
     // one copy brings back the scalars of the whole batch and the line rows of its T frames
     CK(cudaMemcpyAsync(c.h_res, c.d_res, c.res_head + (size_t)T * MDB_MAX_LINES * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                       h->stream3));
-    CK(cudaEventRecord(c.ev_done, h->stream3));
-    TL(c, 7, h->stream3);
+                       s3));
+    CK(cudaEventRecord(c.ev_done, s3));
+    TL(c, 7, s3);
     return MDB_OK;
 }
 
@@ -743,8 +757,14 @@ static int pf_launch_suffix(mdb_detector *h) {
     const unsigned grid = (unsigned)((groups + PF_THREADS - 1) / PF_THREADS);
     const long long hi = h->timer - 1, lo = h->timer - h->n + 1;
     const FrameSrc src = frame_src(h, nullptr, 0);
-    if (src.mask) pf_suffix_kernel<true><<<grid, PF_THREADS, 0, h->stream>>>(src, hi, lo, h->n - 1, h->d_pf_suf, groups);
-    else pf_suffix_kernel<false><<<grid, PF_THREADS, 0, h->stream>>>(src, hi, lo, h->n - 1, h->d_pf_suf, groups);
+    // on the back stream, behind the update kernel of the block's last frame (ev_front): it runs beside that frame's
+    // chain and the next frame's copy; the next update kernel waits for ev_suffix
+    CK(cudaEventRecord(h->ev_front, h->stream));
+    CK(cudaStreamWaitEvent(h->stream2, h->ev_front, 0));
+    if (src.mask) pf_suffix_kernel<true><<<grid, PF_THREADS, 0, h->stream2>>>(src, hi, lo, h->n - 1, h->d_pf_suf, groups);
+    else pf_suffix_kernel<false><<<grid, PF_THREADS, 0, h->stream2>>>(src, hi, lo, h->n - 1, h->d_pf_suf, groups);
+    CK(cudaEventRecord(h->ev_suffix, h->stream2));
+    h->pf_suffix_wait = true;
     h->launches += 1;
     h->pf_suffix_pending = false;
     CK(cudaGetLastError());
@@ -767,6 +787,10 @@ static int pf_update(mdb_detector *h, const uint8_t *frame, int on_device) {
         if (rc) return rc;
     }
     if (h->pf_timer != h->timer) {  // batched calls, reset or seek moved the stream on: rebuild from the ring
+        if (h->pf_suffix_wait) {
+            CK(cudaStreamWaitEvent(h->stream, h->ev_suffix, 0));
+            h->pf_suffix_wait = false;
+        }
         const FrameSrc src = frame_src(h, nullptr, 0);
         if (src.mask) pf_rebuild_kernel<true><<<grid, PF_THREADS, 0, h->stream>>>(src, h->timer, h->n, h->d_pf_sum, h->d_pf_pmax, h->d_pf_suf, groups);
         else pf_rebuild_kernel<false><<<grid, PF_THREADS, 0, h->stream>>>(src, h->timer, h->n, h->d_pf_sum, h->d_pf_pmax, h->d_pf_suf, groups);
@@ -775,10 +799,27 @@ static int pf_update(mdb_detector *h, const uint8_t *frame, int on_device) {
         CK(cudaGetLastError());
     }
     const long long t = h->timer;
-    CK(cudaMemcpyAsync(h->d_pf_stage, frame, h->HW, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
-    // noise sample + threshold of this frame: newest frame from the staging buffer, older ones from the ring
-    int rc = launch_noise_thr(h, h->ctx[0], frame_src(h, h->d_pf_stage, t), 1, t, h->stream);
+    // the frame arrives on the copy stream in two halves; the update kernel follows half by half on the front stream,
+    // and on frames that are not noise-sample timers (nearly all) the threshold recurrence runs beside the copy
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const size_t gA = groups / 2, bytesA = gA * 16;
+    CK(cudaStreamWaitEvent(h->cstream, h->ev_pf_done, 0));  // the staging buffer's last reader (previous update kernel)
+    CK(cudaMemcpyAsync(h->d_pf_stage, frame, bytesA, kind, h->cstream));
+    CK(cudaEventRecord(h->ev_pf_a, h->cstream));
+    CK(cudaMemcpyAsync(h->d_pf_stage + bytesA, frame + bytesA, h->HW - bytesA, kind, h->cstream));
+    CK(cudaEventRecord(h->ev_pf_b, h->cstream));
+    const long long tau = t + 1, std_interval = (long long)h->cfg.nz_interval * h->n;
+    const bool sample = (tau > 1 && tau <= h->n) || (tau > h->n && std_interval > 0 && tau % std_interval == 0);
+    int rc = MDB_OK;
+    if (!sample) rc = launch_noise_thr(h, h->ctx[0], frame_src(h, h->d_pf_stage, t), 1, t, h->stream);
     if (rc) return rc;
+    CK(cudaStreamWaitEvent(h->stream, h->ev_pf_a, 0));
+    if (sample) {
+        // noise sample + threshold of this frame: newest frame from the staging buffer, older ones from the ring
+        CK(cudaStreamWaitEvent(h->stream, h->ev_pf_b, 0));
+        rc = launch_noise_thr(h, h->ctx[0], frame_src(h, h->d_pf_stage, t), 1, t, h->stream);
+        if (rc) return rc;
+    }
     const int pos = (int)(t % h->n);
     const int L = (int)std::min<long long>(h->n, t + 1);
     uint8_t *slot = h->d_ring + (size_t)(t % h->R) * h->HW;
@@ -786,13 +827,24 @@ static int pf_update(mdb_detector *h, const uint8_t *frame, int on_device) {
     // window = prefix of the current block + suffix [pos+1 ..] of the previous one (none for the block's last frame)
     const uint8_t *suf = (pos < h->n - 1) ? h->d_pf_suf + (size_t)(pos + 1) * h->HW : nullptr;
     uint16_t *bits = reinterpret_cast<uint16_t *>(h->sk.d_bits);
-    if (h->cfg.apply_mask)
-        pf_update_kernel<true><<<grid, PF_THREADS, 0, h->stream>>>(h->d_pf_stage, slot, old, h->d_mask, h->d_pf_sum, h->d_pf_pmax, suf,
-                                                                  pos == 0, L, h->ctx[0].d_thr, groups, bits);
-    else
-        pf_update_kernel<false><<<grid, PF_THREADS, 0, h->stream>>>(h->d_pf_stage, slot, old, nullptr, h->d_pf_sum, h->d_pf_pmax, suf,
-                                                                   pos == 0, L, h->ctx[0].d_thr, groups, bits);
-    h->launches += 1;
+    if (h->pf_suffix_wait) {
+        CK(cudaStreamWaitEvent(h->stream, h->ev_suffix, 0));
+        h->pf_suffix_wait = false;
+    }
+    for (int half = 0; half < 2; half++) {
+        const size_t g0 = half ? gA : 0, g1 = half ? groups : gA;
+        if (half) CK(cudaStreamWaitEvent(h->stream, h->ev_pf_b, 0));
+        if (g1 == g0) continue;
+        const unsigned gh = (unsigned)((g1 - g0 + PF_THREADS - 1) / PF_THREADS);
+        if (h->cfg.apply_mask)
+            pf_update_kernel<true><<<gh, PF_THREADS, 0, h->stream>>>(h->d_pf_stage, slot, old, h->d_mask, h->d_pf_sum, h->d_pf_pmax, suf,
+                                                                    pos == 0, L, h->ctx[0].d_thr, g0, g1, bits);
+        else
+            pf_update_kernel<false><<<gh, PF_THREADS, 0, h->stream>>>(h->d_pf_stage, slot, old, nullptr, h->d_pf_sum, h->d_pf_pmax, suf,
+                                                                     pos == 0, L, h->ctx[0].d_thr, g0, g1, bits);
+        h->launches += 1;
+    }
+    CK(cudaEventRecord(h->ev_pf_done, h->stream));
     CK(cudaGetLastError());
     h->timer += 1;
     h->pf_timer = h->pf_bits_timer = h->timer;
@@ -832,15 +884,16 @@ extern "C" int mdb_detect(mdb_handle h, mdb_frame_info *info, int32_t *lines, do
     c.halo = false;
     // update() of this frame already left its predicate bits behind (per-frame O(1) path): spatial passes only
     const bool bits_ready = pf_usable(h) && h->pf_bits_timer == h->timer;
-    rc = launch_fused(h, c, frame_src(h, nullptr, 0), 1, h->timer - 1, h->dy_timer, bits_ready);
-    if (rc) return rc;
-    rc = launch_hough_and_copy(h, c, 1);
-    if (rc) return rc;
-    if (h->pf_suffix_pending && h->pf_timer == h->timer) {  // behind this frame's chain, beside its Hough pass
+    if (bits_ready && h->pf_suffix_pending && h->pf_timer == h->timer) {  // on the back stream, beside this frame's chain
         rc = pf_launch_suffix(h);
         if (rc) return rc;
     }
-    CK(cudaStreamSynchronize(h->stream3));
+    h->single_stream = bits_ready;  // a frame whose bits are ready runs its spatial passes and PPHT on the front stream
+    rc = launch_fused(h, c, frame_src(h, nullptr, 0), 1, h->timer - 1, h->dy_timer, bits_ready);
+    if (!rc) rc = launch_hough_and_copy(h, c, 1);
+    h->single_stream = false;
+    if (rc) return rc;
+    CK(cudaEventSynchronize(c.ev_done));
     {
         float a = 0.f, b = 0.f;
         CK(cudaEventElapsedTime(&a, c.ev_f0, c.ev_f1));

@@ -31,8 +31,8 @@ template <bool MASKED>
 __global__ void __launch_bounds__(PF_THREADS)
 pf_update_kernel(const uint8_t *__restrict__ cur, uint8_t *slot, const uint8_t *old, const uint8_t *__restrict__ mask,
                  uint16_t *S, uint8_t *P, const uint8_t *__restrict__ suf, int first_of_block, int L,
-                 const int *__restrict__ thr_ptr, size_t groups, uint16_t *bits) {
-    const size_t g = blockIdx.x * (size_t)PF_THREADS + threadIdx.x;
+                 const int *__restrict__ thr_ptr, size_t g_begin, size_t groups, uint16_t *bits) {
+    const size_t g = g_begin + blockIdx.x * (size_t)PF_THREADS + threadIdx.x;  // groups [g_begin, groups) of the frame
     if (g >= groups) return;
     uint4 x = pf_ld(cur, g);
     uint4 o = make_uint4(0, 0, 0, 0), sf = o, p = o;
