@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--fps", type=float, default=30.0)
     ap.add_argument("--window", type=int, default=30)
     ap.add_argument("--batch", type=int, default=512, help="frames per library call (per GPU)")
-    ap.add_argument("--bps", type=int, default=12, help="batches per step (a multiple of 4 keeps every rank's chunk in phase "
+    ap.add_argument("--bps", type=int, default=16, help="batches per step (a multiple of 4 keeps every rank's chunk in phase "
                                                         "with the replayed stream)")
     ap.add_argument("--no-dy", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (2, 4, 5)")
     ap.add_argument("--no-extra", action="store_true", help="skip per_frame_api and dense_regime")
     ap.add_argument("--no-parity", action="store_true", help="skip the sequential re-run that checks the sharded result")
-    ap.add_argument("--parity-budget", type=int, default=2600, help="most batches a rank re-runs sequentially for the parity check")
+    ap.add_argument("--parity-budget", type=int, default=4000, help="most batches a rank re-runs sequentially for the parity check")
     ap.add_argument("--generic-kernel", action="store_true", help="force the per-frame fused kernel")
     return ap.parse_args()
 

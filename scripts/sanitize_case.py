@@ -6,6 +6,7 @@ import numpy as np
 from metdetpy_b200 import BinaryCfg, BinaryCoreCfg, DynamicCfg, HoughLineCfg, synth, stacker
 from metdetpy_b200.detector import M3Detector
 W, H, FPS, n, T = 256, 96, 30, 5, 24
+rng_m = np.random.default_rng(4)
 frames = synth.make_stream(T, W, H, FPS, speed_scale=3.0, thickness=2)
 mask = np.ones((H, W), np.uint8); mask[80:, :] = 0
 cfg = BinaryCfg(BinaryCoreCfg(True, 7, "normal", 0.2, 1), HoughLineCfg(8, 8, 6), DynamicCfg(True, 5))
@@ -37,6 +38,24 @@ for nn in (30, 60):
     print("temporal3 n", nn, "lines", sum(len(r[0]) for s in range(0, 80, 40) for r in d3.detect_many(fr[s:s + 40])),
           "generation", int(d3._eng.info("temporal_generation")))
     d3.close()
+# per-frame API on the resident-state path across two block ends, a batched call in between (state rebuild), read-backs
+dp = M3Detector(n / FPS + 1e-9, FPS, mask, 10, cfg, None, max_batch=4, apply_mask=True)
+for t in range(12):
+    dp.update(frames[t]); dp.detect()
+dp.detect_many(frames[12:16])
+for t in range(16, 22):
+    dp.update(frames[t]); dp.detect()
+print("per-frame generation", int(dp._eng.info("temporal_generation")), int(dp.stack.max.sum()), int(dp.stack.sliding_window.sum()))
+dp.close()
+# MFNR mix stacker, both background algorithms, odd and aligned sizes
+for shp in ((40, 52, 3), (37, 45, 3)):
+    clipf = rng_m.integers(0, 256, (9,) + shp, dtype=np.uint8)
+    for algo in ("mean", "sigma-clipping"):
+        bx = stacker.MfnrMixContainer(keep_frames=algo == "sigma-clipping", chunk=4)
+        for f in clipf:
+            bx.append(f)
+        print("mfnr", shp, algo, int(bx.export(0.9, 31, algo, 1.5).sum()))
+        bx.close()
 # dense frame -> tier 3
 rng = np.random.default_rng(0)
 dense = rng.integers(0, 60, (6, H, W)).astype(np.uint8)
