@@ -1765,7 +1765,7 @@ extern "C" int mdb_set_option(mdb_handle h, const char *name, int value) {
             return fail(MDB_ERR_INVALID, "mdb_set_option: temporal_kdiv=%d not possible here", value);
         return MDB_OK;
     }
-    if (!strcmp(name, "temporal_version")) { h->sk.t_version = value >= 1 && value <= 3 ? value : 3; return MDB_OK; }
+    if (!strcmp(name, "temporal_version")) { h->sk.t_version = value == 2 ? 2 : 3; return MDB_OK; }
     if (!strcmp(name, "t3_variant")) { h->sk.t3_variant = value; return MDB_OK; }
     if (!strcmp(name, "force_dense")) { h->sk.force_dense = value; return MDB_OK; }
     if (!strcmp(name, "force_strip")) { h->sk.force_strip = value; return MDB_OK; }

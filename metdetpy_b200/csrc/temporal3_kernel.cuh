@@ -1,7 +1,7 @@
 // temporal3_kernel: stack -> diff -> threshold fused (SlidingWindow.max / .mean, MetLib/utils.py:269-307;
 // M3Detector.detect, MetLib/Detector.py:327-332), one predicate bit per pixel, every frame read once.
 //
-// Third generation of the temporal pass.  The first two (stream_kernel.cuh, temporal_kernel.cuh) keep each
+// Third generation of the temporal pass.  The first two (the second lives on in temporal_kernel.cuh) keep each
 // thread's last n frames in a shared-memory ring fed by cp.async and are bound by instruction issue (10.3
 // thread-instructions per pixel-frame, ALU pipe 65 %, 12 warps/SM because of 68 B of shared memory per pixel).
 // Here the ring lives in REGISTERS:

@@ -1,7 +1,7 @@
 // temporal2_kernel: stack -> diff -> threshold fused (SlidingWindow.max / .mean, utils.py:269-307;
 // M3Detector.detect, Detector.py:327-332), one predicate bit per pixel, every frame read once.
 //
-// Same algorithm as temporal_kernel (stream_kernel.cuh) -- per-thread shared-memory ring fed by
+// Same algorithm as the first-generation kernel it replaced in round 1 -- per-thread shared-memory ring fed by
 // cp.async, van Herk / Gil-Werman sliding max, running window sums, integer predicate
 // max*L - sum > thr*L -- restructured for the instruction issue limit, which is what bounds this
 // pass on sm_100a (the ALU pipe issues one warp instruction every two cycles per SM sub-partition):

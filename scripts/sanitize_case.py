@@ -10,12 +10,12 @@ rng_m = np.random.default_rng(4)
 frames = synth.make_stream(T, W, H, FPS, speed_scale=3.0, thickness=2)
 mask = np.ones((H, W), np.uint8); mask[80:, :] = 0
 cfg = BinaryCfg(BinaryCoreCfg(True, 7, "normal", 0.2, 1), HoughLineCfg(8, 8, 6), DynamicCfg(True, 5))
-for mode in ("stream", "temporal_v3", "stream_dense_dst", "stream_strip_act", "temporal_v1", "generic"):
+for mode in ("stream", "temporal_v3", "stream_dense_dst", "stream_strip_act", "generic"):
     det = M3Detector(n / FPS + 1e-9, FPS, mask, 10, cfg, None, max_batch=8, apply_mask=True)
     det._eng.set_option("stream_kernel", int(mode != "generic"))
     det._eng.set_option("force_dense", int(mode == "stream_dense_dst"))
     det._eng.set_option("force_strip", int(mode == "stream_strip_act"))
-    det._eng.set_option("temporal_version", 1 if mode == "temporal_v1" else 3 if mode == "temporal_v3" else 2)
+    det._eng.set_option("temporal_version", 3 if mode == "temporal_v3" else 2)
     tot = 0
     for s in range(0, T, 8):
         res, dst = det.detect_many(frames[s:s + 8], return_dst=True)

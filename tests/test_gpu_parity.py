@@ -57,14 +57,14 @@ def test_per_frame_api_matches_reference_golden(name):
     det.close()
 
 
-@pytest.mark.parametrize("mode", ["generic", "stream", "stream_dense_dst", "stream_strip_act", "stream_temporal_v1",
-                                  "stream_temporal_v2", "stream_subblocks"])
+@pytest.mark.parametrize("mode", ["generic", "stream", "stream_dense_dst", "stream_strip_act", "stream_temporal_v2",
+                                  "stream_subblocks"])
 @pytest.mark.parametrize("batch", [1, 7, 32])
 @pytest.mark.parametrize("name", DET_CASES)
 def test_batched_api_matches_reference_golden(name, batch, mode):
     """generic = one fused launch per frame; stream = temporal3 (register ring; temporal2 for single-frame
     batches) + act4/act + sparse dst; the extra modes force the full-scan dst kernel (list-overflow path), the
-    warp-strip act kernel and the first- and second-generation temporal kernels."""
+    warp-strip act kernel and the second-generation temporal kernel."""
     from metdetpy_b200.detector import M3Detector
     g = load_det_case(name)
     det = M3Detector(g["n"] / g["fps"] + 1e-9, g["fps"], g["mask"], 10, _cfg(g["cfg"]), None,
@@ -74,7 +74,7 @@ def test_batched_api_matches_reference_golden(name, batch, mode):
     det._eng.set_option("stream_kernel", stream_kernel)
     det._eng.set_option("force_dense", int(mode == "stream_dense_dst"))
     det._eng.set_option("force_strip", int(mode == "stream_strip_act"))
-    det._eng.set_option("temporal_version", {"stream_temporal_v1": 1, "stream_temporal_v2": 2, "stream_subblocks": 2}.get(mode, 3))
+    det._eng.set_option("temporal_version", {"stream_temporal_v2": 2, "stream_subblocks": 2}.get(mode, 3))
     if mode == "stream_subblocks":  # sub-blocked van Herk (long windows use it by default): force a split of n
         k = next((k for k in (5, 4, 3, 2) if g["n"] % k == 0 and g["n"] // k >= 2), 0)
         if not k or W % 32 or not 2 <= g["n"] <= 128:
