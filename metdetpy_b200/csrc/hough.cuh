@@ -215,6 +215,7 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
         if (tid == 0) { s_ctl[2] = 0; s_ctl[3] = 0; }
         __syncthreads();
         bitonic_sort_u32(keys, np2, tid, HOUGH_THREADS);
+        const long long p_sort = clock64() - pc0;  // loads + sort (profile slot 5 of the shared-memory tiers)
         // per-angle rho interval of this frame's points
         int mn = INT_MAX, mx = INT_MIN;
         if (tid < MDB_HOUGH_ANGLES) {
@@ -475,7 +476,7 @@ hough_smem_kernel(HoughParams P, int T, const unsigned *__restrict__ npoints,
         }
         if (prof && tid == 0) {
             long long *o = prof + (size_t)t * 10;
-            o[0] = N; o[1] = p_setup; o[2] = p_vote; o[3] = p_walk; o[4] = p_unvote; o[5] = 0;
+            o[0] = N; o[1] = p_setup; o[2] = p_vote; o[3] = p_walk; o[4] = p_unvote; o[5] = p_sort;
             o[6] = n_vote; o[7] = n_line; o[8] = clock64() - pc0; o[9] = s_ctl[2];
         }
         if (sat) s_ctl[3] = 1;

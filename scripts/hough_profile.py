@@ -17,6 +17,6 @@ out = np.zeros((B, 10), np.int64)
 lib = _lib.load(); lib.mdb_debug_hough_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 assert lib.mdb_debug_hough_profile(det._eng.handle, out.ctypes.data, B) == 0
 np.set_printoptions(linewidth=200)
-print("N setup vote walk unvote reset n_vote n_line total lines  (cycles)")
+print("N setup vote walk unvote [tier1: loads+sort inside setup | tier2: reset | tier3: staging] n_vote n_line total lines  (cycles)")
 o = out[np.argsort(-out[:, 8])]
 print(o[:12]); print("mean", out.mean(0).astype(int)); print("sum-of-total ms @1.9GHz", out[:, 8].sum() / 1.9e6, "max", out[:, 8].max() / 1.9e6)
