@@ -28,7 +28,8 @@ class Config(C.Structure):
 class MfnrParams(C.Structure):
     _fields_ = [("highlight_preserve", C.c_double), ("blur_ksize", C.c_int32), ("bg_algorithm", C.c_int32),
                 ("blur_sigma", C.c_double), ("sigma_high", C.c_double), ("sigma_low", C.c_double),
-                ("bg_fix_factor", C.c_double), ("gumbel_mean", C.c_double)]
+                ("bg_fix_factor", C.c_double), ("gumbel_mean", C.c_double), ("med_block_size", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class FrameInfo(C.Structure):

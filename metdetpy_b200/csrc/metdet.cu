@@ -1620,10 +1620,18 @@ extern "C" int mdb_mfnr_finish(mdb_mfnr_handle m, const mdb_mfnr_params *prm, ui
     if (m->n_frames > 32767) return fail(MDB_ERR_INVALID, "mdb_mfnr_finish: %lld frames: the reference's int16 frame count wraps beyond 32767", m->n_frames);
     if (prm->blur_ksize < 1 || prm->blur_ksize % 2 == 0 || prm->blur_ksize > 255)
         return fail(MDB_ERR_INVALID, "mdb_mfnr_finish: blur_ksize %d must be odd and in 1..255", prm->blur_ksize);
-    if (prm->bg_algorithm != 0 && prm->bg_algorithm != 1)
-        return fail(MDB_ERR_INVALID, "mdb_mfnr_finish: bg_algorithm %d (0 = mean, 1 = sigma-clipping)", prm->bg_algorithm);
-    if (prm->bg_algorithm == 1 && !m->keep)
-        return fail(MDB_ERR_STATE, "mdb_mfnr_finish: sigma clipping needs the frames (create with keep_frames = 1)");
+    if (prm->bg_algorithm < 0 || prm->bg_algorithm > 3)
+        return fail(MDB_ERR_INVALID, "mdb_mfnr_finish: bg_algorithm %d (0 = mean, 1 = sigma-clipping, 2 = median, 3 = med-of-med)", prm->bg_algorithm);
+    if (prm->bg_algorithm != 0 && !m->keep)
+        return fail(MDB_ERR_STATE, "mdb_mfnr_finish: this background algorithm needs the frames (create with keep_frames = 1)");
+    const bool med = prm->bg_algorithm >= 2;
+    // stacker.py:343-347: "median", or "med-of-med" on at most 16 frames -> np.median over all frames
+    int med_block = 0;
+    if (prm->bg_algorithm == 3 && m->n_frames > 16) {
+        med_block = prm->med_block_size > 0 ? prm->med_block_size : (int)std::sqrt((double)m->n_frames);
+        if (med_block < 1 || (m->n_frames - 1) / med_block + 1 > MF_MAX_BLOCKS)
+            return fail(MDB_ERR_INVALID, "mdb_mfnr_finish: block size %d gives more than %d blocks", med_block, MF_MAX_BLOCKS);
+    }
     CK(cudaSetDevice(m->device));
     const int N = (int)m->n_frames, ks = prm->blur_ksize;
     const size_t E = m->E, P = m->P;
@@ -1636,7 +1644,8 @@ extern "C" int mdb_mfnr_finish(mdb_mfnr_handle m, const mdb_mfnr_params *prm, ui
                  o_row = carve(P * sizeof(double)), o_blur = carve(P * sizeof(double)), o_k = carve(ks * sizeof(double)),
                  o_out = carve(out_on_device ? 0 : E), o_sum2 = carve(clip ? E * 2 : 0), o_sq2 = carve(clip ? E * 4 : 0),
                  o_n2 = carve(clip ? E * 4 : 0), o_cptr = carve(clip ? m->chunks.size() * sizeof(uint8_t *) : 0),
-                 o_ccnt = carve(clip ? m->chunks.size() * sizeof(int) : 0);
+                 o_ccnt = carve(clip ? m->chunks.size() * sizeof(int) : 0), o_mu = carve(med ? E * sizeof(float) : 0),
+                 o_fptr = carve(med ? (size_t)N * sizeof(uint8_t *) : 0);
     if (m->scratch_cap < off) {
         CK(cudaStreamSynchronize(m->st));
         cudaFree(m->d_scratch);
@@ -1655,6 +1664,8 @@ extern "C" int mdb_mfnr_finish(mdb_mfnr_handle m, const mdb_mfnr_params *prm, ui
     int32_t *d_n2 = (int32_t *)(sc + o_n2);
     const uint8_t **d_cptr = (const uint8_t **)(sc + o_cptr);
     int *d_ccnt = (int *)(sc + o_ccnt);
+    float *d_mu = med ? (float *)(sc + o_mu) : nullptr;
+    const uint8_t **d_fptr = (const uint8_t **)(sc + o_fptr);
 #define MF_TRY(expr)                                                                      \
     do {                                                                                  \
         cudaError_t e_ = (expr);                                                          \
@@ -1682,6 +1693,18 @@ extern "C" int mdb_mfnr_finish(mdb_mfnr_handle m, const mdb_mfnr_params *prm, ui
         sum = d_sum2;
         n_arr = d_n2;
     }
+    if (med) {
+        std::vector<const uint8_t *> fp;  // one pointer per frame, in arrival order
+        for (size_t c = 0; c < m->chunks.size(); c++)
+            for (int t = 0; t < m->counts[c]; t++) fp.push_back(m->chunks[c] + (size_t)t * E);
+        MF_TRY(cudaMemcpyAsync(d_fptr, fp.data(), fp.size() * sizeof(uint8_t *), cudaMemcpyHostToDevice, m->st));
+        MF_TRY(cudaStreamSynchronize(m->st));  // fp is a local
+        if (E % 4 == 0)
+            mfnr_median_kernel<4><<<(unsigned)((E / 4 + MF_THREADS - 1) / MF_THREADS), MF_THREADS, 0, m->st>>>(d_fptr, E, N, med_block, d_mu);
+        else
+            mfnr_median_kernel<1><<<gE, MF_THREADS, 0, m->st>>>(d_fptr, E, N, med_block, d_mu);
+        MF_TRY(cudaGetLastError());
+    }
     const uint32_t *sq = prm->bg_algorithm == 1 ? d_sq2 : m->d_sq;
     double tot = 0.0;
     unsigned long long cnt = 0;
@@ -1700,7 +1723,7 @@ extern "C" int mdb_mfnr_finish(mdb_mfnr_handle m, const mdb_mfnr_params *prm, ui
     volatile double c2v = est_bg_var * g;            // (est_bg_var * gumble_mean)
     volatile double c1v = c2v * prm->bg_fix_factor;  // est_bg_var * gumble_mean * bg_fix_factor, left to right
     const double c1 = c1v, c2 = c2v;
-    mfnr_diffpos_kernel<<<MF_PARTS, MF_THREADS, 0, m->st>>>(E, N, c1, m->d_max, sum, n_arr, d_pv, d_pc);
+    mfnr_diffpos_kernel<<<MF_PARTS, MF_THREADS, 0, m->st>>>(E, N, c1, m->d_max, sum, n_arr, d_mu, d_pv, d_pc);
     mfnr_final_reduce_kernel<<<1, 32, 0, m->st>>>(MF_PARTS, d_pv, d_pc, d_tot, d_cnt);
     MF_TRY(cudaGetLastError());
     MF_TRY(cudaMemcpyAsync(&tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, m->st));
@@ -1720,11 +1743,11 @@ extern "C" int mdb_mfnr_finish(mdb_mfnr_handle m, const mdb_mfnr_params *prm, ui
     }
     MF_TRY(cudaMemcpyAsync(d_k, taps.data(), ks * sizeof(double), cudaMemcpyHostToDevice, m->st));
     volatile double hl = 255.0 * prm->highlight_preserve, omh = 1.0 - prm->highlight_preserve;
-    mfnr_mask_kernel<<<gP, MF_THREADS, 0, m->st>>>(P, m->C, N, c1, avg, hl, m->d_max, sum, n_arr, d_fg);
+    mfnr_mask_kernel<<<gP, MF_THREADS, 0, m->st>>>(P, m->C, N, c1, avg, hl, m->d_max, sum, n_arr, d_mu, d_fg);
     mfnr_blur_row_kernel<<<gP, MF_THREADS, 0, m->st>>>(m->H, m->W, ks, d_k, d_fg, d_row);
     mfnr_blur_col_kernel<<<gP, MF_THREADS, 0, m->st>>>(m->H, m->W, ks, d_k, d_row, d_blur);
     uint8_t *dst = out_on_device ? out : d_out;
-    mfnr_mix_kernel<<<gE, MF_THREADS, 0, m->st>>>(E, m->C, N, c2, prm->highlight_preserve, omh, m->d_max, sum, n_arr, d_blur, dst);
+    mfnr_mix_kernel<<<gE, MF_THREADS, 0, m->st>>>(E, m->C, N, c2, prm->highlight_preserve, omh, m->d_max, sum, n_arr, d_mu, d_blur, dst);
     MF_TRY(cudaGetLastError());
     if (!out_on_device) MF_TRY(cudaMemcpyAsync(out, d_out, E, cudaMemcpyDeviceToHost, m->st));
     MF_TRY(cudaStreamSynchronize(m->st));

@@ -1,5 +1,6 @@
 // MFNR mix stacker on the device (second half): mfnr_mix_stacker, MetLib/stacker.py:296-403, with
-// connect_lines off and the background algorithms "mean" (:339-342) and "sigma-clipping" (:333-338, :94-115).
+// connect_lines off and the background algorithms "mean" (:339-342), "sigma-clipping" (:333-338, :94-115), "median" and
+// "med-of-med" (:343-349, :62-78).
 // All frames of a clip (colour, full resolution) are accumulated as they arrive: per element the max (MaxImgContainer,
 // :43-49) and the uint16 sum / uint32 sum of squares of FastGaussianParam (utils.py:435-493, wrapping like numpy);
 // sigma clipping needs a second pass over the frames, which therefore stay resident in HBM (a 300-frame 4K colour
@@ -117,6 +118,90 @@ mfnr_sigma_kernel(MfnrChunks ch, size_t E, int N, double sigma_high, double sigm
     }
 }
 
+// ---- median backgrounds (stacker.py:343-349, median_of_medians :62-78) -------------------------------------------------
+// np.median over frames f0 .. f1-1 of one element, V elements per thread: the k-th smallest by bisection on the value
+// (8 counting passes over the frames, no per-element storage), the upper middle element of an even count by one more pass.
+#define MF_MAX_BLOCKS 192  // med-of-med: block_size = int(sqrt(N)) -> at most 182 blocks for N <= 32767
+
+template <int V>
+__device__ __forceinline__ void mf_median_range(const uint8_t *const *fptr, size_t i0, int f0, int f1, float (&med)[V]) {
+    const int m = f1 - f0, k = (m - 1) >> 1;  // lower middle (0-based)
+    unsigned lo[V], hi[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) { lo[v] = 0; hi[v] = 255; }
+    for (int it = 0; it < 8; it++) {
+        unsigned mid[V], c[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) { mid[v] = (lo[v] + hi[v]) >> 1; c[v] = 0; }
+#pragma unroll 4
+        for (int f = f0; f < f1; f++) {
+            unsigned x[V];
+            mf_load<V>(fptr[f] + i0, x);
+#pragma unroll
+            for (int v = 0; v < V; v++) c[v] += x[v] <= mid[v];
+        }
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+            if (lo[v] < hi[v]) {
+                if (c[v] >= (unsigned)(k + 1)) hi[v] = mid[v]; else lo[v] = mid[v] + 1;
+            }
+        }
+    }
+    if (m & 1) {
+#pragma unroll
+        for (int v = 0; v < V; v++) med[v] = (float)lo[v];
+        return;
+    }
+    unsigned c[V], nx[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) { c[v] = 0; nx[v] = 256; }
+    for (int f = f0; f < f1; f++) {
+        unsigned x[V];
+        mf_load<V>(fptr[f] + i0, x);
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+            c[v] += x[v] <= lo[v];
+            if (x[v] > lo[v]) nx[v] = min(nx[v], x[v]);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+        const unsigned b = c[v] >= (unsigned)(k + 2) ? lo[v] : nx[v];  // the (k+1)-th smallest
+        med[v] = (float)(lo[v] + b) * 0.5f;
+    }
+}
+
+// block_size == 0: np.median over all N frames; else median_of_medians with that block size.  mu_out: float plane
+// (values are multiples of 0.25: exact)
+template <int V>
+__global__ void __launch_bounds__(MF_THREADS)
+mfnr_median_kernel(const uint8_t *const *fptr, size_t E, int N, int block_size, float *mu_out) {
+    const size_t i0 = (blockIdx.x * (size_t)MF_THREADS + threadIdx.x) * V;
+    if (i0 >= E) return;
+    float res[V];
+    if (block_size <= 0) {
+        mf_median_range<V>(fptr, i0, 0, N, res);
+    } else {
+        const int nb = (N - 1) / block_size + 1;
+        float meds[V][MF_MAX_BLOCKS];
+        for (int b = 0; b < nb; b++) {
+            float mb[V];
+            mf_median_range<V>(fptr, i0, b * block_size, min((b + 1) * block_size, N), mb);
+#pragma unroll
+            for (int v = 0; v < V; v++) {  // insertion into the sorted prefix
+                int j = b;
+                while (j > 0 && meds[v][j - 1] > mb[v]) { meds[v][j] = meds[v][j - 1]; j--; }
+                meds[v][j] = mb[v];
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < V; v++)
+            res[v] = (nb & 1) ? meds[v][nb >> 1] : (meds[v][(nb >> 1) - 1] + meds[v][nb >> 1]) * 0.5f;
+    }
+#pragma unroll
+    for (int v = 0; v < V; v++) mu_out[i0 + v] = res[v];
+}
+
 // block-level deterministic sum of (value, count): partial[blockIdx.x]
 __device__ __forceinline__ void mf_block_reduce(double v, unsigned long long c, double *part_v, unsigned long long *part_c) {
     __shared__ double sv[MF_THREADS / 32];
@@ -149,13 +234,13 @@ mfnr_sqrtvar_kernel(size_t E, int N, const uint16_t *sum, const uint32_t *sq, co
 
 // max_bias_diff = max - (mu + c1) (stacker.py:351-354); sum and count of its positive entries (:356-357)
 __global__ void __launch_bounds__(MF_THREADS)
-mfnr_diffpos_kernel(size_t E, int N, double c1, const uint8_t *mx, const uint16_t *sum, const int32_t *n_arr, double *part_v,
-                    unsigned long long *part_c) {
+mfnr_diffpos_kernel(size_t E, int N, double c1, const uint8_t *mx, const uint16_t *sum, const int32_t *n_arr,
+                    const float *mu_arr, double *part_v, unsigned long long *part_c) {
     double acc = 0.0;
     unsigned long long cnt = 0;
     for (size_t i = blockIdx.x * (size_t)MF_THREADS + threadIdx.x; i < E; i += (size_t)gridDim.x * MF_THREADS) {
         const int n = n_arr ? n_arr[i] : (int)(int16_t)N;
-        const double d = (double)mx[i] - (mf_mu(sum[i], n) + c1);
+        const double d = (double)mx[i] - ((mu_arr ? (double)mu_arr[i] : mf_mu(sum[i], n)) + c1);
         if (d > 0.0) { acc += d; cnt += 1; }
     }
     mf_block_reduce(acc, cnt, part_v, part_c);
@@ -178,14 +263,14 @@ __global__ void mfnr_final_reduce_kernel(int parts, const double *part_v, const 
 // fg_mask (stacker.py:358-365): a pixel is foreground when any of its channels is an outlier or a highlight
 __global__ void __launch_bounds__(MF_THREADS)
 mfnr_mask_kernel(size_t P, int C, int N, double c1, double avg, double hl, const uint8_t *mx, const uint16_t *sum,
-                 const int32_t *n_arr, uint8_t *fg) {
+                 const int32_t *n_arr, const float *mu_arr, uint8_t *fg) {
     const size_t p = blockIdx.x * (size_t)MF_THREADS + threadIdx.x;
     if (p >= P) return;
     int on = 0;
     for (int c = 0; c < C; c++) {
         const size_t i = p * C + c;
         const int n = n_arr ? n_arr[i] : (int)(int16_t)N;
-        const double d = (double)mx[i] - (mf_mu(sum[i], n) + c1);
+        const double d = (double)mx[i] - ((mu_arr ? (double)mu_arr[i] : mf_mu(sum[i], n)) + c1);
         on |= (d > avg) | ((double)mx[i] > hl);
     }
     fg[p] = (uint8_t)on;
@@ -235,11 +320,11 @@ mfnr_blur_col_kernel(int H, int W, int ksize, const double *__restrict__ k, cons
 // highlight fix + mix (stacker.py:383-397)
 __global__ void __launch_bounds__(MF_THREADS)
 mfnr_mix_kernel(size_t E, int C, int N, double c2, double hp, double one_minus_hp, const uint8_t *mx, const uint16_t *sum,
-                const int32_t *n_arr, const double *__restrict__ blur, uint8_t *out) {
+                const int32_t *n_arr, const float *mu_arr, const double *__restrict__ blur, uint8_t *out) {
     const size_t i = blockIdx.x * (size_t)MF_THREADS + threadIdx.x;
     if (i >= E) return;
     const int n = n_arr ? n_arr[i] : (int)(int16_t)N;
-    const double m = (double)mx[i], mu = mf_mu(sum[i], n), b = blur[i / C];
+    const double m = (double)mx[i], mu = mu_arr ? (double)mu_arr[i] : mf_mu(sum[i], n), b = blur[i / C];
     const double hff = 1.0 - (fmin(fmax(m / 255.0 - hp, 0.0), 1.0) / one_minus_hp);
     double fixed = m - (c2 * hff);
     fixed = fmin(fmax(fixed, 0.0), 255.0);

@@ -201,7 +201,7 @@ def max_stacker(video_loader: Any, start_frame: Optional[int] = None, end_frame:
 
 
 SUPPORT_BG_ALGO = ["median", "med-of-med", "sigma-clipping", "mean"]  # MetLib/stacker.py:13
-_BG_ON_DEVICE = {"mean": 0, "sigma-clipping": 1}
+_BG_ON_DEVICE = {"mean": 0, "sigma-clipping": 1, "median": 2, "med-of-med": 3}
 EULER_CONSTANT = 0.5772  # MetLib/utils.py:24
 
 
@@ -267,6 +267,7 @@ class MfnrMixContainer:
         prm.sigma_high, prm.sigma_low, prm.bg_fix_factor = float(sigma_high), float(sigma_low), float(bg_fix_factor)
         with np.errstate(all="ignore"):
             prm.gumbel_mean = float(get_gumbel_mean(self.count))
+        prm.med_block_size = int(self.count ** (1 / 2))  # median_of_medians' default block size (stacker.py:68-69)
         out = np.empty(self.shape, np.uint8)
         st = (C.c_double * 4)()
         check(_lib.load().mdb_mfnr_finish(self._h, C.byref(prm), out.ctypes.data, 0, st), "mfnr finish")
@@ -288,16 +289,14 @@ class MfnrMixContainer:
 def mfnr_mix_stacker(video_loader: Any, denoise_cfg: Any, start_frame: Optional[int] = None,
                      end_frame: Optional[int] = None, logger: Any = None) -> Optional[np.ndarray]:
     """mfnr_mix_stacker (MetLib/stacker.py:296-403) on the device, same signature; `denoise_cfg` is the reference's
-    DenoiseOption (or anything with its fields).  Built: connect_lines.switch == False with bg_algorithm "mean" or
-    "sigma-clipping".  Refused (NotImplementedError): "median" / "med-of-med" (:343-349) and connect_highlight_area
-    (:239-294: Lab round trips, Otsu, circular-kernel morphology, contour filling)."""
+    DenoiseOption (or anything with its fields).  Built: connect_lines.switch == False with every bg_algorithm ("mean",
+    "sigma-clipping", "median", "med-of-med").  Refused (NotImplementedError): connect_highlight_area (:239-294: Lab
+    round trips, Otsu, circular-kernel morphology, contour filling)."""
     algo = denoise_cfg.mfnr_param.bg_algorithm
     assert algo in SUPPORT_BG_ALGO, f"unsupported bg algo! select from {SUPPORT_BG_ALGO}, but {algo} got."
-    if algo not in _BG_ON_DEVICE:
-        raise NotImplementedError(f"bg_algorithm {algo!r} (MetLib/stacker.py:343-349) is not built on the device")
     if denoise_cfg.connect_lines.switch:
         raise NotImplementedError("connect_lines (connect_highlight_area, MetLib/stacker.py:239-294) is not built on the device")
-    box = MfnrMixContainer(keep_frames=algo == "sigma-clipping")
+    box = MfnrMixContainer(keep_frames=algo != "mean")
     try:
         try:
             if start_frame is not None or end_frame is not None:

@@ -2,7 +2,8 @@
 and bench.py's cpu_baseline may import it).
 
 MetLib/stacker.py:296-403 (`mfnr_mix_stacker`) with `connect_lines.switch = False`, background algorithms "mean"
-(:339-342) and "sigma-clipping" (:333-338 -> `single_sigma_clipping`, :94-115), on top of the containers of :34-59
+(:339-342), "sigma-clipping" (:333-338 -> `single_sigma_clipping`, :94-115), "median" and "med-of-med" (:343-349 ->
+`median_of_medians`, :62-78), on top of the containers of :34-59
 (`MaxImgContainer`, `AllImgContainer`, `FastGaussianContainer`) and `FastGaussianParam.mu/.var/__sub__/mask`
 (MetLib/utils.py:418-509: uint16 sums and uint32 sums of squares that wrap like numpy's fixed-width arithmetic) and
 `get_gumbel_mean` (:118-126).  The SNR estimates of :322-323, :399-400 only feed debug log lines and are left out.
@@ -98,6 +99,14 @@ def single_sigma_clipping(frames: np.ndarray, ref: Stats, sigma_high=3.0, sigma_
     return Stats(ref.sum_mu - cs, ref.square_sum - cq, ref.n - cn)
 
 
+def median_of_medians(frames: np.ndarray, block_size=None) -> np.ndarray:  # stacker.py:62-78
+    if block_size is None:
+        block_size = int(len(frames) ** (1 / 2))
+    block_num = (len(frames) - 1) // block_size + 1
+    medians = [np.median(frames[i * block_size:(i + 1) * block_size], axis=0) for i in range(block_num)]
+    return np.median(medians, axis=0)
+
+
 def mfnr_mix(frames: np.ndarray, *, highlight_preserve=0.9, blur_ksize=31, bg_algorithm="mean", sigma_high=3.0,
              sigma_low=3.0, bg_fix_factor=1.5, backend="cv2", return_stats=False):
     """stacker.py:296-403 for (T, H, W, 3) uint8 frames, connect_lines off.  Note: :333-338 calls single_sigma_clipping
@@ -112,6 +121,12 @@ def mfnr_mix(frames: np.ndarray, *, highlight_preserve=0.9, blur_ksize=31, bg_al
             est_bg_var = np.mean(np.sqrt(sc.var))
         elif bg_algorithm == "mean":
             est_bg_mu = init.mu
+            est_bg_var = np.mean(np.sqrt(init.var))
+        elif bg_algorithm in ("median", "med-of-med"):  # stacker.py:343-349
+            if bg_algorithm == "median" or len(frames) <= 16:
+                est_bg_mu = np.median(frames, axis=0)
+            else:
+                est_bg_mu = median_of_medians(frames)
             est_bg_var = np.mean(np.sqrt(init.var))
         else:
             raise NotImplementedError(bg_algorithm)

@@ -47,11 +47,11 @@ for t in range(16, 22):
     dp.update(frames[t]); dp.detect()
 print("per-frame generation", int(dp._eng.info("temporal_generation")), int(dp.stack.max.sum()), int(dp.stack.sliding_window.sum()))
 dp.close()
-# MFNR mix stacker, both background algorithms, odd and aligned sizes
+# MFNR mix stacker, background algorithms mean / sigma clipping / median, odd and aligned sizes
 for shp in ((40, 52, 3), (37, 45, 3)):
     clipf = rng_m.integers(0, 256, (9,) + shp, dtype=np.uint8)
-    for algo in ("mean", "sigma-clipping"):
-        bx = stacker.MfnrMixContainer(keep_frames=algo == "sigma-clipping", chunk=4)
+    for algo in ("mean", "sigma-clipping", "median"):
+        bx = stacker.MfnrMixContainer(keep_frames=algo != "mean", chunk=4)
         for f in clipf:
             bx.append(f)
         print("mfnr", shp, algo, int(bx.export(0.9, 31, algo, 1.5).sum()))

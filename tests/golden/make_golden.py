@@ -333,7 +333,7 @@ def case_mfnr():
 
     rng = np.random.default_rng(21)
     out = {}
-    for name, T, H, W in [("clip24", 24, 72, 104), ("clip50", 50, 48, 64)]:
+    for name, T, H, W in [("clip24", 24, 72, 104), ("clip50", 50, 48, 64), ("clip13", 13, 40, 56)]:
         base = rng.integers(15, 70, (H, W, 3))
         frames = np.clip(base[None] + rng.normal(0, 4.0, (T, H, W, 3)), 0, 255).astype(np.uint8)
         for t in range(T):  # a moving streak, a saturated lamp, a hot pixel that flickers
@@ -344,7 +344,7 @@ def case_mfnr():
             if t % 7 == 0:
                 frames[t, H - 9, W - 12] = (90, 200, 120)
         out[f"{name}_frames"] = frames
-        for algo in ("mean", "sigma-clipping"):
+        for algo in ("mean", "sigma-clipping", "median", "med-of-med"):
             cfg = DenoiseOption(switch=True, highlight_preserve=0.9, algorithm="mfnr-mix", blur_ksize=31,
                                 connect_lines=ConnectParam(switch=False, ksize_multiplier=1.5, gamma=1.0, threshold=30),
                                 simple_param=SimpleDenoiseParam(10, 20, 10, 15, 6),
@@ -354,7 +354,7 @@ def case_mfnr():
             assert mix is not None and mix.dtype == np.uint8 and mix.shape == (H, W, 3)
             out[f"{name}_{algo}"] = mix
             print("mfnr", name, algo, mix.shape, int(mix.mean() * 1000) / 1000, int((mix != frames.max(0)).sum()))
-    np.savez_compressed(os.path.join(HERE, "mfnr.npz"), names=np.array(["clip24", "clip50"]), **out)
+    np.savez_compressed(os.path.join(HERE, "mfnr.npz"), names=np.array(["clip24", "clip50", "clip13"]), **out)
 
 
 def case_preproc():

@@ -1,4 +1,4 @@
-"""MFNR mix stacker (MetLib/stacker.py:296-403, connect_lines off, bg "mean" / "sigma-clipping"): the CPU oracle against
+"""MFNR mix stacker (MetLib/stacker.py:296-403, connect_lines off, all four background algorithms): the CPU oracle against
 golden images from the live reference (exact), the CUDA path through the C ABI against both (float64 pipeline whose two
 global means are reduced in another order than numpy's: at most one grey level on at most 1e-4 of the elements, the
 scalars to 1e-12)."""
@@ -11,7 +11,7 @@ import pytest
 from conftest import GOLDEN
 from oracle import mfnr_oracle as MO
 
-ALGOS = ("mean", "sigma-clipping")
+ALGOS = ("mean", "sigma-clipping", "median", "med-of-med")
 
 
 def _cfg(algo, connect=False):
@@ -97,7 +97,7 @@ def test_gpu_seeded_clips_against_oracle(shape, T):
         frames[t, H // 3 + t % 5, x:x + 16] = 245
         frames[t, 3:6, 3:9] = 255
     for algo in ALGOS:
-        box = stacker.MfnrMixContainer(keep_frames=algo == "sigma-clipping", chunk=5)
+        box = stacker.MfnrMixContainer(keep_frames=algo != "mean", chunk=5)
         for f in frames:
             box.append(f)
         mix = box.export(0.9, 31, algo, 1.5)
@@ -109,8 +109,6 @@ def test_gpu_seeded_clips_against_oracle(shape, T):
 def test_gpu_refusals_and_errors():
     from metdetpy_b200 import stacker
     fr = [np.zeros((8, 8, 3), np.uint8)] * 3
-    with pytest.raises(NotImplementedError):
-        stacker.mfnr_mix_stacker(Loader(fr), _cfg("median"))
     with pytest.raises(NotImplementedError):
         stacker.mfnr_mix_stacker(Loader(fr), _cfg("mean", connect=True))
     with pytest.raises(AssertionError):
