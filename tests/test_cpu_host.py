@@ -23,9 +23,30 @@ def test_library_exports_every_declared_symbol():
     assert declared <= set(_lib.SYMBOLS), declared - set(_lib.SYMBOLS)
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
     assert ctypes.sizeof(_lib.Config) == 4 * (7 + 4 + 7 + 4)
     assert ctypes.sizeof(_lib.FrameInfo) == 8 + 4 + 4 + 8 * 4 + 4 * 4
+    # the header is plain C: compile it with gcc and compare every field offset with the ctypes mirror
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    structs = {"mdb_config": _lib.Config, "mdb_frame_info": _lib.FrameInfo, "mdb_mfnr_params": _lib.MfnrParams}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "metdet_b200.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
     lib = _lib.load()
     assert lib.mdb_version() >= 100
     assert lib.mdb_device_count() >= 0
@@ -69,8 +90,9 @@ def test_argument_errors_without_gpu():
     m = np.ones((4, 4), np.uint8)
     assert lib.mdb_create(ctypes.byref(cfg), m.ctypes.data, ctypes.byref(h)) == -1  # 0x0 frame
     cfg.width = cfg.height = 4
-    cfg.window = 300
-    assert lib.mdb_create(ctypes.byref(cfg), m.ctypes.data, ctypes.byref(h)) == -1  # window > 255
+    cfg.window = 5000
+    assert lib.mdb_create(ctypes.byref(cfg), m.ctypes.data, ctypes.byref(h)) == -1  # window > MDB_MAX_WINDOW
+    assert b"window" in lib.mdb_last_error()
     k = ctypes.c_int32()
     assert lib.mdb_lineset_nms(None, -1, None, None, ctypes.byref(k)) == -1
 
