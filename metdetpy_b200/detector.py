@@ -500,24 +500,34 @@ class M3Detector(LineDetector):
         self._dst_cache = None
         return self._unpack(0)
 
-    def _unpack_all(self, T: int):
-        """Results of a finished batch as a list of (lines, cls_pred); only frames that have lines
-        cost any per-frame Python work."""
+    def _unpack_all(self, T: int, build: bool = True):
+        """Results of a finished batch as a list of (lines, cls_pred).  The rows of all frames are gathered in two
+        vectorised passes; a frame's result is a pair of views into those arrays (frames without lines share one empty
+        pair), so the per-frame Python work is two slices.  build=False: only the bookkeeping (tie re-NMS, last_infos)."""
         eng = self._eng
         info = np.frombuffer(eng.infos, dtype=_INFO_DTYPE, count=T)
         tied = np.nonzero(info["len_ties"])[0]
         if len(tied):
             self._renms_tied(info, tied)
-        nl = info["n_lines"]
-        empty = (np.array([]), np.zeros((0, self.num_cls)))
-        out = [empty] * T
-        for i in np.nonzero(nl)[0]:
-            k = int(nl[i])
-            cls_pred = np.zeros((k, self.num_cls))
-            p = eng.prob[i, :k]
-            cls_pred[:, -1] = p
-            cls_pred[:, 0] = 1 - p
-            out[i] = (eng.lines[i, :k].copy(), cls_pred)
+        out = None
+        if build:
+            nl = info["n_lines"]
+            empty = (np.array([]), np.zeros((0, self.num_cls)))
+            out = [empty] * T
+            idx = np.nonzero(nl)[0]
+            if len(idx):
+                cnt = nl[idx].astype(np.int64)
+                off = np.concatenate(([0], np.cumsum(cnt)))
+                rows = np.repeat(idx, cnt)
+                cols = np.arange(int(off[-1])) - np.repeat(off[:-1], cnt)
+                lines_all = eng.lines[rows, cols]
+                p = eng.prob[rows, cols]
+                cls_all = np.zeros((len(p), self.num_cls))
+                cls_all[:, -1] = p
+                cls_all[:, 0] = 1 - p
+                offl = off.tolist()
+                for j, i in enumerate(idx.tolist()):
+                    out[i] = (lines_all[offl[j]:offl[j + 1]], cls_all[offl[j]:offl[j + 1]])
         self._unpack(T - 1)
         self.last_infos = info.copy()
         return out
@@ -694,18 +704,20 @@ class M3Detector(LineDetector):
         offs = np.concatenate(([0], np.cumsum(Ts)))
         return [sums[offs[k]:offs[k + 1]] for k in range(len(segs))]
 
-    def collect(self, want_lines: bool = True):
+    def collect(self, want_lines: bool = True, want_infos: bool = False):
         """Waits for the oldest submitted batch (mdb_collect_batch); returns its list of
-        (lines, cls_pred), or None with want_lines=False (scalars of the last frame still update)."""
+        (lines, cls_pred), or None with want_lines=False (scalars of the last frame still update; with want_infos the
+        per-frame records `last_infos` and the NMS rows in the engine's arrays are complete too -- the form a caller
+        takes that packs line records itself, sharding.pack_line_records)."""
         eng = self._eng
         T = self._pending.pop(0)
         check(eng.lib.mdb_collect_batch(eng.handle, C.byref(eng.infos), _ptr(eng.lines), _ptr(eng.prob),
                                         _ptr(eng.raw), None, 0), "collect")
         self._dst_cache = None
-        if not want_lines:
+        if not want_lines and not want_infos:
             self._unpack(T - 1)
             return None
-        return self._unpack_all(T)
+        return self._unpack_all(T, build=want_lines)
 
     def visu(self):
         """Reference visu() (Detector.py:394-448) needs MetLib.metvisu; without it: no overlays."""

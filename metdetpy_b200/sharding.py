@@ -397,6 +397,6 @@ def run_chunk(det, segments: Sequence[Segment], shard: Shard, thr, thr_f, snr, *
             submit(segs[nxt])
             nxt += 1
         halo = sg.t0 + sg.T <= shard.start
-        det.collect(want_lines=not halo)
+        det.collect(want_lines=False, want_infos=not halo)  # records are packed from the engine's arrays (pack_line_records)
         if not halo and on_batch is not None:
             on_batch(det, sg)
