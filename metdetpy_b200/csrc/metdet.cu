@@ -541,9 +541,10 @@ static int launch_hough_kernels(mdb_detector *h, BatchCtx *tl, const HoughParams
     // tier 1a: 2 CTAs/SM (2048 points, 90 KB table); tier 1b: 1 CTA/SM (4096 points, 184 KB table)
     // the CTAs take frames from a queue, so the grid only sets how much of the GPU the (latency-bound, shared-memory
     // hungry: a resident CTA displaces two of an SM's four temporal CTAs) PPHT occupies beside the next batch's
-    // temporal pass.  Measured at 4K (profiles/sweep_hough_ctas2.txt): 3/4 of a CTA per SM is the throughput optimum
-    // (two per SM: -1 %, half per SM: -8 %) and keeps the mask chain at 0.55 of the HBM peak inside the live step
-    const int cap_a = h->hough_ctas > 0 ? h->hough_ctas : 3 * h->sm_count / 4, cap_b = h->hough_ctas > 0 ? h->hough_ctas : h->sm_count;
+    // temporal pass.  Measured at 4K (profiles/sweep_hough_ctas3.txt): 0.7 of a CTA per SM costs 1 % of throughput
+    // against the optimum (0.75 - 0.9 per SM) and keeps the mask chain at 0.6 of the HBM peak inside the live step
+    // (0.5 at the optimum, 0.48 with two per SM); half a CTA per SM costs 8 %
+    const int cap_a = h->hough_ctas > 0 ? h->hough_ctas : 7 * h->sm_count / 10, cap_b = h->hough_ctas > 0 ? h->hough_ctas : h->sm_count;
     hough_smem_kernel<<<std::min(T, cap_a), HOUGH_THREADS, HOUGH_SMEM_SMALL + HOUGH_TABLE_BYTES_SMALL, st>>>(
         hp, T, d_npoints, d_points, d_order, d_lines, d_nlines, d_queue, h->d_prof,
         HOUGH_CAP_SMALL, HOUGH_TABLE_BYTES_SMALL, 0);
