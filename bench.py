@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (2, 4, 5)")
     ap.add_argument("--no-extra", action="store_true", help="skip per_frame_api and dense_regime")
     ap.add_argument("--no-parity", action="store_true", help="skip the sequential re-run that checks the sharded result")
-    ap.add_argument("--parity-budget", type=int, default=4000, help="most batches a rank re-runs sequentially for the parity check")
+    ap.add_argument("--parity-budget", type=int, default=6000, help="most batches a rank re-runs sequentially for the parity check")
     ap.add_argument("--generic-kernel", action="store_true", help="force the per-frame fused kernel")
     return ap.parse_args()
 
@@ -459,7 +459,7 @@ def bind_near_gpu(local):
 class LineGather:
     """All-gather of line records (frame, x1, y1, x2, y2, nonline_prob), one call per step, on a side stream with the
     collective launched asynchronously: nothing on the submitting thread waits for it before the end of the job."""
-    CAP = 8192
+    CAP = 16384
     SLOTS = 4
 
     def __init__(self, world, dev):

@@ -194,7 +194,8 @@ int mdb_replay_thresholds(int nsamples, const int64_t *timers, const uint64_t *s
                           int64_t t_end, int32_t *thr, double *thr_float, double *snr);
 /* Read-only counters / timings of the most recent batch by name: "temporal_ms" (stack->diff->threshold pass),
  * "spatial_ms" (median + close + dy-mask + mask bytes), "temporal_generation" (which temporal kernel ran: 3 =
- * register ring, 2 = shared-memory ring, 4 = per-frame resident state, 0 = none), "stream_kernel" (1 if the time-tiled
+ * register ring, 2 = shared-memory ring, 4 = per-frame resident state, 0 = none), "digest_hi" / "digest_lo" (the two
+ * 32-bit halves of an FNV-1a digest of the batch finished last: thresholds, on-pixel counts, raw segments), "stream_kernel" (1 if the time-tiled
  * streaming path serves this handle), "hough_tier1a" / "hough_tier1b" / "hough_tier2" / "hough_tier3" (frames of the
  * batch collected last that each PPHT tier resolved; "..._total": since creation).  Unknown names return
  * MDB_ERR_INVALID. */

@@ -355,20 +355,11 @@ def pack_line_records(det, T: int, first_frame: int, out: np.ndarray) -> int:
 
 
 def batch_digest(det, T: int) -> bytes:
-    """8-byte digest of a collected batch: per-frame threshold, on-pixel count, raw segment count and the raw Hough
-    segments themselves.  Two runs that agree on every digest produced the same masks' statistics and lines."""
-    import hashlib
+    """8-byte digest of the batch collected last, computed by the library while it fills the results (FNV-1a over
+    per-frame threshold, on-pixel count, raw segment count and the raw Hough segments themselves).  Two runs that agree
+    on every digest produced the same masks' statistics and lines."""
     eng = det._eng
-    info = det.last_infos[:T]
-    h = hashlib.blake2b(digest_size=8)
-    h.update(np.ascontiguousarray(info["bi_threshold"]).tobytes())
-    h.update(np.ascontiguousarray(info["n_on"]).tobytes())
-    h.update(np.ascontiguousarray(info["lines_num"]).tobytes())
-    nraw = info["n_raw"]
-    if nraw.any():
-        rows, cols = ragged_index(nraw)
-        h.update(np.ascontiguousarray(eng.raw[rows, cols]).tobytes())
-    return h.digest()
+    return int(eng.info("digest_hi")).to_bytes(4, "big") + int(eng.info("digest_lo")).to_bytes(4, "big")
 
 
 def run_chunk(det, segments: Sequence[Segment], shard: Shard, thr, thr_f, snr, *, thr_base: int = 0, on_batch=None,
