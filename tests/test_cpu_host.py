@@ -154,3 +154,23 @@ def test_batched_tie_renms_equals_the_checker_frame_by_frame():
     bad = orders.copy(); bad[off[5]] = bad[off[5] + 1]
     assert lib.mdb_lineset_nms_frames(T, fr.ctypes.data, bad.ctypes.data, off.ctypes.data, raw.ctypes.data, C.byref(infos),
                                       lines.ctypes.data, prob.ctypes.data) != 0
+
+
+def test_c_caller_links_against_the_library(tmp_path):
+    """examples/c_abi_example.c: a plain C program compiled against include/metdet_b200.h and linked with the shared
+    library (what a non-Python host of the boundary does).  Without a GPU it must report that and exit 0."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    lib = _lib._build.build()
+    exe = tmp_path / "c_abi_example"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"),
+                           os.path.join(REPO, "examples", "c_abi_example.c"), "-L", os.path.dirname(lib), "-lmetdet_b200",
+                           "-Wl,-rpath," + os.path.dirname(lib), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True)
+    assert f"ABI version {_lib.ABI_VERSION}" in out
+    if _lib.load().mdb_device_count() == 0:
+        assert "no CPU fallback" in out
+    else:
+        assert "lines, first" in out  # the moving bar is found
