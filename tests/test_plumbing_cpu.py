@@ -64,3 +64,26 @@ def test_bench_without_cuda_fails_loudly():
                        text=True, timeout=300)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
     assert not r.stdout.strip().startswith("{")
+
+
+def test_bench_roofline_traffic_comes_from_the_committed_capture():
+    """roofline.traffic is read from profiles/chain_traffic.json (written by profiles/ncu_summary.py --traffic from an ncu
+    --set full capture), never a literal; a configuration without a capture gives null."""
+    import json
+    sys.path.insert(0, REPO)
+    import bench
+    tab = json.load(open(os.path.join(REPO, "profiles", "chain_traffic.json")))
+    assert "3840x2160_n30_b512" in tab
+    v = bench._traffic_from_profile(3840, 2160, 30, 512)
+    e = tab["3840x2160_n30_b512"]
+    assert v == e["bytes_per_launch"] and abs(v * e["launches_per_batch"] - e["bytes_per_batch"]) < 1
+    # the chain moves less than the algorithmic 2*H*W per frame (mask bytes are only rewritten where they change)
+    assert 0.5 * 2 * 3840 * 2160 * 512 < e["bytes_per_batch"] < 2 * 3840 * 2160 * 512
+    assert bench._traffic_from_profile(1234, 567, 8, 9) is None
+
+
+def test_bench_numa_binding_degrades_gracefully():
+    sys.path.insert(0, REPO)
+    import bench
+    r = bench.bind_near_gpu(0)  # no NVML device here: must report, not raise
+    assert r["bound"] is False and "why" in r
