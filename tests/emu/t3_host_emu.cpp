@@ -96,6 +96,9 @@ static int run_shape() {
 
 int main() {
     int bad = 0;
+    bad += run_shape<15, 15, 2, 15>();  // the default shape for n = 30
+    bad += run_shape<30, 15, 2, 15>();  // ... for n = 60
+    bad += run_shape<5, 5, 1, 5>();     // ... for n = 5
     bad += run_shape<30, 10, 1, 6>();
     bad += run_shape<30, 15, 1, 5>();
     bad += run_shape<30, 10, 2, 6>();
