@@ -1,0 +1,174 @@
+// A small CUDA thread-block emulator for CPU tests (test infrastructure, not product code).
+//
+// A kernel's source is compiled for the host and one thread block at a time is run by `blockDim.x` OS threads:
+//   * threadIdx / blockIdx are thread-local, blockDim / gridDim global;
+//   * __syncthreads() is a std::barrier over the block, __syncwarp() and the warp collectives (__ballot_sync,
+//     __shfl_*_sync, __reduce_*_sync, __any/__all_sync) a barrier + exchange slots over the 32 threads of a warp
+//     (full-mask use only: every lane of the warp has to make the call, as CUDA requires for mask 0xffffffff);
+//   * `__shared__` variables become function-local statics (one block runs at a time), dynamic shared memory is the
+//     global array the including file defines under the kernel's `extern __shared__` name (the test's build step
+//     rewrites `extern __shared__` to `extern`);
+//   * atomics map to the GCC __atomic built-ins; the _rn arithmetic intrinsics to plain IEEE operations (compile with
+//     -ffp-contract=off).
+// Blocks run one after the other, which is a legal CUDA schedule for kernels whose blocks do not wait for each other.
+#pragma once
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+
+struct EmuDim { unsigned x = 1, y = 1, z = 1; };
+static thread_local EmuDim emu_threadIdx, emu_blockIdx;
+static EmuDim emu_blockDim, emu_gridDim;
+#define threadIdx emu_threadIdx
+#define blockIdx emu_blockIdx
+#define blockDim emu_blockDim
+#define gridDim emu_gridDim
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __constant__
+
+struct EmuWarp {
+    std::barrier<> bar;
+    unsigned long long slot[32];
+    EmuWarp() : bar(32) {}
+};
+static std::barrier<> *emu_block_bar = nullptr;
+static thread_local EmuWarp *emu_warp = nullptr;
+static thread_local int emu_lane = 0;
+
+static inline void __syncthreads() { emu_block_bar->arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp->bar.arrive_and_wait(); }
+static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline long long clock64() { return 0; }
+
+// every lane publishes a 64-bit value; f(slots) is evaluated by every lane on the complete set
+template <typename F>
+static inline auto emu_warp_collective(unsigned long long mine, F f) {
+    emu_warp->slot[emu_lane] = mine;
+    emu_warp->bar.arrive_and_wait();
+    auto r = f(emu_warp->slot);
+    emu_warp->bar.arrive_and_wait();
+    return r;
+}
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    return emu_warp_collective(pred ? 1ull : 0ull, [](const unsigned long long *s) {
+        unsigned m = 0;
+        for (int l = 0; l < 32; l++) m |= (unsigned)(s[l] & 1ull) << l;
+        return m;
+    });
+}
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
+template <typename T>
+static inline T __shfl_sync(unsigned, T v, int src) {
+    unsigned long long b = 0;
+    memcpy(&b, &v, sizeof(T));
+    const unsigned long long r = emu_warp_collective(b, [src](const unsigned long long *s) { return s[src & 31]; });
+    T o;
+    memcpy(&o, &r, sizeof(T));
+    return o;
+}
+template <typename T>
+static inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
+    unsigned long long b = 0;
+    memcpy(&b, &v, sizeof(T));
+    const int lane = emu_lane;
+    const unsigned long long r = emu_warp_collective(b, [lane, delta](const unsigned long long *s) { return lane >= (int)delta ? s[lane - delta] : s[lane]; });
+    T o;
+    memcpy(&o, &r, sizeof(T));
+    return o;
+}
+template <typename T>
+static inline T __shfl_down_sync(unsigned, T v, unsigned delta) {
+    unsigned long long b = 0;
+    memcpy(&b, &v, sizeof(T));
+    const int lane = emu_lane;
+    const unsigned long long r = emu_warp_collective(b, [lane, delta](const unsigned long long *s) { return lane + (int)delta < 32 ? s[lane + delta] : s[lane]; });
+    T o;
+    memcpy(&o, &r, sizeof(T));
+    return o;
+}
+template <typename T>
+static inline T __shfl_xor_sync(unsigned, T v, int mask) {
+    unsigned long long b = 0;
+    memcpy(&b, &v, sizeof(T));
+    const int lane = emu_lane;
+    const unsigned long long r = emu_warp_collective(b, [lane, mask](const unsigned long long *s) { return s[(lane ^ mask) & 31]; });
+    T o;
+    memcpy(&o, &r, sizeof(T));
+    return o;
+}
+static inline int __reduce_max_sync(unsigned, int v) {
+    return emu_warp_collective((unsigned long long)(long long)v, [](const unsigned long long *s) {
+        int m = (int)(long long)s[0];
+        for (int l = 1; l < 32; l++) m = std::max(m, (int)(long long)s[l]);
+        return m;
+    });
+}
+static inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+    return emu_warp_collective((unsigned long long)v, [](const unsigned long long *s) {
+        unsigned a = 0;
+        for (int l = 0; l < 32; l++) a += (unsigned)s[l];
+        return a;
+    });
+}
+static inline unsigned __activemask() { return 0xffffffffu; }
+
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline T __ldcg(const T *p) { return *const_cast<const volatile T *>(p); }
+template <typename T> static inline void __stcg(T *p, T v) { *p = v; }
+static inline int4 __ldcg(const int4 *p) { int4 v; memcpy(&v, p, sizeof v); return v; }
+static inline uint4 __ldcg(const uint4 *p) { uint4 v; memcpy(&v, p, sizeof v); return v; }
+template <typename T> static inline T atomicAdd(T *p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+template <typename T> static inline T atomicOr(T *p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+template <typename T> static inline T atomicAnd(T *p, T v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s) { s &= 31; return s ? (hi << s) | (lo >> (32 - s)) : hi; }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) { s &= 31; return s ? (lo >> s) | (hi << (32 - s)) : lo; }
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+static inline int __float2int_rn(float v) { return (int)lrintf(v); }
+static inline float __uint_as_float(unsigned v) { float f; memcpy(&f, &v, 4); return f; }
+static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
+using std::max;
+using std::min;
+
+// run `grid` blocks of `block` threads (a multiple of 32), one block after the other
+template <typename F>
+static void emu_launch(unsigned grid, unsigned block, F kernel_call) {
+    emu_gridDim.x = grid;
+    emu_blockDim.x = block;
+    for (unsigned b = 0; b < grid; b++) {
+        std::barrier<> bar(block);
+        emu_block_bar = &bar;
+        std::vector<std::unique_ptr<EmuWarp>> warps;
+        for (unsigned w = 0; w < (block + 31) / 32; w++) warps.emplace_back(new EmuWarp());
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < block; t++)
+            th.emplace_back([&, t, b] {
+                emu_threadIdx.x = t;
+                emu_blockIdx.x = b;
+                emu_warp = warps[t / 32].get();
+                emu_lane = (int)(t % 32);
+                kernel_call();
+            });
+        for (auto &x : th) x.join();
+    }
+    emu_block_bar = nullptr;
+}

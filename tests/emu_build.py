@@ -1,0 +1,51 @@
+"""Build helper of the CPU emulation tests: compiles a harness under tests/emu/ with g++ against the product's kernel
+sources.  Kernels that use dynamic shared memory or PTX hints get two mechanical edits in a scratch copy (`extern __shared__`
+-> `extern`; `asm volatile("prefetch...")` lines dropped); common.cuh is copied with its header include made path-independent."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(REPO, "metdetpy_b200", "csrc")
+
+
+def cuda_include():
+    for p in ("/usr/local/cuda/include", os.path.join(os.environ.get("CUDA_HOME", "/nonexistent"), "include")):
+        if os.path.exists(os.path.join(p, "cuda_runtime.h")):
+            return p
+    return None
+
+
+def patched_sources(tmp, names):
+    """Scratch copies `<name>` -> `<stem>_emu.cuh` of kernel headers (+ common.cuh), edited for the block emulator."""
+    for name in names:
+        src = open(os.path.join(CSRC, name)).read()
+        src = src.replace("extern __shared__", "extern")
+        src = re.sub(r"\n[^\n]*asm volatile\(\"prefetch\.global\.L2[^\n]*", "\n", src)
+        src = src.replace('#include "common.cuh"', '#include "common.cuh"')
+        open(os.path.join(tmp, name.replace(".cuh", "_emu.cuh")), "w").write(src)
+    c = open(os.path.join(CSRC, "common.cuh")).read().replace('#include "../../include/metdet_b200.h"', '#include "metdet_b200.h"')
+    open(os.path.join(tmp, "common.cuh"), "w").write(c)
+
+
+def build(tmp, harness, patched=(), extra_c=(), std="c++20", opt="-O1"):
+    if shutil.which("g++") is None or shutil.which("gcc") is None:
+        pytest.skip("no g++ / gcc")
+    inc = cuda_include()
+    if inc is None:
+        pytest.skip("CUDA headers not found")
+    tmp = str(tmp)
+    patched_sources(tmp, patched)
+    objs = []
+    for c in extra_c:
+        o = os.path.join(tmp, os.path.basename(c) + ".o")
+        subprocess.check_call(["gcc", "-O2", "-c", os.path.join(REPO, c), "-o", o])
+        objs.append(o)
+    exe = os.path.join(tmp, os.path.splitext(os.path.basename(harness))[0])
+    subprocess.check_call(["g++", opt, f"-std={std}", "-ffp-contract=off", "-pthread", "-I", tmp, "-I", os.path.join(REPO, "tests", "emu"),
+                           "-I", os.path.join(REPO, "include"), "-I", inc, os.path.join(REPO, "tests", "emu", harness)] + objs +
+                          ["-o", exe])
+    return exe
