@@ -33,7 +33,9 @@ static EmuDim emu_blockDim, emu_gridDim;
 #define gridDim emu_gridDim
 #undef __launch_bounds__
 #define __launch_bounds__(...)
+#undef __shared__
 #define __shared__ static
+#undef __constant__
 #define __constant__
 
 struct EmuWarp {
@@ -149,26 +151,31 @@ static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; 
 using std::max;
 using std::min;
 
-// run `grid` blocks of `block` threads (a multiple of 32), one block after the other
+// run grid_x * grid_y blocks of `block` threads (a multiple of 32), one block after the other
 template <typename F>
-static void emu_launch(unsigned grid, unsigned block, F kernel_call) {
-    emu_gridDim.x = grid;
+static void emu_launch2(unsigned grid_x, unsigned grid_y, unsigned block, F kernel_call) {
+    emu_gridDim.x = grid_x;
+    emu_gridDim.y = grid_y;
     emu_blockDim.x = block;
-    for (unsigned b = 0; b < grid; b++) {
-        std::barrier<> bar(block);
-        emu_block_bar = &bar;
-        std::vector<std::unique_ptr<EmuWarp>> warps;
-        for (unsigned w = 0; w < (block + 31) / 32; w++) warps.emplace_back(new EmuWarp());
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < block; t++)
-            th.emplace_back([&, t, b] {
-                emu_threadIdx.x = t;
-                emu_blockIdx.x = b;
-                emu_warp = warps[t / 32].get();
-                emu_lane = (int)(t % 32);
-                kernel_call();
-            });
-        for (auto &x : th) x.join();
-    }
+    for (unsigned by = 0; by < grid_y; by++)
+        for (unsigned b = 0; b < grid_x; b++) {
+            std::barrier<> bar(block);
+            emu_block_bar = &bar;
+            std::vector<std::unique_ptr<EmuWarp>> warps;
+            for (unsigned w = 0; w < (block + 31) / 32; w++) warps.emplace_back(new EmuWarp());
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < block; t++)
+                th.emplace_back([&, t, b, by] {
+                    emu_threadIdx.x = t;
+                    emu_blockIdx.x = b;
+                    emu_blockIdx.y = by;
+                    emu_warp = warps[t / 32].get();
+                    emu_lane = (int)(t % 32);
+                    kernel_call();
+                });
+            for (auto &x : th) x.join();
+        }
     emu_block_bar = nullptr;
 }
+template <typename F>
+static void emu_launch(unsigned grid, unsigned block, F kernel_call) { emu_launch2(grid, 1, block, kernel_call); }
