@@ -125,14 +125,31 @@ static inline unsigned __reduce_add_sync(unsigned, unsigned v) {
 }
 static inline unsigned __activemask() { return 0xffffffffu; }
 
+#define __grid_constant__
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline T __ldcs(const T *p) { return *p; }
+static inline unsigned __vmaxu2(unsigned a, unsigned b) {
+    const unsigned lo = std::max(a & 0xffffu, b & 0xffffu), hi = std::max(a >> 16, b >> 16);
+    return (hi << 16) | lo;
+}
+static inline unsigned __vmaxu4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int k = 0; k < 4; k++) r |= std::max((a >> (8 * k)) & 0xffu, (b >> (8 * k)) & 0xffu) << (8 * k);
+    return r;
+}
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {  // unsigned bytes
+    for (int k = 0; k < 4; k++) c += ((a >> (8 * k)) & 0xffu) * ((b >> (8 * k)) & 0xffu);
+    return c;
+}
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline double __dsqrt_rn(double a) { volatile double r = std::sqrt(a); return r; }
 template <typename T> static inline T __ldcg(const T *p) { return *const_cast<const volatile T *>(p); }
 template <typename T> static inline void __stcg(T *p, T v) { *p = v; }
 static inline int4 __ldcg(const int4 *p) { int4 v; memcpy(&v, p, sizeof v); return v; }
 static inline uint4 __ldcg(const uint4 *p) { uint4 v; memcpy(&v, p, sizeof v); return v; }
-template <typename T> static inline T atomicAdd(T *p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-template <typename T> static inline T atomicOr(T *p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
-template <typename T> static inline T atomicAnd(T *p, T v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }
+template <typename T, typename V> static inline T atomicAdd(T *p, V v) { return __atomic_fetch_add(p, (T)v, __ATOMIC_SEQ_CST); }
+template <typename T, typename V> static inline T atomicOr(T *p, V v) { return __atomic_fetch_or(p, (T)v, __ATOMIC_SEQ_CST); }
+template <typename T, typename V> static inline T atomicAnd(T *p, V v) { return __atomic_fetch_and(p, (T)v, __ATOMIC_SEQ_CST); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
@@ -151,30 +168,33 @@ static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; 
 using std::max;
 using std::min;
 
-// run grid_x * grid_y blocks of `block` threads (a multiple of 32), one block after the other
+// run grid_x * grid_y blocks of `block` threads (a multiple of 32), one block after the other: the `block` OS threads are
+// started once per launch and walk through the blocks together (a block barrier between two blocks keeps the function-local
+// "shared memory" statics of one block from being touched by the next)
 template <typename F>
 static void emu_launch2(unsigned grid_x, unsigned grid_y, unsigned block, F kernel_call) {
     emu_gridDim.x = grid_x;
     emu_gridDim.y = grid_y;
     emu_blockDim.x = block;
-    for (unsigned by = 0; by < grid_y; by++)
-        for (unsigned b = 0; b < grid_x; b++) {
-            std::barrier<> bar(block);
-            emu_block_bar = &bar;
-            std::vector<std::unique_ptr<EmuWarp>> warps;
-            for (unsigned w = 0; w < (block + 31) / 32; w++) warps.emplace_back(new EmuWarp());
-            std::vector<std::thread> th;
-            for (unsigned t = 0; t < block; t++)
-                th.emplace_back([&, t, b, by] {
-                    emu_threadIdx.x = t;
+    std::barrier<> bar(block);
+    emu_block_bar = &bar;
+    std::vector<std::unique_ptr<EmuWarp>> warps;
+    for (unsigned w = 0; w < (block + 31) / 32; w++) warps.emplace_back(new EmuWarp());
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < block; t++)
+        th.emplace_back([&, t] {
+            emu_threadIdx.x = t;
+            emu_warp = warps[t / 32].get();
+            emu_lane = (int)(t % 32);
+            for (unsigned by = 0; by < grid_y; by++)
+                for (unsigned b = 0; b < grid_x; b++) {
                     emu_blockIdx.x = b;
                     emu_blockIdx.y = by;
-                    emu_warp = warps[t / 32].get();
-                    emu_lane = (int)(t % 32);
                     kernel_call();
-                });
-            for (auto &x : th) x.join();
-        }
+                    bar.arrive_and_wait();
+                }
+        });
+    for (auto &x : th) x.join();
     emu_block_bar = nullptr;
 }
 template <typename F>

@@ -25,13 +25,15 @@ def patched_sources(tmp, names):
         src = open(os.path.join(CSRC, name)).read()
         src = src.replace("extern __shared__", "extern")
         src = re.sub(r"\n[^\n]*asm volatile\(\"prefetch\.global\.L2[^\n]*", "\n", src)
+        # host-side launchers (<<< >>> syntax) inside kernel headers are not part of the device code under test
+        src = re.sub(r"static inline void launch_noise_samples\(.*?\n}\n", "", src, flags=re.S)
         src = src.replace('#include "common.cuh"', '#include "common.cuh"')
         open(os.path.join(tmp, name.replace(".cuh", "_emu.cuh")), "w").write(src)
     c = open(os.path.join(CSRC, "common.cuh")).read().replace('#include "../../include/metdet_b200.h"', '#include "metdet_b200.h"')
     open(os.path.join(tmp, "common.cuh"), "w").write(c)
 
 
-def build(tmp, harness, patched=(), extra_c=(), std="c++20", opt="-O1"):
+def build(tmp, harness, patched=(), extra_c=(), std="c++20", opt="-O1", shared=False):
     if shutil.which("g++") is None or shutil.which("gcc") is None:
         pytest.skip("no g++ / gcc")
     inc = cuda_include()
@@ -42,10 +44,10 @@ def build(tmp, harness, patched=(), extra_c=(), std="c++20", opt="-O1"):
     objs = []
     for c in extra_c:
         o = os.path.join(tmp, os.path.basename(c) + ".o")
-        subprocess.check_call(["gcc", "-O2", "-c", os.path.join(REPO, c), "-o", o])
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-c", os.path.join(REPO, c), "-o", o])
         objs.append(o)
-    exe = os.path.join(tmp, os.path.splitext(os.path.basename(harness))[0])
-    subprocess.check_call(["g++", opt, f"-std={std}", "-ffp-contract=off", "-pthread", "-I", tmp, "-I", os.path.join(REPO, "tests", "emu"),
+    exe = os.path.join(tmp, os.path.splitext(os.path.basename(harness))[0] + (".so" if shared else ""))
+    subprocess.check_call(["g++", opt, f"-std={std}", "-ffp-contract=off", "-pthread"] + (["-shared", "-fPIC"] if shared else []) + ["-I", tmp, "-I", os.path.join(REPO, "tests", "emu"),
                            "-I", os.path.join(REPO, "include"), "-I", inc, os.path.join(REPO, "tests", "emu", harness)] + objs +
                           ["-o", exe])
     return exe
