@@ -1,0 +1,139 @@
+// The product's batched (streaming) path on the CPU: noise samples + threshold recurrence for a whole batch, temporal3's
+// per-thread code (csrc/temporal3_kernel.cuh, host build of the same source), act4 / act, dst_sparse / dst_dense
+// (csrc/spatial_kernel.cuh) and the PPHT kernels (csrc/hough.cuh) under the thread-block emulator, batch after batch with
+// the frame ring, act ring and mask buffers carried over -- the sequence submit_impl / stream_kernel_launch /
+// launch_hough_kernels issue (csrc/metdet.cu, csrc/stream_kernel.cuh).  Built as a shared library;
+// tests/test_stream_emu_cpu.py feeds it golden trajectories of the live reference.  Test infrastructure.
+#include "cuda_block_emu.h"
+
+#include <cstdio>
+#include <cstdlib>
+
+uint32_t h_sm[96 * 1024];
+uint16_t o_sm[8192];
+#define T3_HOST_EMU 1
+#include "temporal3_kernel_emu.cuh"
+#include "kernels_basic_emu.cuh"
+#include "spatial_kernel_emu.cuh"
+#include "hough_emu.cuh"
+
+template <int U, int BL, int P, int K>
+static void temporal3_batch(const FrameSrc &src, long long t0, int T, int HWG, const int *thr, uint8_t *bits) {
+    typedef t3::Layout<U, BL, P, 0, K> LY;
+    std::vector<unsigned char> smem(LY::smem_bytes(T) + 64);
+    const int Tp = (T + BL - 1) / BL * BL;
+    for (int c = 0; c * T3_NT < HWG; c++) {  // one CTA after the other, its threads one after the other
+        uint2 *tab = reinterpret_cast<uint2 *>(smem.data() + LY::tab_off);
+        for (int i = 0; i < Tp; i++) tab[i] = t3::table_entry(thr[i < T ? i : T - 1], t0 + i, LY::N);
+        for (int tid = 0; tid < T3_NT; tid++) {
+            const int g = c * T3_NT + tid;
+            if (g >= HWG) break;
+            t3::thread_main<U, BL, P, K, false, 0>(src, t0, T, g, tid, smem.data(), bits, (size_t)HWG, nullptr, T3_NT);
+        }
+    }
+}
+
+extern "C" int emu_stream_path(const uint8_t *frames, int Ttot, int W, int H, int n, int B, int adaptive, int init_value,
+                               int sensitivity, int nz_interval, const int *roi, int hough_thr, int hough_min_len,
+                               int hough_max_gap, int dy_on, double mask_area, int *thr_out, double *snr_out, uint8_t *dst_out,
+                               int *n_on_out, int *lines_num_out, int32_t *raw_out /*[Ttot][512][4]*/) {
+    if (W % 32 || n < 2) return -1000;
+    const float theta = (float)(3.14159265358979323846 / 180.0);
+    for (int k = 0; k < MDB_HOUGH_ANGLES; k++) {
+        c_trig[2 * k] = (float)cos((double)k * (double)theta);
+        c_trig[2 * k + 1] = (float)sin((double)k * (double)theta);
+    }
+    const size_t HW = (size_t)W * H;
+    const int Wb = W / 32, R = n - 1 + 2 * B, RA = R, HWG = (int)(HW / 8);
+    const size_t FW = (size_t)H * Wb;
+    std::vector<uint8_t> ringbuf((size_t)R * HW, 0), dst((size_t)B * HW, 0);
+    std::vector<uint32_t> actbuf((size_t)RA * FW, 0), bits((size_t)(B + 32) * FW, 0), dstbits((size_t)B * FW, 0), alist((size_t)B * SPX_ACAP),
+        wlist((size_t)B * SPX_WCAP), points((size_t)B * MDB_POINT_CAP), okeys(HW), oidx(HW), bitmap((HW + 31) / 32, 0), walk(W + H + 2, 0);
+    std::vector<unsigned> acount(B, 0), wcount(B, 0), dense(B + 1, 0), npoints(B, 0);
+    std::vector<uint16_t> order((size_t)B * HOUGH_ORDER_CAP);
+    std::vector<int32_t> lines((size_t)B * 512 * 4), accum((size_t)MDB_HOUGH_ANGLES * (2 * (W + H) + 1), 0);
+    std::vector<int> nlines(B), thr(B);
+    std::vector<double> thrf(B), snr(B);
+    std::vector<unsigned long long> noise((size_t)B * 2);
+    ActRing ring; ring.base = actbuf.data(); ring.RA = RA; ring.Wb = Wb; ring.frame_words = FW;
+    SparseLists sl; sl.alist = alist.data(); sl.acount = acount.data(); sl.wlist = wlist.data(); sl.wcount = wcount.data(); sl.dense = dense.data();
+    DevState st;
+    memset(&st, 0, sizeof st);
+    st.ema_init_m = 1.0 - (double)nz_interval / 60.0;
+    st.ema_cur_m = st.ema_init_m;
+    st.ema_warm = (double)n;
+    static const int abs_sens[3] = {7, 5, 3};
+    st.bi_threshold = adaptive ? abs_sens[sensitivity] : init_value;
+    st.thr_float = (double)st.bi_threshold;
+    HoughParams P;
+    P.W = W; P.H = H; P.numrho = 2 * (W + H) + 1; P.threshold = hough_thr; P.min_len = hough_min_len; P.max_gap = hough_max_gap;
+    P.mask_area = mask_area; P.cap = MDB_POINT_CAP; P.max_lines = 512; P.walk_cap = W + H + 2; P.fixed_gap = -1;
+    const int rh = roi[2] - roi[0], rw = roi[3] - roi[1];
+    const long long std_interval = (long long)nz_interval * n;
+    for (long long t0 = 0; t0 < Ttot; t0 += B) {
+        const int T = (int)std::min<long long>(B, Ttot - t0);
+        FrameSrc src; src.ring = ringbuf.data(); src.cur = frames + (size_t)t0 * HW; src.mask = nullptr; src.t0 = t0; src.R = R; src.HW = HW;
+        // ---- launch_noise_thr ------------------------------------------------------------------------------------------
+        std::fill(noise.begin(), noise.end(), 0ull);
+        SampleList sml; sml.count = 0;
+        for (int i = 0; i < T && sml.count >= 0; i++) {
+            const long long tau = t0 + i + 1;
+            if ((tau > 1 && tau <= n) || (tau > n && std_interval > 0 && tau % std_interval == 0)) {
+                if (sml.count < 63) sml.idx[sml.count++] = i; else sml.count = -1;
+            }
+        }
+        if (sml.count != 0) {
+            const int rows = sml.count < 0 ? T : sml.count, gx = std::max(1, std::min((rh * rw + 255) / 256, 8));
+            emu_launch2(gx, rows, 256, [&] { noise_sample_kernel(src, W, n, t0, std_interval, roi[0], roi[1], rh, rw, noise.data(), 0, sml); });
+        }
+        emu_launch(1, 32, [&] { threshold_kernel(&st, noise.data(), T, t0, n, std_interval, (long long)rh * rw, adaptive, sensitivity, thr.data(), thrf.data(), snr.data()); });
+        // ---- temporal pass (shape table of temporal3_dispatch.cuh) -------------------------------------------------------
+        uint8_t *bits8 = reinterpret_cast<uint8_t *>(bits.data());
+        switch (n) {
+            case 5: temporal3_batch<5, 5, 1, 5>(src, t0, T, HWG, thr.data(), bits8); break;
+            case 6: temporal3_batch<6, 6, 1, 6>(src, t0, T, HWG, thr.data(), bits8); break;
+            case 12: temporal3_batch<12, 12, 1, 6>(src, t0, T, HWG, thr.data(), bits8); break;
+            case 25: temporal3_batch<25, 5, 1, 5>(src, t0, T, HWG, thr.data(), bits8); break;
+            case 30: temporal3_batch<15, 15, 2, 15>(src, t0, T, HWG, thr.data(), bits8); break;
+            default: return -1001;
+        }
+        // history for the next batch: the last min(T, n) frames go into the ring (copy_to_ring)
+        for (long long t = t0 + T - std::min(T, n); t < t0 + T; t++) memcpy(&ringbuf[(size_t)(t % R) * HW], frames + (size_t)t * HW, HW);
+        // ---- stream_kernel_launch: act, dst -------------------------------------------------------------------------------
+        std::fill(npoints.begin(), npoints.end(), 0u);
+        std::fill(acount.begin(), acount.end(), 0u);
+        const int rows_act = 64, strips = (Wb + SP_USE - 1) / SP_USE, bands = (H + rows_act - 1) / rows_act;
+        if (Wb % 4 == 0) {
+            const int chunks = Wb / 4;
+            emu_launch2((chunks * bands + A4_THREADS - 1) / A4_THREADS, T, A4_THREADS, [&] { act4_kernel(bits.data(), H, Wb, rows_act, chunks, bands, ring, t0, sl); });
+        } else {
+            emu_launch2((strips * bands + SP_WARPS - 1) / SP_WARPS, T, SP_WARPS * 32, [&] { act_kernel(bits.data(), W, H, T, rows_act, strips, bands, ring, t0, sl); });
+        }
+        dense[0] = 0;
+        emu_launch(T, 256, [&] { dst_sparse_kernel(ring, W, H, n, t0, dy_on, dst.data(), dstbits.data(), npoints.data(), points.data(), MDB_POINT_CAP, sl); });
+        const int dst_rows = 32, dbands = (H + dst_rows - 1) / dst_rows;
+        if (dense[0])
+            emu_launch2((strips * dbands + SP_WARPS - 1) / SP_WARPS, std::min(T, DENSE_GY), SP_WARPS * 32, [&] {
+                dst_dense_kernel(ring, W, H, n, t0, dy_on, dst_rows, strips, dbands, dst.data(), dstbits.data(), npoints.data(), points.data(), MDB_POINT_CAP, sl);
+            });
+        // ---- launch_hough_kernels (one emulated CTA takes every frame from the queue) ------------------------------------------
+        unsigned queue[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        emu_launch(T, 32, [&] { ppht_order_kernel(T, HOUGH_ORDER_CAP, npoints.data(), order.data()); });
+        emu_launch(1, HOUGH_THREADS, [&] { hough_smem_kernel(P, T, npoints.data(), points.data(), order.data(), lines.data(), nlines.data(), queue, nullptr, HOUGH_CAP_SMALL, HOUGH_TABLE_BYTES_SMALL, 0); });
+        bool f2 = false, f3 = false, f1 = false;
+        for (int i = 0; i < T; i++) f1 |= nlines[i] == -2;
+        if (f1) emu_launch(1, HOUGH_THREADS, [&] { hough_smem_kernel(P, T, npoints.data(), points.data(), order.data(), lines.data(), nlines.data(), queue + 1, nullptr, HOUGH_CAP_LARGE, HOUGH_TABLE_BYTES, 1); });
+        for (int i = 0; i < T; i++) f2 |= nlines[i] == -3;
+        if (f2) emu_launch(1, HOUGH_THREADS, [&] { hough_tier2_kernel(P, T, npoints.data(), points.data(), accum.data(), lines.data(), nlines.data(), nullptr, queue + 7); });
+        for (int i = 0; i < T; i++) f3 |= nlines[i] == -1;
+        if (f3) emu_launch(1, HOUGH_THREADS, [&] { hough_tier3_kernel(P, T, dst.data(), okeys.data(), oidx.data(), accum.data(), bitmap.data(), walk.data(), lines.data(), nlines.data(), queue + 2, nullptr); });
+        for (int i = 0; i < T; i++) {
+            if (nlines[i] < 0) return -(int)(t0 + i + 1);
+            thr_out[t0 + i] = thr[i]; snr_out[t0 + i] = snr[i];
+            n_on_out[t0 + i] = (int)npoints[i]; lines_num_out[t0 + i] = nlines[i];
+            memcpy(dst_out + (size_t)(t0 + i) * HW, dst.data() + (size_t)i * HW, HW);
+            memcpy(raw_out + (size_t)(t0 + i) * 512 * 4, lines.data() + (size_t)i * 512 * 4, (size_t)std::min(nlines[i], 512) * 16);
+        }
+    }
+    return 0;
+}
