@@ -125,6 +125,7 @@ static inline unsigned __reduce_add_sync(unsigned, unsigned v) {
 }
 static inline unsigned __activemask() { return 0xffffffffu; }
 
+#undef __grid_constant__
 #define __grid_constant__
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 template <typename T> static inline T __ldcs(const T *p) { return *p; }
@@ -135,6 +136,20 @@ static inline unsigned __vmaxu2(unsigned a, unsigned b) {
 static inline unsigned __vmaxu4(unsigned a, unsigned b) {
     unsigned r = 0;
     for (int k = 0; k < 4; k++) r |= std::max((a >> (8 * k)) & 0xffu, (b >> (8 * k)) & 0xffu) << (8 * k);
+    return r;
+}
+static inline unsigned __vabsdiffu4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int k = 0; k < 4; k++) {
+        const int x = (a >> (8 * k)) & 0xff, y = (b >> (8 * k)) & 0xff;
+        r |= (unsigned)(x > y ? x - y : y - x) << (8 * k);
+    }
+    return r;
+}
+static inline unsigned __vcmpgtu4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int k = 0; k < 4; k++)
+        if (((a >> (8 * k)) & 0xff) > ((b >> (8 * k)) & 0xff)) r |= 0xffu << (8 * k);
     return r;
 }
 static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {  // unsigned bytes
@@ -172,9 +187,10 @@ using std::min;
 // started once per launch and walk through the blocks together (a block barrier between two blocks keeps the function-local
 // "shared memory" statics of one block from being touched by the next)
 template <typename F>
-static void emu_launch2(unsigned grid_x, unsigned grid_y, unsigned block, F kernel_call) {
+static void emu_launch3(unsigned grid_x, unsigned grid_y, unsigned grid_z, unsigned block, F kernel_call) {
     emu_gridDim.x = grid_x;
     emu_gridDim.y = grid_y;
+    emu_gridDim.z = grid_z;
     emu_blockDim.x = block;
     std::barrier<> bar(block);
     emu_block_bar = &bar;
@@ -186,16 +202,20 @@ static void emu_launch2(unsigned grid_x, unsigned grid_y, unsigned block, F kern
             emu_threadIdx.x = t;
             emu_warp = warps[t / 32].get();
             emu_lane = (int)(t % 32);
-            for (unsigned by = 0; by < grid_y; by++)
-                for (unsigned b = 0; b < grid_x; b++) {
-                    emu_blockIdx.x = b;
-                    emu_blockIdx.y = by;
-                    kernel_call();
-                    bar.arrive_and_wait();
-                }
+            for (unsigned bz = 0; bz < grid_z; bz++)
+                for (unsigned by = 0; by < grid_y; by++)
+                    for (unsigned b = 0; b < grid_x; b++) {
+                        emu_blockIdx.x = b;
+                        emu_blockIdx.y = by;
+                        emu_blockIdx.z = bz;
+                        kernel_call();
+                        bar.arrive_and_wait();
+                    }
         });
     for (auto &x : th) x.join();
     emu_block_bar = nullptr;
 }
 template <typename F>
-static void emu_launch(unsigned grid, unsigned block, F kernel_call) { emu_launch2(grid, 1, block, kernel_call); }
+static void emu_launch2(unsigned grid_x, unsigned grid_y, unsigned block, F kernel_call) { emu_launch3(grid_x, grid_y, 1, block, kernel_call); }
+template <typename F>
+static void emu_launch(unsigned grid, unsigned block, F kernel_call) { emu_launch3(grid, 1, 1, block, kernel_call); }

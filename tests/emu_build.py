@@ -27,7 +27,8 @@ def patched_sources(tmp, names):
         src = re.sub(r"\n[^\n]*asm volatile\(\"prefetch\.global\.L2[^\n]*", "\n", src)
         # host-side launchers (<<< >>> syntax) inside kernel headers are not part of the device code under test
         src = re.sub(r"static inline void launch_noise_samples\(.*?\n}\n", "", src, flags=re.S)
-        src = src.replace('#include "common.cuh"', '#include "common.cuh"')
+        for other in names:  # headers under test that include each other pick up the scratch copies
+            src = src.replace(f'#include "{other}"', f'#include "{other.replace(".cuh", "_emu.cuh")}"')
         open(os.path.join(tmp, name.replace(".cuh", "_emu.cuh")), "w").write(src)
     c = open(os.path.join(CSRC, "common.cuh")).read().replace('#include "../../include/metdet_b200.h"', '#include "metdet_b200.h"')
     open(os.path.join(tmp, "common.cuh"), "w").write(c)
