@@ -33,10 +33,12 @@ static void temporal3_batch(const FrameSrc &src, long long t0, int T, int HWG, c
     }
 }
 
-extern "C" int emu_stream_path(const uint8_t *frames, int Ttot, int W, int H, int n, int B, int adaptive, int init_value,
-                               int sensitivity, int nz_interval, const int *roi, int hough_thr, int hough_min_len,
-                               int hough_max_gap, int dy_on, double mask_area, int *thr_out, double *snr_out, uint8_t *dst_out,
-                               int *n_on_out, int *lines_num_out, int32_t *raw_out /*[Ttot][512][4]*/) {
+// frames[0] is global frame t_first (mdb_seek); the first `halo` frames are look-back frames whose results are not wanted
+// (MDB_SUBMIT_HALO: window and act history only); thr_in != nullptr: thresholds supplied by the caller (mdb_submit_batch_thr)
+static int run_range(const uint8_t *frames, int Ttot, long long t_first, int halo, const int *thr_in, int W, int H, int n, int B,
+                     int adaptive, int init_value, int sensitivity, int nz_interval, const int *roi, int hough_thr,
+                     int hough_min_len, int hough_max_gap, int dy_on, double mask_area, int *thr_out, double *snr_out,
+                     uint8_t *dst_out, int *n_on_out, int *lines_num_out, int32_t *raw_out /*[Ttot][512][4]*/) {
     if (W % 32 || n < 2) return -1000;
     const float theta = (float)(3.14159265358979323846 / 180.0);
     for (int k = 0; k < MDB_HOUGH_ANGLES; k++) {
@@ -70,10 +72,17 @@ extern "C" int emu_stream_path(const uint8_t *frames, int Ttot, int W, int H, in
     P.mask_area = mask_area; P.cap = MDB_POINT_CAP; P.max_lines = 512; P.walk_cap = W + H + 2; P.fixed_gap = -1;
     const int rh = roi[2] - roi[0], rw = roi[3] - roi[1];
     const long long std_interval = (long long)nz_interval * n;
-    for (long long t0 = 0; t0 < Ttot; t0 += B) {
-        const int T = (int)std::min<long long>(B, Ttot - t0);
-        FrameSrc src; src.ring = ringbuf.data(); src.cur = frames + (size_t)t0 * HW; src.mask = nullptr; src.t0 = t0; src.R = R; src.HW = HW;
-        // ---- launch_noise_thr ------------------------------------------------------------------------------------------
+    const long long t_end = t_first + Ttot;
+    for (long long t0 = t_first; t0 < t_end;) {
+        // halo frames go first, in batches of their own (results dropped); then the frames whose results are wanted
+        const bool is_halo = t0 < t_first + halo;
+        const int T = (int)std::min<long long>(B, (is_halo ? t_first + halo : t_end) - t0);
+        const uint8_t *bframes = frames + (size_t)(t0 - t_first) * HW;
+        FrameSrc src; src.ring = ringbuf.data(); src.cur = bframes; src.mask = nullptr; src.t0 = t0; src.R = R; src.HW = HW;
+        // ---- launch_noise_thr (or the caller's thresholds) --------------------------------------------------------------
+        if (thr_in) {
+            for (int i = 0; i < T; i++) { thr[i] = thr_in[t0 - t_first + i]; snr[i] = 0.0; }
+        } else {
         std::fill(noise.begin(), noise.end(), 0ull);
         SampleList sml; sml.count = 0;
         for (int i = 0; i < T && sml.count >= 0; i++) {
@@ -87,6 +96,7 @@ extern "C" int emu_stream_path(const uint8_t *frames, int Ttot, int W, int H, in
             emu_launch2(gx, rows, 256, [&] { noise_sample_kernel(src, W, n, t0, std_interval, roi[0], roi[1], rh, rw, noise.data(), 0, sml); });
         }
         emu_launch(1, 32, [&] { threshold_kernel(&st, noise.data(), T, t0, n, std_interval, (long long)rh * rw, adaptive, sensitivity, thr.data(), thrf.data(), snr.data()); });
+        }
         // ---- temporal pass (shape table of temporal3_dispatch.cuh) -------------------------------------------------------
         uint8_t *bits8 = reinterpret_cast<uint8_t *>(bits.data());
         switch (n) {
@@ -98,7 +108,7 @@ extern "C" int emu_stream_path(const uint8_t *frames, int Ttot, int W, int H, in
             default: return -1001;
         }
         // history for the next batch: the last min(T, n) frames go into the ring (copy_to_ring)
-        for (long long t = t0 + T - std::min(T, n); t < t0 + T; t++) memcpy(&ringbuf[(size_t)(t % R) * HW], frames + (size_t)t * HW, HW);
+        for (long long t = t0 + T - std::min(T, n); t < t0 + T; t++) memcpy(&ringbuf[(size_t)(t % R) * HW], frames + (size_t)(t - t_first) * HW, HW);
         // ---- stream_kernel_launch: act, dst -------------------------------------------------------------------------------
         std::fill(npoints.begin(), npoints.end(), 0u);
         std::fill(acount.begin(), acount.end(), 0u);
@@ -109,6 +119,7 @@ extern "C" int emu_stream_path(const uint8_t *frames, int Ttot, int W, int H, in
         } else {
             emu_launch2((strips * bands + SP_WARPS - 1) / SP_WARPS, T, SP_WARPS * 32, [&] { act_kernel(bits.data(), W, H, T, rows_act, strips, bands, ring, t0, sl); });
         }
+        if (is_halo) { t0 += T; continue; }  // act_only: no dst, no PPHT for look-back frames
         dense[0] = 0;
         emu_launch(T, 256, [&] { dst_sparse_kernel(ring, W, H, n, t0, dy_on, dst.data(), dstbits.data(), npoints.data(), points.data(), MDB_POINT_CAP, sl); });
         const int dst_rows = 32, dbands = (H + dst_rows - 1) / dst_rows;
@@ -129,11 +140,51 @@ extern "C" int emu_stream_path(const uint8_t *frames, int Ttot, int W, int H, in
         if (f3) emu_launch(1, HOUGH_THREADS, [&] { hough_tier3_kernel(P, T, dst.data(), okeys.data(), oidx.data(), accum.data(), bitmap.data(), walk.data(), lines.data(), nlines.data(), queue + 2, nullptr); });
         for (int i = 0; i < T; i++) {
             if (nlines[i] < 0) return -(int)(t0 + i + 1);
-            thr_out[t0 + i] = thr[i]; snr_out[t0 + i] = snr[i];
-            n_on_out[t0 + i] = (int)npoints[i]; lines_num_out[t0 + i] = nlines[i];
-            memcpy(dst_out + (size_t)(t0 + i) * HW, dst.data() + (size_t)i * HW, HW);
-            memcpy(raw_out + (size_t)(t0 + i) * 512 * 4, lines.data() + (size_t)i * 512 * 4, (size_t)std::min(nlines[i], 512) * 16);
+            const size_t k = (size_t)(t0 - t_first + i);
+            thr_out[k] = thr[i]; snr_out[k] = snr[i];
+            n_on_out[k] = (int)npoints[i]; lines_num_out[k] = nlines[i];
+            memcpy(dst_out + k * HW, dst.data() + (size_t)i * HW, HW);
+            memcpy(raw_out + k * 512 * 4, lines.data() + (size_t)i * 512 * 4, (size_t)std::min(nlines[i], 512) * 16);
         }
+        t0 += T;
+    }
+    return 0;
+}
+
+extern "C" int emu_stream_path(const uint8_t *frames, int Ttot, int W, int H, int n, int B, int adaptive, int init_value,
+                               int sensitivity, int nz_interval, const int *roi, int hough_thr, int hough_min_len,
+                               int hough_max_gap, int dy_on, double mask_area, int *thr_out, double *snr_out, uint8_t *dst_out,
+                               int *n_on_out, int *lines_num_out, int32_t *raw_out) {
+    return run_range(frames, Ttot, 0, 0, nullptr, W, H, n, B, adaptive, init_value, sensitivity, nz_interval, roi, hough_thr,
+                     hough_min_len, hough_max_gap, dy_on, mask_area, thr_out, snr_out, dst_out, n_on_out, lines_num_out, raw_out);
+}
+
+// one rank's share of a time-sharded run: seek to t_first, `halo` look-back frames, then the chunk with replayed thresholds
+extern "C" int emu_stream_chunk(const uint8_t *frames, int Ttot, long long t_first, int halo, const int *thr_in, int W, int H, int n,
+                                int B, const int *roi, int hough_thr, int hough_min_len, int hough_max_gap, int dy_on, double mask_area,
+                                int *thr_out, double *snr_out, uint8_t *dst_out, int *n_on_out, int *lines_num_out, int32_t *raw_out) {
+    return run_range(frames, Ttot, t_first, halo, thr_in, W, H, n, B, 0, 0, 1, 1, roi, hough_thr, hough_min_len, hough_max_gap, dy_on,
+                     mask_area, thr_out, snr_out, dst_out, n_on_out, lines_num_out, raw_out);
+}
+
+// integer noise sums (sum d, sum d^2) of the sample timers taus[] (what mdb_noise_sums_dev computes for a rank's chunk);
+// frames[0] is global frame t_first and must reach back far enough for every sample's window
+extern "C" int emu_noise_sums(const uint8_t *frames, int Ttot, long long t_first, int W, int H, int n, int nz_interval, const int *roi,
+                              const long long *taus, int ntaus, unsigned long long *sums) {
+    const size_t HW = (size_t)W * H;
+    std::vector<uint8_t> ringbuf(HW, 0);
+    std::vector<unsigned long long> acc((size_t)Ttot * 2, 0ull);
+    const int rh = roi[2] - roi[0], rw = roi[3] - roi[1];
+    const long long std_interval = (long long)nz_interval * n;
+    FrameSrc src; src.ring = ringbuf.data(); src.cur = frames; src.mask = nullptr; src.t0 = t_first; src.R = 1; src.HW = HW;
+    for (int k = 0; k < ntaus; k++) {
+        const long long tau = taus[k], L = tau < n ? tau : n;
+        const long long i = tau - 1 - t_first;
+        if (i < 0 || i >= Ttot || tau - L < t_first) return -1;
+        SampleList sml; sml.count = 1; sml.idx[0] = (int)i;
+        const int gx = std::max(1, std::min((rh * rw + 255) / 256, 8));
+        emu_launch2(gx, 1, 256, [&] { noise_sample_kernel(src, W, n, t_first, std_interval, roi[0], roi[1], rh, rw, acc.data(), 0, sml); });
+        sums[2 * k] = acc[2 * i]; sums[2 * k + 1] = acc[2 * i + 1];
     }
     return 0;
 }

@@ -55,3 +55,53 @@ def test_streaming_path_kernels_reproduce_the_reference_golden(emu_lib, name, fr
             assert np.array_equal(raw[t, :nl[t]], ragged_get(g["raw_lines"], g["raw_offs"], t)), t
         with_lines += nl[t] > 0
     assert with_lines > 0
+
+
+@pytest.mark.parametrize("name,world,batch", [("synth_384x216_n12_dyon_mask", 3, 7), ("clip_192x144_n25", 2, 16)])
+def test_time_sharded_protocol_on_the_cpu(emu_lib, name, world, batch):
+    """SURVEY 8(e) with product code only: every virtual rank computes the integer noise sums of its chunk's sample timers
+    (noise_sample_kernel, emulated), the sums are pooled (the all-gather), the threshold recurrence is replayed by the
+    library's host code (mdb_replay_thresholds), and every rank runs seek + (2n-2)-frame halo + its chunk with the replayed
+    thresholds through the emulated streaming kernels: thresholds, masks and raw segments of every frame equal the golden
+    trajectory of the live (sequential) reference."""
+    from metdetpy_b200 import sharding as S
+    g = load_det_case(name)
+    fr = np.ascontiguousarray(g["frames"])
+    T, H, W = fr.shape
+    n, c = int(g["n"]), g["cfg"]
+    roi_t = [int(v) for v in g["std_roi"]]
+    roi = (C.c_int * 4)(*roi_t)
+    roi_px = (roi_t[2] - roi_t[0]) * (roi_t[3] - roi_t[1])
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    shards = S.plan_shards(T, world, n)
+    samples = []
+    for sh in shards:
+        taus = np.ascontiguousarray(S.sample_timers(sh.start, sh.end, n, int(c["interval"])), np.int64)
+        if len(taus) == 0:
+            continue
+        lo = max(0, sh.start - (n - 1))
+        part = np.ascontiguousarray(fr[lo:sh.end])
+        sums = np.zeros((len(taus), 2), np.uint64)
+        assert emu_lib.emu_noise_sums(p(part), len(part), C.c_longlong(lo), W, H, n, int(c["interval"]), roi, p(taus), len(taus), p(sums)) == 0
+        samples += [(int(t), int(a), int(b)) for t, (a, b) in zip(taus, sums)]
+    thr, thr_f, snr = S.replay_thresholds_native(samples, roi_px, n, 0, T, adaptive=c["adaptive"], init_value=c["init_value"],
+                                                 sensitivity=c["sensitivity"], interval=c["interval"])
+    assert np.array_equal(thr, g["bi_threshold"]) and np.allclose(snr, g["snr"], rtol=1e-12, atol=0)
+    for sh in shards:
+        part = np.ascontiguousarray(fr[sh.halo_start:sh.end])
+        m = len(part)
+        halo = sh.start - sh.halo_start
+        assert halo == min(sh.start, 2 * n - 2)
+        thr_in = np.ascontiguousarray(thr[sh.halo_start:sh.end], np.int32)
+        o_thr = np.zeros(m, np.int32); o_snr = np.zeros(m); dst = np.zeros((m, H, W), np.uint8)
+        n_on = np.zeros(m, np.int32); nl = np.zeros(m, np.int32); raw = np.zeros((m, 512, 4), np.int32)
+        rc = emu_lib.emu_stream_chunk(p(part), m, C.c_longlong(sh.halo_start), halo, p(thr_in), W, H, n, batch, roi,
+                                      *[int(v) for v in c["hough"]], int(c["dy_mask"]), C.c_double(float(g["mask_area"])),
+                                      p(o_thr), p(o_snr), p(dst), p(n_on), p(nl), p(raw))
+        assert rc == 0, rc
+        for t in range(sh.start, sh.end):
+            k = t - sh.halo_start
+            assert np.array_equal(dst[k], g["dst"][t]), (sh.rank, t, int(np.count_nonzero(dst[k] != g["dst"][t])))
+            assert nl[k] == g["lines_num"][t], (sh.rank, t)
+            if nl[k] <= 500:
+                assert np.array_equal(raw[k, :nl[k]], ragged_get(g["raw_lines"], g["raw_offs"], t)), (sh.rank, t)
