@@ -16,6 +16,7 @@ uint16_t o_sm[8192];
 #include "kernels_basic_emu.cuh"
 #include "spatial_kernel_emu.cuh"
 #include "hough_emu.cuh"
+#include "perframe_kernel_emu.cuh"
 
 template <int U, int BL, int P, int K>
 static void temporal3_batch(const FrameSrc &src, long long t0, int T, int HWG, const int *thr, uint8_t *bits) {
@@ -185,6 +186,115 @@ extern "C" int emu_noise_sums(const uint8_t *frames, int Ttot, long long t_first
         const int gx = std::max(1, std::min((rh * rw + 255) / 256, 8));
         emu_launch2(gx, 1, 256, [&] { noise_sample_kernel(src, W, n, t_first, std_interval, roi[0], roi[1], rh, rw, acc.data(), 0, sml); });
         sums[2 * k] = acc[2 * i]; sums[2 * k + 1] = acc[2 * i + 1];
+    }
+    return 0;
+}
+
+
+// The per-frame API's resident-state path (pf_update() / mdb_detect() with bits_ready in csrc/metdet.cu): per frame the
+// staging copy, noise sample + threshold on (staging, ring), pf_update_kernel in two halves, the suffix rebuild at block ends,
+// then act (one-frame batch: 8-row bands), dst_sparse and the PPHT on the predicate bits it left behind.
+extern "C" int emu_perframe_path(const uint8_t *frames, int Ttot, int W, int H, int n, int adaptive, int init_value, int sensitivity,
+                                 int nz_interval, const int *roi, int hough_thr, int hough_min_len, int hough_max_gap, int dy_on,
+                                 double mask_area, int *thr_out, double *snr_out, uint8_t *dst_out, int *n_on_out, int *lines_num_out,
+                                 int32_t *raw_out) {
+    if (W % 32 || n < 2) return -1000;
+    const float theta = (float)(3.14159265358979323846 / 180.0);
+    for (int k = 0; k < MDB_HOUGH_ANGLES; k++) {
+        c_trig[2 * k] = (float)cos((double)k * (double)theta);
+        c_trig[2 * k + 1] = (float)sin((double)k * (double)theta);
+    }
+    const size_t HW = (size_t)W * H, groups = HW / 16;
+    const int Wb = W / 32, R = n, RA = n;  // max_batch = 1
+    const size_t FW = (size_t)H * Wb;
+    std::vector<uint8_t> ringbuf((size_t)R * HW, 0), dst(HW, 0), stage(HW, 0), Pm(HW, 0xEE), SUF((size_t)n * HW, 0xEE);
+    std::vector<uint16_t> S(HW, 0xEEEE);
+    std::vector<uint32_t> actbuf((size_t)RA * FW, 0), bits(33 * FW, 0), dstbits(FW, 0), alist(SPX_ACAP), wlist(SPX_WCAP), points(MDB_POINT_CAP),
+        okeys(HW), oidx(HW), bitmap((HW + 31) / 32, 0), walk(W + H + 2, 0);
+    std::vector<uint16_t> order(HOUGH_ORDER_CAP);
+    std::vector<int32_t> lines(512 * 4), accum((size_t)MDB_HOUGH_ANGLES * (2 * (W + H) + 1), 0);
+    unsigned acount = 0, wcount = 0, dense[2] = {0, 0}, npoints = 0;
+    ActRing ring; ring.base = actbuf.data(); ring.RA = RA; ring.Wb = Wb; ring.frame_words = FW;
+    SparseLists sl; sl.alist = alist.data(); sl.acount = &acount; sl.wlist = wlist.data(); sl.wcount = &wcount; sl.dense = dense;
+    DevState st;
+    memset(&st, 0, sizeof st);
+    st.ema_init_m = 1.0 - (double)nz_interval / 60.0;
+    st.ema_cur_m = st.ema_init_m;
+    st.ema_warm = (double)n;
+    static const int abs_sens[3] = {7, 5, 3};
+    st.bi_threshold = adaptive ? abs_sens[sensitivity] : init_value;
+    st.thr_float = (double)st.bi_threshold;
+    HoughParams P;
+    P.W = W; P.H = H; P.numrho = 2 * (W + H) + 1; P.threshold = hough_thr; P.min_len = hough_min_len; P.max_gap = hough_max_gap;
+    P.mask_area = mask_area; P.cap = MDB_POINT_CAP; P.max_lines = 512; P.walk_cap = W + H + 2; P.fixed_gap = -1;
+    const int rh = roi[2] - roi[0], rw = roi[3] - roi[1];
+    const long long std_interval = (long long)nz_interval * n;
+    const unsigned pgrid = (unsigned)((groups + PF_THREADS - 1) / PF_THREADS);
+    FrameSrc ringsrc; ringsrc.ring = ringbuf.data(); ringsrc.cur = nullptr; ringsrc.mask = nullptr; ringsrc.t0 = 0; ringsrc.R = R; ringsrc.HW = HW;
+    bool suffix_pending = false;
+    emu_launch(pgrid, PF_THREADS, [&] { pf_rebuild_kernel<false>(ringsrc, 0, n, S.data(), Pm.data(), SUF.data(), groups); });  // pf_timer = -1
+    for (long long t = 0; t < Ttot; t++) {
+        if (suffix_pending) {  // pf_launch_suffix: the block that ended with frame t-1
+            emu_launch(pgrid, PF_THREADS, [&] { pf_suffix_kernel<false>(ringsrc, t - 1, t - n + 1, n - 1, SUF.data(), groups); });
+            suffix_pending = false;
+        }
+        memcpy(stage.data(), frames + (size_t)t * HW, HW);
+        FrameSrc src = ringsrc; src.cur = stage.data(); src.t0 = t;
+        unsigned long long noise[2] = {0, 0};
+        const long long tau = t + 1;
+        SampleList sml; sml.count = 0;
+        if ((tau > 1 && tau <= n) || (tau > n && std_interval > 0 && tau % std_interval == 0)) sml.idx[sml.count++] = 0;
+        if (sml.count) {
+            const int gx = std::max(1, std::min((rh * rw + 255) / 256, 8));
+            emu_launch2(gx, 1, 256, [&] { noise_sample_kernel(src, W, n, t, std_interval, roi[0], roi[1], rh, rw, noise, 0, sml); });
+        }
+        int thr = 0; double thrf = 0, snr = 0;
+        emu_launch(1, 32, [&] { threshold_kernel(&st, noise, 1, t, n, std_interval, (long long)rh * rw, adaptive, sensitivity, &thr, &thrf, &snr); });
+        const int pos = (int)(t % n), L = (int)std::min<long long>(n, t + 1);
+        uint8_t *slot = ringbuf.data() + (size_t)(t % R) * HW;
+        const uint8_t *old = t >= n ? ringbuf.data() + (size_t)((t - n) % R) * HW : nullptr;
+        const uint8_t *suf = pos < n - 1 ? SUF.data() + (size_t)(pos + 1) * HW : nullptr;
+        const size_t gA = groups / 2;
+        for (int half = 0; half < 2; half++) {
+            const size_t g0 = half ? gA : 0, g1 = half ? groups : gA;
+            if (g1 == g0) continue;
+            emu_launch((unsigned)((g1 - g0 + PF_THREADS - 1) / PF_THREADS), PF_THREADS, [&] {
+                pf_update_kernel<false>(stage.data(), slot, old, nullptr, S.data(), Pm.data(), suf, pos == 0, L, &thr, g0, g1,
+                                        reinterpret_cast<uint16_t *>(bits.data()));
+            });
+        }
+        suffix_pending = pos == n - 1;
+        // ---- mdb_detect with bits_ready: spatial passes on the bits, PPHT ------------------------------------------------
+        npoints = 0; acount = 0;
+        const int rows_act = 8, strips = (Wb + SP_USE - 1) / SP_USE, bands = (H + rows_act - 1) / rows_act;
+        if (Wb % 4 == 0) {
+            const int chunks = Wb / 4;
+            emu_launch2((chunks * bands + A4_THREADS - 1) / A4_THREADS, 1, A4_THREADS, [&] { act4_kernel(bits.data(), H, Wb, rows_act, chunks, bands, ring, t, sl); });
+        } else {
+            const int bands64 = (H + 63) / 64;
+            emu_launch2((strips * bands64 + SP_WARPS - 1) / SP_WARPS, 1, SP_WARPS * 32, [&] { act_kernel(bits.data(), W, H, 1, 64, strips, bands64, ring, t, sl); });
+        }
+        dense[0] = 0;
+        emu_launch(1, 256, [&] { dst_sparse_kernel(ring, W, H, n, t, dy_on, dst.data(), dstbits.data(), &npoints, points.data(), MDB_POINT_CAP, sl); });
+        const int dst_rows = 32, dbands = (H + dst_rows - 1) / dst_rows;
+        if (dense[0])
+            emu_launch2((strips * dbands + SP_WARPS - 1) / SP_WARPS, 1, SP_WARPS * 32, [&] {
+                dst_dense_kernel(ring, W, H, n, t, dy_on, dst_rows, strips, dbands, dst.data(), dstbits.data(), &npoints, points.data(), MDB_POINT_CAP, sl);
+            });
+        unsigned queue[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int nlines = -99;
+        if (npoints == 0) nlines = 0;
+        else {
+            emu_launch(1, 32, [&] { ppht_order_kernel(1, HOUGH_ORDER_CAP, &npoints, order.data()); });
+            emu_launch(1, HOUGH_THREADS, [&] { hough_smem_kernel(P, 1, &npoints, points.data(), order.data(), lines.data(), &nlines, queue, nullptr, HOUGH_CAP_SMALL, HOUGH_TABLE_BYTES_SMALL, 0); });
+        }
+        if (nlines == -2) emu_launch(1, HOUGH_THREADS, [&] { hough_smem_kernel(P, 1, &npoints, points.data(), order.data(), lines.data(), &nlines, queue + 1, nullptr, HOUGH_CAP_LARGE, HOUGH_TABLE_BYTES, 1); });
+        if (nlines == -3) emu_launch(1, HOUGH_THREADS, [&] { hough_tier2_kernel(P, 1, &npoints, points.data(), accum.data(), lines.data(), &nlines, nullptr, queue + 7); });
+        if (nlines == -1) emu_launch(1, HOUGH_THREADS, [&] { hough_tier3_kernel(P, 1, dst.data(), okeys.data(), oidx.data(), accum.data(), bitmap.data(), walk.data(), lines.data(), &nlines, queue + 2, nullptr); });
+        if (nlines < 0) return -(int)(t + 1);
+        thr_out[t] = thr; snr_out[t] = snr; n_on_out[t] = (int)npoints; lines_num_out[t] = nlines;
+        memcpy(dst_out + (size_t)t * HW, dst.data(), HW);
+        memcpy(raw_out + (size_t)t * 512 * 4, lines.data(), (size_t)std::min(nlines, 512) * 16);
     }
     return 0;
 }

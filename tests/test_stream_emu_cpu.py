@@ -18,7 +18,7 @@ _SENS = {"low": 0, "normal": 1, "high": 2}
 @pytest.fixture(scope="module")
 def emu_lib(tmp_path_factory):
     so = build(tmp_path_factory.mktemp("stream_emu"), "stream_path_emu.cpp",
-               patched=["temporal3_kernel.cuh", "kernels_basic.cuh", "spatial_kernel.cuh", "hough.cuh"], shared=True)
+               patched=["temporal3_kernel.cuh", "kernels_basic.cuh", "spatial_kernel.cuh", "hough.cuh", "perframe_kernel.cuh"], shared=True)
     lib = C.CDLL(so)
     lib.emu_stream_path.restype = C.c_int
     return lib
@@ -105,3 +105,31 @@ def test_time_sharded_protocol_on_the_cpu(emu_lib, name, world, batch):
             assert nl[k] == g["lines_num"][t], (sh.rank, t)
             if nl[k] <= 500:
                 assert np.array_equal(raw[k, :nl[k]], ragged_get(g["raw_lines"], g["raw_offs"], t)), (sh.rank, t)
+
+
+@pytest.mark.parametrize("name,frames", [("synth_320x240_n5_dyoff", 1000), ("synth_384x216_n12_dyon_mask", 1000), ("clip_192x144_n25", 90)])
+def test_per_frame_resident_state_path_reproduces_the_reference_golden(emu_lib, name, frames):
+    """update(); detect() frame by frame on the O(1) path (pf_update() / mdb_detect() with bits_ready in csrc/metdet.cu):
+    staging copy, noise sample + threshold, pf_update_kernel in two halves, suffix rebuild at block ends, act / dst / PPHT on
+    the predicate bits it leaves behind -- against the golden trajectory of the live reference."""
+    g = load_det_case(name)
+    T = min(frames, len(g["frames"]))
+    fr = np.ascontiguousarray(g["frames"][:T])
+    H, W = fr.shape[1:]
+    c = g["cfg"]
+    roi = (C.c_int * 4)(*[int(v) for v in g["std_roi"]])
+    thr = np.zeros(T, np.int32); snr = np.zeros(T)
+    dst = np.zeros((T, H, W), np.uint8); n_on = np.zeros(T, np.int32); nl = np.zeros(T, np.int32)
+    raw = np.zeros((T, 512, 4), np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = emu_lib.emu_perframe_path(p(fr), T, W, H, int(g["n"]), int(c["adaptive"]), int(c["init_value"]), _SENS[c["sensitivity"]],
+                                   int(c["interval"]), roi, *[int(v) for v in c["hough"]], int(c["dy_mask"]),
+                                   C.c_double(float(g["mask_area"])), p(thr), p(snr), p(dst), p(n_on), p(nl), p(raw))
+    assert rc == 0, rc
+    assert np.array_equal(thr, g["bi_threshold"][:T])
+    assert np.allclose(snr, g["snr"][:T], rtol=1e-12, atol=0)
+    for t in range(T):
+        assert np.array_equal(dst[t], g["dst"][t]), (t, int(np.count_nonzero(dst[t] != g["dst"][t])))
+        assert nl[t] == g["lines_num"][t], t
+        if nl[t] <= 500:
+            assert np.array_equal(raw[t, :nl[t]], ragged_get(g["raw_lines"], g["raw_offs"], t)), t
