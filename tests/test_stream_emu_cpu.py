@@ -107,7 +107,7 @@ def test_time_sharded_protocol_on_the_cpu(emu_lib, name, world, batch):
                 assert np.array_equal(raw[k, :nl[k]], ragged_get(g["raw_lines"], g["raw_offs"], t)), (sh.rank, t)
 
 
-@pytest.mark.parametrize("name,frames", [("synth_320x240_n5_dyoff", 1000), ("synth_384x216_n12_dyon_mask", 1000), ("clip_192x144_n25", 90)])
+@pytest.mark.parametrize("name,frames", [("synth_320x240_n5_dyoff", 1000), ("synth_384x216_n12_dyon_mask", 1000), ("clip_192x144_n25", 56)])
 def test_per_frame_resident_state_path_reproduces_the_reference_golden(emu_lib, name, frames):
     """update(); detect() frame by frame on the O(1) path (pf_update() / mdb_detect() with bits_ready in csrc/metdet.cu):
     staging copy, noise sample + threshold, pf_update_kernel in two halves, suffix rebuild at block ends, act / dst / PPHT on
