@@ -1,10 +1,12 @@
 // A small CUDA thread-block emulator for CPU tests (test infrastructure, not product code).
 //
-// A kernel's source is compiled for the host and one thread block at a time is run by `blockDim.x` OS threads:
-//   * threadIdx / blockIdx are thread-local, blockDim / gridDim global;
-//   * __syncthreads() is a std::barrier over the block, __syncwarp() and the warp collectives (__ballot_sync,
-//     __shfl_*_sync, __reduce_*_sync, __any/__all_sync) a barrier + exchange slots over the 32 threads of a warp
-//     (full-mask use only: every lane of the warp has to make the call, as CUDA requires for mask 0xffffffff);
+// A kernel's source is compiled for the host and one thread block at a time is run by `blockDim.x` cooperative fibers
+// (own stacks, a register-only context switch on x86-64, ucontext elsewhere) on ONE OS thread:
+//   * threadIdx is restored whenever a fiber resumes; blockIdx / blockDim / gridDim are globals;
+//   * __syncthreads() is a generation barrier over the block (a waiting fiber yields to the next one), __syncwarp() and
+//     the warp collectives (__ballot_sync, __shfl_*_sync, __reduce_*_sync, __any/__all_sync) a barrier + exchange slots
+//     over the 32 fibers of a warp (full-mask use only: every lane of the warp has to make the call, as CUDA requires for
+//     mask 0xffffffff).  Kernels whose threads spin on each other WITHOUT a barrier would not make progress here;
 //   * `__shared__` variables become function-local statics (one block runs at a time), dynamic shared memory is the
 //     global array the including file defines under the kernel's `extern __shared__` name (the test's build step
 //     rewrites `extern __shared__` to `extern`);
@@ -13,19 +15,21 @@
 // Blocks run one after the other, which is a legal CUDA schedule for kernels whose blocks do not wait for each other.
 #pragma once
 #include <atomic>
-#include <barrier>
 #include <cmath>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <functional>
 #include <memory>
-#include <thread>
 #include <vector>
+#if !defined(__x86_64__)
+#include <ucontext.h>
+#endif
 #include <algorithm>
 #include <cuda_runtime.h>
 
 struct EmuDim { unsigned x = 1, y = 1, z = 1; };
-static thread_local EmuDim emu_threadIdx, emu_blockIdx;
+static EmuDim emu_threadIdx, emu_blockIdx;
 static EmuDim emu_blockDim, emu_gridDim;
 #define threadIdx emu_threadIdx
 #define blockIdx emu_blockIdx
@@ -38,17 +42,80 @@ static EmuDim emu_blockDim, emu_gridDim;
 #undef __constant__
 #define __constant__
 
+// ---- fibers ------------------------------------------------------------------------------------------------------------
+struct EmuBar { unsigned count = 0, expected = 0; unsigned long long gen = 0; };
 struct EmuWarp {
-    std::barrier<> bar;
+    EmuBar bar;
     unsigned long long slot[32];
-    EmuWarp() : bar(32) {}
 };
-static std::barrier<> *emu_block_bar = nullptr;
-static thread_local EmuWarp *emu_warp = nullptr;
-static thread_local int emu_lane = 0;
+struct EmuFiber {
+    void *sp = nullptr;  // saved stack pointer (x86-64) while the fiber is not running
+#if !defined(__x86_64__)
+    ucontext_t uc;
+#endif
+    unsigned tid = 0;
+    EmuWarp *warp = nullptr;
+    bool done = false;
+    char *stack = nullptr;
+};
+static const size_t EMU_STACK_BYTES = 512 * 1024;
+static EmuFiber *emu_current = nullptr;
+static EmuBar emu_block_bar;
+static EmuWarp *emu_warp = nullptr;
+static int emu_lane = 0;
+static std::function<void()> *emu_body = nullptr;
 
-static inline void __syncthreads() { emu_block_bar->arrive_and_wait(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp->bar.arrive_and_wait(); }
+#if defined(__x86_64__)
+// void emu_ctx_switch(void **save_sp, void *load_sp): callee-saved registers on the own stack, swap the stack pointers
+extern "C" void emu_ctx_switch(void **save_sp, void *load_sp);
+asm(".text\n"
+    ".p2align 4\n"
+    ".globl emu_ctx_switch\n"
+    ".type emu_ctx_switch,@function\n"
+    "emu_ctx_switch:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+    "  movq %rsp, (%rdi)\n"
+    "  movq %rsi, %rsp\n"
+    "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n"
+    "  ret\n"
+    ".size emu_ctx_switch,.-emu_ctx_switch\n");
+static void *emu_main_sp = nullptr;
+#else
+static ucontext_t emu_main_uc;
+#endif
+
+static inline void emu_yield() {  // back to the scheduler; returns when this fiber is resumed
+    EmuFiber *self = emu_current;
+#if defined(__x86_64__)
+    emu_ctx_switch(&self->sp, emu_main_sp);
+#else
+    swapcontext(&self->uc, &emu_main_uc);
+#endif
+    emu_threadIdx.x = self->tid;
+    emu_warp = self->warp;
+    emu_lane = (int)(self->tid & 31);
+}
+static inline void emu_bar_wait(EmuBar &b) {
+    const unsigned long long gen = b.gen;
+    if (++b.count == b.expected) {
+        b.count = 0;
+        b.gen++;
+        return;
+    }
+    while (b.gen == gen) emu_yield();
+}
+static void emu_fiber_entry() {
+    EmuFiber *self = emu_current;
+    emu_threadIdx.x = self->tid;
+    emu_warp = self->warp;
+    emu_lane = (int)(self->tid & 31);
+    (*emu_body)();
+    self->done = true;
+    for (;;) emu_yield();  // never resumed again
+}
+
+static inline void __syncthreads() { emu_bar_wait(emu_block_bar); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu_bar_wait(emu_warp->bar); }
 static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline long long clock64() { return 0; }
 
@@ -56,9 +123,9 @@ static inline long long clock64() { return 0; }
 template <typename F>
 static inline auto emu_warp_collective(unsigned long long mine, F f) {
     emu_warp->slot[emu_lane] = mine;
-    emu_warp->bar.arrive_and_wait();
+    emu_bar_wait(emu_warp->bar);
     auto r = f(emu_warp->slot);
-    emu_warp->bar.arrive_and_wait();
+    emu_bar_wait(emu_warp->bar);
     return r;
 }
 static inline unsigned __ballot_sync(unsigned, int pred) {
@@ -183,37 +250,82 @@ static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; 
 using std::max;
 using std::min;
 
-// run grid_x * grid_y blocks of `block` threads (a multiple of 32), one block after the other: the `block` OS threads are
-// started once per launch and walk through the blocks together (a block barrier between two blocks keeps the function-local
+// run grid_x * grid_y * grid_z blocks of `block` threads (a multiple of 32), one block after the other: the `block` fibers are
+// created once per launch and walk through the blocks together (a block barrier between two blocks keeps the function-local
 // "shared memory" statics of one block from being touched by the next)
+static std::vector<char *> &emu_stacks() {
+    static std::vector<char *> v;
+    return v;
+}
 template <typename F>
 static void emu_launch3(unsigned grid_x, unsigned grid_y, unsigned grid_z, unsigned block, F kernel_call) {
     emu_gridDim.x = grid_x;
     emu_gridDim.y = grid_y;
     emu_gridDim.z = grid_z;
     emu_blockDim.x = block;
-    std::barrier<> bar(block);
-    emu_block_bar = &bar;
+    emu_block_bar = EmuBar();
+    emu_block_bar.expected = block;
     std::vector<std::unique_ptr<EmuWarp>> warps;
-    for (unsigned w = 0; w < (block + 31) / 32; w++) warps.emplace_back(new EmuWarp());
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < block; t++)
-        th.emplace_back([&, t] {
-            emu_threadIdx.x = t;
-            emu_warp = warps[t / 32].get();
-            emu_lane = (int)(t % 32);
-            for (unsigned bz = 0; bz < grid_z; bz++)
-                for (unsigned by = 0; by < grid_y; by++)
-                    for (unsigned b = 0; b < grid_x; b++) {
-                        emu_blockIdx.x = b;
-                        emu_blockIdx.y = by;
-                        emu_blockIdx.z = bz;
-                        kernel_call();
-                        bar.arrive_and_wait();
-                    }
-        });
-    for (auto &x : th) x.join();
-    emu_block_bar = nullptr;
+    for (unsigned w = 0; w < (block + 31) / 32; w++) {
+        warps.emplace_back(new EmuWarp());
+        warps.back()->bar.expected = std::min(32u, block - 32 * w);
+    }
+    std::function<void()> body = [&] {
+        for (unsigned bz = 0; bz < grid_z; bz++)
+            for (unsigned by = 0; by < grid_y; by++)
+                for (unsigned b = 0; b < grid_x; b++) {
+                    // every fiber writes the same values; they all sit between the same two block barriers
+                    emu_blockIdx.x = b;
+                    emu_blockIdx.y = by;
+                    emu_blockIdx.z = bz;
+                    kernel_call();
+                    emu_bar_wait(emu_block_bar);
+                }
+    };
+    // blockIdx is a global: fibers leave the end-of-block barrier one after the other and the first one out moves blockIdx
+    // on while the others still sit in the barrier loop -- they are past kernel_call, and each fiber rewrites the indices
+    // before its own next kernel_call; between two end-of-block barriers all fibers are in the same block.
+    emu_body = &body;
+    std::vector<EmuFiber> fibers(block);
+    auto &stacks = emu_stacks();
+    while (stacks.size() < block) stacks.push_back((char *)aligned_alloc(64, EMU_STACK_BYTES));
+    for (unsigned t = 0; t < block; t++) {
+        EmuFiber &f = fibers[t];
+        f.tid = t;
+        f.warp = warps[t / 32].get();
+        f.stack = stacks[t];
+#if defined(__x86_64__)
+        // initial frame: six callee-saved registers, the entry point as return address, a null return address above it
+        uintptr_t top = ((uintptr_t)f.stack + EMU_STACK_BYTES) & ~(uintptr_t)15;
+        void **sp = (void **)(top - 64);
+        for (int k = 0; k < 6; k++) sp[k] = nullptr;
+        sp[6] = (void *)&emu_fiber_entry;
+        sp[7] = nullptr;
+        f.sp = sp;
+#else
+        getcontext(&f.uc);
+        f.uc.uc_stack.ss_sp = f.stack;
+        f.uc.uc_stack.ss_size = EMU_STACK_BYTES;
+        f.uc.uc_link = nullptr;
+        makecontext(&f.uc, emu_fiber_entry, 0);
+#endif
+    }
+    unsigned alive = block;
+    while (alive) {
+        for (unsigned t = 0; t < block; t++) {
+            EmuFiber &f = fibers[t];
+            if (f.done) continue;
+            emu_current = &f;
+#if defined(__x86_64__)
+            emu_ctx_switch(&emu_main_sp, f.sp);
+#else
+            swapcontext(&emu_main_uc, &f.uc);
+#endif
+            if (f.done) alive--;
+        }
+    }
+    emu_current = nullptr;
+    emu_body = nullptr;
 }
 template <typename F>
 static void emu_launch2(unsigned grid_x, unsigned grid_y, unsigned block, F kernel_call) { emu_launch3(grid_x, grid_y, 1, block, kernel_call); }

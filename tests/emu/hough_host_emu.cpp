@@ -1,5 +1,5 @@
 // The exact-order PPHT kernels (csrc/hough.cuh: ppht_order_kernel, hough_smem_kernel tiers 1a / 1b, hough_tier2_kernel)
-// run on the CPU by the block emulator (cuda_block_emu.h: one OS thread per CUDA thread, barriers and warp collectives
+// run on the CPU by the block emulator (cuda_block_emu.h: one fiber per CUDA thread, barriers and warp collectives
 // emulated) against oracle/ppht.c -- the restatement of cv2.HoughLinesP that is pinned on cv2 itself.  The kernel source
 // is the product's, with two mechanical edits made by the test's build step (tests/test_hough_emu_cpu.py):
 // `extern __shared__` -> `extern` and the PTX prefetch hints removed.  Test infrastructure.

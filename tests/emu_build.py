@@ -48,7 +48,7 @@ def build(tmp, harness, patched=(), extra_c=(), std="c++20", opt="-O1", shared=F
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-c", os.path.join(REPO, c), "-o", o])
         objs.append(o)
     exe = os.path.join(tmp, os.path.splitext(os.path.basename(harness))[0] + (".so" if shared else ""))
-    subprocess.check_call(["g++", opt, f"-std={std}", "-ffp-contract=off", "-pthread"] + (["-shared", "-fPIC"] if shared else []) + ["-I", tmp, "-I", os.path.join(REPO, "tests", "emu"),
+    subprocess.check_call(["g++", opt, f"-std={std}", "-ffp-contract=off"] + (["-shared", "-fPIC"] if shared else []) + ["-I", tmp, "-I", os.path.join(REPO, "tests", "emu"),
                            "-I", os.path.join(REPO, "include"), "-I", inc, os.path.join(REPO, "tests", "emu", harness)] + objs +
                           ["-o", exe])
     return exe

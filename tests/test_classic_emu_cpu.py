@@ -24,15 +24,12 @@ def emu_lib(tmp_path_factory):
     return lib
 
 
-@pytest.mark.parametrize("name,batch,frames", [("synth_320x240", 5, 1000), ("odd_203x157_mask", 16, 12), ("dense_256x160_fixed", 4, 8)])
+@pytest.mark.parametrize("name,batch,frames", [("synth_320x240", 5, 1000), ("odd_203x157_mask", 16, 1000), ("dense_256x160_fixed", 4, 1000)])
 def test_classic_detector_kernels_reproduce_the_reference_golden(emu_lib, name, batch, frames):
     from metdetpy_b200.detector import select_subarea
     g = np.load(os.path.join(GOLDEN, f"classic_{name}.npz"))
     fr = np.ascontiguousarray(g["frames"][:frames])
     T, H, W = fr.shape
-    if "dense" in name:
-        if not os.environ.get("EMU_SLOW"):
-            pytest.skip("dense masks take minutes under the emulator: set EMU_SLOW=1")
     want_dst = np.unpackbits(g["dst_bits"][:T], axis=1)[:, :H * W].reshape(T, H, W) * np.uint8(255)
     adaptive, init_value, area, interval = g["cfg"]
     mask = np.ascontiguousarray(g["mask"], np.uint8)

@@ -22,7 +22,7 @@ def emu_lib(tmp_path_factory):
     return lib
 
 
-@pytest.mark.parametrize("name,frames", [("synth_203x157_n3_high", 16), ("synth_300x200_n7_low", 20), ("clip_192x144_n25", 84)])
+@pytest.mark.parametrize("name,frames", [("synth_203x157_n3_high", 1000), ("synth_300x200_n7_low", 1000), ("clip_192x144_n25", 1000)])
 def test_generic_path_kernels_reproduce_the_reference_golden(emu_lib, name, frames):
     g = load_det_case(name)
     T = min(frames, len(g["frames"]))

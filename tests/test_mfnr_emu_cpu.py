@@ -48,10 +48,7 @@ def test_whole_mfnr_mix_with_emulated_kernels_against_reference_golden(mfnr_path
     from oracle import mfnr_oracle as MO
     lib = mfnr_path_lib
     g = np.load(os.path.join(REPO, "tests", "golden", "mfnr.npz"))
-    # the reductions launch 1024 blocks of 256 emulated threads each: one clip per algorithm unless EMU_SLOW=1 (13 frames: plain
-    # median; 50 frames: med-of-med really runs in blocks)
-    names = list(g["names"]) if os.environ.get("EMU_SLOW") else [{"mean": "clip24", "sigma-clipping": "clip24", "median": "clip13", "med-of-med": "clip50"}[algo]]
-    for name in names:
+    for name in g["names"]:  # 13 frames: plain median; 50 frames: med-of-med really runs in blocks
         frames = np.ascontiguousarray(g[f"{name}_frames"])
         N, H, W, Ch = frames.shape
         out = np.zeros((H, W, Ch), np.uint8)

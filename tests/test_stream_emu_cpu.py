@@ -25,11 +25,9 @@ def emu_lib(tmp_path_factory):
 
 
 @pytest.mark.parametrize("name,frames,batch", [("synth_320x240_n5_dyoff", 1000, 8), ("synth_384x216_n12_dyon_mask", 1000, 7),
-                                               ("clip_192x144_n25", 1000, 16), ("synth_256x160_n6_fixed3_dense", 12, 5)])
+                                               ("clip_192x144_n25", 1000, 16), ("synth_256x160_n6_fixed3_dense", 1000, 5),
+                                               ("clip_cfg1_480x270_n6", 1000, 16), ("clip_cfg1_960x540_n6_range", 1000, 22)])
 def test_streaming_path_kernels_reproduce_the_reference_golden(emu_lib, name, frames, batch):
-    if "dense" in name and not os.environ.get("EMU_SLOW"):
-        pytest.skip("dense masks (tiers 2 / 3, > 500 segments per frame) take minutes under the emulator: set EMU_SLOW=1 "
-                    "(last run: passed in 337 s)")
     g = load_det_case(name)
     T = min(frames, len(g["frames"]))
     fr = np.ascontiguousarray(g["frames"][:T])
@@ -107,7 +105,8 @@ def test_time_sharded_protocol_on_the_cpu(emu_lib, name, world, batch):
                 assert np.array_equal(raw[k, :nl[k]], ragged_get(g["raw_lines"], g["raw_offs"], t)), (sh.rank, t)
 
 
-@pytest.mark.parametrize("name,frames", [("synth_320x240_n5_dyoff", 1000), ("synth_384x216_n12_dyon_mask", 1000), ("clip_192x144_n25", 56)])
+@pytest.mark.parametrize("name,frames", [("synth_320x240_n5_dyoff", 1000), ("synth_384x216_n12_dyon_mask", 1000), ("clip_192x144_n25", 1000),
+                                         ("synth_256x160_n6_fixed3_dense", 1000), ("clip_cfg1_480x270_n6", 1000)])
 def test_per_frame_resident_state_path_reproduces_the_reference_golden(emu_lib, name, frames):
     """update(); detect() frame by frame on the O(1) path (pf_update() / mdb_detect() with bits_ready in csrc/metdet.cu):
     staging copy, noise sample + threshold, pf_update_kernel in two halves, suffix rebuild at block ends, act / dst / PPHT on
