@@ -310,9 +310,22 @@ static void emu_launch3(unsigned grid_x, unsigned grid_y, unsigned grid_z, unsig
         makecontext(&f.uc, emu_fiber_entry, 0);
 #endif
     }
+    // EMU_SCHEDULE: 0 / unset = fibers resumed in ascending thread order, 1 = descending, >= 2 = a fresh pseudo-random
+    // permutation every round (seed = the value).  Any order is a legal CUDA schedule: a kernel whose result depends on it
+    // is missing a barrier (or an atomic).
+    static const long emu_schedule = getenv("EMU_SCHEDULE") ? atol(getenv("EMU_SCHEDULE")) : 0;
+    static unsigned long long emu_sched_rng = 0x9E3779B97F4A7C15ull ^ (unsigned long long)emu_schedule;
+    std::vector<unsigned> order(block);
+    for (unsigned t = 0; t < block; t++) order[t] = emu_schedule == 1 ? block - 1 - t : t;
     unsigned alive = block;
     while (alive) {
-        for (unsigned t = 0; t < block; t++) {
+        if (emu_schedule >= 2)
+            for (unsigned t = block - 1; t > 0; t--) {
+                emu_sched_rng = emu_sched_rng * 6364136223846793005ull + 1442695040888963407ull;
+                std::swap(order[t], order[(unsigned)((emu_sched_rng >> 33) % (t + 1))]);
+            }
+        for (unsigned k = 0; k < block; k++) {
+            const unsigned t = order[k];
             EmuFiber &f = fibers[t];
             if (f.done) continue;
             emu_current = &f;
