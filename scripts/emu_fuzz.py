@@ -1,0 +1,155 @@
+"""Randomised parity runs WITHOUT a GPU: the product's kernels under the CPU block emulator (tests/emu/stream_path_emu.cpp:
+the batched streaming path and the per-frame resident-state path) against the CPU checker (oracle/m3_oracle.py, cv2 backend =
+the reference's own call sites) on random small configurations -- frame sizes, every window that has a temporal3 shape, batch
+lengths that cut the van Herk blocks anywhere, adaptive / fixed thresholds, dynamic mask on / off, Hough parameters, masks,
+bright flashes and stuck hot regions.  Test tooling (tests/test_emu_fuzz_cpu.py runs a few seeds; `python scripts/emu_fuzz.py
+FIRST COUNT` runs more)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+T3_WINDOWS = [2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16, 18, 20, 21, 24, 25, 28, 30, 32, 36, 40, 48, 50, 60, 64]
+_SENS = ["low", "normal", "high"]
+
+
+def build_lib(tmp):
+    from emu_build import build
+    so = build(tmp, "stream_path_emu.cpp",
+               patched=["temporal3_kernel.cuh", "kernels_basic.cuh", "spatial_kernel.cuh", "hough.cuh", "perframe_kernel.cuh"], shared=True)
+    lib = C.CDLL(so)
+    lib.emu_stream_path.restype = C.c_int
+    lib.emu_perframe_path.restype = C.c_int
+    return lib
+
+
+def build_generic_lib(tmp):
+    from emu_build import build
+    lib = C.CDLL(build(tmp, "generic_path_emu.cpp", patched=["kernels_basic.cuh", "hough.cuh"], shared=True))
+    lib.emu_generic_path.restype = C.c_int
+    return lib
+
+
+def make_case(seed, any_width=False):
+    import cv2
+    r = np.random.default_rng(seed)
+    W = int(r.integers(17, 260)) if any_width else 32 * int(r.integers(1, 9))
+    H = int(r.choice([8, 9, 15, 16, 17, 31, 33, 40, 63, 64, 65, 90]))
+    n = int(r.choice(T3_WINDOWS)) if r.random() < 0.8 else int(r.integers(2, 65))  # windows without a shape are skipped by the caller
+    if any_width and r.random() < 0.15:
+        n = int(r.choice([1, 70, 129, 140]))  # the generic kernels take any window
+    T = int(min(110, r.integers(max(2, n // 2), 2 * n + 24)))
+    batch = int(r.integers(1, T + 1)) if r.random() < 0.7 else int(r.integers(1, 9))
+    cfg = dict(adaptive=bool(r.random() < 0.6), init_value=int(r.integers(3, 13)), sensitivity=_SENS[int(r.integers(0, 3))],
+               area=float(r.choice([0.1, 0.2, 0.4])), interval=int(r.integers(1, 4)),
+               hough=(int(r.integers(4, 16)), int(r.integers(3, 16)), int(r.integers(0, 11))), dy_mask=bool(r.random() < 0.6))
+    mask = np.ones((H, W), np.uint8)
+    if r.random() < 0.5:  # a polygon cut out of a corner, like a horizon mask
+        pts = np.array([[0, H], [0, int(H * r.uniform(0.5, 0.95))], [int(W * r.uniform(0.3, 1.0)), H]], np.int32)
+        cv2.fillPoly(mask, [pts], 0)
+    sigma = float(r.uniform(0.8, 3.5))
+    sky = r.uniform(10, 60) + r.normal(0, 3, (H, W))
+    frames = np.empty((T, H, W), np.uint8)
+    ang, x0, y0 = r.uniform(0, 2 * np.pi), r.uniform(0.1, 0.9) * W, r.uniform(0.1, 0.9) * H
+    speed, bright, thick = r.uniform(1.0, 6.0), r.uniform(25, 120), int(r.integers(1, 4))
+    start = int(r.integers(0, max(1, T - 3)))
+    hot = (int(r.integers(0, H - 3)), int(r.integers(0, W - 6))) if r.random() < 0.4 else None
+    flash = int(r.integers(0, T)) if r.random() < 0.3 else -1
+    for t in range(T):
+        f = sky + r.normal(0, sigma, (H, W))
+        if t >= start:
+            k = t - start
+            p1 = (int(x0 + speed * k * np.cos(ang)), int(y0 + speed * k * np.sin(ang)))
+            p2 = (int(x0 + speed * (k + 2) * np.cos(ang)), int(y0 + speed * (k + 2) * np.sin(ang)))
+            m = np.zeros((H, W), np.float32)
+            cv2.line(m, p1, p2, float(bright), thick, cv2.LINE_AA)
+            f = f + m
+        if hot is not None and t % 3 != 2:  # a flickering hot region: what the dynamic mask is for
+            f[hot[0]:hot[0] + 3, hot[1]:hot[1] + 6] += 90
+        if t == flash:
+            f = f + r.uniform(20, 80)
+        frames[t] = np.clip(np.rint(f), 0, 255).astype(np.uint8)
+    raw_frames = frames.copy()
+    frames *= mask  # what the loader hands to the detector (MetLib/imgproc.py:96-101)
+    return dict(W=W, H=H, n=n, T=T, batch=batch, cfg=cfg, mask=mask, frames=frames, raw_frames=raw_frames,
+                apply_mask=bool(r.random() < 0.5))
+
+
+def run_case(lib, case, per_frame=False, generic=False):
+    """None if equal, else a description of the first difference.  generic: `lib` is build_generic_lib()'s -- the per-frame
+    generic kernels (any width, any window), optionally with the mask applied inside the device loads."""
+    from metdetpy_b200.detector import select_subarea
+    from oracle import m3_oracle as O
+    W, H, n, T, cfg, mask, fr = (case[k] for k in ("W", "H", "n", "T", "cfg", "mask", "frames"))
+    fps = 25.0
+    roi_t = select_subarea(mask, cfg["area"])
+    roi = (C.c_int * 4)(*[int(v) for v in roi_t])
+    thr = np.zeros(T, np.int32); snr = np.zeros(T)
+    dst = np.zeros((T, H, W), np.uint8); n_on = np.zeros(T, np.int32); nl = np.zeros(T, np.int32)
+    raw = np.zeros((T, 512, 4), np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    common = (int(cfg["adaptive"]), int(cfg["init_value"]), _SENS.index(cfg["sensitivity"]), int(cfg["interval"]), roi,
+              *[int(v) for v in cfg["hough"]], int(cfg["dy_mask"]), C.c_double(float(np.sum(mask))),
+              p(thr), p(snr), p(dst), p(n_on), p(nl), p(raw))
+    dev_mask = bool(case["apply_mask"]) and not generic and hasattr(lib, "emu_set_device_mask")
+    if dev_mask:  # apply_mask = 1: unmasked frames in, the mask is applied inside the kernels' loads
+        fr = case["raw_frames"]
+        lib.emu_set_device_mask(p(mask))
+    if generic:
+        thrf = np.zeros(T)
+        src = case["raw_frames"] if case["apply_mask"] else fr
+        rc = lib.emu_generic_path(p(src), T, W, H, n, p(mask), int(case["apply_mask"]), *common[:-6], p(thr), p(thrf), *common[-5:])
+    elif per_frame:
+        rc = lib.emu_perframe_path(p(fr), T, W, H, n, *common)
+    else:
+        rc = lib.emu_stream_path(p(fr), T, W, H, n, case["batch"], *common)
+    if dev_mask:
+        lib.emu_set_device_mask(None)
+        fr = case["frames"]
+    if rc in (-1000, -1001):  # width not a multiple of 32 / window without a temporal3 shape (temporal2 on the device)
+        return "skipped"
+    if rc != 0:
+        return f"emulated path failed: rc={rc}"
+    ref = O.M3DetectorOracle(n / fps + 1e-9, fps, mask, 10, adaptive=cfg["adaptive"], init_value=cfg["init_value"],
+                             sensitivity=cfg["sensitivity"], area=cfg["area"], interval=cfg["interval"], hough=cfg["hough"],
+                             dy_mask=cfg["dy_mask"], backend="cv2")
+    assert ref.stack_maxsize == n and tuple(ref.stack.std_roi) == tuple(roi_t)
+    for t in range(T):
+        ref.update(fr[t]); ref.detect()
+        if ref.bi_threshold != thr[t]:
+            return f"frame {t}: threshold {thr[t]} != {ref.bi_threshold}"
+        if not np.isclose(snr[t], ref.stack.snr, rtol=1e-12, atol=0):
+            return f"frame {t}: snr {snr[t]!r} != {ref.stack.snr!r}"
+        if not np.array_equal(dst[t], ref.dst):
+            return f"frame {t}: mask differs in {int(np.count_nonzero(dst[t] != ref.dst))} pixels"
+        if nl[t] != ref.lines_num:
+            return f"frame {t}: {nl[t]} raw segments != {ref.lines_num}"
+        if 0 < nl[t] <= 500 and not np.array_equal(raw[t, :nl[t]], np.asarray(ref.linesp_ext).reshape(-1, 4)):
+            return f"frame {t}: raw segments differ"
+    return None
+
+
+def main():
+    import tempfile
+    first, count = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (0, 50)
+    lib, glib = build_lib(tempfile.mkdtemp()), build_generic_lib(tempfile.mkdtemp())
+    bad = 0
+    for seed in range(first, first + count):
+        case = make_case(seed)
+        res = [run_case(lib, case, pf) for pf in (False, True)]
+        gcase = make_case(seed, any_width=True)
+        res.append(run_case(glib, gcase, generic=True))
+        tag = {k: case[k] for k in ("W", "H", "n", "T", "batch")}
+        print(seed, tag, case["cfg"], "generic", {k: gcase[k] for k in ("W", "H", "n", "T", "apply_mask")}, res, flush=True)
+        bad += any(x not in (None, "skipped") for x in res)
+    print("FAILED" if bad else "ALL OK", bad)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -18,6 +18,31 @@ uint16_t o_sm[8192];
 #include "hough_emu.cuh"
 #include "perframe_kernel_emu.cuh"
 
+// apply_mask = 1 of the product: frames arrive unmasked, every kernel that loads a frame applies this mask (FrameSrc::mask);
+// set by emu_set_device_mask() for the following calls, nullptr = frames are already masked (or there is no mask)
+static const uint8_t *g_dev_mask = nullptr;
+extern "C" void emu_set_device_mask(const uint8_t *mask) { g_dev_mask = mask; }
+
+static int g_noise16_launches = 0;
+extern "C" int emu_noise16_launches() { return g_noise16_launches; }  // how often the 16-byte-load variant was the one selected
+// launch_noise_samples (csrc/kernels_basic.cuh) with the launches replaced by emulated ones: same kernel selection, same grids
+static void emu_noise_samples(const FrameSrc &src, int W, int n, long long timer0, long long std_interval, const int *roi,
+                              unsigned long long *acc, long long min_tau, const SampleList &sl, int T) {
+    const int rh = roi[2] - roi[0], rw = roi[3] - roi[1];
+    const int rows = sl.count < 0 ? T : sl.count;
+    const bool mask_ok = !src.mask || ((uintptr_t)src.mask & 15) == 0;
+    const bool base_ok = ((uintptr_t)src.ring & 15) == 0 && ((uintptr_t)src.cur & 15) == 0 && (src.HW & 15) == 0;
+    if (W % 16 == 0 && n <= 128 && mask_ok && base_ok) {
+        const int groups = rh * ((((roi[1] + rw + 15) & ~15) - (roi[1] & ~15)) >> 4);
+        const int gx = std::max(1, std::min((groups + 255) / 256, 1184));
+        g_noise16_launches++;
+        emu_launch2(gx, rows, 256, [&] { noise_sample16_kernel(src, W, n, timer0, std_interval, roi[0], roi[1], rh, rw, acc, min_tau, sl); });
+    } else {
+        const int gx = std::max(1, std::min((rh * rw + 255) / 256, 592));
+        emu_launch2(gx, rows, 256, [&] { noise_sample_kernel(src, W, n, timer0, std_interval, roi[0], roi[1], rh, rw, acc, min_tau, sl); });
+    }
+}
+
 template <int U, int BL, int P, int K>
 static void temporal3_batch(const FrameSrc &src, long long t0, int T, int HWG, const int *thr, uint8_t *bits) {
     typedef t3::Layout<U, BL, P, 0, K> LY;
@@ -29,7 +54,8 @@ static void temporal3_batch(const FrameSrc &src, long long t0, int T, int HWG, c
         for (int tid = 0; tid < T3_NT; tid++) {
             const int g = c * T3_NT + tid;
             if (g >= HWG) break;
-            t3::thread_main<U, BL, P, K, false, 0>(src, t0, T, g, tid, smem.data(), bits, (size_t)HWG, nullptr, T3_NT);
+            if (src.mask) t3::thread_main<U, BL, P, K, true, 0>(src, t0, T, g, tid, smem.data(), bits, (size_t)HWG, nullptr, T3_NT);
+            else t3::thread_main<U, BL, P, K, false, 0>(src, t0, T, g, tid, smem.data(), bits, (size_t)HWG, nullptr, T3_NT);
         }
     }
 }
@@ -79,7 +105,7 @@ static int run_range(const uint8_t *frames, int Ttot, long long t_first, int hal
         const bool is_halo = t0 < t_first + halo;
         const int T = (int)std::min<long long>(B, (is_halo ? t_first + halo : t_end) - t0);
         const uint8_t *bframes = frames + (size_t)(t0 - t_first) * HW;
-        FrameSrc src; src.ring = ringbuf.data(); src.cur = bframes; src.mask = nullptr; src.t0 = t0; src.R = R; src.HW = HW;
+        FrameSrc src; src.ring = ringbuf.data(); src.cur = bframes; src.mask = g_dev_mask; src.t0 = t0; src.R = R; src.HW = HW;
         // ---- launch_noise_thr (or the caller's thresholds) --------------------------------------------------------------
         if (thr_in) {
             for (int i = 0; i < T; i++) { thr[i] = thr_in[t0 - t_first + i]; snr[i] = 0.0; }
@@ -92,21 +118,16 @@ static int run_range(const uint8_t *frames, int Ttot, long long t_first, int hal
                 if (sml.count < 63) sml.idx[sml.count++] = i; else sml.count = -1;
             }
         }
-        if (sml.count != 0) {
-            const int rows = sml.count < 0 ? T : sml.count, gx = std::max(1, std::min((rh * rw + 255) / 256, 8));
-            emu_launch2(gx, rows, 256, [&] { noise_sample_kernel(src, W, n, t0, std_interval, roi[0], roi[1], rh, rw, noise.data(), 0, sml); });
-        }
+        if (sml.count != 0) emu_noise_samples(src, W, n, t0, std_interval, roi, noise.data(), 0, sml, T);
         emu_launch(1, 32, [&] { threshold_kernel(&st, noise.data(), T, t0, n, std_interval, (long long)rh * rw, adaptive, sensitivity, thr.data(), thrf.data(), snr.data()); });
         }
         // ---- temporal pass (shape table of temporal3_dispatch.cuh) -------------------------------------------------------
         uint8_t *bits8 = reinterpret_cast<uint8_t *>(bits.data());
-        switch (n) {
-            case 5: temporal3_batch<5, 5, 1, 5>(src, t0, T, HWG, thr.data(), bits8); break;
-            case 6: temporal3_batch<6, 6, 1, 6>(src, t0, T, HWG, thr.data(), bits8); break;
-            case 12: temporal3_batch<12, 12, 1, 6>(src, t0, T, HWG, thr.data(), bits8); break;
-            case 25: temporal3_batch<25, 5, 1, 5>(src, t0, T, HWG, thr.data(), bits8); break;
-            case 30: temporal3_batch<15, 15, 2, 15>(src, t0, T, HWG, thr.data(), bits8); break;
-            default: return -1001;
+        switch (n) {  // generated by tests/emu_build.py from the product's table
+#define T3_SHAPE_ARGS src, t0, T, HWG, thr.data(), bits8
+#include "t3_shapes_emu.inc"
+#undef T3_SHAPE_ARGS
+            default: return -1001;  // the product runs temporal2_kernel for this window
         }
         // history for the next batch: the last min(T, n) frames go into the ring (copy_to_ring)
         for (long long t = t0 + T - std::min(T, n); t < t0 + T; t++) memcpy(&ringbuf[(size_t)(t % R) * HW], frames + (size_t)(t - t_first) * HW, HW);
@@ -177,14 +198,13 @@ extern "C" int emu_noise_sums(const uint8_t *frames, int Ttot, long long t_first
     std::vector<unsigned long long> acc((size_t)Ttot * 2, 0ull);
     const int rh = roi[2] - roi[0], rw = roi[3] - roi[1];
     const long long std_interval = (long long)nz_interval * n;
-    FrameSrc src; src.ring = ringbuf.data(); src.cur = frames; src.mask = nullptr; src.t0 = t_first; src.R = 1; src.HW = HW;
+    FrameSrc src; src.ring = ringbuf.data(); src.cur = frames; src.mask = g_dev_mask; src.t0 = t_first; src.R = 1; src.HW = HW;
     for (int k = 0; k < ntaus; k++) {
         const long long tau = taus[k], L = tau < n ? tau : n;
         const long long i = tau - 1 - t_first;
         if (i < 0 || i >= Ttot || tau - L < t_first) return -1;
         SampleList sml; sml.count = 1; sml.idx[0] = (int)i;
-        const int gx = std::max(1, std::min((rh * rw + 255) / 256, 8));
-        emu_launch2(gx, 1, 256, [&] { noise_sample_kernel(src, W, n, t_first, std_interval, roi[0], roi[1], rh, rw, acc.data(), 0, sml); });
+        emu_noise_samples(src, W, n, t_first, std_interval, roi, acc.data(), 0, sml, Ttot);
         sums[2 * k] = acc[2 * i]; sums[2 * k + 1] = acc[2 * i + 1];
     }
     return 0;
@@ -230,12 +250,19 @@ extern "C" int emu_perframe_path(const uint8_t *frames, int Ttot, int W, int H, 
     const int rh = roi[2] - roi[0], rw = roi[3] - roi[1];
     const long long std_interval = (long long)nz_interval * n;
     const unsigned pgrid = (unsigned)((groups + PF_THREADS - 1) / PF_THREADS);
-    FrameSrc ringsrc; ringsrc.ring = ringbuf.data(); ringsrc.cur = nullptr; ringsrc.mask = nullptr; ringsrc.t0 = 0; ringsrc.R = R; ringsrc.HW = HW;
+    FrameSrc ringsrc; ringsrc.ring = ringbuf.data(); ringsrc.cur = nullptr; ringsrc.mask = g_dev_mask; ringsrc.t0 = 0; ringsrc.R = R; ringsrc.HW = HW;
     bool suffix_pending = false;
-    emu_launch(pgrid, PF_THREADS, [&] { pf_rebuild_kernel<false>(ringsrc, 0, n, S.data(), Pm.data(), SUF.data(), groups); });  // pf_timer = -1
+    const uint8_t *dm = g_dev_mask;
+    emu_launch(pgrid, PF_THREADS, [&] {  // pf_timer = -1
+        if (dm) pf_rebuild_kernel<true>(ringsrc, 0, n, S.data(), Pm.data(), SUF.data(), groups);
+        else pf_rebuild_kernel<false>(ringsrc, 0, n, S.data(), Pm.data(), SUF.data(), groups);
+    });
     for (long long t = 0; t < Ttot; t++) {
         if (suffix_pending) {  // pf_launch_suffix: the block that ended with frame t-1
-            emu_launch(pgrid, PF_THREADS, [&] { pf_suffix_kernel<false>(ringsrc, t - 1, t - n + 1, n - 1, SUF.data(), groups); });
+            emu_launch(pgrid, PF_THREADS, [&] {
+                if (dm) pf_suffix_kernel<true>(ringsrc, t - 1, t - n + 1, n - 1, SUF.data(), groups);
+                else pf_suffix_kernel<false>(ringsrc, t - 1, t - n + 1, n - 1, SUF.data(), groups);
+            });
             suffix_pending = false;
         }
         memcpy(stage.data(), frames + (size_t)t * HW, HW);
@@ -244,10 +271,7 @@ extern "C" int emu_perframe_path(const uint8_t *frames, int Ttot, int W, int H, 
         const long long tau = t + 1;
         SampleList sml; sml.count = 0;
         if ((tau > 1 && tau <= n) || (tau > n && std_interval > 0 && tau % std_interval == 0)) sml.idx[sml.count++] = 0;
-        if (sml.count) {
-            const int gx = std::max(1, std::min((rh * rw + 255) / 256, 8));
-            emu_launch2(gx, 1, 256, [&] { noise_sample_kernel(src, W, n, t, std_interval, roi[0], roi[1], rh, rw, noise, 0, sml); });
-        }
+        if (sml.count) emu_noise_samples(src, W, n, t, std_interval, roi, noise, 0, sml, 1);
         int thr = 0; double thrf = 0, snr = 0;
         emu_launch(1, 32, [&] { threshold_kernel(&st, noise, 1, t, n, std_interval, (long long)rh * rw, adaptive, sensitivity, &thr, &thrf, &snr); });
         const int pos = (int)(t % n), L = (int)std::min<long long>(n, t + 1);
@@ -259,8 +283,10 @@ extern "C" int emu_perframe_path(const uint8_t *frames, int Ttot, int W, int H, 
             const size_t g0 = half ? gA : 0, g1 = half ? groups : gA;
             if (g1 == g0) continue;
             emu_launch((unsigned)((g1 - g0 + PF_THREADS - 1) / PF_THREADS), PF_THREADS, [&] {
-                pf_update_kernel<false>(stage.data(), slot, old, nullptr, S.data(), Pm.data(), suf, pos == 0, L, &thr, g0, g1,
-                                        reinterpret_cast<uint16_t *>(bits.data()));
+                if (dm) pf_update_kernel<true>(stage.data(), slot, old, dm, S.data(), Pm.data(), suf, pos == 0, L, &thr, g0, g1,
+                                               reinterpret_cast<uint16_t *>(bits.data()));
+                else pf_update_kernel<false>(stage.data(), slot, old, nullptr, S.data(), Pm.data(), suf, pos == 0, L, &thr, g0, g1,
+                                             reinterpret_cast<uint16_t *>(bits.data()));
             });
         }
         suffix_pending = pos == n - 1;

@@ -30,6 +30,16 @@ def patched_sources(tmp, names):
         for other in names:  # headers under test that include each other pick up the scratch copies
             src = src.replace(f'#include "{other}"', f'#include "{other.replace(".cuh", "_emu.cuh")}"')
         open(os.path.join(tmp, name.replace(".cuh", "_emu.cuh")), "w").write(src)
+    # the default window -> shape table of temporal3_dispatch.cuh as `case n: temporal3_batch<U, BL, P, K>(...)` lines, so that
+    # an emulated path runs a window with exactly the shape the product launches for it
+    disp = open(os.path.join(CSRC, "temporal3_dispatch.cuh")).read()
+    table = disp[disp.rindex("switch (n) {"):]
+    table = table[:table.index("default: return -2;")]
+    rows = re.findall(r"T3_CASE\((\d+), (\d+), (\d+), (\d+), (\d+), \d+\)", table)
+    assert len(rows) >= 27, len(rows)
+    with open(os.path.join(tmp, "t3_shapes_emu.inc"), "w") as f:
+        for n, u, bl, pp, k in rows:
+            f.write(f"case {n}: temporal3_batch<{u}, {bl}, {pp}, {k}>(T3_SHAPE_ARGS); break;\n")
     c = open(os.path.join(CSRC, "common.cuh")).read().replace('#include "../../include/metdet_b200.h"', '#include "metdet_b200.h"')
     open(os.path.join(tmp, "common.cuh"), "w").write(c)
 

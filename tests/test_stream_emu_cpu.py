@@ -53,6 +53,7 @@ def test_streaming_path_kernels_reproduce_the_reference_golden(emu_lib, name, fr
             assert np.array_equal(raw[t, :nl[t]], ragged_get(g["raw_lines"], g["raw_offs"], t)), t
         with_lines += nl[t] > 0
     assert with_lines > 0
+    assert emu_lib.emu_noise16_launches() > 0  # the noise kernel the product selects for aligned frames (16-byte loads)
 
 
 @pytest.mark.parametrize("name,world,batch", [("synth_384x216_n12_dyon_mask", 3, 7), ("clip_192x144_n25", 2, 16)])
