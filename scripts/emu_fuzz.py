@@ -134,16 +134,94 @@ def run_case(lib, case, per_frame=False, generic=False):
     return None
 
 
+def build_classic_lib(tmp):
+    from emu_build import build
+    lib = C.CDLL(build(tmp, "classic_path_emu.cpp", patched=["kernels_basic.cuh", "spatial_kernel.cuh", "hough.cuh", "classic.cuh", "preproc.cuh"],
+                       shared=True))
+    lib.emu_classic_path.restype = C.c_int
+    lib.emu_preproc.restype = C.c_int
+    return lib
+
+
+def run_classic_case(lib, case):
+    """ClassicDetector (MetLib/Detector.py:245-299) through the emulated classic.cuh kernels + PPHT with the configured gap."""
+    from metdetpy_b200.detector import select_subarea
+    from oracle import classic_oracle as CO
+    W, H, T, cfg, mask, fr = (case[k] for k in ("W", "H", "T", "cfg", "mask", "frames"))
+    roi = (C.c_int * 4)(*[int(v) for v in select_subarea(mask, cfg["area"])])
+    cap = 8192
+    thr = np.zeros(T, np.int32); snr = np.zeros(T); dst = np.zeros((T, H, W), np.uint8); nl = np.zeros(T, np.int32)
+    raw = np.zeros((T, cap, 4), np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.emu_classic_path(p(fr), T, W, H, case["batch"], int(cfg["adaptive"]), int(cfg["init_value"]), _SENS.index(cfg["sensitivity"]),
+                              int(cfg["interval"]), roi, *[int(v) for v in cfg["hough"]], C.c_double(float(mask.sum())), p(thr), p(snr),
+                              p(dst), p(nl), p(raw), cap)
+    if rc != 0:
+        return f"emulated path failed: rc={rc}"
+    ref = CO.ClassicDetectorOracle(1.0, 25.0, mask, 10, adaptive=cfg["adaptive"], init_value=cfg["init_value"], sensitivity=cfg["sensitivity"],
+                                   area=cfg["area"], interval=cfg["interval"], hough=cfg["hough"], backend="cv2")
+    for t in range(T):
+        ref.update(fr[t]); lines, _ = ref.detect()
+        if ref.bi_threshold != thr[t]:
+            return f"frame {t}: threshold {thr[t]} != {ref.bi_threshold}"
+        if not np.isclose(snr[t], ref.stack.snr, rtol=1e-12, atol=0):
+            return f"frame {t}: snr {snr[t]!r} != {ref.stack.snr!r}"
+        if t < 3:
+            continue  # no lines and no mask before four frames are there (Detector.py:264-265)
+        if not np.array_equal(dst[t], ref.dst):
+            return f"frame {t}: mask differs in {int(np.count_nonzero(dst[t] != ref.dst))} pixels"
+        want = np.asarray(lines, np.int32).reshape(-1, 4)
+        if nl[t] != len(want) or (nl[t] <= cap and not np.array_equal(raw[t, :nl[t]], want)):
+            return f"frame {t}: segments differ ({nl[t]} vs {len(want)})"
+    return None
+
+
+def run_preproc_case(lib, seed):
+    """Transform chain of the loader (MetLib/imgproc.py:70-139; resize, BGR2GRAY, mask, exposure merge) through the emulated
+    preproc_kernel with the library's own tap tables, against oracle/preproc_oracle.py (which is pinned on cv2)."""
+    from metdetpy_b200 import _lib
+    from oracle import preproc_oracle as PO
+    nat = _lib.load()
+    r = np.random.default_rng([seed, 77])
+    W0, H0 = int(r.integers(20, 200)), int(r.integers(12, 120))
+    resize = r.random() < 0.8
+    W, H = (int(r.integers(8, 2 * W0)), int(r.integers(6, 2 * H0))) if resize else (W0, H0)
+    ch = 3 if r.random() < 0.8 else 1
+    exp = int(r.integers(1, 5))
+    T = int(r.integers(1, 9))
+    fr = r.integers(0, 256, (T, H0, W0, 3) if ch == 3 else (T, H0, W0), dtype=np.uint8)
+    mask = (r.random((H, W)) > 0.2).astype(np.uint8)
+    taps = []
+    for dst_n, src_n, clamp, stride in ((W, W0, 1, ch), (H, H0, 0, 1)):
+        a = [np.zeros(dst_n, np.int32) for _ in range(4)]
+        if nat.mdb_preproc_axis_taps(dst_n, src_n, clamp, *[x.ctypes.data for x in a]) != 0:
+            return "mdb_preproc_axis_taps failed"
+        a[0] *= stride; a[1] *= stride
+        taps.append(np.ascontiguousarray(np.stack(a, 1)))
+    G = (T + exp - 1) // exp
+    out = np.zeros((G, H, W), np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.emu_preproc(p(fr), T, W0, H0, ch, 0, W, H, int((W0, H0) != (W, H)), exp, p(taps[0]), p(taps[1]), p(mask), p(out))
+    if rc != 0:
+        return f"emu_preproc rc={rc}"
+    want = PO.preprocess_stream(fr, (W, H), ch == 3, mask, exp)
+    if not np.array_equal(out, want):
+        return f"{W0}x{H0}x{ch} -> {W}x{H}, exp {exp}, T {T}: {int(np.count_nonzero(out != want))} pixels differ"
+    return None
+
+
 def main():
     import tempfile
     first, count = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (0, 50)
-    lib, glib = build_lib(tempfile.mkdtemp()), build_generic_lib(tempfile.mkdtemp())
+    lib, glib, clib = build_lib(tempfile.mkdtemp()), build_generic_lib(tempfile.mkdtemp()), build_classic_lib(tempfile.mkdtemp())
     bad = 0
     for seed in range(first, first + count):
         case = make_case(seed)
         res = [run_case(lib, case, pf) for pf in (False, True)]
         gcase = make_case(seed, any_width=True)
         res.append(run_case(glib, gcase, generic=True))
+        res.append(run_classic_case(clib, gcase))
+        res.append(run_preproc_case(clib, seed))
         tag = {k: case[k] for k in ("W", "H", "n", "T", "batch")}
         print(seed, tag, case["cfg"], "generic", {k: gcase[k] for k in ("W", "H", "n", "T", "apply_mask")}, res, flush=True)
         bad += any(x not in (None, "skipped") for x in res)

@@ -46,3 +46,23 @@ def test_random_configuration_through_the_generic_kernels(fuzz, generic_lib, see
     case = fuzz.make_case(seed, any_width=True)
     res = fuzz.run_case(generic_lib, case, generic=True)
     assert res is None, (seed, {k: case[k] for k in ("W", "H", "n", "T", "apply_mask")}, case["cfg"], res)
+
+
+@pytest.fixture(scope="module")
+def classic_lib(fuzz, tmp_path_factory):
+    return fuzz.build_classic_lib(str(tmp_path_factory.mktemp("emu_fuzz_classic")))
+
+
+@pytest.mark.parametrize("seed", [1, 3, 6, 9, 12])
+def test_random_configuration_through_the_classic_detector(fuzz, classic_lib, seed):
+    case = fuzz.make_case(seed, any_width=True)
+    res = fuzz.run_classic_case(classic_lib, case)
+    assert res is None, (seed, {k: case[k] for k in ("W", "H", "T", "batch")}, case["cfg"], res)
+
+
+def test_random_loader_transform_chains(fuzz, classic_lib):
+    """Random source / target sizes (down- and up-scaling, no resize), colour and gray sources, exposure merges of 1..4 frames
+    with a ragged last group, random masks."""
+    for seed in range(40):
+        res = fuzz.run_preproc_case(classic_lib, seed)
+        assert res is None, (seed, res)
