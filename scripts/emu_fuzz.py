@@ -35,7 +35,7 @@ def build_generic_lib(tmp):
     return lib
 
 
-def make_case(seed, any_width=False):
+def make_case(seed, any_width=False, dense=False):
     import cv2
     r = np.random.default_rng(seed)
     W = int(r.integers(17, 260)) if any_width else 32 * int(r.integers(1, 9))
@@ -53,6 +53,10 @@ def make_case(seed, any_width=False):
         pts = np.array([[0, H], [0, int(H * r.uniform(0.5, 0.95))], [int(W * r.uniform(0.3, 1.0)), H]], np.int32)
         cv2.fillPoly(mask, [pts], 0)
     sigma = float(r.uniform(0.8, 3.5))
+    if dense:  # low fixed threshold on a noisy sky: thousands of on-pixels per frame (PPHT tiers 1b / 2 / 3, dst_dense, list overflows)
+        cfg.update(adaptive=False, init_value=int(r.integers(1, 4)))
+        sigma = float(r.uniform(3.0, 6.0))
+        T = min(T, 24)
     sky = r.uniform(10, 60) + r.normal(0, 3, (H, W))
     frames = np.empty((T, H, W), np.uint8)
     ang, x0, y0 = r.uniform(0, 2 * np.pi), r.uniform(0.1, 0.9) * W, r.uniform(0.1, 0.9) * H
@@ -222,6 +226,9 @@ def main():
         res.append(run_case(glib, gcase, generic=True))
         res.append(run_classic_case(clib, gcase))
         res.append(run_preproc_case(clib, seed))
+        if seed % 4 == 3:  # a dense variant of every fourth case
+            dcase = make_case(seed, dense=True)
+            res += [run_case(lib, dcase, pf) for pf in (False, True)]
         tag = {k: case[k] for k in ("W", "H", "n", "T", "batch")}
         print(seed, tag, case["cfg"], "generic", {k: gcase[k] for k in ("W", "H", "n", "T", "apply_mask")}, res, flush=True)
         bad += any(x not in (None, "skipped") for x in res)

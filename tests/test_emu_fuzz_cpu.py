@@ -40,6 +40,15 @@ def test_random_configuration_equals_the_checker(fuzz, lib, seed):
         assert res is None, (seed, per_frame, {k: case[k] for k in ("W", "H", "n", "T", "batch")}, case["cfg"], res)
 
 
+@pytest.mark.parametrize("seed", [0, 2, 6, 9])
+def test_random_dense_configuration_equals_the_checker(fuzz, lib, seed):
+    """Low fixed thresholds on a noisy sky: thousands of on-pixels per frame (word-list overflows -> dst_dense, PPHT tiers 1b / 2)."""
+    case = fuzz.make_case(seed, dense=True)
+    for per_frame in (False, True):
+        res = fuzz.run_case(lib, case, per_frame)
+        assert res is None, (seed, per_frame, {k: case[k] for k in ("W", "H", "n", "T", "batch")}, case["cfg"], res)
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2, 5, 7, 9, 11])
 def test_random_configuration_through_the_generic_kernels(fuzz, generic_lib, seed):
     """Any width, any window (1, 31, 38, 129, 140 ...), mask on the device or applied by the loader."""
