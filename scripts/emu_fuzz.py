@@ -21,10 +21,11 @@ _SENS = ["low", "normal", "high"]
 def build_lib(tmp):
     from emu_build import build
     so = build(tmp, "stream_path_emu.cpp",
-               patched=["temporal3_kernel.cuh", "kernels_basic.cuh", "spatial_kernel.cuh", "hough.cuh", "perframe_kernel.cuh"], shared=True)
+               patched=["temporal3_kernel.cuh", "temporal_kernel.cuh", "kernels_basic.cuh", "spatial_kernel.cuh", "hough.cuh", "perframe_kernel.cuh"], shared=True)
     lib = C.CDLL(so)
     lib.emu_stream_path.restype = C.c_int
     lib.emu_perframe_path.restype = C.c_int
+    lib.emu_temporal2_launches.restype = C.c_int
     return lib
 
 
@@ -226,6 +227,10 @@ def main():
         res.append(run_case(glib, gcase, generic=True))
         res.append(run_classic_case(clib, gcase))
         res.append(run_preproc_case(clib, seed))
+        if seed % 3 == 0:  # the second-generation temporal kernel on every third case
+            lib.emu_set_temporal_version(2)
+            res.append(run_case(lib, case))
+            lib.emu_set_temporal_version(3)
         if seed % 4 == 3:  # a dense variant of every fourth case
             dcase = make_case(seed, dense=True)
             res += [run_case(lib, dcase, pf) for pf in (False, True)]

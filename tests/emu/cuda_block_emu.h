@@ -200,6 +200,7 @@ static inline unsigned __vmaxu2(unsigned a, unsigned b) {
     const unsigned lo = std::max(a & 0xffffu, b & 0xffffu), hi = std::max(a >> 16, b >> 16);
     return (hi << 16) | lo;
 }
+static inline unsigned __vimax3_u16x2(unsigned a, unsigned b, unsigned c) { return __vmaxu2(__vmaxu2(a, b), c); }
 static inline unsigned __vmaxu4(unsigned a, unsigned b) {
     unsigned r = 0;
     for (int k = 0; k < 4; k++) r |= std::max((a >> (8 * k)) & 0xffu, (b >> (8 * k)) & 0xffu) << (8 * k);

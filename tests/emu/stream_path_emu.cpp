@@ -17,6 +17,66 @@ uint16_t o_sm[8192];
 #include "spatial_kernel_emu.cuh"
 #include "hough_emu.cuh"
 #include "perframe_kernel_emu.cuh"
+// temporal2_kernel (csrc/temporal_kernel.cuh): the second-generation temporal pass the product launches for windows without a
+// temporal3 shape (n = 11, 13, 17, 19, 22, 23, 26, 27, 29, 31 ...) and when temporal_version = 2 is forced
+uint4 t_smem[16 * 1024];  // 256 KB of emulated dynamic shared memory
+#define __cvta_generic_to_shared(p) ((size_t)0)
+#include "temporal_kernel_emu.cuh"
+
+static int g_temporal_version = 3;
+extern "C" void emu_set_temporal_version(int v) { g_temporal_version = v; }  // the library's "temporal_version" option
+static int g_t2_launches = 0;
+extern "C" int emu_temporal2_launches() { return g_t2_launches; }
+
+// stream_choose_kdiv / stream_state_config / stream_state_init (csrc/stream_kernel.cuh:65-111), restated: sub-blocks per
+// window, words per thread and CTA size of temporal2 for a window of n frames
+struct T2Config { int kdiv, wpt, nt; };
+static bool t2_config(int n, int max_batch, T2Config &c) {
+    c.kdiv = 1;
+    if (n >= 48)
+        for (int k = T2_KMAX; k >= 2; k--)
+            if (n % k == 0 && n / k >= 15) { c.kdiv = k; break; }
+    auto config = [&](int wpt) {
+        const size_t sm_bytes = 228 * 1024, cta_max = 220 * 1024, reserved = 1024;
+        const size_t per_thread = (size_t)(n + T2_K + n / c.kdiv) * 4 * wpt, table = ((size_t)2 * max_batch + 15) & ~(size_t)15;
+        int best_nt = 0;
+        size_t best_warps = 0;
+        for (int nt = 128; nt >= 32; nt >>= 1) {
+            const size_t cta = per_thread * nt + table;
+            if (cta > cta_max) continue;
+            const size_t warps = sm_bytes / (cta + reserved) * (nt / 32);
+            if (warps > best_warps) { best_warps = warps; best_nt = nt; }
+        }
+        c.wpt = wpt; c.nt = best_nt;
+        return best_nt != 0;
+    };
+    const bool wide = (size_t)(2 * n + T2_K) * 16 * 32 * 8 <= (size_t)220 * 1024;
+    return config(wide ? 4 : 2) || config(2);
+}
+template <bool M, int WPT, int NT>
+static void temporal2_launch_nt(const FrameSrc &src, long long t0, int T, int n, int kdiv, int HWG, const int *thr, uint8_t *bits) {
+    const unsigned grid = (unsigned)((HWG + NT - 1) / NT);
+    if (kdiv > 1) emu_launch(grid, NT, [&] { temporal2_kernel<M, WPT, NT, true>(src, t0, T, n, kdiv, HWG, thr, bits); });
+    else emu_launch(grid, NT, [&] { temporal2_kernel<M, WPT, NT, false>(src, t0, T, n, 1, HWG, thr, bits); });
+}
+template <bool M, int WPT>
+static void temporal2_launch_wpt(int nt, const FrameSrc &src, long long t0, int T, int n, int kdiv, int HWG, const int *thr, uint8_t *bits) {
+    if (nt == 32) temporal2_launch_nt<M, WPT, 32>(src, t0, T, n, kdiv, HWG, thr, bits);
+    else if (nt == 64) temporal2_launch_nt<M, WPT, 64>(src, t0, T, n, kdiv, HWG, thr, bits);
+    else temporal2_launch_nt<M, WPT, 128>(src, t0, T, n, kdiv, HWG, thr, bits);
+}
+// the temporal2 branch of stream_kernel_launch (csrc/stream_kernel.cuh:160-176)
+static int temporal2_batch(const FrameSrc &src, long long t0, int T, int n, int max_batch, size_t HW, const int *thr, uint8_t *bits) {
+    T2Config c;
+    if (!t2_config(n, max_batch, c)) return -1;
+    const size_t smem = (size_t)(n + T2_K + n / c.kdiv) * 4 * c.wpt * c.nt + (((size_t)2 * T + 15) & ~(size_t)15);
+    if (smem > sizeof t_smem) return -1;
+    const int HWG = (int)(HW / (4 * c.wpt));
+    g_t2_launches++;
+    if (c.wpt == 2) { if (src.mask) temporal2_launch_wpt<true, 2>(c.nt, src, t0, T, n, c.kdiv, HWG, thr, bits); else temporal2_launch_wpt<false, 2>(c.nt, src, t0, T, n, c.kdiv, HWG, thr, bits); }
+    else { if (src.mask) temporal2_launch_wpt<true, 4>(c.nt, src, t0, T, n, c.kdiv, HWG, thr, bits); else temporal2_launch_wpt<false, 4>(c.nt, src, t0, T, n, c.kdiv, HWG, thr, bits); }
+    return 0;
+}
 
 // apply_mask = 1 of the product: frames arrive unmasked, every kernel that loads a frame applies this mask (FrameSrc::mask);
 // set by emu_set_device_mask() for the following calls, nullptr = frames are already masked (or there is no mask)
@@ -66,7 +126,7 @@ static int run_range(const uint8_t *frames, int Ttot, long long t_first, int hal
                      int adaptive, int init_value, int sensitivity, int nz_interval, const int *roi, int hough_thr,
                      int hough_min_len, int hough_max_gap, int dy_on, double mask_area, int *thr_out, double *snr_out,
                      uint8_t *dst_out, int *n_on_out, int *lines_num_out, int32_t *raw_out /*[Ttot][512][4]*/) {
-    if (W % 32 || n < 2) return -1000;
+    if (W % 32 || n < 2 || n > 128) return -1000;  // stream_state_init: the generic kernels serve these
     const float theta = (float)(3.14159265358979323846 / 180.0);
     for (int k = 0; k < MDB_HOUGH_ANGLES; k++) {
         c_trig[2 * k] = (float)cos((double)k * (double)theta);
@@ -123,12 +183,14 @@ static int run_range(const uint8_t *frames, int Ttot, long long t_first, int hal
         }
         // ---- temporal pass (shape table of temporal3_dispatch.cuh) -------------------------------------------------------
         uint8_t *bits8 = reinterpret_cast<uint8_t *>(bits.data());
-        switch (n) {  // generated by tests/emu_build.py from the product's table
+        bool t3_done = g_temporal_version == 3;
+        if (t3_done) switch (n) {  // generated by tests/emu_build.py from the product's table
 #define T3_SHAPE_ARGS src, t0, T, HWG, thr.data(), bits8
 #include "t3_shapes_emu.inc"
 #undef T3_SHAPE_ARGS
-            default: return -1001;  // the product runs temporal2_kernel for this window
+            default: t3_done = false;  // no shape: the product runs temporal2_kernel for this window
         }
+        if (!t3_done && temporal2_batch(src, t0, T, n, B, HW, thr.data(), bits8) != 0) return -1001;
         // history for the next batch: the last min(T, n) frames go into the ring (copy_to_ring)
         for (long long t = t0 + T - std::min(T, n); t < t0 + T; t++) memcpy(&ringbuf[(size_t)(t % R) * HW], frames + (size_t)(t - t_first) * HW, HW);
         // ---- stream_kernel_launch: act, dst -------------------------------------------------------------------------------
@@ -218,7 +280,7 @@ extern "C" int emu_perframe_path(const uint8_t *frames, int Ttot, int W, int H, 
                                  int nz_interval, const int *roi, int hough_thr, int hough_min_len, int hough_max_gap, int dy_on,
                                  double mask_area, int *thr_out, double *snr_out, uint8_t *dst_out, int *n_on_out, int *lines_num_out,
                                  int32_t *raw_out) {
-    if (W % 32 || n < 2) return -1000;
+    if (W % 32 || n < 2 || n > 128) return -1000;  // stream_state_init: the generic kernels serve these
     const float theta = (float)(3.14159265358979323846 / 180.0);
     for (int k = 0; k < MDB_HOUGH_ANGLES; k++) {
         c_trig[2 * k] = (float)cos((double)k * (double)theta);

@@ -27,6 +27,16 @@ def patched_sources(tmp, names):
         src = re.sub(r"\n[^\n]*asm volatile\(\"prefetch\.global\.L2[^\n]*", "\n", src)
         # host-side launchers (<<< >>> syntax) inside kernel headers are not part of the device code under test
         src = re.sub(r"static inline void launch_noise_samples\(.*?\n}\n", "", src, flags=re.S)
+        if name == "temporal_kernel.cuh":  # temporal2's inline-PTX helpers -> tests/emu/t2_ptx_shims.h
+            def cut(text, first, stop):
+                a, b = text.index(first), text.index(stop)
+                assert a < b, (first, stop)
+                return text[:a] + text[b:]
+            src = cut(src, "__device__ __forceinline__ void t2_commit()", "// bytes 1 and 3 of x as clean u16x2 lanes")
+            src = cut(src, "template <int WPT>\n__device__ __forceinline__ void t2_cp(", "// per-thread running state of the window")
+            src = cut(src, "// base + idx * stride as one IMAD.WIDE", "// Compute stage.")
+            src = src.replace("#define T2_K 8", '#define T2_K 8\n#include "t2_ptx_shims.h"', 1)
+            assert "asm" not in src.split("#pragma once", 1)[1], "temporal_kernel.cuh has PTX the shims do not cover"
         for other in names:  # headers under test that include each other pick up the scratch copies
             src = src.replace(f'#include "{other}"', f'#include "{other.replace(".cuh", "_emu.cuh")}"')
         open(os.path.join(tmp, name.replace(".cuh", "_emu.cuh")), "w").write(src)

@@ -40,6 +40,29 @@ def test_random_configuration_equals_the_checker(fuzz, lib, seed):
         assert res is None, (seed, per_frame, {k: case[k] for k in ("W", "H", "n", "T", "batch")}, case["cfg"], res)
 
 
+@pytest.mark.parametrize("seed", [5, 7, 8, 15, 28])
+def test_windows_without_a_temporal3_shape_run_temporal2(fuzz, lib, seed):
+    """n = 31, 38, 13, 17, 54: the product launches temporal2_kernel (csrc/temporal_kernel.cuh; its inline PTX replaced by
+    tests/emu/t2_ptx_shims.h) -- what a 29.97 fps or 23.976 fps video with a one-second window gets."""
+    case = fuzz.make_case(seed)
+    before = lib.emu_temporal2_launches()
+    res = fuzz.run_case(lib, case)
+    assert res is None, (seed, {k: case[k] for k in ("W", "H", "n", "T", "batch")}, case["cfg"], res)
+    assert lib.emu_temporal2_launches() > before
+
+
+@pytest.mark.parametrize("seed", [0, 2, 4, 6, 9, 10])
+def test_temporal2_forced_equals_the_checker(fuzz, lib, seed):
+    """temporal_version = 2 on windows that do have a temporal3 shape (incl. n = 60: sub-blocked van Herk, 4 blocks of 15)."""
+    case = fuzz.make_case(seed)
+    lib.emu_set_temporal_version(2)
+    try:
+        res = fuzz.run_case(lib, case)
+    finally:
+        lib.emu_set_temporal_version(3)
+    assert res is None, (seed, {k: case[k] for k in ("W", "H", "n", "T", "batch")}, case["cfg"], res)
+
+
 @pytest.mark.parametrize("seed", [0, 2, 6, 9])
 def test_random_dense_configuration_equals_the_checker(fuzz, lib, seed):
     """Low fixed thresholds on a noisy sky: thousands of on-pixels per frame (word-list overflows -> dst_dense, PPHT tiers 1b / 2)."""

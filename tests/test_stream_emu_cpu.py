@@ -18,7 +18,7 @@ _SENS = {"low": 0, "normal": 1, "high": 2}
 @pytest.fixture(scope="module")
 def emu_lib(tmp_path_factory):
     so = build(tmp_path_factory.mktemp("stream_emu"), "stream_path_emu.cpp",
-               patched=["temporal3_kernel.cuh", "kernels_basic.cuh", "spatial_kernel.cuh", "hough.cuh", "perframe_kernel.cuh"], shared=True)
+               patched=["temporal3_kernel.cuh", "temporal_kernel.cuh", "kernels_basic.cuh", "spatial_kernel.cuh", "hough.cuh", "perframe_kernel.cuh"], shared=True)
     lib = C.CDLL(so)
     lib.emu_stream_path.restype = C.c_int
     return lib
@@ -54,6 +54,17 @@ def test_streaming_path_kernels_reproduce_the_reference_golden(emu_lib, name, fr
         with_lines += nl[t] > 0
     assert with_lines > 0
     assert emu_lib.emu_noise16_launches() > 0  # the noise kernel the product selects for aligned frames (16-byte loads)
+
+
+@pytest.mark.parametrize("name,batch", [("synth_384x216_n12_dyon_mask", 7), ("clip_192x144_n25", 16)])
+def test_streaming_path_with_the_second_generation_temporal_kernel(emu_lib, name, batch):
+    """temporal_version = 2 (temporal2_kernel, the kernel windows without a temporal3 shape get) against the same goldens."""
+    emu_lib.emu_set_temporal_version(2)
+    try:
+        test_streaming_path_kernels_reproduce_the_reference_golden(emu_lib, name, 1000, batch)
+        assert emu_lib.emu_temporal2_launches() > 0
+    finally:
+        emu_lib.emu_set_temporal_version(3)
 
 
 @pytest.mark.parametrize("name,world,batch", [("synth_384x216_n12_dyon_mask", 3, 7), ("clip_192x144_n25", 2, 16)])
