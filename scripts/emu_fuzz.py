@@ -19,10 +19,8 @@ _SENS = ["low", "normal", "high"]
 
 
 def build_lib(tmp):
-    from emu_build import build
-    so = build(tmp, "stream_path_emu.cpp",
-               patched=["temporal3_kernel.cuh", "temporal_kernel.cuh", "kernels_basic.cuh", "spatial_kernel.cuh", "hough.cuh", "perframe_kernel.cuh"], shared=True)
-    lib = C.CDLL(so)
+    from emu_build import build_stream
+    lib = C.CDLL(build_stream(tmp))
     lib.emu_stream_path.restype = C.c_int
     lib.emu_perframe_path.restype = C.c_int
     lib.emu_temporal2_launches.restype = C.c_int
@@ -30,8 +28,8 @@ def build_lib(tmp):
 
 
 def build_generic_lib(tmp):
-    from emu_build import build
-    lib = C.CDLL(build(tmp, "generic_path_emu.cpp", patched=["kernels_basic.cuh", "hough.cuh"], shared=True))
+    from emu_build import build_generic
+    lib = C.CDLL(build_generic(tmp))
     lib.emu_generic_path.restype = C.c_int
     return lib
 
@@ -140,9 +138,8 @@ def run_case(lib, case, per_frame=False, generic=False):
 
 
 def build_classic_lib(tmp):
-    from emu_build import build
-    lib = C.CDLL(build(tmp, "classic_path_emu.cpp", patched=["kernels_basic.cuh", "spatial_kernel.cuh", "hough.cuh", "classic.cuh", "preproc.cuh"],
-                       shared=True))
+    from emu_build import build_classic
+    lib = C.CDLL(build_classic(tmp))
     lib.emu_classic_path.restype = C.c_int
     lib.emu_preproc.restype = C.c_int
     return lib

@@ -254,6 +254,11 @@ using std::min;
 // run grid_x * grid_y * grid_z blocks of `block` threads (a multiple of 32), one block after the other: the `block` fibers are
 // created once per launch and walk through the blocks together (a block barrier between two blocks keeps the function-local
 // "shared memory" statics of one block from being touched by the next)
+static long &emu_schedule_mode() {  // initial value from the environment; emu_set_schedule() changes it at run time
+    static long mode = getenv("EMU_SCHEDULE") ? atol(getenv("EMU_SCHEDULE")) : 0;
+    return mode;
+}
+extern "C" void emu_set_schedule(long mode) { emu_schedule_mode() = mode; }
 static std::vector<char *> &emu_stacks() {
     static std::vector<char *> v;
     return v;
@@ -311,11 +316,12 @@ static void emu_launch3(unsigned grid_x, unsigned grid_y, unsigned grid_z, unsig
         makecontext(&f.uc, emu_fiber_entry, 0);
 #endif
     }
-    // EMU_SCHEDULE: 0 / unset = fibers resumed in ascending thread order, 1 = descending, >= 2 = a fresh pseudo-random
+    // EMU_SCHEDULE / emu_set_schedule(): 0 / unset = fibers resumed in ascending thread order, 1 = descending, >= 2 = a fresh pseudo-random
     // permutation every round (seed = the value).  Any order is a legal CUDA schedule: a kernel whose result depends on it
     // is missing a barrier (or an atomic).
-    static const long emu_schedule = getenv("EMU_SCHEDULE") ? atol(getenv("EMU_SCHEDULE")) : 0;
-    static unsigned long long emu_sched_rng = 0x9E3779B97F4A7C15ull ^ (unsigned long long)emu_schedule;
+    const long emu_schedule = emu_schedule_mode();
+    static unsigned long long emu_sched_rng = 0x9E3779B97F4A7C15ull;
+    emu_sched_rng ^= (unsigned long long)emu_schedule;
     std::vector<unsigned> order(block);
     for (unsigned t = 0; t < block; t++) order[t] = emu_schedule == 1 ? block - 1 - t : t;
     unsigned alive = block;

@@ -54,7 +54,18 @@ def patched_sources(tmp, names):
     open(os.path.join(tmp, "common.cuh"), "w").write(c)
 
 
+_BUILT = {}  # one build per harness and process: several test modules share the larger libraries
+
+
 def build(tmp, harness, patched=(), extra_c=(), std="c++20", opt="-O1", shared=False):
+    key = (harness, tuple(patched), tuple(extra_c), std, opt, shared)
+    if key in _BUILT and os.path.exists(_BUILT[key]):
+        return _BUILT[key]
+    _BUILT[key] = _build(tmp, harness, patched, extra_c, std, opt, shared)
+    return _BUILT[key]
+
+
+def _build(tmp, harness, patched, extra_c, std, opt, shared):
     if shutil.which("g++") is None or shutil.which("gcc") is None:
         pytest.skip("no g++ / gcc")
     inc = cuda_include()
@@ -72,3 +83,21 @@ def build(tmp, harness, patched=(), extra_c=(), std="c++20", opt="-O1", shared=F
                            "-I", os.path.join(REPO, "include"), "-I", inc, os.path.join(REPO, "tests", "emu", harness)] + objs +
                           ["-o", exe])
     return exe
+
+
+# the three larger harness libraries, shared by several test modules and scripts/emu_fuzz.py
+STREAM_PATCHED = ["temporal3_kernel.cuh", "temporal_kernel.cuh", "kernels_basic.cuh", "spatial_kernel.cuh", "hough.cuh", "perframe_kernel.cuh"]
+GENERIC_PATCHED = ["kernels_basic.cuh", "hough.cuh"]
+CLASSIC_PATCHED = ["kernels_basic.cuh", "spatial_kernel.cuh", "classic.cuh", "preproc.cuh", "hough.cuh"]
+
+
+def build_stream(tmp):
+    return build(tmp, "stream_path_emu.cpp", patched=STREAM_PATCHED, shared=True)
+
+
+def build_generic(tmp):
+    return build(tmp, "generic_path_emu.cpp", patched=GENERIC_PATCHED, shared=True)
+
+
+def build_classic(tmp):
+    return build(tmp, "classic_path_emu.cpp", patched=CLASSIC_PATCHED, shared=True)

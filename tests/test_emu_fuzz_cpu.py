@@ -30,9 +30,9 @@ def generic_lib(fuzz, tmp_path_factory):
     return fuzz.build_generic_lib(str(tmp_path_factory.mktemp("emu_fuzz_generic")))
 
 
-@pytest.mark.parametrize("seed", [2, 4, 6, 10, 11, 18, 20, 21, 22, 27, 36])
+@pytest.mark.parametrize("seed", [2, 4, 10, 11, 18, 21, 22, 27, 36])
 def test_random_configuration_equals_the_checker(fuzz, lib, seed):
-    """Streaming path and per-frame resident-state path; seeds 6, 18, 21, 36 have the mask applied inside the kernels' loads
+    """Streaming path and per-frame resident-state path; seeds 2, 18, 21, 22, 36 have the mask applied inside the kernels' loads
     (apply_mask = 1) instead of by the loader."""
     case = fuzz.make_case(seed)
     for per_frame in (False, True):
@@ -40,9 +40,9 @@ def test_random_configuration_equals_the_checker(fuzz, lib, seed):
         assert res is None, (seed, per_frame, {k: case[k] for k in ("W", "H", "n", "T", "batch")}, case["cfg"], res)
 
 
-@pytest.mark.parametrize("seed", [5, 7, 8, 15, 28])
+@pytest.mark.parametrize("seed", [7, 8, 15])
 def test_windows_without_a_temporal3_shape_run_temporal2(fuzz, lib, seed):
-    """n = 31, 38, 13, 17, 54: the product launches temporal2_kernel (csrc/temporal_kernel.cuh; its inline PTX replaced by
+    """n = 38, 13, 17: the product launches temporal2_kernel (csrc/temporal_kernel.cuh; its inline PTX replaced by
     tests/emu/t2_ptx_shims.h) -- what a 29.97 fps or 23.976 fps video with a one-second window gets."""
     case = fuzz.make_case(seed)
     before = lib.emu_temporal2_launches()
@@ -51,7 +51,7 @@ def test_windows_without_a_temporal3_shape_run_temporal2(fuzz, lib, seed):
     assert lib.emu_temporal2_launches() > before
 
 
-@pytest.mark.parametrize("seed", [0, 2, 4, 6, 9, 10])
+@pytest.mark.parametrize("seed", [0, 2, 4, 9, 10, 11])
 def test_temporal2_forced_equals_the_checker(fuzz, lib, seed):
     """temporal_version = 2 on windows that do have a temporal3 shape (incl. n = 60: sub-blocked van Herk, 4 blocks of 15)."""
     case = fuzz.make_case(seed)
@@ -63,7 +63,7 @@ def test_temporal2_forced_equals_the_checker(fuzz, lib, seed):
     assert res is None, (seed, {k: case[k] for k in ("W", "H", "n", "T", "batch")}, case["cfg"], res)
 
 
-@pytest.mark.parametrize("seed", [0, 2, 6, 9])
+@pytest.mark.parametrize("seed", [0, 2, 9])
 def test_random_dense_configuration_equals_the_checker(fuzz, lib, seed):
     """Low fixed thresholds on a noisy sky: thousands of on-pixels per frame (word-list overflows -> dst_dense, PPHT tiers 1b / 2)."""
     case = fuzz.make_case(seed, dense=True)
@@ -72,7 +72,7 @@ def test_random_dense_configuration_equals_the_checker(fuzz, lib, seed):
         assert res is None, (seed, per_frame, {k: case[k] for k in ("W", "H", "n", "T", "batch")}, case["cfg"], res)
 
 
-@pytest.mark.parametrize("seed", [0, 1, 2, 5, 7, 9, 11])
+@pytest.mark.parametrize("seed", [0, 1, 2, 7, 9, 11])
 def test_random_configuration_through_the_generic_kernels(fuzz, generic_lib, seed):
     """Any width, any window (1, 31, 38, 129, 140 ...), mask on the device or applied by the loader."""
     case = fuzz.make_case(seed, any_width=True)

@@ -5,7 +5,6 @@ per-frame and time-sharded paths must reproduce the same oracle / golden results
 missing a barrier or an atomic.  (compute-sanitizer's racecheck on the B200 is the device-side counterpart: profiles/r02_sanitizer_*.log.)"""
 import os
 import subprocess
-import sys
 
 import pytest
 
@@ -21,11 +20,26 @@ def test_ppht_tiers_under_other_thread_schedules(tmp_path, schedule):
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("schedule", ["1", "977"])
-def test_whole_paths_under_other_thread_schedules(schedule):
-    """The emulated streaming / per-frame / sharded paths against the golden trajectories (the masked dy-mask case through all three, the dense case with
-    tiers 2 and 3 through the streaming path) in a child process whose emulator uses another schedule."""
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(REPO, "tests", "test_stream_emu_cpu.py"), "-q", "-x",
-                        "-p", "no:cacheprovider", "-k", "synth_384x216 or (dense and streaming_path)"],
-                       capture_output=True, text=True, timeout=1800, cwd=REPO, env=dict(os.environ, EMU_SCHEDULE=schedule))
-    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+@pytest.fixture(scope="module")
+def stream_lib(tmp_path_factory):
+    import ctypes as C
+    from emu_build import build_stream
+    lib = C.CDLL(build_stream(tmp_path_factory.mktemp("stream_sched")))  # the build of tests/test_stream_emu_cpu.py when that ran first
+    lib.emu_stream_path.restype = C.c_int
+    return lib
+
+
+@pytest.mark.parametrize("schedule", [1, 977])
+def test_whole_paths_under_other_thread_schedules(stream_lib, schedule):
+    """The emulated streaming / per-frame / sharded paths against the golden trajectories (the masked dy-mask case through all
+    three, the dense case with tiers 2 and 3 through the streaming path) with the emulator switched to another schedule."""
+    import ctypes as C
+    import test_stream_emu_cpu as TS
+    stream_lib.emu_set_schedule(C.c_long(schedule))
+    try:
+        TS.test_streaming_path_kernels_reproduce_the_reference_golden(stream_lib, "synth_384x216_n12_dyon_mask", 1000, 7)
+        TS.test_streaming_path_kernels_reproduce_the_reference_golden(stream_lib, "synth_256x160_n6_fixed3_dense", 12, 5)
+        TS.test_per_frame_resident_state_path_reproduces_the_reference_golden(stream_lib, "synth_384x216_n12_dyon_mask", 1000)
+        TS.test_time_sharded_protocol_on_the_cpu(stream_lib, "synth_384x216_n12_dyon_mask", 3, 7)
+    finally:
+        stream_lib.emu_set_schedule(C.c_long(0))

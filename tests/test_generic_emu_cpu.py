@@ -9,14 +9,14 @@ import numpy as np
 import pytest
 
 from conftest import load_det_case, ragged_get
-from emu_build import build
+from emu_build import build_generic
 
 _SENS = {"low": 0, "normal": 1, "high": 2}
 
 
 @pytest.fixture(scope="module")
 def emu_lib(tmp_path_factory):
-    so = build(tmp_path_factory.mktemp("generic_emu"), "generic_path_emu.cpp", patched=["kernels_basic.cuh", "hough.cuh"], shared=True)
+    so = build_generic(tmp_path_factory.mktemp("generic_emu"))
     lib = C.CDLL(so)
     lib.emu_generic_path.restype = C.c_int
     return lib
