@@ -137,6 +137,64 @@ def run_case(lib, case, per_frame=False, generic=False):
     return None
 
 
+def run_sharded_case(lib, case, world):
+    """SURVEY 8(e) on a random case: per-rank noise sums -> pooled -> mdb_replay_thresholds -> seek + halo + chunk per virtual rank
+    (all emulated product kernels + the library's host code) against the sequential emulated run of the same case."""
+    from metdetpy_b200 import sharding as S
+    from metdetpy_b200.detector import select_subarea
+    W, H, n, T, cfg, mask, fr = (case[k] for k in ("W", "H", "n", "T", "cfg", "mask", "frames"))
+    if T < world or n > 128:
+        return "skipped"
+    roi_t = [int(v) for v in select_subarea(mask, cfg["area"])]
+    roi = (C.c_int * 4)(*roi_t)
+    roi_px = (roi_t[2] - roi_t[0]) * (roi_t[3] - roi_t[1])
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    hough = [int(v) for v in cfg["hough"]]
+    area = C.c_double(float(np.sum(mask)))
+    # sequential run
+    s_thr = np.zeros(T, np.int32); s_snr = np.zeros(T); s_dst = np.zeros((T, H, W), np.uint8)
+    s_on = np.zeros(T, np.int32); s_nl = np.zeros(T, np.int32); s_raw = np.zeros((T, 512, 4), np.int32)
+    rc = lib.emu_stream_path(p(fr), T, W, H, n, case["batch"], int(cfg["adaptive"]), int(cfg["init_value"]), _SENS.index(cfg["sensitivity"]),
+                             int(cfg["interval"]), roi, *hough, int(cfg["dy_mask"]), area, p(s_thr), p(s_snr), p(s_dst), p(s_on), p(s_nl), p(s_raw))
+    if rc != 0:
+        return "skipped" if rc in (-1000, -1001) else f"sequential run failed: rc={rc}"
+    shards = S.plan_shards(T, world, n)
+    samples = []
+    for sh in shards:
+        taus = np.ascontiguousarray(S.sample_timers(sh.start, sh.end, n, int(cfg["interval"])), np.int64)
+        if len(taus) == 0:
+            continue
+        lo = max(0, sh.start - (n - 1))
+        part = np.ascontiguousarray(fr[lo:sh.end])
+        sums = np.zeros((len(taus), 2), np.uint64)
+        if lib.emu_noise_sums(p(part), len(part), C.c_longlong(lo), W, H, n, int(cfg["interval"]), roi, p(taus), len(taus), p(sums)) != 0:
+            return f"rank {sh.rank}: emu_noise_sums failed"
+        samples += [(int(t), int(a), int(b)) for t, (a, b) in zip(taus, sums)]
+    thr, thr_f, snr = S.replay_thresholds_native(samples, roi_px, n, 0, T, adaptive=cfg["adaptive"], init_value=cfg["init_value"],
+                                                 sensitivity=cfg["sensitivity"], interval=cfg["interval"])
+    if not np.array_equal(thr, s_thr):
+        return f"replayed thresholds differ at frame {int(np.flatnonzero(np.asarray(thr) != s_thr)[0])}"
+    if not np.allclose(snr, s_snr, rtol=1e-12, atol=0):
+        return "replayed snr differs"
+    for sh in shards:
+        part = np.ascontiguousarray(fr[sh.halo_start:sh.end])
+        m, halo = len(part), sh.start - sh.halo_start
+        thr_in = np.ascontiguousarray(thr[sh.halo_start:sh.end], np.int32)
+        o_thr = np.zeros(m, np.int32); o_snr = np.zeros(m); dst = np.zeros((m, H, W), np.uint8)
+        n_on = np.zeros(m, np.int32); nl = np.zeros(m, np.int32); raw = np.zeros((m, 512, 4), np.int32)
+        rc = lib.emu_stream_chunk(p(part), m, C.c_longlong(sh.halo_start), halo, p(thr_in), W, H, n, case["batch"], roi, *hough,
+                                  int(cfg["dy_mask"]), area, p(o_thr), p(o_snr), p(dst), p(n_on), p(nl), p(raw))
+        if rc != 0:
+            return f"rank {sh.rank}: chunk failed rc={rc}"
+        for t in range(sh.start, sh.end):
+            k = t - sh.halo_start
+            if not np.array_equal(dst[k], s_dst[t]):
+                return f"rank {sh.rank} frame {t}: mask differs in {int(np.count_nonzero(dst[k] != s_dst[t]))} pixels"
+            if nl[k] != s_nl[t] or not np.array_equal(raw[k, :min(nl[k], 512)], s_raw[t, :min(nl[k], 512)]):
+                return f"rank {sh.rank} frame {t}: segments differ"
+    return None
+
+
 def build_classic_lib(tmp):
     from emu_build import build_classic
     lib = C.CDLL(build_classic(tmp))
@@ -224,6 +282,7 @@ def main():
         res.append(run_case(glib, gcase, generic=True))
         res.append(run_classic_case(clib, gcase))
         res.append(run_preproc_case(clib, seed))
+        res.append(run_sharded_case(lib, case, 2 + seed % 4))
         if seed % 3 == 0:  # the second-generation temporal kernel on every third case
             lib.emu_set_temporal_version(2)
             res.append(run_case(lib, case))

@@ -98,3 +98,12 @@ def test_random_loader_transform_chains(fuzz, classic_lib):
     for seed in range(40):
         res = fuzz.run_preproc_case(classic_lib, seed)
         assert res is None, (seed, res)
+
+
+@pytest.mark.parametrize("seed", [2, 7, 11, 15, 18, 23])
+def test_random_time_sharded_run_equals_the_sequential_run(fuzz, lib, seed):
+    """SURVEY 8(e) on random cases with 2..5 virtual ranks (chunks shorter than the window and the halo included; n = 38 and 17 run
+    temporal2): pooled noise sums, natively replayed thresholds, seek + halo + chunk per rank == the sequential emulated run."""
+    case = fuzz.make_case(seed)
+    res = fuzz.run_sharded_case(lib, case, 2 + seed % 4)
+    assert res is None, (seed, {k: case[k] for k in ("W", "H", "n", "T", "batch")}, case["cfg"], res)
