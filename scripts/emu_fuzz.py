@@ -195,6 +195,33 @@ def run_sharded_case(lib, case, world):
     return None
 
 
+def run_stack_case(glib, seed):
+    """max_stack_kernel / gauss_stack_kernel (MaxImgContainer, FastGaussianContainer: MetLib/stacker.py:43-59) through the
+    emulator against numpy with the reference's dtypes (uint16 sums and uint32 sums of squares wrap); aligned and unaligned
+    buffers, chunked accumulation, clips long enough to wrap."""
+    r = np.random.default_rng([seed, 5])
+    fb = int(r.choice([16, 48, 160, 1000, 4096, 37, 1001])) * (1 if r.random() < 0.5 else 3)
+    T = int(r.choice([1, 2, 5, 17, 64, 300]))
+    off = int(r.choice([0, 0, 1, 8]))  # an unaligned base takes the byte-wise branch
+    buf = np.empty(T * fb + 16, np.uint8)
+    fr = buf[off:off + T * fb].reshape(T, fb)
+    fr[:] = r.integers(0, 256, (T, fb), dtype=np.uint8) if r.random() < 0.5 else r.integers(200, 256, (T, fb), dtype=np.uint8)
+    chunk = int(r.integers(1, T + 1))
+    grid = int(r.integers(1, 9))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    out = np.full(fb, 0xEE, np.uint8)
+    glib.emu_max_stack(p(fr), T, C.c_size_t(fb), chunk, grid, p(out))
+    if not np.array_equal(out, fr.max(axis=0)):
+        return f"max stack differs (fb={fb}, T={T}, chunk={chunk}, off={off})"
+    sm = np.full(fb, 0xEEEE, np.uint16); sq = np.full(fb, 0xEEEEEEEE, np.uint32)
+    glib.emu_gauss_stack(p(fr), T, C.c_size_t(fb), chunk, grid, 0, p(sm), p(sq))
+    want_s = fr.astype(np.uint16).sum(axis=0, dtype=np.uint16)
+    want_q = (fr.astype(np.uint32) ** 2).sum(axis=0, dtype=np.uint32)
+    if not (np.array_equal(sm, want_s) and np.array_equal(sq, want_q)):
+        return f"gauss stack differs (fb={fb}, T={T}, chunk={chunk}, off={off})"
+    return None
+
+
 def build_classic_lib(tmp):
     from emu_build import build_classic
     lib = C.CDLL(build_classic(tmp))
@@ -282,6 +309,7 @@ def main():
         res.append(run_case(glib, gcase, generic=True))
         res.append(run_classic_case(clib, gcase))
         res.append(run_preproc_case(clib, seed))
+        res.append(run_stack_case(glib, seed))
         res.append(run_sharded_case(lib, case, 2 + seed % 4))
         if seed % 3 == 0:  # the second-generation temporal kernel on every third case
             lib.emu_set_temporal_version(2)

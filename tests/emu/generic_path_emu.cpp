@@ -86,3 +86,23 @@ extern "C" int emu_generic_path(const uint8_t *frames, int T, int W, int H, int 
     }
     return 0;
 }
+
+// Clip stackers of kernels_basic.cuh (mdb_max_stack / mdb_gauss_stack in csrc/metdet.cu feed them chunk by chunk):
+// MaxImgContainer (MetLib/stacker.py:43-49) and FastGaussianContainer (:52-59, uint16 / uint32 wrap-around)
+extern "C" int emu_max_stack(const uint8_t *frames, int T, size_t frame_bytes, int chunk, unsigned grid, uint8_t *out) {
+    for (int t0 = 0; t0 < T; t0 += chunk) {
+        const int c = std::min(chunk, T - t0);
+        const uint8_t *src = frames + (size_t)t0 * frame_bytes;
+        emu_launch(grid, 256, [&] { max_stack_kernel(src, c, frame_bytes, out, t0 > 0); });
+    }
+    return 0;
+}
+extern "C" int emu_gauss_stack(const uint8_t *frames, int T, size_t frame_bytes, int chunk, unsigned grid, int accumulate, uint16_t *sum,
+                               uint32_t *sq) {
+    for (int t0 = 0; t0 < T; t0 += chunk) {
+        const int c = std::min(chunk, T - t0);
+        const uint8_t *src = frames + (size_t)t0 * frame_bytes;
+        emu_launch(grid, 256, [&] { gauss_stack_kernel(src, c, frame_bytes, sum, sq, accumulate || t0 > 0); });
+    }
+    return 0;
+}

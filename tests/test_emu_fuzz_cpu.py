@@ -107,3 +107,11 @@ def test_random_time_sharded_run_equals_the_sequential_run(fuzz, lib, seed):
     case = fuzz.make_case(seed)
     res = fuzz.run_sharded_case(lib, case, 2 + seed % 4)
     assert res is None, (seed, {k: case[k] for k in ("W", "H", "n", "T", "batch")}, case["cfg"], res)
+
+
+def test_random_clip_stacks(fuzz, generic_lib):
+    """MaxImgContainer / FastGaussianContainer kernels: aligned and unaligned buffers, chunked accumulation, 300-frame clips whose
+    uint16 sums wrap like the reference's."""
+    for seed in range(60):
+        res = fuzz.run_stack_case(generic_lib, seed)
+        assert res is None, (seed, res)
