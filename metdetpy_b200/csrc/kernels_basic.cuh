@@ -402,51 +402,6 @@ __global__ void stack_std_kernel(FrameSrc src, size_t HW, int n, long long t, in
     if ((threadIdx.x & 31) == 0) atomicAdd(total, acc);
 }
 
-// Ordered (row-major) compaction of one dst mask into keys (y<<16|x): the overflow path for
-// frames whose on-pixel count exceeds the shared-memory PPHT capacity. One CTA of 1024 threads.
-__global__ void __launch_bounds__(1024)
-compact_ordered_kernel(const uint8_t *dst, int W, int H, uint32_t *keys, unsigned *n_out) {
-    __shared__ unsigned wsum[32];
-    __shared__ unsigned base_s;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) base_s = 0;
-    __syncthreads();
-    const size_t HW = (size_t)W * H;
-    for (size_t start = 0; start < HW; start += 1024 * 8) {
-        const size_t p0 = start + (size_t)tid * 8;
-        unsigned bits = 0;
-        for (int k = 0; k < 8; k++)
-            if (p0 + k < HW && dst[p0 + k]) bits |= 1u << k;
-        const unsigned c = __popc(bits);
-        unsigned inc = c;
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        if (lane == 31) wsum[w] = inc;
-        __syncthreads();
-        if (w == 0) {
-            unsigned v = wsum[lane], s = v;
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned u = __shfl_up_sync(0xffffffffu, s, o);
-                if (lane >= o) s += u;
-            }
-            wsum[lane] = s - v;  // exclusive
-        }
-        __syncthreads();
-        unsigned off = base_s + wsum[w] + inc - c;
-        for (int k = 0; k < 8; k++)
-            if (bits >> k & 1) {
-                const size_t p = p0 + k;
-                keys[off++] = ((unsigned)(p / W) << 16) | (unsigned)(p % W);
-            }
-        __syncthreads();
-        if (tid == 1023) base_s = base_s + wsum[31] + inc;
-        __syncthreads();
-    }
-    if (tid == 0) *n_out = base_s;
-}
-
 // stacker.MaxImgContainer / MergeFunction.max: out = max(out?, frames[0..T)) element-wise.
 // 16-byte lanes; per-byte max via the masked even/odd u16x2 trick (VIMNMX.U16x2 is native on
 // sm_100a, the u8x4 SIMD max is emulated).

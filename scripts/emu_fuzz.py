@@ -222,6 +222,43 @@ def run_stack_case(glib, seed):
     return None
 
 
+def run_readback_case(glib, seed):
+    """stack_readback_kernel / stack_std_kernel / window_frame_kernel (mdb_get_stack, mdb_get_std, mdb_get_window) against the
+    checker's SlidingWindow (MetLib/utils.py:225-321: max, mean, sum, std with calc_std / force_int) at a random timer, windows up
+    to 300 frames (more than the kernels' 256-entry pointer table), mask on the device or none."""
+    from oracle import m3_oracle as O
+    r = np.random.default_rng([seed, 9])
+    W, H = int(r.integers(5, 40)), int(r.integers(3, 20))
+    n = int(r.choice([1, 2, 5, 30, 64, 257, 300]))
+    T = int(r.integers(1, min(2 * n + 3, 320)))
+    R = n + int(r.integers(0, 5))
+    fr = r.integers(0, 256, (T, H, W), dtype=np.uint8)
+    mask = (r.random((H, W)) > 0.3).astype(np.uint8) if r.random() < 0.5 else None
+    sw = O.SlidingWindow(n, (H, W))
+    for f in fr:
+        sw.update(f * mask if mask is not None else f)
+    p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    mx = np.zeros((H, W), np.uint8); mean = np.zeros((H, W), np.uint8); sm = np.zeros((H, W), np.uint32); newest = np.zeros((H, W), np.uint8)
+    tot = C.c_ulonglong(0)
+    rc = glib.emu_stack_readback(p(fr), C.c_longlong(T - 1), W, H, n, R, p(mask), int(r.integers(1, 5)), p(mx), p(mean), p(sm), C.byref(tot), p(newest))
+    if rc != 0:
+        return f"rc={rc}"
+    tag = f"(W={W}, H={H}, n={n}, T={T}, R={R}, mask={'yes' if mask is not None else 'no'})"
+    if not np.array_equal(mx, sw.max):
+        return "max differs " + tag
+    if not np.array_equal(mean, sw.mean):
+        return "mean differs " + tag
+    if not np.array_equal(sm, sw.sum):
+        return "sum differs " + tag
+    L = min(n, T)
+    std = float(np.sqrt(tot.value / (H * W)))  # the two double operations on the host side of mdb_get_std
+    if not np.isclose(std, float(sw.std), rtol=1e-12, atol=0):
+        return f"std {std!r} != {float(sw.std)!r} " + tag
+    if mask is not None and not np.array_equal(newest, fr[-1] * mask):
+        return "window frame differs " + tag
+    return None
+
+
 def build_classic_lib(tmp):
     from emu_build import build_classic
     lib = C.CDLL(build_classic(tmp))
@@ -310,6 +347,7 @@ def main():
         res.append(run_classic_case(clib, gcase))
         res.append(run_preproc_case(clib, seed))
         res.append(run_stack_case(glib, seed))
+        res.append(run_readback_case(glib, seed))
         res.append(run_sharded_case(lib, case, 2 + seed % 4))
         if seed % 3 == 0:  # the second-generation temporal kernel on every third case
             lib.emu_set_temporal_version(2)

@@ -106,3 +106,21 @@ extern "C" int emu_gauss_stack(const uint8_t *frames, int T, size_t frame_bytes,
     }
     return 0;
 }
+
+// API read-backs (mdb_get_stack / mdb_get_window / mdb_get_std in csrc/metdet.cu): SlidingWindow.max / .mean / .sum / .std and
+// the window's frames (MetLib/utils.py:269-321).  frames[0 .. t] are all frames fed so far, written into a ring of R slots
+// as the library keeps them; the kernels read the ring only.
+extern "C" int emu_stack_readback(const uint8_t *frames, long long t, int W, int H, int n, int R, const uint8_t *mask, unsigned grid,
+                                  uint8_t *mx, uint8_t *mean, uint32_t *sum, unsigned long long *std_total, uint8_t *newest_masked) {
+    const size_t HW = (size_t)W * H;
+    if (R < n) return -1;
+    std::vector<uint8_t> ring((size_t)R * HW, 0);
+    for (long long k = std::max<long long>(0, t - R + 1); k <= t; k++) memcpy(&ring[(size_t)(k % R) * HW], frames + (size_t)k * HW, HW);
+    FrameSrc src; src.ring = ring.data(); src.cur = nullptr; src.mask = mask; src.t0 = 0; src.R = R; src.HW = HW;
+    const int L = (int)std::min<long long>(n, t + 1);
+    emu_launch(grid, 256, [&] { stack_readback_kernel(src, HW, n, t, L, mx, mean, sum); });
+    *std_total = 0;
+    emu_launch(grid, 256, [&] { stack_std_kernel(src, HW, n, t, L, std_total); });
+    if (mask && newest_masked) emu_launch(grid, 256, [&] { window_frame_kernel(src.frame(t), mask, HW, newest_masked); });
+    return 0;
+}

@@ -115,3 +115,11 @@ def test_random_clip_stacks(fuzz, generic_lib):
     for seed in range(60):
         res = fuzz.run_stack_case(generic_lib, seed)
         assert res is None, (seed, res)
+
+
+def test_random_window_readbacks(fuzz, generic_lib):
+    """mdb_get_stack / mdb_get_std / mdb_get_window kernels against the checker's SlidingWindow (max, mean, sum, std, newest frame):
+    windows of 1 .. 300 frames (beyond the 256-entry pointer table), rings of exactly n slots and larger, mask on the device."""
+    for seed in range(40):
+        res = fuzz.run_readback_case(generic_lib, seed)
+        assert res is None, (seed, res)
