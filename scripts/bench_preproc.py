@@ -28,7 +28,10 @@ for f in host:
     _ = cv2.cvtColor(cv2.resize(f, (W, H), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2GRAY) * mask
 cpu_fps = len(host) / (time.perf_counter() - t0)
 # 4x downscale touches 2 of every 4 source rows: bytes a perfect kernel must read = rows used * row bytes
-rows_used = len(set(np.concatenate(__import__("oracle.preproc_oracle", fromlist=["x"]).axis_taps(H, H0, False)[:2]).tolist()))
+from metdetpy_b200 import _lib as _L  # the library's own tap table (mdb_preproc_axis_taps): source rows the vertical taps touch
+_taps = [np.zeros(H, np.int32) for _ in range(4)]
+_L.check(_L.load().mdb_preproc_axis_taps(H, H0, 0, *[a.ctypes.data for a in _taps]), "axis taps")
+rows_used = len(set(np.concatenate(_taps[:2]).tolist()))
 need = T * rows_used * W0 * 3 + out_bytes
 print(json.dumps({"workload": f"{T} frames {W0}x{H0} BGR -> {W}x{H} gray, mask, exp_frame={EXP}, device-resident",
                   "kernel_ms": ms, "frames_per_s": T / (ms * 1e-3),

@@ -85,7 +85,7 @@ def _build(tmp, harness, patched, extra_c, std, opt, shared):
     return exe
 
 
-# the three larger harness libraries, shared by several test modules and scripts/emu_fuzz.py
+# the three larger harness libraries, shared by several test modules and tests/emu_fuzz.py
 STREAM_PATCHED = ["temporal3_kernel.cuh", "temporal_kernel.cuh", "kernels_basic.cuh", "spatial_kernel.cuh", "hough.cuh", "perframe_kernel.cuh"]
 GENERIC_PATCHED = ["kernels_basic.cuh", "hough.cuh"]
 CLASSIC_PATCHED = ["kernels_basic.cuh", "spatial_kernel.cuh", "classic.cuh", "preproc.cuh", "hough.cuh"]

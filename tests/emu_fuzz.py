@@ -2,7 +2,7 @@
 the batched streaming path and the per-frame resident-state path) against the CPU checker (oracle/m3_oracle.py, cv2 backend =
 the reference's own call sites) on random small configurations -- frame sizes, every window that has a temporal3 shape, batch
 lengths that cut the van Herk blocks anywhere, adaptive / fixed thresholds, dynamic mask on / off, Hough parameters, masks,
-bright flashes and stuck hot regions.  Test tooling (tests/test_emu_fuzz_cpu.py runs a few seeds; `python scripts/emu_fuzz.py
+bright flashes and stuck hot regions.  Test tooling (tests/test_emu_fuzz_cpu.py runs a few seeds; `python tests/emu_fuzz.py
 FIRST COUNT` runs more)."""
 import ctypes as C
 import os
@@ -12,7 +12,7 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
-sys.path.insert(0, os.path.join(REPO, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 T3_WINDOWS = [2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16, 18, 20, 21, 24, 25, 28, 30, 32, 36, 40, 48, 50, 60, 64]
 _SENS = ["low", "normal", "high"]

@@ -1,16 +1,15 @@
-"""Randomised parity without a GPU (scripts/emu_fuzz.py): the product's streaming and per-frame kernels under the CPU block
+"""Randomised parity without a GPU (tests/emu_fuzz.py): the product's streaming and per-frame kernels under the CPU block
 emulator against the CPU checker (cv2 backend = the reference's own calls, MetLib/Detector.py:186-392) on random small
 configurations -- frame shapes, windows with every kind of temporal3 shape (whole ring in registers, half in the shared page,
 sub-blocked), batch lengths that cut the van Herk blocks anywhere, adaptive / fixed thresholds, dynamic mask, Hough parameters,
 polygon masks, flashes and flickering hot regions.  Thresholds, masks and raw Hough segments must be identical, snr to 1e-12.
-A handful of fixed seeds here; `python scripts/emu_fuzz.py FIRST COUNT` runs as many as wanted."""
+A handful of fixed seeds here; `python tests/emu_fuzz.py FIRST COUNT` runs as many as wanted."""
 import os
 import sys
 
 import pytest
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(REPO, "scripts"))
 
 
 @pytest.fixture(scope="module")
