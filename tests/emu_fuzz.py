@@ -259,6 +259,50 @@ def run_readback_case(glib, seed):
     return None
 
 
+def build_mfnr_lib(tmp):
+    from emu_build import build
+    lib = C.CDLL(build(tmp, "mfnr_path_emu.cpp", patched=["mfnr.cuh"], shared=True))
+    lib.emu_mfnr_mix.restype = C.c_int
+    return lib
+
+
+def run_mfnr_case(mlib, seed):
+    """mfnr_mix_stacker (MetLib/stacker.py:296-403, connect off) on a random small clip -- every mfnr.cuh kernel in the library's
+    order -- against oracle/mfnr_oracle.py (pinned on golden images of the live function): at most one grey level on at most
+    1e-4 of the elements (the two global means are reduced in another order), est_bg_var to 1e-12."""
+    from metdetpy_b200.stacker import get_gumbel_mean
+    from oracle import mfnr_oracle as MO
+    r = np.random.default_rng([seed, 13])
+    H, W, Ch = int(r.integers(33, 70)), int(r.integers(33, 90)), 3  # the reference function is written for colour frames
+    N = int(r.choice([2, 3, 9, 16, 17, 30, 50]))
+    algo = int(r.integers(0, 4))
+    base = r.integers(15, 80, (H, W, Ch))
+    clip = np.clip(base[None] + r.normal(0, r.uniform(1.5, 6.0), (N, H, W, Ch)), 0, 255).astype(np.uint8)
+    for _ in range(int(r.integers(0, 3))):  # bright trails in single frames
+        y, x0, x1 = int(r.integers(0, H - 2)), int(r.integers(0, W // 2)), int(r.integers(W // 2, W))
+        clip[int(r.integers(0, N)), y:y + 2, x0:x1] = int(r.integers(180, 256))
+    clip = np.ascontiguousarray(clip if Ch == 3 else clip[..., 0])
+    shape = clip.shape[1:]
+    out = np.zeros(shape, np.uint8)
+    st = (C.c_double * 4)()
+    hp, fix = float(r.choice([0.8, 0.9, 0.95])), float(r.choice([1.0, 1.5, 2.0]))
+    with np.errstate(all="ignore"):
+        gm = float(get_gumbel_mean(N))
+    rc = mlib.emu_mfnr_mix(clip.ctypes.data_as(C.c_void_p), N, H, W, Ch, int(r.integers(1, N + 1)), algo, C.c_double(hp), 31, C.c_double(3.0),
+                           C.c_double(3.0), C.c_double(3.0), C.c_double(fix), C.c_double(gm), int(N ** 0.5), out.ctypes.data_as(C.c_void_p), st)
+    if rc != 0:
+        return f"rc={rc}"
+    name = ["mean", "sigma-clipping", "median", "med-of-med"][algo]
+    ref, ost = MO.mfnr_mix(clip, highlight_preserve=hp, bg_algorithm=name, bg_fix_factor=fix, return_stats=True, backend="numpy")
+    d = np.abs(out.astype(np.int16) - ref.astype(np.int16))
+    tag = f"({H}x{W}x{Ch}, N={N}, {name}, hp={hp}, fix={fix})"
+    if not (d.max() <= 1 and np.count_nonzero(d) <= max(1, int(1e-4 * d.size))):
+        return f"image differs: max {int(d.max())}, {int(np.count_nonzero(d))} elements " + tag
+    if not np.isclose(st[0], ost["est_bg_var"], rtol=1e-12, atol=0):
+        return f"est_bg_var {st[0]!r} != {ost['est_bg_var']!r} " + tag
+    return None
+
+
 def build_classic_lib(tmp):
     from emu_build import build_classic
     lib = C.CDLL(build_classic(tmp))
@@ -338,6 +382,7 @@ def main():
     import tempfile
     first, count = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (0, 50)
     lib, glib, clib = build_lib(tempfile.mkdtemp()), build_generic_lib(tempfile.mkdtemp()), build_classic_lib(tempfile.mkdtemp())
+    mlib = build_mfnr_lib(tempfile.mkdtemp())
     bad = 0
     for seed in range(first, first + count):
         case = make_case(seed)
@@ -348,6 +393,7 @@ def main():
         res.append(run_preproc_case(clib, seed))
         res.append(run_stack_case(glib, seed))
         res.append(run_readback_case(glib, seed))
+        res.append(run_mfnr_case(mlib, seed))
         res.append(run_sharded_case(lib, case, 2 + seed % 4))
         if seed % 3 == 0:  # the second-generation temporal kernel on every third case
             lib.emu_set_temporal_version(2)

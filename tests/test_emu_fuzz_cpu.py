@@ -122,3 +122,12 @@ def test_random_window_readbacks(fuzz, generic_lib):
     for seed in range(40):
         res = fuzz.run_readback_case(generic_lib, seed)
         assert res is None, (seed, res)
+
+
+def test_random_mfnr_clips(fuzz, tmp_path_factory):
+    """Random small colour clips (2 .. 50 frames, trails in single frames, every background algorithm, random highlight / fix
+    factors, random chunking) through every mfnr.cuh kernel against oracle/mfnr_oracle.py."""
+    mlib = fuzz.build_mfnr_lib(str(tmp_path_factory.mktemp("emu_fuzz_mfnr")))
+    for seed in range(16):
+        res = fuzz.run_mfnr_case(mlib, seed)
+        assert res is None, (seed, res)
