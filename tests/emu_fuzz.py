@@ -34,15 +34,22 @@ def build_generic_lib(tmp):
     return lib
 
 
-def make_case(seed, any_width=False, dense=False):
+def make_case(seed, any_width=False, dense=False, big=False):
     import cv2
     r = np.random.default_rng(seed)
     W = int(r.integers(17, 260)) if any_width else 32 * int(r.integers(1, 9))
     H = int(r.choice([8, 9, 15, 16, 17, 31, 33, 40, 63, 64, 65, 90]))
+    if big:  # wide frames: many 32-px words per row (strips of the act kernel, 16-byte chunks of act4), several row bands
+        W = 32 * int(r.choice([16, 32, 41, 60])) + (int(r.integers(1, 32)) if any_width else 0)
+        H = int(r.choice([65, 130, 200]))
     n = int(r.choice(T3_WINDOWS)) if r.random() < 0.8 else int(r.integers(2, 65))  # windows without a shape are skipped by the caller
+    if big:
+        n = int(r.choice([2, 5, 6, 12, 17, 30]))
     if any_width and r.random() < 0.15:
         n = int(r.choice([1, 70, 129, 140]))  # the generic kernels take any window
     T = int(min(110, r.integers(max(2, n // 2), 2 * n + 24)))
+    if big:
+        T = int(min(T, n + 8))
     batch = int(r.integers(1, T + 1)) if r.random() < 0.7 else int(r.integers(1, 9))
     cfg = dict(adaptive=bool(r.random() < 0.6), init_value=int(r.integers(3, 13)), sensitivity=_SENS[int(r.integers(0, 3))],
                area=float(r.choice([0.1, 0.2, 0.4])), interval=int(r.integers(1, 4)),
@@ -399,6 +406,9 @@ def main():
             lib.emu_set_temporal_version(2)
             res.append(run_case(lib, case))
             lib.emu_set_temporal_version(3)
+        if seed % 10 == 9:  # wide frames on every tenth case
+            bcase, bg = make_case(seed, big=True), make_case(seed, any_width=True, big=True)
+            res += [run_case(lib, bcase, pf) for pf in (False, True)] + [run_case(glib, bg, generic=True), run_classic_case(clib, bg)]
         if seed % 4 == 3:  # a dense variant of every fourth case
             dcase = make_case(seed, dense=True)
             res += [run_case(lib, dcase, pf) for pf in (False, True)]

@@ -131,3 +131,14 @@ def test_random_mfnr_clips(fuzz, tmp_path_factory):
     for seed in range(16):
         res = fuzz.run_mfnr_case(mlib, seed)
         assert res is None, (seed, res)
+
+
+@pytest.mark.parametrize("seed", [0, 2, 3])
+def test_random_wide_frames(fuzz, lib, generic_lib, classic_lib, seed):
+    """512 .. 1312 pixel wide frames (16 .. 41 words per row: act4's 16-byte chunks and the strip kernel for word counts that are
+    not a multiple of 4), widths that are not a multiple of 32 through the generic and classic kernels."""
+    case = fuzz.make_case(seed, big=True)
+    gcase = fuzz.make_case(seed, any_width=True, big=True)
+    res = [fuzz.run_case(lib, case, pf) for pf in (False, True)] + [fuzz.run_case(generic_lib, gcase, generic=True),
+                                                                   fuzz.run_classic_case(classic_lib, gcase)]
+    assert res == [None] * 4, (seed, {k: case[k] for k in ("W", "H", "n", "T", "batch")}, gcase["W"], res)
