@@ -142,3 +142,17 @@ def test_random_wide_frames(fuzz, lib, generic_lib, classic_lib, seed):
     res = [fuzz.run_case(lib, case, pf) for pf in (False, True)] + [fuzz.run_case(generic_lib, gcase, generic=True),
                                                                    fuzz.run_classic_case(classic_lib, gcase)]
     assert res == [None] * 4, (seed, {k: case[k] for k in ("W", "H", "n", "T", "batch")}, gcase["W"], res)
+
+
+@pytest.mark.parametrize("W,H,n,T,batch,dy", [(1920, 1080, 5, 12, 6, False), (3840, 2160, 30, 34, 4, True)])
+def test_baseline_frame_sizes_through_the_emulated_streaming_path(fuzz, lib, W, H, n, T, batch, dy):
+    """BASELINE configs 2 and 3 at their FULL frame sizes (synthetic stream of the bench generator, a few frames beyond a full
+    window) through the emulated product kernels against the checker.  The 4K case takes ~45 s: EMU_FULLSIZE=1."""
+    import numpy as np
+    from metdetpy_b200 import synth
+    if W > 1920 and not os.environ.get("EMU_FULLSIZE"):
+        pytest.skip("3840x2160, n = 30 takes ~45 s on the CPU: set EMU_FULLSIZE=1 (last run: identical)")
+    fr = synth.make_stream(T, W, H, 30, speed_scale=3.0, thickness=2)
+    case = dict(W=W, H=H, n=n, T=T, batch=batch, mask=np.ones((H, W), np.uint8), frames=fr, raw_frames=fr, apply_mask=False,
+                cfg=dict(adaptive=True, init_value=7, sensitivity="normal", area=0.1, interval=2, hough=(10, 10, 10), dy_mask=dy))
+    assert fuzz.run_case(lib, case) is None
