@@ -23,3 +23,6 @@ for name,(W,H,fps,n,T,B,dy,masked) in {"config2":(1920,1080,30,5,12,6,False,Fals
     case=dict(W=W,H=H,n=n,T=T,batch=B,cfg=dict(adaptive=True,init_value=7,sensitivity="normal",area=0.1,interval=2,hough=(10,10,10),dy_mask=dy),
               mask=mask,frames=fr*mask,raw_frames=fr,apply_mask=masked)
     r=F.run_case(lib,case); print(name,dict(W=W,H=H,n=n,frames=T,batch=B,dy_mask=dy),"->",r,"(%.0f s)"%(time.time()-t),flush=True)
+    if name=="config3":  # the per-frame resident-state path (update(); detect() frame by frame) at the bench's frame size
+        t=time.time(); r=F.run_case(lib,case,per_frame=True)
+        print(name,"per-frame API path",dict(W=W,H=H,n=n,frames=T),"->",r,"(%.0f s)"%(time.time()-t),flush=True)
